@@ -1,0 +1,536 @@
+// himut_b200.cu — context, device memory, launches and the C ABI of include/himut_b200.h.
+//
+// Host work kept here on purpose (it is sequential by definition in the reference):
+//   - the som_seen carry between chunks of a contig (caller.py:243,347; bamlib.py:77):
+//     the device evaluates every chunk independently, the host replays chunk order and
+//     drops sites a previous chunk already claimed;
+//   - the 15 / 14 log counters, summed from record statuses.
+// Everything per base / per read / per site runs in the kernels of kernels.cuh and
+// normcounts.cuh.  There is no CPU fallback: without a CUDA device hm_create fails.
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <unordered_set>
+#include <vector>
+
+#include <cub/device/device_radix_sort.cuh>
+
+#include "kernels.cuh"
+#include "normcounts.cuh"
+
+namespace {
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t ensure(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+  template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct KTime { const char* name; cudaEvent_t a, b; float ms; };
+
+}  // namespace
+
+struct hm_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = true;
+  std::string err;
+  bool have_params = false, have_batch = false;
+  hm_params params;
+  DevParams dp;
+  // resident batch
+  uint64_t n_reads = 0, n_ops_total = 0, seq_bytes = 0, bq_bytes = 0;
+  uint32_t max_qname_id = 0;
+  std::vector<int32_t> h_pmax;
+  DevBuf b_tstart, b_tend, b_qstart, b_qlen, b_mapq, b_flags, b_qname, b_seq_off, b_bq_off, b_op_off, b_n_ops,
+      b_seq, b_bq, b_ops, b_op_t, b_op_q, b_mm, b_bq_total, b_n_match, b_n_sub, b_ins_len, b_del_len, b_n_mm, b_gate,
+      b_pmax;
+  DevBatch db;
+  // sets / phase
+  DevBuf b_common, b_pon, b_hpos, b_href, b_halt, b_hbit, b_set_off;
+  DevSets dsets = {nullptr, 0, nullptr, 0};
+  DevPhase dphase = {nullptr, nullptr, nullptr, nullptr, nullptr, 0};
+  // work buffers
+  DevBuf b_chunks, b_pair_off, b_pair_hap, b_qseen, b_keys, b_keys_sorted, b_cub, b_records, b_counters;
+  DevBuf b_ref, b_norm_out;
+  // timing
+  std::vector<KTime> ktimes;
+  std::vector<cudaEvent_t> ev_pool;
+  size_t ev_used = 0;
+  float last_total_ms = 0.f;
+  int last_launches = 0;
+};
+
+namespace {
+
+int fail(hm_ctx* c, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  if (c) c->err = buf;
+  return code;
+}
+#define CU(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess) return fail(ctx, HM_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e_)); \
+  } while (0)
+
+cudaEvent_t next_event(hm_ctx* ctx) {
+  if (ctx->ev_used == ctx->ev_pool.size()) {
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    ctx->ev_pool.push_back(e);
+  }
+  return ctx->ev_pool[ctx->ev_used++];
+}
+void t_begin(hm_ctx* ctx, const char* name) {
+  KTime k{name, next_event(ctx), next_event(ctx), 0.f};
+  cudaEventRecord(k.a, ctx->stream);
+  ctx->ktimes.push_back(k);
+}
+void t_end(hm_ctx* ctx) { cudaEventRecord(ctx->ktimes.back().b, ctx->stream); }
+void t_reset(hm_ctx* ctx) { ctx->ktimes.clear(); ctx->ev_used = 0; }
+void t_collect(hm_ctx* ctx) {
+  ctx->last_total_ms = 0.f;
+  ctx->last_launches = (int)ctx->ktimes.size();
+  for (auto& k : ctx->ktimes) cudaEventElapsedTime(&k.ms, k.a, k.b);
+  if (!ctx->ktimes.empty()) cudaEventElapsedTime(&ctx->last_total_ms, ctx->ktimes.front().a, ctx->ktimes.back().b);
+}
+
+template <typename T>
+int upload(hm_ctx* ctx, DevBuf& buf, const T* src, size_t n, size_t pad_elems = 0) {
+  CU(buf.ensure((n + pad_elems) * sizeof(T) + 16));
+  if (n) CU(cudaMemcpyAsync(buf.p, src, n * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+  return HM_OK;
+}
+
+void make_dev_params(hm_ctx* ctx) {
+  const hm_params& p = ctx->params;
+  DevParams& d = ctx->dp;
+  d.min_qv = p.min_qv; d.min_mapq = p.min_mapq; d.qlen_lower_limit = p.qlen_lower_limit;
+  d.qlen_upper_limit = p.qlen_upper_limit; d.min_gq = p.min_gq; d.min_bq = p.min_bq;
+  d.max_mismatch_count = p.max_mismatch_count; d.mismatch_window = p.mismatch_window;
+  d.min_ref_count = p.min_ref_count; d.min_alt_count = p.min_alt_count; d.min_hap_count = p.min_hap_count;
+  d.phase = p.phase; d.non_human_sample = p.non_human_sample; d.create_panel_of_normals = p.create_panel_of_normals;
+  d.min_sequence_identity = p.min_sequence_identity; d.min_trim = p.min_trim; d.md_threshold = p.md_threshold;
+}
+
+int check_ready(hm_ctx* ctx, const hm_chunk* chunks, size_t n_chunks) {
+  if (!ctx) return HM_ERR_ARG;
+  if (!ctx->have_params) return fail(ctx, HM_ERR_STATE, "hm_set_params has not been called");
+  if (!ctx->have_batch) return fail(ctx, HM_ERR_STATE, "no resident batch: call hm_upload_batch first");
+  if (n_chunks && !chunks) return fail(ctx, HM_ERR_ARG, "chunks is NULL");
+  if (n_chunks >= (1ull << 28)) return fail(ctx, HM_ERR_ARG, "too many chunks");
+  for (size_t i = 0; i < n_chunks; i++) {
+    if (chunks[i].read_lo > chunks[i].read_hi || chunks[i].read_hi > ctx->n_reads)
+      return fail(ctx, HM_ERR_ARG, "chunk %zu: read range [%u, %u) outside the batch (%llu reads)", i, chunks[i].read_lo,
+                  chunks[i].read_hi, (unsigned long long)ctx->n_reads);
+    if (ctx->params.phase && (chunks[i].phase_set < 0 || (uint32_t)chunks[i].phase_set >= ctx->dphase.n_sets))
+      return fail(ctx, HM_ERR_ARG, "chunk %zu: phase_set %d is not in the phase table", i, chunks[i].phase_set);
+  }
+  return HM_OK;
+}
+
+// k_read_scan over the resident batch
+int launch_read_scan(hm_ctx* ctx) {
+  if (ctx->n_reads == 0) return HM_OK;
+  const unsigned blocks = (unsigned)((ctx->n_reads * 32 + 255) / 256);
+  t_begin(ctx, "k_read_scan");
+  k_read_scan<<<blocks, 256, 0, ctx->stream>>>(ctx->db, ctx->dp);
+  t_end(ctx);
+  CU(cudaGetLastError());
+  return HM_OK;
+}
+
+int upload_chunks(hm_ctx* ctx, const hm_chunk* chunks, size_t n_chunks, std::vector<uint64_t>& pair_off) {
+  pair_off.assign(n_chunks + 1, 0);
+  for (size_t i = 0; i < n_chunks; i++) pair_off[i + 1] = pair_off[i] + (chunks[i].read_hi - chunks[i].read_lo);
+  int rc = upload(ctx, ctx->b_chunks, chunks, n_chunks);
+  if (rc) return rc;
+  return upload(ctx, ctx->b_pair_off, pair_off.data(), pair_off.size());
+}
+
+}  // namespace
+
+extern "C" {
+
+int hm_abi_version(void) { return HM_ABI_VERSION; }
+
+size_t hm_abi_sizeof(int which) {
+  switch (which) {
+    case 0: return sizeof(hm_read_batch);
+    case 1: return sizeof(hm_chunk);
+    case 2: return sizeof(hm_params);
+    case 3: return sizeof(hm_site_record);
+    default: return 0;
+  }
+}
+
+int hm_create(int cuda_device, hm_ctx** out) {
+  if (!out) return HM_ERR_ARG;
+  *out = nullptr;
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0 || cuda_device < 0 || cuda_device >= n) return HM_ERR_NO_DEVICE;
+  if (cudaSetDevice(cuda_device) != cudaSuccess) return HM_ERR_NO_DEVICE;
+  hm_ctx* ctx = new hm_ctx();
+  ctx->device = cuda_device;
+  if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    delete ctx;
+    return HM_ERR_CUDA;
+  }
+  memset(&ctx->db, 0, sizeof(ctx->db));
+  *out = ctx;
+  return HM_OK;
+}
+
+void hm_destroy(hm_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  DevBuf* bufs[] = {&ctx->b_tstart, &ctx->b_tend, &ctx->b_qstart, &ctx->b_qlen, &ctx->b_mapq, &ctx->b_flags, &ctx->b_qname,
+                    &ctx->b_seq_off, &ctx->b_bq_off, &ctx->b_op_off, &ctx->b_n_ops, &ctx->b_seq, &ctx->b_bq, &ctx->b_ops,
+                    &ctx->b_op_t, &ctx->b_op_q, &ctx->b_mm, &ctx->b_bq_total, &ctx->b_n_match, &ctx->b_n_sub,
+                    &ctx->b_ins_len, &ctx->b_del_len, &ctx->b_n_mm, &ctx->b_gate, &ctx->b_pmax, &ctx->b_common, &ctx->b_pon,
+                    &ctx->b_hpos, &ctx->b_href, &ctx->b_halt, &ctx->b_hbit, &ctx->b_set_off, &ctx->b_chunks,
+                    &ctx->b_pair_off, &ctx->b_pair_hap, &ctx->b_qseen, &ctx->b_keys, &ctx->b_keys_sorted, &ctx->b_cub,
+                    &ctx->b_records, &ctx->b_counters, &ctx->b_ref, &ctx->b_norm_out};
+  for (DevBuf* b : bufs) b->release();
+  for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
+  if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+const char* hm_last_error(const hm_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+/* run the context's work on a caller-owned CUDA stream (cudaStream_t as void*), so that
+ * the caller's own events bracket it; NULL restores the private stream */
+int hm_set_stream(hm_ctx* ctx, void* cuda_stream) {
+  if (!ctx) return HM_ERR_ARG;
+  CU(cudaSetDevice(ctx->device));
+  CU(cudaStreamSynchronize(ctx->stream));
+  if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+  if (cuda_stream) { ctx->stream = (cudaStream_t)cuda_stream; ctx->own_stream = false; }
+  else { CU(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)); ctx->own_stream = true; }
+  return HM_OK;
+}
+
+/* page-lock / unlock caller memory so the H2D copies of hm_upload_batch run at PCIe speed */
+int hm_host_register(hm_ctx* ctx, void* p, size_t bytes) {
+  if (!ctx || !p) return HM_ERR_ARG;
+  CU(cudaSetDevice(ctx->device));
+  CU(cudaHostRegister(p, bytes, cudaHostRegisterDefault));
+  return HM_OK;
+}
+int hm_host_unregister(hm_ctx* ctx, void* p) {
+  if (!ctx || !p) return HM_ERR_ARG;
+  CU(cudaHostUnregister(p));
+  return HM_OK;
+}
+
+int hm_set_params(hm_ctx* ctx, const hm_params* params) {
+  if (!ctx || !params) return HM_ERR_ARG;
+  if (params->mismatch_window < 0 || params->qlen_upper_limit < 0) return fail(ctx, HM_ERR_ARG, "negative window / qlen limit");
+  CU(cudaSetDevice(ctx->device));
+  ctx->params = *params;
+  make_dev_params(ctx);
+  DevTables t;
+  memcpy(t.lut[0], params->lut_hom, sizeof(t.lut[0]));
+  memcpy(t.lut[1], params->lut_het, sizeof(t.lut[1]));
+  memcpy(t.lut[2], params->lut_err, sizeof(t.lut[2]));
+  memcpy(t.log10_prior, params->log10_prior, sizeof(t.log10_prior));
+  CU(cudaStreamSynchronize(ctx->stream));
+  CU(cudaMemcpyToSymbol(c_tab, &t, sizeof(t)));
+  ctx->have_params = true;
+  return HM_OK;
+}
+
+int hm_set_site_sets(hm_ctx* ctx, const uint64_t* common_sorted, size_t n_common, const uint64_t* pon_sorted, size_t n_pon) {
+  if (!ctx) return HM_ERR_ARG;
+  CU(cudaSetDevice(ctx->device));
+  for (size_t i = 1; i < n_common; i++) if (common_sorted[i - 1] > common_sorted[i]) return fail(ctx, HM_ERR_ARG, "common-SNP keys are not sorted");
+  for (size_t i = 1; i < n_pon; i++) if (pon_sorted[i - 1] > pon_sorted[i]) return fail(ctx, HM_ERR_ARG, "panel-of-normals keys are not sorted");
+  int rc = upload(ctx, ctx->b_common, common_sorted, n_common);
+  if (rc) return rc;
+  rc = upload(ctx, ctx->b_pon, pon_sorted, n_pon);
+  if (rc) return rc;
+  CU(cudaStreamSynchronize(ctx->stream));
+  ctx->dsets = DevSets{ctx->b_common.as<uint64_t>(), n_common, ctx->b_pon.as<uint64_t>(), n_pon};
+  return HM_OK;
+}
+
+int hm_set_phase_sets(hm_ctx* ctx, const int32_t* hpos, const uint8_t* href, const uint8_t* halt, const uint8_t* hbit,
+                      size_t n_hetsnp, const uint64_t* set_off, size_t n_sets) {
+  if (!ctx) return HM_ERR_ARG;
+  CU(cudaSetDevice(ctx->device));
+  if (n_sets && (!set_off || set_off[n_sets] != n_hetsnp)) return fail(ctx, HM_ERR_ARG, "set_off[n_sets] must equal n_hetsnp");
+  for (size_t s = 0; s < n_sets; s++) {
+    if (set_off[s] > set_off[s + 1]) return fail(ctx, HM_ERR_ARG, "set_off is not ascending");
+    for (uint64_t k = set_off[s] + 1; k < set_off[s + 1]; k++)
+      if (hpos[k - 1] > hpos[k]) return fail(ctx, HM_ERR_ARG, "hpos is not ascending inside phase set %zu", s);
+  }
+  int rc;
+  if ((rc = upload(ctx, ctx->b_hpos, hpos, n_hetsnp))) return rc;
+  if ((rc = upload(ctx, ctx->b_href, href, n_hetsnp))) return rc;
+  if ((rc = upload(ctx, ctx->b_halt, halt, n_hetsnp))) return rc;
+  if ((rc = upload(ctx, ctx->b_hbit, hbit, n_hetsnp))) return rc;
+  if ((rc = upload(ctx, ctx->b_set_off, set_off, n_sets ? n_sets + 1 : 0))) return rc;
+  CU(cudaStreamSynchronize(ctx->stream));
+  ctx->dphase = DevPhase{ctx->b_hpos.as<int32_t>(), ctx->b_href.as<uint8_t>(), ctx->b_halt.as<uint8_t>(),
+                         ctx->b_hbit.as<uint8_t>(), ctx->b_set_off.as<uint64_t>(), (uint32_t)n_sets};
+  return HM_OK;
+}
+
+int hm_upload_batch(hm_ctx* ctx, const hm_read_batch* b) {
+  if (!ctx || !b) return HM_ERR_ARG;
+  CU(cudaSetDevice(ctx->device));
+  ctx->have_batch = false;
+  const uint64_t n = b->n_reads;
+  if (n >= (1ull << 32)) return fail(ctx, HM_ERR_ARG, "too many reads in one batch");
+  if ((b->seq_bytes & 15) || (b->bq_bytes & 15)) return fail(ctx, HM_ERR_ARG, "seq / bq buffers must be padded to 16 bytes");
+  // structural validation (cheap, O(reads)); the kernels binary-search on these invariants
+  ctx->h_pmax.resize(n);
+  int32_t run = INT32_MIN;
+  uint32_t max_q = 0;
+  for (uint64_t r = 0; r < n; r++) {
+    if (r && b->tstart[r] < b->tstart[r - 1]) return fail(ctx, HM_ERR_ARG, "read %llu: batch is not sorted by reference_start", (unsigned long long)r);
+    if (b->tend[r] < b->tstart[r] || b->qlen[r] <= 0 || b->qstart[r] < 0 || b->qstart[r] > b->qlen[r])
+      return fail(ctx, HM_ERR_ARG, "read %llu: inconsistent coordinates", (unsigned long long)r);
+    if ((b->seq_off[r] & 15) || (b->bq_off[r] & 15)) return fail(ctx, HM_ERR_ARG, "read %llu: seq_off / bq_off not 16-byte aligned", (unsigned long long)r);
+    if (b->bq_off[r] + (uint64_t)b->qlen[r] > b->bq_bytes || b->seq_off[r] + ((uint64_t)b->qlen[r] + 3) / 4 > b->seq_bytes ||
+        b->op_off[r] + b->n_ops[r] > b->n_ops_total)
+      return fail(ctx, HM_ERR_ARG, "read %llu: offsets outside the buffers", (unsigned long long)r);
+    if (b->tend[r] > run) run = b->tend[r];
+    ctx->h_pmax[r] = run;
+    if (b->qname_id[r] > max_q) max_q = b->qname_id[r];
+  }
+  ctx->max_qname_id = max_q;
+  int rc;
+#define UP(buf, field, count) if ((rc = upload(ctx, ctx->buf, b->field, (size_t)(count)))) return rc
+  UP(b_tstart, tstart, n); UP(b_tend, tend, n); UP(b_qstart, qstart, n); UP(b_qlen, qlen, n);
+  UP(b_mapq, mapq, n); UP(b_flags, flags, n); UP(b_qname, qname_id, n);
+  UP(b_seq_off, seq_off, n); UP(b_bq_off, bq_off, n); UP(b_op_off, op_off, n); UP(b_n_ops, n_ops, n);
+  UP(b_seq, seq, b->seq_bytes); UP(b_bq, bq, b->bq_bytes); UP(b_ops, ops, b->n_ops_total);
+#undef UP
+  if ((rc = upload(ctx, ctx->b_pmax, ctx->h_pmax.data(), n))) return rc;
+  const size_t no = (size_t)b->n_ops_total;
+  CU(ctx->b_op_t.ensure(no * 4 + 16)); CU(ctx->b_op_q.ensure(no * 4 + 16)); CU(ctx->b_mm.ensure(no * 4 + 16));
+  CU(ctx->b_bq_total.ensure(n * 8 + 16)); CU(ctx->b_n_match.ensure(n * 4 + 16)); CU(ctx->b_n_sub.ensure(n * 4 + 16));
+  CU(ctx->b_ins_len.ensure(n * 4 + 16)); CU(ctx->b_del_len.ensure(n * 4 + 16)); CU(ctx->b_n_mm.ensure(n * 4 + 16));
+  CU(ctx->b_gate.ensure(n + 16));
+  DevBatch& d = ctx->db;
+  d.n_reads = n;
+  d.tstart = ctx->b_tstart.as<int32_t>(); d.tend = ctx->b_tend.as<int32_t>(); d.qstart = ctx->b_qstart.as<int32_t>();
+  d.qlen = ctx->b_qlen.as<int32_t>(); d.mapq = ctx->b_mapq.as<uint8_t>(); d.flags = ctx->b_flags.as<uint8_t>();
+  d.qname_id = ctx->b_qname.as<uint32_t>(); d.seq_off = ctx->b_seq_off.as<uint64_t>(); d.bq_off = ctx->b_bq_off.as<uint64_t>();
+  d.op_off = ctx->b_op_off.as<uint64_t>(); d.n_ops = ctx->b_n_ops.as<uint32_t>(); d.seq = ctx->b_seq.as<uint8_t>();
+  d.bq = ctx->b_bq.as<uint8_t>(); d.ops = ctx->b_ops.as<uint32_t>();
+  d.op_t = ctx->b_op_t.as<uint32_t>(); d.op_q = ctx->b_op_q.as<uint32_t>(); d.mm_pos = ctx->b_mm.as<int32_t>();
+  d.bq_total = ctx->b_bq_total.as<unsigned long long>(); d.n_match = ctx->b_n_match.as<int32_t>();
+  d.n_sub = ctx->b_n_sub.as<int32_t>(); d.ins_len = ctx->b_ins_len.as<int32_t>(); d.del_len = ctx->b_del_len.as<int32_t>();
+  d.n_mm = ctx->b_n_mm.as<int32_t>(); d.gate = ctx->b_gate.as<uint8_t>(); d.pmax_tend = ctx->b_pmax.as<int32_t>();
+  ctx->n_reads = n; ctx->n_ops_total = b->n_ops_total; ctx->seq_bytes = b->seq_bytes; ctx->bq_bytes = b->bq_bytes;
+  CU(cudaStreamSynchronize(ctx->stream)); // caller may reuse its buffers after return
+  ctx->have_batch = true;
+  return HM_OK;
+}
+
+int hm_call_chunks(hm_ctx* ctx, const hm_chunk* chunks, size_t n_chunks, hm_site_record* out, size_t cap, size_t* n_out,
+                   int64_t log[HM_CALL_LOG_LEN]) {
+  int rc = check_ready(ctx, chunks, n_chunks);
+  if (rc) return rc;
+  if (!log || !n_out) return fail(ctx, HM_ERR_ARG, "log / n_out is NULL");
+  CU(cudaSetDevice(ctx->device));
+  memset(log, 0, sizeof(int64_t) * HM_CALL_LOG_LEN);
+  *n_out = 0;
+  t_reset(ctx);
+  std::vector<uint64_t> pair_off;
+  if ((rc = upload_chunks(ctx, chunks, n_chunks, pair_off))) return rc;
+  const uint64_t n_pairs = pair_off.back();
+  if ((rc = launch_read_scan(ctx))) return rc;
+
+  // counters: [0] n_keys, [1] n_records, [2] num_ccs, [3] error flag
+  CU(ctx->b_counters.ensure(64));
+  CU(ctx->b_qseen.ensure((size_t)ctx->max_qname_id + 1));
+  if (ctx->params.phase) CU(ctx->b_pair_hap.ensure(n_pairs + 16));
+  unsigned long long h_cnt[4] = {0, 0, 0, 0};
+  unsigned long long key_cap = std::max<unsigned long long>(ctx->n_ops_total, 1024);
+  for (int attempt = 0; attempt < 2 && n_pairs; attempt++) {
+    CU(ctx->b_keys.ensure(key_cap * 8));
+    CU(cudaMemsetAsync(ctx->b_counters.p, 0, 64, ctx->stream));
+    CU(cudaMemsetAsync(ctx->b_qseen.p, 0, (size_t)ctx->max_qname_id + 1, ctx->stream));
+    const unsigned blocks = (unsigned)((n_pairs * 32 + 255) / 256);
+    t_begin(ctx, "k_candidates");
+    k_candidates<<<blocks, 256, 0, ctx->stream>>>(ctx->db, ctx->dp, ctx->dphase, ctx->b_chunks.as<hm_chunk>(), (uint32_t)n_chunks,
+                                                  ctx->b_pair_off.as<uint64_t>(), n_pairs,
+                                                  ctx->params.phase ? ctx->b_pair_hap.as<uint8_t>() : nullptr,
+                                                  ctx->b_qseen.as<uint8_t>(), ctx->b_keys.as<unsigned long long>(), key_cap,
+                                                  ctx->b_counters.as<unsigned long long>());
+    t_end(ctx);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(h_cnt, ctx->b_counters.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (h_cnt[0] <= key_cap) break;
+    key_cap = h_cnt[0];
+  }
+  const unsigned long long n_keys = h_cnt[0];
+  std::vector<hm_site_record> recs;
+  if (n_keys) {
+    CU(ctx->b_keys_sorted.ensure(n_keys * 8));
+    size_t tmp = 0;
+    int end_bit = 36;
+    for (size_t c = n_chunks; c > 1; c >>= 1) end_bit++;
+    end_bit = std::min(end_bit + 1, 64);
+    CU(cub::DeviceRadixSort::SortKeys(nullptr, tmp, ctx->b_keys.as<unsigned long long>(), ctx->b_keys_sorted.as<unsigned long long>(),
+                                      (int64_t)n_keys, 0, end_bit, ctx->stream));
+    CU(ctx->b_cub.ensure(tmp));
+    t_begin(ctx, "cub_radix_sort_keys");
+    CU(cub::DeviceRadixSort::SortKeys(ctx->b_cub.p, tmp, ctx->b_keys.as<unsigned long long>(), ctx->b_keys_sorted.as<unsigned long long>(),
+                                      (int64_t)n_keys, 0, end_bit, ctx->stream));
+    t_end(ctx);
+    CU(ctx->b_records.ensure(n_keys * sizeof(hm_site_record)));
+    const unsigned blocks = (unsigned)((n_keys * 32 + 127) / 128);
+    t_begin(ctx, "k_eval_sites");
+    k_eval_sites<<<blocks, 128, 0, ctx->stream>>>(ctx->db, ctx->dp, ctx->dsets, ctx->b_chunks.as<hm_chunk>(),
+                                                  ctx->b_pair_off.as<uint64_t>(), ctx->b_pair_hap.as<uint8_t>(),
+                                                  ctx->b_keys_sorted.as<unsigned long long>(), n_keys, ctx->b_records.as<hm_site_record>(),
+                                                  n_keys, ctx->b_counters.as<unsigned long long>() + 1,
+                                                  reinterpret_cast<int*>(ctx->b_counters.as<unsigned long long>() + 3));
+    t_end(ctx);
+    CU(cudaGetLastError());
+  }
+  if (n_pairs) {
+    t_begin(ctx, "k_count_flags");
+    k_count_flags<<<148, 256, 0, ctx->stream>>>(ctx->b_qseen.as<uint8_t>(), (uint64_t)ctx->max_qname_id + 1,
+                                                ctx->b_counters.as<unsigned long long>() + 2);
+    t_end(ctx);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(h_cnt, ctx->b_counters.p, 32, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    if ((int)h_cnt[3] == HM_ERR_BQ_ZERO) return fail(ctx, HM_ERR_BQ_ZERO, "a base quality of 0 reached the genotype model (the reference raises ValueError: math.log10(0))");
+    recs.resize(h_cnt[1]);
+    if (h_cnt[1]) {
+      CU(cudaMemcpyAsync(recs.data(), ctx->b_records.p, h_cnt[1] * sizeof(hm_site_record), cudaMemcpyDeviceToHost, ctx->stream));
+      CU(cudaStreamSynchronize(ctx->stream));
+    }
+  }
+  t_collect(ctx);
+
+  // sequential part: chunk order, som_seen carry, counters (caller.py:324-347,625-641)
+  std::sort(recs.begin(), recs.end(), [](const hm_site_record& a, const hm_site_record& b) {
+    if (a.chunk != b.chunk) return a.chunk < b.chunk;
+    if (a.tpos != b.tpos) return a.tpos < b.tpos;
+    if (a.ref != b.ref) return a.ref < b.ref;
+    return a.alt < b.alt;
+  });
+  std::unordered_set<int32_t> som_seen;
+  std::vector<int32_t> adds;
+  size_t n_final = 0, i = 0;
+  log[0] = (int64_t)h_cnt[2];
+  while (i < recs.size()) {
+    const int32_t chunk = recs[i].chunk;
+    adds.clear();
+    for (; i < recs.size() && recs[i].chunk == chunk; i++) {
+      const hm_site_record& R = recs[i];
+      if (som_seen.count(R.tpos)) continue; // dropped in get_tsbs_candidates (bamlib.py:77)
+      log[1]++;
+      switch (R.status) {
+        case HM_ST_GERM_HET: log[2]++; break;
+        case HM_ST_GERM_HETALT: log[3]++; break;
+        case HM_ST_GERM_HOMALT: log[4]++; break;
+        case HM_ST_GERM_HOMREF: break;
+        case HM_ST_HET_SITE: case HM_ST_HETALT_SITE: case HM_ST_HOMALT_SITE: log[5]++; break;
+        case HM_ST_INDEL_SITE: log[7]++; break;
+        default:
+          log[6]++;
+          if (R.status == HM_ST_LOW_GQ) log[8]++;
+          else if (R.status == HM_ST_LOW_BQ) log[9]++;
+          else if (R.status == HM_ST_PON) log[10]++;
+          else if (R.status == HM_ST_COMSNP) log[11]++;
+          else if (R.status == HM_ST_HIGH_DEPTH) log[12]++;
+          else if (R.status == HM_ST_LOW_DEPTH) log[13]++;
+          else log[14]++; // PASS / Unphased: num_som is counted before the phase verdict
+      }
+      if (R.status > HM_ST_GERM_HOMREF) adds.push_back(R.tpos);
+      if (n_final < cap && out) out[n_final] = R;
+      n_final++;
+    }
+    for (int32_t t : adds) som_seen.insert(t);
+  }
+  *n_out = n_final;
+  if (n_final > cap) return fail(ctx, HM_ERR_CAPACITY, "output holds %zu records, %zu needed", cap, n_final);
+  return HM_OK;
+}
+
+int hm_call_batch(hm_ctx* ctx, const hm_read_batch* batch, const hm_chunk* chunks, size_t n_chunks, hm_site_record* out,
+                  size_t cap, size_t* n_out, int64_t log[HM_CALL_LOG_LEN]) {
+  int rc = hm_upload_batch(ctx, batch);
+  if (rc) return rc;
+  return hm_call_chunks(ctx, chunks, n_chunks, out, cap, n_out, log);
+}
+
+int hm_read_stats(hm_ctx* ctx, int64_t* bq_total, int32_t* n_match, int32_t* n_sub, int32_t* ins_len, int32_t* del_len,
+                  int32_t* n_mismatch) {
+  if (!ctx) return HM_ERR_ARG;
+  if (!ctx->have_params) return fail(ctx, HM_ERR_STATE, "hm_set_params has not been called");
+  if (!ctx->have_batch) return fail(ctx, HM_ERR_STATE, "no resident batch");
+  CU(cudaSetDevice(ctx->device));
+  t_reset(ctx);
+  int rc = launch_read_scan(ctx);
+  if (rc) return rc;
+  const size_t n = ctx->n_reads;
+  static_assert(sizeof(unsigned long long) == sizeof(int64_t), "");
+#define DN(dst, buf, T) if (dst && n) CU(cudaMemcpyAsync(dst, ctx->buf.p, n * sizeof(T), cudaMemcpyDeviceToHost, ctx->stream))
+  DN(bq_total, b_bq_total, int64_t); DN(n_match, b_n_match, int32_t); DN(n_sub, b_n_sub, int32_t);
+  DN(ins_len, b_ins_len, int32_t); DN(del_len, b_del_len, int32_t); DN(n_mismatch, b_n_mm, int32_t);
+#undef DN
+  CU(cudaStreamSynchronize(ctx->stream));
+  t_collect(ctx);
+  return HM_OK;
+}
+
+int hm_normcounts_chunks(hm_ctx* ctx, const uint8_t* refseq, size_t ref_len, const hm_chunk* chunks, size_t n_chunks,
+                         int64_t ccs_tri[HM_TRI_BINS], int64_t ref_tri[HM_TRI_BINS], int64_t log[HM_NORM_LOG_LEN],
+                         int64_t* n_alt_tie) {
+  int rc = check_ready(ctx, chunks, n_chunks);
+  if (rc) return rc;
+  return hm_normcounts_impl(ctx, refseq, ref_len, chunks, n_chunks, ccs_tri, ref_tri, log, n_alt_tie);
+}
+
+int hm_last_timing(hm_ctx* ctx, float* total_ms, int* n_launches) {
+  if (!ctx) return HM_ERR_ARG;
+  if (total_ms) *total_ms = ctx->last_total_ms;
+  if (n_launches) *n_launches = ctx->last_launches;
+  return HM_OK;
+}
+
+int hm_last_kernel_times(hm_ctx* ctx, const char** names, float* ms, size_t cap, size_t* n) {
+  if (!ctx || !n) return HM_ERR_ARG;
+  size_t k = 0;
+  for (; k < ctx->ktimes.size() && k < cap; k++) {
+    if (names) names[k] = ctx->ktimes[k].name;
+    if (ms) ms[k] = ctx->ktimes[k].ms;
+  }
+  *n = k;
+  return HM_OK;
+}
+
+}  // extern "C"
+
+static int hm_normcounts_impl(hm_ctx* ctx, const uint8_t*, size_t, const hm_chunk*, size_t, int64_t*, int64_t*, int64_t*, int64_t*) {
+  return fail(ctx, HM_ERR_STATE, "hm_normcounts_chunks: kernel not built yet");
+}

@@ -1,0 +1,534 @@
+// kernels.cuh — sm_100a device code of the himut per-region calling path (`himut call`).
+//
+//   k_read_scan     cs op stream -> per-op reference / query prefix positions, mismatch list,
+//                   match / sub / indel totals, whole-read BQ sum, read gates
+//                   (cslib.cs2tuple + cs2subindel, src/himut/cslib.py:13-64;
+//                    bamlib.get_qv / get_blast_sequence_identity, src/himut/bamlib.py:34-63;
+//                    read gates of caller.py:310-317)
+//   k_candidates    per (chunk, read) pair: fetch rule, [--phase: read haplotype], gates,
+//                   then trim + mismatch-window filter of every substitution
+//                   (bamlib.get_tsbs_candidates, src/himut/bamlib.py:69-86,222-282;
+//                    haplib.get_ccs_hap, src/himut/haplib.py:46-83)
+//   k_eval_sites    per distinct candidate: ordered pileup of the chunk's reads at the site,
+//                   10-genotype PL / GQ, germline-restatement test and the filter cascade
+//                   (caller.update_allelecounts, caller.py:44-72; gtlib.py:72-174;
+//                    caller.py:324-621)
+//
+// All streaming, integer / byte work plus ordered fp64 adds; no tensor-core work exists on
+// this path.  fp64 sums use __dadd_rn / __dmul_rn so nothing is contracted into FMAs: the
+// reference's Python float adds are plain IEEE operations and GQ = int(PL2 - PL1) is taken
+// from them.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/himut_b200.h"
+
+#define HM_FULL 0xffffffffu
+
+struct DevBatch {
+  uint64_t n_reads;
+  const int32_t* tstart;
+  const int32_t* tend;
+  const int32_t* qstart;
+  const int32_t* qlen;
+  const uint8_t* mapq;
+  const uint8_t* flags;
+  const uint32_t* qname_id;
+  const uint64_t* seq_off;
+  const uint64_t* bq_off;
+  const uint64_t* op_off;
+  const uint32_t* n_ops;
+  const uint8_t* seq;
+  const uint8_t* bq;
+  const uint32_t* ops;
+  // derived by k_read_scan
+  uint32_t* op_t;  // reference offset (from tstart) at the start of each op
+  uint32_t* op_q;  // query position at the start of each op
+  int32_t* mm_pos; // per read, at op_off: 1-based positions of cs2subindel's mismatch_lst
+  unsigned long long* bq_total;
+  int32_t* n_match;
+  int32_t* n_sub;
+  int32_t* ins_len;
+  int32_t* del_len;
+  int32_t* n_mm;
+  uint8_t* gate;            // 1: passes the qv / mapq / identity / qlen gates
+  const int32_t* pmax_tend; // running maximum of tend (host computed)
+};
+
+// scalar worker arguments, by value
+struct DevParams {
+  int32_t min_qv, min_mapq, qlen_lower_limit, qlen_upper_limit, min_gq, min_bq;
+  int32_t max_mismatch_count, mismatch_window, min_ref_count, min_alt_count, min_hap_count;
+  int32_t phase, non_human_sample, create_panel_of_normals;
+  double min_sequence_identity, min_trim, md_threshold;
+};
+
+// per-BQ genotype terms and priors (hm_params.lut_*, log10_prior)
+struct DevTables {
+  double lut[3][256]; // 0 hom, 1 het, 2 err
+  double log10_prior[4];
+};
+__constant__ DevTables c_tab;
+
+struct DevPhase {
+  const int32_t* hpos;
+  const uint8_t* href;
+  const uint8_t* halt;
+  const uint8_t* hbit;
+  const uint64_t* set_off;
+  uint32_t n_sets;
+};
+
+struct DevSets {
+  const uint64_t* common;
+  uint64_t n_common;
+  const uint64_t* pon;
+  uint64_t n_pon;
+};
+
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint4 ldg_stream16(const uint4* p) {
+  uint4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+               : "l"(p));
+  return v;
+}
+__device__ __forceinline__ uint32_t sum4(uint32_t w, uint32_t acc) { return __dp4a(w, 0x01010101u, acc); }
+
+__device__ __forceinline__ int op_ref_len(uint32_t w) {
+  uint32_t kind = w & 3u, v = w >> 2;
+  return kind == HM_OP_MATCH ? (int)v : kind == HM_OP_SUB ? 1 : kind == HM_OP_DEL ? (int)v : 0;
+}
+__device__ __forceinline__ int op_qry_len(uint32_t w) {
+  uint32_t kind = w & 3u, v = w >> 2;
+  return kind == HM_OP_MATCH ? (int)v : kind == HM_OP_SUB ? 1 : kind == HM_OP_INS ? (int)v : 0;
+}
+
+// ============================================================================ k_read_scan
+// One warp per read.  Phase 1: 32 ops at a time, warp inclusive scan of (ref_len, qry_len).
+// Phase 2: the read's qualities as 16-byte words, 4 in flight per lane, summed with dp4a.
+__global__ void __launch_bounds__(256) k_read_scan(DevBatch b, DevParams p) {
+  const uint64_t r = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (r >= b.n_reads) return;
+  const uint64_t o0 = b.op_off[r];
+  const uint32_t nops = b.n_ops[r];
+  const int32_t tstart = b.tstart[r];
+  const int32_t qlen = b.qlen[r];
+  uint32_t t_carry = 0, q_carry = (uint32_t)b.qstart[r];
+  int mm_base = 0, nm = 0, ns = 0, il = 0, dl = 0;
+  for (uint32_t base = 0; base < nops; base += 32) {
+    const uint32_t k = base + lane;
+    const bool valid = k < nops;
+    const uint32_t w = valid ? __ldg(b.ops + o0 + k) : 0u;
+    const uint32_t kind = w & 3u, v = w >> 2;
+    const uint32_t rl = (uint32_t)op_ref_len(w), al = (uint32_t)op_qry_len(w);
+    uint32_t rs = rl, qs = al;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      uint32_t a = __shfl_up_sync(HM_FULL, rs, d), c = __shfl_up_sync(HM_FULL, qs, d);
+      if (lane >= d) { rs += a; qs += c; }
+    }
+    const uint32_t t_ex = t_carry + rs - rl, q_ex = q_carry + qs - al;
+    if (valid) { b.op_t[o0 + k] = t_ex; b.op_q[o0 + k] = q_ex; }
+    const bool is_mm = valid && ((kind == HM_OP_SUB && (v & 7u) != HM_BASE_N) || kind == HM_OP_INS || kind == HM_OP_DEL);
+    const uint32_t bal = __ballot_sync(HM_FULL, is_mm);
+    if (is_mm) b.mm_pos[o0 + mm_base + __popc(bal & ((1u << lane) - 1u))] = tstart + (int32_t)t_ex + 1;
+    mm_base += __popc(bal);
+    if (valid) {
+      if (kind == HM_OP_MATCH) nm += (int)v;
+      else if (kind == HM_OP_SUB) ns += 1;
+      else if (kind == HM_OP_INS) il += (int)v;
+      else dl += (int)v;
+    }
+    t_carry += __shfl_sync(HM_FULL, rs, 31);
+    q_carry += __shfl_sync(HM_FULL, qs, 31);
+  }
+  nm = __reduce_add_sync(HM_FULL, nm);
+  ns = __reduce_add_sync(HM_FULL, ns);
+  il = __reduce_add_sync(HM_FULL, il);
+  dl = __reduce_add_sync(HM_FULL, dl);
+
+  // whole-read quality sum (np.mean(bq_int_lst) is an exact integer sum divided once)
+  const uint8_t* bq = b.bq + b.bq_off[r];
+  const uint4* q4 = reinterpret_cast<const uint4*>(bq);
+  const int n16 = qlen >> 4;
+  uint32_t acc = 0;
+  int i = lane;
+  for (; i + 96 < n16; i += 128) {
+    uint4 a0 = ldg_stream16(q4 + i), a1 = ldg_stream16(q4 + i + 32), a2 = ldg_stream16(q4 + i + 64), a3 = ldg_stream16(q4 + i + 96);
+    acc = sum4(a0.x, acc); acc = sum4(a0.y, acc); acc = sum4(a0.z, acc); acc = sum4(a0.w, acc);
+    acc = sum4(a1.x, acc); acc = sum4(a1.y, acc); acc = sum4(a1.z, acc); acc = sum4(a1.w, acc);
+    acc = sum4(a2.x, acc); acc = sum4(a2.y, acc); acc = sum4(a2.z, acc); acc = sum4(a2.w, acc);
+    acc = sum4(a3.x, acc); acc = sum4(a3.y, acc); acc = sum4(a3.z, acc); acc = sum4(a3.w, acc);
+  }
+  for (; i < n16; i += 32) {
+    uint4 a0 = ldg_stream16(q4 + i);
+    acc = sum4(a0.x, acc); acc = sum4(a0.y, acc); acc = sum4(a0.z, acc); acc = sum4(a0.w, acc);
+  }
+  for (int j = (n16 << 4) + lane; j < qlen; j += 32) acc += bq[j];
+  unsigned long long tot = acc;
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) tot += __shfl_xor_sync(HM_FULL, tot, d);
+
+  if (lane == 0) {
+    b.bq_total[r] = tot;
+    b.n_match[r] = nm; b.n_sub[r] = ns; b.ins_len[r] = il; b.del_len[r] = dl; b.n_mm[r] = mm_base;
+    // caller.py:310-317, in order
+    bool ok = true;
+    const double qv = __ddiv_rn((double)tot, (double)qlen);
+    if (qv < (double)p.min_qv) ok = false;
+    if ((int)b.mapq[r] < p.min_mapq) ok = false;
+    const double ident = __ddiv_rn((double)nm, (double)(nm + ns + il + dl));
+    if (ident < p.min_sequence_identity) ok = false;
+    if (!(p.qlen_lower_limit < qlen && qlen < p.qlen_upper_limit)) ok = false;
+    b.gate[r] = ok ? 1 : 0;
+  }
+}
+
+// ============================================================================ lookups
+// allele of read r at 0-based reference position rpos (tstart <= rpos <= tend):
+//   0..3 base, 5 deleted, -1 no base; *bq = quality of the base; *ins = insertions whose
+//   reference position is rpos (caller.update_allelecounts: counts[tpos][4] += 1).
+__device__ __forceinline__ int read_allele_at(const DevBatch& b, uint64_t r, int32_t rpos, int* bq, int* ins) {
+  const uint32_t n = b.n_ops[r];
+  *bq = 0; *ins = 0;
+  if (n == 0) return -1;
+  const uint64_t o0 = b.op_off[r];
+  const uint32_t off = (uint32_t)(rpos - b.tstart[r]);
+  uint32_t lo = 0, hi = n;
+  while (lo < hi) { // last op with op_t <= off
+    uint32_t mid = (lo + hi) >> 1;
+    if (__ldg(b.op_t + o0 + mid) <= off) lo = mid + 1; else hi = mid;
+  }
+  const int k = (int)lo - 1;
+  int cnt = 0;
+  for (int j = k; j >= 0 && __ldg(b.op_t + o0 + j) == off; j--)
+    if ((__ldg(b.ops + o0 + j) & 3u) == HM_OP_INS) cnt++;
+  *ins = cnt;
+  const uint32_t w = __ldg(b.ops + o0 + k);
+  const uint32_t kind = w & 3u, v = w >> 2, t0 = __ldg(b.op_t + o0 + k);
+  const uint32_t rl = (uint32_t)op_ref_len(w);
+  if (rl == 0 || off >= t0 + rl) return -1;
+  if (kind == HM_OP_DEL) return 5;
+  const uint32_t q = __ldg(b.op_q + o0 + k) + (kind == HM_OP_MATCH ? off - t0 : 0u);
+  *bq = b.bq[b.bq_off[r] + q];
+  if (kind == HM_OP_SUB) return (int)((v >> 3) & 7u);
+  return (b.seq[b.seq_off[r] + (q >> 2)] >> (2 * (q & 3u))) & 3;
+}
+
+template <typename T>
+__device__ __forceinline__ uint32_t upper_bound_dev(const T* a, uint32_t n, T x) { // first a[i] > x
+  uint32_t lo = 0, hi = n;
+  while (lo < hi) { uint32_t m = (lo + hi) >> 1; if (x < __ldg(a + m)) hi = m; else lo = m + 1; }
+  return lo;
+}
+template <typename T>
+__device__ __forceinline__ uint32_t lower_bound_dev(const T* a, uint32_t n, T x) { // first a[i] >= x
+  uint32_t lo = 0, hi = n;
+  while (lo < hi) { uint32_t m = (lo + hi) >> 1; if (__ldg(a + m) < x) lo = m + 1; else hi = m; }
+  return lo;
+}
+__device__ __forceinline__ bool key_in_dev(const uint64_t* a, uint64_t n, uint64_t key) {
+  uint64_t lo = 0, hi = n;
+  while (lo < hi) { uint64_t m = (lo + hi) >> 1; if (__ldg(a + m) < key) lo = m + 1; else hi = m; }
+  return lo < n && __ldg(a + lo) == key;
+}
+
+// haplib.get_ccs_hap (haplib.py:61-83) for a whole warp: 0 / 1 / 2 (".")
+__device__ __forceinline__ int warp_read_hap(const DevBatch& b, uint64_t r, const DevPhase& ph, int set, int lane) {
+  if (set < 0 || (uint32_t)set >= ph.n_sets) return 2;
+  const uint64_t s0 = ph.set_off[set];
+  const uint32_t n = (uint32_t)(ph.set_off[set + 1] - s0);
+  const int32_t* hp = ph.hpos + s0;
+  const uint32_t idx = upper_bound_dev(hp, n, b.tstart[r]);
+  const uint32_t jdx = upper_bound_dev(hp, n, b.tend[r]);
+  if (jdx - idx < 2) return 2;
+  bool h0 = true, h1 = true;
+  for (uint32_t k = idx + lane; k < jdx; k += 32) {
+    int bq, ins;
+    const int a = read_allele_at(b, r, hp[k] - 1, &bq, &ins);
+    int bit = 2;
+    if (a >= 0 && a < 4) {
+      if (a == (int)ph.href[s0 + k]) bit = 0;
+      else if (a == (int)ph.halt[s0 + k]) bit = 1;
+    }
+    const int hb = ph.hbit[s0 + k];
+    if (bit != hb) h0 = false;
+    if (bit != 1 - hb) h1 = false;
+  }
+  h0 = __all_sync(HM_FULL, h0);
+  h1 = __all_sync(HM_FULL, h1);
+  return h0 ? 0 : (h1 ? 1 : 2);
+}
+
+// ============================================================================ k_candidates
+// One warp per (chunk, read) pair, pairs enumerated chunk-major over [read_lo, read_hi).
+// Emits keys chunk << 36 | tpos << 4 | ref << 2 | alt for every substitution that survives
+// get_tsbs_candidates and lies in the chunk (is_chunk, caller.py:325).  som_seen is applied
+// later on the host, where the chunk order is sequential.
+__global__ void __launch_bounds__(256) k_candidates(DevBatch b, DevParams p, DevPhase ph, const hm_chunk* chunks,
+                                                    uint32_t n_chunks, const uint64_t* pair_off, uint64_t n_pairs,
+                                                    uint8_t* pair_hap, uint8_t* qname_seen,
+                                                    unsigned long long* keys, unsigned long long cap,
+                                                    unsigned long long* n_keys) {
+  const uint64_t pr = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (pr >= n_pairs) return;
+  uint32_t c = upper_bound_dev(pair_off, n_chunks + 1, pr) - 1;
+  const hm_chunk ch = chunks[c];
+  const uint64_t r = (uint64_t)ch.read_lo + (pr - pair_off[c]);
+  if (pair_hap && lane == 0) pair_hap[pr] = 3; // not fetched
+  if (b.flags[r] & HM_READ_SECONDARY) return;
+  const int32_t tstart = b.tstart[r], tend = b.tend[r];
+  if (!(tstart < ch.end && tend > ch.start)) return;
+  if (p.phase) {
+    const int hap = warp_read_hap(b, r, ph, ch.phase_set, lane);
+    if (lane == 0) pair_hap[pr] = (uint8_t)hap;
+    if (hap > 1) return;
+  }
+  if (!b.gate[r]) return;
+  if (lane == 0) qname_seen[b.qname_id[r]] = 1;
+
+  const int32_t qlen = b.qlen[r];
+  const double trim_s = floor(__dmul_rn(p.min_trim, (double)qlen));
+  const double trim_e = ceil(__dmul_rn(__dsub_rn(1.0, p.min_trim), (double)qlen));
+  const uint64_t o0 = b.op_off[r];
+  const uint32_t nops = b.n_ops[r];
+  const int32_t* mm = b.mm_pos + o0;
+  const uint32_t nmm = (uint32_t)b.n_mm[r];
+  const int w = p.mismatch_window;
+  for (uint32_t base = 0; base < nops; base += 32) {
+    const uint32_t k = base + lane;
+    bool emit = false;
+    unsigned long long key = 0;
+    if (k < nops) {
+      const uint32_t op = __ldg(b.ops + o0 + k);
+      const uint32_t v = op >> 2;
+      if ((op & 3u) == HM_OP_SUB && (v & 7u) != HM_BASE_N) {
+        const int32_t tpos = tstart + (int32_t)b.op_t[o0 + k] + 1;
+        const int32_t qpos = (int32_t)b.op_q[o0 + k];
+        if (ch.start <= tpos && tpos <= ch.end && !((double)qpos < trim_s) && !((double)qpos > trim_e)) {
+          // bamlib.get_mismatch_range
+          const int qs = qpos - w, qe = qpos + w;
+          int u, d;
+          if (qs < 0) { u = w + qs; d = w + (-qs); }
+          else if (qe > qlen) { u = w + (qe - qlen); d = qlen - qpos; }
+          else { u = w; d = w; }
+          const int cnt = (int)upper_bound_dev(mm, nmm, tpos + d) - (int)lower_bound_dev(mm, nmm, tpos - u) - 1;
+          if (!(cnt > p.max_mismatch_count)) {
+            emit = true;
+            key = ((unsigned long long)c << 36) | ((unsigned long long)(uint32_t)tpos << 4) | ((v & 3u) << 2) | ((v >> 3) & 3u);
+          }
+        }
+      }
+    }
+    const uint32_t bal = __ballot_sync(HM_FULL, emit);
+    if (bal) {
+      unsigned long long at = 0;
+      if (lane == 0) at = atomicAdd(n_keys, (unsigned long long)__popc(bal));
+      at = __shfl_sync(HM_FULL, at, 0);
+      if (emit) {
+        const unsigned long long slot = at + __popc(bal & ((1u << lane) - 1u));
+        if (slot < cap) keys[slot] = key;
+      }
+    }
+  }
+}
+
+// ============================================================================ k_eval_sites
+// gtlib.gt_lst (gtlib.py:9) as base codes A0 T1 G2 C3
+__device__ __constant__ int8_t c_gt_b1[10] = {0, 1, 3, 2, 1, 3, 2, 3, 2, 2};
+__device__ __constant__ int8_t c_gt_b2[10] = {0, 0, 0, 0, 1, 1, 1, 3, 3, 2};
+
+__device__ __forceinline__ int gt_state_dev(int b1, int b2, int ref) { // 0 homref 1 het 2 hetalt 3 homalt
+  if (b1 == ref && b2 == ref) return 0;
+  if ((b1 == ref) != (b2 == ref)) return 1;
+  if (b1 != b2) return 2;
+  return 3;
+}
+
+// PL of genotype g from the 12 ordered sums S[allele][kind] (gtlib.get_log10_gt_pD,
+// gtlib.py:72-96): A,T,G,C terms added left to right from 0, then the prior, then * -10.
+// skip >= 0 leaves that allele out (get_germ_gq with a 1-char alt, normcounts.py:389).
+__device__ __forceinline__ double gt_pl_dev(const double S[4][3], int g, int ref, int skip) {
+  const int b1 = c_gt_b1[g], b2 = c_gt_b2[g];
+  double acc = 0.0;
+#pragma unroll
+  for (int base = 0; base < 4; base++) {
+    if (base == skip) continue;
+    int kind;
+    if (b1 == b2 && base == b1) kind = 0;
+    else if (b1 != b2 && (base == b1 || base == b2)) kind = 1;
+    else kind = 2;
+    acc = __dadd_rn(acc, S[base][kind]);
+  }
+  acc = __dadd_rn(acc, c_tab.log10_prior[gt_state_dev(b1, b2, ref)]);
+  return __dmul_rn(-10.0, acc);
+}
+
+// gtlib.get_argmin_gt (gtlib.py:113-119)
+__device__ __forceinline__ int argmin_gt_dev(const double pl[10], int* gq, bool* tie) {
+  int best = 0;
+#pragma unroll
+  for (int g = 1; g < 10; g++) if (pl[g] < pl[best]) best = g;
+  double second = __longlong_as_double(0x7ff0000000000000ll);
+#pragma unroll
+  for (int g = 0; g < 10; g++) if (g != best && pl[g] < second) second = pl[g];
+  const double d = __dsub_rn(second, pl[best]);
+  *gq = d < 99.0 ? (int)d : 99;
+  *tie = (second == pl[best]);
+  return best;
+}
+
+// One warp per sorted candidate key; duplicates of the previous key exit at once.
+// Lanes take one read each (32 at a time, file order); the per-allele ordered fp64 sums are
+// owned by lanes 0..11 (allele = lane / 3, kind = lane % 3) and fed in read order.
+__global__ void __launch_bounds__(128) k_eval_sites(DevBatch b, DevParams p, DevSets sets, const hm_chunk* chunks,
+                                                    const uint64_t* pair_off, const uint8_t* pair_hap,
+                                                    const unsigned long long* keys, unsigned long long n_keys,
+                                                    hm_site_record* out, unsigned long long cap,
+                                                    unsigned long long* n_out, int* err_flag) {
+  __shared__ double s_lut[3][256];
+  for (int i = threadIdx.x; i < 768; i += blockDim.x) s_lut[i >> 8][i & 255] = c_tab.lut[i >> 8][i & 255];
+  __syncthreads();
+  const uint64_t ki = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (ki >= n_keys) return;
+  const unsigned long long key = keys[ki];
+  if (ki > 0 && keys[ki - 1] == key) return;
+  const uint32_t c = (uint32_t)(key >> 36);
+  const int32_t tpos = (int32_t)((key >> 4) & 0xffffffffull);
+  const int ref = (int)((key >> 2) & 3), alt = (int)(key & 3);
+  const int32_t rpos = tpos - 1;
+  const hm_chunk ch = chunks[c];
+
+  // reads that can touch rpos: running-max(tend) >= rpos (a trailing insertion sits at tend)
+  // and tstart <= rpos, inside the chunk's fetch range
+  uint32_t lo = lower_bound_dev(b.pmax_tend, (uint32_t)b.n_reads, rpos);
+  uint32_t hi = upper_bound_dev(b.tstart, (uint32_t)b.n_reads, rpos);
+  if (lo < ch.read_lo) lo = ch.read_lo;
+  if (hi > ch.read_hi) hi = ch.read_hi;
+
+  int cnt[6] = {0, 0, 0, 0, 0, 0}, bqs[4] = {0, 0, 0, 0};
+  int hi_bq_alt = 0, h0 = 0, h1 = 0, som_mask = 0;
+  bool bq_zero = false;
+  double S = 0.0; // lanes 0..11
+  const int my_a = lane / 3, my_k = lane % 3;
+  for (uint32_t base = lo; base < hi; base += 32) {
+    const uint32_t r = base + lane;
+    int a = -1, bq = 0, ins = 0, hap = 2;
+    bool next_cov = false;
+    if (r < hi && !(b.flags[r] & HM_READ_SECONDARY)) {
+      const int32_t ts = b.tstart[r], te = b.tend[r];
+      if (ts < ch.end && te > ch.start && ts <= rpos && rpos <= te) {
+        a = read_allele_at(b, r, rpos, &bq, &ins);
+        next_cov = te > tpos; // overlaps [tpos, tpos+1) (caller.py:558)
+        if (p.phase) hap = pair_hap[pair_off[c] + (r - ch.read_lo)];
+      }
+    }
+    const uint32_t m_base = __ballot_sync(HM_FULL, a >= 0 && a < 4);
+#pragma unroll
+    for (int x = 0; x < 4; x++) {
+      const uint32_t m = __ballot_sync(HM_FULL, a == x);
+      cnt[x] += __popc(m);
+      bqs[x] += __reduce_add_sync(HM_FULL, a == x ? bq : 0);
+    }
+    cnt[5] += __popc(__ballot_sync(HM_FULL, a == 5));
+    cnt[4] += __reduce_add_sync(HM_FULL, ins);
+    hi_bq_alt += __popc(__ballot_sync(HM_FULL, a == alt && bq >= p.min_bq));
+    bq_zero |= __any_sync(HM_FULL, a >= 0 && a < 4 && bq == 0);
+    if (p.phase) {
+      h0 += __popc(__ballot_sync(HM_FULL, a == ref && next_cov && hap == 0));
+      h1 += __popc(__ballot_sync(HM_FULL, a == ref && next_cov && hap == 1));
+      if (__any_sync(HM_FULL, a == alt && next_cov && hap == 0)) som_mask |= 1;
+      if (__any_sync(HM_FULL, a == alt && next_cov && hap == 1)) som_mask |= 2;
+    }
+    // ordered sums: walk the base-carrying lanes in read order
+    uint32_t m = m_base;
+    while (m) {
+      const int src = __ffs(m) - 1;
+      m &= m - 1;
+      const int sa = __shfl_sync(HM_FULL, a, src), sq = __shfl_sync(HM_FULL, bq, src);
+      if (lane < 12 && sa == my_a) S = __dadd_rn(S, s_lut[my_k][sq]);
+    }
+  }
+  // gather the 12 sums on every lane
+  double SS[4][3];
+#pragma unroll
+  for (int x = 0; x < 4; x++)
+#pragma unroll
+    for (int k = 0; k < 3; k++) SS[x][k] = __shfl_sync(HM_FULL, S, x * 3 + k);
+  if (lane != 0) return;
+  if (bq_zero) *err_flag = HM_ERR_BQ_ZERO;
+
+  double pl[10];
+#pragma unroll
+  for (int g = 0; g < 10; g++) pl[g] = gt_pl_dev(SS, g, ref, -1);
+  int gq; bool tie;
+  const int best = argmin_gt_dev(pl, &gq, &tie);
+  int g0 = c_gt_b1[best], g1 = c_gt_b2[best];
+  const int state = gt_state_dev(g0, g1, ref);
+  if (g0 != ref && ((g0 == ref) + (g1 == ref)) == 1) { int t = g0; g0 = g1; g1 = t; } // gtlib.py:133-134
+  const int ins_count = cnt[4], del_count = cnt[5];
+  const int depth = cnt[0] + cnt[1] + cnt[2] + cnt[3] + cnt[5];
+  const int ref_count = cnt[ref], alt_count = cnt[alt];
+
+  // caller.is_germ_gt (caller.py:111-147)
+  bool germ;
+  if (state == 1) germ = (g0 == ref && g1 == alt);
+  else if (state == 2) germ = (cnt[0] + cnt[1] + cnt[2] + cnt[3] == cnt[g0] + cnt[g1]) && (alt == g0 || alt == g1);
+  else if (state == 3) germ = (ref_count == 0 && g0 == alt && g1 == alt);
+  else germ = (alt == g0);
+
+  int status, phase_set = -1;
+  if (germ) status = state == 1 ? HM_ST_GERM_HET : state == 2 ? HM_ST_GERM_HETALT : state == 3 ? HM_ST_GERM_HOMALT : HM_ST_GERM_HOMREF;
+  else if (state == 1) status = HM_ST_HET_SITE;
+  else if (state == 2) status = HM_ST_HETALT_SITE;
+  else if (state == 3) status = HM_ST_HOMALT_SITE;
+  else if (del_count != 0 || ins_count != 0) status = HM_ST_INDEL_SITE;
+  else {
+    const uint64_t skey = ((uint64_t)(uint32_t)tpos << 4) | ((uint64_t)ref << 2) | (uint64_t)alt;
+    if (gq < p.min_gq) status = HM_ST_LOW_GQ;
+    else if (hi_bq_alt == 0) status = HM_ST_LOW_BQ;
+    else if (!p.non_human_sample && !p.create_panel_of_normals && key_in_dev(sets.pon, sets.n_pon, skey)) status = HM_ST_PON;
+    else if (!p.non_human_sample && key_in_dev(sets.common, sets.n_common, skey)) status = HM_ST_COMSNP;
+    else if (!(ref_count >= p.min_ref_count && alt_count >= p.min_alt_count)) status = HM_ST_LOW_DEPTH;
+    else if ((double)depth > p.md_threshold) status = HM_ST_HIGH_DEPTH;
+    else {
+      status = HM_ST_PASS;
+      if (p.phase) { // caller.py:552-603
+        if (h0 >= p.min_hap_count && h1 >= p.min_hap_count && (som_mask == 1 || som_mask == 2)) phase_set = ch.start;
+        else status = HM_ST_UNPHASED;
+      }
+    }
+  }
+  const unsigned long long slot = atomicAdd(n_out, 1ull);
+  if (slot < cap) {
+    hm_site_record R;
+    R.tpos = tpos; R.ref = (uint8_t)ref; R.alt = (uint8_t)alt; R.status = (uint8_t)status;
+    R.flags = tie ? HM_SITE_PL_TIE : 0;
+    R.chunk = (int32_t)c; R.gq = gq;
+    R.germ_gt[0] = (uint8_t)g0; R.germ_gt[1] = (uint8_t)g1; R.germ_state = (uint8_t)state; R.pad0 = 0;
+#pragma unroll
+    for (int x = 0; x < 6; x++) R.counts[x] = cnt[x];
+#pragma unroll
+    for (int x = 0; x < 4; x++) R.bq_sum[x] = bqs[x];
+    const bool ph_eval = p.phase && (status == HM_ST_PASS || status == HM_ST_UNPHASED);
+    R.hap_count[0] = ph_eval ? h0 : 0; R.hap_count[1] = ph_eval ? h1 : 0;
+    R.som_hap_mask = ph_eval ? som_mask : 0;
+    R.phase_set = phase_set;
+    out[slot] = R;
+  }
+}
+
+// number of set bytes in flags[0..n)
+__global__ void k_count_flags(const uint8_t* flags, uint64_t n, unsigned long long* out) {
+  unsigned long long c = 0;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) c += flags[i] != 0;
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(HM_FULL, c, d);
+  if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, c);
+}

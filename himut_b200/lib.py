@@ -1,0 +1,189 @@
+"""ctypes binding of libhimut_b200.so (include/himut_b200.h).
+
+There is no CPU fallback: if the shared library is missing or no CUDA device is usable the
+calls raise.  Build with `python -c "import __graft_entry__ as g; g.build()"`.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import abi
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libhimut_b200.so")
+_LIB = None
+
+# every symbol include/himut_b200.h declares (tests/test_abi.py checks the export table)
+EXPORTS = [
+    "hm_abi_version", "hm_create", "hm_destroy", "hm_last_error", "hm_set_params", "hm_set_site_sets",
+    "hm_set_phase_sets", "hm_upload_batch", "hm_call_chunks", "hm_call_batch", "hm_normcounts_chunks",
+    "hm_read_stats", "hm_last_timing", "hm_last_kernel_times", "hm_set_stream", "hm_host_register",
+    "hm_host_unregister", "hm_abi_sizeof",
+]
+
+
+class HimutError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("himut_b200 error %d: %s" % (code, msg))
+        self.code = code
+
+
+def load():
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError("%s is missing (no CPU fallback exists): build it with "
+                               "`python -c 'import __graft_entry__ as g; g.build()'`" % LIB_PATH)
+        lib = C.CDLL(LIB_PATH)
+        vp, sz = C.c_void_p, C.c_size_t
+        lib.hm_abi_version.restype = C.c_int
+        lib.hm_abi_sizeof.restype = sz
+        lib.hm_abi_sizeof.argtypes = [C.c_int]
+        lib.hm_create.argtypes = [C.c_int, C.POINTER(vp)]
+        lib.hm_destroy.argtypes = [vp]
+        lib.hm_destroy.restype = None
+        lib.hm_last_error.argtypes = [vp]
+        lib.hm_last_error.restype = C.c_char_p
+        lib.hm_set_params.argtypes = [vp, C.POINTER(abi.hm_params)]
+        lib.hm_set_site_sets.argtypes = [vp, vp, sz, vp, sz]
+        lib.hm_set_phase_sets.argtypes = [vp, vp, vp, vp, vp, sz, vp, sz]
+        lib.hm_upload_batch.argtypes = [vp, C.POINTER(abi.hm_read_batch)]
+        lib.hm_call_chunks.argtypes = [vp, vp, sz, vp, sz, C.POINTER(sz), vp]
+        lib.hm_call_batch.argtypes = [vp, C.POINTER(abi.hm_read_batch), vp, sz, vp, sz, C.POINTER(sz), vp]
+        lib.hm_normcounts_chunks.argtypes = [vp, vp, sz, vp, sz, vp, vp, vp, C.POINTER(C.c_int64)]
+        lib.hm_read_stats.argtypes = [vp, vp, vp, vp, vp, vp, vp]
+        lib.hm_last_timing.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_int)]
+        lib.hm_last_kernel_times.argtypes = [vp, vp, vp, sz, C.POINTER(sz)]
+        lib.hm_set_stream.argtypes = [vp, vp]
+        lib.hm_host_register.argtypes = [vp, vp, sz]
+        lib.hm_host_unregister.argtypes = [vp, vp]
+        _LIB = lib
+    return _LIB
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None and a.size else None
+
+
+class Context:
+    """one hm_ctx: single-threaded, bound to one GPU; create it inside the worker process"""
+
+    def __init__(self, device=0):
+        self.lib = load()
+        h = C.c_void_p()
+        rc = self.lib.hm_create(int(device), C.byref(h))
+        if rc != 0:
+            raise HimutError(rc, "hm_create(device=%d) failed: no usable CUDA device (there is no CPU fallback)" % device)
+        self.h = h
+        self._keep = {}
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.hm_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _chk(self, rc):
+        if rc != 0:
+            raise HimutError(rc, self.lib.hm_last_error(self.h).decode())
+
+    # ---- configuration ----------------------------------------------------------------
+    def set_params(self, params):
+        self._chk(self.lib.hm_set_params(self.h, C.byref(params)))
+
+    def set_site_sets(self, common=None, pon=None):
+        common = np.zeros(0, np.uint64) if common is None else np.ascontiguousarray(common, np.uint64)
+        pon = np.zeros(0, np.uint64) if pon is None else np.ascontiguousarray(pon, np.uint64)
+        self._chk(self.lib.hm_set_site_sets(self.h, _p(common), common.size, _p(pon), pon.size))
+
+    def set_phase_sets(self, phase):
+        k = {n: np.ascontiguousarray(phase[n], dt) for n, dt in
+             (("hpos", np.int32), ("href", np.uint8), ("halt", np.uint8), ("hbit", np.uint8), ("set_off", np.uint64))}
+        self._chk(self.lib.hm_set_phase_sets(self.h, _p(k["hpos"]), _p(k["href"]), _p(k["halt"]), _p(k["hbit"]),
+                                             k["hpos"].size, _p(k["set_off"]), max(k["set_off"].size - 1, 0)))
+
+    def set_stream(self, cuda_stream):
+        self._chk(self.lib.hm_set_stream(self.h, C.c_void_p(cuda_stream)))
+
+    def pin(self, batch):
+        """page-lock the batch's big arrays so uploads run at PCIe speed"""
+        for name in ("seq", "bq", "ops"):
+            a = getattr(batch, name)
+            if a.size:
+                self._chk(self.lib.hm_host_register(self.h, _p(a), a.nbytes))
+                self._keep[id(a)] = a
+
+    def unpin(self, batch):
+        for name in ("seq", "bq", "ops"):
+            a = getattr(batch, name)
+            if id(a) in self._keep:
+                self.lib.hm_host_unregister(self.h, _p(a))
+                del self._keep[id(a)]
+
+    # ---- work -------------------------------------------------------------------------
+    def upload(self, batch):
+        self._chk(self.lib.hm_upload_batch(self.h, C.byref(batch.as_struct())))
+
+    def _call(self, fn, head, chunks, cap):
+        chunks = np.ascontiguousarray(chunks, dtype=abi.CHUNK_DTYPE)
+        cap = int(cap or 65536)
+        while True:
+            out = np.zeros(cap, dtype=abi.SITE_DTYPE)
+            n = C.c_size_t(0)
+            log = np.zeros(abi.CALL_LOG_LEN, np.int64)
+            rc = fn(self.h, *head, _p(chunks), len(chunks), _p(out), cap, C.byref(n), _p(log))
+            if rc == abi.HM_ERR_CAPACITY:
+                cap = int(n.value)
+                continue
+            self._chk(rc)
+            return out[: n.value].copy(), log
+
+    def call_chunks(self, chunks, cap=None):
+        """`himut call` over the resident batch -> (records, log[15])"""
+        return self._call(self.lib.hm_call_chunks, (), chunks, cap)
+
+    def call_batch(self, batch, chunks, cap=None):
+        """upload + call (host buffers in, records out): the end-to-end path"""
+        return self._call(self.lib.hm_call_batch, (C.byref(batch.as_struct()),), chunks, cap)
+
+    def normcounts_chunks(self, refseq, chunks):
+        """callable-base half of `himut normcounts` -> (ccs_tri[33], ref_tri[33], log[14], n_alt_tie)"""
+        chunks = np.ascontiguousarray(chunks, dtype=abi.CHUNK_DTYPE)
+        ref = np.frombuffer(refseq, dtype=np.uint8)
+        ccs = np.zeros(abi.TRI_BINS, np.int64)
+        rt = np.zeros(abi.TRI_BINS, np.int64)
+        log = np.zeros(abi.NORM_LOG_LEN, np.int64)
+        ties = C.c_int64(0)
+        self._chk(self.lib.hm_normcounts_chunks(self.h, _p(ref), ref.size, _p(chunks), len(chunks), _p(ccs), _p(rt),
+                                                _p(log), C.byref(ties)))
+        return ccs, rt, log, int(ties.value)
+
+    def read_stats(self, batch):
+        """per-read statistics of the resident batch (must be `batch`) from k_read_scan"""
+        n = batch.n_reads
+        out = dict(bq_total=np.zeros(n, np.int64), n_match=np.zeros(n, np.int32), n_sub=np.zeros(n, np.int32),
+                   ins_len=np.zeros(n, np.int32), del_len=np.zeros(n, np.int32), n_mismatch=np.zeros(n, np.int32))
+        self._chk(self.lib.hm_read_stats(self.h, *[_p(out[k]) for k in
+                                                   ("bq_total", "n_match", "n_sub", "ins_len", "del_len", "n_mismatch")]))
+        return out
+
+    def last_timing(self):
+        ms, n = C.c_float(0), C.c_int(0)
+        self._chk(self.lib.hm_last_timing(self.h, C.byref(ms), C.byref(n)))
+        return float(ms.value), int(n.value)
+
+    def last_kernel_times(self):
+        cap = 64
+        names = (C.c_char_p * cap)()
+        ms = (C.c_float * cap)()
+        n = C.c_size_t(0)
+        self._chk(self.lib.hm_last_kernel_times(self.h, C.cast(names, C.c_void_p), C.cast(ms, C.c_void_p), cap, C.byref(n)))
+        return [(names[i].decode(), float(ms[i])) for i in range(n.value)]

@@ -1,0 +1,287 @@
+"""Deterministic parity cases shared by tests/golden/make_golden.py (reference side, run in the
+build container) and the parity tests (oracle / CUDA side, run anywhere)."""
+import hashlib
+import os
+import random
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+from himut_b200 import abi, gtmodel, pack, synth  # noqa: E402
+
+CHROM = "chr1"
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def chunkloci(start, end):
+    """reference util.chunkloci (src/himut/util.py:119-132) restated for (start, end)"""
+    if end - start > 200000:
+        out = [(1, 200000)]
+        starts = list(range(200000, end, 200000))
+        for i, s in enumerate(starts[:-1]):
+            out.append((s, starts[i + 1]))
+        if (starts[-1], end) not in out:
+            out.append((starts[-1], end - 2))
+        return out
+    return [(start, end)]
+
+
+def batch_digest(batch):
+    h = hashlib.sha256()
+    for name, _ in abi.ReadBatch._FIELDS:
+        h.update(np.ascontiguousarray(getattr(batch, name)).tobytes())
+    return h.hexdigest()
+
+
+def adversarial_batch(seed, contig_len=3000, n_reads=120, max_len=900):
+    """short, dirty reads: dense subs/indels, N reference bases, soft clips, BQ spread,
+    secondary records, duplicate query names, reads ending at every kind of op boundary"""
+    rnd = random.Random(seed)
+    ref = [rnd.choice("ACGT") for _ in range(contig_len)]
+    for _ in range(contig_len // 200):
+        ref[rnd.randrange(contig_len)] = "N"
+    # a handful of "germline" positions so genotypes other than homref appear
+    germ = {}
+    for _ in range(contig_len // 60):
+        p = rnd.randrange(contig_len)
+        if ref[p] != "N":
+            alts = [b for b in "ACGT" if b != ref[p]]
+            rnd.shuffle(alts)
+            # kind 0/1: het on that haplotype, 2: hom-alt, 3: het-alt (a different alt per haplotype)
+            germ[p] = (alts[0], rnd.choice([0, 1, 2, 2, 3]), alts[1])
+    starts = sorted(rnd.randrange(0, contig_len - 60) for _ in range(n_reads))
+    bb = pack.BatchBuilder()
+    for i, ts in enumerate(starts):
+        length = rnd.randrange(40, max_len)
+        te = min(ts + length, contig_len)
+        hap = rnd.randrange(2)
+        lead = rnd.choice([0, 0, 0, rnd.randrange(1, 30)])
+        trail = rnd.choice([0, 0, 0, rnd.randrange(1, 30)])
+        bq_mode = rnd.choice(["hi", "hi", "mix", "low"])
+
+        def bq():
+            if bq_mode == "hi":
+                return 93 if rnd.random() < 0.9 else rnd.randrange(1, 94)
+            if bq_mode == "mix":
+                return rnd.choice([93, 93, 60, 40, 20, 10, 3, 1])
+            return rnd.randrange(1, 45)
+
+        qseq, bqs, cs = [], [], []
+        for _ in range(lead):
+            qseq.append(rnd.choice("ACGTN")); bqs.append(bq())
+        t, run, last_indel = ts, 0, True  # no indel before the first matched base
+        div = rnd.choice([0.0, 0.002, 0.01, 0.05])
+        while t < te:
+            r = ref[t]
+            g = germ.get(t)
+            u = rnd.random()
+            if r == "N":
+                if run:
+                    cs.append(":%d" % run); run = 0
+                a = rnd.choice("ACGT")
+                cs.append("*n%s" % a.lower()); qseq.append(a); bqs.append(bq()); t += 1; last_indel = False
+            elif g and (g[1] >= 2 or g[1] == hap) and rnd.random() < 0.95:
+                if run:
+                    cs.append(":%d" % run); run = 0
+                ga = g[2] if (g[1] == 3 and hap == 1) else g[0]
+                cs.append("*%s%s" % (r.lower(), ga.lower())); qseq.append(ga); bqs.append(bq()); t += 1; last_indel = False
+            elif u < div:
+                if run:
+                    cs.append(":%d" % run); run = 0
+                a = rnd.choice([b for b in "ACGT" if b != r])
+                cs.append("*%s%s" % (r.lower(), a.lower())); qseq.append(a); bqs.append(bq()); t += 1; last_indel = False
+            elif u < 2 * div and not last_indel and t + 6 < te:
+                if run:
+                    cs.append(":%d" % run); run = 0
+                n = rnd.randrange(1, 5)
+                if rnd.random() < 0.5:
+                    ins = [rnd.choice("ACGT") for _ in range(n)]
+                    cs.append("+" + "".join(ins).lower()); qseq.extend(ins); bqs.extend(bq() for _ in range(n))
+                else:
+                    cs.append("-" + "".join(x.lower() for x in ref[t:t + n])); t += n
+                last_indel = True
+            else:
+                qseq.append(r); bqs.append(bq()); run += 1; t += 1; last_indel = False
+        if run:
+            cs.append(":%d" % run)
+        qend = len(qseq)
+        for _ in range(trail):
+            qseq.append(rnd.choice("ACGTN")); bqs.append(bq())
+        qname = "r%d" % (i if rnd.random() > 0.03 else max(i - 1, 0))
+        bb.add(tstart=ts, tend=None, qstart=lead, qend=qend, qseq="".join(qseq), bq=bytes(bqs),
+               mapq=rnd.choice([60, 60, 60, 60, 30, 0]), is_secondary=rnd.random() < 0.03,
+               qname=qname, cs="".join(cs))
+    return bb.finish(), "".join(ref)
+
+
+# ------------------------------------------------------------------------------------------
+# case table: name -> dict(kind, make() -> (batch, refseq str), chunks, args, sets, phase)
+# ------------------------------------------------------------------------------------------
+def _synth_case(contig_len, seed, **over):
+    d = synth.generate(contig_len, seed=seed, **over)
+    return d
+
+
+def call_args(**over):
+    a = dict(gtmodel.DEFAULT_CALL_ARGS)
+    a.update(over)
+    return a
+
+
+def site_sets_from_synth(d, seed):
+    """synthetic common-SNP and PoN sets: most germline sites + a few somatic
+    sites are 'common'; a few error + somatic sites are in the panel of normals"""
+    rng = np.random.default_rng(seed)
+    g, s, e = d.germ, d.som, d.err
+    pick = lambda n, f: rng.random(n) < f
+    gm, sm, em, sm2 = pick(g["pos"].size, 0.8), pick(s["pos"].size, 0.3), pick(e["pos"].size, 0.3), pick(s["pos"].size, 0.3)
+    common = np.concatenate([synth.site_keys(g["pos"][gm], g["ref"][gm], g["alt"][gm]),
+                             synth.site_keys(s["pos"][sm], s["ref"][sm], s["alt"][sm])])
+    pon = np.concatenate([synth.site_keys(e["pos"][em], e["ref"][em], e["alt"][em]),
+                          synth.site_keys(s["pos"][sm2], s["ref"][sm2], s["alt"][sm2])])
+    return np.unique(common), np.unique(pon)
+
+
+def phase_case(d, phase_block):
+    """phase table + chunks = one (first_hpos, last_hpos) span per phase set (vcflib.py:655-662)"""
+    ph = synth.phase_table(d.germ, phase_block)
+    chunks, sets = [], []
+    for s in range(ph["set_off"].size - 1):
+        a, b = int(ph["set_off"][s]), int(ph["set_off"][s + 1])
+        chunks.append((int(ph["hpos"][a]), int(ph["hpos"][b - 1])))
+        sets.append(s)
+    return ph, chunks, sets
+
+
+CASES = {}
+
+
+def case(name):
+    def deco(fn):
+        CASES[name] = fn
+        return fn
+    return deco
+
+
+@case("call_basic")
+def _call_basic():
+    d = _synth_case(260_000, 11)
+    return dict(kind="call", batch=d.batch, ref=d.ref.decode(), contig_len=260_000,
+                chunks=chunkloci(0, 260_000), args=call_args())
+
+
+@case("call_sets")
+def _call_sets():
+    d = _synth_case(230_000, 12, somatic_rate=2e-5)
+    common, pon = site_sets_from_synth(d, 12)
+    return dict(kind="call", batch=d.batch, ref=d.ref.decode(), contig_len=230_000,
+                chunks=chunkloci(0, 230_000), args=call_args(), common=common, pon=pon)
+
+
+@case("call_lowdepth")
+def _call_lowdepth():
+    d = _synth_case(150_000, 13, depth=9.0, somatic_rate=2e-5, sub_err_rate=4e-4)
+    return dict(kind="call", batch=d.batch, ref=d.ref.decode(), contig_len=150_000,
+                chunks=chunkloci(0, 150_000), args=call_args(md_threshold=14, min_gq=10))
+
+
+@case("call_pon_params")
+def _call_pon_params():
+    # --create_panel_of_normals preset (util.load_pon_params, src/himut/util.py:44-63)
+    d = _synth_case(120_000, 14, sub_err_rate=5e-4)
+    common, pon = site_sets_from_synth(d, 14)
+    return dict(kind="call", batch=d.batch, ref=d.ref.decode(), contig_len=120_000,
+                chunks=chunkloci(0, 120_000),
+                args=call_args(min_bq=20, min_gq=10, min_qv=20, min_mapq=30, min_trim=0, min_hap_count=0,
+                               min_sequence_identity=0.8, create_panel_of_normals=True),
+                common=common, pon=pon)
+
+
+@case("call_phase")
+def _call_phase():
+    d = _synth_case(210_000, 15, somatic_rate=2e-5, phase_block=50_000)
+    ph, chunks, sets = phase_case(d, 50_000)
+    return dict(kind="call", batch=d.batch, ref=d.ref.decode(), contig_len=210_000,
+                chunks=chunks, phase_sets=sets, phase=ph, args=call_args(phase=True))
+
+
+@case("call_phase_shallow")
+def _call_phase_shallow():
+    # thin coverage: haplotype counts fall under min_hap_count -> Unphased rows
+    d = _synth_case(150_000, 16, depth=14.0, somatic_rate=6e-5, phase_block=30_000)
+    ph, chunks, sets = phase_case(d, 30_000)
+    return dict(kind="call", batch=d.batch, ref=d.ref.decode(), contig_len=150_000,
+                chunks=chunks, phase_sets=sets, phase=ph, args=call_args(phase=True, md_threshold=30))
+
+
+def _adv(seed, **over):
+    batch, ref = adversarial_batch(seed)
+    args = call_args(min_qv=20, min_mapq=20, qlen_lower_limit=30, qlen_upper_limit=900,
+                     min_sequence_identity=0.9, min_gq=5, min_bq=30, min_trim=0.05,
+                     max_mismatch_count=2, mismatch_window=8, md_threshold=45, min_ref_count=2)
+    args.update(over)
+    return batch, ref, args
+
+
+@case("call_adversarial_a")
+def _call_adv_a():
+    batch, ref, args = _adv(101)
+    return dict(kind="call", batch=batch, ref=ref, contig_len=len(ref), args=args,
+                chunks=[(0, 1000), (1000, 2000), (2000, 3000)])
+
+
+@case("call_adversarial_b")
+def _call_adv_b():
+    # overlapping / repeated regions (a --region_list with overlaps) and a strict window
+    batch, ref, args = _adv(102, max_mismatch_count=0, mismatch_window=20, min_trim=0.01)
+    return dict(kind="call", batch=batch, ref=ref, contig_len=len(ref), args=args,
+                chunks=[(0, 1500), (1200, 2400), (1200, 2400), (2399, 3000)])
+
+
+@case("norm_basic")
+def _norm_basic():
+    d = _synth_case(60_000, 21)
+    return dict(kind="norm", batch=d.batch, ref=d.ref.decode(), contig_len=60_000,
+                chunks=chunkloci(0, 60_000), args=call_args())
+
+
+@case("norm_sets")
+def _norm_sets():
+    d = _synth_case(50_000, 22, sub_err_rate=1e-3, somatic_rate=1e-4)
+    common, pon = site_sets_from_synth(d, 22)
+    return dict(kind="norm", batch=d.batch, ref=d.ref.decode(), contig_len=50_000,
+                chunks=[(1, 20000), (20000, 49998)], args=call_args(min_bq=60), common=common, pon=pon)
+
+
+@case("norm_phase")
+def _norm_phase():
+    d = _synth_case(60_000, 23, phase_block=20_000)
+    ph, chunks, sets = phase_case(d, 20_000)
+    return dict(kind="norm", batch=d.batch, ref=d.ref.decode(), contig_len=60_000,
+                chunks=chunks, phase_sets=sets, phase=ph, args=call_args(phase=True))
+
+
+@case("norm_adversarial")
+def _norm_adv():
+    batch, ref, args = _adv(103)
+    ref = ref[:500] + ref[500:520].lower() + ref[520:]
+    return dict(kind="norm", batch=batch, ref=ref, contig_len=len(ref), args=args,
+                chunks=[(0, 1000), (1000, 2000), (2000, 3000)])
+
+
+def build_case(name):
+    c = CASES[name]()
+    c["name"] = name
+    c.setdefault("common", np.zeros(0, np.uint64))
+    c.setdefault("pon", np.zeros(0, np.uint64))
+    c.setdefault("phase", None)
+    c.setdefault("phase_sets", None)
+    # the reference only loads the sets when neither flag is given (caller.py:248-289)
+    c["common_vcf"], c["pon_vcf"] = c["common"], c["pon"]
+    if c["args"].get("create_panel_of_normals") or c["args"].get("non_human_sample"):
+        c["common"], c["pon"] = np.zeros(0, np.uint64), np.zeros(0, np.uint64)
+    c["chunk_table"] = c["batch"].chunk_table(c["chunks"], c["phase_sets"])
+    c["params"] = gtmodel.make_params(**c["args"])
+    return c
