@@ -184,7 +184,7 @@ def _call_sets():
 def _call_lowdepth():
     d = _synth_case(150_000, 13, depth=9.0, somatic_rate=2e-5, sub_err_rate=4e-4)
     return dict(kind="call", batch=d.batch, ref=d.ref.decode(), contig_len=150_000,
-                chunks=chunkloci(0, 150_000), args=call_args(md_threshold=14, min_gq=10))
+                chunks=chunkloci(0, 150_000), args=call_args(md_threshold=14, min_gq=10, min_ref_count=7))
 
 
 @case("call_pon_params")
@@ -235,7 +235,7 @@ def _call_adv_a():
 @case("call_adversarial_b")
 def _call_adv_b():
     # overlapping / repeated regions (a --region_list with overlaps) and a strict window
-    batch, ref, args = _adv(102, max_mismatch_count=0, mismatch_window=20, min_trim=0.01)
+    batch, ref, args = _adv(102, max_mismatch_count=0, mismatch_window=20, min_trim=0.01, min_ref_count=8)
     return dict(kind="call", batch=batch, ref=ref, contig_len=len(ref), args=args,
                 chunks=[(0, 1500), (1200, 2400), (1200, 2400), (2399, 3000)])
 
