@@ -1,0 +1,325 @@
+#!/usr/bin/env python
+"""bench.py — `himut call` hot-path throughput on synthetic 30x CCS data (BASELINE.json).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--contig-mb M]
+
+A step is one pass of the whole `himut call` device path (k_read_scan -> k_candidates -> sort ->
+k_eval_sites -> host som_seen replay) over one contig's packed read batch.
+
+  value   aligned CCS bases/s with the batch already resident in HBM (hm_call_chunks),
+          CUDA events on the launching stream, barrier + synchronize on both sides, max over ranks
+  e2e     the same metric through the C-ABI call a worker makes with HOST buffers
+          (hm_call_batch: pinned host -> device copies, kernels, records back)
+  roofline  dominant kernel (k_read_scan): algorithmic bytes / its CUDA-event duration vs the
+          measured HBM copy bandwidth of MEASURED_PEAKS.json
+  cpu_baseline  the CPU oracle port (oracle/himut_oracle.c, 1 core like the reference on a
+          single contig) on a bounded sample of the same workload, rank 0 only
+
+N > 1 (torchrun, one rank per GPU): every rank owns one contig of the same size (different
+seed) — the genome shards by contig with no data-path collective; the 15 log counters are
+all-reduced over NCCL and record counts gathered at the end.  Weak scaling.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import numpy as np  # noqa: E402
+
+
+def chunkloci(end):
+    out = [(1, 200000)]
+    starts = list(range(200000, end, 200000))
+    for i, s in enumerate(starts[:-1]):
+        out.append((s, starts[i + 1]))
+    out.append((starts[-1], end - 2))
+    return out
+
+
+def make_workload(contig_len, seed):
+    from himut_b200 import gtmodel, synth
+    d = synth.generate(contig_len, seed=seed, copy=False)
+    params = gtmodel.make_params(**gtmodel.DEFAULT_CALL_ARGS)
+    chunks = d.batch.chunk_table(chunkloci(contig_len))
+    return d, params, chunks
+
+
+def kernel_alg_bytes(batch):
+    """algorithmic bytes of one k_read_scan launch: every quality byte once,
+    every op word once, per-read metadata once; outputs: two u32 prefix words + one mismatch
+    position per op at most, 29 B of per-read results"""
+    n_base = int(batch.qlen.astype(np.int64).sum())
+    n_op = int(batch.ops.size)
+    n_read = int(batch.n_reads)
+    return 1.0 * n_base + 4.0 * n_op + 33.0 * n_read + 12.0 * n_op + 29.0 * n_read, n_base, n_op, n_read
+
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.path = tempfile.mktemp(suffix=".csv")
+        self.gpu = gpu_index
+        self.proc = None
+
+    def start(self):
+        try:
+            self.f = open(self.path, "w")
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        self.proc.wait()
+        self.f.close()
+        sm, mx, reasons = [], [], set()
+        for line in open(self.path):
+            p = [x.strip() for x in line.split(",")]
+            if len(p) < 9:
+                continue
+            try:
+                sm.append(float(p[1])); mx.append(float(p[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.path)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def ncu_traffic():
+    """dram bytes per k_read_scan launch from the committed ncu capture, if one exists"""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)).get("k_read_scan_dram_bytes_per_launch")
+        except Exception:
+            return None
+    return None
+
+
+def cpu_baseline(d, params, chunks, n_chunks, reps=1):
+    """oracle port over the first n_chunks chunks; -> (bases/s, bases, seconds)"""
+    from oracle import oracle
+    sub = chunks[:n_chunks]
+    hi = int(sub["read_hi"].max())
+    # distinct reads fetched by the sample's chunks = reads [0, hi) that overlap [start0, endN)
+    b = d.batch
+    ov = (b.tstart[:hi] < int(sub["end"][-1])) & (b.tend[:hi] > int(sub["start"][0]))
+    kind, val = b.ops & 3, (b.ops >> 2).astype(np.int64)
+    qspan = np.where(kind == 0, val, 0) + (kind == 1) + np.where(kind == 2, val, 0)
+    per_read = np.add.reduceat(qspan, b.op_off.astype(np.int64))[:hi]
+    bases = int(per_read[ov].sum())
+    best = None
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        oracle.call_chunks(params, b, sub)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    return bases / best, bases, best
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the CPU implementation of the path (the oracle port: the reference is
+    pure Python and is not on this box), one core, on a bounded sample of the workload."""
+    if rank != 0:
+        return
+    contig_len = args.contig_mb * 1_000_000
+    d, params, chunks = make_workload(contig_len, args.seed)
+    n = min(len(chunks), args.cpu_chunks)
+    for _ in range(args.warmup):
+        cpu_baseline(d, params, chunks, n)
+    t0 = time.perf_counter()
+    tot = 0
+    for _ in range(args.steps):
+        v, bases, dt = cpu_baseline(d, params, chunks, n)
+        tot += bases
+    el = time.perf_counter() - t0
+    value = tot / el
+    sample = "first %d of %d chunks (%.1f Mb, %d aligned bases) of the %d Mb 30x contig per step" % (n, len(chunks), n * 0.2, bases, args.contig_mb)
+    print(json.dumps({
+        "impl": "reference", "metric": "aligned CCS bases/sec (himut call, 30x synthetic)", "value": value, "unit": "bases/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * el / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/f64", "data": "synthetic",
+        "config": workload_config(args, world),
+        "cpu_baseline": {"value": value, "unit": "bases/s", "cores": 1, "kind": "port", "sample": sample,
+                         "note": "C restatement of the pure-Python reference (oracle/himut_oracle.c); the reference itself ran "
+                                 "at 3e5-6e5 bases/s/core in the build container (tests/golden/*.json reference_seconds)"},
+        "e2e": {"value": value, "unit": "bases/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def workload_config(args, world):
+    return {"workload": "himut call on a %d Mb synthetic contig at 30x CCS (15 kb reads, cs tags), %d x 200 kb chunks%s"
+                        % (args.contig_mb, len(chunkloci(args.contig_mb * 1_000_000)), " per GPU" if world > 1 else ""),
+            "baseline_config": "configs[1]" if args.contig_mb == 64 else "custom",
+            "contig_mb": args.contig_mb, "depth": 30, "parallelism": "contig-sharded x%d" % world,
+            "l2": "inputs (>= 2 GB per step) are larger than the 126 MB L2; no explicit flush"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--contig-mb", type=int, default=64)
+    ap.add_argument("--seed", type=int, default=20260101)
+    ap.add_argument("--cpu-chunks", type=int, default=25)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    import __graft_entry__ as g
+    g.build()
+
+    if args.impl == "reference":
+        return run_reference(args, rank, world)
+
+    import torch
+    import torch.distributed as dist
+    from himut_b200 import lib
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    contig_len = args.contig_mb * 1_000_000
+    d, params, chunks = make_workload(contig_len, args.seed + 7919 * rank)
+    batch = d.batch
+    ctx = lib.Context(local_rank)
+    stream = torch.cuda.current_stream()
+    ctx.set_stream(stream.cuda_stream)
+    ctx.set_params(params)
+    ctx.set_site_sets()
+    ctx.pin(batch)
+    aligned = d.aligned_bases
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- resident (HBM) timing ----------------
+    ctx.upload(batch)
+    for _ in range(args.warmup):
+        rec, log = ctx.call_chunks(chunks, view=True)
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    k_ms = {}
+    e0.record(stream)
+    for _ in range(args.steps):
+        rec, log = ctx.call_chunks(chunks, view=True)
+        for name, ms in ctx.last_kernel_times():
+            k_ms.setdefault(name, []).append(ms)
+    e1.record(stream)
+    barrier()
+    clocks = sampler.stop()
+    ms_total = e0.elapsed_time(e1)
+
+    # ---------------- end to end (host buffers through the C ABI) ----------------
+    for _ in range(2):
+        ctx.call_batch(batch, chunks, view=True)
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record(stream)
+    for _ in range(args.steps):
+        rec_e, log_e = ctx.call_batch(batch, chunks, view=True)
+    f1.record(stream)
+    barrier()
+    ms_e2e = f0.elapsed_time(f1)
+    assert list(log_e) == list(log)
+
+    # ---------------- reduce over ranks ----------------
+    t = torch.tensor([ms_total, ms_e2e], device=dev, dtype=torch.float64)
+    tot = torch.tensor([float(aligned), float(rec.size)], device=dev, dtype=torch.float64)
+    logt = torch.tensor(np.asarray(log, np.int64), device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+        dist.all_reduce(logt, op=dist.ReduceOp.SUM)  # the only cross-GPU step of the path: 15 counters
+    ms_total, ms_e2e = float(t[0]), float(t[1])
+    all_bases, all_recs = float(tot[0]), int(tot[1])
+
+    if rank == 0:
+        value = all_bases * args.steps / (ms_total * 1e-3)
+        e2e = all_bases * args.steps / (ms_e2e * 1e-3)
+        alg, n_base, n_op, n_read = kernel_alg_bytes(batch)
+        scan_ms = float(np.mean(k_ms["k_read_scan"]))
+        peak, peak_src = measured_peak()
+        achieved = alg / (scan_ms * 1e-3) / 1e9
+        step_ms = {k: float(np.mean(v)) for k, v in k_ms.items()}
+        dev_ms = sum(step_ms.values())
+        # whole-step figure with SURVEY.md §8(d)'s formula (1.25 B per shipped base + ops + reads + records)
+        survey_bytes = 1.25 * n_base + 4.0 * n_op + 40.0 * n_read + 48.0 * rec.size
+        out = {
+            "metric": "aligned CCS bases/sec (himut call, 30x synthetic)", "value": value, "unit": "bases/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/f64", "data": "synthetic",
+            "config": workload_config(args, world),
+            "clocks": clocks,
+            "e2e": {"value": e2e, "unit": "bases/s", "h2d_bytes_per_step": int(batch.nbytes() + chunks.nbytes),
+                    "d2h_bytes_per_step": int(rec.nbytes + 32), "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": int(args.steps * sum(1 for k in step_ms if k.startswith("k_"))),
+            "dominant_kernel": max(step_ms, key=step_ms.get),
+            "library_launches_per_step": "cub::DeviceRadixSort (candidate keys)",
+            "roofline": {"bound": "hbm", "kernel": "k_read_scan", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": ncu_traffic(), "peak_source": peak_src,
+                         "alg_bytes_per_launch": alg, "kernel_ms": scan_ms,
+                         "share_of_step_device_time": scan_ms / dev_ms if dev_ms else None},
+            "roofline_step": {"formula": "SURVEY 8(d): 1.25*N_base + 4*N_op + 40*N_read + 48*N_cand", "bytes": survey_bytes,
+                              "device_ms": dev_ms, "achieved_gbs": survey_bytes / (dev_ms * 1e-3) / 1e9,
+                              "frac_of_peak": survey_bytes / (dev_ms * 1e-3) / 1e9 / peak},
+            "kernel_ms_per_step": step_ms,
+            "aligned_bases_per_step": int(all_bases), "site_records_per_step": all_recs,
+            "log_counters_sum": [int(v) for v in logt.tolist()],
+        }
+        if not args.no_cpu_baseline:
+            n = min(len(chunks), args.cpu_chunks)
+            v, bases, dt = cpu_baseline(d, params, chunks, n)
+            out["cpu_baseline"] = {"value": v, "unit": "bases/s", "cores": 1, "kind": "port",
+                                   "sample": "first %d of %d chunks (%d aligned bases, %.1f s) of the same contig" % (n, len(chunks), bases, dt)}
+        print(json.dumps(out))
+    ctx.unpin(batch)
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -16,6 +16,7 @@
 #include <vector>
 
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_select.cuh>
 
 #include "kernels.cuh"
 #include "normcounts.cuh"
@@ -64,7 +65,12 @@ struct hm_ctx {
   DevPhase dphase = {nullptr, nullptr, nullptr, nullptr, nullptr, 0};
   // work buffers
   DevBuf b_chunks, b_pair_off, b_pair_hap, b_qseen, b_keys, b_keys_sorted, b_cub, b_records, b_counters;
-  DevBuf b_ref, b_norm_out;
+  DevBuf b_ref, b_norm_out, b_lut, b_tile_off, b_agg, b_geom, b_bidx;
+  DevLut dlut = {nullptr};
+  // pinned staging for records coming back, final records of the last call
+  hm_site_record* h_stage = nullptr;
+  size_t h_stage_cap = 0;
+  std::vector<hm_site_record> final_recs;
   // timing
   std::vector<KTime> ktimes;
   std::vector<cudaEvent_t> ev_pool;
@@ -208,8 +214,9 @@ void hm_destroy(hm_ctx* ctx) {
                     &ctx->b_ins_len, &ctx->b_del_len, &ctx->b_n_mm, &ctx->b_gate, &ctx->b_pmax, &ctx->b_common, &ctx->b_pon,
                     &ctx->b_hpos, &ctx->b_href, &ctx->b_halt, &ctx->b_hbit, &ctx->b_set_off, &ctx->b_chunks,
                     &ctx->b_pair_off, &ctx->b_pair_hap, &ctx->b_qseen, &ctx->b_keys, &ctx->b_keys_sorted, &ctx->b_cub,
-                    &ctx->b_records, &ctx->b_counters, &ctx->b_ref, &ctx->b_norm_out};
+                    &ctx->b_records, &ctx->b_counters, &ctx->b_ref, &ctx->b_norm_out, &ctx->b_lut, &ctx->b_tile_off, &ctx->b_agg, &ctx->b_geom, &ctx->b_bidx};
   for (DevBuf* b : bufs) b->release();
+  if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
   for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
   if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
@@ -255,6 +262,9 @@ int hm_set_params(hm_ctx* ctx, const hm_params* params) {
   memcpy(t.log10_prior, params->log10_prior, sizeof(t.log10_prior));
   CU(cudaStreamSynchronize(ctx->stream));
   CU(cudaMemcpyToSymbol(c_tab, &t, sizeof(t)));
+  CU(ctx->b_lut.ensure(sizeof(t.lut)));
+  CU(cudaMemcpy(ctx->b_lut.p, t.lut, sizeof(t.lut), cudaMemcpyHostToDevice));
+  ctx->dlut.lut = ctx->b_lut.as<double>();
   ctx->have_params = true;
   return HM_OK;
 }
@@ -357,29 +367,32 @@ int hm_call_chunks(hm_ctx* ctx, const hm_chunk* chunks, size_t n_chunks, hm_site
   CU(cudaSetDevice(ctx->device));
   memset(log, 0, sizeof(int64_t) * HM_CALL_LOG_LEN);
   *n_out = 0;
+  ctx->final_recs.clear();
   t_reset(ctx);
   std::vector<uint64_t> pair_off;
   if ((rc = upload_chunks(ctx, chunks, n_chunks, pair_off))) return rc;
   const uint64_t n_pairs = pair_off.back();
   if ((rc = launch_read_scan(ctx))) return rc;
 
-  // counters: [0] n_keys, [1] n_records, [2] num_ccs, [3] error flag
-  CU(ctx->b_counters.ensure(64));
+  // counters (u64): [0] n_keys, [1] n_unique, [2] num_ccs, [3] error flag, [4] n_boundary, [8..23] status histogram
+  const size_t CNT_BYTES = 256;
+  CU(ctx->b_counters.ensure(CNT_BYTES));
   CU(ctx->b_qseen.ensure((size_t)ctx->max_qname_id + 1));
   if (ctx->params.phase) CU(ctx->b_pair_hap.ensure(n_pairs + 16));
-  unsigned long long h_cnt[4] = {0, 0, 0, 0};
+  unsigned long long h_cnt[32];
+  memset(h_cnt, 0, sizeof(h_cnt));
+  unsigned long long* d_cnt = ctx->b_counters.as<unsigned long long>();
   unsigned long long key_cap = std::max<unsigned long long>(ctx->n_ops_total, 1024);
   for (int attempt = 0; attempt < 2 && n_pairs; attempt++) {
     CU(ctx->b_keys.ensure(key_cap * 8));
-    CU(cudaMemsetAsync(ctx->b_counters.p, 0, 64, ctx->stream));
+    CU(cudaMemsetAsync(ctx->b_counters.p, 0, CNT_BYTES, ctx->stream));
     CU(cudaMemsetAsync(ctx->b_qseen.p, 0, (size_t)ctx->max_qname_id + 1, ctx->stream));
     const unsigned blocks = (unsigned)((n_pairs * 32 + 255) / 256);
     t_begin(ctx, "k_candidates");
     k_candidates<<<blocks, 256, 0, ctx->stream>>>(ctx->db, ctx->dp, ctx->dphase, ctx->b_chunks.as<hm_chunk>(), (uint32_t)n_chunks,
                                                   ctx->b_pair_off.as<uint64_t>(), n_pairs,
                                                   ctx->params.phase ? ctx->b_pair_hap.as<uint8_t>() : nullptr,
-                                                  ctx->b_qseen.as<uint8_t>(), ctx->b_keys.as<unsigned long long>(), key_cap,
-                                                  ctx->b_counters.as<unsigned long long>());
+                                                  ctx->b_qseen.as<uint8_t>(), ctx->b_keys.as<unsigned long long>(), key_cap, d_cnt);
     t_end(ctx);
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(h_cnt, ctx->b_counters.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
@@ -388,91 +401,161 @@ int hm_call_chunks(hm_ctx* ctx, const hm_chunk* chunks, size_t n_chunks, hm_site
     key_cap = h_cnt[0];
   }
   const unsigned long long n_keys = h_cnt[0];
-  std::vector<hm_site_record> recs;
-  if (n_keys) {
-    CU(ctx->b_keys_sorted.ensure(n_keys * 8));
-    size_t tmp = 0;
-    int end_bit = 36;
-    for (size_t c = n_chunks; c > 1; c >>= 1) end_bit++;
-    end_bit = std::min(end_bit + 1, 64);
-    CU(cub::DeviceRadixSort::SortKeys(nullptr, tmp, ctx->b_keys.as<unsigned long long>(), ctx->b_keys_sorted.as<unsigned long long>(),
-                                      (int64_t)n_keys, 0, end_bit, ctx->stream));
-    CU(ctx->b_cub.ensure(tmp));
-    t_begin(ctx, "cub_radix_sort_keys");
-    CU(cub::DeviceRadixSort::SortKeys(ctx->b_cub.p, tmp, ctx->b_keys.as<unsigned long long>(), ctx->b_keys_sorted.as<unsigned long long>(),
-                                      (int64_t)n_keys, 0, end_bit, ctx->stream));
-    t_end(ctx);
-    CU(ctx->b_records.ensure(n_keys * sizeof(hm_site_record)));
-    const unsigned blocks = (unsigned)((n_keys * 32 + 127) / 128);
-    t_begin(ctx, "k_eval_sites");
-    k_eval_sites<<<blocks, 128, 0, ctx->stream>>>(ctx->db, ctx->dp, ctx->dsets, ctx->b_chunks.as<hm_chunk>(),
-                                                  ctx->b_pair_off.as<uint64_t>(), ctx->b_pair_hap.as<uint8_t>(),
-                                                  ctx->b_keys_sorted.as<unsigned long long>(), n_keys, ctx->b_records.as<hm_site_record>(),
-                                                  n_keys, ctx->b_counters.as<unsigned long long>() + 1,
-                                                  reinterpret_cast<int*>(ctx->b_counters.as<unsigned long long>() + 3));
-    t_end(ctx);
-    CU(cudaGetLastError());
+
+  // chunk geometry for the som_seen carry: a position can only have been claimed by an earlier
+  // chunk if it lies at or below the largest chunk end seen so far, and only needs remembering if
+  // a later chunk starts at or below it.  With the reference's own chunking that is just the
+  // shared boundary position, so very few records ever reach the host replay.
+  std::vector<int32_t> geom(2 * n_chunks + 2);
+  int32_t* prev_max_end = geom.data();
+  int32_t* next_min_start = geom.data() + n_chunks;
+  {
+    int32_t m = INT32_MIN;
+    for (size_t i = 0; i < n_chunks; i++) { prev_max_end[i] = m; m = std::max(m, chunks[i].end); }
+    m = INT32_MAX;
+    for (size_t i = n_chunks; i-- > 0;) { next_min_start[i] = m; m = std::min(m, chunks[i].start); }
   }
+
+  size_t n_unique = 0, n_boundary = 0;
+  hm_site_record* recs = nullptr; // where the device records land on the host
+  bool direct = false;
+  std::vector<uint32_t> bidx;
   if (n_pairs) {
+    if (n_keys) {
+      // sort + unique of the candidate keys (library plumbing: cub), then the site kernels
+      CU(ctx->b_keys_sorted.ensure(n_keys * 8));
+      size_t tmp_sort = 0, tmp_uniq = 0;
+      int end_bit = 37;
+      for (size_t c = n_chunks; c > 1; c >>= 1) end_bit++;
+      end_bit = std::min(end_bit, 64);
+      unsigned long long* k_in = ctx->b_keys.as<unsigned long long>();
+      unsigned long long* k_sorted = ctx->b_keys_sorted.as<unsigned long long>();
+      CU(cub::DeviceRadixSort::SortKeys(nullptr, tmp_sort, k_in, k_sorted, (int64_t)n_keys, 0, end_bit, ctx->stream));
+      CU(cub::DeviceSelect::Unique(nullptr, tmp_uniq, k_sorted, k_in, d_cnt + 1, (int64_t)n_keys, ctx->stream));
+      CU(ctx->b_cub.ensure(std::max(tmp_sort, tmp_uniq)));
+      t_begin(ctx, "cub_sort_unique_keys");
+      CU(cub::DeviceRadixSort::SortKeys(ctx->b_cub.p, tmp_sort, k_in, k_sorted, (int64_t)n_keys, 0, end_bit, ctx->stream));
+      CU(cub::DeviceSelect::Unique(ctx->b_cub.p, tmp_uniq, k_sorted, k_in, d_cnt + 1, (int64_t)n_keys, ctx->stream));
+      t_end(ctx);
+      CU(cudaMemcpyAsync(h_cnt + 1, d_cnt + 1, 8, cudaMemcpyDeviceToHost, ctx->stream));
+      if ((rc = upload(ctx, ctx->b_geom, geom.data(), 2 * n_chunks))) return rc;
+      CU(cudaStreamSynchronize(ctx->stream));
+      n_unique = (size_t)h_cnt[1];
+      CU(ctx->b_agg.ensure(n_unique * sizeof(SiteAgg)));
+      CU(ctx->b_records.ensure(n_unique * sizeof(hm_site_record)));
+      CU(ctx->b_bidx.ensure(n_unique * 4));
+      t_begin(ctx, "k_site_gather");
+      k_site_gather<<<(unsigned)((n_unique * 32 + 255) / 256), 256, 0, ctx->stream>>>(
+          ctx->db, ctx->dp, ctx->dlut, ctx->b_chunks.as<hm_chunk>(), ctx->b_pair_off.as<uint64_t>(), ctx->b_pair_hap.as<uint8_t>(),
+          k_in, d_cnt + 1, ctx->b_agg.as<SiteAgg>());
+      t_end(ctx);
+      CU(cudaGetLastError());
+      t_begin(ctx, "k_site_verdict");
+      k_site_verdict<<<(unsigned)((n_unique + 255) / 256), 256, 0, ctx->stream>>>(
+          ctx->dp, ctx->dsets, ctx->b_chunks.as<hm_chunk>(), ctx->b_geom.as<int32_t>(), ctx->b_geom.as<int32_t>() + n_chunks, k_in,
+          d_cnt + 1, ctx->b_agg.as<SiteAgg>(), ctx->b_records.as<hm_site_record>(), d_cnt + 8, ctx->b_bidx.as<uint32_t>(),
+          (uint32_t)n_unique, d_cnt + 4, reinterpret_cast<int*>(d_cnt + 3));
+      t_end(ctx);
+      CU(cudaGetLastError());
+    }
     t_begin(ctx, "k_count_flags");
-    k_count_flags<<<148, 256, 0, ctx->stream>>>(ctx->b_qseen.as<uint8_t>(), (uint64_t)ctx->max_qname_id + 1,
-                                                ctx->b_counters.as<unsigned long long>() + 2);
+    k_count_flags<<<148, 256, 0, ctx->stream>>>(ctx->b_qseen.as<uint8_t>(), (uint64_t)ctx->max_qname_id + 1, d_cnt + 2);
     t_end(ctx);
     CU(cudaGetLastError());
-    CU(cudaMemcpyAsync(h_cnt, ctx->b_counters.p, 32, cudaMemcpyDeviceToHost, ctx->stream));
+    // records straight into the caller's buffer when it is large enough, else into pinned staging
+    direct = out && cap >= n_unique;
+    if (n_unique) {
+      if (!direct) {
+        if (n_unique > ctx->h_stage_cap) {
+          if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+          ctx->h_stage = nullptr; ctx->h_stage_cap = 0;
+          const size_t want = n_unique + n_unique / 4 + 1024;
+          CU(cudaHostAlloc((void**)&ctx->h_stage, want * sizeof(hm_site_record), cudaHostAllocDefault));
+          ctx->h_stage_cap = want;
+        }
+        recs = ctx->h_stage;
+      } else recs = out;
+      CU(cudaMemcpyAsync(recs, ctx->b_records.p, n_unique * sizeof(hm_site_record), cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    CU(cudaMemcpyAsync(h_cnt, ctx->b_counters.p, CNT_BYTES, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     if ((int)h_cnt[3] == HM_ERR_BQ_ZERO) return fail(ctx, HM_ERR_BQ_ZERO, "a base quality of 0 reached the genotype model (the reference raises ValueError: math.log10(0))");
-    recs.resize(h_cnt[1]);
-    if (h_cnt[1]) {
-      CU(cudaMemcpyAsync(recs.data(), ctx->b_records.p, h_cnt[1] * sizeof(hm_site_record), cudaMemcpyDeviceToHost, ctx->stream));
+    n_boundary = n_keys ? (size_t)h_cnt[4] : 0;
+    if (n_boundary) {
+      bidx.resize(n_boundary);
+      CU(cudaMemcpyAsync(bidx.data(), ctx->b_bidx.p, n_boundary * 4, cudaMemcpyDeviceToHost, ctx->stream));
       CU(cudaStreamSynchronize(ctx->stream));
     }
   }
   t_collect(ctx);
 
-  // sequential part: chunk order, som_seen carry, counters (caller.py:324-347,625-641)
-  std::sort(recs.begin(), recs.end(), [](const hm_site_record& a, const hm_site_record& b) {
-    if (a.chunk != b.chunk) return a.chunk < b.chunk;
-    if (a.tpos != b.tpos) return a.tpos < b.tpos;
-    if (a.ref != b.ref) return a.ref < b.ref;
-    return a.alt < b.alt;
-  });
-  std::unordered_set<int32_t> som_seen;
-  std::vector<int32_t> adds;
-  size_t n_final = 0, i = 0;
-  log[0] = (int64_t)h_cnt[2];
-  while (i < recs.size()) {
-    const int32_t chunk = recs[i].chunk;
-    adds.clear();
-    for (; i < recs.size() && recs[i].chunk == chunk; i++) {
-      const hm_site_record& R = recs[i];
-      if (som_seen.count(R.tpos)) continue; // dropped in get_tsbs_candidates (bamlib.py:77)
-      log[1]++;
-      switch (R.status) {
-        case HM_ST_GERM_HET: log[2]++; break;
-        case HM_ST_GERM_HETALT: log[3]++; break;
-        case HM_ST_GERM_HOMALT: log[4]++; break;
-        case HM_ST_GERM_HOMREF: break;
-        case HM_ST_HET_SITE: case HM_ST_HETALT_SITE: case HM_ST_HOMALT_SITE: log[5]++; break;
-        case HM_ST_INDEL_SITE: log[7]++; break;
-        default:
-          log[6]++;
-          if (R.status == HM_ST_LOW_GQ) log[8]++;
-          else if (R.status == HM_ST_LOW_BQ) log[9]++;
-          else if (R.status == HM_ST_PON) log[10]++;
-          else if (R.status == HM_ST_COMSNP) log[11]++;
-          else if (R.status == HM_ST_HIGH_DEPTH) log[12]++;
-          else if (R.status == HM_ST_LOW_DEPTH) log[13]++;
-          else log[14]++; // PASS / Unphased: num_som is counted before the phase verdict
+  // sequential part: chunk order, som_seen carry (caller.py:324-347; bamlib.py:77), over the
+  // boundary records only.  Indices are positions in the key order = (chunk, tpos, ref, alt).
+  unsigned long long* hist = h_cnt + 8;
+  std::vector<uint32_t> dropped;
+  if (n_boundary) {
+    std::sort(bidx.begin(), bidx.end());
+    std::unordered_set<int32_t> som_seen;
+    std::vector<int32_t> adds;
+    size_t i = 0;
+    while (i < n_boundary) {
+      const int32_t chunk = recs[bidx[i]].chunk;
+      adds.clear();
+      for (; i < n_boundary && recs[bidx[i]].chunk == chunk; i++) {
+        const hm_site_record& R = recs[bidx[i]];
+        if (R.tpos <= prev_max_end[chunk] && som_seen.count(R.tpos)) { // dropped in get_tsbs_candidates
+          dropped.push_back(bidx[i]);
+          hist[R.status]--;
+          continue;
+        }
+        const bool restates = R.status >= HM_ST_GERM_HET && R.status <= HM_ST_GERM_HOMREF;
+        if (!restates && R.tpos >= next_min_start[chunk]) adds.push_back(R.tpos); // som_seen.add(tpos), caller.py:347
       }
-      if (R.status > HM_ST_GERM_HOMREF) adds.push_back(R.tpos);
-      if (n_final < cap && out) out[n_final] = R;
-      n_final++;
+      for (int32_t t : adds) som_seen.insert(t);
     }
-    for (int32_t t : adds) som_seen.insert(t);
+  }
+  // chrom2tsbs_log (caller.py:625-641) from the status tallies
+  {
+    unsigned long long total = 0;
+    for (int k = 0; k < 16; k++) total += hist[k];
+    log[0] = (int64_t)h_cnt[2];
+    log[1] = (int64_t)total;
+    log[2] = (int64_t)hist[HM_ST_GERM_HET]; log[3] = (int64_t)hist[HM_ST_GERM_HETALT]; log[4] = (int64_t)hist[HM_ST_GERM_HOMALT];
+    log[5] = (int64_t)(hist[HM_ST_HET_SITE] + hist[HM_ST_HETALT_SITE] + hist[HM_ST_HOMALT_SITE]);
+    log[7] = (int64_t)hist[HM_ST_INDEL_SITE];
+    log[8] = (int64_t)hist[HM_ST_LOW_GQ]; log[9] = (int64_t)hist[HM_ST_LOW_BQ]; log[10] = (int64_t)hist[HM_ST_PON];
+    log[11] = (int64_t)hist[HM_ST_COMSNP]; log[12] = (int64_t)hist[HM_ST_HIGH_DEPTH]; log[13] = (int64_t)hist[HM_ST_LOW_DEPTH];
+    log[14] = (int64_t)(hist[HM_ST_PASS] + hist[HM_ST_UNPHASED]); // num_som is counted before the phase verdict
+    log[6] = log[8] + log[9] + log[10] + log[11] + log[12] + log[13] + log[14];
+  }
+  // squeeze the dropped records out (ascending indices)
+  size_t n_final = n_unique;
+  if (!dropped.empty() && recs) {
+    size_t w = dropped[0];
+    for (size_t d = 0; d < dropped.size(); d++) {
+      const size_t from = (size_t)dropped[d] + 1, to = d + 1 < dropped.size() ? dropped[d + 1] : n_unique;
+      memmove(recs + w, recs + from, (to - from) * sizeof(hm_site_record));
+      w += to - from;
+    }
+    n_final = w;
   }
   *n_out = n_final;
-  if (n_final > cap) return fail(ctx, HM_ERR_CAPACITY, "output holds %zu records, %zu needed", cap, n_final);
+  if (!direct && n_final) {
+    if (out && cap >= n_final) memcpy(out, recs, n_final * sizeof(hm_site_record));
+    else {
+      ctx->final_recs.assign(recs, recs + n_final);
+      return fail(ctx, HM_ERR_CAPACITY, "output holds %zu records, %zu needed (hm_last_records fetches them without recomputing)", cap, n_final);
+    }
+  }
+  return HM_OK;
+}
+
+/* records of the last hm_call_chunks that returned HM_ERR_CAPACITY, without recomputing */
+int hm_last_records(hm_ctx* ctx, hm_site_record* out, size_t cap, size_t* n_out) {
+  if (!ctx || !n_out) return HM_ERR_ARG;
+  *n_out = ctx->final_recs.size();
+  if (cap < ctx->final_recs.size() || (!out && !ctx->final_recs.empty())) return fail(ctx, HM_ERR_CAPACITY, "output holds %zu records, %zu needed", cap, ctx->final_recs.size());
+  if (!ctx->final_recs.empty()) memcpy(out, ctx->final_recs.data(), ctx->final_recs.size() * sizeof(hm_site_record));
   return HM_OK;
 }
 
@@ -531,6 +614,69 @@ int hm_last_kernel_times(hm_ctx* ctx, const char** names, float* ms, size_t cap,
 
 }  // extern "C"
 
-static int hm_normcounts_impl(hm_ctx* ctx, const uint8_t*, size_t, const hm_chunk*, size_t, int64_t*, int64_t*, int64_t*, int64_t*) {
-  return fail(ctx, HM_ERR_STATE, "hm_normcounts_chunks: kernel not built yet");
+static int hm_normcounts_impl(hm_ctx* ctx, const uint8_t* refseq, size_t ref_len, const hm_chunk* chunks, size_t n_chunks,
+                              int64_t* ccs_tri, int64_t* ref_tri, int64_t* log, int64_t* n_alt_tie) {
+  if (!refseq || !ccs_tri || !ref_tri || !log) return fail(ctx, HM_ERR_ARG, "refseq / output pointer is NULL");
+  CU(cudaSetDevice(ctx->device));
+  memset(ccs_tri, 0, sizeof(int64_t) * HM_TRI_BINS);
+  memset(ref_tri, 0, sizeof(int64_t) * HM_TRI_BINS);
+  memset(log, 0, sizeof(int64_t) * HM_NORM_LOG_LEN);
+  if (n_alt_tie) *n_alt_tie = 0;
+  t_reset(ctx);
+  std::vector<uint64_t> pair_off;
+  int rc = upload_chunks(ctx, chunks, n_chunks, pair_off);
+  if (rc) return rc;
+  const uint64_t n_pairs = pair_off.back();
+  std::vector<uint64_t> tile_off(n_chunks + 1, 0);
+  for (size_t i = 0; i < n_chunks; i++) {
+    const int64_t span = (int64_t)chunks[i].end - (int64_t)chunks[i].start;
+    tile_off[i + 1] = tile_off[i] + (span > 0 ? (uint64_t)((span + HM_TILE_W - 1) / HM_TILE_W) : 0);
+  }
+  const uint64_t n_tiles = tile_off.back();
+  if (n_tiles >= (1ull << 31)) return fail(ctx, HM_ERR_ARG, "too many tiles in one call");
+  if ((rc = upload(ctx, ctx->b_tile_off, tile_off.data(), tile_off.size()))) return rc;
+  if ((rc = upload(ctx, ctx->b_ref, refseq, ref_len))) return rc;
+  if ((rc = launch_read_scan(ctx))) return rc;
+  CU(ctx->b_norm_out.ensure(sizeof(NormOut)));
+  CU(ctx->b_counters.ensure(64));
+  CU(ctx->b_qseen.ensure((size_t)ctx->max_qname_id + 1));
+  CU(ctx->b_pair_hap.ensure(n_pairs + 16));
+  CU(cudaMemsetAsync(ctx->b_norm_out.p, 0, sizeof(NormOut), ctx->stream));
+  CU(cudaMemsetAsync(ctx->b_counters.p, 0, 64, ctx->stream));
+  CU(cudaMemsetAsync(ctx->b_qseen.p, 0, (size_t)ctx->max_qname_id + 1, ctx->stream));
+  NormOut h;
+  memset(&h, 0, sizeof(h));
+  unsigned long long h_cnt[4] = {0, 0, 0, 0};
+  if (n_pairs && n_tiles) {
+    unsigned blocks = (unsigned)((n_pairs * 32 + 255) / 256);
+    t_begin(ctx, "k_pair_info");
+    k_pair_info<<<blocks, 256, 0, ctx->stream>>>(ctx->db, ctx->dp, ctx->dphase, ctx->b_chunks.as<hm_chunk>(), (uint32_t)n_chunks,
+                                                 ctx->b_pair_off.as<uint64_t>(), n_pairs, ctx->b_pair_hap.as<uint8_t>(),
+                                                 ctx->b_qseen.as<uint8_t>());
+    t_end(ctx);
+    CU(cudaGetLastError());
+    t_begin(ctx, "k_norm_tiles");
+    k_norm_tiles<<<(unsigned)n_tiles, HM_TILE_W, 0, ctx->stream>>>(ctx->db, ctx->dp, ctx->dsets, ctx->dlut, ctx->b_chunks.as<hm_chunk>(),
+                                                                   (uint32_t)n_chunks, ctx->b_pair_off.as<uint64_t>(),
+                                                                   ctx->b_pair_hap.as<uint8_t>(), ctx->b_tile_off.as<uint64_t>(),
+                                                                   ctx->b_ref.as<uint8_t>(), (uint64_t)ref_len,
+                                                                   ctx->b_norm_out.as<NormOut>());
+    t_end(ctx);
+    CU(cudaGetLastError());
+    t_begin(ctx, "k_count_flags");
+    k_count_flags<<<148, 256, 0, ctx->stream>>>(ctx->b_qseen.as<uint8_t>(), (uint64_t)ctx->max_qname_id + 1,
+                                                ctx->b_counters.as<unsigned long long>() + 2);
+    t_end(ctx);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(&h, ctx->b_norm_out.p, sizeof(NormOut), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(h_cnt, ctx->b_counters.p, 32, cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  CU(cudaStreamSynchronize(ctx->stream));
+  t_collect(ctx);
+  if (h.err == HM_ERR_BQ_ZERO) return fail(ctx, HM_ERR_BQ_ZERO, "a base quality of 0 reached the genotype model (the reference raises ValueError: math.log10(0))");
+  for (int i = 0; i < HM_TRI_BINS; i++) { ccs_tri[i] = (int64_t)h.ccs_tri[i]; ref_tri[i] = (int64_t)h.ref_tri[i]; }
+  for (int i = 1; i < HM_NORM_LOG_LEN; i++) log[i] = (int64_t)h.log[i];
+  log[0] = (int64_t)h_cnt[2];
+  if (n_alt_tie) *n_alt_tie = (int64_t)h.alt_tie;
+  return HM_OK;
 }

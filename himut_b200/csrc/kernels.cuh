@@ -9,10 +9,11 @@
 //                   then trim + mismatch-window filter of every substitution
 //                   (bamlib.get_tsbs_candidates, src/himut/bamlib.py:69-86,222-282;
 //                    haplib.get_ccs_hap, src/himut/haplib.py:46-83)
-//   k_eval_sites    per distinct candidate: ordered pileup of the chunk's reads at the site,
-//                   10-genotype PL / GQ, germline-restatement test and the filter cascade
-//                   (caller.update_allelecounts, caller.py:44-72; gtlib.py:72-174;
-//                    caller.py:324-621)
+//   k_site_gather   per distinct candidate: ordered pileup of the chunk's reads at the site
+//                   (caller.update_allelecounts, caller.py:44-72): 6 counts, BQ sums, the 12
+//                   ordered fp64 sums of the genotype model, haplotype tallies
+//   k_site_verdict  per distinct candidate: 10-genotype PL / GQ (gtlib.py:72-174), germline
+//                   restatement test and the filter cascade (caller.py:324-621) -> record
 //
 // All streaming, integer / byte work plus ordered fp64 adds; no tensor-core work exists on
 // this path.  fp64 sums use __dadd_rn / __dmul_rn so nothing is contracted into FMAs: the
@@ -79,6 +80,10 @@ struct DevPhase {
   const uint64_t* set_off;
   uint32_t n_sets;
 };
+
+// the three per-BQ tables again, in global memory: lanes index them with different bq, which
+// would serialise on the constant cache
+struct DevLut { const double* lut; }; // [3][256]
 
 struct DevSets {
   const uint64_t* common;
@@ -338,7 +343,7 @@ __global__ void __launch_bounds__(256) k_candidates(DevBatch b, DevParams p, Dev
   }
 }
 
-// ============================================================================ k_eval_sites
+// ============================================================================ genotype model
 // gtlib.gt_lst (gtlib.py:9) as base codes A0 T1 G2 C3
 __device__ __constant__ int8_t c_gt_b1[10] = {0, 1, 3, 2, 1, 3, 2, 3, 2, 2};
 __device__ __constant__ int8_t c_gt_b2[10] = {0, 0, 0, 0, 1, 1, 1, 3, 3, 2};
@@ -383,61 +388,129 @@ __device__ __forceinline__ int argmin_gt_dev(const double pl[10], int* gq, bool*
   return best;
 }
 
-// One warp per sorted candidate key; duplicates of the previous key exit at once.
-// Lanes take one read each (32 at a time, file order); the per-allele ordered fp64 sums are
-// owned by lanes 0..11 (allele = lane / 3, kind = lane % 3) and fed in read order.
-__global__ void __launch_bounds__(128) k_eval_sites(DevBatch b, DevParams p, DevSets sets, const hm_chunk* chunks,
-                                                    const uint64_t* pair_off, const uint8_t* pair_hap,
-                                                    const unsigned long long* keys, unsigned long long n_keys,
-                                                    hm_site_record* out, unsigned long long cap,
-                                                    unsigned long long* n_out, int* err_flag) {
-  __shared__ double s_lut[3][256];
-  for (int i = threadIdx.x; i < 768; i += blockDim.x) s_lut[i >> 8][i & 255] = c_tab.lut[i >> 8][i & 255];
-  __syncthreads();
+// ---- searches with short dependency chains -------------------------------------------------
+// number of elements <= x in sorted a[0..n): 8-ary, the 7 pivots of a level are independent loads
+__device__ __forceinline__ uint32_t count_le_kary(const uint32_t* a, uint32_t n, uint32_t x) {
+  uint32_t lo = 0, len = n;
+  while (len > 8) {
+    const uint32_t step = (len + 7) >> 3, end = lo + len;
+    uint32_t c = 0;
+#pragma unroll
+    for (uint32_t i = 1; i < 8; i++) {
+      const uint32_t idx = lo + step * i - 1;
+      if (idx < end) c += (__ldg(a + idx) <= x);
+    }
+    lo += c * step;
+    len = min(step, end - lo);
+  }
+  uint32_t c = 0;
+#pragma unroll
+  for (uint32_t i = 0; i < 8; i++)
+    if (i < len) c += (__ldg(a + lo + i) <= x);
+  return lo + c;
+}
+// warp-cooperative: number of elements of sorted a[0..n) that are < x (strict) or <= x
+template <bool kStrict>
+__device__ __forceinline__ uint32_t warp_count_below(const int32_t* a, uint32_t n, int32_t x, int lane) {
+  uint32_t lo = 0, len = n;
+  while (len > 32) {
+    const uint32_t step = (len + 32) / 33, end = lo + len;
+    const uint32_t idx = lo + step * (lane + 1) - 1;
+    bool below = false;
+    if (idx < end) { const int32_t v = __ldg(a + idx); below = kStrict ? (v < x) : (v <= x); }
+    const uint32_t c = __popc(__ballot_sync(HM_FULL, below));
+    lo += c * step;
+    len = min(step, end - lo);
+  }
+  bool below = false;
+  if ((uint32_t)lane < len) { const int32_t v = __ldg(a + lo + lane); below = kStrict ? (v < x) : (v <= x); }
+  return lo + __popc(__ballot_sync(HM_FULL, below));
+}
+
+// read_allele_at with the 8-ary op search
+__device__ __forceinline__ int read_allele_fast(const DevBatch& b, uint32_t r, int32_t rpos, int32_t ts, int* bq, int* ins) {
+  const uint32_t n = __ldg(b.n_ops + r);
+  *bq = 0; *ins = 0;
+  if (n == 0) return -1;
+  const uint64_t o0 = __ldg(b.op_off + r);
+  const uint32_t off = (uint32_t)(rpos - ts);
+  const int k = (int)count_le_kary(b.op_t + o0, n, off) - 1;
+  int cnt = 0;
+  for (int j = k; j >= 0 && __ldg(b.op_t + o0 + j) == off; j--)
+    if ((__ldg(b.ops + o0 + j) & 3u) == HM_OP_INS) cnt++;
+  *ins = cnt;
+  const uint32_t w = __ldg(b.ops + o0 + k);
+  const uint32_t kind = w & 3u, v = w >> 2, t0 = __ldg(b.op_t + o0 + k);
+  const uint32_t rl = (uint32_t)op_ref_len(w);
+  if (rl == 0 || off >= t0 + rl) return -1;
+  if (kind == HM_OP_DEL) return 5;
+  const uint32_t q = __ldg(b.op_q + o0 + k) + (kind == HM_OP_MATCH ? off - t0 : 0u);
+  *bq = b.bq[__ldg(b.bq_off + r) + q];
+  if (kind == HM_OP_SUB) return (int)((v >> 3) & 7u);
+  return (b.seq[__ldg(b.seq_off + r) + (q >> 2)] >> (2 * (q & 3u))) & 3;
+}
+
+// what k_site_gather hands to k_site_verdict, one per distinct candidate key
+struct SiteAgg {
+  double S[12];      // ordered fp64 sums, [allele * 3 + kind]
+  int32_t cnt[6];    // rpos2allelecounts
+  int32_t bqs[4];    // sum of BQ per base allele
+  int32_t hi_bq_alt; // alt reads with BQ >= min_bq (caller.is_low_bq)
+  int32_t h0, h1, som_mask;
+  int32_t bq_zero;
+  int32_t pad;
+};
+
+// ============================================================================ k_site_gather
+// One warp per distinct candidate key (sorted by chunk, position, ref, alt).  Lanes take one
+// read each (32 at a time, file order) and look the read's allele / BQ / insertion up at the
+// site; the per-allele ordered fp64 sums are owned by lanes 0..11 (allele = lane / 3,
+// kind = lane % 3) and fed in read order (caller.update_allelecounts appends in fetch order).
+__global__ void __launch_bounds__(256, 5) k_site_gather(DevBatch b, DevParams p, DevLut lut, const hm_chunk* chunks,
+                                                     const uint64_t* pair_off, const uint8_t* pair_hap,
+                                                     const unsigned long long* keys, const unsigned long long* n_keys_dev,
+                                                     SiteAgg* agg) {
   const uint64_t ki = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
-  if (ki >= n_keys) return;
+  if (ki >= *n_keys_dev) return;
   const unsigned long long key = keys[ki];
-  if (ki > 0 && keys[ki - 1] == key) return;
   const uint32_t c = (uint32_t)(key >> 36);
   const int32_t tpos = (int32_t)((key >> 4) & 0xffffffffull);
   const int ref = (int)((key >> 2) & 3), alt = (int)(key & 3);
   const int32_t rpos = tpos - 1;
   const hm_chunk ch = chunks[c];
 
-  // reads that can touch rpos: running-max(tend) >= rpos (a trailing insertion sits at tend)
-  // and tstart <= rpos, inside the chunk's fetch range
-  uint32_t lo = lower_bound_dev(b.pmax_tend, (uint32_t)b.n_reads, rpos);
-  uint32_t hi = upper_bound_dev(b.tstart, (uint32_t)b.n_reads, rpos);
-  if (lo < ch.read_lo) lo = ch.read_lo;
-  if (hi > ch.read_hi) hi = ch.read_hi;
+  // reads that can touch rpos, inside the chunk's fetch range: running-max(tend) >= rpos
+  // (a trailing insertion sits at tend) and tstart <= rpos
+  const uint32_t n_in = ch.read_hi - ch.read_lo;
+  const uint32_t lo = ch.read_lo + warp_count_below<true>(b.pmax_tend + ch.read_lo, n_in, rpos, lane);
+  const uint32_t hi = ch.read_lo + warp_count_below<false>(b.tstart + ch.read_lo, n_in, rpos, lane);
+  const double* my_lut = lut.lut + (lane % 3) * 256;
+  const int my_a = lane / 3;
 
-  int cnt[6] = {0, 0, 0, 0, 0, 0}, bqs[4] = {0, 0, 0, 0};
+  int cnt0 = 0, cnt1 = 0, cnt2 = 0, cnt3 = 0, cnt4 = 0, cnt5 = 0, bq0 = 0, bq1 = 0, bq2 = 0, bq3 = 0;
   int hi_bq_alt = 0, h0 = 0, h1 = 0, som_mask = 0;
   bool bq_zero = false;
   double S = 0.0; // lanes 0..11
-  const int my_a = lane / 3, my_k = lane % 3;
   for (uint32_t base = lo; base < hi; base += 32) {
     const uint32_t r = base + lane;
     int a = -1, bq = 0, ins = 0, hap = 2;
     bool next_cov = false;
-    if (r < hi && !(b.flags[r] & HM_READ_SECONDARY)) {
-      const int32_t ts = b.tstart[r], te = b.tend[r];
+    if (r < hi && !(__ldg(b.flags + r) & HM_READ_SECONDARY)) {
+      const int32_t ts = __ldg(b.tstart + r), te = __ldg(b.tend + r);
       if (ts < ch.end && te > ch.start && ts <= rpos && rpos <= te) {
-        a = read_allele_at(b, r, rpos, &bq, &ins);
+        a = read_allele_fast(b, r, rpos, ts, &bq, &ins);
         next_cov = te > tpos; // overlaps [tpos, tpos+1) (caller.py:558)
         if (p.phase) hap = pair_hap[pair_off[c] + (r - ch.read_lo)];
       }
     }
-    const uint32_t m_base = __ballot_sync(HM_FULL, a >= 0 && a < 4);
-#pragma unroll
-    for (int x = 0; x < 4; x++) {
-      const uint32_t m = __ballot_sync(HM_FULL, a == x);
-      cnt[x] += __popc(m);
-      bqs[x] += __reduce_add_sync(HM_FULL, a == x ? bq : 0);
-    }
-    cnt[5] += __popc(__ballot_sync(HM_FULL, a == 5));
-    cnt[4] += __reduce_add_sync(HM_FULL, ins);
+    const uint32_t m0 = __ballot_sync(HM_FULL, a == 0), m1 = __ballot_sync(HM_FULL, a == 1);
+    const uint32_t m2 = __ballot_sync(HM_FULL, a == 2), m3 = __ballot_sync(HM_FULL, a == 3);
+    cnt0 += __popc(m0); cnt1 += __popc(m1); cnt2 += __popc(m2); cnt3 += __popc(m3);
+    bq0 += __reduce_add_sync(HM_FULL, a == 0 ? bq : 0); bq1 += __reduce_add_sync(HM_FULL, a == 1 ? bq : 0);
+    bq2 += __reduce_add_sync(HM_FULL, a == 2 ? bq : 0); bq3 += __reduce_add_sync(HM_FULL, a == 3 ? bq : 0);
+    cnt5 += __popc(__ballot_sync(HM_FULL, a == 5));
+    cnt4 += __reduce_add_sync(HM_FULL, ins);
     hi_bq_alt += __popc(__ballot_sync(HM_FULL, a == alt && bq >= p.min_bq));
     bq_zero |= __any_sync(HM_FULL, a >= 0 && a < 4 && bq == 0);
     if (p.phase) {
@@ -447,66 +520,91 @@ __global__ void __launch_bounds__(128) k_eval_sites(DevBatch b, DevParams p, Dev
       if (__any_sync(HM_FULL, a == alt && next_cov && hap == 1)) som_mask |= 2;
     }
     // ordered sums: walk the base-carrying lanes in read order
-    uint32_t m = m_base;
+    uint32_t m = m0 | m1 | m2 | m3;
     while (m) {
       const int src = __ffs(m) - 1;
       m &= m - 1;
       const int sa = __shfl_sync(HM_FULL, a, src), sq = __shfl_sync(HM_FULL, bq, src);
-      if (lane < 12 && sa == my_a) S = __dadd_rn(S, s_lut[my_k][sq]);
+      if (lane < 12 && sa == my_a) S = __dadd_rn(S, __ldg(my_lut + sq));
     }
   }
-  // gather the 12 sums on every lane
-  double SS[4][3];
-#pragma unroll
-  for (int x = 0; x < 4; x++)
-#pragma unroll
-    for (int k = 0; k < 3; k++) SS[x][k] = __shfl_sync(HM_FULL, S, x * 3 + k);
-  if (lane != 0) return;
-  if (bq_zero) *err_flag = HM_ERR_BQ_ZERO;
+  SiteAgg* A = agg + ki;
+  if (lane < 12) A->S[lane] = S;
+  if (lane == 12) { A->cnt[0] = cnt0; A->cnt[1] = cnt1; A->cnt[2] = cnt2; A->cnt[3] = cnt3; A->cnt[4] = cnt4; A->cnt[5] = cnt5; }
+  if (lane == 13) { A->bqs[0] = bq0; A->bqs[1] = bq1; A->bqs[2] = bq2; A->bqs[3] = bq3; }
+  if (lane == 14) { A->hi_bq_alt = hi_bq_alt; A->h0 = h0; A->h1 = h1; A->som_mask = som_mask; A->bq_zero = bq_zero ? 1 : 0; A->pad = 0; }
+}
 
-  double pl[10];
+// ============================================================================ k_site_verdict
+// One thread per distinct candidate: 10-genotype PL / GQ (gtlib.py:72-135), germline
+// restatement (caller.is_germ_gt), the filter cascade (caller.py:349-621) and the record.
+// Also tallies statuses (the host turns them into chrom2tsbs_log) and lists the records whose
+// position another chunk can also reach — the only ones the host's som_seen replay must see.
+__global__ void __launch_bounds__(256) k_site_verdict(DevParams p, DevSets sets, const hm_chunk* chunks, const int32_t* prev_max_end,
+                                                      const int32_t* next_min_start, const unsigned long long* keys,
+                                                      const unsigned long long* n_keys_dev, const SiteAgg* agg,
+                                                      hm_site_record* out, unsigned long long* status_hist,
+                                                      uint32_t* boundary_idx, uint32_t boundary_cap, unsigned long long* n_boundary,
+                                                      int* err_flag) {
+  __shared__ unsigned int s_hist[16];
+  if (threadIdx.x < 16) s_hist[threadIdx.x] = 0;
+  __syncthreads();
+  const uint64_t ki = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (ki < *n_keys_dev) {
+    const unsigned long long key = keys[ki];
+    const uint32_t c = (uint32_t)(key >> 36);
+    const int32_t tpos = (int32_t)((key >> 4) & 0xffffffffull);
+    const int ref = (int)((key >> 2) & 3), alt = (int)(key & 3);
+    const hm_chunk ch = chunks[c];
+    const SiteAgg A = agg[ki];
+    if (A.bq_zero) *err_flag = HM_ERR_BQ_ZERO;
+    double SS[4][3];
 #pragma unroll
-  for (int g = 0; g < 10; g++) pl[g] = gt_pl_dev(SS, g, ref, -1);
-  int gq; bool tie;
-  const int best = argmin_gt_dev(pl, &gq, &tie);
-  int g0 = c_gt_b1[best], g1 = c_gt_b2[best];
-  const int state = gt_state_dev(g0, g1, ref);
-  if (g0 != ref && ((g0 == ref) + (g1 == ref)) == 1) { int t = g0; g0 = g1; g1 = t; } // gtlib.py:133-134
-  const int ins_count = cnt[4], del_count = cnt[5];
-  const int depth = cnt[0] + cnt[1] + cnt[2] + cnt[3] + cnt[5];
-  const int ref_count = cnt[ref], alt_count = cnt[alt];
+    for (int x = 0; x < 4; x++)
+#pragma unroll
+      for (int k = 0; k < 3; k++) SS[x][k] = A.S[x * 3 + k];
+    double pl[10];
+#pragma unroll
+    for (int g = 0; g < 10; g++) pl[g] = gt_pl_dev(SS, g, ref, -1);
+    int gq; bool tie;
+    const int best = argmin_gt_dev(pl, &gq, &tie);
+    int g0 = c_gt_b1[best], g1 = c_gt_b2[best];
+    const int state = gt_state_dev(g0, g1, ref);
+    if (g0 != ref && ((g0 == ref) + (g1 == ref)) == 1) { int t = g0; g0 = g1; g1 = t; } // gtlib.py:133-134
+    const int* cnt = A.cnt;
+    const int ins_count = cnt[4], del_count = cnt[5];
+    const int depth = cnt[0] + cnt[1] + cnt[2] + cnt[3] + cnt[5];
+    const int ref_count = cnt[ref], alt_count = cnt[alt];
 
-  // caller.is_germ_gt (caller.py:111-147)
-  bool germ;
-  if (state == 1) germ = (g0 == ref && g1 == alt);
-  else if (state == 2) germ = (cnt[0] + cnt[1] + cnt[2] + cnt[3] == cnt[g0] + cnt[g1]) && (alt == g0 || alt == g1);
-  else if (state == 3) germ = (ref_count == 0 && g0 == alt && g1 == alt);
-  else germ = (alt == g0);
+    // caller.is_germ_gt (caller.py:111-147)
+    bool germ;
+    if (state == 1) germ = (g0 == ref && g1 == alt);
+    else if (state == 2) germ = (cnt[0] + cnt[1] + cnt[2] + cnt[3] == cnt[g0] + cnt[g1]) && (alt == g0 || alt == g1);
+    else if (state == 3) germ = (ref_count == 0 && g0 == alt && g1 == alt);
+    else germ = (alt == g0);
 
-  int status, phase_set = -1;
-  if (germ) status = state == 1 ? HM_ST_GERM_HET : state == 2 ? HM_ST_GERM_HETALT : state == 3 ? HM_ST_GERM_HOMALT : HM_ST_GERM_HOMREF;
-  else if (state == 1) status = HM_ST_HET_SITE;
-  else if (state == 2) status = HM_ST_HETALT_SITE;
-  else if (state == 3) status = HM_ST_HOMALT_SITE;
-  else if (del_count != 0 || ins_count != 0) status = HM_ST_INDEL_SITE;
-  else {
-    const uint64_t skey = ((uint64_t)(uint32_t)tpos << 4) | ((uint64_t)ref << 2) | (uint64_t)alt;
-    if (gq < p.min_gq) status = HM_ST_LOW_GQ;
-    else if (hi_bq_alt == 0) status = HM_ST_LOW_BQ;
-    else if (!p.non_human_sample && !p.create_panel_of_normals && key_in_dev(sets.pon, sets.n_pon, skey)) status = HM_ST_PON;
-    else if (!p.non_human_sample && key_in_dev(sets.common, sets.n_common, skey)) status = HM_ST_COMSNP;
-    else if (!(ref_count >= p.min_ref_count && alt_count >= p.min_alt_count)) status = HM_ST_LOW_DEPTH;
-    else if ((double)depth > p.md_threshold) status = HM_ST_HIGH_DEPTH;
+    int status, phase_set = -1;
+    if (germ) status = state == 1 ? HM_ST_GERM_HET : state == 2 ? HM_ST_GERM_HETALT : state == 3 ? HM_ST_GERM_HOMALT : HM_ST_GERM_HOMREF;
+    else if (state == 1) status = HM_ST_HET_SITE;
+    else if (state == 2) status = HM_ST_HETALT_SITE;
+    else if (state == 3) status = HM_ST_HOMALT_SITE;
+    else if (del_count != 0 || ins_count != 0) status = HM_ST_INDEL_SITE;
     else {
-      status = HM_ST_PASS;
-      if (p.phase) { // caller.py:552-603
-        if (h0 >= p.min_hap_count && h1 >= p.min_hap_count && (som_mask == 1 || som_mask == 2)) phase_set = ch.start;
-        else status = HM_ST_UNPHASED;
+      const uint64_t skey = ((uint64_t)(uint32_t)tpos << 4) | ((uint64_t)ref << 2) | (uint64_t)alt;
+      if (gq < p.min_gq) status = HM_ST_LOW_GQ;
+      else if (A.hi_bq_alt == 0) status = HM_ST_LOW_BQ;
+      else if (!p.non_human_sample && !p.create_panel_of_normals && key_in_dev(sets.pon, sets.n_pon, skey)) status = HM_ST_PON;
+      else if (!p.non_human_sample && key_in_dev(sets.common, sets.n_common, skey)) status = HM_ST_COMSNP;
+      else if (!(ref_count >= p.min_ref_count && alt_count >= p.min_alt_count)) status = HM_ST_LOW_DEPTH;
+      else if ((double)depth > p.md_threshold) status = HM_ST_HIGH_DEPTH;
+      else {
+        status = HM_ST_PASS;
+        if (p.phase) { // caller.py:552-603
+          if (A.h0 >= p.min_hap_count && A.h1 >= p.min_hap_count && (A.som_mask == 1 || A.som_mask == 2)) phase_set = ch.start;
+          else status = HM_ST_UNPHASED;
+        }
       }
     }
-  }
-  const unsigned long long slot = atomicAdd(n_out, 1ull);
-  if (slot < cap) {
     hm_site_record R;
     R.tpos = tpos; R.ref = (uint8_t)ref; R.alt = (uint8_t)alt; R.status = (uint8_t)status;
     R.flags = tie ? HM_SITE_PL_TIE : 0;
@@ -515,13 +613,20 @@ __global__ void __launch_bounds__(128) k_eval_sites(DevBatch b, DevParams p, Dev
 #pragma unroll
     for (int x = 0; x < 6; x++) R.counts[x] = cnt[x];
 #pragma unroll
-    for (int x = 0; x < 4; x++) R.bq_sum[x] = bqs[x];
+    for (int x = 0; x < 4; x++) R.bq_sum[x] = A.bqs[x];
     const bool ph_eval = p.phase && (status == HM_ST_PASS || status == HM_ST_UNPHASED);
-    R.hap_count[0] = ph_eval ? h0 : 0; R.hap_count[1] = ph_eval ? h1 : 0;
-    R.som_hap_mask = ph_eval ? som_mask : 0;
+    R.hap_count[0] = ph_eval ? A.h0 : 0; R.hap_count[1] = ph_eval ? A.h1 : 0;
+    R.som_hap_mask = ph_eval ? A.som_mask : 0;
     R.phase_set = phase_set;
-    out[slot] = R;
+    out[ki] = R;
+    atomicAdd(&s_hist[status], 1u);
+    if (tpos <= prev_max_end[c] || tpos >= next_min_start[c]) {
+      const unsigned long long at = atomicAdd(n_boundary, 1ull);
+      if (at < boundary_cap) boundary_idx[at] = (uint32_t)ki;
+    }
   }
+  __syncthreads();
+  if (threadIdx.x < 16 && s_hist[threadIdx.x]) atomicAdd(status_hist + threadIdx.x, (unsigned long long)s_hist[threadIdx.x]);
 }
 
 // number of set bytes in flags[0..n)

@@ -19,7 +19,7 @@ EXPORTS = [
     "hm_abi_version", "hm_create", "hm_destroy", "hm_last_error", "hm_set_params", "hm_set_site_sets",
     "hm_set_phase_sets", "hm_upload_batch", "hm_call_chunks", "hm_call_batch", "hm_normcounts_chunks",
     "hm_read_stats", "hm_last_timing", "hm_last_kernel_times", "hm_set_stream", "hm_host_register",
-    "hm_host_unregister", "hm_abi_sizeof",
+    "hm_host_unregister", "hm_abi_sizeof", "hm_last_records",
 ]
 
 
@@ -55,6 +55,7 @@ def load():
         lib.hm_read_stats.argtypes = [vp, vp, vp, vp, vp, vp, vp]
         lib.hm_last_timing.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_int)]
         lib.hm_last_kernel_times.argtypes = [vp, vp, vp, sz, C.POINTER(sz)]
+        lib.hm_last_records.argtypes = [vp, vp, sz, C.POINTER(sz)]
         lib.hm_set_stream.argtypes = [vp, vp]
         lib.hm_host_register.argtypes = [vp, vp, sz]
         lib.hm_host_unregister.argtypes = [vp, vp]
@@ -80,6 +81,9 @@ class Context:
 
     def close(self):
         if getattr(self, "h", None):
+            if getattr(self, "_out", None) is not None:
+                self.lib.hm_host_unregister(self.h, _p(self._out))
+                self._out = None
             self.lib.hm_destroy(self.h)
             self.h = None
 
@@ -132,27 +136,39 @@ class Context:
     def upload(self, batch):
         self._chk(self.lib.hm_upload_batch(self.h, C.byref(batch.as_struct())))
 
-    def _call(self, fn, head, chunks, cap):
+    def _out_buffer(self, cap):
+        """persistent page-locked record buffer (records are copied device -> here directly)"""
+        buf = getattr(self, "_out", None)
+        if buf is None or buf.shape[0] < cap:
+            if buf is not None:
+                self.lib.hm_host_unregister(self.h, _p(buf))
+            buf = np.empty(cap, dtype=abi.SITE_DTYPE)
+            self._chk(self.lib.hm_host_register(self.h, _p(buf), buf.nbytes))
+            self._out = buf
+        return self._out
+
+    def _call(self, fn, head, chunks, cap, view):
         chunks = np.ascontiguousarray(chunks, dtype=abi.CHUNK_DTYPE)
-        cap = int(cap or 65536)
-        while True:
-            out = np.zeros(cap, dtype=abi.SITE_DTYPE)
-            n = C.c_size_t(0)
-            log = np.zeros(abi.CALL_LOG_LEN, np.int64)
-            rc = fn(self.h, *head, _p(chunks), len(chunks), _p(out), cap, C.byref(n), _p(log))
-            if rc == abi.HM_ERR_CAPACITY:
-                cap = int(n.value)
-                continue
-            self._chk(rc)
-            return out[: n.value].copy(), log
+        out = self._out_buffer(int(cap or getattr(self, "_cap", 65536)))
+        n = C.c_size_t(0)
+        log = np.zeros(abi.CALL_LOG_LEN, np.int64)
+        rc = fn(self.h, *head, _p(chunks), len(chunks), _p(out), out.shape[0], C.byref(n), _p(log))
+        if rc == abi.HM_ERR_CAPACITY:  # results are kept by the library: fetch, do not recompute
+            self._cap = int(n.value) + int(n.value) // 4 + 1024
+            out = self._out_buffer(self._cap)
+            rc = self.lib.hm_last_records(self.h, _p(out), out.shape[0], C.byref(n))
+        self._chk(rc)
+        res = out[: n.value]
+        return (res if view else res.copy()), log
 
-    def call_chunks(self, chunks, cap=None):
-        """`himut call` over the resident batch -> (records, log[15])"""
-        return self._call(self.lib.hm_call_chunks, (), chunks, cap)
+    def call_chunks(self, chunks, cap=None, view=False):
+        """`himut call` over the resident batch -> (records, log[15]).
+        view=True returns a view of the context's pinned buffer, valid until the next call."""
+        return self._call(self.lib.hm_call_chunks, (), chunks, cap, view)
 
-    def call_batch(self, batch, chunks, cap=None):
+    def call_batch(self, batch, chunks, cap=None, view=False):
         """upload + call (host buffers in, records out): the end-to-end path"""
-        return self._call(self.lib.hm_call_batch, (C.byref(batch.as_struct()),), chunks, cap)
+        return self._call(self.lib.hm_call_batch, (C.byref(batch.as_struct()),), chunks, cap, view)
 
     def normcounts_chunks(self, refseq, chunks):
         """callable-base half of `himut normcounts` -> (ccs_tri[33], ref_tri[33], log[14], n_alt_tie)"""

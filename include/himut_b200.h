@@ -241,6 +241,10 @@ int hm_call_chunks(hm_ctx* ctx, const hm_chunk* chunks, size_t n_chunks,
                    hm_site_record* out, size_t cap, size_t* n_out,
                    int64_t log[HM_CALL_LOG_LEN]);
 
+/* after hm_call_chunks / hm_call_batch returned HM_ERR_CAPACITY: copy the records of that call
+ * into a buffer of at least *n_out entries, without recomputing anything */
+int hm_last_records(hm_ctx* ctx, hm_site_record* out, size_t cap, size_t* n_out);
+
 /* convenience: upload + call in one step (the end-to-end path bench.py times) */
 int hm_call_batch(hm_ctx* ctx, const hm_read_batch* batch, const hm_chunk* chunks,
                   size_t n_chunks, hm_site_record* out, size_t cap, size_t* n_out,
