@@ -112,15 +112,14 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def ncu_traffic():
-    """dram bytes per k_read_scan launch from the committed ncu capture, if one exists"""
+def ncu_traffic(alg_bytes):
+    """DRAM bytes per k_read_scan launch: dram/algorithmic ratio of the committed ncu capture
+    (profiles/traffic.json, taken on a 16 Mb contig) applied to this launch's algorithmic bytes"""
     p = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(p):
-        try:
-            return json.load(open(p)).get("k_read_scan_dram_bytes_per_launch")
-        except Exception:
-            return None
-    return None
+    try:
+        return float(json.load(open(p))["k_read_scan_dram_over_alg"]) * alg_bytes
+    except Exception:
+        return None
 
 
 def cpu_baseline(d, params, chunks, n_chunks, reps=1):
@@ -299,7 +298,7 @@ def main():
             "dominant_kernel": max(step_ms, key=step_ms.get),
             "library_launches_per_step": "cub::DeviceRadixSort (candidate keys)",
             "roofline": {"bound": "hbm", "kernel": "k_read_scan", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": ncu_traffic(), "peak_source": peak_src,
+                         "frac": achieved / peak, "traffic": ncu_traffic(alg), "peak_source": peak_src,
                          "alg_bytes_per_launch": alg, "kernel_ms": scan_ms,
                          "share_of_step_device_time": scan_ms / dev_ms if dev_ms else None},
             "roofline_step": {"formula": "SURVEY 8(d): 1.25*N_base + 4*N_op + 40*N_read + 48*N_cand", "bytes": survey_bytes,

@@ -1,0 +1,81 @@
+"""GPU worker of `himut call`: drop-in for himut.caller.get_somatic_substitutions.
+
+Same positional signature, same contract as the reference worker (src/himut/caller.py:208-642):
+it fills chrom2tsbs_lst[chrom] with the natsorted 12-tuples and chrom2tsbs_log[chrom] with the
+15 counters.  Install with himut_b200.patch.install().
+"""
+import numpy as np
+
+from . import abi, gtmodel, records, vcfio, worker
+
+_RESTATES = (abi.ST_GERM_HET, abi.ST_GERM_HETALT, abi.ST_GERM_HOMALT, abi.ST_GERM_HOMREF)
+
+
+def _log_from_records(rec, num_ccs):
+    """chrom2tsbs_log vector (caller.py:625-641) from record statuses"""
+    h = np.bincount(rec["status"], minlength=16).astype(np.int64)
+    log = np.zeros(abi.CALL_LOG_LEN, np.int64)
+    log[0] = num_ccs
+    log[1] = rec.size
+    log[2], log[3], log[4] = h[abi.ST_GERM_HET], h[abi.ST_GERM_HETALT], h[abi.ST_GERM_HOMALT]
+    log[5] = h[abi.ST_HET_SITE] + h[abi.ST_HETALT_SITE] + h[abi.ST_HOMALT_SITE]
+    log[7] = h[abi.ST_INDEL_SITE]
+    log[8], log[9], log[10], log[11] = h[abi.ST_LOW_GQ], h[abi.ST_LOW_BQ], h[abi.ST_PON], h[abi.ST_COMSNP]
+    log[12], log[13] = h[abi.ST_HIGH_DEPTH], h[abi.ST_LOW_DEPTH]
+    log[14] = h[abi.ST_PASS] + h[abi.ST_UNPHASED]
+    log[6] = log[8:15].sum()
+    return log
+
+
+def get_somatic_substitutions(
+    chrom, bam_file, common_snps, panel_of_normals, chunkloci_lst, phase_set2hbit_lst, phase_set2hpos_lst,
+    phase_set2hetsnp_lst, min_qv, min_mapq, qlen_lower_limit, qlen_upper_limit, min_sequence_identity, min_gq,
+    min_bq, min_trim, max_mismatch_count, mismatch_window_size, md_threshold, min_ref_count, min_alt_count,
+    min_hap_count, somatic_snv_prior, germline_snv_prior, germline_indel_prior, phase, non_human_sample,
+    create_panel_of_normals, chrom2tsbs_lst, chrom2tsbs_log,
+):
+    ctx = worker.context()
+    params = gtmodel.make_params(
+        min_qv=min_qv, min_mapq=min_mapq, qlen_lower_limit=qlen_lower_limit, qlen_upper_limit=qlen_upper_limit,
+        min_sequence_identity=min_sequence_identity, min_gq=min_gq, min_bq=min_bq, min_trim=min_trim,
+        max_mismatch_count=max_mismatch_count, mismatch_window=mismatch_window_size, md_threshold=md_threshold,
+        min_ref_count=min_ref_count, min_alt_count=min_alt_count, min_hap_count=min_hap_count,
+        germline_snv_prior=germline_snv_prior, phase=phase, non_human_sample=non_human_sample,
+        create_panel_of_normals=create_panel_of_normals)
+    ctx.set_params(params)
+    # the reference only loads the sets when neither flag is given (caller.py:248-289)
+    if non_human_sample or create_panel_of_normals:
+        ctx.set_site_sets()
+    else:
+        ctx.set_site_sets(vcfio.load_common_snps(chrom, common_snps), vcfio.load_pon(chrom, panel_of_normals))
+    chunk_sets = None
+    if phase:
+        table, chunk_sets = vcfio.phase_tables(chunkloci_lst, phase_set2hbit_lst, phase_set2hpos_lst, phase_set2hetsnp_lst)
+        ctx.set_phase_sets(table)
+
+    src = worker.RegionSource(bam_file)
+    tally = worker.QnameTally()
+    kept, som_seen = [], set()
+    starts = [s for _, s, _e in chunkloci_lst]
+    groups = worker.group_chunks(chunkloci_lst)
+    for gi, idx in enumerate(groups):
+        loci = [chunkloci_lst[i] for i in idx]
+        batch, table = src.batch(chrom, loci, None if chunk_sets is None else [chunk_sets[i] for i in idx])
+        if batch.n_reads == 0:
+            continue
+        ctx.upload(batch)
+        rec, _log = ctx.call_chunks(table)
+        tally.add(ctx.qname_seen())
+        # som_seen carries across groups exactly as across chunks (caller.py:243,347; bamlib.py:77)
+        if som_seen and rec.size:
+            rec = rec[~np.isin(rec["tpos"], np.fromiter(som_seen, np.int32, len(som_seen)))]
+        later = min(starts[idx[-1] + 1:], default=None)
+        if later is not None and rec.size:
+            claim = rec[(~np.isin(rec["status"], _RESTATES)) & (rec["tpos"] >= later)]
+            som_seen.update(int(t) for t in claim["tpos"])
+        kept.append(rec)
+    src.close()
+    rec = np.concatenate(kept) if kept else np.zeros(0, abi.SITE_DTYPE)
+    chrom2tsbs_lst[chrom] = records.records_to_tsbs_lst(chrom, rec)
+    chrom2tsbs_log[chrom] = [int(v) for v in _log_from_records(rec, tally.count())]
+    return int((rec["flags"] & abi.SITE_PL_TIE).astype(bool).sum())

@@ -594,6 +594,20 @@ int hm_normcounts_chunks(hm_ctx* ctx, const uint8_t* refseq, size_t ref_len, con
   return hm_normcounts_impl(ctx, refseq, ref_len, chunks, n_chunks, ccs_tri, ref_tri, log, n_alt_tie);
 }
 
+/* per-qname_id flags of the last call: 1 where some record with that id passed the read gates in
+ * a chunk that fetched it (the reads m.num_ccs counts, caller.py:318-320) */
+int hm_qname_seen(hm_ctx* ctx, uint8_t* out, size_t cap, size_t* n) {
+  if (!ctx || !n) return HM_ERR_ARG;
+  if (!ctx->have_batch) return fail(ctx, HM_ERR_STATE, "no resident batch");
+  *n = (size_t)ctx->max_qname_id + 1;
+  if (cap < *n || !out) return fail(ctx, HM_ERR_CAPACITY, "output holds %zu flags, %zu needed", cap, *n);
+  CU(cudaSetDevice(ctx->device));
+  if (ctx->b_qseen.cap < *n) return fail(ctx, HM_ERR_STATE, "no call has run on this batch yet");
+  CU(cudaMemcpyAsync(out, ctx->b_qseen.p, *n, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return HM_OK;
+}
+
 int hm_last_timing(hm_ctx* ctx, float* total_ms, int* n_launches) {
   if (!ctx) return HM_ERR_ARG;
   if (total_ms) *total_ms = ctx->last_total_ms;

@@ -19,7 +19,7 @@ EXPORTS = [
     "hm_abi_version", "hm_create", "hm_destroy", "hm_last_error", "hm_set_params", "hm_set_site_sets",
     "hm_set_phase_sets", "hm_upload_batch", "hm_call_chunks", "hm_call_batch", "hm_normcounts_chunks",
     "hm_read_stats", "hm_last_timing", "hm_last_kernel_times", "hm_set_stream", "hm_host_register",
-    "hm_host_unregister", "hm_abi_sizeof", "hm_last_records",
+    "hm_host_unregister", "hm_abi_sizeof", "hm_last_records", "hm_qname_seen",
 ]
 
 
@@ -56,6 +56,7 @@ def load():
         lib.hm_last_timing.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_int)]
         lib.hm_last_kernel_times.argtypes = [vp, vp, vp, sz, C.POINTER(sz)]
         lib.hm_last_records.argtypes = [vp, vp, sz, C.POINTER(sz)]
+        lib.hm_qname_seen.argtypes = [vp, vp, sz, C.POINTER(sz)]
         lib.hm_set_stream.argtypes = [vp, vp]
         lib.hm_host_register.argtypes = [vp, vp, sz]
         lib.hm_host_unregister.argtypes = [vp, vp]
@@ -189,6 +190,14 @@ class Context:
                    ins_len=np.zeros(n, np.int32), del_len=np.zeros(n, np.int32), n_mismatch=np.zeros(n, np.int32))
         self._chk(self.lib.hm_read_stats(self.h, *[_p(out[k]) for k in
                                                    ("bq_total", "n_match", "n_sub", "ins_len", "del_len", "n_mismatch")]))
+        return out
+
+    def qname_seen(self):
+        """flags per qname_id of the last call: which query names passed the read gates"""
+        n = C.c_size_t(0)
+        self.lib.hm_qname_seen(self.h, None, 0, C.byref(n))
+        out = np.zeros(n.value, np.uint8)
+        self._chk(self.lib.hm_qname_seen(self.h, _p(out), out.size, C.byref(n)))
         return out
 
     def last_timing(self):

@@ -1,0 +1,27 @@
+"""Re-points the reference's two starmap targets at the GPU workers.
+
+The reference resolves its workers as module globals at call time (src/himut/caller.py:805-806,
+src/himut/normcounts.py:536), so assigning the attributes before the driver runs is enough; the
+CLI, header, thresholds, natsort and writers stay the reference's own code.
+"""
+
+
+def install():
+    import himut.caller
+    import himut.normcounts
+
+    from . import caller, normcounts
+    himut.caller.get_somatic_substitutions = caller.get_somatic_substitutions
+    himut.normcounts.get_callable_tricounts = normcounts.get_callable_tricounts
+    return himut
+
+
+def main():
+    """console entry: `python -m himut_b200.patch call -i in.bam ...` = `himut call ...` on GPUs"""
+    install()
+    import himut.__main__
+    himut.__main__.main()
+
+
+if __name__ == "__main__":
+    main()

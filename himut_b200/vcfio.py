@@ -1,0 +1,105 @@
+"""Common-SNP / panel-of-normals / phased-hetSNP inputs -> the sorted key arrays and tables the
+library takes (hm_set_site_sets, hm_set_phase_sets).
+
+Mirrors the reference's loaders, quirks included (src/himut/vcflib.py:356-459):
+  * plain `.vcf` common SNPs keep records whose CHROM *differs* from the worker's contig
+    (`chrom != arr[0]`, vcflib.py:434) — reproduced so results stay identical;
+  * `.bgz` inputs are queried per chunk ± qlen_upper_limit by the reference, which for sites
+    inside the chunk equals contig-wide membership, so one contig-wide set is built;
+  * only FILTER == PASS records; common SNPs need a single one-letter ALT, the PoN needs a
+    bi-allelic SNP.
+"""
+import gzip
+
+import numpy as np
+
+from . import abi
+
+
+def _open_text(path):
+    with open(path, "rb") as f:
+        magic = f.read(2)
+    return gzip.open(path, "rt") if magic == b"\x1f\x8b" else open(path, "rt")
+
+
+def _key(pos, ref, alt):
+    r, a = abi.BASE2CODE.get(ref), abi.BASE2CODE.get(alt)
+    if r is None or a is None:
+        return None  # can never equal a candidate (ref, alt are A/T/G/C there)
+    return (int(pos) << 4) | (r << 2) | a
+
+
+def _finish(keys):
+    return np.unique(np.asarray(sorted(keys), dtype=np.uint64)) if keys else np.zeros(0, np.uint64)
+
+
+def load_common_snps(chrom, path):
+    """vcflib.load_common_snp (.vcf) / load_bgz_common_snp (.bgz) as sorted keys"""
+    if path is None:
+        return np.zeros(0, np.uint64)
+    plain = path.endswith(".vcf")
+    keys = []
+    with _open_text(path) as f:
+        for line in f:
+            if line.startswith("#"):
+                continue
+            arr = line.strip().split()
+            if len(arr) < 7:
+                continue
+            same = arr[0] == chrom
+            if plain and same:      # vcflib.py:434 keeps `chrom != arr[0]`
+                continue
+            if not plain and not same:
+                continue
+            alts = arr[4].split(",")
+            if arr[6] == "PASS" and len(alts) == 1 and len(arr[3]) == 1 and len(alts[0]) == 1:
+                k = _key(arr[1], arr[3], alts[0])
+                if k is not None:
+                    keys.append(k)
+    return _finish(keys)
+
+
+def load_pon(chrom, path):
+    """vcflib.load_pon (.vcf) / load_bgz_pon (.bgz) as sorted keys"""
+    if path is None:
+        return np.zeros(0, np.uint64)
+    keys = []
+    with _open_text(path) as f:
+        for line in f:
+            if line.startswith("#"):
+                continue
+            arr = line.strip().split()
+            if len(arr) < 7 or arr[0] != chrom:
+                continue
+            alts = arr[4].split(",")
+            if arr[6] == "PASS" and len(alts) == 1 and len(arr[3]) == 1 and len(alts[0]) == 1:
+                k = _key(arr[1], arr[3], alts[0])
+                if k is not None:
+                    keys.append(k)
+    return _finish(keys)
+
+
+def phase_tables(chunkloci_lst, phase_set2hbit_lst, phase_set2hpos_lst, phase_set2hetsnp_lst):
+    """the worker's three per-phase-set dicts (vcflib.load_phased_hetsnps, vcflib.py:617-663) ->
+    (phase table for hm_set_phase_sets, phase-set index per chunk).  The reference looks the
+    lists up with str(chunk_start) (caller.py:292)."""
+    hpos, href, halt, hbit, set_off, chunk_sets = [], [], [], [], [0], []
+    index = {}
+    for (_c, start, _e) in chunkloci_lst:
+        key = str(start)
+        if key not in index:
+            pos = phase_set2hpos_lst[key]
+            snp = phase_set2hetsnp_lst[key]
+            bits = phase_set2hbit_lst[key]
+            index[key] = len(set_off) - 1
+            for p, s, b in zip(pos, snp, bits):
+                hpos.append(int(p))
+                # multi-base (indel) alleles can never equal a read base: code 255
+                href.append(abi.BASE2CODE.get(s[1], 255) if len(s[1]) == 1 else 255)
+                halt.append(abi.BASE2CODE.get(s[2], 255) if len(s[2]) == 1 else 255)
+                hbit.append(int(b) if b in ("0", "1") else 2)
+            set_off.append(len(hpos))
+        chunk_sets.append(index[key])
+    table = dict(hpos=np.asarray(hpos, np.int32), href=np.asarray(href, np.uint8), halt=np.asarray(halt, np.uint8),
+                 hbit=np.asarray(hbit, np.uint8), set_off=np.asarray(set_off, np.uint64))
+    return table, chunk_sets

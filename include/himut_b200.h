@@ -260,6 +260,12 @@ int hm_normcounts_chunks(hm_ctx* ctx, const uint8_t* refseq, size_t ref_len,
                          int64_t ccs_tri[HM_TRI_BINS], int64_t ref_tri[HM_TRI_BINS],
                          int64_t log[HM_NORM_LOG_LEN], int64_t* n_alt_tie);
 
+/* after hm_call_chunks / hm_normcounts_chunks: one byte per qname_id (0 .. max id of the batch),
+ * 1 where a record with that id passed the read gates in a chunk that fetched it — the reads
+ * m.num_ccs counts (caller.py:318-320).  Lets a host that feeds a contig in several batches
+ * count distinct names across them.                                                          */
+int hm_qname_seen(hm_ctx* ctx, uint8_t* out, size_t cap, size_t* n);
+
 /* per-read statistics of the resident batch, for parity tests of the expansion kernel
  * (cslib.cs2subindel / bamlib.get_blast_sequence_identity / BAM.get_qv):
  * bq_total = sum of all base qualities, n_match / n_sub / ins_len / del_len as in

@@ -36,26 +36,8 @@ def _plain(v):
     return v
 
 
-def write_sites_vcf(path, chrom, keys):
-    with open(path, "w") as f:
-        f.write("##fileformat=VCFv4.2\n#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\tS\n")
-        for k in keys:
-            k = int(k)
-            f.write("%s\t%d\t.\t%s\t%s\t.\tPASS\t.\tGT\t0/1\n" % (chrom, k >> 4, "ATGC"[(k >> 2) & 3], "ATGC"[k & 3]))
-
-
-def phase_dicts(c):
-    ph = c["phase"]
-    hbit, hpos, hetsnp = {}, {}, {}
-    if ph is None:
-        return hbit, hpos, hetsnp
-    for s in range(ph["set_off"].size - 1):
-        a, b = int(ph["set_off"][s]), int(ph["set_off"][s + 1])
-        key = str(int(ph["hpos"][a]))
-        hpos[key] = [int(x) for x in ph["hpos"][a:b]]
-        hbit[key] = [str(int(x)) for x in ph["hbit"][a:b]]
-        hetsnp[key] = [(int(p), "ATGC"[r], "ATGC"[al]) for p, r, al in zip(ph["hpos"][a:b], ph["href"][a:b], ph["halt"][a:b])]
-    return hbit, hpos, hetsnp
+write_sites_vcf = cases.write_sites_vcf
+phase_dicts = cases.phase_dicts
 
 
 def run_case(name, himut, tmp):

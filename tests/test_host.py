@@ -1,0 +1,84 @@
+"""Host-side logic that needs no GPU: BAM round trip, fetch semantics, set loaders, natsort,
+chunk tables, chunk grouping."""
+import os
+
+import numpy as np
+
+import cases
+from himut_b200 import abi, bamio, natsort_compat, pack, synth, vcfio, worker
+
+
+def test_bam_round_trip_and_fetch(tmp_path):
+    d = synth.generate(120_000, seed=9)
+    path = str(tmp_path / "t.bam")
+    bamio.write_batch_bam(path, "chr1", 120_000, d.batch)
+    assert os.path.exists(path + ".bai")
+    rd = bamio.BamReader(path)
+    assert rd.references == ["chr1"] and rd.lengths == [120_000]
+    assert "SM:synth" in rd.header_text
+    back = bamio.read_batch(rd, "chr1", 0, 120_000)
+    assert cases.batch_digest(back) == cases.batch_digest(d.batch)
+    b = d.batch
+    for s, e in [(1, 60_000), (60_000, 119_998), (33_333, 33_334), (119_990, 120_000), (0, 1)]:
+        got = [r.query_name for r in rd.fetch("chr1", s, e)]
+        exp = ["read%d" % i for i in range(b.n_reads) if b.tstart[i] < e and b.tend[i] > s]
+        assert got == exp, (s, e)
+    rd.close()
+
+
+def test_chunk_table_is_the_fetch_range():
+    d = synth.generate(120_000, seed=10)
+    b = d.batch
+    t = b.chunk_table([(1, 50_000), (50_000, 119_998), (70_000, 70_001)])
+    for row in t:
+        idx = [i for i in range(b.n_reads) if b.tstart[i] < row["end"] and b.tend[i] > row["start"]]
+        assert idx and row["read_lo"] <= idx[0] and idx[-1] < row["read_hi"]
+        assert row["read_hi"] == np.searchsorted(b.tstart, row["end"], "left")
+
+
+def test_pack_rejects_what_the_reference_crashes_on():
+    bb = pack.BatchBuilder()
+    good = dict(tstart=5, tend=9, qstart=0, qend=4, qseq="ACGT", bq=b"\x20" * 4, mapq=60, is_secondary=False, qname="q")
+    bb.add(cs=":4", **good)
+    for bad_cs, kw in [(":5", {}), (":2*an:1", {}), (":4", {"qseq": "ACNT"}), (":4", {"bq": b"\x20" * 3})]:
+        try:
+            pack.BatchBuilder().add(cs=bad_cs, **dict(good, **kw))
+            assert False, (bad_cs, kw)
+        except pack.BatchFormatError:
+            pass
+    # N in a soft clip is fine; N as the *reference* base of a substitution is fine
+    pack.BatchBuilder().add(cs=":2*ng:1", tstart=5, tend=9, qstart=1, qend=5, qseq="NACGTN", bq=b"\x20" * 6, mapq=60,
+                            is_secondary=False, qname="q")
+
+
+def test_set_loaders_keep_the_reference_quirks(tmp_path):
+    p = str(tmp_path / "c.vcf")
+    with open(p, "w") as f:
+        f.write("##x\n#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\tS\n")
+        f.write("chr1\t100\t.\tA\tG\t.\tPASS\t.\tGT\t0/1\n")
+        f.write("chr2\t200\t.\tC\tT\t.\tPASS\t.\tGT\t0/1\n")
+        f.write("chr2\t300\t.\tC\tT,G\t.\tPASS\t.\tGT\t0/1\n")
+        f.write("chr2\t400\t.\tC\tT\t.\tLowQ\t.\tGT\t0/1\n")
+        f.write("chr2\t500\t.\tCA\tC\t.\tPASS\t.\tGT\t0/1\n")
+    # plain .vcf common SNPs: records whose CHROM differs are the ones kept (vcflib.py:434)
+    assert list(vcfio.load_common_snps("chr1", p)) == [(200 << 4) | (3 << 2) | 1]
+    assert list(vcfio.load_pon("chr1", p)) == [(100 << 4) | (0 << 2) | 2]
+    q = str(tmp_path / "c.vcf.bgz")
+    os.rename(p, q)
+    assert list(vcfio.load_common_snps("chr1", q)) == [(100 << 4) | (0 << 2) | 2]
+
+
+def test_natsort_compat():
+    ns = natsort_compat.natsorted
+    assert ns(["chr10", "chr2", "chr1", "chrX"]) == ["chr1", "chr2", "chr10", "chrX"]
+    rows = [("chr1", 20, "A", "T", "PASS", 5), ("chr1", 3, "C", "G", "LowBQ", 7), ("chr1", 20, "A", "G", "PASS", 1)]
+    assert ns(rows) == [rows[1], rows[2], rows[0]]
+    mixed = [("c", 5, "A", "C,G", "HetAltSite", 9, "30.1,25.0"), ("c", 5, "A", "C", "PASS", 9, 30.0)]
+    assert ns(mixed) == [mixed[1], mixed[0]]
+
+
+def test_group_chunks():
+    loci = [("c", 1, 200000), ("c", 200000, 400000), ("c", 400000, 600000), ("c", 600000, 799998)]
+    assert worker.group_chunks(loci, span=450_000) == [[0, 1], [2, 3]]
+    assert worker.group_chunks(loci, span=10) == [[0], [1], [2], [3]]
+    assert worker.group_chunks(loci, span=10**9) == [[0, 1, 2, 3]]
