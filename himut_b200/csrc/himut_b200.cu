@@ -10,6 +10,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <unordered_set>
@@ -441,20 +442,30 @@ int hm_call_chunks(hm_ctx* ctx, const hm_chunk* chunks, size_t n_chunks, hm_site
       if ((rc = upload(ctx, ctx->b_geom, geom.data(), 2 * n_chunks))) return rc;
       CU(cudaStreamSynchronize(ctx->stream));
       n_unique = (size_t)h_cnt[1];
-      CU(ctx->b_agg.ensure(n_unique * sizeof(SiteAgg)));
+      const uint64_t stride = (n_unique + 31) & ~31ull;
+      CU(ctx->b_agg.ensure(stride * HM_SITE_SLOTS * 4 + n_unique * 8));
+      uint32_t* entries = ctx->b_agg.as<uint32_t>();
+      uint32_t* site_lo = entries + stride * HM_SITE_SLOTS;
+      uint32_t* site_n = site_lo + n_unique;
       CU(ctx->b_records.ensure(n_unique * sizeof(hm_site_record)));
       CU(ctx->b_bidx.ensure(n_unique * 4));
-      t_begin(ctx, "k_site_gather");
-      k_site_gather<<<(unsigned)((n_unique * 32 + 255) / 256), 256, 0, ctx->stream>>>(
-          ctx->db, ctx->dp, ctx->dlut, ctx->b_chunks.as<hm_chunk>(), ctx->b_pair_off.as<uint64_t>(), ctx->b_pair_hap.as<uint8_t>(),
-          k_in, d_cnt + 1, ctx->b_agg.as<SiteAgg>());
+      t_begin(ctx, "k_site_range");
+      k_site_range<<<(unsigned)((n_unique + 255) / 256), 256, 0, ctx->stream>>>(ctx->db, ctx->b_chunks.as<hm_chunk>(), k_in, d_cnt + 1,
+                                                                              site_lo, site_n);
       t_end(ctx);
       CU(cudaGetLastError());
-      t_begin(ctx, "k_site_verdict");
-      k_site_verdict<<<(unsigned)((n_unique + 255) / 256), 256, 0, ctx->stream>>>(
-          ctx->dp, ctx->dsets, ctx->b_chunks.as<hm_chunk>(), ctx->b_geom.as<int32_t>(), ctx->b_geom.as<int32_t>() + n_chunks, k_in,
-          d_cnt + 1, ctx->b_agg.as<SiteAgg>(), ctx->b_records.as<hm_site_record>(), d_cnt + 8, ctx->b_bidx.as<uint32_t>(),
-          (uint32_t)n_unique, d_cnt + 4, reinterpret_cast<int*>(d_cnt + 3));
+      t_begin(ctx, "k_site_entries");
+      k_site_entries<<<(unsigned)((n_unique + 15) / 16), 1024, 0, ctx->stream>>>(
+          ctx->db, ctx->dp, ctx->b_chunks.as<hm_chunk>(), ctx->b_pair_off.as<uint64_t>(), ctx->b_pair_hap.as<uint8_t>(), k_in,
+          d_cnt + 1, site_lo, site_n, entries, stride);
+      t_end(ctx);
+      CU(cudaGetLastError());
+      t_begin(ctx, "k_site_reduce");
+      k_site_reduce<<<(unsigned)((n_unique + 127) / 128), 128, 0, ctx->stream>>>(
+          ctx->db, ctx->dp, ctx->dsets, ctx->dlut, ctx->b_chunks.as<hm_chunk>(), ctx->b_pair_off.as<uint64_t>(),
+          ctx->b_pair_hap.as<uint8_t>(), ctx->b_geom.as<int32_t>(), ctx->b_geom.as<int32_t>() + n_chunks, k_in, d_cnt + 1, site_lo,
+          site_n, entries, stride, ctx->b_records.as<hm_site_record>(), d_cnt + 8, ctx->b_bidx.as<uint32_t>(), (uint32_t)n_unique,
+          d_cnt + 4, reinterpret_cast<int*>(d_cnt + 3));
       t_end(ctx);
       CU(cudaGetLastError());
     }
@@ -641,12 +652,15 @@ static int hm_normcounts_impl(hm_ctx* ctx, const uint8_t* refseq, size_t ref_len
   int rc = upload_chunks(ctx, chunks, n_chunks, pair_off);
   if (rc) return rc;
   const uint64_t n_pairs = pair_off.back();
-  std::vector<uint64_t> tile_off(n_chunks + 1, 0);
+  // tile prefix sums for the 256-wide (v1) and 512-wide (TMA) kernels, back to back
+  std::vector<uint64_t> tile_off(2 * (n_chunks + 1), 0);
+  uint64_t* tile_off2 = tile_off.data() + n_chunks + 1;
   for (size_t i = 0; i < n_chunks; i++) {
     const int64_t span = (int64_t)chunks[i].end - (int64_t)chunks[i].start;
     tile_off[i + 1] = tile_off[i] + (span > 0 ? (uint64_t)((span + HM_TILE_W - 1) / HM_TILE_W) : 0);
+    tile_off2[i + 1] = tile_off2[i] + (span > 0 ? (uint64_t)((span + HM_TW - 1) / HM_TW) : 0);
   }
-  const uint64_t n_tiles = tile_off.back();
+  const uint64_t n_tiles = tile_off[n_chunks], n_tiles_tma = tile_off2[n_chunks];
   if (n_tiles >= (1ull << 31)) return fail(ctx, HM_ERR_ARG, "too many tiles in one call");
   if ((rc = upload(ctx, ctx->b_tile_off, tile_off.data(), tile_off.size()))) return rc;
   if ((rc = upload(ctx, ctx->b_ref, refseq, ref_len))) return rc;
@@ -669,13 +683,34 @@ static int hm_normcounts_impl(hm_ctx* ctx, const uint8_t* refseq, size_t ref_len
                                                  ctx->b_qseen.as<uint8_t>());
     t_end(ctx);
     CU(cudaGetLastError());
-    t_begin(ctx, "k_norm_tiles");
-    k_norm_tiles<<<(unsigned)n_tiles, HM_TILE_W, 0, ctx->stream>>>(ctx->db, ctx->dp, ctx->dsets, ctx->dlut, ctx->b_chunks.as<hm_chunk>(),
-                                                                   (uint32_t)n_chunks, ctx->b_pair_off.as<uint64_t>(),
-                                                                   ctx->b_pair_hap.as<uint8_t>(), ctx->b_tile_off.as<uint64_t>(),
-                                                                   ctx->b_ref.as<uint8_t>(), (uint64_t)ref_len,
-                                                                   ctx->b_norm_out.as<NormOut>());
-    t_end(ctx);
+    static const bool use_v1 = getenv("HIMUT_B200_NORM_V1") != nullptr;
+    if (use_v1) {
+      t_begin(ctx, "k_norm_tiles");
+      k_norm_tiles<<<(unsigned)n_tiles, HM_TILE_W, 0, ctx->stream>>>(ctx->db, ctx->dp, ctx->dsets, ctx->dlut, ctx->b_chunks.as<hm_chunk>(),
+                                                                     (uint32_t)n_chunks, ctx->b_pair_off.as<uint64_t>(),
+                                                                     ctx->b_pair_hap.as<uint8_t>(), ctx->b_tile_off.as<uint64_t>(),
+                                                                     ctx->b_ref.as<uint8_t>(), (uint64_t)ref_len,
+                                                                     ctx->b_norm_out.as<NormOut>());
+      t_end(ctx);
+    } else {
+      const size_t smem = sizeof(TileStage) * HM_NSTAGE;
+      static bool attr_set = false;
+      if (!attr_set) {
+        CU(cudaFuncSetAttribute(k_norm_tiles_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+      }
+      int n_sm = 148;
+      cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, ctx->device);
+      unsigned grid = (unsigned)std::min<uint64_t>(n_tiles_tma, (uint64_t)n_sm);
+      if (const char* g = getenv("HIMUT_B200_NORM_GRID")) grid = (unsigned)std::max(1, std::min<int>(atoi(g), (int)n_tiles_tma));
+      t_begin(ctx, "k_norm_tiles_tma");
+      k_norm_tiles_tma<<<grid, HM_TW + 32 * HM_NPROD, smem, ctx->stream>>>(ctx->db, ctx->dp, ctx->dsets, ctx->dlut, ctx->b_chunks.as<hm_chunk>(),
+                                                                (uint32_t)n_chunks, ctx->b_pair_off.as<uint64_t>(),
+                                                                ctx->b_pair_hap.as<uint8_t>(), ctx->b_tile_off.as<uint64_t>() + n_chunks + 1,
+                                                                (uint32_t)n_tiles_tma, ctx->b_ref.as<uint8_t>(), (uint64_t)ref_len,
+                                                                ctx->b_norm_out.as<NormOut>());
+      t_end(ctx);
+    }
     CU(cudaGetLastError());
     t_begin(ctx, "k_count_flags");
     k_count_flags<<<148, 256, 0, ctx->stream>>>(ctx->b_qseen.as<uint8_t>(), (uint64_t)ctx->max_qname_id + 1,

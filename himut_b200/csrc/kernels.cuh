@@ -9,11 +9,12 @@
 //                   then trim + mismatch-window filter of every substitution
 //                   (bamlib.get_tsbs_candidates, src/himut/bamlib.py:69-86,222-282;
 //                    haplib.get_ccs_hap, src/himut/haplib.py:46-83)
-//   k_site_gather   per distinct candidate: ordered pileup of the chunk's reads at the site
-//                   (caller.update_allelecounts, caller.py:44-72): 6 counts, BQ sums, the 12
-//                   ordered fp64 sums of the genotype model, haplotype tallies
-//   k_site_verdict  per distinct candidate: 10-genotype PL / GQ (gtlib.py:72-174), germline
-//                   restatement test and the filter cascade (caller.py:324-621) -> record
+//   k_site_range / k_site_entries / k_site_reduce
+//                   per distinct candidate: the pileup column of the chunk's reads at the site
+//                   (caller.update_allelecounts, caller.py:44-72) gathered with one thread per
+//                   (site, read), then per site in file order: counts, ordered fp64 sums,
+//                   10-genotype PL / GQ (gtlib.py:72-174), germline restatement test and the
+//                   filter cascade (caller.py:324-621) -> record
 //
 // All streaming, integer / byte work plus ordered fp64 adds; no tensor-core work exists on
 // this path.  fp64 sums use __dadd_rn / __dmul_rn so nothing is contracted into FMAs: the
@@ -409,6 +410,25 @@ __device__ __forceinline__ uint32_t count_le_kary(const uint32_t* a, uint32_t n,
     if (i < len) c += (__ldg(a + lo + i) <= x);
   return lo + c;
 }
+__device__ __forceinline__ uint32_t count_le_kary_i32(const int32_t* a, uint32_t n, int32_t x) {
+  uint32_t lo = 0, len = n;
+  while (len > 8) {
+    const uint32_t step = (len + 7) >> 3, end = lo + len;
+    uint32_t c = 0;
+#pragma unroll
+    for (uint32_t i = 1; i < 8; i++) {
+      const uint32_t idx = lo + step * i - 1;
+      if (idx < end) c += (__ldg(a + idx) <= x);
+    }
+    lo += c * step;
+    len = min(step, end - lo);
+  }
+  uint32_t c = 0;
+#pragma unroll
+  for (uint32_t i = 0; i < 8; i++)
+    if (i < len) c += (__ldg(a + lo + i) <= x);
+  return lo + c;
+}
 // warp-cooperative: number of elements of sorted a[0..n) that are < x (strict) or <= x
 template <bool kStrict>
 __device__ __forceinline__ uint32_t warp_count_below(const int32_t* a, uint32_t n, int32_t x, int lane) {
@@ -450,103 +470,83 @@ __device__ __forceinline__ int read_allele_fast(const DevBatch& b, uint32_t r, i
   return (b.seq[__ldg(b.seq_off + r) + (q >> 2)] >> (2 * (q & 3u))) & 3;
 }
 
-// what k_site_gather hands to k_site_verdict, one per distinct candidate key
-struct SiteAgg {
-  double S[12];      // ordered fp64 sums, [allele * 3 + kind]
-  int32_t cnt[6];    // rpos2allelecounts
-  int32_t bqs[4];    // sum of BQ per base allele
-  int32_t hi_bq_alt; // alt reads with BQ >= min_bq (caller.is_low_bq)
-  int32_t h0, h1, som_mask;
-  int32_t bq_zero;
-  int32_t pad;
-};
+// ============================================================================ site kernels
+// The pileup column of a candidate site is gathered in three steps so every thread has work and
+// the order-sensitive part stays sequential per site:
+//   k_site_range    1 thread / distinct candidate: the file-order index range [lo, lo + n) of the
+//                   chunk's reads that can touch the site (two 8-ary searches);
+//   k_site_entries  1 thread / (candidate, read slot < 64): allele, BQ, insertion count, haplotype
+//                   of that read at the site, packed into one u32, stored slot-major so both this
+//                   kernel's writes and the next kernel's reads are coalesced;
+//   k_site_reduce   1 thread / candidate: walks the slots in file order — 6 counts, BQ sums, the
+//                   12 ordered fp64 sums (caller.update_allelecounts appends in fetch order,
+//                   caller.py:44-72), haplotype tallies — then 10-genotype PL / GQ
+//                   (gtlib.py:72-135), germline restatement (caller.is_germ_gt), the cascade
+//                   (caller.py:349-621) and the record; status tallies and the boundary list for
+//                   the host's som_seen replay.
+#define HM_SITE_SLOTS 64
+#define HM_ENT_NONE 7u
 
-// ============================================================================ k_site_gather
-// One warp per distinct candidate key (sorted by chunk, position, ref, alt).  Lanes take one
-// read each (32 at a time, file order) and look the read's allele / BQ / insertion up at the
-// site; the per-allele ordered fp64 sums are owned by lanes 0..11 (allele = lane / 3,
-// kind = lane % 3) and fed in read order (caller.update_allelecounts appends in fetch order).
-__global__ void __launch_bounds__(256, 5) k_site_gather(DevBatch b, DevParams p, DevLut lut, const hm_chunk* chunks,
-                                                     const uint64_t* pair_off, const uint8_t* pair_hap,
-                                                     const unsigned long long* keys, const unsigned long long* n_keys_dev,
-                                                     SiteAgg* agg) {
-  const uint64_t ki = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
+// entry: bits 0-2 allele (0-3 base, 5 deleted, 7 none), 3-10 BQ, 11-18 insertions at the site,
+//        19-20 haplotype (0, 1, 2 ".", 3 not fetched), 21 read also covers the next position
+__device__ __forceinline__ uint32_t site_entry(const DevBatch& b, const DevParams& p, const hm_chunk& ch, uint32_t c,
+                                               const uint64_t* pair_off, const uint8_t* pair_hap, uint32_t r, int32_t rpos) {
+  uint32_t e = HM_ENT_NONE;
+  if (!(__ldg(b.flags + r) & HM_READ_SECONDARY)) {
+    const int32_t ts = __ldg(b.tstart + r), te = __ldg(b.tend + r);
+    if (ts < ch.end && te > ch.start && ts <= rpos && rpos <= te) {
+      int bq, ins;
+      const int a = read_allele_fast(b, r, rpos, ts, &bq, &ins);
+      const uint32_t hap = p.phase ? pair_hap[pair_off[c] + (r - ch.read_lo)] : 2u;
+      e = (a < 0 ? HM_ENT_NONE : (uint32_t)a) | ((uint32_t)bq << 3) | ((uint32_t)min(ins, 255) << 11) | ((hap & 3u) << 19) |
+          ((te > rpos + 1) ? (1u << 21) : 0u); // overlaps [tpos, tpos + 1) (caller.py:558)
+    }
+  }
+  return e;
+}
+
+__global__ void __launch_bounds__(256) k_site_range(DevBatch b, const hm_chunk* chunks, const unsigned long long* keys,
+                                                    const unsigned long long* n_keys_dev, uint32_t* site_lo, uint32_t* site_n) {
+  const uint64_t ki = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (ki >= *n_keys_dev) return;
   const unsigned long long key = keys[ki];
-  const uint32_t c = (uint32_t)(key >> 36);
-  const int32_t tpos = (int32_t)((key >> 4) & 0xffffffffull);
-  const int ref = (int)((key >> 2) & 3), alt = (int)(key & 3);
-  const int32_t rpos = tpos - 1;
-  const hm_chunk ch = chunks[c];
-
+  const hm_chunk ch = chunks[(uint32_t)(key >> 36)];
+  const int32_t rpos = (int32_t)((key >> 4) & 0xffffffffull) - 1;
   // reads that can touch rpos, inside the chunk's fetch range: running-max(tend) >= rpos
   // (a trailing insertion sits at tend) and tstart <= rpos
   const uint32_t n_in = ch.read_hi - ch.read_lo;
-  const uint32_t lo = ch.read_lo + warp_count_below<true>(b.pmax_tend + ch.read_lo, n_in, rpos, lane);
-  const uint32_t hi = ch.read_lo + warp_count_below<false>(b.tstart + ch.read_lo, n_in, rpos, lane);
-  const double* my_lut = lut.lut + (lane % 3) * 256;
-  const int my_a = lane / 3;
-
-  int cnt0 = 0, cnt1 = 0, cnt2 = 0, cnt3 = 0, cnt4 = 0, cnt5 = 0, bq0 = 0, bq1 = 0, bq2 = 0, bq3 = 0;
-  int hi_bq_alt = 0, h0 = 0, h1 = 0, som_mask = 0;
-  bool bq_zero = false;
-  double S = 0.0; // lanes 0..11
-  for (uint32_t base = lo; base < hi; base += 32) {
-    const uint32_t r = base + lane;
-    int a = -1, bq = 0, ins = 0, hap = 2;
-    bool next_cov = false;
-    if (r < hi && !(__ldg(b.flags + r) & HM_READ_SECONDARY)) {
-      const int32_t ts = __ldg(b.tstart + r), te = __ldg(b.tend + r);
-      if (ts < ch.end && te > ch.start && ts <= rpos && rpos <= te) {
-        a = read_allele_fast(b, r, rpos, ts, &bq, &ins);
-        next_cov = te > tpos; // overlaps [tpos, tpos+1) (caller.py:558)
-        if (p.phase) hap = pair_hap[pair_off[c] + (r - ch.read_lo)];
-      }
-    }
-    const uint32_t m0 = __ballot_sync(HM_FULL, a == 0), m1 = __ballot_sync(HM_FULL, a == 1);
-    const uint32_t m2 = __ballot_sync(HM_FULL, a == 2), m3 = __ballot_sync(HM_FULL, a == 3);
-    cnt0 += __popc(m0); cnt1 += __popc(m1); cnt2 += __popc(m2); cnt3 += __popc(m3);
-    bq0 += __reduce_add_sync(HM_FULL, a == 0 ? bq : 0); bq1 += __reduce_add_sync(HM_FULL, a == 1 ? bq : 0);
-    bq2 += __reduce_add_sync(HM_FULL, a == 2 ? bq : 0); bq3 += __reduce_add_sync(HM_FULL, a == 3 ? bq : 0);
-    cnt5 += __popc(__ballot_sync(HM_FULL, a == 5));
-    cnt4 += __reduce_add_sync(HM_FULL, ins);
-    hi_bq_alt += __popc(__ballot_sync(HM_FULL, a == alt && bq >= p.min_bq));
-    bq_zero |= __any_sync(HM_FULL, a >= 0 && a < 4 && bq == 0);
-    if (p.phase) {
-      h0 += __popc(__ballot_sync(HM_FULL, a == ref && next_cov && hap == 0));
-      h1 += __popc(__ballot_sync(HM_FULL, a == ref && next_cov && hap == 1));
-      if (__any_sync(HM_FULL, a == alt && next_cov && hap == 0)) som_mask |= 1;
-      if (__any_sync(HM_FULL, a == alt && next_cov && hap == 1)) som_mask |= 2;
-    }
-    // ordered sums: walk the base-carrying lanes in read order
-    uint32_t m = m0 | m1 | m2 | m3;
-    while (m) {
-      const int src = __ffs(m) - 1;
-      m &= m - 1;
-      const int sa = __shfl_sync(HM_FULL, a, src), sq = __shfl_sync(HM_FULL, bq, src);
-      if (lane < 12 && sa == my_a) S = __dadd_rn(S, __ldg(my_lut + sq));
-    }
-  }
-  SiteAgg* A = agg + ki;
-  if (lane < 12) A->S[lane] = S;
-  if (lane == 12) { A->cnt[0] = cnt0; A->cnt[1] = cnt1; A->cnt[2] = cnt2; A->cnt[3] = cnt3; A->cnt[4] = cnt4; A->cnt[5] = cnt5; }
-  if (lane == 13) { A->bqs[0] = bq0; A->bqs[1] = bq1; A->bqs[2] = bq2; A->bqs[3] = bq3; }
-  if (lane == 14) { A->hi_bq_alt = hi_bq_alt; A->h0 = h0; A->h1 = h1; A->som_mask = som_mask; A->bq_zero = bq_zero ? 1 : 0; A->pad = 0; }
+  const uint32_t lo = count_le_kary_i32(b.pmax_tend + ch.read_lo, n_in, rpos - 1);
+  const uint32_t hi = count_le_kary_i32(b.tstart + ch.read_lo, n_in, rpos);
+  site_lo[ki] = ch.read_lo + lo;
+  site_n[ki] = hi > lo ? hi - lo : 0u;
 }
 
-// ============================================================================ k_site_verdict
-// One thread per distinct candidate: 10-genotype PL / GQ (gtlib.py:72-135), germline
-// restatement (caller.is_germ_gt), the filter cascade (caller.py:349-621) and the record.
-// Also tallies statuses (the host turns them into chrom2tsbs_log) and lists the records whose
-// position another chunk can also reach — the only ones the host's som_seen replay must see.
-__global__ void __launch_bounds__(256) k_site_verdict(DevParams p, DevSets sets, const hm_chunk* chunks, const int32_t* prev_max_end,
-                                                      const int32_t* next_min_start, const unsigned long long* keys,
-                                                      const unsigned long long* n_keys_dev, const SiteAgg* agg,
-                                                      hm_site_record* out, unsigned long long* status_hist,
-                                                      uint32_t* boundary_idx, uint32_t boundary_cap, unsigned long long* n_boundary,
-                                                      int* err_flag) {
+// block = 16 sites x 64 slots; thread (site = tid & 15, slot = tid >> 4)
+__global__ void __launch_bounds__(1024) k_site_entries(DevBatch b, DevParams p, const hm_chunk* chunks, const uint64_t* pair_off,
+                                                       const uint8_t* pair_hap, const unsigned long long* keys,
+                                                       const unsigned long long* n_keys_dev, const uint32_t* site_lo,
+                                                       const uint32_t* site_n, uint32_t* entries, uint64_t stride) {
+  const uint64_t ki = (uint64_t)blockIdx.x * 16 + (threadIdx.x & 15);
+  const uint32_t slot = threadIdx.x >> 4;
+  if (ki >= *n_keys_dev) return;
+  if (slot >= __ldg(site_n + ki)) return;
+  const unsigned long long key = keys[ki];
+  const uint32_t c = (uint32_t)(key >> 36);
+  const int32_t rpos = (int32_t)((key >> 4) & 0xffffffffull) - 1;
+  const hm_chunk ch = chunks[c];
+  entries[(uint64_t)slot * stride + ki] = site_entry(b, p, ch, c, pair_off, pair_hap, __ldg(site_lo + ki) + slot, rpos);
+}
+
+__global__ void __launch_bounds__(128) k_site_reduce(DevBatch b, DevParams p, DevSets sets, DevLut lut, const hm_chunk* chunks,
+                                                     const uint64_t* pair_off, const uint8_t* pair_hap, const int32_t* prev_max_end,
+                                                     const int32_t* next_min_start, const unsigned long long* keys,
+                                                     const unsigned long long* n_keys_dev, const uint32_t* site_lo,
+                                                     const uint32_t* site_n, const uint32_t* entries, uint64_t stride,
+                                                     hm_site_record* out, unsigned long long* status_hist, uint32_t* boundary_idx,
+                                                     uint32_t boundary_cap, unsigned long long* n_boundary, int* err_flag) {
   __shared__ unsigned int s_hist[16];
+  __shared__ double s_lut[3][256];
+  for (int i = threadIdx.x; i < 768; i += blockDim.x) s_lut[i >> 8][i & 255] = __ldg(lut.lut + i);
   if (threadIdx.x < 16) s_hist[threadIdx.x] = 0;
   __syncthreads();
   const uint64_t ki = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -556,13 +556,41 @@ __global__ void __launch_bounds__(256) k_site_verdict(DevParams p, DevSets sets,
     const int32_t tpos = (int32_t)((key >> 4) & 0xffffffffull);
     const int ref = (int)((key >> 2) & 3), alt = (int)(key & 3);
     const hm_chunk ch = chunks[c];
-    const SiteAgg A = agg[ki];
-    if (A.bq_zero) *err_flag = HM_ERR_BQ_ZERO;
+    const uint32_t n = site_n[ki], lo = site_lo[ki];
+
+    int cnt[6] = {0, 0, 0, 0, 0, 0}, bqs[4] = {0, 0, 0, 0};
+    int hi_bq_alt = 0, h0 = 0, h1 = 0, som_mask = 0;
+    bool bq_zero = false;
     double SS[4][3];
 #pragma unroll
-    for (int x = 0; x < 4; x++)
+    for (int x = 0; x < 4; x++) { SS[x][0] = 0.0; SS[x][1] = 0.0; SS[x][2] = 0.0; }
+    for (uint32_t s = 0; s < n; s++) {
+      const uint32_t e = s < HM_SITE_SLOTS ? __ldg(entries + (uint64_t)s * stride + ki)
+                                           : site_entry(b, p, ch, c, pair_off, pair_hap, lo + s, tpos - 1); // very deep pileups
+      const uint32_t a = e & 7u;
+      cnt[4] += (int)((e >> 11) & 255u);
+      if (a == HM_ENT_NONE) continue;
+      if (a == 5u) { cnt[5]++; continue; }
+      const int bq = (int)((e >> 3) & 255u);
+      const uint32_t hap = (e >> 19) & 3u;
+      const bool next_cov = (e >> 21) & 1u;
+      if (bq == 0) bq_zero = true;
+      const double x0 = s_lut[0][bq], x1 = s_lut[1][bq], x2 = s_lut[2][bq];
 #pragma unroll
-      for (int k = 0; k < 3; k++) SS[x][k] = A.S[x * 3 + k];
+      for (int x = 0; x < 4; x++) {
+        if ((int)a == x) {
+          cnt[x]++; bqs[x] += bq;
+          SS[x][0] = __dadd_rn(SS[x][0], x0); SS[x][1] = __dadd_rn(SS[x][1], x1); SS[x][2] = __dadd_rn(SS[x][2], x2);
+        }
+      }
+      if ((int)a == alt && bq >= p.min_bq) hi_bq_alt++;
+      if (p.phase && next_cov) {
+        if ((int)a == ref) { h0 += (hap == 0u); h1 += (hap == 1u); }
+        else if ((int)a == alt) { if (hap == 0u) som_mask |= 1; else if (hap == 1u) som_mask |= 2; }
+      }
+    }
+    if (bq_zero) *err_flag = HM_ERR_BQ_ZERO;
+
     double pl[10];
 #pragma unroll
     for (int g = 0; g < 10; g++) pl[g] = gt_pl_dev(SS, g, ref, -1);
@@ -571,7 +599,6 @@ __global__ void __launch_bounds__(256) k_site_verdict(DevParams p, DevSets sets,
     int g0 = c_gt_b1[best], g1 = c_gt_b2[best];
     const int state = gt_state_dev(g0, g1, ref);
     if (g0 != ref && ((g0 == ref) + (g1 == ref)) == 1) { int t = g0; g0 = g1; g1 = t; } // gtlib.py:133-134
-    const int* cnt = A.cnt;
     const int ins_count = cnt[4], del_count = cnt[5];
     const int depth = cnt[0] + cnt[1] + cnt[2] + cnt[3] + cnt[5];
     const int ref_count = cnt[ref], alt_count = cnt[alt];
@@ -592,7 +619,7 @@ __global__ void __launch_bounds__(256) k_site_verdict(DevParams p, DevSets sets,
     else {
       const uint64_t skey = ((uint64_t)(uint32_t)tpos << 4) | ((uint64_t)ref << 2) | (uint64_t)alt;
       if (gq < p.min_gq) status = HM_ST_LOW_GQ;
-      else if (A.hi_bq_alt == 0) status = HM_ST_LOW_BQ;
+      else if (hi_bq_alt == 0) status = HM_ST_LOW_BQ;
       else if (!p.non_human_sample && !p.create_panel_of_normals && key_in_dev(sets.pon, sets.n_pon, skey)) status = HM_ST_PON;
       else if (!p.non_human_sample && key_in_dev(sets.common, sets.n_common, skey)) status = HM_ST_COMSNP;
       else if (!(ref_count >= p.min_ref_count && alt_count >= p.min_alt_count)) status = HM_ST_LOW_DEPTH;
@@ -600,7 +627,7 @@ __global__ void __launch_bounds__(256) k_site_verdict(DevParams p, DevSets sets,
       else {
         status = HM_ST_PASS;
         if (p.phase) { // caller.py:552-603
-          if (A.h0 >= p.min_hap_count && A.h1 >= p.min_hap_count && (A.som_mask == 1 || A.som_mask == 2)) phase_set = ch.start;
+          if (h0 >= p.min_hap_count && h1 >= p.min_hap_count && (som_mask == 1 || som_mask == 2)) phase_set = ch.start;
           else status = HM_ST_UNPHASED;
         }
       }
@@ -613,10 +640,10 @@ __global__ void __launch_bounds__(256) k_site_verdict(DevParams p, DevSets sets,
 #pragma unroll
     for (int x = 0; x < 6; x++) R.counts[x] = cnt[x];
 #pragma unroll
-    for (int x = 0; x < 4; x++) R.bq_sum[x] = A.bqs[x];
+    for (int x = 0; x < 4; x++) R.bq_sum[x] = bqs[x];
     const bool ph_eval = p.phase && (status == HM_ST_PASS || status == HM_ST_UNPHASED);
-    R.hap_count[0] = ph_eval ? A.h0 : 0; R.hap_count[1] = ph_eval ? A.h1 : 0;
-    R.som_hap_mask = ph_eval ? A.som_mask : 0;
+    R.hap_count[0] = ph_eval ? h0 : 0; R.hap_count[1] = ph_eval ? h1 : 0;
+    R.som_hap_mask = ph_eval ? som_mask : 0;
     R.phase_set = phase_set;
     out[ki] = R;
     atomicAdd(&s_hist[status], 1u);

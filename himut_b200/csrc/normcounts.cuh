@@ -272,6 +272,417 @@ __global__ void __launch_bounds__(HM_TILE_W) k_norm_tiles(DevBatch b, DevParams 
   if (threadIdx.x == 0 && s_tie) atomicAdd(&out->alt_tie, s_tie);
 }
 
+// ============================================================================ k_norm_tiles_tma
+// Warp-specialised, persistent version of k_norm_tiles.
+//   producer warp: for the tile's reads, 32 at a time (one lane per read), finds the slice of the
+//     op stream and of the mismatch list that touches the tile (8-ary searches), writes a compact
+//     descriptor into shared memory and stages the read's quality bytes and 2-bit bases for the
+//     tile with cp.async.bulk (TMA 1-D bulk copy, 16-byte granules) completing on an mbarrier;
+//   16 consumer warps: one reference position per thread; they wait on the stage's "full"
+//     mbarrier, walk its reads in file order out of shared memory and release the stage through
+//     the "empty" mbarrier.  Per-position state lives in registers: 6 counts, the ordered fp64
+//     sums of the position's first-seen allele (other alleles go to a rarely taken path), the
+//     callable count and the haplotype tallies.
+// A stage is one batch of <= 32 reads of one tile; the producer runs ahead across tiles.
+#define HM_TW 512            // positions per tile = consumer threads
+#define HM_NPROD 2           // producer warps, alternating batches
+#define HM_NSTAGE 4
+#define HM_SLOTS 32          // reads per stage
+#define HM_BQ_BUF 640        // staged quality bytes per read: tile + insertions + alignment slack
+#define HM_SEQ_BUF 176       // staged 2-bit bytes per read
+#define HM_MAX_SOPS 12       // ops of one read inside one tile kept in the descriptor
+#define HM_MAX_SMM 8         // mismatch-list entries near the tile kept in the descriptor
+
+struct __align__(16) TileSlot {
+  uint8_t bq[HM_BQ_BUF];
+  uint8_t seq[HM_SEQ_BUF];
+  uint32_t op_w[HM_MAX_SOPS];   // op word
+  uint32_t op_t[HM_MAX_SOPS];   // reference offset from tstart
+  uint32_t op_q[HM_MAX_SOPS];   // query position
+  int32_t mm[HM_MAX_SMM];
+  int32_t ts, te, qlen, trim_s, trim_e;
+  uint32_t q_base;              // query position of bq[0] (multiple of 64)
+  uint32_t n_ops, n_mm, flags;  // flags: HM_PF_* | HM_SLOT_SLOW
+  uint32_t read;                // read index (slow path)
+  uint32_t pad[2];
+};
+#define HM_SLOT_SLOW 0x100u
+
+struct __align__(16) TileStage {
+  TileSlot slot[HM_SLOTS];
+  int32_t n_slots;
+  int32_t last;                 // last batch of its tile
+  int32_t pad[2];
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok = 0;
+  while (!ok) {
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  }
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+// producer lane: descriptor + bulk copies of read r for tile [t0, t1)
+__device__ __forceinline__ void fill_slot(const DevBatch& b, const DevParams& p, TileSlot* S, uint64_t* full_bar, uint32_t r,
+                                          uint32_t pf, int32_t t0, int32_t t1) {
+  const int32_t ts = __ldg(b.tstart + r), te = __ldg(b.tend + r);
+  uint32_t flags = 0, nb_bq = 0, nb_seq = 0;
+  const uint8_t *src_bq = nullptr, *src_seq = nullptr;
+  if ((pf & HM_PF_FETCHED) && ts < t1 && te >= t0) {
+    const uint32_t n = __ldg(b.n_ops + r);
+    const uint64_t o0 = __ldg(b.op_off + r);
+    const int32_t qlen = __ldg(b.qlen + r);
+    if (n > 0) {
+      flags = pf & 0xffu;
+      const uint32_t reflen = (uint32_t)(te - ts);
+      const uint32_t woff = (uint32_t)max(t0 - ts, 0);
+      const uint32_t eoff = min((uint32_t)(t1 - 1 - ts), reflen); // last offset the tile can ask for
+      uint32_t k0 = count_le_kary(b.op_t + o0, n, woff) - 1;
+      while (k0 > 0 && __ldg(b.op_t + o0 + k0 - 1) == woff) k0--;
+      const uint32_t k1 = count_le_kary(b.op_t + o0, n, eoff);
+      const uint32_t ns = k1 - k0;
+      // mismatch-list slice near the tile (window reach <= 2w, list is 1-based)
+      const int32_t* mm = b.mm_pos + o0;
+      const uint32_t nmm = (uint32_t)__ldg(b.n_mm + r);
+      const int w = p.mismatch_window;
+      const uint32_t m_lo = count_le_kary_i32(mm, nmm, t0 - 2 * w - 2);
+      const uint32_t m_hi = count_le_kary_i32(mm, nmm, t1 + 2 * w + 2);
+      bool slow = ns > HM_MAX_SOPS || (m_hi - m_lo) > HM_MAX_SMM;
+      uint32_t q_lo = 0, q_hi = 0;
+      if (!slow) {
+        for (uint32_t i = 0; i < ns; i++) {
+          const uint32_t wd = __ldg(b.ops + o0 + k0 + i), ot = __ldg(b.op_t + o0 + k0 + i), oq = __ldg(b.op_q + o0 + k0 + i);
+          S->op_w[i] = wd; S->op_t[i] = ot; S->op_q[i] = oq;
+          const uint32_t kind = wd & 3u, v = wd >> 2;
+          if (i == 0) q_lo = oq + ((kind == HM_OP_MATCH && woff > ot) ? woff - ot : 0u);
+          if (i == ns - 1) {
+            if (kind == HM_OP_MATCH) q_hi = oq + min(v, eoff + 1 - ot);
+            else q_hi = oq + (uint32_t)op_qry_len(wd);
+          }
+        }
+        for (uint32_t i = 0; i < m_hi - m_lo; i++) S->mm[i] = __ldg(mm + m_lo + i);
+        const uint32_t qb = q_lo & ~63u;
+        const uint32_t qe = min((q_hi + 15u) & ~15u, ((uint32_t)qlen + 15u) & ~15u);
+        const uint32_t sb0 = qb >> 2, sb1 = min(((((q_hi + 3u) >> 2) + 15u) & ~15u), (((((uint32_t)qlen + 3u) >> 2) + 15u) & ~15u));
+        S->q_base = qb;
+        if (q_hi > q_lo) {
+          if (qe - qb > HM_BQ_BUF || sb1 - sb0 > HM_SEQ_BUF) slow = true;
+          else { nb_bq = qe - qb; nb_seq = sb1 - sb0; src_bq = b.bq + __ldg(b.bq_off + r) + qb; src_seq = b.seq + __ldg(b.seq_off + r) + sb0; }
+        }
+      }
+      if (slow) { flags |= HM_SLOT_SLOW; nb_bq = nb_seq = 0; }
+      S->n_ops = slow ? 0 : ns;
+      S->n_mm = slow ? 0 : (m_hi - m_lo);
+      S->ts = ts; S->te = te; S->qlen = qlen; S->read = r;
+      S->trim_s = (int32_t)floor(__dmul_rn(p.min_trim, (double)qlen));
+      S->trim_e = (int32_t)ceil(__dmul_rn(__dsub_rn(1.0, p.min_trim), (double)qlen));
+    }
+  }
+  S->flags = flags;
+  // the descriptor is complete: arrive (release) last, then let the bulk copies land on the barrier
+  if (nb_bq + nb_seq == 0) mbar_arrive(full_bar);
+  else {
+    mbar_arrive_expect_tx(full_bar, nb_bq + nb_seq);
+    bulk_g2s(S->bq, src_bq, nb_bq, full_bar);
+    bulk_g2s(S->seq, src_seq, nb_seq, full_bar);
+  }
+}
+
+__global__ void __launch_bounds__(HM_TW + 32 * HM_NPROD, 1) k_norm_tiles_tma(DevBatch b, DevParams p, DevSets sets, DevLut lut, const hm_chunk* chunks,
+                                                                   uint32_t n_chunks, const uint64_t* pair_off, const uint8_t* pair_flag,
+                                                                   const uint64_t* tile_off, uint32_t n_tiles, const uint8_t* refseq,
+                                                                   uint64_t ref_len, NormOut* out) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  TileStage* stages = reinterpret_cast<TileStage*>(smem_raw);
+  __shared__ double s_lut[3][256];
+  __shared__ uint64_t full_bar[HM_NSTAGE], empty_bar[HM_NSTAGE];
+  __shared__ unsigned long long s_ccs[HM_TRI_BINS], s_ref[HM_TRI_BINS], s_log[HM_NORM_LOG_LEN], s_tie;
+  __shared__ int s_err;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const bool is_producer = tid >= HM_TW;
+  for (int i = tid; i < 768; i += blockDim.x) s_lut[i >> 8][i & 255] = __ldg(lut.lut + i);
+  if (tid < HM_TRI_BINS) { s_ccs[tid] = 0; s_ref[tid] = 0; }
+  if (tid < HM_NORM_LOG_LEN) s_log[tid] = 0;
+  if (tid == 0) {
+    s_tie = 0; s_err = 0;
+    for (int i = 0; i < HM_NSTAGE; i++) { mbar_init(&full_bar[i], HM_SLOTS); mbar_init(&empty_bar[i], HM_TW / 32); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  uint32_t batch_no = 0; // same sequence on both sides
+  if (is_producer) {
+    // ------------------------------------------------------------------ producer warps
+    const uint32_t pw = (uint32_t)(tid - HM_TW) >> 5;
+    for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      const uint32_t c = upper_bound_dev(tile_off, n_chunks + 1, (uint64_t)tile) - 1;
+      const hm_chunk ch = chunks[c];
+      const int32_t t0 = ch.start + (int32_t)(tile - tile_off[c]) * HM_TW;
+      const int32_t t1 = min(t0 + HM_TW, ch.end);
+      const uint32_t n_in = ch.read_hi - ch.read_lo;
+      const uint32_t r_lo = ch.read_lo + warp_count_below<true>(b.pmax_tend + ch.read_lo, n_in, t0, lane);
+      const uint32_t r_hi = ch.read_lo + warp_count_below<true>(b.tstart + ch.read_lo, n_in, t1, lane);
+      const uint64_t pbase = pair_off[c];
+      uint32_t r0 = r_lo;
+      do {
+        if (batch_no % HM_NPROD != pw) { batch_no++; r0 += HM_SLOTS; continue; }
+        const uint32_t st = batch_no % HM_NSTAGE, ph = (batch_no / HM_NSTAGE) & 1;
+        mbar_wait(&empty_bar[st], ph ^ 1);
+        TileStage* T = &stages[st];
+        const uint32_t r = r0 + lane;
+        const uint32_t nb = min(r_hi > r0 ? r_hi - r0 : 0u, (uint32_t)HM_SLOTS);
+        if (lane == 0) { T->n_slots = (int32_t)nb; T->last = (r0 + HM_SLOTS >= r_hi) ? 1 : 0; }
+        if ((uint32_t)lane < nb) {
+          const uint32_t pf = pair_flag[pbase + (r - ch.read_lo)];
+          fill_slot(b, p, &T->slot[lane], &full_bar[st], r, pf, t0, t1);
+        } else {
+          mbar_arrive(&full_bar[st]);
+        }
+        batch_no++;
+        r0 += HM_SLOTS;
+      } while (r0 < r_hi);
+    }
+    return;
+  }
+
+  // -------------------------------------------------------------------- consumer warps
+  const int w = p.mismatch_window;
+  for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const uint32_t c = upper_bound_dev(tile_off, n_chunks + 1, (uint64_t)tile) - 1;
+    const hm_chunk ch = chunks[c];
+    const int32_t t0 = ch.start + (int32_t)(tile - tile_off[c]) * HM_TW;
+    const int32_t t1 = min(t0 + HM_TW, ch.end);
+    const int32_t pos = t0 + tid;
+    const bool live = pos < t1 && pos >= 0 && (uint64_t)pos < ref_len;
+
+    int cnt0 = 0, cnt1 = 0, cnt2 = 0, cnt3 = 0, cnt_ins = 0, cnt_del = 0;
+    int a_main = -1;
+    double M0 = 0.0, M1 = 0.0, M2 = 0.0;             // ordered sums of the first-seen allele
+    double O[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}}; // alleles (a_main + 1..3) & 3
+    int callable = 0, h0 = 0, h1 = 0;
+    bool bq_zero = false;
+
+    for (;;) {
+      const uint32_t st = batch_no % HM_NSTAGE, ph = (batch_no / HM_NSTAGE) & 1;
+      mbar_wait(&full_bar[st], ph);
+      const TileStage* T = &stages[st];
+      const int nslots = T->n_slots;
+      const int last = T->last;
+      for (int si = 0; si < nslots; si++) {
+        const TileSlot* S = &T->slot[si];
+        const uint32_t fl = S->flags;
+        if (!(fl & HM_PF_FETCHED) || !live) continue;
+        const int32_t ts = S->ts, te = S->te;
+        if (pos < ts || pos > te) continue;
+        const uint32_t off = (uint32_t)(pos - ts);
+        int a = -1, bq = 0, ins = 0;
+        uint32_t q = 0, kind = 0, t_op = 0, q0 = 0;
+        if (fl & HM_SLOT_SLOW) {
+          // pathological read (many ops / long insertions inside one tile): global-memory lookup
+          const uint32_t r = S->read;
+          const uint32_t n = __ldg(b.n_ops + r);
+          const uint64_t o0 = __ldg(b.op_off + r);
+          const int k = (int)count_le_kary(b.op_t + o0, n, off) - 1;
+          for (int j = k; j >= 0 && __ldg(b.op_t + o0 + j) == off; j--)
+            if ((__ldg(b.ops + o0 + j) & 3u) == HM_OP_INS) ins++;
+          const uint32_t wd = __ldg(b.ops + o0 + k);
+          kind = wd & 3u; t_op = __ldg(b.op_t + o0 + k); q0 = __ldg(b.op_q + o0 + k);
+          const uint32_t rl = (uint32_t)op_ref_len(wd);
+          if (rl != 0 && off < t_op + rl) {
+            if (kind == HM_OP_DEL) a = 5;
+            else {
+              q = q0 + (kind == HM_OP_MATCH ? off - t_op : 0u);
+              bq = b.bq[__ldg(b.bq_off + r) + q];
+              a = kind == HM_OP_SUB ? (int)((wd >> 5) & 3u) : (int)((b.seq[__ldg(b.seq_off + r) + (q >> 2)] >> (2 * (q & 3u))) & 3u);
+            }
+          }
+        } else {
+          const uint32_t n = S->n_ops;
+          uint32_t k = 0, wd = S->op_w[0];
+          t_op = S->op_t[0];
+          for (;;) {
+            if (t_op == off && (wd & 3u) == HM_OP_INS) ins++;
+            if (k + 1 >= n) break;
+            const uint32_t tn = S->op_t[k + 1];
+            if (tn > off) break;
+            k++; wd = S->op_w[k]; t_op = tn;
+          }
+          kind = wd & 3u; q0 = S->op_q[k];
+          const uint32_t rl = (uint32_t)op_ref_len(wd);
+          if (rl != 0 && off >= t_op && off < t_op + rl) {
+            if (kind == HM_OP_DEL) a = 5;
+            else {
+              q = q0 + (kind == HM_OP_MATCH ? off - t_op : 0u);
+              const uint32_t qb = S->q_base;
+              bq = S->bq[q - qb];
+              a = kind == HM_OP_SUB ? (int)((wd >> 5) & 3u) : (int)((S->seq[(q >> 2) - (qb >> 2)] >> (2 * (q & 3u))) & 3u);
+            }
+          }
+        }
+        cnt_ins += ins;
+        if (a < 0) continue;
+        if (a == 5) { cnt_del++; continue; }
+        if (bq == 0) bq_zero = true;
+        cnt0 += (a == 0); cnt1 += (a == 1); cnt2 += (a == 2); cnt3 += (a == 3);
+        const double x0 = s_lut[0][bq], x1 = s_lut[1][bq], x2 = s_lut[2][bq];
+        if (a_main < 0) a_main = a;
+        if (a == a_main) { M0 = __dadd_rn(M0, x0); M1 = __dadd_rn(M1, x1); M2 = __dadd_rn(M2, x2); }
+        else {
+          const int j = ((a - a_main) & 3) - 1;
+#pragma unroll
+          for (int jj = 0; jj < 3; jj++)
+            if (j == jj) { O[jj][0] = __dadd_rn(O[jj][0], x0); O[jj][1] = __dadd_rn(O[jj][1], x1); O[jj][2] = __dadd_rn(O[jj][2], x2); }
+        }
+        const int hap = (int)(fl >> HM_PF_HAP_SHIFT) & 3;
+        h0 += (hap == 0); h1 += (hap == 1);
+        if (!(fl & HM_PF_PASS)) continue;
+        // update_tri2count (normcounts.py:65-110)
+        if (kind == HM_OP_SUB) { callable++; continue; }
+        if (bq < p.min_bq) continue;
+        if ((int32_t)q < S->trim_s || (int32_t)q > S->trim_e) continue;
+        const int32_t qlen = S->qlen;
+        const int32_t rpos0 = ts + (int32_t)t_op, qpos0 = (int32_t)q0, j = (int32_t)(off - t_op);
+        const int qs = qpos0 - w, qe = qpos0 + w;
+        int u, d;
+        if (qs < 0) { u = w + qs; d = w + (-qs); }
+        else if (qe > qlen) { u = w + (qe - qlen); d = qlen - qpos0; }
+        else { u = w; d = w; }
+        const int32_t lo = rpos0 - u + j, hi = rpos0 + d + j;
+        int mc = 0;
+        if (fl & HM_SLOT_SLOW) {
+          const uint32_t r = S->read;
+          const int32_t* mm = b.mm_pos + __ldg(b.op_off + r);
+          const uint32_t nmm = (uint32_t)__ldg(b.n_mm + r);
+          mc = (int)count_le_kary_i32(mm, nmm, hi) - (int)count_le_kary_i32(mm, nmm, lo - 1);
+        } else {
+          const uint32_t nm = S->n_mm;
+          for (uint32_t m = 0; m < nm; m++) { const int32_t x = S->mm[m]; mc += (x >= lo && x <= hi); }
+        }
+        if (mc > p.max_mismatch_count) continue;
+        callable++;
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty_bar[st]);
+      batch_no++;
+      if (last) break;
+    }
+
+    // ---- position loop body (normcounts.py:317-400) ----
+    unsigned long long lg[HM_NORM_LOG_LEN];
+#pragma unroll
+    for (int i = 0; i < HM_NORM_LOG_LEN; i++) lg[i] = 0;
+    int tri = -1;
+    bool tie_alt = false;
+    const int ridx = live ? (refseq[pos] == 'A' ? 0 : refseq[pos] == 'T' ? 1 : refseq[pos] == 'G' ? 2 : refseq[pos] == 'C' ? 3 : -1) : -1;
+    if (ridx >= 0 && callable > 0) {
+      // rebuild S[allele][kind] from the first-seen allele's registers and the others
+      double S[4][3];
+#pragma unroll
+      for (int x = 0; x < 4; x++) {
+        const int j = a_main < 0 ? -2 : ((x - a_main) & 3) - 1; // -1: main allele
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+          double v = 0.0;
+          if (j == -1) v = k == 0 ? M0 : k == 1 ? M1 : M2;
+          else if (j == 0) v = O[0][k];
+          else if (j == 1) v = O[1][k];
+          else if (j == 2) v = O[2][k];
+          S[x][k] = v;
+        }
+      }
+      int cnt[6] = {cnt0, cnt1, cnt2, cnt3, cnt_ins, cnt_del};
+      const unsigned long long ts_ = (unsigned long long)callable;
+      lg[1] = ts_;
+      bool go = true;
+      if (p.phase && !(h0 >= p.min_hap_count && h1 >= p.min_hap_count)) { lg[2] = ts_; go = false; }
+      if (go) {
+        double pl[10];
+#pragma unroll
+        for (int g = 0; g < 10; g++) pl[g] = gt_pl_dev(S, g, ridx, -1);
+        int gq; bool tie;
+        const int best = argmin_gt_dev(pl, &gq, &tie);
+        const int state = gt_state_dev(c_gt_b1[best], c_gt_b2[best], ridx);
+        const int depth = cnt[0] + cnt[1] + cnt[2] + cnt[3] + cnt[5];
+        const int ref_count = cnt[ridx];
+        if (state == 1) lg[3] = ts_;
+        else if (state == 2) lg[4] = ts_;
+        else if (state == 3) lg[5] = ts_;
+        else {
+          lg[6] = ts_;
+          if (cnt[5] != 0 || cnt[4] != 0) lg[7] = ts_;
+          else if ((double)depth > p.md_threshold) lg[8] = ts_;
+          else if (depth == ref_count) {
+            if (gq < p.min_gq) lg[10] = ts_;
+            else if (ref_count < p.min_ref_count) lg[9] = ts_;
+            else tri = tri_bin_dev(refseq, ref_len, pos);
+          } else {
+            bool filtered = false;
+            int alt = -1, amax = -1, nmax = 0;
+#pragma unroll
+            for (int x = 0; x < 4; x++) {
+              if (x == ridx || filtered) continue;
+              if (cnt[x] > 0) {
+                const uint64_t key = ((uint64_t)(uint32_t)(pos + 1) << 4) | ((uint64_t)ridx << 2) | (uint64_t)x;
+                if (!p.non_human_sample && key_in_dev(sets.pon, sets.n_pon, key)) { lg[11] = ts_; filtered = true; }
+                else if (!p.non_human_sample && key_in_dev(sets.common, sets.n_common, key)) { lg[12] = ts_; filtered = true; }
+              }
+              if (cnt[x] > amax) { amax = cnt[x]; alt = x; nmax = 1; }
+              else if (cnt[x] == amax) nmax++;
+            }
+            if (!filtered) {
+              tie_alt = nmax > 1;
+#pragma unroll
+              for (int g = 0; g < 10; g++) pl[g] = gt_pl_dev(S, g, ridx, alt);
+              int gq2; bool tie2;
+              argmin_gt_dev(pl, &gq2, &tie2);
+              if (gq2 < p.min_gq) lg[10] = ts_;
+              else if (!(ref_count >= p.min_ref_count && cnt[alt] >= p.min_alt_count)) lg[9] = ts_;
+              else tri = tri_bin_dev(refseq, ref_len, pos);
+            }
+          }
+        }
+      }
+      if (tri >= 0) lg[13] = ts_;
+      if (bq_zero) s_err = HM_ERR_BQ_ZERO;
+    }
+#pragma unroll
+    for (int i = 1; i < HM_NORM_LOG_LEN; i++) {
+      unsigned long long v = lg[i];
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(HM_FULL, v, d);
+      if (lane == 0 && v) atomicAdd(&s_log[i], v);
+    }
+    if (tri >= 0) { atomicAdd(&s_ref[tri], 1ull); atomicAdd(&s_ccs[tri], (unsigned long long)callable); }
+    if (tie_alt) atomicAdd(&s_tie, 1ull);
+  }
+  // consumers only: named barrier over the 512 consumer threads, then flush the CTA tallies
+  asm volatile("bar.sync 1, %0;" ::"n"(HM_TW));
+  if (tid < HM_TRI_BINS) {
+    if (s_ccs[tid]) atomicAdd(&out->ccs_tri[tid], s_ccs[tid]);
+    if (s_ref[tid]) atomicAdd(&out->ref_tri[tid], s_ref[tid]);
+  }
+  if (tid < HM_NORM_LOG_LEN && s_log[tid]) atomicAdd(&out->log[tid], s_log[tid]);
+  if (tid == 0) {
+    if (s_tie) atomicAdd(&out->alt_tie, s_tie);
+    if (s_err) out->err = s_err;
+  }
+}
+
 struct hm_ctx;
 static int hm_normcounts_impl(hm_ctx* ctx, const uint8_t* refseq, size_t ref_len, const hm_chunk* chunks, size_t n_chunks,
                               int64_t* ccs_tri, int64_t* ref_tri, int64_t* log, int64_t* n_alt_tie);

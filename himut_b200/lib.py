@@ -88,7 +88,11 @@ class Context:
             self.lib.hm_destroy(self.h)
             self.h = None
 
-    __del__ = close
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # interpreter shutdown: the driver reclaims the context
+            pass
 
     def __enter__(self):
         return self
