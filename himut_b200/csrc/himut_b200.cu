@@ -722,6 +722,12 @@ static int hm_normcounts_impl(hm_ctx* ctx, const uint8_t* refseq, size_t ref_len
   }
   CU(cudaStreamSynchronize(ctx->stream));
   t_collect(ctx);
+#ifdef HM_NORM_DEBUG
+  fprintf(stderr, "[norm dbg, CTA 0] producer: wait %.0f fill %.0f cycles per batch (%llu batches) | consumer warp 0: wait %.0f compute %.0f cycles per batch, %.1f slots per batch | epilogue %.0f cycles per tile (%llu tiles)\n",
+          (double)h.dbg[0] / (double)std::max<unsigned long long>(h.dbg[2], 1), (double)h.dbg[1] / (double)std::max<unsigned long long>(h.dbg[2], 1), h.dbg[2],
+          (double)h.dbg[3] / (double)std::max<unsigned long long>(h.dbg[2], 1), (double)h.dbg[4] / (double)std::max<unsigned long long>(h.dbg[2], 1),
+          (double)h.dbg[5] / (double)std::max<unsigned long long>(h.dbg[2], 1), (double)h.dbg[6] / (double)std::max<unsigned long long>(h.dbg[7], 1), h.dbg[7]);
+#endif
   if (h.err == HM_ERR_BQ_ZERO) return fail(ctx, HM_ERR_BQ_ZERO, "a base quality of 0 reached the genotype model (the reference raises ValueError: math.log10(0))");
   for (int i = 0; i < HM_TRI_BINS; i++) { ccs_tri[i] = (int64_t)h.ccs_tri[i]; ref_tri[i] = (int64_t)h.ref_tri[i]; }
   for (int i = 1; i < HM_NORM_LOG_LEN; i++) log[i] = (int64_t)h.log[i];
