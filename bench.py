@@ -4,7 +4,7 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--contig-mb M]
 
 A step is one pass of the whole `himut call` device path (k_read_scan -> k_candidates -> sort ->
-k_eval_sites -> host som_seen replay) over one contig's packed read batch.
+k_site_range|entries|reduce -> host som_seen replay) over one contig's packed read batch.
 
   value   aligned CCS bases/s with the batch already resident in HBM (hm_call_chunks),
           CUDA events on the launching stream, barrier + synchronize on both sides, max over ranks

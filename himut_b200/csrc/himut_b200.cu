@@ -78,6 +78,7 @@ struct hm_ctx {
   size_t ev_used = 0;
   float last_total_ms = 0.f;
   int last_launches = 0;
+  size_t ref_len = 0; // length of the contig left resident by hm_set_reference (0: none)
 };
 
 namespace {
@@ -619,6 +620,18 @@ int hm_qname_seen(hm_ctx* ctx, uint8_t* out, size_t cap, size_t* n) {
   return HM_OK;
 }
 
+/* keep a contig's reference sequence resident for subsequent hm_normcounts_chunks(refseq = NULL) */
+int hm_set_reference(hm_ctx* ctx, const uint8_t* refseq, size_t ref_len) {
+  if (!ctx || (!refseq && ref_len)) return HM_ERR_ARG;
+  CU(cudaSetDevice(ctx->device));
+  ctx->ref_len = 0;
+  int rc = upload(ctx, ctx->b_ref, refseq, ref_len);
+  if (rc) return rc;
+  CU(cudaStreamSynchronize(ctx->stream));
+  ctx->ref_len = ref_len;
+  return HM_OK;
+}
+
 int hm_last_timing(hm_ctx* ctx, float* total_ms, int* n_launches) {
   if (!ctx) return HM_ERR_ARG;
   if (total_ms) *total_ms = ctx->last_total_ms;
@@ -641,7 +654,9 @@ int hm_last_kernel_times(hm_ctx* ctx, const char** names, float* ms, size_t cap,
 
 static int hm_normcounts_impl(hm_ctx* ctx, const uint8_t* refseq, size_t ref_len, const hm_chunk* chunks, size_t n_chunks,
                               int64_t* ccs_tri, int64_t* ref_tri, int64_t* log, int64_t* n_alt_tie) {
-  if (!refseq || !ccs_tri || !ref_tri || !log) return fail(ctx, HM_ERR_ARG, "refseq / output pointer is NULL");
+  if (!ccs_tri || !ref_tri || !log) return fail(ctx, HM_ERR_ARG, "output pointer is NULL");
+  if (!refseq && !ctx->ref_len) return fail(ctx, HM_ERR_STATE, "refseq is NULL and no reference was set with hm_set_reference");
+  if (!refseq) ref_len = ctx->ref_len;
   CU(cudaSetDevice(ctx->device));
   memset(ccs_tri, 0, sizeof(int64_t) * HM_TRI_BINS);
   memset(ref_tri, 0, sizeof(int64_t) * HM_TRI_BINS);
@@ -663,7 +678,10 @@ static int hm_normcounts_impl(hm_ctx* ctx, const uint8_t* refseq, size_t ref_len
   const uint64_t n_tiles = tile_off[n_chunks], n_tiles_tma = tile_off2[n_chunks];
   if (n_tiles >= (1ull << 31)) return fail(ctx, HM_ERR_ARG, "too many tiles in one call");
   if ((rc = upload(ctx, ctx->b_tile_off, tile_off.data(), tile_off.size()))) return rc;
-  if ((rc = upload(ctx, ctx->b_ref, refseq, ref_len))) return rc;
+  if (refseq) { // per-call reference: replaces whatever hm_set_reference left
+    if ((rc = upload(ctx, ctx->b_ref, refseq, ref_len))) return rc;
+    ctx->ref_len = 0;
+  }
   if ((rc = launch_read_scan(ctx))) return rc;
   CU(ctx->b_norm_out.ensure(sizeof(NormOut)));
   CU(ctx->b_counters.ensure(64));

@@ -19,7 +19,7 @@ EXPORTS = [
     "hm_abi_version", "hm_create", "hm_destroy", "hm_last_error", "hm_set_params", "hm_set_site_sets",
     "hm_set_phase_sets", "hm_upload_batch", "hm_call_chunks", "hm_call_batch", "hm_normcounts_chunks",
     "hm_read_stats", "hm_last_timing", "hm_last_kernel_times", "hm_set_stream", "hm_host_register",
-    "hm_host_unregister", "hm_abi_sizeof", "hm_last_records", "hm_qname_seen",
+    "hm_host_unregister", "hm_abi_sizeof", "hm_last_records", "hm_qname_seen", "hm_set_reference",
 ]
 
 
@@ -57,6 +57,7 @@ def load():
         lib.hm_last_kernel_times.argtypes = [vp, vp, vp, sz, C.POINTER(sz)]
         lib.hm_last_records.argtypes = [vp, vp, sz, C.POINTER(sz)]
         lib.hm_qname_seen.argtypes = [vp, vp, sz, C.POINTER(sz)]
+        lib.hm_set_reference.argtypes = [vp, vp, sz]
         lib.hm_set_stream.argtypes = [vp, vp]
         lib.hm_host_register.argtypes = [vp, vp, sz]
         lib.hm_host_unregister.argtypes = [vp, vp]
@@ -178,7 +179,11 @@ class Context:
     def normcounts_chunks(self, refseq, chunks):
         """callable-base half of `himut normcounts` -> (ccs_tri[33], ref_tri[33], log[14], n_alt_tie)"""
         chunks = np.ascontiguousarray(chunks, dtype=abi.CHUNK_DTYPE)
-        ref = np.frombuffer(refseq, dtype=np.uint8)
+        if refseq is not getattr(self, "_ref_obj", None):  # upload a contig's reference once
+            ref = np.frombuffer(refseq, dtype=np.uint8)
+            self._chk(self.lib.hm_set_reference(self.h, _p(ref), ref.size))
+            self._ref_obj = refseq
+        ref = np.zeros(0, np.uint8)
         ccs = np.zeros(abi.TRI_BINS, np.int64)
         rt = np.zeros(abi.TRI_BINS, np.int64)
         log = np.zeros(abi.NORM_LOG_LEN, np.int64)

@@ -250,6 +250,10 @@ int hm_call_batch(hm_ctx* ctx, const hm_read_batch* batch, const hm_chunk* chunk
                   size_t n_chunks, hm_site_record* out, size_t cap, size_t* n_out,
                   int64_t log[HM_CALL_LOG_LEN]);
 
+/* keep a contig's reference sequence (the `seq` argument of get_callable_tricounts,
+ * normcounts.py:208) resident on the device; hm_normcounts_chunks then accepts refseq = NULL */
+int hm_set_reference(hm_ctx* ctx, const uint8_t* refseq, size_t ref_len);
+
 /* callable-base half of `himut normcounts` over chunks of the resident batch (replaces the
  * body of normcounts.get_callable_tricounts, normcounts.py:240-419).  refseq is the contig
  * as upper/lower-case ASCII (positions outside A/T/G/C upper-case are skipped as in
