@@ -1,0 +1,557 @@
+/*
+ * bamdec.c — native BAM region -> packed hm_read_batch decoder (host side, no CUDA).
+ *
+ * Replaces, for the GPU workers, what the reference does per record through pysam/htslib and
+ * Python: alignments.fetch(chrom, start, end) (src/himut/caller.py:299) + bamlib.BAM.__init__
+ * (src/himut/bamlib.py:15-32) + the regex walk of cslib.cs2lst / cs2tuple
+ * (src/himut/cslib.py:7-44).  Same rules as himut_b200/bamio.py + pack.py (which stay as the
+ * readable specification and are compared against this file in tests/test_host.py):
+ *   - records overlapping [start, end) of the contig, file order, secondary (0x100) skipped,
+ *     supplementary kept;
+ *   - coordinates from the CIGAR, query span and reference span cross-checked against cs;
+ *   - inputs the reference would crash on are rejected with a message (no cs tag, missing
+ *     qualities, hard clips, read base outside ACGT under a cs match, '~' introns).
+ * BGZF blocks are inflated by a small pthread pool; parsing is a single pass.
+ */
+#define _GNU_SOURCE
+#include <pthread.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <zlib.h>
+
+#include "../../include/himut_b200.h"
+
+typedef struct {
+  char* name;
+  int32_t len;
+  uint64_t* lin; /* linear index */
+  int32_t n_lin;
+  int has_index;
+} bam_ref_t;
+
+typedef struct {
+  uint64_t* keys_hash;
+  uint32_t* ids;
+  char** names;
+  uint32_t cap, n;
+} qtab_t;
+
+typedef struct hm_bam {
+  FILE* f;
+  char* path;
+  char* header;
+  int32_t n_ref;
+  bam_ref_t* refs;
+  uint64_t first_record; /* virtual offset */
+  int have_bai;
+  qtab_t qt;
+  char err[512];
+  /* last decoded batch (owned) */
+  hm_read_batch batch;
+  int32_t *tstart, *tend, *qstart, *qlen;
+  uint8_t *mapq, *flags;
+  uint32_t *qname_id, *n_ops;
+  uint64_t *seq_off, *bq_off, *op_off;
+  uint8_t *seq, *bq;
+  uint32_t* ops;
+  size_t cap_reads, cap_seq, cap_bq, cap_ops;
+} hm_bam;
+
+static int fail(hm_bam* b, const char* fmt, const char* a, long x) {
+  snprintf(b->err, sizeof(b->err), fmt, a ? a : "", x);
+  return HM_ERR_ARG;
+}
+
+/* ------------------------------------------------------------------ qname table (FNV-1a) */
+static uint64_t fnv(const char* s, size_t n) {
+  uint64_t h = 1469598103934665603ull;
+  for (size_t i = 0; i < n; i++) { h ^= (uint8_t)s[i]; h *= 1099511628211ull; }
+  return h ? h : 1;
+}
+static int qt_grow(qtab_t* t) {
+  uint32_t ncap = t->cap ? t->cap * 2 : 1u << 16;
+  uint64_t* nk = (uint64_t*)calloc(ncap, sizeof(uint64_t));
+  uint32_t* ni = (uint32_t*)malloc(ncap * sizeof(uint32_t));
+  if (!nk || !ni) return -1;
+  for (uint32_t i = 0; i < t->cap; i++)
+    if (t->keys_hash[i]) {
+      uint32_t j = (uint32_t)(t->keys_hash[i] & (ncap - 1));
+      while (nk[j]) j = (j + 1) & (ncap - 1);
+      nk[j] = t->keys_hash[i]; ni[j] = t->ids[i];
+    }
+  free(t->keys_hash); free(t->ids);
+  t->keys_hash = nk; t->ids = ni; t->cap = ncap;
+  return 0;
+}
+static int64_t qt_get(qtab_t* t, const char* s, size_t n) {
+  if (t->n * 2 >= t->cap && qt_grow(t)) return -1;
+  uint64_t h = fnv(s, n);
+  uint32_t j = (uint32_t)(h & (t->cap - 1));
+  while (t->keys_hash[j]) {
+    if (t->keys_hash[j] == h) {
+      const char* o = t->names[t->ids[j]];
+      if (strlen(o) == n && memcmp(o, s, n) == 0) return t->ids[j];
+    }
+    j = (j + 1) & (t->cap - 1);
+  }
+  if ((t->n & 0xffff) == 0) {
+    char** nn = (char**)realloc(t->names, ((size_t)t->n + 0x10000) * sizeof(char*));
+    if (!nn) return -1;
+    t->names = nn;
+  }
+  char* c = (char*)malloc(n + 1);
+  if (!c) return -1;
+  memcpy(c, s, n); c[n] = 0;
+  t->names[t->n] = c;
+  t->keys_hash[j] = h; t->ids[j] = t->n;
+  return t->n++;
+}
+
+static inline uint32_t rd32(const uint8_t* p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24); }
+
+/* ------------------------------------------------------------------ BGZF */
+typedef struct {
+  uint64_t coff;      /* file offset of the block */
+  uint32_t csize;     /* whole block size */
+  uint32_t usize;     /* ISIZE */
+  uint64_t uoff;      /* offset of its payload in the inflated buffer */
+} blk_t;
+
+static int read_block_header(FILE* f, uint64_t coff, blk_t* b) {
+  uint8_t h[18];
+  if (fseeko(f, (off_t)coff, SEEK_SET)) return -1;
+  size_t got = fread(h, 1, 18, f);
+  if (got == 0) return 1; /* EOF */
+  if (got < 18 || h[0] != 0x1f || h[1] != 0x8b || h[2] != 8 || !(h[3] & 4)) return -1;
+  uint16_t xlen = (uint16_t)(h[10] | (h[11] << 8));
+  uint8_t extra[4096];
+  if (xlen < 6 || xlen > sizeof(extra)) return -1;
+  memcpy(extra, h + 12, 6);
+  if (xlen > 6 && fread(extra + 6, 1, xlen - 6, f) != (size_t)(xlen - 6)) return -1;
+  int bsize = -1;
+  for (int p = 0; p + 4 <= xlen;) {
+    int slen = extra[p + 2] | (extra[p + 3] << 8);
+    if (extra[p] == 66 && extra[p + 1] == 67 && slen == 2) bsize = extra[p + 4] | (extra[p + 5] << 8);
+    p += 4 + slen;
+  }
+  if (bsize < 0) return -1;
+  b->coff = coff; b->csize = (uint32_t)bsize + 1;
+  uint8_t tail[4];
+  if (fseeko(f, (off_t)(coff + b->csize - 4), SEEK_SET) || fread(tail, 1, 4, f) != 4) return -1;
+  b->usize = (uint32_t)tail[0] | ((uint32_t)tail[1] << 8) | ((uint32_t)tail[2] << 16) | ((uint32_t)tail[3] << 24);
+  return 0;
+}
+
+typedef struct {
+  const uint8_t* comp; /* compressed bytes of the span; blocks[i].coff is relative to it */
+  const blk_t* blocks;
+  size_t n_blocks;
+  uint8_t* out;
+  size_t next;
+  pthread_mutex_t mu;
+  int error;
+} inflate_job_t;
+
+static void* inflate_worker(void* arg) {
+  inflate_job_t* j = (inflate_job_t*)arg;
+  z_stream zs;
+  memset(&zs, 0, sizeof(zs));
+  if (inflateInit2(&zs, -15) != Z_OK) { j->error = 1; return NULL; }
+  for (;;) {
+    pthread_mutex_lock(&j->mu);
+    size_t i0 = j->next;
+    j->next += 16; /* a few blocks per grab */
+    pthread_mutex_unlock(&j->mu);
+    if (i0 >= j->n_blocks) break;
+    for (size_t i = i0; i < i0 + 16 && i < j->n_blocks; i++) {
+      const blk_t* b = &j->blocks[i];
+      const uint8_t* src = j->comp + b->coff;
+      uint16_t xlen = (uint16_t)(src[10] | (src[11] << 8));
+      if (b->usize == 0) continue;
+      inflateReset(&zs);
+      zs.next_in = (Bytef*)(src + 12 + xlen);
+      zs.avail_in = b->csize - 12 - xlen - 8;
+      zs.next_out = j->out + b->uoff;
+      zs.avail_out = b->usize;
+      if (inflate(&zs, Z_FINISH) != Z_STREAM_END) { j->error = 1; break; }
+    }
+    if (j->error) break;
+  }
+  inflateEnd(&zs);
+  return NULL;
+}
+
+/* sequential reader over the inflated stream: compressed spans are read in one piece, their
+ * BGZF headers walked in memory, and the blocks inflated by the pool */
+typedef struct {
+  hm_bam* b;
+  uint64_t next_coff;
+  uint8_t* buf;      /* inflated bytes not yet consumed */
+  size_t len, pos, cap;
+  size_t span;       /* compressed bytes to read next time (grows 1 MB -> 64 MB) */
+  int eof, threads;
+} stream_t;
+
+static int stream_fill(stream_t* s) {
+  if (s->eof) return 1;
+  if (s->span == 0) s->span = 1u << 20;
+  for (;;) {
+    uint8_t* comp = (uint8_t*)malloc(s->span);
+    if (!comp) return -1;
+    if (fseeko(s->b->f, (off_t)s->next_coff, SEEK_SET)) { free(comp); return -1; }
+    size_t got = fread(comp, 1, s->span, s->b->f);
+    if (got == 0) { free(comp); s->eof = 1; return 1; }
+    size_t nb = 0, cap_b = got / 200 + 16, off = 0;
+    uint64_t usum = 0;
+    blk_t* blocks = (blk_t*)malloc(cap_b * sizeof(blk_t));
+    if (!blocks) { free(comp); return -1; }
+    int bad = 0;
+    while (off + 18 <= got) {
+      const uint8_t* h = comp + off;
+      if (h[0] != 0x1f || h[1] != 0x8b || h[2] != 8 || !(h[3] & 4)) { bad = 1; break; }
+      uint16_t xlen = (uint16_t)(h[10] | (h[11] << 8));
+      if (off + 12 + xlen > got) break;
+      int bsize = -1;
+      for (int q = 0; q + 4 <= xlen;) {
+        int slen = h[12 + q + 2] | (h[12 + q + 3] << 8);
+        if (h[12 + q] == 66 && h[12 + q + 1] == 67 && slen == 2) bsize = h[12 + q + 4] | (h[12 + q + 5] << 8);
+        q += 4 + slen;
+      }
+      if (bsize < 0) { bad = 1; break; }
+      size_t csize = (size_t)bsize + 1;
+      if (off + csize > got) break;
+      if (nb == cap_b) { cap_b *= 2; blk_t* nbk = (blk_t*)realloc(blocks, cap_b * sizeof(blk_t)); if (!nbk) { bad = 1; break; } blocks = nbk; }
+      blocks[nb].coff = off; blocks[nb].csize = (uint32_t)csize; blocks[nb].usize = rd32(h + csize - 4); blocks[nb].uoff = usum;
+      usum += blocks[nb].usize; off += csize; nb++;
+    }
+    if (bad) { free(blocks); free(comp); return -1; }
+    if (nb == 0) { /* a block larger than the span, or a truncated file */
+      free(blocks); free(comp);
+      if (got < s->span) return -1;
+      s->span *= 2;
+      continue;
+    }
+    size_t keep = s->len - s->pos;
+    if (s->pos && keep) memmove(s->buf, s->buf + s->pos, keep);
+    s->len = keep; s->pos = 0;
+    if (s->len + usum > s->cap) {
+      size_t nc = s->len + usum + (1 << 20);
+      uint8_t* nbuf = (uint8_t*)realloc(s->buf, nc);
+      if (!nbuf) { free(blocks); free(comp); return -1; }
+      s->buf = nbuf; s->cap = nc;
+    }
+    inflate_job_t job;
+    memset(&job, 0, sizeof(job));
+    job.comp = comp; job.blocks = blocks; job.n_blocks = nb; job.out = s->buf + s->len;
+    pthread_mutex_init(&job.mu, NULL);
+    int nt = s->threads < 1 ? 1 : (s->threads > 64 ? 64 : s->threads);
+    if ((size_t)nt > (nb + 15) / 16) nt = (int)((nb + 15) / 16);
+    pthread_t th[64];
+    for (int t = 1; t < nt; t++) pthread_create(&th[t], NULL, inflate_worker, &job);
+    inflate_worker(&job);
+    for (int t = 1; t < nt; t++) pthread_join(th[t], NULL);
+    pthread_mutex_destroy(&job.mu);
+    free(comp); free(blocks);
+    if (job.error) return -1;
+    s->len += usum;
+    s->next_coff += off;
+    if (s->span < (64u << 20)) s->span *= 2;
+    return 0;
+  }
+}
+/* make `n` bytes available at buf+pos; 0 ok, 1 EOF, -1 error */
+static int stream_need(stream_t* s, size_t n) {
+  while (s->len - s->pos < n) {
+    int rc = stream_fill(s);
+    if (rc) return (s->len - s->pos >= n) ? 0 : rc;
+  }
+  return 0;
+}
+static int stream_seek(stream_t* s, uint64_t voffset) {
+  s->next_coff = voffset >> 16;
+  s->len = s->pos = 0; s->eof = 0;
+  int rc = stream_fill(s);
+  if (rc < 0) return rc;
+  s->pos = voffset & 0xffff;
+  return 0;
+}
+
+/* ------------------------------------------------------------------ open / close */
+static int load_bai(hm_bam* b) {
+  size_t n = strlen(b->path);
+  char* p = (char*)malloc(n + 5);
+  if (!p) return -1;
+  memcpy(p, b->path, n); memcpy(p + n, ".bai", 5);
+  FILE* f = fopen(p, "rb");
+  free(p);
+  if (!f) return 0;
+  fseeko(f, 0, SEEK_END);
+  size_t sz = (size_t)ftello(f);
+  fseeko(f, 0, SEEK_SET);
+  uint8_t* d = (uint8_t*)malloc(sz + 8);
+  if (!d || fread(d, 1, sz, f) != sz) { free(d); fclose(f); return -1; }
+  fclose(f);
+  if (sz < 8 || memcmp(d, "BAI\1", 4)) { free(d); return -1; }
+  size_t q = 8;
+  int32_t nref = (int32_t)rd32(d + 4);
+  for (int32_t r = 0; r < nref && r < b->n_ref; r++) {
+    int32_t nbin = (int32_t)rd32(d + q); q += 4;
+    for (int32_t k = 0; k < nbin; k++) { int32_t nchunk = (int32_t)rd32(d + q + 4); q += 8 + 16 * (size_t)nchunk; }
+    int32_t nintv = (int32_t)rd32(d + q); q += 4;
+    b->refs[r].lin = (uint64_t*)malloc(((size_t)nintv + 1) * 8);
+    b->refs[r].n_lin = nintv;
+    b->refs[r].has_index = (nbin || nintv);
+    for (int32_t k = 0; k < nintv; k++) { memcpy(&b->refs[r].lin[k], d + q, 8); q += 8; }
+  }
+  free(d);
+  b->have_bai = 1;
+  return 0;
+}
+
+void hm_bam_close(hm_bam* b) {
+  if (!b) return;
+  if (b->f) fclose(b->f);
+  for (int32_t i = 0; i < b->n_ref; i++) { free(b->refs[i].name); free(b->refs[i].lin); }
+  free(b->refs); free(b->header); free(b->path);
+  for (uint32_t i = 0; i < b->qt.n; i++) free(b->qt.names[i]);
+  free(b->qt.names); free(b->qt.keys_hash); free(b->qt.ids);
+  free(b->tstart); free(b->tend); free(b->qstart); free(b->qlen); free(b->mapq); free(b->flags); free(b->qname_id);
+  free(b->n_ops); free(b->seq_off); free(b->bq_off); free(b->op_off); free(b->seq); free(b->bq); free(b->ops);
+  free(b);
+}
+
+int hm_bam_open(const char* path, hm_bam** out) {
+  if (!path || !out) return HM_ERR_ARG;
+  *out = NULL;
+  hm_bam* b = (hm_bam*)calloc(1, sizeof(hm_bam));
+  if (!b) return HM_ERR_ARG;
+  b->path = strdup(path);
+  b->f = fopen(path, "rb");
+  if (!b->f) { hm_bam_close(b); return HM_ERR_ARG; }
+  stream_t s;
+  memset(&s, 0, sizeof(s));
+  s.b = b; s.threads = 1;
+  int rc = HM_ERR_ARG;
+  if (stream_seek(&s, 0) || stream_need(&s, 12) || memcmp(s.buf + s.pos, "BAM\1", 4)) goto done;
+  {
+    uint32_t ltext = rd32(s.buf + s.pos + 4);
+    if (stream_need(&s, 12 + (size_t)ltext)) goto done;
+    b->header = (char*)malloc((size_t)ltext + 1);
+    memcpy(b->header, s.buf + s.pos + 8, ltext); b->header[ltext] = 0;
+    b->n_ref = (int32_t)rd32(s.buf + s.pos + 8 + ltext);
+    size_t consumed = 12 + (size_t)ltext;
+    b->refs = (bam_ref_t*)calloc((size_t)b->n_ref + 1, sizeof(bam_ref_t));
+    for (int32_t i = 0; i < b->n_ref; i++) {
+      if (stream_need(&s, consumed + 4)) goto done;
+      uint32_t ln = rd32(s.buf + s.pos + consumed);
+      if (stream_need(&s, consumed + 8 + ln)) goto done;
+      b->refs[i].name = (char*)malloc(ln + 1);
+      memcpy(b->refs[i].name, s.buf + s.pos + consumed + 4, ln); b->refs[i].name[ln] = 0;
+      b->refs[i].len = (int32_t)rd32(s.buf + s.pos + consumed + 4 + ln);
+      consumed += 8 + ln;
+    }
+    /* virtual offset of the first record: walk the blocks again, cheaply */
+    uint64_t coff = 0, left = consumed;
+    for (;;) {
+      blk_t blk;
+      if (read_block_header(b->f, coff, &blk)) goto done;
+      if (left < blk.usize) { b->first_record = (coff << 16) | left; break; }
+      if (left == blk.usize) { b->first_record = ((coff + blk.csize) << 16); break; }
+      left -= blk.usize; coff += blk.csize;
+    }
+  }
+  if (load_bai(b) < 0) goto done;
+  rc = HM_OK;
+done:
+  free(s.buf);
+  if (rc) { hm_bam_close(b); return rc; }
+  *out = b;
+  return HM_OK;
+}
+
+const char* hm_bam_error(const hm_bam* b) { return b ? b->err : "null handle"; }
+const char* hm_bam_header_text(const hm_bam* b) { return b->header; }
+int hm_bam_n_refs(const hm_bam* b) { return b->n_ref; }
+const char* hm_bam_ref_name(const hm_bam* b, int i) { return (i >= 0 && i < b->n_ref) ? b->refs[i].name : NULL; }
+int hm_bam_ref_len(const hm_bam* b, int i) { return (i >= 0 && i < b->n_ref) ? b->refs[i].len : -1; }
+uint32_t hm_bam_n_qnames(const hm_bam* b) { return b->qt.n; }
+const char* hm_bam_qname(const hm_bam* b, uint32_t id) { return id < b->qt.n ? b->qt.names[id] : NULL; }
+
+/* ------------------------------------------------------------------ decode */
+#define GROW(ptr, cap, need, type)                                    \
+  do {                                                                \
+    if ((need) > (cap)) {                                             \
+      size_t nc_ = (cap) ? (cap) : 1024;                              \
+      while (nc_ < (need)) nc_ += nc_ / 2 + 1024;                     \
+      type* np_ = (type*)realloc((ptr), nc_ * sizeof(type));          \
+      if (!np_) return fail(b, "out of memory%s (%ld)", NULL, (long)nc_); \
+      (ptr) = np_; (cap) = nc_;                                       \
+    }                                                                 \
+  } while (0)
+
+static const int8_t NIB2CODE[16] = {-1, 0, 3, -1, 2, -1, -1, -1, 1, -1, -1, -1, -1, -1, -1, -1}; /* A1 C2 G4 T8 -> A0 T1 G2 C3 */
+static inline int base_code(char c) {
+  switch (c) { case 'A': case 'a': return 0; case 'T': case 't': return 1; case 'G': case 'g': return 2; case 'C': case 'c': return 3; default: return -1; }
+}
+
+int hm_bam_read_batch(hm_bam* b, int rid, int32_t start, int32_t end, int threads, hm_read_batch* out) {
+  if (!b || !out) return HM_ERR_ARG;
+  if (rid < 0 || rid >= b->n_ref) return fail(b, "invalid contig index%s %ld", NULL, rid);
+  if (start < 0) start = 0;
+  if (end > b->refs[rid].len) end = b->refs[rid].len;
+  size_t n_reads = 0, n_seq = 0, n_bq = 0, n_ops = 0;
+  memset(out, 0, sizeof(*out));
+  uint64_t voff = b->first_record;
+  if (b->have_bai) {
+    const bam_ref_t* R = &b->refs[rid];
+    if (!R->has_index) goto finish; /* no reads on this contig */
+    int32_t w = start >> 14;
+    if (w >= R->n_lin) w = R->n_lin - 1;
+    uint64_t v = 0;
+    for (; w >= 0 && !v; w--) v = R->lin[w];
+    if (v) voff = v;
+  }
+  {
+    stream_t s;
+    memset(&s, 0, sizeof(s));
+    s.b = b; s.threads = threads;
+    if (stream_seek(&s, voff) < 0) { free(s.buf); return fail(b, "cannot read BGZF blocks of %s (%ld)", b->path, 0); }
+    uint8_t* codes = NULL; size_t codes_cap = 0;
+    int rc = HM_OK;
+    for (;;) {
+      int st = stream_need(&s, 4);
+      if (st == 1) break;
+      if (st < 0) { rc = fail(b, "truncated BAM %s (%ld)", b->path, 0); break; }
+      uint32_t bs = rd32(s.buf + s.pos);
+      if (stream_need(&s, 4 + (size_t)bs)) { rc = fail(b, "truncated BAM record in %s (%ld)", b->path, 0); break; }
+      const uint8_t* r = s.buf + s.pos + 4;
+      s.pos += 4 + (size_t)bs;
+      int32_t ref_id = (int32_t)rd32(r), pos = (int32_t)rd32(r + 4);
+      if (ref_id != rid) { if (ref_id > rid || ref_id < 0) break; continue; }
+      if (pos >= end) break;
+      uint32_t l_name = r[8], mapq = r[9], n_cig = r[12] | (r[13] << 8), flag = r[14] | (r[15] << 8);
+      int32_t l_seq = (int32_t)rd32(r + 16);
+      const char* qname = (const char*)(r + 32);
+      const uint8_t* cig = r + 32 + l_name;
+      int32_t ref_span = 0, lead = 0, trail = 0;
+      int hard = 0;
+      for (uint32_t k = 0; k < n_cig; k++) {
+        uint32_t c = rd32(cig + 4 * k), op = c & 15, ln = c >> 4;
+        if (op == 0 || op == 2 || op == 3 || op == 7 || op == 8) ref_span += (int32_t)ln;
+        if (op == 5) hard = 1;
+      }
+      for (uint32_t k = 0; k < n_cig; k++) { uint32_t c = rd32(cig + 4 * k), op = c & 15; if (op == 4) lead += (int32_t)(c >> 4); else if (op != 5) break; }
+      for (uint32_t k = n_cig; k-- > 0;) { uint32_t c = rd32(cig + 4 * k), op = c & 15; if (op == 4) trail += (int32_t)(c >> 4); else if (op != 5) break; }
+      int32_t rend = pos + (ref_span > 0 ? ref_span : 1);
+      if (rend <= start) continue;
+      if (flag & 0x100) continue; /* secondary: bamlib.py:17 */
+      const uint8_t* seq4 = cig + 4 * (size_t)n_cig;
+      const uint8_t* qual = seq4 + ((size_t)l_seq + 1) / 2;
+      const uint8_t* tag = qual + l_seq;
+      const uint8_t* rec_end = r + bs;
+      const char* cs = NULL;
+      while (tag + 3 <= rec_end) {
+        char ty = (char)tag[2];
+        const uint8_t* v = tag + 3;
+        size_t adv;
+        if (ty == 'Z' || ty == 'H') { adv = strlen((const char*)v) + 1; if (tag[0] == 'c' && tag[1] == 's' && ty == 'Z') cs = (const char*)v; }
+        else if (ty == 'A' || ty == 'c' || ty == 'C') adv = 1;
+        else if (ty == 's' || ty == 'S') adv = 2;
+        else if (ty == 'i' || ty == 'I' || ty == 'f') adv = 4;
+        else if (ty == 'B') { char sub = (char)v[0]; uint32_t cnt = rd32(v + 1); adv = 5 + (size_t)cnt * ((sub == 'c' || sub == 'C') ? 1 : (sub == 's' || sub == 'S') ? 2 : 4); }
+        else { rc = fail(b, "unknown tag type in record %s (%ld)", qname, ty); break; }
+        tag = v + adv;
+      }
+      if (rc) break;
+      if (!cs) { rc = fail(b, "%s has no cs:Z tag (the reference raises KeyError in BAM.__init__) (%ld)", qname, 0); break; }
+      if (hard) { rc = fail(b, "%s is hard clipped: cs / SEQ indexing breaks in the reference (pre-filter with -F 0x900) (%ld)", qname, 0); break; }
+      if (l_seq <= 0 || qual[0] == 0xff) { rc = fail(b, "%s has no base qualities (%ld)", qname, 0); break; }
+      /* unpack bases to codes (-1 = not ACGT) */
+      GROW(codes, codes_cap, (size_t)l_seq + 2, uint8_t);
+      for (int32_t i = 0; i < l_seq; i++) { uint8_t nb = (i & 1) ? (seq4[i >> 1] & 15) : (seq4[i >> 1] >> 4); codes[i] = (uint8_t)NIB2CODE[nb]; }
+      /* cs -> ops (cslib.cs2lst grammar), with span and base checks */
+      GROW(b->ops, b->cap_ops, n_ops + strlen(cs) / 2 + 4, uint32_t);
+      size_t op0 = n_ops;
+      int32_t q = lead, rspan = 0;
+      const char* c = cs;
+      while (*c && !rc) {
+        if (*c == ':') {
+          long n = 0; c++;
+          if (*c < '0' || *c > '9') { rc = fail(b, "%s: unsupported cs token (%ld)", qname, (long)(c - cs)); break; }
+          while (*c >= '0' && *c <= '9') n = n * 10 + (*c++ - '0');
+          if (q + n > l_seq) { rc = fail(b, "%s: cs runs past the read (%ld)", qname, q + n); break; }
+          for (long k = 0; k < n; k++) if (codes[q + k] == 0xff) { rc = fail(b, "%s: read base outside A/C/G/T under a cs match (reference: KeyError) (%ld)", qname, q + k); break; }
+          if (n) b->ops[n_ops++] = HM_MAKE_OP(HM_OP_MATCH, n);
+          q += (int32_t)n; rspan += (int32_t)n;
+        } else if (*c == '=') {
+          long n = 0; c++;
+          while ((c[n] >= 'A' && c[n] <= 'Z') || (c[n] >= 'a' && c[n] <= 'z')) n++;
+          if (n == 0 || q + n > l_seq) { rc = fail(b, "%s: unsupported cs token (%ld)", qname, (long)(c - cs)); break; }
+          for (long k = 0; k < n; k++) {
+            int bc = base_code(c[k]);
+            if (bc < 0 || codes[q + k] != (uint8_t)bc) { rc = fail(b, "%s: cs long-form bases disagree with SEQ at query %ld", qname, q + k); break; }
+          }
+          b->ops[n_ops++] = HM_MAKE_OP(HM_OP_MATCH, n);
+          c += n; q += (int32_t)n; rspan += (int32_t)n;
+        } else if (*c == '*') {
+          int rc_ = base_code(c[1]), ac = base_code(c[2]);
+          if (!c[1] || !c[2]) { rc = fail(b, "%s: unsupported cs token (%ld)", qname, (long)(c - cs)); break; }
+          if (ac < 0) { rc = fail(b, "%s: substitution to a base outside A/C/G/T (the reference pileup raises KeyError) (%ld)", qname, q); break; }
+          b->ops[n_ops++] = HM_MAKE_SUB(rc_ < 0 ? HM_BASE_N : (uint32_t)rc_, (uint32_t)ac);
+          c += 3; q += 1; rspan += 1;
+        } else if (*c == '+' || *c == '-') {
+          int ins = *c == '+';
+          long n = 0; c++;
+          while ((c[n] >= 'A' && c[n] <= 'Z') || (c[n] >= 'a' && c[n] <= 'z')) n++;
+          if (n == 0) { rc = fail(b, "%s: unsupported cs token (%ld)", qname, (long)(c - cs)); break; }
+          b->ops[n_ops++] = HM_MAKE_OP(ins ? HM_OP_INS : HM_OP_DEL, n);
+          c += n;
+          if (ins) q += (int32_t)n; else rspan += (int32_t)n;
+        } else {
+          rc = fail(b, "%s: unsupported cs token (%ld)", qname, (long)(c - cs));
+        }
+      }
+      if (rc) break;
+      if (rspan != ref_span) { rc = fail(b, "%s: cs reference span != CIGAR span (%ld)", qname, rspan); break; }
+      if (q - lead != l_seq - trail - lead) { rc = fail(b, "%s: cs query span != aligned query span (%ld)", qname, q - lead); break; }
+      /* append the read */
+      if (n_reads + 1 > b->cap_reads) {
+        size_t cr = b->cap_reads ? b->cap_reads + b->cap_reads / 2 + 1024 : 4096;
+#define RE(ptr, type) do { type* np_ = (type*)realloc(ptr, cr * sizeof(type)); if (!np_) rc = fail(b, "out of memory%s (%ld)", NULL, (long)cr); else ptr = np_; } while (0)
+        RE(b->tstart, int32_t); RE(b->tend, int32_t); RE(b->qstart, int32_t); RE(b->qlen, int32_t); RE(b->mapq, uint8_t);
+        RE(b->flags, uint8_t); RE(b->qname_id, uint32_t); RE(b->n_ops, uint32_t); RE(b->seq_off, uint64_t);
+        RE(b->bq_off, uint64_t); RE(b->op_off, uint64_t);
+#undef RE
+        if (rc) break;
+        b->cap_reads = cr;
+      }
+      size_t sb = ((size_t)l_seq + 3) / 4, sb16 = (sb + 15) & ~(size_t)15, qb16 = ((size_t)l_seq + 15) & ~(size_t)15;
+      GROW(b->seq, b->cap_seq, n_seq + sb16 + 16, uint8_t);
+      GROW(b->bq, b->cap_bq, n_bq + qb16 + 16, uint8_t);
+      memset(b->seq + n_seq, 0, sb16);
+      for (int32_t i = 0; i < l_seq; i++) { uint8_t cd = codes[i] == 0xff ? 0 : codes[i]; b->seq[n_seq + (i >> 2)] |= (uint8_t)(cd << (2 * (i & 3))); }
+      memcpy(b->bq + n_bq, qual, (size_t)l_seq);
+      memset(b->bq + n_bq + l_seq, 0, qb16 - (size_t)l_seq);
+      int64_t id = qt_get(&b->qt, qname, strlen(qname));
+      if (id < 0) { rc = fail(b, "out of memory%s (%ld)", NULL, 0); break; }
+      b->tstart[n_reads] = pos; b->tend[n_reads] = pos + rspan; b->qstart[n_reads] = lead; b->qlen[n_reads] = l_seq;
+      b->mapq[n_reads] = (uint8_t)mapq; b->flags[n_reads] = 0; b->qname_id[n_reads] = (uint32_t)id;
+      b->seq_off[n_reads] = n_seq; b->bq_off[n_reads] = n_bq; b->op_off[n_reads] = op0; b->n_ops[n_reads] = (uint32_t)(n_ops - op0);
+      n_seq += sb16; n_bq += qb16; n_reads++;
+    }
+    free(codes); free(s.buf);
+    if (rc) return rc;
+  }
+finish:
+  if (n_seq == 0) { GROW(b->seq, b->cap_seq, 16, uint8_t); memset(b->seq, 0, 16); n_seq = 16; }
+  if (n_bq == 0) { GROW(b->bq, b->cap_bq, 16, uint8_t); memset(b->bq, 0, 16); n_bq = 16; }
+  out->n_reads = n_reads;
+  out->tstart = b->tstart; out->tend = b->tend; out->qstart = b->qstart; out->qlen = b->qlen; out->mapq = b->mapq;
+  out->flags = b->flags; out->qname_id = b->qname_id; out->seq_off = b->seq_off; out->bq_off = b->bq_off;
+  out->op_off = b->op_off; out->n_ops = b->n_ops; out->seq = b->seq; out->seq_bytes = n_seq; out->bq = b->bq;
+  out->bq_bytes = n_bq; out->ops = b->ops; out->n_ops_total = n_ops;
+  b->batch = *out;
+  return HM_OK;
+}

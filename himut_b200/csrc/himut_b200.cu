@@ -632,6 +632,31 @@ int hm_set_reference(hm_ctx* ctx, const uint8_t* refseq, size_t ref_len) {
   return HM_OK;
 }
 
+/* reference-genome trinucleotide counts of one contig (reflib.get_chrom_tricount) */
+int hm_ref_tricounts(hm_ctx* ctx, const uint8_t* refseq, size_t ref_len, int64_t tri[HM_TRI_BINS]) {
+  if (!ctx || !tri || (!refseq && ref_len)) return HM_ERR_ARG;
+  CU(cudaSetDevice(ctx->device));
+  memset(tri, 0, sizeof(int64_t) * HM_TRI_BINS);
+  t_reset(ctx);
+  int rc = upload(ctx, ctx->b_ref, refseq, ref_len);
+  ctx->ref_len = 0;
+  if (rc) return rc;
+  CU(ctx->b_norm_out.ensure(sizeof(NormOut)));
+  CU(cudaMemsetAsync(ctx->b_norm_out.p, 0, sizeof(NormOut), ctx->stream));
+  if (ref_len > 2) {
+    t_begin(ctx, "k_ref_tricounts");
+    k_ref_tricounts<<<148 * 8, 256, 0, ctx->stream>>>(ctx->b_ref.as<uint8_t>(), (uint64_t)ref_len, ctx->b_norm_out.as<NormOut>()->ccs_tri);
+    t_end(ctx);
+    CU(cudaGetLastError());
+  }
+  NormOut h;
+  CU(cudaMemcpyAsync(&h, ctx->b_norm_out.p, sizeof(NormOut), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  t_collect(ctx);
+  for (int i = 0; i < HM_TRI_BINS; i++) tri[i] = (int64_t)h.ccs_tri[i];
+  return HM_OK;
+}
+
 int hm_last_timing(hm_ctx* ctx, float* total_ms, int* n_launches) {
   if (!ctx) return HM_ERR_ARG;
   if (total_ms) *total_ms = ctx->last_total_ms;

@@ -856,6 +856,48 @@ __global__ void __launch_bounds__(HM_TW + 32 * HM_NPROD, 1) k_norm_tiles_tma(Dev
   }
 }
 
+// ============================================================================ k_ref_tricounts
+// reflib.get_chrom_tricount (src/himut/reflib.py:11-33): for i in range(len(seq) - 2), skip when
+// seq[i] == "N" (the *first* base of the window), otherwise count the pyrimidine-centred
+// trinucleotide seq[i:i+3] (reverse complement when the centre is A/G; anything that is not
+// upper-case A/C/G/T makes a key outside mutlib.tri_lst, tallied in bin 32).
+// Streaming histogram: 16 windows per thread from one 16-byte load + 2 halo bytes, per-warp bins.
+__global__ void __launch_bounds__(256) k_ref_tricounts(const uint8_t* seq, uint64_t n, unsigned long long* out) {
+  __shared__ unsigned int s_bins[8][HM_TRI_BINS + 1];
+  for (int i = threadIdx.x; i < 8 * (HM_TRI_BINS + 1); i += blockDim.x) (&s_bins[0][0])[i] = 0;
+  __syncthreads();
+  unsigned int* bins = s_bins[threadIdx.x >> 5];
+  const uint64_t n_win = n >= 2 ? n - 2 : 0;
+  for (uint64_t base = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * 16; base < n_win; base += (uint64_t)gridDim.x * blockDim.x * 16) {
+    uint8_t c[18];
+    if (base + 18 <= n && ((uintptr_t)(seq + base) & 15) == 0) {
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(seq + base));
+      const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int k = 0; k < 16; k++) c[k] = (uint8_t)(w[k >> 2] >> (8 * (k & 3)));
+      c[16] = __ldg(seq + base + 16); c[17] = __ldg(seq + base + 17);
+    } else {
+#pragma unroll
+      for (int k = 0; k < 18; k++) c[k] = base + k < n ? __ldg(seq + base + k) : (uint8_t)0;
+    }
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+      if (base + k >= n_win || c[k] == 'N') continue;
+      int t0 = tri_code(c[k]), t1 = tri_code(c[k + 1]), t2 = tri_code(c[k + 2]);
+      if (t1 == 0 || t1 == 2) { const int u0 = t2 < 0 ? -1 : 3 - t2, u2 = t0 < 0 ? -1 : 3 - t0; t0 = u0; t1 = 3 - t1; t2 = u2; }
+      const int bin = (t0 < 0 || t1 < 0 || t2 < 0) ? 32 : t0 * 8 + (t1 == 3 ? 4 : 0) + t2;
+      atomicAdd(&bins[bin], 1u);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < HM_TRI_BINS; i += blockDim.x) {
+    unsigned long long t = 0;
+#pragma unroll
+    for (int wv = 0; wv < 8; wv++) t += s_bins[wv][i];
+    if (t) atomicAdd(out + i, t);
+  }
+}
+
 struct hm_ctx;
 static int hm_normcounts_impl(hm_ctx* ctx, const uint8_t* refseq, size_t ref_len, const hm_chunk* chunks, size_t n_chunks,
                               int64_t* ccs_tri, int64_t* ref_tri, int64_t* log, int64_t* n_alt_tie);

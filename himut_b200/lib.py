@@ -19,7 +19,7 @@ EXPORTS = [
     "hm_abi_version", "hm_create", "hm_destroy", "hm_last_error", "hm_set_params", "hm_set_site_sets",
     "hm_set_phase_sets", "hm_upload_batch", "hm_call_chunks", "hm_call_batch", "hm_normcounts_chunks",
     "hm_read_stats", "hm_last_timing", "hm_last_kernel_times", "hm_set_stream", "hm_host_register",
-    "hm_host_unregister", "hm_abi_sizeof", "hm_last_records", "hm_qname_seen", "hm_set_reference",
+    "hm_host_unregister", "hm_abi_sizeof", "hm_last_records", "hm_qname_seen", "hm_set_reference", "hm_ref_tricounts",
 ]
 
 
@@ -58,6 +58,7 @@ def load():
         lib.hm_last_records.argtypes = [vp, vp, sz, C.POINTER(sz)]
         lib.hm_qname_seen.argtypes = [vp, vp, sz, C.POINTER(sz)]
         lib.hm_set_reference.argtypes = [vp, vp, sz]
+        lib.hm_ref_tricounts.argtypes = [vp, vp, sz, vp]
         lib.hm_set_stream.argtypes = [vp, vp]
         lib.hm_host_register.argtypes = [vp, vp, sz]
         lib.hm_host_unregister.argtypes = [vp, vp]
@@ -199,6 +200,14 @@ class Context:
                    ins_len=np.zeros(n, np.int32), del_len=np.zeros(n, np.int32), n_mismatch=np.zeros(n, np.int32))
         self._chk(self.lib.hm_read_stats(self.h, *[_p(out[k]) for k in
                                                    ("bq_total", "n_match", "n_sub", "ins_len", "del_len", "n_mismatch")]))
+        return out
+
+    def ref_tricounts(self, refseq):
+        """reference trinucleotide counts of one contig -> int64[33] (reflib.get_chrom_tricount)"""
+        ref = np.frombuffer(refseq, dtype=np.uint8)
+        out = np.zeros(abi.TRI_BINS, np.int64)
+        self._chk(self.lib.hm_ref_tricounts(self.h, _p(ref), ref.size, _p(out)))
+        self._ref_obj = None
         return out
 
     def qname_seen(self):

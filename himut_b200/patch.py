@@ -9,10 +9,12 @@ CLI, header, thresholds, natsort and writers stay the reference's own code.
 def install():
     import himut.caller
     import himut.normcounts
+    import himut.reflib
 
-    from . import caller, normcounts
+    from . import caller, normcounts, reflib
     himut.caller.get_somatic_substitutions = caller.get_somatic_substitutions
     himut.normcounts.get_callable_tricounts = normcounts.get_callable_tricounts
+    himut.reflib.get_chrom_tricount = reflib.get_chrom_tricount  # reflib.py:42-52 starmap target
     return himut
 
 

@@ -270,6 +270,10 @@ int hm_normcounts_chunks(hm_ctx* ctx, const uint8_t* refseq, size_t ref_len,
  * count distinct names across them.                                                          */
 int hm_qname_seen(hm_ctx* ctx, uint8_t* out, size_t cap, size_t* n);
 
+/* reference-genome trinucleotide counts of one contig, bins as above (replaces
+ * reflib.get_chrom_tricount, src/himut/reflib.py:11-33: windows whose first base is "N" are skipped) */
+int hm_ref_tricounts(hm_ctx* ctx, const uint8_t* refseq, size_t ref_len, int64_t tri[HM_TRI_BINS]);
+
 /* per-read statistics of the resident batch, for parity tests of the expansion kernel
  * (cslib.cs2subindel / bamlib.get_blast_sequence_identity / BAM.get_qv):
  * bq_total = sum of all base qualities, n_match / n_sub / ins_len / del_len as in

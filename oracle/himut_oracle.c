@@ -23,6 +23,7 @@
  *                                                              src/himut/caller.py:243-641
  *   `normcounts` worker              normcounts.get_callable_tricounts, update_tri2count,
  *                                    get_tri_context           src/himut/normcounts.py:49-110,240-419
+ *   reference tri counts             reflib.get_chrom_tricount src/himut/reflib.py:11-33
  * It keeps the reference's dataflow — per chunk, per read in fetch order, per-position
  * per-allele BQ lists in append order, left-to-right fp64 sums — so that the order-sensitive
  * results (PL, GQ) are reproduced bit for bit.  The three per-BQ log10 tables and the four
@@ -726,4 +727,23 @@ done:
   if (n_alt_tie) *n_alt_tie = ties;
   if (rc != HM_OK) return rc;
   return bq_zero ? HM_ERR_BQ_ZERO : HM_OK;
+}
+
+/* ---------------------------------------------------------------- reference tri counts */
+/* reflib.get_chrom_tricount (src/himut/reflib.py:11-33) */
+int orc_ref_tricounts(const uint8_t* seq, size_t n, int64_t tri[HM_TRI_BINS]) {
+  memset(tri, 0, sizeof(int64_t) * HM_TRI_BINS);
+  for (size_t i = 0; i + 2 < n; i++) {
+    if (seq[i] == 'N') continue;
+    int t[3];
+    for (int k = 0; k < 3; k++) {
+      switch (seq[i + k]) { case 'A': t[k] = 0; break; case 'C': t[k] = 1; break; case 'G': t[k] = 2; break; case 'T': t[k] = 3; break; default: t[k] = -1; }
+    }
+    if (t[1] == 0 || t[1] == 2) {
+      int u0 = t[2] < 0 ? -1 : 3 - t[2], u1 = 3 - t[1], u2 = t[0] < 0 ? -1 : 3 - t[0];
+      t[0] = u0; t[1] = u1; t[2] = u2;
+    }
+    tri[(t[0] < 0 || t[1] < 0 || t[2] < 0) ? 32 : t[0] * 8 + (t[1] == 3 ? 4 : 0) + t[2]]++;
+  }
+  return HM_OK;
 }

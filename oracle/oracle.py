@@ -95,3 +95,12 @@ def normcounts_chunks(params, batch, refseq, chunks, common=None, pon=None, phas
     if rc != 0:
         raise RuntimeError("orc_normcounts_chunks failed: %d" % rc)
     return ccs, rt, log, ties.value
+
+
+def ref_tricounts(refseq):
+    """-> int64[33] (reflib.get_chrom_tricount)"""
+    ref = np.frombuffer(refseq, dtype=np.uint8)
+    out = np.zeros(abi.TRI_BINS, np.int64)
+    rc = lib().orc_ref_tricounts(_p(ref), C.c_size_t(ref.size), _p(out))
+    assert rc == 0
+    return out
