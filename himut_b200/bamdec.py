@@ -1,0 +1,117 @@
+"""ctypes binding of the native BAM region decoder (include/himut_io.h, csrc/bamdec.c).
+
+The GPU workers read their regions through this module: BGZF inflate on a pthread pool, record
+parse and cs -> op stream in C, straight into the packed batch the C ABI takes.  It replaces
+pysam's fetch + bamlib.BAM.__init__ + cslib.cs2tuple of the reference
+(src/himut/caller.py:299, bamlib.py:15-32, cslib.py:7-44).  bamio.py / pack.py remain the
+readable specification of the same rules (tests/test_bamdec.py compares the two byte for byte)
+and provide the BAM writer used by the tests and tools.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import abi, pack
+
+_LIB = None
+EXPORTS = ["hm_bam_open", "hm_bam_close", "hm_bam_error", "hm_bam_header_text", "hm_bam_n_refs", "hm_bam_ref_name",
+           "hm_bam_ref_len", "hm_bam_read_batch", "hm_bam_n_qnames", "hm_bam_qname"]
+
+
+def lib_path():
+    return os.path.join(os.path.dirname(os.path.abspath(__file__)), "libhimut_io.so")
+
+
+def load():
+    global _LIB
+    if _LIB is None:
+        path = lib_path()
+        if not os.path.exists(path):
+            raise RuntimeError("%s is missing: run `python __graft_entry__.py` to build it" % path)
+        lib = C.CDLL(path)
+        vp = C.c_void_p
+        lib.hm_bam_open.argtypes = [C.c_char_p, C.POINTER(vp)]
+        lib.hm_bam_close.argtypes = [vp]
+        lib.hm_bam_close.restype = None
+        lib.hm_bam_error.argtypes = [vp]
+        lib.hm_bam_error.restype = C.c_char_p
+        lib.hm_bam_header_text.argtypes = [vp]
+        lib.hm_bam_header_text.restype = C.c_char_p
+        lib.hm_bam_n_refs.argtypes = [vp]
+        lib.hm_bam_ref_name.argtypes = [vp, C.c_int]
+        lib.hm_bam_ref_name.restype = C.c_char_p
+        lib.hm_bam_ref_len.argtypes = [vp, C.c_int]
+        lib.hm_bam_read_batch.argtypes = [vp, C.c_int, C.c_int32, C.c_int32, C.c_int, C.POINTER(abi.hm_read_batch)]
+        lib.hm_bam_n_qnames.argtypes = [vp]
+        lib.hm_bam_n_qnames.restype = C.c_uint32
+        lib.hm_bam_qname.argtypes = [vp, C.c_uint32]
+        lib.hm_bam_qname.restype = C.c_char_p
+        _LIB = lib
+    return _LIB
+
+
+def default_threads():
+    t = os.environ.get("HIMUT_B200_DECODE_THREADS")
+    if t:
+        return max(1, int(t))
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def _view(ptr, n, dtype):
+    if n == 0 or not ptr:
+        return np.zeros(0, dtype)
+    dt = np.dtype(dtype)
+    buf = (C.c_char * (n * dt.itemsize)).from_address(ptr)
+    return np.frombuffer(buf, dtype=dt, count=n)
+
+
+class NativeBam:
+    """one open BAM (+ .bai); read_batch() returns an abi.ReadBatch copied out of the handle"""
+
+    def __init__(self, path, threads=None):
+        self.lib = load()
+        self.h = C.c_void_p()
+        rc = self.lib.hm_bam_open(os.fsencode(path), C.byref(self.h))
+        if rc != 0:
+            raise IOError("cannot open %s as BAM" % path)
+        self.threads = threads or default_threads()
+        self.references = [self.lib.hm_bam_ref_name(self.h, i).decode() for i in range(self.lib.hm_bam_n_refs(self.h))]
+        self.lengths = [self.lib.hm_bam_ref_len(self.h, i) for i in range(len(self.references))]
+        self.header_text = self.lib.hm_bam_header_text(self.h).decode()
+
+    def read_batch(self, chrom, start, end, copy=True):
+        if chrom not in self.references:
+            raise KeyError(chrom)
+        s = abi.hm_read_batch()
+        rc = self.lib.hm_bam_read_batch(self.h, self.references.index(chrom), int(max(start, 0)), int(end), self.threads, C.byref(s))
+        if rc != 0:
+            raise pack.BatchFormatError(self.lib.hm_bam_error(self.h).decode())
+        n = int(s.n_reads)
+        cp = (lambda a: a.copy()) if copy else (lambda a: a)
+        sizes = {"seq": int(s.seq_bytes), "bq": int(s.bq_bytes), "ops": int(s.n_ops_total)}
+        arrays = {}
+        for name, dt in abi.ReadBatch._FIELDS:
+            arrays[name] = cp(_view(getattr(s, name), sizes.get(name, n), dt))
+        return abi.ReadBatch(keepalive=None if copy else self, **arrays)
+
+    def n_qnames(self):
+        return int(self.lib.hm_bam_n_qnames(self.h))
+
+    def qname(self, i):
+        v = self.lib.hm_bam_qname(self.h, i)
+        return None if v is None else v.decode()
+
+    def close(self):
+        if self.h:
+            self.lib.hm_bam_close(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

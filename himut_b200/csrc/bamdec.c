@@ -21,7 +21,7 @@
 #include <string.h>
 #include <zlib.h>
 
-#include "../../include/himut_b200.h"
+#include "../../include/himut_io.h"
 
 typedef struct {
   char* name;

@@ -4,7 +4,7 @@ import os
 
 import numpy as np
 
-from . import abi, bamio, lib, pack
+from . import abi, bamdec, lib
 
 _CTX = None
 _CTX_PID = None
@@ -59,15 +59,15 @@ class RegionSource:
     """decodes the records a group of chunks fetches into one packed batch"""
 
     def __init__(self, bam_file):
-        self.reader = bamio.BamReader(bam_file)
-        self.qnames = {}
+        # native decoder (csrc/bamdec.c): threaded BGZF inflate, record parse and cs -> ops in C;
+        # query-name ids are interned per handle, so they stay global across groups
+        # (num_ccs counts distinct names per contig)
+        self.reader = bamdec.NativeBam(bam_file)
 
     def batch(self, chrom, chunkloci, phase_sets=None):
         lo = min(s for _, s, _e in chunkloci)
         hi = max(e for _, _s, e in chunkloci)
-        bb = pack.BatchBuilder()
-        bb.qnames = self.qnames  # ids stay global across groups: num_ccs counts distinct names
-        batch = bamio.read_batch(self.reader, chrom, lo, hi, builder=bb)
+        batch = self.reader.read_batch(chrom, lo, hi, copy=False)
         table = batch.chunk_table([(s, e) for _, s, e in chunkloci], phase_sets)
         return batch, table
 

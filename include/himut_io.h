@@ -1,0 +1,56 @@
+/*
+ * himut_io.h — C ABI of the native BAM region decoder (host side, no CUDA):
+ * himut_b200/csrc/bamdec.c -> himut_b200/libhimut_io.so.
+ *
+ * SURVEY.md §8(f) row 1.  It replaces, for the GPU workers, what the reference does per record
+ * through pysam / htslib and Python:
+ *     alignments.fetch(chrom, start, end)          reference src/himut/caller.py:267,299
+ *                                                  src/himut/normcounts.py:259,292
+ *     bamlib.BAM.__init__ (9 attribute pulls)      reference src/himut/bamlib.py:15-32
+ *     cslib.cs2lst / cs2tuple (regex over cs:Z)    reference src/himut/cslib.py:7-44
+ * and hands back the packed structure-of-arrays batch of himut_b200.h directly, so no Python
+ * object is created per record.  BGZF blocks are inflated by a pthread pool (zlib).
+ *
+ * Conventions: every function returns an int status (HM_OK == 0, codes of himut_b200.h);
+ * hm_bam_error() gives the message.  A handle is single-threaded.  The arrays of a decoded
+ * batch are owned by the handle and stay valid until the next hm_bam_read_batch / close.
+ */
+#ifndef HIMUT_IO_H
+#define HIMUT_IO_H
+
+#include "himut_b200.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct hm_bam hm_bam;
+
+/* open <path> (and <path>.bai when it exists: without it every query scans from the first
+ * record), read the header text and the @SQ table (bamlib.get_tname2tsize, bamlib.py:109-129) */
+int hm_bam_open(const char* path, hm_bam** out);
+void hm_bam_close(hm_bam* b);
+const char* hm_bam_error(const hm_bam* b);
+
+const char* hm_bam_header_text(const hm_bam* b); /* SAM header text, as str(alignments.header) */
+int hm_bam_n_refs(const hm_bam* b);
+const char* hm_bam_ref_name(const hm_bam* b, int i);
+int hm_bam_ref_len(const hm_bam* b, int i);
+
+/* the records of contig `rid` overlapping the 0-based half-open window [start, end), in file
+ * order, each once (pysam fetch semantics, caller.py:299); secondary records (0x100) are
+ * dropped as bamlib.BAM.__init__ drops them (bamlib.py:17), supplementary ones are kept.
+ * Inputs the reference would crash on are rejected with HM_ERR_ARG and a message: no cs:Z tag,
+ * missing qualities, hard clips, a read base outside A/C/G/T under a cs match or as the
+ * substituted base, cs spans that disagree with the CIGAR.  `threads` = inflate threads. */
+int hm_bam_read_batch(hm_bam* b, int rid, int32_t start, int32_t end, int threads, hm_read_batch* out);
+
+/* query names are interned per handle: qname_id of a batch indexes this table, ids are stable
+ * across hm_bam_read_batch calls (m.num_ccs counts distinct names per contig, caller.py:318-320) */
+uint32_t hm_bam_n_qnames(const hm_bam* b);
+const char* hm_bam_qname(const hm_bam* b, uint32_t id);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,131 @@
+"""Native BAM decoder (csrc/bamdec.c, include/himut_io.h) against the Python specification
+(bamio.py + pack.py): same packed batch byte for byte, same fetch rule, same rejections."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import cases
+from himut_b200 import bamdec, bamio, pack, synth
+
+
+def _same(a, b):
+    for name, _ in a._FIELDS:
+        x, y = getattr(a, name), getattr(b, name)
+        assert x.shape == y.shape and np.array_equal(x, y), name
+
+
+def test_io_library_exports_every_declared_symbol():
+    lib = C.CDLL(bamdec.lib_path())
+    hdr = open(os.path.join(os.path.dirname(cases.GOLDEN_DIR), "..", "include", "himut_io.h")).read()
+    import re
+    declared = set(re.findall(r"\b(hm_bam_\w+)\s*\(", hdr))
+    assert declared == set(bamdec.EXPORTS)
+    for name in declared:
+        assert hasattr(lib, name), name
+
+
+@pytest.mark.parametrize("threads", [1, 4])
+def test_native_batch_equals_python_batch(tmp_path, threads):
+    d = synth.generate(300_000, seed=11)
+    path = str(tmp_path / "t.bam")
+    bamio.write_batch_bam(path, "chr1", 300_000, d.batch)
+    nb = bamdec.NativeBam(path, threads=threads)
+    rd = bamio.BamReader(path)
+    assert nb.references == rd.references and nb.lengths == rd.lengths and nb.header_text == rd.header_text
+    qnames = {}  # the handle interns query names across windows; give the Python builder the same table
+    for s, e in [(0, 300_000), (1, 200_000), (200_000, 299_998), (123_456, 123_457), (299_990, 300_000), (0, 1)]:
+        bb = pack.BatchBuilder()
+        bb.qnames = qnames
+        _same(nb.read_batch("chr1", s, e), bamio.read_batch(rd, "chr1", s, e, builder=bb))
+    whole = nb.read_batch("chr1", 0, 300_000)
+    assert cases.batch_digest(whole) == cases.batch_digest(d.batch)
+    assert nb.n_qnames() == len(set(d.batch.qname_id.tolist()))
+    assert nb.qname(int(whole.qname_id[5])) == "read5"
+    nb.close(); rd.close()
+
+
+def test_qname_ids_are_stable_across_windows(tmp_path):
+    d = synth.generate(200_000, seed=12)
+    path = str(tmp_path / "t.bam")
+    bamio.write_batch_bam(path, "chr1", 200_000, d.batch)
+    nb = bamdec.NativeBam(path, threads=2)
+    a = nb.read_batch("chr1", 0, 120_000)
+    b = nb.read_batch("chr1", 100_000, 200_000)
+    names_a = {nb.qname(int(i)) for i in a.qname_id}
+    names_b = {nb.qname(int(i)) for i in b.qname_id}
+    both = names_a & names_b
+    assert both  # reads spanning the seam appear in both windows under the same id
+    ids_a = {nb.qname(int(i)): int(i) for i in a.qname_id}
+    ids_b = {nb.qname(int(i)): int(i) for i in b.qname_id}
+    assert all(ids_a[n] == ids_b[n] for n in both)
+
+
+def _write(path, records, reflen=1000):
+    w = bamio.BamWriter(path, [("chr1", reflen), ("chr2", reflen)])
+    for r in records:
+        w.add(**r)
+    w.close()
+
+
+def _rec(pos=10, cigar=((0, 8),), seq="ACGTACGT", cs=":8", flag=0, qual=None, ref_id=0, qname="q", extra=()):
+    tags = [("tp", "A", "P")] + ([("cs", "Z", cs)] if cs is not None else []) + list(extra)
+    return dict(ref_id=ref_id, pos=pos, qname=qname, flag=flag, mapq=60, cigar=list(cigar), seq=seq,
+                qual=bytes([40] * len(seq)) if qual is None else qual, tags=tags)
+
+
+def test_soft_clips_secondary_supplementary_and_contigs(tmp_path):
+    path = str(tmp_path / "m.bam")
+    _write(path, [
+        _rec(pos=10, cigar=((4, 2), (0, 6), (4, 1)), seq="NNACGTACN", cs=":6", qname="clip"),
+        _rec(pos=12, flag=0x100, qname="secondary", cs=None),           # dropped before the cs lookup
+        _rec(pos=14, flag=0x800, qname="supp", cs=":3*ag:2+tt-ca:0", cigar=((0, 6), (1, 2), (2, 2)), seq="ACGGACTT"),
+        _rec(pos=20, cs="=ACGT*ct=CGT", seq="ACGTTCGT", qname="longform"),
+        _rec(pos=5, ref_id=1, qname="other"),
+    ])
+    nb = bamdec.NativeBam(path, threads=1)
+    rd = bamio.BamReader(path)
+    qnames = {}
+    for chrom in ("chr1", "chr2"):
+        for s, e in [(0, 1000), (15, 16), (0, 11), (27, 40)]:
+            bb = pack.BatchBuilder()
+            bb.qnames = qnames
+            _same(nb.read_batch(chrom, s, e), bamio.read_batch(rd, chrom, s, e, builder=bb))
+    b = nb.read_batch("chr1", 0, 1000)
+    assert [nb.qname(int(i)) for i in b.qname_id] == ["clip", "supp", "longform"]
+    assert b.qstart.tolist() == [2, 0, 0] and b.qlen.tolist() == [9, 8, 8]
+
+
+@pytest.mark.parametrize("bad", [
+    dict(cs=None),                                      # KeyError in BAM.__init__
+    dict(cigar=((5, 3), (0, 8))),                       # hard clip
+    dict(seq="ACNTACGT"),                               # N under a match
+    dict(cs=":2*an:5"),                                 # substitution to N
+    dict(cs=":9"),                                      # cs longer than the read
+    dict(cs=":7"),                                      # cs / CIGAR span mismatch
+    dict(cs=":4~gt12ag:4"),                             # intron token
+    dict(qual=b"\xff" * 8),                             # missing qualities
+])
+def test_rejections_match_the_python_specification(tmp_path, bad):
+    path = str(tmp_path / "b.bam")
+    _write(path, [_rec(**bad)])
+    nb = bamdec.NativeBam(path, threads=1)
+    with pytest.raises(pack.BatchFormatError):
+        nb.read_batch("chr1", 0, 1000)
+    with pytest.raises(pack.BatchFormatError):
+        bamio.read_batch(bamio.BamReader(path), "chr1", 0, 1000)
+
+
+def test_without_index_and_empty_contig(tmp_path):
+    d = synth.generate(60_000, seed=13)
+    path = str(tmp_path / "t.bam")
+    bamio.write_batch_bam(path, "chr1", 60_000, d.batch)
+    os.remove(path + ".bai")
+    nb = bamdec.NativeBam(path, threads=2)
+    _same(nb.read_batch("chr1", 20_000, 30_000), bamio.read_batch(bamio.BamReader(path), "chr1", 20_000, 30_000))
+    path2 = str(tmp_path / "e.bam")
+    _write(path2, [_rec(ref_id=1)])
+    nb2 = bamdec.NativeBam(path2)
+    b = nb2.read_batch("chr1", 0, 1000)
+    assert b.n_reads == 0 and b.seq.size == 16 and b.bq.size == 16
