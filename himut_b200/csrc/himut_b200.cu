@@ -8,6 +8,7 @@
 // Everything per base / per read / per site runs in the kernels of kernels.cuh and
 // normcounts.cuh.  There is no CPU fallback: without a CUDA device hm_create fails.
 #include <algorithm>
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -21,6 +22,7 @@
 
 #include "kernels.cuh"
 #include "normcounts.cuh"
+#include "normfast.cuh"
 
 namespace {
 
@@ -56,9 +58,11 @@ struct hm_ctx {
   uint64_t n_reads = 0, n_ops_total = 0, seq_bytes = 0, bq_bytes = 0;
   uint32_t max_qname_id = 0;
   std::vector<int32_t> h_pmax;
+  std::vector<uint32_t> h_tix_off; // per read: first entry of its tile index (k_tile_index)
+  uint64_t n_tix = 0;
   DevBuf b_tstart, b_tend, b_qstart, b_qlen, b_mapq, b_flags, b_qname, b_seq_off, b_bq_off, b_op_off, b_n_ops,
       b_seq, b_bq, b_ops, b_op_t, b_op_q, b_mm, b_bq_total, b_n_match, b_n_sub, b_ins_len, b_del_len, b_n_mm, b_gate,
-      b_pmax;
+      b_pmax, b_tix_off, b_tix;
   DevBatch db;
   // sets / phase
   DevBuf b_common, b_pon, b_hpos, b_href, b_halt, b_hbit, b_set_off;
@@ -79,6 +83,9 @@ struct hm_ctx {
   float last_total_ms = 0.f;
   int last_launches = 0;
   size_t ref_len = 0; // length of the contig left resident by hm_set_reference (0: none)
+  NormCert cert;      // certified-verdict constants of the normcounts fast pass
+  unsigned long long last_norm_sites = 0; // positions the last normcounts call evaluated exactly
+  DevBuf b_sites;
 };
 
 namespace {
@@ -136,6 +143,39 @@ void make_dev_params(hm_ctx* ctx) {
   d.min_ref_count = p.min_ref_count; d.min_alt_count = p.min_alt_count; d.min_hap_count = p.min_hap_count;
   d.phase = p.phase; d.non_human_sample = p.non_human_sample; d.create_panel_of_normals = p.create_panel_of_normals;
   d.min_sequence_identity = p.min_sequence_identity; d.min_trim = p.min_trim; d.md_threshold = p.md_threshold;
+}
+
+// Constants of the certified homref verdict at pure positions (normfast.cuh).  The derivation
+// assumes the three per-BQ tables are the reference's own (gtlib.py:47-69); that is verified here
+// numerically, and the fast pass is switched off for anything else.
+void make_norm_cert(hm_ctx* ctx) {
+  const hm_params& p = ctx->params;
+  NormCert& c = ctx->cert;
+  memset(&c, 0, sizeof(c));
+  const double L2 = 0.30102999566398119521; // log10(2)
+  const double f1 = -p.lut_hom[1];
+  bool ok = p.min_bq >= 1 && p.min_bq <= 128 && p.min_gq <= 99 && f1 > 0.0 && f1 < 1.0;
+  for (int bq = 1; bq < 256 && ok; bq++) {
+    const double hom = p.lut_hom[bq], het = p.lut_het[bq], err = p.lut_err[bq];
+    if (!(hom <= 0.0) || !(fabs(het - (hom - L2)) <= 1e-9) || !(fabs(err + (double)bq / 30.0) <= 1e-9)) ok = false;
+    if (!(-hom <= f1 * (double)(255 - bq) / 254.0 + 1e-12)) ok = false; // chord bound of the convex -lut_hom
+  }
+  for (int k = 0; k < 4 && ok; k++) if (!(p.log10_prior[k] == p.log10_prior[k]) || fabs(p.log10_prior[k]) > 1e6) ok = false;
+  if (!ok) return;
+  const double margin = 1e-6;
+  c.need = (p.min_gq > 0 ? (double)p.min_gq : 0.0) + margin;
+  const double c_het = 10.0 * (p.log10_prior[0] - p.log10_prior[1]);
+  double n_min = ceil((c.need + margin - c_het) / (10.0 * L2));
+  if (n_min < 1.0) n_min = 1.0;
+  if (n_min > 1e6) return;
+  c.n_min = (int32_t)n_min;
+  c.a_bq = 10.0 / 30.0 * (1.0 - 1e-12);
+  c.a_x = 10.0 * f1 / 254.0 * (1.0 + 1e-12);
+  c.c_oth = 10.0 * (p.log10_prior[0] - std::max(p.log10_prior[2], p.log10_prior[3])) - margin;
+  c.ia_bq = (long long)floor(c.a_bq * 1048576.0);
+  c.ia_x = (long long)ceil(c.a_x * 1048576.0);
+  c.i_need = (long long)ceil((c.need - c.c_oth) * 1048576.0);
+  c.enabled = 1;
 }
 
 int check_ready(hm_ctx* ctx, const hm_chunk* chunks, size_t n_chunks) {
@@ -213,10 +253,10 @@ void hm_destroy(hm_ctx* ctx) {
   DevBuf* bufs[] = {&ctx->b_tstart, &ctx->b_tend, &ctx->b_qstart, &ctx->b_qlen, &ctx->b_mapq, &ctx->b_flags, &ctx->b_qname,
                     &ctx->b_seq_off, &ctx->b_bq_off, &ctx->b_op_off, &ctx->b_n_ops, &ctx->b_seq, &ctx->b_bq, &ctx->b_ops,
                     &ctx->b_op_t, &ctx->b_op_q, &ctx->b_mm, &ctx->b_bq_total, &ctx->b_n_match, &ctx->b_n_sub,
-                    &ctx->b_ins_len, &ctx->b_del_len, &ctx->b_n_mm, &ctx->b_gate, &ctx->b_pmax, &ctx->b_common, &ctx->b_pon,
+                    &ctx->b_ins_len, &ctx->b_del_len, &ctx->b_n_mm, &ctx->b_gate, &ctx->b_pmax, &ctx->b_tix_off, &ctx->b_tix, &ctx->b_common, &ctx->b_pon,
                     &ctx->b_hpos, &ctx->b_href, &ctx->b_halt, &ctx->b_hbit, &ctx->b_set_off, &ctx->b_chunks,
                     &ctx->b_pair_off, &ctx->b_pair_hap, &ctx->b_qseen, &ctx->b_keys, &ctx->b_keys_sorted, &ctx->b_cub,
-                    &ctx->b_records, &ctx->b_counters, &ctx->b_ref, &ctx->b_norm_out, &ctx->b_lut, &ctx->b_tile_off, &ctx->b_agg, &ctx->b_geom, &ctx->b_bidx};
+                    &ctx->b_records, &ctx->b_counters, &ctx->b_ref, &ctx->b_norm_out, &ctx->b_lut, &ctx->b_tile_off, &ctx->b_agg, &ctx->b_geom, &ctx->b_bidx, &ctx->b_sites};
   for (DevBuf* b : bufs) b->release();
   if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
   for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
@@ -257,6 +297,7 @@ int hm_set_params(hm_ctx* ctx, const hm_params* params) {
   CU(cudaSetDevice(ctx->device));
   ctx->params = *params;
   make_dev_params(ctx);
+  make_norm_cert(ctx);
   DevTables t;
   memcpy(t.lut[0], params->lut_hom, sizeof(t.lut[0]));
   memcpy(t.lut[1], params->lut_het, sizeof(t.lut[1]));
@@ -316,6 +357,8 @@ int hm_upload_batch(hm_ctx* ctx, const hm_read_batch* b) {
   if ((b->seq_bytes & 15) || (b->bq_bytes & 15)) return fail(ctx, HM_ERR_ARG, "seq / bq buffers must be padded to 16 bytes");
   // structural validation (cheap, O(reads)); the kernels binary-search on these invariants
   ctx->h_pmax.resize(n);
+  ctx->h_tix_off.resize(n + 1);
+  uint64_t n_tix = 0;
   int32_t run = INT32_MIN;
   uint32_t max_q = 0;
   for (uint64_t r = 0; r < n; r++) {
@@ -328,6 +371,8 @@ int hm_upload_batch(hm_ctx* ctx, const hm_read_batch* b) {
       return fail(ctx, HM_ERR_ARG, "read %llu: offsets outside the buffers", (unsigned long long)r);
     if (b->tend[r] > run) run = b->tend[r];
     ctx->h_pmax[r] = run;
+    ctx->h_tix_off[r] = (uint32_t)n_tix;
+    n_tix += (uint64_t)((b->tend[r] >> 11) - (b->tstart[r] >> 11) + 1);
     if (b->qname_id[r] > max_q) max_q = b->qname_id[r];
   }
   ctx->max_qname_id = max_q;
@@ -338,7 +383,11 @@ int hm_upload_batch(hm_ctx* ctx, const hm_read_batch* b) {
   UP(b_seq_off, seq_off, n); UP(b_bq_off, bq_off, n); UP(b_op_off, op_off, n); UP(b_n_ops, n_ops, n);
   UP(b_seq, seq, b->seq_bytes); UP(b_bq, bq, b->bq_bytes); UP(b_ops, ops, b->n_ops_total);
 #undef UP
+  if (b->n_reads && (b->tstart[0] < 0 || n_tix >= (1ull << 32))) return fail(ctx, HM_ERR_ARG, "negative reference_start, or too many (read, tile) pairs in one batch");
+  ctx->h_tix_off[n] = (uint32_t)n_tix;
+  ctx->n_tix = n_tix;
   if ((rc = upload(ctx, ctx->b_pmax, ctx->h_pmax.data(), n))) return rc;
+  if ((rc = upload(ctx, ctx->b_tix_off, ctx->h_tix_off.data(), n + 1))) return rc;
   const size_t no = (size_t)b->n_ops_total;
   CU(ctx->b_op_t.ensure(no * 4 + 16)); CU(ctx->b_op_q.ensure(no * 4 + 16)); CU(ctx->b_mm.ensure(no * 4 + 16));
   CU(ctx->b_bq_total.ensure(n * 8 + 16)); CU(ctx->b_n_match.ensure(n * 4 + 16)); CU(ctx->b_n_sub.ensure(n * 4 + 16));
@@ -657,6 +706,14 @@ int hm_ref_tricounts(hm_ctx* ctx, const uint8_t* refseq, size_t ref_len, int64_t
   return HM_OK;
 }
 
+/* how many positions the last hm_normcounts_chunks evaluated with the exact genotype arithmetic
+ * (the rest were decided by the certified integer pass) */
+int hm_last_norm_exact_sites(hm_ctx* ctx, uint64_t* n) {
+  if (!ctx || !n) return HM_ERR_ARG;
+  *n = (uint64_t)ctx->last_norm_sites;
+  return HM_OK;
+}
+
 int hm_last_timing(hm_ctx* ctx, float* total_ms, int* n_launches) {
   if (!ctx) return HM_ERR_ARG;
   if (total_ms) *total_ms = ctx->last_total_ms;
@@ -687,20 +744,25 @@ static int hm_normcounts_impl(hm_ctx* ctx, const uint8_t* refseq, size_t ref_len
   memset(ref_tri, 0, sizeof(int64_t) * HM_TRI_BINS);
   memset(log, 0, sizeof(int64_t) * HM_NORM_LOG_LEN);
   if (n_alt_tie) *n_alt_tie = 0;
+  ctx->last_norm_sites = 0;
   t_reset(ctx);
   std::vector<uint64_t> pair_off;
   int rc = upload_chunks(ctx, chunks, n_chunks, pair_off);
   if (rc) return rc;
   const uint64_t n_pairs = pair_off.back();
   // tile prefix sums for the 256-wide (v1) and 512-wide (TMA) kernels, back to back
-  std::vector<uint64_t> tile_off(2 * (n_chunks + 1), 0);
+  std::vector<uint64_t> tile_off(3 * (n_chunks + 1), 0);
   uint64_t* tile_off2 = tile_off.data() + n_chunks + 1;
+  uint64_t* tile_off3 = tile_off.data() + 2 * (n_chunks + 1);
+  uint64_t total_span = 0;
   for (size_t i = 0; i < n_chunks; i++) {
     const int64_t span = (int64_t)chunks[i].end - (int64_t)chunks[i].start;
     tile_off[i + 1] = tile_off[i] + (span > 0 ? (uint64_t)((span + HM_TILE_W - 1) / HM_TILE_W) : 0);
     tile_off2[i + 1] = tile_off2[i] + (span > 0 ? (uint64_t)((span + HM_TW - 1) / HM_TW) : 0);
+    tile_off3[i + 1] = tile_off3[i] + (span > 0 ? (uint64_t)(((chunks[i].end - 1) >> 11) - (chunks[i].start >> 11) + 1) : 0); // absolute 2048 grid
+    if (span > 0) total_span += (uint64_t)span;
   }
-  const uint64_t n_tiles = tile_off[n_chunks], n_tiles_tma = tile_off2[n_chunks];
+  const uint64_t n_tiles = tile_off[n_chunks], n_tiles_tma = tile_off2[n_chunks], n_tiles_fast = tile_off3[n_chunks];
   if (n_tiles >= (1ull << 31)) return fail(ctx, HM_ERR_ARG, "too many tiles in one call");
   if ((rc = upload(ctx, ctx->b_tile_off, tile_off.data(), tile_off.size()))) return rc;
   if (refseq) { // per-call reference: replaces whatever hm_set_reference left
@@ -726,7 +788,10 @@ static int hm_normcounts_impl(hm_ctx* ctx, const uint8_t* refseq, size_t ref_len
                                                  ctx->b_qseen.as<uint8_t>());
     t_end(ctx);
     CU(cudaGetLastError());
-    static const bool use_v1 = getenv("HIMUT_B200_NORM_V1") != nullptr;
+    const bool use_v1 = getenv("HIMUT_B200_NORM_V1") != nullptr;
+    const bool use_v2 = getenv("HIMUT_B200_NORM_V2") != nullptr;
+    int n_sm = 148;
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, ctx->device);
     if (use_v1) {
       t_begin(ctx, "k_norm_tiles");
       k_norm_tiles<<<(unsigned)n_tiles, HM_TILE_W, 0, ctx->stream>>>(ctx->db, ctx->dp, ctx->dsets, ctx->dlut, ctx->b_chunks.as<hm_chunk>(),
@@ -735,15 +800,13 @@ static int hm_normcounts_impl(hm_ctx* ctx, const uint8_t* refseq, size_t ref_len
                                                                      ctx->b_ref.as<uint8_t>(), (uint64_t)ref_len,
                                                                      ctx->b_norm_out.as<NormOut>());
       t_end(ctx);
-    } else {
+    } else if (use_v2 || !ctx->cert.enabled) {
       const size_t smem = sizeof(TileStage) * HM_NSTAGE;
       static bool attr_set = false;
       if (!attr_set) {
         CU(cudaFuncSetAttribute(k_norm_tiles_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = true;
       }
-      int n_sm = 148;
-      cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, ctx->device);
       unsigned grid = (unsigned)std::min<uint64_t>(n_tiles_tma, (uint64_t)n_sm);
       if (const char* g = getenv("HIMUT_B200_NORM_GRID")) grid = (unsigned)std::max(1, std::min<int>(atoi(g), (int)n_tiles_tma));
       t_begin(ctx, "k_norm_tiles_tma");
@@ -753,6 +816,70 @@ static int hm_normcounts_impl(hm_ctx* ctx, const uint8_t* refseq, size_t ref_len
                                                                 (uint32_t)n_tiles_tma, ctx->b_ref.as<uint8_t>(), (uint64_t)ref_len,
                                                                 ctx->b_norm_out.as<NormOut>());
       t_end(ctx);
+    } else {
+      // fast integer pass over every position, then the exact pass over the listed sites
+      const size_t smem = sizeof(FastStage) * HF_NSTAGE;
+      static bool attr_set = false;
+      if (!attr_set) {
+        CU(cudaFuncSetAttribute(k_norm_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+      }
+      const unsigned grid = (unsigned)std::min<uint64_t>(n_tiles_fast, (uint64_t)n_sm);
+      unsigned long long* d_nsites = ctx->b_counters.as<unsigned long long>() + 4;
+      unsigned long long site_cap = std::max<unsigned long long>(1ull << 16, total_span / 16);
+      if (const char* g = getenv("HIMUT_B200_NORM_SITE_CAP")) site_cap = std::max(1ll, atoll(g));
+      unsigned long long n_sites = 0;
+      CU(ctx->b_tix.ensure((size_t)ctx->n_tix * 16 + 16));
+      t_begin(ctx, "k_tile_index");
+      k_tile_index<<<(unsigned)((ctx->n_reads * 32 + 255) / 256), 256, 0, ctx->stream>>>(ctx->db, ctx->dp.mismatch_window,
+                                                                                         ctx->b_tix_off.as<uint32_t>(), ctx->b_tix.as<uint4>());
+      t_end(ctx);
+      CU(cudaGetLastError());
+      for (int attempt = 0; attempt < 2; attempt++) {
+        CU(ctx->b_sites.ensure(site_cap * 8));
+        if (attempt) { // the list overflowed: start over with the exact size
+          CU(cudaMemsetAsync(ctx->b_norm_out.p, 0, sizeof(NormOut), ctx->stream));
+          CU(cudaMemsetAsync(d_nsites, 0, 8, ctx->stream));
+        }
+        t_begin(ctx, "k_norm_fast");
+        k_norm_fast<<<grid, HF_CONS + 32 * HF_NPROD, smem, ctx->stream>>>(
+            ctx->db, ctx->dp, ctx->cert, ctx->b_chunks.as<hm_chunk>(), (uint32_t)n_chunks, ctx->b_pair_off.as<uint64_t>(),
+            ctx->b_pair_hap.as<uint8_t>(), ctx->b_tile_off.as<uint64_t>() + 2 * (n_chunks + 1), (uint32_t)n_tiles_fast,
+            ctx->b_tix_off.as<uint32_t>(), ctx->b_tix.as<uint4>(), ctx->b_ref.as<uint8_t>(), (uint64_t)ref_len, ctx->b_norm_out.as<NormOut>(), ctx->b_sites.as<unsigned long long>(), site_cap,
+            d_nsites);
+        t_end(ctx);
+        CU(cudaGetLastError());
+        CU(cudaMemcpyAsync(&n_sites, d_nsites, 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        if (n_sites <= site_cap) break;
+        site_cap = n_sites;
+      }
+      ctx->last_norm_sites = n_sites;
+      const unsigned long long SITE_BATCH = 1ull << 21;
+      for (unsigned long long s0 = 0; s0 < n_sites; s0 += SITE_BATCH) {
+        const uint64_t nb = (uint64_t)std::min<unsigned long long>(SITE_BATCH, n_sites - s0);
+        const uint64_t stride = (nb + 31) & ~31ull;
+        CU(ctx->b_agg.ensure(stride * HM_SITE_SLOTS * 4 + nb * 8));
+        uint32_t* entries = ctx->b_agg.as<uint32_t>();
+        uint32_t* site_lo = entries + stride * HM_SITE_SLOTS;
+        uint32_t* site_n = site_lo + nb;
+        const unsigned long long* keys = ctx->b_sites.as<unsigned long long>() + s0;
+        t_begin(ctx, "k_norm_site_range");
+        k_norm_site_range<<<(unsigned)((nb + 255) / 256), 256, 0, ctx->stream>>>(ctx->db, ctx->b_chunks.as<hm_chunk>(), keys, nb, site_lo, site_n);
+        t_end(ctx);
+        t_begin(ctx, "k_norm_entries");
+        k_norm_entries<<<(unsigned)((nb + 15) / 16), 1024, 0, ctx->stream>>>(ctx->db, ctx->dp, ctx->b_chunks.as<hm_chunk>(),
+                                                                            ctx->b_pair_off.as<uint64_t>(), ctx->b_pair_hap.as<uint8_t>(),
+                                                                            keys, nb, site_lo, site_n, entries, stride);
+        t_end(ctx);
+        t_begin(ctx, "k_norm_reduce");
+        k_norm_reduce<<<(unsigned)((nb + 127) / 128), 128, 0, ctx->stream>>>(
+            ctx->db, ctx->dp, ctx->dsets, ctx->dlut, ctx->b_chunks.as<hm_chunk>(), ctx->b_pair_off.as<uint64_t>(),
+            ctx->b_pair_hap.as<uint8_t>(), keys, nb, site_lo, site_n, entries, stride, ctx->b_ref.as<uint8_t>(), (uint64_t)ref_len,
+            ctx->b_norm_out.as<NormOut>());
+        t_end(ctx);
+        CU(cudaGetLastError());
+      }
     }
     CU(cudaGetLastError());
     t_begin(ctx, "k_count_flags");
@@ -766,6 +893,13 @@ static int hm_normcounts_impl(hm_ctx* ctx, const uint8_t* refseq, size_t ref_len
   CU(cudaStreamSynchronize(ctx->stream));
   t_collect(ctx);
 #ifdef HM_NORM_DEBUG
+  {
+    unsigned long long fd[8];
+    cudaMemcpyFromSymbol(fd, g_fill_dbg, sizeof(fd));
+    fprintf(stderr, "[fill dbg, cycles summed over CTA 0's producer warps] meta %llu scans %llu scratch %llu walk %llu classify %llu tma %llu\n", fd[0], fd[1], fd[2], fd[3], fd[4], fd[5]);
+    memset(fd, 0, sizeof(fd));
+    cudaMemcpyToSymbol(g_fill_dbg, fd, sizeof(fd));
+  }
   fprintf(stderr, "[norm dbg, CTA 0] producer: wait %.0f fill %.0f cycles per batch (%llu batches) | consumer warp 0: wait %.0f compute %.0f cycles per batch, %.1f slots per batch | epilogue %.0f cycles per tile (%llu tiles)\n",
           (double)h.dbg[0] / (double)std::max<unsigned long long>(h.dbg[2], 1), (double)h.dbg[1] / (double)std::max<unsigned long long>(h.dbg[2], 1), h.dbg[2],
           (double)h.dbg[3] / (double)std::max<unsigned long long>(h.dbg[2], 1), (double)h.dbg[4] / (double)std::max<unsigned long long>(h.dbg[2], 1),

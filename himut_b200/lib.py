@@ -11,7 +11,7 @@ import numpy as np
 from . import abi
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libhimut_b200.so")
+LIB_PATH = os.environ.get("HIMUT_B200_LIB") or os.path.join(_HERE, "libhimut_b200.so")  # override: instrumented builds
 _LIB = None
 
 # every symbol include/himut_b200.h declares (tests/test_abi.py checks the export table)
@@ -19,7 +19,7 @@ EXPORTS = [
     "hm_abi_version", "hm_create", "hm_destroy", "hm_last_error", "hm_set_params", "hm_set_site_sets",
     "hm_set_phase_sets", "hm_upload_batch", "hm_call_chunks", "hm_call_batch", "hm_normcounts_chunks",
     "hm_read_stats", "hm_last_timing", "hm_last_kernel_times", "hm_set_stream", "hm_host_register",
-    "hm_host_unregister", "hm_abi_sizeof", "hm_last_records", "hm_qname_seen", "hm_set_reference", "hm_ref_tricounts",
+    "hm_host_unregister", "hm_abi_sizeof", "hm_last_records", "hm_qname_seen", "hm_set_reference", "hm_ref_tricounts", "hm_last_norm_exact_sites",
 ]
 
 
@@ -59,6 +59,7 @@ def load():
         lib.hm_qname_seen.argtypes = [vp, vp, sz, C.POINTER(sz)]
         lib.hm_set_reference.argtypes = [vp, vp, sz]
         lib.hm_ref_tricounts.argtypes = [vp, vp, sz, vp]
+        lib.hm_last_norm_exact_sites.argtypes = [vp, C.POINTER(C.c_uint64)]
         lib.hm_set_stream.argtypes = [vp, vp]
         lib.hm_host_register.argtypes = [vp, vp, sz]
         lib.hm_host_unregister.argtypes = [vp, vp]
@@ -209,6 +210,12 @@ class Context:
         self._chk(self.lib.hm_ref_tricounts(self.h, _p(ref), ref.size, _p(out)))
         self._ref_obj = None
         return out
+
+    def last_norm_exact_sites(self):
+        """positions the last normcounts call evaluated exactly (the rest: certified integer pass)"""
+        n = C.c_uint64(0)
+        self._chk(self.lib.hm_last_norm_exact_sites(self.h, C.byref(n)))
+        return int(n.value)
 
     def qname_seen(self):
         """flags per qname_id of the last call: which query names passed the read gates"""

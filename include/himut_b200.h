@@ -270,6 +270,11 @@ int hm_normcounts_chunks(hm_ctx* ctx, const uint8_t* refseq, size_t ref_len,
  * count distinct names across them.                                                          */
 int hm_qname_seen(hm_ctx* ctx, uint8_t* out, size_t cap, size_t* n);
 
+/* diagnostics: how many positions the last hm_normcounts_chunks evaluated with the exact ordered
+ * fp64 genotype arithmetic; all the others were pure-reference positions whose verdict the integer
+ * pass certified.  0 when the single-pass kernel ran.                            */
+int hm_last_norm_exact_sites(hm_ctx* ctx, uint64_t* n);
+
 /* reference-genome trinucleotide counts of one contig, bins as above (replaces
  * reflib.get_chrom_tricount, src/himut/reflib.py:11-33: windows whose first base is "N" are skipped) */
 int hm_ref_tricounts(hm_ctx* ctx, const uint8_t* refseq, size_t ref_len, int64_t tri[HM_TRI_BINS]);
