@@ -152,6 +152,9 @@ __device__ unsigned long long g_fill_dbg[8];
 __device__ __forceinline__ void fast_fill_slot(const DevBatch& b, const DevParams& p, const uint32_t* tix_off, const uint4* tix,
                                                FastSlot* S, uint64_t* full_bar, uint32_t r, uint32_t pf, int32_t t0, int32_t lo_pos,
                                                int32_t t1) {
+  // The lanes of a producer warp walk different reads; every phase below ends in a __syncwarp over the lanes that
+  // entered, so the warp executes the longest path of a phase once instead of one lane group after the other.
+  const unsigned fm = __activemask();
 #ifdef HM_NORM_DEBUG
   long long tp_ = clock64();
 #endif
@@ -163,93 +166,106 @@ __device__ __forceinline__ void fast_fill_slot(const DevBatch& b, const DevParam
   const uint64_t bq_off = __ldg(b.bq_off + r), seq_off = __ldg(b.seq_off + r);
   const uint32_t tx0 = __ldg(tix_off + r);
   uint32_t sp_touch = 0, bl_touch = 0;
-  uint32_t flags = 0, nb_bq = 0, nb_seq = 0, cov = 1u, q_base = 0, nseg = 0;
+  uint32_t nb_bq = 0, nb_seq = 0, cov = 1u, q_base = 0, nseg = 0;
   int32_t delta0 = 0;
   const uint8_t *src_bq = nullptr, *src_seq = nullptr;
-  if ((pf & HM_PF_FETCHED) && ts < t1 && te >= lo_pos && n > 0) {
-    flags = pf & 0xffu;
-    const int32_t* mm = b.mm_pos + o0;
-    const int w = p.mismatch_window;
-    FILL_T(0);
-    // round 2: the read's slice for this tile (k_tile_index)
-    const uint4 te4 = __ldg(tix + (uint64_t)tx0 + (uint32_t)((t0 >> 11) - (ts >> 11)));
-    const uint32_t k0 = te4.x, k1 = te4.y, m_lo = te4.z, m_hi = te4.w;
-    const uint32_t ns = k1 - k0, nmv = m_hi - m_lo;
-    bool slow = ns > HF_SCR_OPS || nmv > HF_SCR_MM || (uint64_t)ns * (uint64_t)(nmv + 1) > HF_MAX_WALK;
-    // round 3: park the op triples and the mismatch entries in shared memory
-    uint32_t* scr = reinterpret_cast<uint32_t*>(S->bq);
-    int32_t* smm = reinterpret_cast<int32_t*>(S->bq) + 3 * HF_SCR_OPS;
-    if (!slow) {
+  const bool act = (pf & HM_PF_FETCHED) && ts < t1 && te >= lo_pos && n > 0;
+  const uint32_t flags = act ? (pf & 0xffu) : 0u;
+  const int32_t* mm = b.mm_pos + o0;
+  const int w = p.mismatch_window;
+  FILL_T(0);
+  // round 2: the read's slice for this tile (k_tile_index)
+  uint4 te4 = make_uint4(0u, 0u, 0u, 0u);
+  if (act) te4 = __ldg(tix + (uint64_t)tx0 + (uint32_t)((t0 >> 11) - (ts >> 11)));
+  const uint32_t k0 = te4.x, m_lo = te4.z;
+  uint32_t ns = te4.y - te4.x, nmv = te4.w - te4.z;
+  bool slow = act && (ns > HF_SCR_OPS || nmv > HF_SCR_MM || (uint64_t)ns * (uint64_t)(nmv + 1) > HF_MAX_WALK);
+  if (slow) { ns = 0; nmv = 0; }
+  // round 3: park the op triples and the mismatch entries in shared memory
+  uint32_t* scr = reinterpret_cast<uint32_t*>(S->bq);
+  int32_t* smm = reinterpret_cast<int32_t*>(S->bq) + 3 * HF_SCR_OPS;
 #pragma unroll 4
-      for (uint32_t i = 0; i < ns; i++) {
-        scr[3 * i] = __ldg(b.ops + o0 + k0 + i); scr[3 * i + 1] = __ldg(b.op_t + o0 + k0 + i); scr[3 * i + 2] = __ldg(b.op_q + o0 + k0 + i);
-      }
+  for (uint32_t i = 0; i < ns; i++) {
+    scr[3 * i] = __ldg(b.ops + o0 + k0 + i); scr[3 * i + 1] = __ldg(b.op_t + o0 + k0 + i); scr[3 * i + 2] = __ldg(b.op_q + o0 + k0 + i);
+  }
 #pragma unroll 4
-      for (uint32_t m = 0; m < nmv; m++) smm[m] = __ldg(mm + m_lo + m);
-    }
-    FILL_T(2);
-    uint4* mz = reinterpret_cast<uint4*>(S->mask);
+  for (uint32_t m = 0; m < nmv; m++) smm[m] = __ldg(mm + m_lo + m);
+  uint4* mz = reinterpret_cast<uint4*>(S->mask);
+  if (act) {
 #pragma unroll 4
     for (int i = 0; i < (int)(sizeof(S->mask) / 16); i++) mz[i] = make_uint4(0u, 0u, 0u, 0u);
-    const int32_t trim_s = (int32_t)floor(__dmul_rn(p.min_trim, (double)qlen));
-    const int32_t trim_e = (int32_t)ceil(__dmul_rn(__dsub_rn(1.0, p.min_trim), (double)qlen));
-    const int32_t W = HF_TW; // bits beyond the chunk's end land on positions the consumers never count
-    int32_t cur_delta = INT32_MIN, q_lo = 0, q_hi = 0;
-    bool have_q = false;
-    // a matched base is not callable when a mismatch lies within the window of its block (normcounts.py:82-94).
-    // For every block but those starting within `w` of a read end the window is (w, w): one range per mismatch,
-    // laid over the whole read here; the edge blocks are redone with their own (u, d) below.
-    if (p.max_mismatch_count == 0 && !slow)
-      for (uint32_t m = 0; m < nmv; m++) { const int32_t x = smm[m]; fmask_set(S->mask, 1, x - w - t0, x + w - t0 + 1, &bl_touch); }
-    for (uint32_t i = 0; i < ns && !slow; i++) {
+  }
+  __syncwarp(fm);
+  FILL_T(2);
+  const int32_t trim_s = (int32_t)floor(__dmul_rn(p.min_trim, (double)qlen));
+  const int32_t trim_e = (int32_t)ceil(__dmul_rn(__dsub_rn(1.0, p.min_trim), (double)qlen));
+  const int32_t W = HF_TW; // bits beyond the chunk's end land on positions the consumers never count
+  int32_t cur_delta = INT32_MIN, q_lo = 0, q_hi = 0;
+  bool have_q = false;
+  // a matched base is not callable when a mismatch lies within the window of its block (normcounts.py:82-94).
+  // For every block but those starting within `w` of a read end the window is (w, w): one range per mismatch,
+  // laid over the whole read here; the edge blocks are redone with their own (u, d) below.
+  if (p.max_mismatch_count == 0)
+    for (uint32_t m = 0; m < nmv; m++) { const int32_t x = smm[m]; fmask_set(S->mask, 1, x - w - t0, x + w - t0 + 1, &bl_touch); }
+  __syncwarp(fm);
+  const uint32_t ns_max = __reduce_max_sync(fm, ns);
+  for (uint32_t i = 0; i < ns_max; i++) {
+    if (i < ns && !slow) {
       const uint32_t wd = scr[3 * i], ot = scr[3 * i + 1];
       const uint32_t kind = wd & 3u;
       const int32_t a = ts + (int32_t)ot - t0, rl = op_ref_len(wd);
       if (kind == HM_OP_MATCH) {
         const int32_t lo_p = max(a, 0), hi_p = min(a + rl, W);
-        if (lo_p >= hi_p) continue;
-        const int32_t qpos0 = (int32_t)scr[3 * i + 2], delta = qpos0 - a;
-        if (delta != cur_delta) {
-          if (nseg == HF_MAX_SEG) { slow = true; break; }
-          S->seg_start[nseg] = lo_p; S->seg_delta[nseg] = delta;
-          if (nseg == 0) delta0 = delta;
-          else fmask_set(S->mask, 0, lo_p, (lo_p + 3) & ~3, &sp_touch); // rest of the 4-position group after an indel
-          nseg++; cur_delta = delta;
-        }
-        if (!have_q) { q_lo = lo_p + delta; have_q = true; }
-        q_hi = hi_p + delta;
-        // bamlib.get_mismatch_range anchored at the block start (normcounts.py:82)
-        const int qs = qpos0 - w, qe2 = qpos0 + w;
-        int u, d;
-        if (qs < 0) { u = w + qs; d = w + (-qs); }
-        else if (qe2 > qlen) { u = w + (qe2 - qlen); d = qlen - qpos0; }
-        else { u = w; d = w; }
-        if (p.max_mismatch_count == 0) {
-          if (u != w || d != w) {
-            fmask_clear(S->mask, 1, lo_p, hi_p);
-            for (uint32_t m = 0; m < nmv; m++) {
-              const int32_t x = smm[m];
-              fmask_set(S->mask, 1, max(x - d - t0, lo_p), min(x + u - t0 + 1, hi_p), &bl_touch);
+        if (lo_p < hi_p) {
+          const int32_t qpos0 = (int32_t)scr[3 * i + 2], delta = qpos0 - a;
+          if (delta != cur_delta) {
+            if (nseg == HF_MAX_SEG) slow = true;
+            else {
+              S->seg_start[nseg] = lo_p; S->seg_delta[nseg] = delta;
+              if (nseg == 0) delta0 = delta;
+              else fmask_set(S->mask, 0, lo_p, (lo_p + 3) & ~3, &sp_touch); // rest of the 4-position group after an indel
+              nseg++; cur_delta = delta;
             }
           }
-        } else if (nmv > (uint32_t)p.max_mismatch_count) {
-          // general threshold: count per position (rare setting; window reach is small)
-          if ((uint64_t)(hi_p - lo_p) * nmv > 4 * HF_MAX_WALK) { slow = true; break; }
-          for (int32_t pp = lo_p; pp < hi_p; pp++) {
-            int mc = 0;
-            for (uint32_t m = 0; m < nmv; m++) { const int32_t x = smm[m]; mc += (x >= t0 + pp - u && x <= t0 + pp + d); }
-            if (mc > p.max_mismatch_count) fmask_set(S->mask, 1, pp, pp + 1, &bl_touch);
+          if (!have_q) { q_lo = lo_p + delta; have_q = true; }
+          q_hi = hi_p + delta;
+          // bamlib.get_mismatch_range anchored at the block start (normcounts.py:82)
+          const int qs = qpos0 - w, qe2 = qpos0 + w;
+          int u, d;
+          if (qs < 0) { u = w + qs; d = w + (-qs); }
+          else if (qe2 > qlen) { u = w + (qe2 - qlen); d = qlen - qpos0; }
+          else { u = w; d = w; }
+          if (p.max_mismatch_count == 0) {
+            if (u != w || d != w) {
+              fmask_clear(S->mask, 1, lo_p, hi_p);
+              for (uint32_t m = 0; m < nmv; m++) {
+                const int32_t x = smm[m];
+                fmask_set(S->mask, 1, max(x - d - t0, lo_p), min(x + u - t0 + 1, hi_p), &bl_touch);
+              }
+            }
+          } else if (nmv > (uint32_t)p.max_mismatch_count) {
+            // general threshold: count per position (rare setting; window reach is small)
+            if ((uint64_t)(hi_p - lo_p) * nmv > 4 * HF_MAX_WALK) slow = true;
+            else
+              for (int32_t pp = lo_p; pp < hi_p; pp++) {
+                int mc = 0;
+                for (uint32_t m = 0; m < nmv; m++) { const int32_t x = smm[m]; mc += (x >= t0 + pp - u && x <= t0 + pp + d); }
+                if (mc > p.max_mismatch_count) fmask_set(S->mask, 1, pp, pp + 1, &bl_touch);
+              }
           }
+          if (lo_p + delta < trim_s) fmask_set(S->mask, 1, lo_p, min(hi_p, trim_s - delta), &bl_touch);         // q < trim_s
+          if (hi_p - 1 + delta > trim_e) fmask_set(S->mask, 1, max(lo_p, trim_e - delta + 1), hi_p, &bl_touch); // q > trim_e
         }
-        fmask_set(S->mask, 1, lo_p, min(hi_p, trim_s - delta), &bl_touch);        // q < trim_s
-        fmask_set(S->mask, 1, max(lo_p, trim_e - delta + 1), hi_p, &bl_touch);    // q > trim_e
       } else if (kind == HM_OP_DEL) {
         fmask_set(S->mask, 0, max(a, 0), min(a + rl, W), &sp_touch);
       } else if (a >= 0 && a < W) {
         fmask_set(S->mask, 0, a, a + 1, &sp_touch); // substitution, or the base an insertion precedes
       }
     }
-    FILL_T(3);
+    __syncwarp(fm);
+  }
+  FILL_T(3);
+  if (act) {
     cov = (uint32_t)max(ts - t0, 0) | ((uint32_t)max(min(te - 1 - t0, W - 1), 0) << 16);
     if (te - 1 < t0) cov = 1u; // lo 1 > hi 0: nothing aligned inside the tile (trailing insertion only)
     if (!slow && have_q) {
@@ -267,30 +283,29 @@ __device__ __forceinline__ void fast_fill_slot(const DevBatch& b, const DevParam
       nb_bq = nb_seq = 0; nseg = 0; sp_touch = 0xffffu;
     }
   }
+  __syncwarp(fm);
   S->head = make_uint4(flags | (nseg << 16), cov, q_base, (uint32_t)delta0);
-  if (!(flags & HM_PF_FETCHED)) {
-    uint4* cz = reinterpret_cast<uint4*>(S->chunk);
-#pragma unroll
-    for (int i = 0; i < (int)(sizeof(S->chunk) / 16); i++) cz[i] = make_uint4(0u, 0u, 0u, 0u);
-  } else {
+  {
     const int cov_lo = (int)(cov & 0xffffu), cov_hi = (int)(cov >> 16);
     // chunks the read touches at all / covers completely, as 16-bit masks
     uint32_t any = 0, full = 0;
-    if (cov_hi >= cov_lo) {
+    if (act && cov_hi >= cov_lo) {
       any = (2u << (cov_hi >> 7)) - (1u << (cov_lo >> 7));
       const int f_lo = (cov_lo + 127) >> 7, f_hi = ((cov_hi + 1) >> 7) - 1;
       if (f_hi >= f_lo) full = (2u << f_hi) - (1u << f_lo);
     }
-    const uint32_t plain = full & ~sp_touch & ~bl_touch, none = ~any & ~sp_touch;
+    const uint32_t plain = full & ~sp_touch & ~bl_touch, none = act ? (~any & ~sp_touch) : 0xffffu;
+    const int32_t dbase = 64 - (int32_t)q_base;
     uint32_t sg = 0;
 #pragma unroll 4
     for (int wi = 0; wi < HF_CONS / 32; wi++) {
       const uint32_t cls = ((plain >> wi) & 1u) ? 1u : ((none >> wi) & 1u) ? 0u : 2u;
-      while (sg + 1 < nseg && S->seg_start[sg + 1] <= wi * 128) sg++;
-      const int32_t dl = nseg ? S->seg_delta[sg] : 0;
-      S->chunk[wi] = make_uint2(cls | (flags << 8), (uint32_t)(dl - (int32_t)q_base + 64));
+      if (nseg > 1) while (sg + 1 < nseg && S->seg_start[sg + 1] <= wi * 128) sg++;
+      const int32_t dl = nseg > 1 ? S->seg_delta[sg] : delta0;
+      S->chunk[wi] = make_uint2(cls | (flags << 8), (uint32_t)(dl + dbase));
     }
   }
+  __syncwarp(fm);
   FILL_T(4);
   // the descriptor is complete: arrive (release) last, then let the bulk copies land on the barrier
   if (nb_bq + nb_seq == 0) mbar_arrive(full_bar);
@@ -367,6 +382,7 @@ k_norm_fast(DevBatch b, DevParams p, NormCert cert, const hm_chunk* chunks, uint
             mbar_arrive(&full_bar[st]);
           }
         }
+        __syncwarp(); // idle lanes must not run ahead into the next wait: their polling would stall the working lanes
 #ifdef HM_NORM_DEBUG
         if (lane == 0 && blockIdx.x == 0) { atomicAdd(&out->dbg[0], (unsigned long long)(c1 - c0)); atomicAdd(&out->dbg[1], (unsigned long long)(clock64() - c1)); atomicAdd(&out->dbg[2], 1ull); }
 #endif
