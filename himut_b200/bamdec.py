@@ -16,7 +16,7 @@ from . import abi, pack
 
 _LIB = None
 EXPORTS = ["hm_bam_open", "hm_bam_close", "hm_bam_error", "hm_bam_header_text", "hm_bam_n_refs", "hm_bam_ref_name",
-           "hm_bam_ref_len", "hm_bam_read_batch", "hm_bam_n_qnames", "hm_bam_qname"]
+           "hm_bam_ref_len", "hm_bam_read_batch", "hm_bam_n_qnames", "hm_bam_qname", "hm_bam_window_qlens"]
 
 
 def lib_path():
@@ -43,6 +43,7 @@ def load():
         lib.hm_bam_ref_name.restype = C.c_char_p
         lib.hm_bam_ref_len.argtypes = [vp, C.c_int]
         lib.hm_bam_read_batch.argtypes = [vp, C.c_int, C.c_int32, C.c_int32, C.c_int, C.POINTER(abi.hm_read_batch)]
+        lib.hm_bam_window_qlens.argtypes = [vp, C.c_int, C.c_int32, C.c_int32, C.c_int, vp, C.c_size_t, C.POINTER(C.c_size_t)]
         lib.hm_bam_n_qnames.argtypes = [vp]
         lib.hm_bam_n_qnames.restype = C.c_uint32
         lib.hm_bam_qname.argtypes = [vp, C.c_uint32]
@@ -97,6 +98,22 @@ class NativeBam:
         for name, dt in abi.ReadBatch._FIELDS:
             arrays[name] = cp(_view(getattr(s, name), sizes.get(name, n), dt))
         return abi.ReadBatch(keepalive=None if copy else self, **arrays)
+
+    def window_qlens(self, chrom, start, end):
+        """len(query_sequence) of the records overlapping [start, end) with MAPQ > 0 and tp:A:P, fetch order
+        (the list bamlib.get_thresholds builds per window, src/himut/bamlib.py:156-164)"""
+        rid = self.references.index(chrom)
+        cap = 4096
+        while True:
+            out = np.empty(cap, np.int32)
+            n = C.c_size_t(0)
+            rc = self.lib.hm_bam_window_qlens(self.h, rid, int(max(start, 0)), int(end), self.threads, out.ctypes.data_as(C.c_void_p), cap, C.byref(n))
+            if rc == 3:  # HM_ERR_CAPACITY
+                cap = int(n.value)
+                continue
+            if rc != 0:
+                raise pack.BatchFormatError(self.lib.hm_bam_error(self.h).decode())
+            return out[: int(n.value)]
 
     def n_qnames(self):
         return int(self.lib.hm_bam_n_qnames(self.h))

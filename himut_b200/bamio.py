@@ -418,7 +418,18 @@ class BamWriter:
 
 def write_batch_bam(path, chrom, contig_len, batch, sample="synth"):
     """ReadBatch -> coordinate-sorted BAM + BAI (cs:Z short form, tp:A:P), for tests and tools"""
-    w = BamWriter(path, [(chrom, contig_len)], header_extra="@RG\tID:rg\tSM:%s\n" % sample)
+    write_batches_bam(path, [(chrom, contig_len, batch)], sample)
+
+
+def write_batches_bam(path, contigs, sample="synth"):
+    """[(chrom, contig_len, ReadBatch), ...] -> one coordinate-sorted BAM + BAI"""
+    w = BamWriter(path, [(c, n) for c, n, _ in contigs], header_extra="@RG\tID:rg\tSM:%s\n" % sample)
+    for rid, (_c, _n, batch) in enumerate(contigs):
+        _add_batch(w, rid, batch)
+    w.close()
+
+
+def _add_batch(w, rid, batch):
     for r in range(batch.n_reads):
         ql = int(batch.qlen[r])
         so, bo, oo = int(batch.seq_off[r]), int(batch.bq_off[r]), int(batch.op_off[r])
@@ -449,6 +460,5 @@ def write_batch_bam(path, chrom, contig_len, batch, sample="synth"):
             else:
                 merged.append((o, l))
         flag = 0x100 if (batch.flags[r] & abi.READ_SECONDARY) else 0
-        w.add(0, int(batch.tstart[r]), "read%d" % int(batch.qname_id[r]), flag, int(batch.mapq[r]), merged, qseq,
+        w.add(rid, int(batch.tstart[r]), "read%d" % int(batch.qname_id[r]), flag, int(batch.mapq[r]), merged, qseq,
               batch.bq[bo:bo + ql].tobytes(), [("cs", "Z", "".join(cs)), ("tp", "A", "P")])
-    w.close()

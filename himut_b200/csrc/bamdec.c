@@ -555,3 +555,81 @@ finish:
   b->batch = *out;
   return HM_OK;
 }
+
+/* ------------------------------------------------------------------ pre-pass: read lengths of a window */
+/* bamlib.get_thresholds (src/himut/bamlib.py:137-178) fetches 100 random 100 kb windows per contig and keeps
+ * len(query_sequence) of every record with mapping_quality > 0 and tp:A:P (secondary / supplementary records
+ * included, as pysam's fetch returns them).  Only the fixed part of each record, its CIGAR and the tp tag are
+ * looked at here: no base / quality unpacking, no cs parsing.  Lengths come back in fetch order. */
+int hm_bam_window_qlens(hm_bam* b, int rid, int32_t start, int32_t end, int threads, int32_t* out, size_t cap, size_t* n_out) {
+  if (!b || !n_out) return HM_ERR_ARG;
+  *n_out = 0;
+  if (rid < 0 || rid >= b->n_ref) return fail(b, "invalid contig index%s %ld", NULL, rid);
+  if (start < 0) start = 0;
+  if (end > b->refs[rid].len) end = b->refs[rid].len;
+  if (start >= end) return HM_OK;
+  uint64_t voff = b->first_record;
+  if (b->have_bai) {
+    const bam_ref_t* R = &b->refs[rid];
+    if (!R->has_index) return HM_OK;
+    int32_t w = start >> 14;
+    if (w >= R->n_lin) w = R->n_lin - 1;
+    uint64_t v = 0;
+    for (; w >= 0 && !v; w--) v = R->lin[w];
+    if (v) voff = v;
+  }
+  stream_t s;
+  memset(&s, 0, sizeof(s));
+  s.b = b; s.threads = threads;
+  s.span = 1u << 18; /* windows are small: start with 256 KB of compressed data */
+  if (stream_seek(&s, voff) < 0) { free(s.buf); return fail(b, "cannot read BGZF blocks of %s (%ld)", b->path, 0); }
+  int rc = HM_OK;
+  size_t n = 0;
+  for (;;) {
+    int st = stream_need(&s, 4);
+    if (st == 1) break;
+    if (st < 0) { rc = fail(b, "truncated BAM %s (%ld)", b->path, 0); break; }
+    uint32_t bs = rd32(s.buf + s.pos);
+    if (stream_need(&s, 4 + (size_t)bs)) { rc = fail(b, "truncated BAM record in %s (%ld)", b->path, 0); break; }
+    const uint8_t* r = s.buf + s.pos + 4;
+    s.pos += 4 + (size_t)bs;
+    int32_t ref_id = (int32_t)rd32(r), pos = (int32_t)rd32(r + 4);
+    if (ref_id != rid) { if (ref_id > rid || ref_id < 0) break; continue; }
+    if (pos >= end) break;
+    uint32_t l_name = r[8], mapq = r[9], n_cig = r[12] | (r[13] << 8);
+    int32_t l_seq = (int32_t)rd32(r + 16);
+    const uint8_t* cig = r + 32 + l_name;
+    int32_t ref_span = 0;
+    for (uint32_t k = 0; k < n_cig; k++) {
+      uint32_t c = rd32(cig + 4 * k), op = c & 15, ln = c >> 4;
+      if (op == 0 || op == 2 || op == 3 || op == 7 || op == 8) ref_span += (int32_t)ln;
+    }
+    if (pos + (ref_span > 0 ? ref_span : 1) <= start) continue;
+    if (mapq == 0) continue;
+    const uint8_t* tag = cig + 4 * (size_t)n_cig + ((size_t)l_seq + 1) / 2 + (size_t)l_seq;
+    const uint8_t* rec_end = r + bs;
+    int tp_primary = 0;
+    while (tag + 3 <= rec_end) {
+      char ty = (char)tag[2];
+      const uint8_t* v = tag + 3;
+      size_t adv;
+      if (ty == 'Z' || ty == 'H') adv = strlen((const char*)v) + 1;
+      else if (ty == 'A' || ty == 'c' || ty == 'C') { adv = 1; if (tag[0] == 't' && tag[1] == 'p' && ty == 'A') tp_primary = (v[0] == 'P'); }
+      else if (ty == 's' || ty == 'S') adv = 2;
+      else if (ty == 'i' || ty == 'I' || ty == 'f') adv = 4;
+      else if (ty == 'B') { char sub = (char)v[0]; uint32_t cnt = rd32(v + 1); adv = 5 + (size_t)cnt * ((sub == 'c' || sub == 'C') ? 1 : (sub == 's' || sub == 'S') ? 2 : 4); }
+      else { rc = fail(b, "unknown tag type in record %s (%ld)", (const char*)(r + 32), ty); break; }
+      tag = v + adv;
+    }
+    if (rc) break;
+    if (!tp_primary) continue;
+    if (l_seq <= 0) { rc = fail(b, "%s has no SEQ: len(read.query_sequence) raises TypeError in the reference (%ld)", (const char*)(r + 32), 0); break; }
+    if (out && n < cap) out[n] = l_seq;
+    n++;
+  }
+  free(s.buf);
+  *n_out = n;
+  if (rc) return rc;
+  if (n > cap) return HM_ERR_CAPACITY;
+  return HM_OK;
+}

@@ -1,4 +1,4 @@
-"""Re-points the reference's two starmap targets at the GPU workers.
+"""Re-points the reference's starmap targets (and its BAM pre-pass) at the GPU workers.
 
 The reference resolves its workers as module globals at call time (src/himut/caller.py:805-806,
 src/himut/normcounts.py:536), so assigning the attributes before the driver runs is enough; the
@@ -9,12 +9,14 @@ CLI, header, thresholds, natsort and writers stay the reference's own code.
 def install():
     import himut.caller
     import himut.normcounts
+    import himut.bamlib
     import himut.reflib
 
-    from . import caller, normcounts, reflib
+    from . import bamlib, caller, normcounts, reflib
     himut.caller.get_somatic_substitutions = caller.get_somatic_substitutions
     himut.normcounts.get_callable_tricounts = normcounts.get_callable_tricounts
     himut.reflib.get_chrom_tricount = reflib.get_chrom_tricount  # reflib.py:42-52 starmap target
+    himut.bamlib.get_thresholds = bamlib.get_thresholds          # BAM pre-pass, called at caller.py:690
     return himut
 
 

@@ -45,6 +45,12 @@ int hm_bam_ref_len(const hm_bam* b, int i);
  * substituted base, cs spans that disagree with the CIGAR.  `threads` = inflate threads. */
 int hm_bam_read_batch(hm_bam* b, int rid, int32_t start, int32_t end, int threads, hm_read_batch* out);
 
+/* BAM pre-pass of bamlib.get_thresholds (reference src/himut/bamlib.py:137-178): len(query_sequence) of
+ * every record of contig `rid` that overlaps [start, end) with mapping_quality > 0 and tp:A:P, in fetch
+ * order (secondary / supplementary records included: the reference does not test the flag there).  Only
+ * record headers, CIGARs and tags are parsed.  HM_ERR_CAPACITY when cap is too small (*n_out = needed). */
+int hm_bam_window_qlens(hm_bam* b, int rid, int32_t start, int32_t end, int threads, int32_t* out, size_t cap, size_t* n_out);
+
 /* query names are interned per handle: qname_id of a batch indexes this table, ids are stable
  * across hm_bam_read_batch calls (m.num_ccs counts distinct names per contig, caller.py:318-320) */
 uint32_t hm_bam_n_qnames(const hm_bam* b);
