@@ -85,7 +85,7 @@ struct hm_ctx {
   size_t ref_len = 0; // length of the contig left resident by hm_set_reference (0: none)
   NormCert cert;      // certified-verdict constants of the normcounts fast pass
   unsigned long long last_norm_sites = 0; // positions the last normcounts call evaluated exactly
-  DevBuf b_sites;
+  DevBuf b_sites, b_koff;
 };
 
 namespace {
@@ -256,7 +256,7 @@ void hm_destroy(hm_ctx* ctx) {
                     &ctx->b_ins_len, &ctx->b_del_len, &ctx->b_n_mm, &ctx->b_gate, &ctx->b_pmax, &ctx->b_tix_off, &ctx->b_tix, &ctx->b_common, &ctx->b_pon,
                     &ctx->b_hpos, &ctx->b_href, &ctx->b_halt, &ctx->b_hbit, &ctx->b_set_off, &ctx->b_chunks,
                     &ctx->b_pair_off, &ctx->b_pair_hap, &ctx->b_qseen, &ctx->b_keys, &ctx->b_keys_sorted, &ctx->b_cub,
-                    &ctx->b_records, &ctx->b_counters, &ctx->b_ref, &ctx->b_norm_out, &ctx->b_lut, &ctx->b_tile_off, &ctx->b_agg, &ctx->b_geom, &ctx->b_bidx, &ctx->b_sites};
+                    &ctx->b_records, &ctx->b_counters, &ctx->b_ref, &ctx->b_norm_out, &ctx->b_lut, &ctx->b_tile_off, &ctx->b_agg, &ctx->b_geom, &ctx->b_bidx, &ctx->b_sites, &ctx->b_koff};
   for (DevBuf* b : bufs) b->release();
   if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
   for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
@@ -504,11 +504,23 @@ int hm_call_chunks(hm_ctx* ctx, const hm_chunk* chunks, size_t n_chunks, hm_site
                                                                               site_lo, site_n);
       t_end(ctx);
       CU(cudaGetLastError());
-      t_begin(ctx, "k_site_entries");
-      k_site_entries<<<(unsigned)((n_unique + 15) / 16), 1024, 0, ctx->stream>>>(
-          ctx->db, ctx->dp, ctx->b_chunks.as<hm_chunk>(), ctx->b_pair_off.as<uint64_t>(), ctx->b_pair_hap.as<uint8_t>(), k_in,
-          d_cnt + 1, site_lo, site_n, entries, stride);
-      t_end(ctx);
+      const bool by_site = getenv("HIMUT_B200_ENTRIES_BY_SITE") != nullptr; // the earlier thread-per-(site, read) gather (A/B)
+      if (by_site) {
+        t_begin(ctx, "k_site_entries");
+        k_site_entries<<<(unsigned)((n_unique + 15) / 16), 1024, 0, ctx->stream>>>(
+            ctx->db, ctx->dp, ctx->b_chunks.as<hm_chunk>(), ctx->b_pair_off.as<uint64_t>(), ctx->b_pair_hap.as<uint8_t>(), k_in,
+            d_cnt + 1, site_lo, site_n, entries, stride);
+        t_end(ctx);
+      } else {
+        CU(ctx->b_koff.ensure((n_chunks + 2) * 4));
+        t_begin(ctx, "k_site_entries_by_read");
+        CU(cudaMemsetAsync(entries, 0xff, stride * HM_SITE_SLOTS * 4, ctx->stream));
+        k_chunk_key_ranges<<<(unsigned)((n_chunks + 1 + 127) / 128), 128, 0, ctx->stream>>>(k_in, d_cnt + 1, (uint32_t)n_chunks, ctx->b_koff.as<uint32_t>());
+        k_site_entries_by_read<<<(unsigned)((n_pairs * 32 + 255) / 256), 256, 0, ctx->stream>>>(
+            ctx->db, ctx->dp, ctx->b_chunks.as<hm_chunk>(), (uint32_t)n_chunks, ctx->b_pair_off.as<uint64_t>(), n_pairs,
+            ctx->b_pair_hap.as<uint8_t>(), k_in, ctx->b_koff.as<uint32_t>(), site_lo, site_n, entries, stride);
+        t_end(ctx);
+      }
       CU(cudaGetLastError());
       t_begin(ctx, "k_site_reduce");
       k_site_reduce<<<(unsigned)((n_unique + 127) / 128), 128, 0, ctx->stream>>>(

@@ -537,6 +537,106 @@ __global__ void __launch_bounds__(1024) k_site_entries(DevBatch b, DevParams p, 
   entries[(uint64_t)slot * stride + ki] = site_entry(b, p, ch, c, pair_off, pair_hap, __ldg(site_lo + ki) + slot, rpos);
 }
 
+// ---- gather by read ------------------------------------------------------------------------------
+// k_site_entries asks, for every (site, read) pair, "which op of this read holds the site" with a search over
+// the read's op arrays in global memory.  k_site_entries_by_read turns the loop around: one warp per
+// (chunk, read) pair stages the read's op arrays in shared memory once and then serves all the chunk's sites
+// the read covers (about 60 per 15 kb read), 32 sites at a time; the only scattered global loads left are the
+// site's quality byte and its 2-bit base.  Entries nobody writes (reads that do not reach a site) keep the
+// 0xffffffff the buffer is initialised with; k_site_reduce skips them.
+#define HM_ENT_UNWRITTEN 0xffffffffu
+#define HM_BYREAD_MAX_OPS 192
+
+// warp-cooperative: first index in [lo, hi) with a[i] >= x (32 pivots per round)
+__device__ __forceinline__ uint32_t warp_lower_bound_u64(const unsigned long long* a, uint32_t lo, uint32_t hi, unsigned long long x, int lane) {
+  while (hi - lo > 32) {
+    const uint32_t step = (hi - lo + 32) / 33;
+    const uint32_t idx = lo + step * (uint32_t)(lane + 1) - 1;
+    const bool below = idx < hi && __ldg(a + idx) < x;
+    const uint32_t cnt = __popc(__ballot_sync(HM_FULL, below));
+    lo += cnt * step;
+    hi = min(hi, lo + step);
+  }
+  const bool below = lo + (uint32_t)lane < hi && __ldg(a + lo + lane) < x;
+  return lo + __popc(__ballot_sync(HM_FULL, below));
+}
+
+// first key of each chunk in the sorted distinct keys: koff[c] = lower_bound(keys, c << 36), koff[n_chunks] = n_keys
+__global__ void k_chunk_key_ranges(const unsigned long long* keys, const unsigned long long* n_keys_dev, uint32_t n_chunks,
+                                   uint32_t* koff) {
+  const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c > n_chunks) return;
+  const uint64_t n = *n_keys_dev;
+  const unsigned long long want = (unsigned long long)c << 36;
+  uint64_t lo = 0, hi = n;
+  while (lo < hi) { const uint64_t m = (lo + hi) >> 1; if (__ldg(keys + m) < want) lo = m + 1; else hi = m; }
+  koff[c] = (uint32_t)lo;
+}
+
+__global__ void __launch_bounds__(256) k_site_entries_by_read(DevBatch b, DevParams p, const hm_chunk* chunks, uint32_t n_chunks,
+                                                              const uint64_t* pair_off, uint64_t n_pairs, const uint8_t* pair_hap,
+                                                              const unsigned long long* keys, const uint32_t* koff,
+                                                              const uint32_t* site_lo, const uint32_t* site_n, uint32_t* entries,
+                                                              uint64_t stride) {
+  __shared__ uint32_t s_w[8][HM_BYREAD_MAX_OPS], s_t[8][HM_BYREAD_MAX_OPS], s_q[8][HM_BYREAD_MAX_OPS];
+  const uint64_t pr = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (pr >= n_pairs) return;
+  const uint32_t c = upper_bound_dev(pair_off, n_chunks + 1, pr) - 1;
+  const hm_chunk ch = chunks[c];
+  const uint32_t r = ch.read_lo + (uint32_t)(pr - pair_off[c]);
+  if (__ldg(b.flags + r) & HM_READ_SECONDARY) return;
+  const int32_t ts = __ldg(b.tstart + r), te = __ldg(b.tend + r);
+  if (!(ts < ch.end && te > ch.start)) return;
+  const uint32_t n = __ldg(b.n_ops + r);
+  if (n == 0) return;
+  // the chunk's sites with rpos in [ts, te], i.e. tpos in [ts + 1, te + 1]
+  const uint32_t k_lo = koff[c], k_hi = koff[c + 1];
+  if (k_lo == k_hi) return;
+  const unsigned long long base = (unsigned long long)c << 36;
+  const unsigned long long want_lo = base | ((unsigned long long)(uint32_t)(ts + 1) << 4);
+  const unsigned long long want_hi = base | ((unsigned long long)(uint32_t)(te + 2) << 4);
+  const uint32_t s_lo = warp_lower_bound_u64(keys, k_lo, k_hi, want_lo, lane);
+  const uint32_t s_hi = warp_lower_bound_u64(keys, s_lo, k_hi, want_hi, lane);
+  if (s_lo >= s_hi) return;
+  const uint64_t o0 = __ldg(b.op_off + r);
+  const bool staged = n <= HM_BYREAD_MAX_OPS;
+  if (staged) {
+    for (uint32_t k = lane; k < n; k += 32) {
+      s_w[wid][k] = __ldg(b.ops + o0 + k); s_t[wid][k] = __ldg(b.op_t + o0 + k); s_q[wid][k] = __ldg(b.op_q + o0 + k);
+    }
+    __syncwarp();
+  }
+  const uint64_t bq0 = __ldg(b.bq_off + r), sq0 = __ldg(b.seq_off + r);
+  const uint32_t hap = p.phase ? pair_hap[pr] : 2u;
+  for (uint32_t ki = s_lo + lane; ki < s_hi; ki += 32) {
+    const uint32_t slot = r - __ldg(site_lo + ki);
+    if (slot >= HM_SITE_SLOTS || slot >= __ldg(site_n + ki)) continue; // deep pileups: k_site_reduce computes these itself
+    const int32_t rpos = (int32_t)((__ldg(keys + ki) >> 4) & 0xffffffffull) - 1;
+    int a, bq = 0, ins = 0;
+    if (staged) {
+      const uint32_t off = (uint32_t)(rpos - ts);
+      uint32_t lo = 0, hi = n; // last op with op_t <= off
+      while (lo < hi) { const uint32_t m = (lo + hi) >> 1; if (s_t[wid][m] <= off) lo = m + 1; else hi = m; }
+      const int k = (int)lo - 1;
+      for (int j = k; j >= 0 && s_t[wid][j] == off; j--) ins += ((s_w[wid][j] & 3u) == HM_OP_INS);
+      const uint32_t wd = s_w[wid][k], kind = wd & 3u, v = wd >> 2, t_op = s_t[wid][k];
+      const uint32_t rl = (uint32_t)op_ref_len(wd);
+      if (rl == 0 || off >= t_op + rl) a = -1;
+      else if (kind == HM_OP_DEL) a = 5;
+      else {
+        const uint32_t q = s_q[wid][k] + (kind == HM_OP_MATCH ? off - t_op : 0u);
+        bq = b.bq[bq0 + q];
+        a = kind == HM_OP_SUB ? (int)((v >> 3) & 7u) : (int)((b.seq[sq0 + (q >> 2)] >> (2 * (q & 3u))) & 3u);
+      }
+    } else {
+      a = read_allele_fast(b, r, rpos, ts, &bq, &ins);
+    }
+    entries[(uint64_t)slot * stride + ki] = (a < 0 ? HM_ENT_NONE : (uint32_t)a) | ((uint32_t)bq << 3) | ((uint32_t)min(ins, 255) << 11) |
+                                            ((hap & 3u) << 19) | ((te > rpos + 1) ? (1u << 21) : 0u);
+  }
+}
+
 __global__ void __launch_bounds__(128) k_site_reduce(DevBatch b, DevParams p, DevSets sets, DevLut lut, const hm_chunk* chunks,
                                                      const uint64_t* pair_off, const uint8_t* pair_hap, const int32_t* prev_max_end,
                                                      const int32_t* next_min_start, const unsigned long long* keys,
@@ -567,6 +667,7 @@ __global__ void __launch_bounds__(128) k_site_reduce(DevBatch b, DevParams p, De
     for (uint32_t s = 0; s < n; s++) {
       const uint32_t e = s < HM_SITE_SLOTS ? __ldg(entries + (uint64_t)s * stride + ki)
                                            : site_entry(b, p, ch, c, pair_off, pair_hap, lo + s, tpos - 1); // very deep pileups
+      if (e == HM_ENT_UNWRITTEN) continue; // a read of the range that does not reach the site
       const uint32_t a = e & 7u;
       cnt[4] += (int)((e >> 11) & 255u);
       if (a == HM_ENT_NONE) continue;
