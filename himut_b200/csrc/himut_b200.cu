@@ -434,6 +434,12 @@ int hm_call_chunks(hm_ctx* ctx, const hm_chunk* chunks, size_t n_chunks, hm_site
   memset(h_cnt, 0, sizeof(h_cnt));
   unsigned long long* d_cnt = ctx->b_counters.as<unsigned long long>();
   unsigned long long key_cap = std::max<unsigned long long>(ctx->n_ops_total, 1024);
+  // bits of (tpos - chunk.start): candidates satisfy start <= tpos <= end (is_chunk, caller.py:325)
+  int pos_bits = 1;
+  for (size_t i = 0; i < n_chunks; i++) {
+    const int64_t span = (int64_t)chunks[i].end - (int64_t)chunks[i].start;
+    while (pos_bits < 32 && span >= (1ll << pos_bits)) pos_bits++;
+  }
   for (int attempt = 0; attempt < 2 && n_pairs; attempt++) {
     CU(ctx->b_keys.ensure(key_cap * 8));
     CU(cudaMemsetAsync(ctx->b_counters.p, 0, CNT_BYTES, ctx->stream));
@@ -443,7 +449,7 @@ int hm_call_chunks(hm_ctx* ctx, const hm_chunk* chunks, size_t n_chunks, hm_site
     k_candidates<<<blocks, 256, 0, ctx->stream>>>(ctx->db, ctx->dp, ctx->dphase, ctx->b_chunks.as<hm_chunk>(), (uint32_t)n_chunks,
                                                   ctx->b_pair_off.as<uint64_t>(), n_pairs,
                                                   ctx->params.phase ? ctx->b_pair_hap.as<uint8_t>() : nullptr,
-                                                  ctx->b_qseen.as<uint8_t>(), ctx->b_keys.as<unsigned long long>(), key_cap, d_cnt);
+                                                  ctx->b_qseen.as<uint8_t>(), ctx->b_keys.as<unsigned long long>(), key_cap, d_cnt, pos_bits);
     t_end(ctx);
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(h_cnt, ctx->b_counters.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
@@ -476,8 +482,8 @@ int hm_call_chunks(hm_ctx* ctx, const hm_chunk* chunks, size_t n_chunks, hm_site
       // sort + unique of the candidate keys (library plumbing: cub), then the site kernels
       CU(ctx->b_keys_sorted.ensure(n_keys * 8));
       size_t tmp_sort = 0, tmp_uniq = 0;
-      int end_bit = 37;
-      for (size_t c = n_chunks; c > 1; c >>= 1) end_bit++;
+      int end_bit = pos_bits + 4;
+      for (size_t c = n_chunks; c > 0; c >>= 1) end_bit++;
       end_bit = std::min(end_bit, 64);
       unsigned long long* k_in = ctx->b_keys.as<unsigned long long>();
       unsigned long long* k_sorted = ctx->b_keys_sorted.as<unsigned long long>();
@@ -487,6 +493,7 @@ int hm_call_chunks(hm_ctx* ctx, const hm_chunk* chunks, size_t n_chunks, hm_site
       t_begin(ctx, "cub_sort_unique_keys");
       CU(cub::DeviceRadixSort::SortKeys(ctx->b_cub.p, tmp_sort, k_in, k_sorted, (int64_t)n_keys, 0, end_bit, ctx->stream));
       CU(cub::DeviceSelect::Unique(ctx->b_cub.p, tmp_uniq, k_sorted, k_in, d_cnt + 1, (int64_t)n_keys, ctx->stream));
+      k_expand_keys<<<(unsigned)((n_keys + 255) / 256), 256, 0, ctx->stream>>>(k_in, d_cnt + 1, ctx->b_chunks.as<hm_chunk>(), pos_bits);
       t_end(ctx);
       CU(cudaMemcpyAsync(h_cnt + 1, d_cnt + 1, 8, cudaMemcpyDeviceToHost, ctx->stream));
       if ((rc = upload(ctx, ctx->b_geom, geom.data(), 2 * n_chunks))) return rc;

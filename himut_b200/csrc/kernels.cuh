@@ -279,7 +279,7 @@ __global__ void __launch_bounds__(256) k_candidates(DevBatch b, DevParams p, Dev
                                                     uint32_t n_chunks, const uint64_t* pair_off, uint64_t n_pairs,
                                                     uint8_t* pair_hap, uint8_t* qname_seen,
                                                     unsigned long long* keys, unsigned long long cap,
-                                                    unsigned long long* n_keys) {
+                                                    unsigned long long* n_keys, int pos_bits) {
   const uint64_t pr = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (pr >= n_pairs) return;
@@ -326,7 +326,9 @@ __global__ void __launch_bounds__(256) k_candidates(DevBatch b, DevParams p, Dev
           const int cnt = (int)upper_bound_dev(mm, nmm, tpos + d) - (int)lower_bound_dev(mm, nmm, tpos - u) - 1;
           if (!(cnt > p.max_mismatch_count)) {
             emit = true;
-            key = ((unsigned long long)c << 36) | ((unsigned long long)(uint32_t)tpos << 4) | ((v & 3u) << 2) | ((v >> 3) & 3u);
+            // sort key: chunk | position inside the chunk | ref | alt, packed so the radix sort sees as few bits as
+            // possible; k_expand_keys turns it into chunk << 36 | tpos << 4 | ref << 2 | alt afterwards
+            key = ((unsigned long long)c << (pos_bits + 4)) | ((unsigned long long)(uint32_t)(tpos - ch.start) << 4) | ((v & 3u) << 2) | ((v >> 3) & 3u);
           }
         }
       }
@@ -342,6 +344,16 @@ __global__ void __launch_bounds__(256) k_candidates(DevBatch b, DevParams p, Dev
       }
     }
   }
+}
+
+// compact sort key -> chunk << 36 | tpos << 4 | ref << 2 | alt (order is preserved: same fields, same significance)
+__global__ void k_expand_keys(unsigned long long* keys, const unsigned long long* n_keys_dev, const hm_chunk* chunks, int pos_bits) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= *n_keys_dev) return;
+  const unsigned long long k = keys[i];
+  const uint32_t c = (uint32_t)(k >> (pos_bits + 4));
+  const uint32_t rel = (uint32_t)((k >> 4) & ((1ull << pos_bits) - 1ull));
+  keys[i] = ((unsigned long long)c << 36) | ((unsigned long long)(uint32_t)(chunks[c].start + (int32_t)rel) << 4) | (k & 15ull);
 }
 
 // ============================================================================ genotype model
