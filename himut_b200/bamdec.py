@@ -16,7 +16,7 @@ from . import abi, pack
 
 _LIB = None
 EXPORTS = ["hm_bam_open", "hm_bam_close", "hm_bam_error", "hm_bam_header_text", "hm_bam_n_refs", "hm_bam_ref_name",
-           "hm_bam_ref_len", "hm_bam_read_batch", "hm_bam_n_qnames", "hm_bam_qname", "hm_bam_window_qlens"]
+           "hm_bam_ref_len", "hm_bam_read_batch", "hm_bam_n_qnames", "hm_bam_qname", "hm_bam_window_qlens", "hm_bam_write_batch"]
 
 
 def lib_path():
@@ -44,6 +44,7 @@ def load():
         lib.hm_bam_ref_len.argtypes = [vp, C.c_int]
         lib.hm_bam_read_batch.argtypes = [vp, C.c_int, C.c_int32, C.c_int32, C.c_int, C.POINTER(abi.hm_read_batch)]
         lib.hm_bam_window_qlens.argtypes = [vp, C.c_int, C.c_int32, C.c_int32, C.c_int, vp, C.c_size_t, C.POINTER(C.c_size_t)]
+        lib.hm_bam_write_batch.argtypes = [C.c_char_p, C.c_char_p, C.c_int32, C.c_char_p, C.POINTER(abi.hm_read_batch), C.c_int, C.c_int]
         lib.hm_bam_n_qnames.argtypes = [vp]
         lib.hm_bam_n_qnames.restype = C.c_uint32
         lib.hm_bam_qname.argtypes = [vp, C.c_uint32]
@@ -68,6 +69,14 @@ def _view(ptr, n, dtype):
     dt = np.dtype(dtype)
     buf = (C.c_char * (n * dt.itemsize)).from_address(ptr)
     return np.frombuffer(buf, dtype=dt, count=n)
+
+
+def write_batch_bam(path, chrom, contig_len, batch, sample="synth", level=1, threads=None):
+    """ReadBatch -> coordinate-sorted BAM + BAI, natively (same content as bamio.write_batch_bam)"""
+    rc = load().hm_bam_write_batch(os.fsencode(path), chrom.encode(), int(contig_len), sample.encode(), C.byref(batch.as_struct()),
+                                   int(level), int(threads or default_threads()))
+    if rc != 0:
+        raise IOError("cannot write %s" % path)
 
 
 class NativeBam:

@@ -396,6 +396,123 @@ static inline int base_code(char c) {
   switch (c) { case 'A': case 'a': return 0; case 'T': case 't': return 1; case 'G': case 'g': return 2; case 'C': case 'c': return 3; default: return -1; }
 }
 
+/* one selected record between the serial scan (phase A) and the parallel decode (phase B) */
+typedef struct {
+  const uint8_t* rec;   /* start of the fixed part (after block_size) */
+  const char* cs;
+  int32_t pos, l_seq, lead, trail, ref_span;
+  size_t seq_off, bq_off, op_slot; /* where its outputs go; op_slot is an upper-bound slot, compacted afterwards */
+  uint32_t n_ops;
+  int32_t rspan;
+  int err;              /* 0 ok, else index into the message table below */
+  long err_arg;
+} rec_t;
+
+enum { E_CS_TOKEN = 1, E_CS_PAST, E_N_MATCH, E_CS_LONG, E_SUB_N, E_SPAN_REF, E_SPAN_QRY };
+static const char* const REC_ERR[] = {
+    "", "%s: unsupported cs token (%ld)", "%s: cs runs past the read (%ld)",
+    "%s: read base outside A/C/G/T under a cs match (reference: KeyError) (%ld)",
+    "%s: cs long-form bases disagree with SEQ at query %ld",
+    "%s: substitution to a base outside A/C/G/T (the reference pileup raises KeyError) (%ld)",
+    "%s: cs reference span != CIGAR span (%ld)", "%s: cs query span != aligned query span (%ld)"};
+
+typedef struct {
+  hm_bam* b;
+  rec_t* recs;
+  size_t n, next;
+  pthread_mutex_t mu;
+} decode_job_t;
+
+/* phase B for one record: SEQ -> 2-bit, QUAL copy, cs -> ops (cslib.cs2lst grammar) with span and base checks */
+static void decode_record(hm_bam* b, rec_t* R, uint8_t** codes_p, size_t* codes_cap) {
+  const uint8_t* r = R->rec;
+  const uint32_t l_name = r[8], n_cig = r[12] | (r[13] << 8);
+  const int32_t l_seq = R->l_seq;
+  const uint8_t* seq4 = r + 32 + l_name + 4 * (size_t)n_cig;
+  const uint8_t* qual = seq4 + ((size_t)l_seq + 1) / 2;
+  if ((size_t)l_seq + 2 > *codes_cap) {
+    size_t nc = (size_t)l_seq + 4096;
+    uint8_t* np_ = (uint8_t*)realloc(*codes_p, nc);
+    if (!np_) { R->err = E_CS_TOKEN; R->err_arg = -1; return; }
+    *codes_p = np_; *codes_cap = nc;
+  }
+  uint8_t* codes = *codes_p;
+  for (int32_t i = 0; i + 1 < l_seq; i += 2) { const uint8_t by = seq4[i >> 1]; codes[i] = (uint8_t)NIB2CODE[by >> 4]; codes[i + 1] = (uint8_t)NIB2CODE[by & 15]; }
+  if (l_seq & 1) codes[l_seq - 1] = (uint8_t)NIB2CODE[seq4[(l_seq - 1) >> 1] >> 4];
+  uint32_t* ops = b->ops + R->op_slot;
+  uint32_t n_ops = 0;
+  int32_t q = R->lead, rspan = 0;
+  const char* cs = R->cs;
+  const char* c = cs;
+  while (*c) {
+    if (*c == ':') {
+      long n = 0; c++;
+      if (*c < '0' || *c > '9') { R->err = E_CS_TOKEN; R->err_arg = (long)(c - cs); return; }
+      while (*c >= '0' && *c <= '9') n = n * 10 + (*c++ - '0');
+      if (q + n > l_seq) { R->err = E_CS_PAST; R->err_arg = q + n; return; }
+      for (long k = 0; k < n; k++) if (codes[q + k] == 0xff) { R->err = E_N_MATCH; R->err_arg = q + k; return; }
+      if (n) ops[n_ops++] = HM_MAKE_OP(HM_OP_MATCH, n);
+      q += (int32_t)n; rspan += (int32_t)n;
+    } else if (*c == '=') {
+      long n = 0; c++;
+      while ((c[n] >= 'A' && c[n] <= 'Z') || (c[n] >= 'a' && c[n] <= 'z')) n++;
+      if (n == 0 || q + n > l_seq) { R->err = E_CS_TOKEN; R->err_arg = (long)(c - cs); return; }
+      for (long k = 0; k < n; k++) {
+        int bc = base_code(c[k]);
+        if (bc < 0 || codes[q + k] != (uint8_t)bc) { R->err = E_CS_LONG; R->err_arg = q + k; return; }
+      }
+      ops[n_ops++] = HM_MAKE_OP(HM_OP_MATCH, n);
+      c += n; q += (int32_t)n; rspan += (int32_t)n;
+    } else if (*c == '*') {
+      if (!c[1] || !c[2]) { R->err = E_CS_TOKEN; R->err_arg = (long)(c - cs); return; }
+      int rc_ = base_code(c[1]), ac = base_code(c[2]);
+      if (ac < 0) { R->err = E_SUB_N; R->err_arg = q; return; }
+      ops[n_ops++] = HM_MAKE_SUB(rc_ < 0 ? HM_BASE_N : (uint32_t)rc_, (uint32_t)ac);
+      c += 3; q += 1; rspan += 1;
+    } else if (*c == '+' || *c == '-') {
+      int ins = *c == '+';
+      long n = 0; c++;
+      while ((c[n] >= 'A' && c[n] <= 'Z') || (c[n] >= 'a' && c[n] <= 'z')) n++;
+      if (n == 0) { R->err = E_CS_TOKEN; R->err_arg = (long)(c - cs); return; }
+      ops[n_ops++] = HM_MAKE_OP(ins ? HM_OP_INS : HM_OP_DEL, n);
+      c += n;
+      if (ins) q += (int32_t)n; else rspan += (int32_t)n;
+    } else { R->err = E_CS_TOKEN; R->err_arg = (long)(c - cs); return; }
+  }
+  if (rspan != R->ref_span) { R->err = E_SPAN_REF; R->err_arg = rspan; return; }
+  if (q - R->lead != l_seq - R->trail - R->lead) { R->err = E_SPAN_QRY; R->err_arg = q - R->lead; return; }
+  R->n_ops = n_ops; R->rspan = rspan;
+  const size_t sb = ((size_t)l_seq + 3) / 4, sb16 = (sb + 15) & ~(size_t)15, qb16 = ((size_t)l_seq + 15) & ~(size_t)15;
+  uint8_t* dst = b->seq + R->seq_off;
+  int32_t i = 0;
+  for (; i + 3 < l_seq; i += 4) {
+    const uint8_t c0 = codes[i] & 3, c1 = codes[i + 1] & 3, c2 = codes[i + 2] & 3, c3 = codes[i + 3] & 3; /* 0xff (N in a clip) -> 3; fixed below */
+    dst[i >> 2] = (uint8_t)(c0 | (c1 << 2) | (c2 << 4) | (c3 << 6));
+  }
+  if (i < l_seq) { uint8_t v = 0; for (int32_t k = i; k < l_seq; k++) v |= (uint8_t)((codes[k] & 3) << (2 * (k & 3))); dst[i >> 2] = v; }
+  /* bases outside A/C/G/T (soft clips only, checked above) are stored as code 0, like the Python packer */
+  for (int32_t k = 0; k < R->lead; k++) if (codes[k] == 0xff) dst[k >> 2] &= (uint8_t)~(3u << (2 * (k & 3)));
+  for (int32_t k = l_seq - R->trail; k < l_seq; k++) if (codes[k] == 0xff) dst[k >> 2] &= (uint8_t)~(3u << (2 * (k & 3)));
+  memset(dst + sb, 0, sb16 - sb);
+  memcpy(b->bq + R->bq_off, qual, (size_t)l_seq);
+  memset(b->bq + R->bq_off + l_seq, 0, qb16 - (size_t)l_seq);
+}
+
+static void* decode_worker(void* arg) {
+  decode_job_t* j = (decode_job_t*)arg;
+  uint8_t* codes = NULL; size_t cap = 0;
+  for (;;) {
+    pthread_mutex_lock(&j->mu);
+    size_t i0 = j->next;
+    j->next += 64;
+    pthread_mutex_unlock(&j->mu);
+    if (i0 >= j->n) break;
+    for (size_t i = i0; i < i0 + 64 && i < j->n; i++) decode_record(j->b, &j->recs[i], &codes, &cap);
+  }
+  free(codes);
+  return NULL;
+}
+
 int hm_bam_read_batch(hm_bam* b, int rid, int32_t start, int32_t end, int threads, hm_read_batch* out) {
   if (!b || !out) return HM_ERR_ARG;
   if (rid < 0 || rid >= b->n_ref) return fail(b, "invalid contig index%s %ld", NULL, rid);
@@ -418,130 +535,122 @@ int hm_bam_read_batch(hm_bam* b, int rid, int32_t start, int32_t end, int thread
     memset(&s, 0, sizeof(s));
     s.b = b; s.threads = threads;
     if (stream_seek(&s, voff) < 0) { free(s.buf); return fail(b, "cannot read BGZF blocks of %s (%ld)", b->path, 0); }
-    uint8_t* codes = NULL; size_t codes_cap = 0;
-    int rc = HM_OK;
-    for (;;) {
+    rec_t* recs = NULL; size_t recs_cap = 0;
+    int rc = HM_OK, done = 0;
+    const int nt = threads < 1 ? 1 : (threads > 64 ? 64 : threads);
+    while (!done && !rc) {
+      /* phase A (serial): every complete record now in the buffer — select, validate what needs file order,
+       * intern the query name, assign output space */
       int st = stream_need(&s, 4);
       if (st == 1) break;
       if (st < 0) { rc = fail(b, "truncated BAM %s (%ld)", b->path, 0); break; }
-      uint32_t bs = rd32(s.buf + s.pos);
-      if (stream_need(&s, 4 + (size_t)bs)) { rc = fail(b, "truncated BAM record in %s (%ld)", b->path, 0); break; }
-      const uint8_t* r = s.buf + s.pos + 4;
-      s.pos += 4 + (size_t)bs;
-      int32_t ref_id = (int32_t)rd32(r), pos = (int32_t)rd32(r + 4);
-      if (ref_id != rid) { if (ref_id > rid || ref_id < 0) break; continue; }
-      if (pos >= end) break;
-      uint32_t l_name = r[8], mapq = r[9], n_cig = r[12] | (r[13] << 8), flag = r[14] | (r[15] << 8);
-      int32_t l_seq = (int32_t)rd32(r + 16);
-      const char* qname = (const char*)(r + 32);
-      const uint8_t* cig = r + 32 + l_name;
-      int32_t ref_span = 0, lead = 0, trail = 0;
-      int hard = 0;
-      for (uint32_t k = 0; k < n_cig; k++) {
-        uint32_t c = rd32(cig + 4 * k), op = c & 15, ln = c >> 4;
-        if (op == 0 || op == 2 || op == 3 || op == 7 || op == 8) ref_span += (int32_t)ln;
-        if (op == 5) hard = 1;
+      {
+        uint32_t bs0 = rd32(s.buf + s.pos);
+        if (stream_need(&s, 4 + (size_t)bs0)) { rc = fail(b, "truncated BAM record in %s (%ld)", b->path, 0); break; }
       }
-      for (uint32_t k = 0; k < n_cig; k++) { uint32_t c = rd32(cig + 4 * k), op = c & 15; if (op == 4) lead += (int32_t)(c >> 4); else if (op != 5) break; }
-      for (uint32_t k = n_cig; k-- > 0;) { uint32_t c = rd32(cig + 4 * k), op = c & 15; if (op == 4) trail += (int32_t)(c >> 4); else if (op != 5) break; }
-      int32_t rend = pos + (ref_span > 0 ? ref_span : 1);
-      if (rend <= start) continue;
-      if (flag & 0x100) continue; /* secondary: bamlib.py:17 */
-      const uint8_t* seq4 = cig + 4 * (size_t)n_cig;
-      const uint8_t* qual = seq4 + ((size_t)l_seq + 1) / 2;
-      const uint8_t* tag = qual + l_seq;
-      const uint8_t* rec_end = r + bs;
-      const char* cs = NULL;
-      while (tag + 3 <= rec_end) {
-        char ty = (char)tag[2];
-        const uint8_t* v = tag + 3;
-        size_t adv;
-        if (ty == 'Z' || ty == 'H') { adv = strlen((const char*)v) + 1; if (tag[0] == 'c' && tag[1] == 's' && ty == 'Z') cs = (const char*)v; }
-        else if (ty == 'A' || ty == 'c' || ty == 'C') adv = 1;
-        else if (ty == 's' || ty == 'S') adv = 2;
-        else if (ty == 'i' || ty == 'I' || ty == 'f') adv = 4;
-        else if (ty == 'B') { char sub = (char)v[0]; uint32_t cnt = rd32(v + 1); adv = 5 + (size_t)cnt * ((sub == 'c' || sub == 'C') ? 1 : (sub == 's' || sub == 'S') ? 2 : 4); }
-        else { rc = fail(b, "unknown tag type in record %s (%ld)", qname, ty); break; }
-        tag = v + adv;
+      size_t nsel = 0, seg_ops = 0;
+      const size_t first_read = n_reads;
+      while (s.len - s.pos >= 4) {
+        uint32_t bs = rd32(s.buf + s.pos);
+        if (s.len - s.pos < 4 + (size_t)bs) break; /* partial record: next fill */
+        const uint8_t* r = s.buf + s.pos + 4;
+        s.pos += 4 + (size_t)bs;
+        int32_t ref_id = (int32_t)rd32(r), pos = (int32_t)rd32(r + 4);
+        if (ref_id != rid) { if (ref_id > rid || ref_id < 0) { done = 1; break; } continue; }
+        if (pos >= end) { done = 1; break; }
+        uint32_t l_name = r[8], mapq = r[9], n_cig = r[12] | (r[13] << 8), flag = r[14] | (r[15] << 8);
+        int32_t l_seq = (int32_t)rd32(r + 16);
+        const char* qname = (const char*)(r + 32);
+        const uint8_t* cig = r + 32 + l_name;
+        int32_t ref_span = 0, lead = 0, trail = 0;
+        int hard = 0;
+        for (uint32_t k = 0; k < n_cig; k++) {
+          uint32_t c = rd32(cig + 4 * k), op = c & 15, ln = c >> 4;
+          if (op == 0 || op == 2 || op == 3 || op == 7 || op == 8) ref_span += (int32_t)ln;
+          if (op == 5) hard = 1;
+        }
+        for (uint32_t k = 0; k < n_cig; k++) { uint32_t c = rd32(cig + 4 * k), op = c & 15; if (op == 4) lead += (int32_t)(c >> 4); else if (op != 5) break; }
+        for (uint32_t k = n_cig; k-- > 0;) { uint32_t c = rd32(cig + 4 * k), op = c & 15; if (op == 4) trail += (int32_t)(c >> 4); else if (op != 5) break; }
+        int32_t rend = pos + (ref_span > 0 ? ref_span : 1);
+        if (rend <= start) continue;
+        if (flag & 0x100) continue; /* secondary: bamlib.py:17 */
+        const uint8_t* seq4 = cig + 4 * (size_t)n_cig;
+        const uint8_t* qual = seq4 + ((size_t)l_seq + 1) / 2;
+        const uint8_t* tag = qual + (l_seq > 0 ? l_seq : 0);
+        const uint8_t* rec_end = r + bs;
+        const char* cs = NULL;
+        while (tag + 3 <= rec_end) {
+          char ty = (char)tag[2];
+          const uint8_t* v = tag + 3;
+          size_t adv;
+          if (ty == 'Z' || ty == 'H') { adv = strlen((const char*)v) + 1; if (tag[0] == 'c' && tag[1] == 's' && ty == 'Z') cs = (const char*)v; }
+          else if (ty == 'A' || ty == 'c' || ty == 'C') adv = 1;
+          else if (ty == 's' || ty == 'S') adv = 2;
+          else if (ty == 'i' || ty == 'I' || ty == 'f') adv = 4;
+          else if (ty == 'B') { char sub = (char)v[0]; uint32_t cnt = rd32(v + 1); adv = 5 + (size_t)cnt * ((sub == 'c' || sub == 'C') ? 1 : (sub == 's' || sub == 'S') ? 2 : 4); }
+          else { rc = fail(b, "unknown tag type in record %s (%ld)", qname, ty); break; }
+          tag = v + adv;
+        }
+        if (rc) break;
+        if (!cs) { rc = fail(b, "%s has no cs:Z tag (the reference raises KeyError in BAM.__init__) (%ld)", qname, 0); break; }
+        if (hard) { rc = fail(b, "%s is hard clipped: cs / SEQ indexing breaks in the reference (pre-filter with -F 0x900) (%ld)", qname, 0); break; }
+        if (l_seq <= 0 || qual[0] == 0xff) { rc = fail(b, "%s has no base qualities (%ld)", qname, 0); break; }
+        if (nsel == recs_cap) {
+          size_t nc = recs_cap ? recs_cap * 2 : 8192;
+          rec_t* nr = (rec_t*)realloc(recs, nc * sizeof(rec_t));
+          if (!nr) { rc = fail(b, "out of memory%s (%ld)", NULL, (long)nc); break; }
+          recs = nr; recs_cap = nc;
+        }
+        if (n_reads + 1 > b->cap_reads) {
+          size_t cr = b->cap_reads ? b->cap_reads + b->cap_reads / 2 + 1024 : 4096;
+#define RE(ptr, type) do { type* np_ = (type*)realloc(ptr, cr * sizeof(type)); if (!np_) rc = fail(b, "out of memory%s (%ld)", NULL, (long)cr); else ptr = np_; } while (0)
+          RE(b->tstart, int32_t); RE(b->tend, int32_t); RE(b->qstart, int32_t); RE(b->qlen, int32_t); RE(b->mapq, uint8_t);
+          RE(b->flags, uint8_t); RE(b->qname_id, uint32_t); RE(b->n_ops, uint32_t); RE(b->seq_off, uint64_t);
+          RE(b->bq_off, uint64_t); RE(b->op_off, uint64_t);
+#undef RE
+          if (rc) break;
+          b->cap_reads = cr;
+        }
+        int64_t id = qt_get(&b->qt, qname, strlen(qname));
+        if (id < 0) { rc = fail(b, "out of memory%s (%ld)", NULL, 0); break; }
+        const size_t sb = ((size_t)l_seq + 3) / 4, sb16 = (sb + 15) & ~(size_t)15, qb16 = ((size_t)l_seq + 15) & ~(size_t)15;
+        rec_t* R = &recs[nsel++];
+        R->rec = r; R->cs = cs; R->pos = pos; R->l_seq = l_seq; R->lead = lead; R->trail = trail; R->ref_span = ref_span;
+        R->seq_off = n_seq; R->bq_off = n_bq; R->op_slot = n_ops + seg_ops; R->n_ops = 0; R->rspan = 0; R->err = 0; R->err_arg = 0;
+        b->tstart[n_reads] = pos; b->qstart[n_reads] = lead; b->qlen[n_reads] = l_seq;
+        b->mapq[n_reads] = (uint8_t)mapq; b->flags[n_reads] = 0; b->qname_id[n_reads] = (uint32_t)id;
+        b->seq_off[n_reads] = n_seq; b->bq_off[n_reads] = n_bq;
+        n_seq += sb16; n_bq += qb16; seg_ops += strlen(cs) / 2 + 2; n_reads++;
       }
       if (rc) break;
-      if (!cs) { rc = fail(b, "%s has no cs:Z tag (the reference raises KeyError in BAM.__init__) (%ld)", qname, 0); break; }
-      if (hard) { rc = fail(b, "%s is hard clipped: cs / SEQ indexing breaks in the reference (pre-filter with -F 0x900) (%ld)", qname, 0); break; }
-      if (l_seq <= 0 || qual[0] == 0xff) { rc = fail(b, "%s has no base qualities (%ld)", qname, 0); break; }
-      /* unpack bases to codes (-1 = not ACGT) */
-      GROW(codes, codes_cap, (size_t)l_seq + 2, uint8_t);
-      for (int32_t i = 0; i < l_seq; i++) { uint8_t nb = (i & 1) ? (seq4[i >> 1] & 15) : (seq4[i >> 1] >> 4); codes[i] = (uint8_t)NIB2CODE[nb]; }
-      /* cs -> ops (cslib.cs2lst grammar), with span and base checks */
-      GROW(b->ops, b->cap_ops, n_ops + strlen(cs) / 2 + 4, uint32_t);
-      size_t op0 = n_ops;
-      int32_t q = lead, rspan = 0;
-      const char* c = cs;
-      while (*c && !rc) {
-        if (*c == ':') {
-          long n = 0; c++;
-          if (*c < '0' || *c > '9') { rc = fail(b, "%s: unsupported cs token (%ld)", qname, (long)(c - cs)); break; }
-          while (*c >= '0' && *c <= '9') n = n * 10 + (*c++ - '0');
-          if (q + n > l_seq) { rc = fail(b, "%s: cs runs past the read (%ld)", qname, q + n); break; }
-          for (long k = 0; k < n; k++) if (codes[q + k] == 0xff) { rc = fail(b, "%s: read base outside A/C/G/T under a cs match (reference: KeyError) (%ld)", qname, q + k); break; }
-          if (n) b->ops[n_ops++] = HM_MAKE_OP(HM_OP_MATCH, n);
-          q += (int32_t)n; rspan += (int32_t)n;
-        } else if (*c == '=') {
-          long n = 0; c++;
-          while ((c[n] >= 'A' && c[n] <= 'Z') || (c[n] >= 'a' && c[n] <= 'z')) n++;
-          if (n == 0 || q + n > l_seq) { rc = fail(b, "%s: unsupported cs token (%ld)", qname, (long)(c - cs)); break; }
-          for (long k = 0; k < n; k++) {
-            int bc = base_code(c[k]);
-            if (bc < 0 || codes[q + k] != (uint8_t)bc) { rc = fail(b, "%s: cs long-form bases disagree with SEQ at query %ld", qname, q + k); break; }
-          }
-          b->ops[n_ops++] = HM_MAKE_OP(HM_OP_MATCH, n);
-          c += n; q += (int32_t)n; rspan += (int32_t)n;
-        } else if (*c == '*') {
-          int rc_ = base_code(c[1]), ac = base_code(c[2]);
-          if (!c[1] || !c[2]) { rc = fail(b, "%s: unsupported cs token (%ld)", qname, (long)(c - cs)); break; }
-          if (ac < 0) { rc = fail(b, "%s: substitution to a base outside A/C/G/T (the reference pileup raises KeyError) (%ld)", qname, q); break; }
-          b->ops[n_ops++] = HM_MAKE_SUB(rc_ < 0 ? HM_BASE_N : (uint32_t)rc_, (uint32_t)ac);
-          c += 3; q += 1; rspan += 1;
-        } else if (*c == '+' || *c == '-') {
-          int ins = *c == '+';
-          long n = 0; c++;
-          while ((c[n] >= 'A' && c[n] <= 'Z') || (c[n] >= 'a' && c[n] <= 'z')) n++;
-          if (n == 0) { rc = fail(b, "%s: unsupported cs token (%ld)", qname, (long)(c - cs)); break; }
-          b->ops[n_ops++] = HM_MAKE_OP(ins ? HM_OP_INS : HM_OP_DEL, n);
-          c += n;
-          if (ins) q += (int32_t)n; else rspan += (int32_t)n;
-        } else {
-          rc = fail(b, "%s: unsupported cs token (%ld)", qname, (long)(c - cs));
+      if (nsel) {
+        GROW(b->seq, b->cap_seq, n_seq + 16, uint8_t);
+        GROW(b->bq, b->cap_bq, n_bq + 16, uint8_t);
+        GROW(b->ops, b->cap_ops, n_ops + seg_ops + 4, uint32_t);
+        /* phase B (parallel): bases, qualities, cs -> ops */
+        decode_job_t job;
+        memset(&job, 0, sizeof(job));
+        job.b = b; job.recs = recs; job.n = nsel;
+        pthread_mutex_init(&job.mu, NULL);
+        int use = nt;
+        if ((size_t)use > (nsel + 63) / 64) use = (int)((nsel + 63) / 64);
+        pthread_t th[64];
+        for (int t = 1; t < use; t++) pthread_create(&th[t], NULL, decode_worker, &job);
+        decode_worker(&job);
+        for (int t = 1; t < use; t++) pthread_join(th[t], NULL);
+        pthread_mutex_destroy(&job.mu);
+        /* serial tail: first error in file order, op compaction */
+        for (size_t i = 0; i < nsel; i++) {
+          rec_t* R = &recs[i];
+          if (R->err) { rc = fail(b, REC_ERR[R->err], (const char*)(R->rec + 32), R->err_arg); break; }
+          const size_t rd = first_read + i;
+          if (R->op_slot != n_ops) memmove(b->ops + n_ops, b->ops + R->op_slot, (size_t)R->n_ops * sizeof(uint32_t));
+          b->op_off[rd] = n_ops; b->n_ops[rd] = R->n_ops; b->tend[rd] = R->pos + R->rspan;
+          n_ops += R->n_ops;
         }
       }
-      if (rc) break;
-      if (rspan != ref_span) { rc = fail(b, "%s: cs reference span != CIGAR span (%ld)", qname, rspan); break; }
-      if (q - lead != l_seq - trail - lead) { rc = fail(b, "%s: cs query span != aligned query span (%ld)", qname, q - lead); break; }
-      /* append the read */
-      if (n_reads + 1 > b->cap_reads) {
-        size_t cr = b->cap_reads ? b->cap_reads + b->cap_reads / 2 + 1024 : 4096;
-#define RE(ptr, type) do { type* np_ = (type*)realloc(ptr, cr * sizeof(type)); if (!np_) rc = fail(b, "out of memory%s (%ld)", NULL, (long)cr); else ptr = np_; } while (0)
-        RE(b->tstart, int32_t); RE(b->tend, int32_t); RE(b->qstart, int32_t); RE(b->qlen, int32_t); RE(b->mapq, uint8_t);
-        RE(b->flags, uint8_t); RE(b->qname_id, uint32_t); RE(b->n_ops, uint32_t); RE(b->seq_off, uint64_t);
-        RE(b->bq_off, uint64_t); RE(b->op_off, uint64_t);
-#undef RE
-        if (rc) break;
-        b->cap_reads = cr;
-      }
-      size_t sb = ((size_t)l_seq + 3) / 4, sb16 = (sb + 15) & ~(size_t)15, qb16 = ((size_t)l_seq + 15) & ~(size_t)15;
-      GROW(b->seq, b->cap_seq, n_seq + sb16 + 16, uint8_t);
-      GROW(b->bq, b->cap_bq, n_bq + qb16 + 16, uint8_t);
-      memset(b->seq + n_seq, 0, sb16);
-      for (int32_t i = 0; i < l_seq; i++) { uint8_t cd = codes[i] == 0xff ? 0 : codes[i]; b->seq[n_seq + (i >> 2)] |= (uint8_t)(cd << (2 * (i & 3))); }
-      memcpy(b->bq + n_bq, qual, (size_t)l_seq);
-      memset(b->bq + n_bq + l_seq, 0, qb16 - (size_t)l_seq);
-      int64_t id = qt_get(&b->qt, qname, strlen(qname));
-      if (id < 0) { rc = fail(b, "out of memory%s (%ld)", NULL, 0); break; }
-      b->tstart[n_reads] = pos; b->tend[n_reads] = pos + rspan; b->qstart[n_reads] = lead; b->qlen[n_reads] = l_seq;
-      b->mapq[n_reads] = (uint8_t)mapq; b->flags[n_reads] = 0; b->qname_id[n_reads] = (uint32_t)id;
-      b->seq_off[n_reads] = n_seq; b->bq_off[n_reads] = n_bq; b->op_off[n_reads] = op0; b->n_ops[n_reads] = (uint32_t)(n_ops - op0);
-      n_seq += sb16; n_bq += qb16; n_reads++;
     }
-    free(codes); free(s.buf);
+    free(recs); free(s.buf);
     if (rc) return rc;
   }
 finish:
@@ -632,4 +741,220 @@ int hm_bam_window_qlens(hm_bam* b, int rid, int32_t start, int32_t end, int thre
   if (rc) return rc;
   if (n > cap) return HM_ERR_CAPACITY;
   return HM_OK;
+}
+
+/* ------------------------------------------------------------------ writer (tests, tools, bench) */
+/* A packed batch back to a coordinate-sorted BAM + BAI: cs:Z short form, tp:A:P, query names "read<id>",
+ * deleted bases written as "n" (they are not stored).  Mirrors bamio.write_batch_bam; exists so that the
+ * benchmark can put a contig-sized BAM on disk in seconds.  Not on the calling path. */
+typedef struct { uint8_t* p; size_t n, cap; } wbuf_t;
+static int wb_need(wbuf_t* w, size_t add) {
+  if (w->n + add <= w->cap) return 0;
+  size_t nc = w->cap ? w->cap : (1u << 20);
+  while (nc < w->n + add) nc += nc / 2;
+  uint8_t* np_ = (uint8_t*)realloc(w->p, nc);
+  if (!np_) return -1;
+  w->p = np_; w->cap = nc;
+  return 0;
+}
+static void wb_u32(wbuf_t* w, uint32_t v) { w->p[w->n++] = (uint8_t)v; w->p[w->n++] = (uint8_t)(v >> 8); w->p[w->n++] = (uint8_t)(v >> 16); w->p[w->n++] = (uint8_t)(v >> 24); }
+static int reg2bin(int32_t beg, int32_t end) {
+  --end;
+  if (beg >> 14 == end >> 14) return ((1 << 15) - 1) / 7 + (beg >> 14);
+  if (beg >> 17 == end >> 17) return ((1 << 12) - 1) / 7 + (beg >> 17);
+  if (beg >> 20 == end >> 20) return ((1 << 9) - 1) / 7 + (beg >> 20);
+  if (beg >> 23 == end >> 23) return ((1 << 6) - 1) / 7 + (beg >> 23);
+  if (beg >> 26 == end >> 26) return ((1 << 3) - 1) / 7 + (beg >> 26);
+  return 0;
+}
+#define WBLK 0xff00u
+typedef struct {
+  const uint8_t* src; size_t n_src;
+  uint8_t* dst;        /* n_blocks * 65536 */
+  uint32_t* csize;
+  size_t n_blocks, next;
+  int level, error;
+  pthread_mutex_t mu;
+} deflate_job_t;
+static void* deflate_worker(void* arg) {
+  deflate_job_t* j = (deflate_job_t*)arg;
+  for (;;) {
+    pthread_mutex_lock(&j->mu);
+    size_t i0 = j->next; j->next += 8;
+    pthread_mutex_unlock(&j->mu);
+    if (i0 >= j->n_blocks) break;
+    for (size_t i = i0; i < i0 + 8 && i < j->n_blocks; i++) {
+      const size_t off = i * WBLK, len = j->n_src - off < WBLK ? j->n_src - off : WBLK;
+      uint8_t* o = j->dst + i * 65536;
+      z_stream zs; memset(&zs, 0, sizeof(zs));
+      if (deflateInit2(&zs, j->level, Z_DEFLATED, -15, 8, Z_DEFAULT_STRATEGY) != Z_OK) { j->error = 1; return NULL; }
+      zs.next_in = (Bytef*)(j->src + off); zs.avail_in = (uInt)len;
+      zs.next_out = o + 18; zs.avail_out = 65536 - 18 - 8;
+      if (deflate(&zs, Z_FINISH) != Z_STREAM_END) { deflateEnd(&zs); j->error = 1; return NULL; }
+      const uint32_t clen = (uint32_t)zs.total_out, bsize = clen + 25;
+      deflateEnd(&zs);
+      static const uint8_t head[16] = {0x1f, 0x8b, 8, 4, 0, 0, 0, 0, 0, 0xff, 6, 0, 'B', 'C', 2, 0};
+      memcpy(o, head, 16); o[16] = (uint8_t)bsize; o[17] = (uint8_t)(bsize >> 8);
+      const uint32_t crc = (uint32_t)crc32(crc32(0L, Z_NULL, 0), j->src + off, (uInt)len);
+      uint8_t* t = o + 18 + clen;
+      t[0] = (uint8_t)crc; t[1] = (uint8_t)(crc >> 8); t[2] = (uint8_t)(crc >> 16); t[3] = (uint8_t)(crc >> 24);
+      t[4] = (uint8_t)len; t[5] = (uint8_t)(len >> 8); t[6] = (uint8_t)(len >> 16); t[7] = (uint8_t)(len >> 24);
+      j->csize[i] = bsize + 1;
+    }
+  }
+  return NULL;
+}
+
+int hm_bam_write_batch(const char* path, const char* chrom, int32_t contig_len, const char* sample, const hm_read_batch* b,
+                       int level, int threads) {
+  if (!path || !chrom || !b) return HM_ERR_ARG;
+  wbuf_t w; memset(&w, 0, sizeof(w));
+  char text[1024];
+  int ltext = snprintf(text, sizeof(text), "@HD\tVN:1.6\tSO:coordinate\n@SQ\tSN:%s\tLN:%d\n@RG\tID:rg\tSM:%s\n", chrom, contig_len, sample ? sample : "synth");
+  const size_t lname = strlen(chrom) + 1;
+  if (wb_need(&w, 64 + (size_t)ltext + lname)) return HM_ERR_ARG;
+  memcpy(w.p, "BAM\1", 4); w.n = 4; wb_u32(&w, (uint32_t)ltext); memcpy(w.p + w.n, text, (size_t)ltext); w.n += (size_t)ltext;
+  wb_u32(&w, 1); wb_u32(&w, (uint32_t)lname); memcpy(w.p + w.n, chrom, lname); w.n += lname; wb_u32(&w, (uint32_t)contig_len);
+  const size_t n = (size_t)b->n_reads;
+  uint64_t* rec_off = (uint64_t*)malloc((n + 1) * sizeof(uint64_t));
+  int32_t* rec_end = (int32_t*)malloc((n + 1) * sizeof(int32_t));
+  char* cs = NULL; size_t cs_cap = 0;
+  uint32_t* cig = NULL; size_t cig_cap = 0;
+  int rc = HM_OK;
+  static const char DEC[4] = {'a', 't', 'g', 'c'};
+  static const uint8_t NIB[4] = {1, 8, 4, 2}; /* A T G C */
+  for (size_t r = 0; r < n && !rc; r++) {
+    const int32_t ql = b->qlen[r], qstart = b->qstart[r];
+    const uint32_t nops = b->n_ops[r];
+    const uint32_t* ops = b->ops + b->op_off[r];
+    const uint8_t* seq = b->seq + b->seq_off[r];
+    size_t need_cs = 16;
+    for (uint32_t k = 0; k < nops; k++) { const uint32_t kind = ops[k] & 3u, v = ops[k] >> 2; need_cs += (kind == HM_OP_MATCH) ? 12 : (kind == HM_OP_SUB) ? 3 : (size_t)v + 1; }
+    if (need_cs > cs_cap) { cs_cap = need_cs * 2; cs = (char*)realloc(cs, cs_cap); }
+    if ((size_t)nops + 4 > cig_cap) { cig_cap = ((size_t)nops + 4) * 2; cig = (uint32_t*)realloc(cig, cig_cap * 4); }
+    if (!cs || !cig) { rc = HM_ERR_ARG; break; }
+    size_t lc = 0, ncig = 0;
+    int32_t q = qstart, rspan = 0;
+#define CIG(op, len) do { if (ncig && (cig[ncig - 1] & 15u) == (uint32_t)(op)) cig[ncig - 1] += (uint32_t)(len) << 4; else cig[ncig++] = ((uint32_t)(len) << 4) | (uint32_t)(op); } while (0)
+    if (qstart) CIG(4, qstart);
+    for (uint32_t k = 0; k < nops; k++) {
+      const uint32_t kind = ops[k] & 3u, v = ops[k] >> 2;
+      if (kind == HM_OP_MATCH) { lc += (size_t)sprintf(cs + lc, ":%u", v); CIG(7, v); q += (int32_t)v; rspan += (int32_t)v; }
+      else if (kind == HM_OP_SUB) { cs[lc++] = '*'; cs[lc++] = (v & 7u) < 4 ? DEC[v & 7u] : 'n'; cs[lc++] = DEC[(v >> 3) & 3u]; CIG(8, 1); q += 1; rspan += 1; }
+      else if (kind == HM_OP_INS) { cs[lc++] = '+'; for (uint32_t i = 0; i < v; i++) { const int32_t qq = q + (int32_t)i; cs[lc++] = DEC[(seq[qq >> 2] >> (2 * (qq & 3))) & 3]; } CIG(1, v); q += (int32_t)v; }
+      else { cs[lc++] = '-'; for (uint32_t i = 0; i < v; i++) cs[lc++] = 'n'; CIG(2, v); rspan += (int32_t)v; }
+    }
+    if (ql - q > 0) CIG(4, ql - q);
+#undef CIG
+    cs[lc] = 0;
+    char qname[32];
+    const int lq = snprintf(qname, sizeof(qname), "read%u", b->qname_id[r]) + 1;
+    const int32_t pos = b->tstart[r], endp = pos + (rspan > 0 ? rspan : 1);
+    const size_t body = 32 + (size_t)lq + 4 * ncig + ((size_t)ql + 1) / 2 + (size_t)ql + (3 + lc + 1) + 4;
+    if (wb_need(&w, body + 8)) { rc = HM_ERR_ARG; break; }
+    rec_off[r] = w.n; rec_end[r] = endp;
+    wb_u32(&w, (uint32_t)body);
+    wb_u32(&w, 0); wb_u32(&w, (uint32_t)pos);
+    w.p[w.n++] = (uint8_t)lq; w.p[w.n++] = b->mapq[r];
+    const int bin = reg2bin(pos, endp);
+    w.p[w.n++] = (uint8_t)bin; w.p[w.n++] = (uint8_t)(bin >> 8);
+    w.p[w.n++] = (uint8_t)ncig; w.p[w.n++] = (uint8_t)(ncig >> 8);
+    const uint32_t flag = (b->flags[r] & HM_READ_SECONDARY) ? 0x100u : 0u;
+    w.p[w.n++] = (uint8_t)flag; w.p[w.n++] = (uint8_t)(flag >> 8);
+    wb_u32(&w, (uint32_t)ql); wb_u32(&w, 0xffffffffu); wb_u32(&w, 0xffffffffu); wb_u32(&w, 0);
+    memcpy(w.p + w.n, qname, (size_t)lq); w.n += (size_t)lq;
+    for (size_t k = 0; k < ncig; k++) wb_u32(&w, cig[k]);
+    for (int32_t i = 0; i < ql; i += 2) {
+      const uint8_t hi = NIB[(seq[i >> 2] >> (2 * (i & 3))) & 3];
+      const uint8_t lo = (i + 1 < ql) ? NIB[(seq[(i + 1) >> 2] >> (2 * ((i + 1) & 3))) & 3] : 0;
+      w.p[w.n++] = (uint8_t)((hi << 4) | lo);
+    }
+    memcpy(w.p + w.n, b->bq + b->bq_off[r], (size_t)ql); w.n += (size_t)ql;
+    w.p[w.n++] = 'c'; w.p[w.n++] = 's'; w.p[w.n++] = 'Z'; memcpy(w.p + w.n, cs, lc + 1); w.n += lc + 1;
+    w.p[w.n++] = 't'; w.p[w.n++] = 'p'; w.p[w.n++] = 'A'; w.p[w.n++] = 'P';
+  }
+  free(cs); free(cig);
+  if (rc) { free(w.p); free(rec_off); free(rec_end); return rc; }
+  rec_off[n] = w.n;
+  /* BGZF: fixed 0xff00-byte blocks, deflated in parallel */
+  deflate_job_t job; memset(&job, 0, sizeof(job));
+  job.src = w.p; job.n_src = w.n; job.n_blocks = (w.n + WBLK - 1) / WBLK; job.level = level < 0 ? 1 : level;
+  job.dst = (uint8_t*)malloc(job.n_blocks * 65536 + 1); job.csize = (uint32_t*)calloc(job.n_blocks + 1, 4);
+  uint64_t* coff = (uint64_t*)malloc((job.n_blocks + 2) * sizeof(uint64_t));
+  if (!job.dst || !job.csize || !coff) { free(w.p); free(rec_off); free(rec_end); free(job.dst); free(job.csize); free(coff); return HM_ERR_ARG; }
+  pthread_mutex_init(&job.mu, NULL);
+  int nt = threads < 1 ? 1 : (threads > 64 ? 64 : threads);
+  pthread_t th[64];
+  for (int t = 1; t < nt; t++) pthread_create(&th[t], NULL, deflate_worker, &job);
+  deflate_worker(&job);
+  for (int t = 1; t < nt; t++) pthread_join(th[t], NULL);
+  pthread_mutex_destroy(&job.mu);
+  FILE* f = job.error ? NULL : fopen(path, "wb");
+  if (!f) rc = HM_ERR_ARG;
+  coff[0] = 0;
+  for (size_t i = 0; i < job.n_blocks && !rc; i++) {
+    if (fwrite(job.dst + i * 65536, 1, job.csize[i], f) != job.csize[i]) rc = HM_ERR_ARG;
+    coff[i + 1] = coff[i] + job.csize[i];
+  }
+  static const uint8_t BGZF_EOF[28] = {0x1f, 0x8b, 8, 4, 0, 0, 0, 0, 0, 0xff, 6, 0, 0x42, 0x43, 2, 0, 0x1b, 0, 3, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  if (!rc && fwrite(BGZF_EOF, 1, 28, f) != 28) rc = HM_ERR_ARG;
+  if (f) fclose(f);
+  /* BAI: bins (adjacent records of one bin merged into one chunk) + 16 kb linear index */
+  if (!rc) {
+#define VOFF(o) ((coff[(o) / WBLK] << 16) | (uint64_t)((o) % WBLK))
+    const int32_t n_lin = contig_len > 0 ? ((contig_len - 1) >> 14) + 1 : 0;
+    uint64_t* lin = (uint64_t*)calloc((size_t)n_lin + 1, 8);
+    typedef struct { uint32_t bin; uint64_t beg, end; } bchunk_t;
+    bchunk_t* ch = (bchunk_t*)malloc((n + 1) * sizeof(bchunk_t));
+    size_t nch = 0;
+    for (size_t r = 0; r < n; r++) {
+      const int32_t pos = b->tstart[r], endp = rec_end[r];
+      const uint64_t v0 = VOFF(rec_off[r]), v1 = VOFF(rec_off[r + 1]);
+      const uint32_t bin = (uint32_t)reg2bin(pos, endp);
+      if (nch && ch[nch - 1].bin == bin && ch[nch - 1].end == v0) ch[nch - 1].end = v1;
+      else { ch[nch].bin = bin; ch[nch].beg = v0; ch[nch].end = v1; nch++; }
+      for (int32_t wv = pos >> 14; wv <= ((endp - 1) >> 14) && wv < n_lin; wv++) if (!lin[wv]) lin[wv] = v0;
+    }
+    /* group chunks by bin (stable insertion into per-bin lists via a sort on (bin, order)) */
+    size_t* order = (size_t*)malloc((nch + 1) * sizeof(size_t));
+    for (size_t i = 0; i < nch; i++) order[i] = i;
+    /* counting sort by bin (bins < 37450) */
+    uint32_t* cnt = (uint32_t*)calloc(37451, 4);
+    for (size_t i = 0; i < nch; i++) cnt[ch[i].bin + 1]++;
+    for (int i = 0; i < 37450; i++) cnt[i + 1] += cnt[i];
+    for (size_t i = 0; i < nch; i++) order[cnt[ch[i].bin]++] = i;
+    size_t lp = strlen(path);
+    char* ip = (char*)malloc(lp + 5); memcpy(ip, path, lp); memcpy(ip + lp, ".bai", 5);
+    FILE* g = fopen(ip, "wb");
+    free(ip);
+    if (!g) rc = HM_ERR_ARG;
+    else {
+      wbuf_t x; memset(&x, 0, sizeof(x));
+      wb_need(&x, 64 + nch * 28 + (size_t)n_lin * 8);
+      memcpy(x.p, "BAI\1", 4); x.n = 4; wb_u32(&x, 1);
+      uint32_t n_bins = 0;
+      for (size_t i = 0; i < nch; i++) if (i == 0 || ch[order[i]].bin != ch[order[i - 1]].bin) n_bins++;
+      wb_u32(&x, n_bins);
+      for (size_t i = 0; i < nch;) {
+        size_t j = i;
+        while (j < nch && ch[order[j]].bin == ch[order[i]].bin) j++;
+        wb_u32(&x, ch[order[i]].bin); wb_u32(&x, (uint32_t)(j - i));
+        for (size_t k = i; k < j; k++) {
+          const uint64_t a = ch[order[k]].beg, e = ch[order[k]].end;
+          wb_u32(&x, (uint32_t)a); wb_u32(&x, (uint32_t)(a >> 32)); wb_u32(&x, (uint32_t)e); wb_u32(&x, (uint32_t)(e >> 32));
+        }
+        i = j;
+      }
+      wb_u32(&x, (uint32_t)n_lin);
+      uint64_t last = 0;
+      for (int32_t k = 0; k < n_lin; k++) { if (lin[k]) last = lin[k]; const uint64_t v = lin[k] ? lin[k] : last; wb_u32(&x, (uint32_t)v); wb_u32(&x, (uint32_t)(v >> 32)); }
+      wb_u32(&x, 0); wb_u32(&x, 0);
+      if (fwrite(x.p, 1, x.n, g) != x.n) rc = HM_ERR_ARG;
+      fclose(g); free(x.p);
+    }
+    free(lin); free(ch); free(order); free(cnt);
+#undef VOFF
+  }
+  free(w.p); free(rec_off); free(rec_end); free(job.dst); free(job.csize); free(coff);
+  return rc;
 }

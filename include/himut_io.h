@@ -51,6 +51,11 @@ int hm_bam_read_batch(hm_bam* b, int rid, int32_t start, int32_t end, int thread
  * record headers, CIGARs and tags are parsed.  HM_ERR_CAPACITY when cap is too small (*n_out = needed). */
 int hm_bam_window_qlens(hm_bam* b, int rid, int32_t start, int32_t end, int threads, int32_t* out, size_t cap, size_t* n_out);
 
+/* tests / tools / bench only: a packed batch back to a coordinate-sorted BAM + BAI (cs:Z short form, tp:A:P,
+ * query names "read<qname_id>"), BGZF blocks deflated on `threads` threads at zlib `level` */
+int hm_bam_write_batch(const char* path, const char* chrom, int32_t contig_len, const char* sample, const hm_read_batch* b,
+                       int level, int threads);
+
 /* query names are interned per handle: qname_id of a batch indexes this table, ids are stable
  * across hm_bam_read_batch calls (m.num_ccs counts distinct names per contig, caller.py:318-320) */
 uint32_t hm_bam_n_qnames(const hm_bam* b);

@@ -129,3 +129,18 @@ def test_without_index_and_empty_contig(tmp_path):
     nb2 = bamdec.NativeBam(path2)
     b = nb2.read_batch("chr1", 0, 1000)
     assert b.n_reads == 0 and b.seq.size == 16 and b.bq.size == 16
+
+
+def test_native_writer_equals_python_writer(tmp_path):
+    d = synth.generate(150_000, seed=14)
+    p_py, p_c = str(tmp_path / "py.bam"), str(tmp_path / "c.bam")
+    bamio.write_batch_bam(p_py, "chr1", 150_000, d.batch)
+    bamdec.write_batch_bam(p_c, "chr1", 150_000, d.batch, threads=3)
+    a, b = bamio.BamReader(p_py), bamio.BamReader(p_c)
+    assert a.header_text == b.header_text and a.references == b.references and a.lengths == b.lengths
+    key = lambda r: (r.query_name, r.reference_start, r.reference_end, r.flag, r.mapping_quality, r.tags.get("cs"), r.tags.get("tp"),
+                     bytes(r.qual), bytes(r.seq_nibbles), r.query_alignment_start, r.query_alignment_end)
+    for s, e in [(0, 150_000), (70_000, 70_001), (149_000, 150_000)]:
+        assert [key(r) for r in a.fetch("chr1", s, e)] == [key(r) for r in b.fetch("chr1", s, e)]
+    nb = bamdec.NativeBam(p_c, threads=2)
+    assert cases.batch_digest(nb.read_batch("chr1", 0, 150_000)) == cases.batch_digest(d.batch)
