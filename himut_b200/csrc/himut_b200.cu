@@ -874,6 +874,25 @@ static int hm_normcounts_impl(hm_ctx* ctx, const uint8_t* refseq, size_t ref_len
         site_cap = n_sites;
       }
       ctx->last_norm_sites = n_sites;
+      const bool by_site = getenv("HIMUT_B200_ENTRIES_BY_SITE") != nullptr; // thread-per-(site, read) gather (A/B)
+      const unsigned long long* site_keys = ctx->b_sites.as<unsigned long long>();
+      if (n_sites && !by_site) {
+        // the list comes out in tile-completion order: sort it (chunk, position) so a read finds its sites by range
+        CU(ctx->b_keys_sorted.ensure(n_sites * 8));
+        int end_bit = 36;
+        for (size_t cc = n_chunks; cc > 0; cc >>= 1) end_bit++;
+        size_t tmp_sort = 0;
+        CU(cub::DeviceRadixSort::SortKeys(nullptr, tmp_sort, ctx->b_sites.as<unsigned long long>(), ctx->b_keys_sorted.as<unsigned long long>(),
+                                          (int64_t)n_sites, 4, std::min(end_bit, 64), ctx->stream));
+        CU(ctx->b_cub.ensure(tmp_sort));
+        CU(ctx->b_koff.ensure((n_chunks + 2) * 4));
+        t_begin(ctx, "cub_sort_site_list");
+        CU(cub::DeviceRadixSort::SortKeys(ctx->b_cub.p, tmp_sort, ctx->b_sites.as<unsigned long long>(), ctx->b_keys_sorted.as<unsigned long long>(),
+                                          (int64_t)n_sites, 4, std::min(end_bit, 64), ctx->stream));
+        site_keys = ctx->b_keys_sorted.as<unsigned long long>();
+        k_chunk_key_ranges<<<(unsigned)((n_chunks + 1 + 127) / 128), 128, 0, ctx->stream>>>(site_keys, d_nsites, (uint32_t)n_chunks, ctx->b_koff.as<uint32_t>());
+        t_end(ctx);
+      }
       const unsigned long long SITE_BATCH = 1ull << 21;
       for (unsigned long long s0 = 0; s0 < n_sites; s0 += SITE_BATCH) {
         const uint64_t nb = (uint64_t)std::min<unsigned long long>(SITE_BATCH, n_sites - s0);
@@ -882,15 +901,24 @@ static int hm_normcounts_impl(hm_ctx* ctx, const uint8_t* refseq, size_t ref_len
         uint32_t* entries = ctx->b_agg.as<uint32_t>();
         uint32_t* site_lo = entries + stride * HM_SITE_SLOTS;
         uint32_t* site_n = site_lo + nb;
-        const unsigned long long* keys = ctx->b_sites.as<unsigned long long>() + s0;
+        const unsigned long long* keys = site_keys + s0;
         t_begin(ctx, "k_norm_site_range");
         k_norm_site_range<<<(unsigned)((nb + 255) / 256), 256, 0, ctx->stream>>>(ctx->db, ctx->b_chunks.as<hm_chunk>(), keys, nb, site_lo, site_n);
         t_end(ctx);
-        t_begin(ctx, "k_norm_entries");
-        k_norm_entries<<<(unsigned)((nb + 15) / 16), 1024, 0, ctx->stream>>>(ctx->db, ctx->dp, ctx->b_chunks.as<hm_chunk>(),
-                                                                            ctx->b_pair_off.as<uint64_t>(), ctx->b_pair_hap.as<uint8_t>(),
-                                                                            keys, nb, site_lo, site_n, entries, stride);
-        t_end(ctx);
+        if (by_site) {
+          t_begin(ctx, "k_norm_entries");
+          k_norm_entries<<<(unsigned)((nb + 15) / 16), 1024, 0, ctx->stream>>>(ctx->db, ctx->dp, ctx->b_chunks.as<hm_chunk>(),
+                                                                              ctx->b_pair_off.as<uint64_t>(), ctx->b_pair_hap.as<uint8_t>(),
+                                                                              keys, nb, site_lo, site_n, entries, stride);
+          t_end(ctx);
+        } else {
+          t_begin(ctx, "k_norm_entries_by_read");
+          CU(cudaMemsetAsync(entries, 0xff, stride * HM_SITE_SLOTS * 4, ctx->stream));
+          k_norm_entries_by_read<<<(unsigned)((n_pairs * 32 + 255) / 256), 256, 0, ctx->stream>>>(
+              ctx->db, ctx->dp, ctx->b_chunks.as<hm_chunk>(), (uint32_t)n_chunks, ctx->b_pair_off.as<uint64_t>(), n_pairs,
+              ctx->b_pair_hap.as<uint8_t>(), site_keys, ctx->b_koff.as<uint32_t>(), (uint64_t)s0, nb, site_lo, site_n, entries, stride);
+          t_end(ctx);
+        }
         t_begin(ctx, "k_norm_reduce");
         k_norm_reduce<<<(unsigned)((nb + 127) / 128), 128, 0, ctx->stream>>>(
             ctx->db, ctx->dp, ctx->dsets, ctx->dlut, ctx->b_chunks.as<hm_chunk>(), ctx->b_pair_off.as<uint64_t>(),

@@ -668,6 +668,95 @@ __global__ void __launch_bounds__(1024) k_norm_entries(DevBatch b, DevParams p, 
   entries[(uint64_t)slot * stride + ki] = norm_entry(b, p, ch, pair_flag[pair_off[c] + (r - ch.read_lo)], r, pos);
 }
 
+// The same gather turned around (see k_site_entries_by_read): one warp per (chunk, read) pair stages the read's op
+// arrays and mismatch list in shared memory and serves every listed site of the chunk the read covers.  `keys` must
+// be sorted (chunk, position); [s0, s0 + nb) is the slice of it this launch fills (entries are slice relative).
+__global__ void __launch_bounds__(256) k_norm_entries_by_read(DevBatch b, DevParams p, const hm_chunk* chunks, uint32_t n_chunks,
+                                                              const uint64_t* pair_off, uint64_t n_pairs, const uint8_t* pair_flag,
+                                                              const unsigned long long* keys, const uint32_t* koff, uint64_t s0, uint64_t nb,
+                                                              const uint32_t* site_lo, const uint32_t* site_n, uint32_t* entries,
+                                                              uint64_t stride) {
+  __shared__ uint32_t s_w[8][HM_BYREAD_MAX_OPS], s_t[8][HM_BYREAD_MAX_OPS], s_q[8][HM_BYREAD_MAX_OPS];
+  __shared__ int32_t s_m[8][HM_BYREAD_MAX_OPS];
+  const uint64_t pr = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (pr >= n_pairs) return;
+  const uint32_t pf = pair_flag[pr];
+  if (!(pf & HM_PF_FETCHED)) return;
+  const uint32_t c = upper_bound_dev(pair_off, n_chunks + 1, pr) - 1;
+  const hm_chunk ch = chunks[c];
+  const uint32_t r = ch.read_lo + (uint32_t)(pr - pair_off[c]);
+  const int32_t ts = __ldg(b.tstart + r), te = __ldg(b.tend + r);
+  const uint32_t n = __ldg(b.n_ops + r);
+  if (n == 0) return;
+  const uint32_t k_lo = max(koff[c], (uint32_t)s0), k_hi = min(koff[c + 1], (uint32_t)(s0 + nb));
+  if (k_lo >= k_hi) return;
+  const unsigned long long base = (unsigned long long)c << 36;
+  const uint32_t s_lo = warp_lower_bound_u64(keys, k_lo, k_hi, base | ((unsigned long long)(uint32_t)(ts + 1) << 4), lane);
+  const uint32_t s_hi = warp_lower_bound_u64(keys, s_lo, k_hi, base | ((unsigned long long)(uint32_t)(te + 2) << 4), lane);
+  if (s_lo >= s_hi) return;
+  const uint64_t o0 = __ldg(b.op_off + r);
+  const uint32_t nmm = (uint32_t)__ldg(b.n_mm + r);
+  const bool staged = n <= HM_BYREAD_MAX_OPS;
+  if (staged) {
+    for (uint32_t k = lane; k < n; k += 32) {
+      s_w[wid][k] = __ldg(b.ops + o0 + k); s_t[wid][k] = __ldg(b.op_t + o0 + k); s_q[wid][k] = __ldg(b.op_q + o0 + k);
+      if (k < nmm) s_m[wid][k] = __ldg(b.mm_pos + o0 + k);
+    }
+    __syncwarp();
+  }
+  const uint64_t bq0 = __ldg(b.bq_off + r), sq0 = __ldg(b.seq_off + r);
+  const int32_t qlen = __ldg(b.qlen + r);
+  const int32_t trim_s = (int32_t)floor(__dmul_rn(p.min_trim, (double)qlen));
+  const int32_t trim_e = (int32_t)ceil(__dmul_rn(__dsub_rn(1.0, p.min_trim), (double)qlen));
+  const int w = p.mismatch_window;
+  for (uint32_t ki = s_lo + lane; ki < s_hi; ki += 32) {
+    const uint32_t li = ki - (uint32_t)s0;
+    const uint32_t slot = r - __ldg(site_lo + li);
+    if (slot >= HM_SITE_SLOTS || slot >= __ldg(site_n + li)) continue; // deep pileups: k_norm_reduce computes these itself
+    const int32_t pos = (int32_t)((__ldg(keys + ki) >> 4) & 0xffffffffull) - 1;
+    uint32_t e;
+    if (!staged) e = norm_entry(b, p, ch, pf, r, pos);
+    else {
+      const uint32_t off = (uint32_t)(pos - ts);
+      uint32_t lo = 0, hi = n; // last op with op_t <= off
+      while (lo < hi) { const uint32_t m = (lo + hi) >> 1; if (s_t[wid][m] <= off) lo = m + 1; else hi = m; }
+      const int k = (int)lo - 1;
+      int ins = 0;
+      for (int j = k; j >= 0 && s_t[wid][j] == off; j--) ins += ((s_w[wid][j] & 3u) == HM_OP_INS);
+      const uint32_t wd = s_w[wid][k], kind = wd & 3u, t_op = s_t[wid][k], q0 = s_q[wid][k];
+      const uint32_t rl = (uint32_t)op_ref_len(wd);
+      uint32_t a = HM_ENT_NONE, bq = 0, cnt = 0;
+      if (rl != 0 && off < t_op + rl) {
+        if (kind == HM_OP_DEL) a = 5u;
+        else {
+          const uint32_t q = q0 + (kind == HM_OP_MATCH ? off - t_op : 0u);
+          bq = b.bq[bq0 + q];
+          a = kind == HM_OP_SUB ? ((wd >> 5) & 3u) : (uint32_t)((b.seq[sq0 + (q >> 2)] >> (2 * (q & 3u))) & 3u);
+          if (pf & HM_PF_PASS) {
+            if (kind == HM_OP_SUB) cnt = 1; // normcounts.py:95-108: always counted
+            else if ((int)bq >= p.min_bq && !((int32_t)q < trim_s || (int32_t)q > trim_e)) {
+              const int32_t qpos0 = (int32_t)q0;
+              const int qs = qpos0 - w, qe = qpos0 + w;
+              int u, d;
+              if (qs < 0) { u = w + qs; d = w + (-qs); }
+              else if (qe > qlen) { u = w + (qe - qlen); d = qlen - qpos0; }
+              else { u = w; d = w; }
+              // mismatches x with pos - u <= x <= pos + d (1-based list against the 0-based position, normcounts.py:82-87)
+              uint32_t l1 = 0, h1 = nmm, l2 = 0, h2 = nmm;
+              while (l1 < h1) { const uint32_t m = (l1 + h1) >> 1; if (s_m[wid][m] <= pos + d) l1 = m + 1; else h1 = m; }
+              while (l2 < h2) { const uint32_t m = (l2 + h2) >> 1; if (s_m[wid][m] <= pos - u - 1) l2 = m + 1; else h2 = m; }
+              cnt = !((int)l1 - (int)l2 > p.max_mismatch_count);
+            }
+          }
+        }
+      }
+      e = a | (bq << 3) | ((uint32_t)min(ins, 255) << 11) | (((pf >> HM_PF_HAP_SHIFT) & 3u) << 19) | (cnt << 21);
+    }
+    entries[(uint64_t)slot * stride + li] = e;
+  }
+}
+
 __global__ void __launch_bounds__(128) k_norm_reduce(DevBatch b, DevParams p, DevSets sets, DevLut lut, const hm_chunk* chunks,
                                                      const uint64_t* pair_off, const uint8_t* pair_flag,
                                                      const unsigned long long* keys, uint64_t n_keys, const uint32_t* site_lo,
@@ -700,6 +789,7 @@ __global__ void __launch_bounds__(128) k_norm_reduce(DevBatch b, DevParams p, De
     for (uint32_t s = 0; s < n; s++) {
       const uint32_t e = s < HM_SITE_SLOTS ? __ldg(entries + (uint64_t)s * stride + ki)
                                            : norm_entry(b, p, ch, pair_flag[pair_off[c] + (lo + s - ch.read_lo)], lo + s, pos);
+      if (e == HM_ENT_UNWRITTEN) continue; // a read of the range that does not reach the site
       const uint32_t a = e & 7u;
       cnt[4] += (int)((e >> 11) & 255u);
       if (a == HM_ENT_NONE) continue;
