@@ -85,7 +85,7 @@ struct hm_ctx {
   size_t ref_len = 0; // length of the contig left resident by hm_set_reference (0: none)
   NormCert cert;      // certified-verdict constants of the normcounts fast pass
   unsigned long long last_norm_sites = 0; // positions the last normcounts call evaluated exactly
-  DevBuf b_sites, b_koff;
+  DevBuf b_sites, b_koff, b_tile_info;
 };
 
 namespace {
@@ -256,7 +256,7 @@ void hm_destroy(hm_ctx* ctx) {
                     &ctx->b_ins_len, &ctx->b_del_len, &ctx->b_n_mm, &ctx->b_gate, &ctx->b_pmax, &ctx->b_tix_off, &ctx->b_tix, &ctx->b_common, &ctx->b_pon,
                     &ctx->b_hpos, &ctx->b_href, &ctx->b_halt, &ctx->b_hbit, &ctx->b_set_off, &ctx->b_chunks,
                     &ctx->b_pair_off, &ctx->b_pair_hap, &ctx->b_qseen, &ctx->b_keys, &ctx->b_keys_sorted, &ctx->b_cub,
-                    &ctx->b_records, &ctx->b_counters, &ctx->b_ref, &ctx->b_norm_out, &ctx->b_lut, &ctx->b_tile_off, &ctx->b_agg, &ctx->b_geom, &ctx->b_bidx, &ctx->b_sites, &ctx->b_koff};
+                    &ctx->b_records, &ctx->b_counters, &ctx->b_ref, &ctx->b_norm_out, &ctx->b_lut, &ctx->b_tile_off, &ctx->b_agg, &ctx->b_geom, &ctx->b_bidx, &ctx->b_sites, &ctx->b_koff, &ctx->b_tile_info};
   for (DevBuf* b : bufs) b->release();
   if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
   for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
@@ -849,7 +849,11 @@ static int hm_normcounts_impl(hm_ctx* ctx, const uint8_t* refseq, size_t ref_len
       if (const char* g = getenv("HIMUT_B200_NORM_SITE_CAP")) site_cap = std::max(1ll, atoll(g));
       unsigned long long n_sites = 0;
       CU(ctx->b_tix.ensure((size_t)ctx->n_tix * 16 + 16));
+      CU(ctx->b_tile_info.ensure((size_t)n_tiles_fast * 16 + 16));
       t_begin(ctx, "k_tile_index");
+      k_tile_ranges<<<(unsigned)((n_tiles_fast + 255) / 256), 256, 0, ctx->stream>>>(ctx->db, ctx->b_chunks.as<hm_chunk>(), (uint32_t)n_chunks,
+                                                                                  ctx->b_tile_off.as<uint64_t>() + 2 * (n_chunks + 1),
+                                                                                  (uint32_t)n_tiles_fast, ctx->b_tile_info.as<uint4>());
       k_tile_index<<<(unsigned)((ctx->n_reads * 32 + 255) / 256), 256, 0, ctx->stream>>>(ctx->db, ctx->dp.mismatch_window,
                                                                                          ctx->b_tix_off.as<uint32_t>(), ctx->b_tix.as<uint4>());
       t_end(ctx);
@@ -863,7 +867,7 @@ static int hm_normcounts_impl(hm_ctx* ctx, const uint8_t* refseq, size_t ref_len
         t_begin(ctx, "k_norm_fast");
         k_norm_fast<<<grid, HF_CONS + 32 * HF_NPROD, smem, ctx->stream>>>(
             ctx->db, ctx->dp, ctx->cert, ctx->b_chunks.as<hm_chunk>(), (uint32_t)n_chunks, ctx->b_pair_off.as<uint64_t>(),
-            ctx->b_pair_hap.as<uint8_t>(), ctx->b_tile_off.as<uint64_t>() + 2 * (n_chunks + 1), (uint32_t)n_tiles_fast,
+            ctx->b_pair_hap.as<uint8_t>(), ctx->b_tile_info.as<uint4>(), (uint32_t)n_tiles_fast,
             ctx->b_tix_off.as<uint32_t>(), ctx->b_tix.as<uint4>(), ctx->b_ref.as<uint8_t>(), (uint64_t)ref_len, ctx->b_norm_out.as<NormOut>(), ctx->b_sites.as<unsigned long long>(), site_cap,
             d_nsites);
         t_end(ctx);

@@ -30,13 +30,17 @@
 
 #define HF_TW 2048                         // positions per tile
 #define HF_CONS (HF_TW / 4)                // consumer threads, 4 positions each
-#define HF_NPROD 4                         // producer warps
 #define HF_NSTAGE 4
+#define HF_NSPLIT 2                        // producer warps that share one stage (each fills HF_SLOTS / HF_NSPLIT slots)
+#define HF_NPROD (HF_NSTAGE * HF_NSPLIT)   // producer warps: a lane's work is serial, so throughput comes from the warp count
 #define HF_SLOTS 16                        // reads per stage
 #define HF_PAD 16                          // bytes of slack in front of the staged data (64 bases)
 #define HF_BQ_BUF (HF_PAD + HF_TW + 128)   // staged quality bytes per read
 #define HF_SEQ_BUF (HF_PAD + HF_TW / 4 + 48)
 #define HF_MAX_SEG 6                       // runs of constant (query - reference) offset per read and tile
+#ifndef HF_WAIT_NS
+#define HF_WAIT_NS 128
+#endif
 #define HF_MAX_WALK 1024                   // ops x mismatches a producer lane is willing to fold
 
 // Certified verdict of the genotype model at a pure position (host-computed from hm_params, see
@@ -135,6 +139,23 @@ __global__ void __launch_bounds__(256) k_tile_index(DevBatch b, int32_t window, 
     }
     tix[(uint64_t)tix_off[r] + (uint32_t)(g - g0)] = e;
   }
+}
+
+// Per tile of the fast pass: its chunk, origin on the 2048 grid and the file-order range of reads that can touch
+// it (running-max(tend) >= first position, tstart < end), so that neither the producer nor the consumer warps of
+// k_norm_fast search for them.  One thread per tile.
+__global__ void __launch_bounds__(256) k_tile_ranges(DevBatch b, const hm_chunk* chunks, uint32_t n_chunks, const uint64_t* tile_off,
+                                                     uint32_t n_tiles, uint4* tile_info) {
+  const uint32_t tile = blockIdx.x * blockDim.x + threadIdx.x;
+  if (tile >= n_tiles) return;
+  const uint32_t c = upper_bound_dev(tile_off, n_chunks + 1, (uint64_t)tile) - 1;
+  const hm_chunk ch = chunks[c];
+  const int32_t t0 = ((ch.start >> 11) + (int32_t)(tile - tile_off[c])) << 11;
+  const int32_t lo_pos = max(t0, ch.start), t1 = min(t0 + HF_TW, ch.end);
+  const uint32_t n_in = ch.read_hi - ch.read_lo;
+  const uint32_t r_lo = ch.read_lo + count_le_kary_i32(b.pmax_tend + ch.read_lo, n_in, lo_pos - 1);
+  const uint32_t r_hi = ch.read_lo + count_le_kary_i32(b.tstart + ch.read_lo, n_in, t1 - 1);
+  tile_info[tile] = make_uint4(c, (uint32_t)t0, r_lo, r_hi);
 }
 
 #define HF_SCR_OPS 128   // ops of one read inside one tile the producer stages (3 words each) ...
@@ -318,11 +339,23 @@ __device__ __forceinline__ void fast_fill_slot(const DevBatch& b, const DevParam
   FILL_T(5);
 }
 
+// consumer-side wait: a warp that finds the stage not ready sleeps between probes, so that the 16 waiting
+// consumer warps leave the issue slots to the 4 producer warps they are waiting for
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity) {
+  uint32_t ok = 0;
+  for (;;) {
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    if (ok) break;
+    __nanosleep(HF_WAIT_NS);
+  }
+}
+
 __device__ __forceinline__ uint32_t spread4(uint32_t nib) { return (nib * 0x00204081u) & 0x01010101u; } // bit k -> bit 8k
 
 __global__ void __launch_bounds__(HF_CONS + 32 * HF_NPROD, 1)
 k_norm_fast(DevBatch b, DevParams p, NormCert cert, const hm_chunk* chunks, uint32_t n_chunks, const uint64_t* pair_off,
-            const uint8_t* pair_flag, const uint64_t* tile_off, uint32_t n_tiles, const uint32_t* tix_off, const uint4* tix,
+            const uint8_t* pair_flag, const uint4* tile_info, uint32_t n_tiles, const uint32_t* tix_off, const uint4* tix,
             const uint8_t* refseq, uint64_t ref_len,
             NormOut* out, unsigned long long* sites, unsigned long long site_cap, unsigned long long* n_sites) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
@@ -345,23 +378,20 @@ k_norm_fast(DevBatch b, DevParams p, NormCert cert, const hm_chunk* chunks, uint
   if (is_producer) {
     // ------------------------------------------------------------------ producer warps
     const uint32_t pw = (uint32_t)(tid - HF_CONS) >> 5;
-    uint32_t c = 0; // tiles are visited in increasing order: a running chunk cursor replaces a search
     for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-      while (c + 1 < n_chunks && (uint64_t)tile >= __ldg(tile_off + c + 1)) c++;
+      const uint4 ti = __ldg(tile_info + tile); // chunk, origin on the 2048 grid, read range (k_tile_ranges)
+      const uint32_t c = ti.x, r_lo = ti.z, r_hi = ti.w;
       const hm_chunk ch = chunks[c];
-      // tiles sit on the absolute 2048 grid (k_tile_index); the chunk clips the first and the last one
-      const int32_t t0 = ((ch.start >> 11) + (int32_t)(tile - tile_off[c])) << 11;
+      const int32_t t0 = (int32_t)ti.y;
       const int32_t lo_pos = max(t0, ch.start);
       const int32_t t1 = min(t0 + HF_TW, ch.end);
-      const uint32_t n_in = ch.read_hi - ch.read_lo;
-      const uint32_t r_lo = ch.read_lo + warp_count_below<true>(b.pmax_tend + ch.read_lo, n_in, lo_pos, lane);
-      const uint32_t r_hi = ch.read_lo + warp_count_below<true>(b.tstart + ch.read_lo, n_in, t1, lane);
       const bool deep = r_hi > r_lo && r_hi - r_lo > 255u; // the packed 8-bit tallies would overflow
       const uint64_t pbase = pair_off[c];
       const uint32_t n_batches = (deep || r_hi <= r_lo) ? 1u : (r_hi - r_lo + HF_SLOTS - 1) / HF_SLOTS;
       for (uint32_t bi = 0; bi < n_batches; bi++, batch_no++) {
-        if (batch_no % HF_NPROD != pw) continue;
+        if (batch_no % HF_NSTAGE != pw / HF_NSPLIT) continue; // warps pw / HF_NSPLIT == stage fill it together
         const uint32_t st = batch_no % HF_NSTAGE, ph = (batch_no / HF_NSTAGE) & 1;
+        const uint32_t part = pw % HF_NSPLIT;
 #ifdef HM_NORM_DEBUG
         const long long c0 = clock64();
 #endif
@@ -371,13 +401,14 @@ k_norm_fast(DevBatch b, DevParams p, NormCert cert, const hm_chunk* chunks, uint
 #endif
         FastStage* T = &stages[st];
         const uint32_t r0 = r_lo + bi * HF_SLOTS;
-        const uint32_t r = r0 + lane;
+        const uint32_t slot = part * (HF_SLOTS / HF_NSPLIT) + (uint32_t)lane;
+        const uint32_t r = r0 + slot;
         const uint32_t nb = deep ? 0u : min(r_hi > r0 ? r_hi - r0 : 0u, (uint32_t)HF_SLOTS);
-        if (lane == 0) { T->n_slots = (int32_t)nb; T->last = (bi + 1 == n_batches) ? 1 : 0; T->deep = deep ? 1 : 0; }
-        if (lane < HF_SLOTS) {
-          if ((uint32_t)lane < nb) {
+        if (lane == 0 && part == 0) { T->n_slots = (int32_t)nb; T->last = (bi + 1 == n_batches) ? 1 : 0; T->deep = deep ? 1 : 0; }
+        if (lane < HF_SLOTS / HF_NSPLIT) {
+          if (slot < nb) {
             const uint32_t pf = pair_flag[pbase + (r - ch.read_lo)];
-            fast_fill_slot(b, p, tix_off, tix, &T->slot[lane], &full_bar[st], r, pf, t0, lo_pos, t1);
+            fast_fill_slot(b, p, tix_off, tix, &T->slot[slot], &full_bar[st], r, pf, t0, lo_pos, t1);
           } else {
             mbar_arrive(&full_bar[st]);
           }
@@ -395,11 +426,11 @@ k_norm_fast(DevBatch b, DevParams p, NormCert cert, const hm_chunk* chunks, uint
   const int p0 = tid * 4;                 // first tile-relative position of this thread
   const uint32_t sh4 = (uint32_t)(tid & 7) * 4u;
   const uint32_t kge = (uint32_t)(128 - p.min_bq) * 0x01010101u; // byte >= min_bq  <=>  bit 7 of (byte & 0x7f) + 128 - min_bq, or of byte
-  uint32_t c = 0;
   for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    while (c + 1 < n_chunks && (uint64_t)tile >= __ldg(tile_off + c + 1)) c++;
+    const uint4 ti = __ldg(tile_info + tile);
+    const uint32_t c = ti.x;
     const hm_chunk ch = chunks[c];
-    const int32_t t0 = ((ch.start >> 11) + (int32_t)(tile - tile_off[c])) << 11;
+    const int32_t t0 = (int32_t)ti.y;
     const int32_t t1 = min(t0 + HF_TW, ch.end);
     // reference bases pos-1 .. pos+4 now, so the loads hide behind the read loop
     uint8_t rb[6];
@@ -426,7 +457,7 @@ k_norm_fast(DevBatch b, DevParams p, NormCert cert, const hm_chunk* chunks, uint
 #ifdef HM_NORM_DEBUG
       const long long d0 = clock64();
 #endif
-      mbar_wait(&full_bar[st], ph);
+      mbar_wait_sleep(&full_bar[st], ph);
 #ifdef HM_NORM_DEBUG
       const long long d1 = clock64();
 #endif
