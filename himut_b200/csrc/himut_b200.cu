@@ -85,7 +85,9 @@ struct hm_ctx {
   size_t ref_len = 0; // length of the contig left resident by hm_set_reference (0: none)
   NormCert cert;      // certified-verdict constants of the normcounts fast pass
   unsigned long long last_norm_sites = 0; // positions the last normcounts call evaluated exactly
-  DevBuf b_sites, b_koff, b_tile_info;
+  DevBuf b_sites, b_koff, b_tile_info, b_edge_counts, b_edge_hpos, b_edge_href;
+  uint64_t edge_n = 0;
+  uint32_t edge_band = 0;
 };
 
 namespace {
@@ -256,7 +258,7 @@ void hm_destroy(hm_ctx* ctx) {
                     &ctx->b_ins_len, &ctx->b_del_len, &ctx->b_n_mm, &ctx->b_gate, &ctx->b_pmax, &ctx->b_tix_off, &ctx->b_tix, &ctx->b_common, &ctx->b_pon,
                     &ctx->b_hpos, &ctx->b_href, &ctx->b_halt, &ctx->b_hbit, &ctx->b_set_off, &ctx->b_chunks,
                     &ctx->b_pair_off, &ctx->b_pair_hap, &ctx->b_qseen, &ctx->b_keys, &ctx->b_keys_sorted, &ctx->b_cub,
-                    &ctx->b_records, &ctx->b_counters, &ctx->b_ref, &ctx->b_norm_out, &ctx->b_lut, &ctx->b_tile_off, &ctx->b_agg, &ctx->b_geom, &ctx->b_bidx, &ctx->b_sites, &ctx->b_koff, &ctx->b_tile_info};
+                    &ctx->b_records, &ctx->b_counters, &ctx->b_ref, &ctx->b_norm_out, &ctx->b_lut, &ctx->b_tile_off, &ctx->b_agg, &ctx->b_geom, &ctx->b_bidx, &ctx->b_sites, &ctx->b_koff, &ctx->b_tile_info, &ctx->b_edge_counts, &ctx->b_edge_hpos, &ctx->b_edge_href};
   for (DevBuf* b : bufs) b->release();
   if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
   for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
@@ -730,6 +732,64 @@ int hm_ref_tricounts(hm_ctx* ctx, const uint8_t* refseq, size_t ref_len, int64_t
 int hm_last_norm_exact_sites(hm_ctx* ctx, uint64_t* n) {
   if (!ctx || !n) return HM_ERR_ARG;
   *n = (uint64_t)ctx->last_norm_sites;
+  return HM_OK;
+}
+
+/* ---- `himut phase` edge counting (phaselib.get_edges) ---- */
+int hm_phase_edges_begin(hm_ctx* ctx, const int32_t* hpos, const uint8_t* href, size_t n_hetsnp, uint32_t band) {
+  if (!ctx || (n_hetsnp && (!hpos || !href)) || band == 0) return HM_ERR_ARG;
+  CU(cudaSetDevice(ctx->device));
+  for (size_t i = 1; i < n_hetsnp; i++) if (hpos[i - 1] > hpos[i]) return fail(ctx, HM_ERR_ARG, "hpos is not ascending");
+  if ((uint64_t)n_hetsnp * band * 16 > (64ull << 30)) return fail(ctx, HM_ERR_ARG, "edge table of %zu x %u entries is too large", n_hetsnp, band);
+  int rc;
+  if ((rc = upload(ctx, ctx->b_edge_hpos, hpos, n_hetsnp))) return rc;
+  if ((rc = upload(ctx, ctx->b_edge_href, href, n_hetsnp))) return rc;
+  const size_t bytes = (size_t)n_hetsnp * band * 16 + 16;
+  CU(ctx->b_edge_counts.ensure(bytes));
+  CU(cudaMemsetAsync(ctx->b_edge_counts.p, 0, bytes, ctx->stream));
+  CU(ctx->b_counters.ensure(256));
+  CU(cudaMemsetAsync(ctx->b_counters.as<unsigned long long>() + 6, 0, 8, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  ctx->edge_n = n_hetsnp; ctx->edge_band = band;
+  return HM_OK;
+}
+
+int hm_phase_edges_add(hm_ctx* ctx, int32_t min_bq, int32_t min_mapq, int32_t min_tstart, uint32_t* need_band) {
+  if (!ctx || !need_band) return HM_ERR_ARG;
+  if (!ctx->have_batch) return fail(ctx, HM_ERR_STATE, "no resident batch: call hm_upload_batch first");
+  if (!ctx->edge_band) return fail(ctx, HM_ERR_STATE, "hm_phase_edges_begin has not been called");
+  CU(cudaSetDevice(ctx->device));
+  t_reset(ctx);
+  int rc = launch_read_scan(ctx); // for its op prefixes; the read gates it also computes are not used here
+  if (rc) return rc;
+  unsigned int* d_need = reinterpret_cast<unsigned int*>(ctx->b_counters.as<unsigned long long>() + 6);
+  if (ctx->n_reads && ctx->edge_n >= 2) {
+    t_begin(ctx, "k_phase_edges");
+    k_phase_edges<<<(unsigned)((ctx->n_reads * 32 + 127) / 128), 128, 0, ctx->stream>>>(
+        ctx->db, ctx->b_edge_hpos.as<int32_t>(), ctx->b_edge_href.as<uint8_t>(), (uint32_t)ctx->edge_n, min_bq, min_mapq, min_tstart,
+        ctx->edge_band, ctx->b_edge_counts.as<unsigned int>(), d_need);
+    t_end(ctx);
+    CU(cudaGetLastError());
+  }
+  unsigned int need = 0;
+  CU(cudaMemcpyAsync(&need, d_need, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  t_collect(ctx);
+  *need_band = need;
+  if (need == 0xffffffffu) return fail(ctx, HM_ERR_CAPACITY, "a read covers more than %d hetSNPs", HM_EDGE_MAX_SNPS);
+  if (need > ctx->edge_band) return fail(ctx, HM_ERR_CAPACITY, "a read pairs hetSNPs %u apart in the list; the band is %u", need, ctx->edge_band);
+  return HM_OK;
+}
+
+int hm_phase_edges_end(hm_ctx* ctx, uint32_t* counts, size_t cap_entries) {
+  if (!ctx || !counts) return HM_ERR_ARG;
+  if (!ctx->edge_band) return fail(ctx, HM_ERR_STATE, "hm_phase_edges_begin has not been called");
+  const size_t n = (size_t)ctx->edge_n * ctx->edge_band * 4;
+  if (cap_entries < n) return fail(ctx, HM_ERR_CAPACITY, "output holds %zu counters, %zu needed", cap_entries, n);
+  CU(cudaSetDevice(ctx->device));
+  if (n) CU(cudaMemcpyAsync(counts, ctx->b_edge_counts.p, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  ctx->edge_band = 0; ctx->edge_n = 0;
   return HM_OK;
 }
 

@@ -928,3 +928,50 @@ __global__ void __launch_bounds__(256) k_norm_site_range(DevBatch b, const hm_ch
   site_lo[ki] = ch.read_lo + lo;
   site_n[ki] = hi > lo ? hi - lo : 0u;
 }
+
+// ============================================================================ k_phase_edges
+// `himut phase` edge counting (phaselib.get_edges, src/himut/phaselib.py:16-67): for every primary read with
+// MAPQ >= min_mapq that covers at least two hetSNPs (hpos in (tstart, tend]), every ordered pair (a < b) of them
+// whose bases both have BQ >= min_bq adds one to a 2 x 2 table: cis1 (ref, ref), cis2 (non-ref, non-ref),
+// trans1 (ref, non-ref), trans2 (non-ref, ref).  Tables live in a band: counts[(a * band + (b - a - 1)) * 4 + k].
+// One warp per read: lanes classify the read at its hetSNPs (32 at a time, states kept in shared memory), then
+// lanes enumerate the pairs.  *need_band reports the widest pair seen so the host can retry with a wider band.
+#define HM_EDGE_MAX_SNPS 1024 // hetSNPs per read held in shared memory
+__global__ void __launch_bounds__(128) k_phase_edges(DevBatch b, const int32_t* hpos, const uint8_t* href, uint32_t n_snp,
+                                                     int32_t min_bq, int32_t min_mapq, int32_t min_tstart, uint32_t band,
+                                                     unsigned int* counts, unsigned int* need_band) {
+  __shared__ uint8_t s_state[4][HM_EDGE_MAX_SNPS];
+  const uint64_t r = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (r >= b.n_reads) return;
+  if (b.flags[r] & HM_READ_SECONDARY) return;           // BAM.is_primary (bamlib.py:17-20)
+  if ((int32_t)b.mapq[r] < min_mapq) return;
+  const int32_t ts = b.tstart[r], te = b.tend[r];
+  if (ts < min_tstart) return;                           // counted with the previous window of the contig
+  const uint32_t idx = upper_bound_dev(hpos, n_snp, ts), jdx = upper_bound_dev(hpos, n_snp, te);
+  if (jdx - idx < 2) return;
+  const uint32_t k = jdx - idx;
+  if (k > HM_EDGE_MAX_SNPS) { if (lane == 0) atomicMax(need_band, 0xffffffffu); return; }
+  for (uint32_t i = lane; i < k; i += 32) {
+    int bq, ins;
+    const int a = read_allele_fast(b, (uint32_t)r, hpos[idx + i] - 1, ts, &bq, &ins);
+    // tpos2qbase: deleted base ("-", 0); every covered position has an entry (cslib.py:153-170)
+    uint8_t st = 2;                                      // 2: skipped (BQ below min_bq)
+    if (!(bq < min_bq)) st = (a >= 0 && a < 4 && a == (int)href[idx + i]) ? 0 : 1;
+    s_state[wid][i] = st;
+  }
+  __syncwarp();
+  if (k - 1 > band) { if (lane == 0) atomicMax(need_band, k - 1); return; }
+  // pairs (x, y), x < y: lane strides over y for each x
+  for (uint32_t x = 0; x + 1 < k; x++) {
+    const uint32_t sx = s_state[wid][x];
+    if (sx == 2u) continue;
+    for (uint32_t y = x + 1 + lane; y < k; y += 32) {
+      const uint32_t sy = s_state[wid][y];
+      if (sy == 2u) continue;
+      const uint32_t kind = sx == 0u ? (sy == 0u ? 0u : 2u) : (sy == 1u ? 1u : 3u);
+      atomicAdd(counts + ((uint64_t)(idx + x) * band + (y - x - 1)) * 4 + kind, 1u);
+    }
+  }
+}
+

@@ -20,6 +20,7 @@ EXPORTS = [
     "hm_set_phase_sets", "hm_upload_batch", "hm_call_chunks", "hm_call_batch", "hm_normcounts_chunks",
     "hm_read_stats", "hm_last_timing", "hm_last_kernel_times", "hm_set_stream", "hm_host_register",
     "hm_host_unregister", "hm_abi_sizeof", "hm_last_records", "hm_qname_seen", "hm_set_reference", "hm_ref_tricounts", "hm_last_norm_exact_sites",
+    "hm_phase_edges_begin", "hm_phase_edges_add", "hm_phase_edges_end",
 ]
 
 
@@ -60,6 +61,9 @@ def load():
         lib.hm_set_reference.argtypes = [vp, vp, sz]
         lib.hm_ref_tricounts.argtypes = [vp, vp, sz, vp]
         lib.hm_last_norm_exact_sites.argtypes = [vp, C.POINTER(C.c_uint64)]
+        lib.hm_phase_edges_begin.argtypes = [vp, vp, vp, sz, C.c_uint32]
+        lib.hm_phase_edges_add.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_uint32)]
+        lib.hm_phase_edges_end.argtypes = [vp, vp, sz]
         lib.hm_set_stream.argtypes = [vp, vp]
         lib.hm_host_register.argtypes = [vp, vp, sz]
         lib.hm_host_unregister.argtypes = [vp, vp]
@@ -209,6 +213,27 @@ class Context:
         out = np.zeros(abi.TRI_BINS, np.int64)
         self._chk(self.lib.hm_ref_tricounts(self.h, _p(ref), ref.size, _p(out)))
         self._ref_obj = None
+        return out
+
+    def phase_edges_begin(self, hpos, href, band):
+        self._edge_hpos = np.ascontiguousarray(hpos, np.int32)
+        self._edge_href = np.ascontiguousarray(href, np.uint8)
+        self._edge_band = int(band)
+        self._chk(self.lib.hm_phase_edges_begin(self.h, _p(self._edge_hpos), _p(self._edge_href), self._edge_hpos.size, self._edge_band))
+
+    def phase_edges_add(self, min_bq, min_mapq, min_tstart=-2**31):
+        """accumulate the resident batch; -> 0, or the band a retry needs (nothing usable was added then)"""
+        need = C.c_uint32(0)
+        rc = self.lib.hm_phase_edges_add(self.h, int(min_bq), int(min_mapq), int(max(min_tstart, -2**31)), C.byref(need))
+        if rc == abi.HM_ERR_CAPACITY and need.value != 0xFFFFFFFF:
+            return int(need.value)
+        self._chk(rc)
+        return 0
+
+    def phase_edges_end(self):
+        """-> uint32[n_hetsnp, band, 4]"""
+        out = np.zeros((self._edge_hpos.size, self._edge_band, 4), np.uint32)
+        self._chk(self.lib.hm_phase_edges_end(self.h, _p(out), out.size))
         return out
 
     def last_norm_exact_sites(self):

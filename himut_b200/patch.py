@@ -17,6 +17,7 @@ def install():
     himut.normcounts.get_callable_tricounts = normcounts.get_callable_tricounts
     himut.reflib.get_chrom_tricount = reflib.get_chrom_tricount  # reflib.py:42-52 starmap target
     himut.bamlib.get_thresholds = bamlib.get_thresholds          # BAM pre-pass, called at caller.py:690
+    himut.phaselib.get_edges = phaselib.get_edges                # `himut phase` pair tables, called at phaselib.py:248
     return himut
 
 

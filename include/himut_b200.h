@@ -275,6 +275,20 @@ int hm_qname_seen(hm_ctx* ctx, uint8_t* out, size_t cap, size_t* n);
  * pass certified.  0 when the single-pass kernel ran.                            */
 int hm_last_norm_exact_sites(hm_ctx* ctx, uint64_t* n);
 
+/* ---- `himut phase`: hetSNP pair tables (replaces phaselib.get_edges, src/himut/phaselib.py:16-67) -------
+ * hpos: ascending 1-based hetSNP positions of the contig (vcflib.load_hetsnps), href: their reference base codes
+ * (4 = anything the read can never equal).  For every non-secondary read of the resident batch with
+ * mapq >= min_mapq and reference_start >= min_tstart (so that a read shared by two decoded windows of a contig
+ * is counted once) that covers at least two hetSNPs, every ordered pair a < b of them whose bases both have
+ * BQ >= min_bq adds one to  counts[(a * band + (b - a - 1)) * 4 + k],  k = 0 cis1 (ref, ref), 1 cis2
+ * (non-ref, non-ref), 2 trans1 (ref, non-ref), 3 trans2 (non-ref, ref); a, b index hpos.
+ * begin zeroes the table on the device, add accumulates one resident batch (HM_ERR_CAPACITY and *need_band when a
+ * read pairs hetSNPs further apart than the band: begin again with a wider one), end copies n_hetsnp * band * 4
+ * counters out.                                                                                              */
+int hm_phase_edges_begin(hm_ctx* ctx, const int32_t* hpos, const uint8_t* href, size_t n_hetsnp, uint32_t band);
+int hm_phase_edges_add(hm_ctx* ctx, int32_t min_bq, int32_t min_mapq, int32_t min_tstart, uint32_t* need_band);
+int hm_phase_edges_end(hm_ctx* ctx, uint32_t* counts, size_t cap_entries);
+
 /* reference-genome trinucleotide counts of one contig, bins as above (replaces
  * reflib.get_chrom_tricount, src/himut/reflib.py:11-33: windows whose first base is "N" are skipped) */
 int hm_ref_tricounts(hm_ctx* ctx, const uint8_t* refseq, size_t ref_len, int64_t tri[HM_TRI_BINS]);

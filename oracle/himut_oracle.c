@@ -747,3 +747,49 @@ int orc_ref_tricounts(const uint8_t* seq, size_t n, int64_t tri[HM_TRI_BINS]) {
   }
   return HM_OK;
 }
+
+/* ---------------------------------------------------------------- `himut phase` edges */
+/* phaselib.get_edges (src/himut/phaselib.py:16-67) over one packed batch: same band layout as
+ * hm_phase_edges_* (include/himut_b200.h).  Returns the widest pair distance seen (0 = fits). */
+static int read_bq_at(const hm_read_batch* b, uint64_t r, int32_t pos1) {
+  const uint32_t* ops = b->ops + b->op_off[r];
+  int tpos = b->tstart[r], qpos = b->qstart[r];
+  int rpos = pos1 - 1;
+  for (uint32_t k = 0; k < b->n_ops[r]; k++) {
+    op_t o = decode_op(ops[k]);
+    if (o.ref_len > 0 && rpos >= tpos && rpos < tpos + o.ref_len) {
+      if (o.kind == HM_OP_MATCH) return b->bq[b->bq_off[r] + (uint64_t)(qpos + (rpos - tpos))];
+      if (o.kind == HM_OP_SUB) return b->bq[b->bq_off[r] + (uint64_t)qpos];
+      return 0; /* deleted base: ("-", 0) */
+    }
+    tpos += o.ref_len; qpos += o.alt_len;
+  }
+  return 0;
+}
+uint32_t orc_phase_edges(const hm_read_batch* b, const int32_t* hpos, const uint8_t* href, size_t n_snp, int32_t min_bq,
+                         int32_t min_mapq, int32_t min_tstart, uint32_t band, uint32_t* counts) {
+  uint32_t need = 0;
+  for (uint64_t r = 0; r < b->n_reads; r++) {
+    if (b->flags[r] & HM_READ_SECONDARY) continue;
+    if ((int32_t)b->mapq[r] < min_mapq) continue;
+    if (b->tstart[r] < min_tstart) continue;
+    int idx = bisect_right_i32(hpos, (int)n_snp, b->tstart[r]);
+    int jdx = bisect_right_i32(hpos, (int)n_snp, b->tend[r]);
+    if (jdx - idx < 2) continue;
+    if ((uint32_t)(jdx - idx - 1) > band) { if ((uint32_t)(jdx - idx - 1) > need) need = (uint32_t)(jdx - idx - 1); continue; }
+    for (int x = idx; x < jdx; x++) {
+      if (read_bq_at(b, r, hpos[x]) < min_bq) continue;
+      int ax = read_allele_at(b, r, hpos[x]);
+      int sx = (ax >= 0 && ax < 4 && ax == (int)href[x]) ? 0 : 1;
+      for (int y = x + 1; y < jdx; y++) {
+        if (read_bq_at(b, r, hpos[y]) < min_bq) continue;
+        int ay = read_allele_at(b, r, hpos[y]);
+        int sy = (ay >= 0 && ay < 4 && ay == (int)href[y]) ? 0 : 1;
+        int kind = sx == 0 ? (sy == 0 ? 0 : 2) : (sy == 1 ? 1 : 3);
+        counts[((uint64_t)x * band + (uint64_t)(y - x - 1)) * 4 + kind]++;
+      }
+    }
+  }
+  return need;
+}
+

@@ -104,3 +104,16 @@ def ref_tricounts(refseq):
     rc = lib().orc_ref_tricounts(_p(ref), C.c_size_t(ref.size), _p(out))
     assert rc == 0
     return out
+
+
+def phase_edges(batch, hpos, href, band, min_bq, min_mapq, min_tstart=-2**31):
+    """-> (uint32[n, band, 4], needed_band) (phaselib.get_edges in the band layout of hm_phase_edges_*)"""
+    hpos = np.ascontiguousarray(hpos, np.int32)
+    href = np.ascontiguousarray(href, np.uint8)
+    out = np.zeros((hpos.size, band, 4), np.uint32)
+    f = lib().orc_phase_edges
+    f.restype = C.c_uint32
+    need = f(C.byref(batch.as_struct()), _p(hpos), _p(href), C.c_size_t(hpos.size), C.c_int32(min_bq), C.c_int32(min_mapq),
+             C.c_int32(max(min_tstart, -2**31)), C.c_uint32(band), _p(out))
+    return out, int(need)
+
