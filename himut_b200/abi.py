@@ -47,6 +47,26 @@ class hm_read_batch(C.Structure):
     ]
 
 
+class hm_bq_compact(C.Structure):
+    _fields_ = [("mask", C.c_void_p), ("mask_bytes", C.c_uint64), ("exc", C.c_void_p), ("exc_bytes", C.c_uint64),
+                ("exc_off", C.c_void_p), ("modal", C.c_uint8), ("reserved", C.c_uint8 * 7)]
+
+
+class BqCompact:
+    """numpy-backed hm_bq_compact: the quality stream of a ReadBatch as modal-value bitmap + exceptions"""
+
+    def __init__(self, mask, exc, exc_off, modal, n_exc):
+        self.mask, self.exc, self.exc_off, self.modal, self.n_exc = mask, exc, exc_off, modal, n_exc
+        s = hm_bq_compact()
+        s.mask, s.mask_bytes = _ptr(mask), mask.size
+        s.exc, s.exc_bytes = _ptr(exc), n_exc
+        s.exc_off, s.modal = _ptr(exc_off), modal
+        self.struct = s
+
+    def nbytes(self):
+        return self.mask.nbytes + self.n_exc + self.exc_off.nbytes
+
+
 class hm_chunk(C.Structure):
     _fields_ = [("start", C.c_int32), ("end", C.c_int32), ("read_lo", C.c_uint32),
                 ("read_hi", C.c_uint32), ("phase_set", C.c_int32), ("reserved", C.c_int32)]

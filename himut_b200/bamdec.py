@@ -16,7 +16,8 @@ from . import abi, pack
 
 _LIB = None
 EXPORTS = ["hm_bam_open", "hm_bam_close", "hm_bam_error", "hm_bam_header_text", "hm_bam_n_refs", "hm_bam_ref_name",
-           "hm_bam_ref_len", "hm_bam_read_batch", "hm_bam_n_qnames", "hm_bam_qname", "hm_bam_window_qlens", "hm_bam_write_batch"]
+           "hm_bam_ref_len", "hm_bam_read_batch", "hm_bam_n_qnames", "hm_bam_qname", "hm_bam_window_qlens", "hm_bam_write_batch", "hm_bq_compact_build",
+           "hm_bq_compact_free"]
 
 
 def lib_path():
@@ -45,6 +46,9 @@ def load():
         lib.hm_bam_read_batch.argtypes = [vp, C.c_int, C.c_int32, C.c_int32, C.c_int, C.POINTER(abi.hm_read_batch)]
         lib.hm_bam_window_qlens.argtypes = [vp, C.c_int, C.c_int32, C.c_int32, C.c_int, vp, C.c_size_t, C.POINTER(C.c_size_t)]
         lib.hm_bam_write_batch.argtypes = [C.c_char_p, C.c_char_p, C.c_int32, C.c_char_p, C.POINTER(abi.hm_read_batch), C.c_int, C.c_int]
+        lib.hm_bq_compact_build.argtypes = [C.POINTER(abi.hm_read_batch), C.c_int, vp, vp, C.POINTER(vp), C.POINTER(C.c_uint64), C.POINTER(C.c_uint8)]
+        lib.hm_bq_compact_free.argtypes = [vp]
+        lib.hm_bq_compact_free.restype = None
         lib.hm_bam_n_qnames.argtypes = [vp]
         lib.hm_bam_n_qnames.restype = C.c_uint32
         lib.hm_bam_qname.argtypes = [vp, C.c_uint32]
@@ -77,6 +81,24 @@ def write_batch_bam(path, chrom, contig_len, batch, sample="synth", level=1, thr
                                    int(level), int(threads or default_threads()))
     if rc != 0:
         raise IOError("cannot write %s" % path)
+
+
+def compact_bq(batch, threads=None):
+    """abi.BqCompact of a batch: bitmap of the modal quality + exceptions (lossless; expanded on the device)"""
+    L = load()
+    mask = np.zeros(batch.bq.size // 8, np.uint8)
+    exc_off = np.zeros(batch.n_reads + 1, np.uint64)
+    exc_p, exc_n, modal = C.c_void_p(), C.c_uint64(0), C.c_uint8(0)
+    rc = L.hm_bq_compact_build(C.byref(batch.as_struct()), int(threads or default_threads()), mask.ctypes.data_as(C.c_void_p),
+                               exc_off.ctypes.data_as(C.c_void_p), C.byref(exc_p), C.byref(exc_n), C.byref(modal))
+    if rc != 0:
+        raise RuntimeError("hm_bq_compact_build failed: %d" % rc)
+    n = int(exc_n.value)
+    exc = np.zeros((n + 31) & ~15, np.uint8)
+    if n:
+        exc[:n] = _view(exc_p.value, n, np.uint8)
+    L.hm_bq_compact_free(exc_p)
+    return abi.BqCompact(mask, exc, exc_off, int(modal.value), n)
 
 
 class NativeBam:

@@ -958,3 +958,80 @@ int hm_bam_write_batch(const char* path, const char* chrom, int32_t contig_len, 
   free(w.p); free(rec_off); free(rec_end); free(job.dst); free(job.csize); free(coff);
   return rc;
 }
+
+/* ------------------------------------------------------------------ compact quality stream */
+/* hm_bq_compact of a packed batch (include/himut_b200.h): bitmap of the modal quality + the exceptions.
+ * mask (bq_bytes / 8 bytes) and exc_off (n_reads + 1) are caller allocated; exc is malloc'ed here and handed
+ * over in *exc_out (free with hm_bq_compact_free).  The modal value is the most frequent quality of the batch. */
+typedef struct {
+  const hm_read_batch* b;
+  uint8_t* mask; uint8_t* exc; uint64_t* exc_off;
+  uint8_t modal;
+  size_t next;
+  int pass;
+  pthread_mutex_t mu;
+} bqc_job_t;
+static void* bqc_worker(void* arg) {
+  bqc_job_t* j = (bqc_job_t*)arg;
+  const hm_read_batch* b = j->b;
+  for (;;) {
+    pthread_mutex_lock(&j->mu);
+    size_t r0 = j->next; j->next += 256;
+    pthread_mutex_unlock(&j->mu);
+    if (r0 >= b->n_reads) break;
+    for (size_t r = r0; r < r0 + 256 && r < b->n_reads; r++) {
+      const uint8_t* q = b->bq + b->bq_off[r];
+      const int32_t n = b->qlen[r];
+      if (j->pass == 0) {
+        uint64_t c = 0;
+        for (int32_t i = 0; i < n; i++) c += (q[i] != j->modal);
+        j->exc_off[r + 1] = c;
+      } else {
+        uint8_t* m = j->mask + (b->bq_off[r] >> 3);
+        uint8_t* e = j->exc + j->exc_off[r];
+        const size_t mb = (((size_t)n + 15) & ~(size_t)15) >> 3;
+        memset(m, 0, mb);
+        for (int32_t i = 0; i < n; i++) {
+          if (q[i] == j->modal) m[i >> 3] |= (uint8_t)(1u << (i & 7));
+          else *e++ = q[i];
+        }
+      }
+    }
+  }
+  return NULL;
+}
+int hm_bq_compact_build(const hm_read_batch* b, int threads, uint8_t* mask, uint64_t* exc_off, uint8_t** exc_out,
+                        uint64_t* exc_bytes, uint8_t* modal_out) {
+  if (!b || !b->bq || !mask || !exc_off || !exc_out || !exc_bytes || !modal_out) return HM_ERR_ARG;
+  uint64_t hist[256];
+  memset(hist, 0, sizeof(hist));
+  const uint64_t step = b->bq_bytes > (1u << 24) ? b->bq_bytes >> 22 : 1; /* a sample is enough to find the mode */
+  for (uint64_t i = 0; i < b->bq_bytes; i += step) hist[b->bq[i]]++;
+  int modal = 1;
+  for (int v = 1; v < 256; v++) if (hist[v] > hist[modal]) modal = v;
+  bqc_job_t job; memset(&job, 0, sizeof(job));
+  job.b = b; job.mask = mask; job.exc_off = exc_off; job.modal = (uint8_t)modal;
+  pthread_mutex_init(&job.mu, NULL);
+  const int nt = threads < 1 ? 1 : (threads > 64 ? 64 : threads);
+  pthread_t th[64];
+  memset(mask, 0, (size_t)(b->bq_bytes >> 3));
+  exc_off[0] = 0;
+  for (int pass = 0; pass < 2; pass++) {
+    job.pass = pass; job.next = 0;
+    for (int t = 1; t < nt; t++) pthread_create(&th[t], NULL, bqc_worker, &job);
+    bqc_worker(&job);
+    for (int t = 1; t < nt; t++) pthread_join(th[t], NULL);
+    if (pass == 0) {
+      for (uint64_t r = 0; r < b->n_reads; r++) exc_off[r + 1] += exc_off[r];
+      const uint64_t tot = exc_off[b->n_reads];
+      job.exc = (uint8_t*)calloc(((size_t)tot + 31) & ~(size_t)15, 1);
+      if (!job.exc) { pthread_mutex_destroy(&job.mu); return HM_ERR_ARG; }
+      *exc_bytes = tot;
+    }
+  }
+  pthread_mutex_destroy(&job.mu);
+  *exc_out = job.exc; *modal_out = (uint8_t)modal;
+  return HM_OK;
+}
+void hm_bq_compact_free(uint8_t* exc) { free(exc); }
+

@@ -85,7 +85,7 @@ struct hm_ctx {
   size_t ref_len = 0; // length of the contig left resident by hm_set_reference (0: none)
   NormCert cert;      // certified-verdict constants of the normcounts fast pass
   unsigned long long last_norm_sites = 0; // positions the last normcounts call evaluated exactly
-  DevBuf b_sites, b_koff, b_tile_info, b_edge_counts, b_edge_hpos, b_edge_href;
+  DevBuf b_sites, b_koff, b_tile_info, b_edge_counts, b_edge_hpos, b_edge_href, b_bqmask, b_bqexc, b_bqexc_off;
   uint64_t edge_n = 0;
   uint32_t edge_band = 0;
 };
@@ -227,6 +227,7 @@ size_t hm_abi_sizeof(int which) {
     case 1: return sizeof(hm_chunk);
     case 2: return sizeof(hm_params);
     case 3: return sizeof(hm_site_record);
+    case 4: return sizeof(hm_bq_compact);
     default: return 0;
   }
 }
@@ -258,7 +259,7 @@ void hm_destroy(hm_ctx* ctx) {
                     &ctx->b_ins_len, &ctx->b_del_len, &ctx->b_n_mm, &ctx->b_gate, &ctx->b_pmax, &ctx->b_tix_off, &ctx->b_tix, &ctx->b_common, &ctx->b_pon,
                     &ctx->b_hpos, &ctx->b_href, &ctx->b_halt, &ctx->b_hbit, &ctx->b_set_off, &ctx->b_chunks,
                     &ctx->b_pair_off, &ctx->b_pair_hap, &ctx->b_qseen, &ctx->b_keys, &ctx->b_keys_sorted, &ctx->b_cub,
-                    &ctx->b_records, &ctx->b_counters, &ctx->b_ref, &ctx->b_norm_out, &ctx->b_lut, &ctx->b_tile_off, &ctx->b_agg, &ctx->b_geom, &ctx->b_bidx, &ctx->b_sites, &ctx->b_koff, &ctx->b_tile_info, &ctx->b_edge_counts, &ctx->b_edge_hpos, &ctx->b_edge_href};
+                    &ctx->b_records, &ctx->b_counters, &ctx->b_ref, &ctx->b_norm_out, &ctx->b_lut, &ctx->b_tile_off, &ctx->b_agg, &ctx->b_geom, &ctx->b_bidx, &ctx->b_sites, &ctx->b_koff, &ctx->b_tile_info, &ctx->b_edge_counts, &ctx->b_edge_hpos, &ctx->b_edge_href, &ctx->b_bqmask, &ctx->b_bqexc, &ctx->b_bqexc_off};
   for (DevBuf* b : bufs) b->release();
   if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
   for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
@@ -350,8 +351,22 @@ int hm_set_phase_sets(hm_ctx* ctx, const int32_t* hpos, const uint8_t* href, con
   return HM_OK;
 }
 
-int hm_upload_batch(hm_ctx* ctx, const hm_read_batch* b) {
+static int upload_batch_impl(hm_ctx* ctx, const hm_read_batch* b, const hm_bq_compact* cq);
+
+int hm_upload_batch(hm_ctx* ctx, const hm_read_batch* b) { return upload_batch_impl(ctx, b, nullptr); }
+
+int hm_upload_batch_compact(hm_ctx* ctx, const hm_read_batch* b, const hm_bq_compact* cq) {
+  if (!cq) return HM_ERR_ARG;
+  return upload_batch_impl(ctx, b, cq);
+}
+
+static int upload_batch_impl(hm_ctx* ctx, const hm_read_batch* b, const hm_bq_compact* cq) {
   if (!ctx || !b) return HM_ERR_ARG;
+  if (!cq && !b->bq) return fail(ctx, HM_ERR_ARG, "batch has no quality stream");
+  if (cq) {
+    if (!cq->mask || !cq->exc_off || (cq->exc_bytes && !cq->exc)) return fail(ctx, HM_ERR_ARG, "incomplete hm_bq_compact");
+    if (cq->mask_bytes * 8 != b->bq_bytes) return fail(ctx, HM_ERR_ARG, "hm_bq_compact.mask_bytes must be bq_bytes / 8");
+  }
   CU(cudaSetDevice(ctx->device));
   ctx->have_batch = false;
   const uint64_t n = b->n_reads;
@@ -383,7 +398,17 @@ int hm_upload_batch(hm_ctx* ctx, const hm_read_batch* b) {
   UP(b_tstart, tstart, n); UP(b_tend, tend, n); UP(b_qstart, qstart, n); UP(b_qlen, qlen, n);
   UP(b_mapq, mapq, n); UP(b_flags, flags, n); UP(b_qname, qname_id, n);
   UP(b_seq_off, seq_off, n); UP(b_bq_off, bq_off, n); UP(b_op_off, op_off, n); UP(b_n_ops, n_ops, n);
-  UP(b_seq, seq, b->seq_bytes); UP(b_bq, bq, b->bq_bytes); UP(b_ops, ops, b->n_ops_total);
+  UP(b_seq, seq, b->seq_bytes); UP(b_ops, ops, b->n_ops_total);
+  if (!cq) { UP(b_bq, bq, b->bq_bytes); }
+  else {
+    for (uint64_t r = 0; r < n; r++)
+      if (cq->exc_off[r] > cq->exc_off[r + 1] || cq->exc_off[r + 1] > cq->exc_bytes || cq->exc_off[r + 1] - cq->exc_off[r] > (uint64_t)b->qlen[r])
+        return fail(ctx, HM_ERR_ARG, "read %llu: hm_bq_compact.exc_off is inconsistent", (unsigned long long)r);
+    CU(ctx->b_bq.ensure(b->bq_bytes + 16));
+    if ((rc = upload(ctx, ctx->b_bqmask, cq->mask, (size_t)cq->mask_bytes))) return rc;
+    if ((rc = upload(ctx, ctx->b_bqexc, cq->exc, (size_t)cq->exc_bytes, 16))) return rc;
+    if ((rc = upload(ctx, ctx->b_bqexc_off, cq->exc_off, (size_t)n + 1))) return rc;
+  }
 #undef UP
   if (b->n_reads && (b->tstart[0] < 0 || n_tix >= (1ull << 32))) return fail(ctx, HM_ERR_ARG, "negative reference_start, or too many (read, tile) pairs in one batch");
   ctx->h_tix_off[n] = (uint32_t)n_tix;
@@ -407,6 +432,14 @@ int hm_upload_batch(hm_ctx* ctx, const hm_read_batch* b) {
   d.n_sub = ctx->b_n_sub.as<int32_t>(); d.ins_len = ctx->b_ins_len.as<int32_t>(); d.del_len = ctx->b_del_len.as<int32_t>();
   d.n_mm = ctx->b_n_mm.as<int32_t>(); d.gate = ctx->b_gate.as<uint8_t>(); d.pmax_tend = ctx->b_pmax.as<int32_t>();
   ctx->n_reads = n; ctx->n_ops_total = b->n_ops_total; ctx->seq_bytes = b->seq_bytes; ctx->bq_bytes = b->bq_bytes;
+  if (cq && n) {
+    t_reset(ctx);
+    t_begin(ctx, "k_bq_expand");
+    k_bq_expand<<<(unsigned)((n * 32 + 255) / 256), 256, 0, ctx->stream>>>(ctx->db, ctx->b_bqmask.as<uint8_t>(), ctx->b_bqexc.as<uint8_t>(),
+                                                                         ctx->b_bqexc_off.as<uint64_t>(), (uint32_t)cq->modal, ctx->b_bq.as<uint8_t>());
+    t_end(ctx);
+    CU(cudaGetLastError());
+  }
   CU(cudaStreamSynchronize(ctx->stream)); // caller may reuse its buffers after return
   ctx->have_batch = true;
   return HM_OK;
@@ -644,6 +677,13 @@ int hm_last_records(hm_ctx* ctx, hm_site_record* out, size_t cap, size_t* n_out)
 int hm_call_batch(hm_ctx* ctx, const hm_read_batch* batch, const hm_chunk* chunks, size_t n_chunks, hm_site_record* out,
                   size_t cap, size_t* n_out, int64_t log[HM_CALL_LOG_LEN]) {
   int rc = hm_upload_batch(ctx, batch);
+  if (rc) return rc;
+  return hm_call_chunks(ctx, chunks, n_chunks, out, cap, n_out, log);
+}
+
+int hm_call_batch_compact(hm_ctx* ctx, const hm_read_batch* batch, const hm_bq_compact* bq, const hm_chunk* chunks, size_t n_chunks,
+                          hm_site_record* out, size_t cap, size_t* n_out, int64_t log[HM_CALL_LOG_LEN]) {
+  int rc = hm_upload_batch_compact(ctx, batch, bq);
   if (rc) return rc;
   return hm_call_chunks(ctx, chunks, n_chunks, out, cap, n_out, log);
 }

@@ -194,6 +194,58 @@ __global__ void __launch_bounds__(256) k_read_scan(DevBatch b, DevParams p) {
   }
 }
 
+// ============================================================================ k_bq_expand
+// hm_bq_compact -> the one-byte-per-base quality stream.  One warp per read, 16 bases per lane and step: the lane's
+// 16 mask bits, a warp scan of the clear-bit counts to find its first exception, then the exceptions dropped into
+// the modal-filled 16-byte word.  Bytes past the read's length (padding) are written as 0.
+__global__ void __launch_bounds__(256) k_bq_expand(DevBatch b, const uint8_t* mask, const uint8_t* exc, const uint64_t* exc_off,
+                                                   uint32_t modal, uint8_t* bq_out) {
+  const uint64_t r = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (r >= b.n_reads) return;
+  const uint32_t qlen = (uint32_t)b.qlen[r];
+  const uint64_t off = b.bq_off[r];
+  const uint16_t* m16 = reinterpret_cast<const uint16_t*>(mask + (off >> 3));
+  uint4* out = reinterpret_cast<uint4*>(bq_out + off);
+  const uint8_t* ex = exc + exc_off[r];
+  const uint32_t n16 = (qlen + 15u) >> 4;
+  const uint32_t fill = modal * 0x01010101u;
+  uint32_t run = 0; // exceptions consumed by earlier steps
+  for (uint32_t base = 0; base < n16; base += 32) {
+    const uint32_t i = base + lane;
+    uint32_t bits = 0xffffu, valid = 0;
+    if (i < n16) {
+      bits = __ldg(m16 + i);
+      const uint32_t left = qlen - 16u * i;
+      valid = left >= 16u ? 0xffffu : ((1u << left) - 1u);
+    }
+    const uint32_t zeros = ~bits & valid;
+    const uint32_t c = __popc(zeros);
+    uint32_t incl = c;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(HM_FULL, incl, d); if (lane >= d) incl += t; }
+    uint32_t at = run + incl - c;
+    run += __shfl_sync(HM_FULL, incl, 31);
+    if (i < n16) {
+      uint32_t o[4];
+#pragma unroll
+      for (int wd = 0; wd < 4; wd++) {
+        const uint32_t v4 = (valid >> (4 * wd)) & 15u;
+        uint32_t word = fill & (((v4 * 0x00204081u) & 0x01010101u) * 0xffu); // modal where the base exists, 0 in the padding
+        uint32_t z4 = (zeros >> (4 * wd)) & 15u;
+        while (z4) {
+          const int k = __ffs(z4) - 1;
+          z4 &= z4 - 1;
+          word = (word & ~(0xffu << (8 * k))) | ((uint32_t)__ldg(ex + at) << (8 * k));
+          at++;
+        }
+        o[wd] = word;
+      }
+      out[i] = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+  }
+}
+
 // ============================================================================ lookups
 // allele of read r at 0-based reference position rpos (tstart <= rpos <= tend):
 //   0..3 base, 5 deleted, -1 no base; *bq = quality of the base; *ins = insertions whose

@@ -20,7 +20,7 @@ EXPORTS = [
     "hm_set_phase_sets", "hm_upload_batch", "hm_call_chunks", "hm_call_batch", "hm_normcounts_chunks",
     "hm_read_stats", "hm_last_timing", "hm_last_kernel_times", "hm_set_stream", "hm_host_register",
     "hm_host_unregister", "hm_abi_sizeof", "hm_last_records", "hm_qname_seen", "hm_set_reference", "hm_ref_tricounts", "hm_last_norm_exact_sites",
-    "hm_phase_edges_begin", "hm_phase_edges_add", "hm_phase_edges_end",
+    "hm_phase_edges_begin", "hm_phase_edges_add", "hm_phase_edges_end", "hm_upload_batch_compact", "hm_call_batch_compact",
 ]
 
 
@@ -147,6 +147,26 @@ class Context:
     # ---- work -------------------------------------------------------------------------
     def upload(self, batch):
         self._chk(self.lib.hm_upload_batch(self.h, C.byref(batch.as_struct())))
+
+    def upload_compact(self, batch, cq):
+        """upload with the quality stream as modal bitmap + exceptions (abi.BqCompact); expanded on the device"""
+        self._chk(self.lib.hm_upload_batch_compact(self.h, C.byref(batch.as_struct()), C.byref(cq.struct)))
+
+    def call_batch_compact(self, batch, cq, chunks, cap=None, view=False):
+        """call_batch with the compact quality stream: fewer bytes over PCIe, identical records"""
+        return self._call(self.lib.hm_call_batch_compact, (C.byref(batch.as_struct()), C.byref(cq.struct)), chunks, cap, view)
+
+    def pin_arrays(self, arrays):
+        for a in arrays:
+            if a.size and id(a) not in self._keep:
+                self._chk(self.lib.hm_host_register(self.h, _p(a), a.nbytes))
+                self._keep[id(a)] = a
+
+    def unpin_arrays(self, arrays):
+        for a in arrays:
+            if id(a) in self._keep:
+                self.lib.hm_host_unregister(self.h, _p(a))
+                del self._keep[id(a)]
 
     def _out_buffer(self, cap):
         """persistent page-locked record buffer (records are copied device -> here directly)"""

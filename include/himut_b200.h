@@ -92,6 +92,23 @@ typedef struct hm_read_batch {
   uint64_t n_ops_total;
 } hm_read_batch;
 
+/* Optional compact form of the quality stream for the host -> device copy.  CCS qualities are dominated by one
+ * value (the Q93 cap), so `bq` (1 byte per base, 80 % of a batch) travels as a bitmap plus the exceptions and is
+ * expanded on the device (k_bq_expand) into exactly the layout bq_off / bq_bytes describe.  Lossless.
+ *   mask  one bit per byte of the expanded stream, padding included: bit (i & 7) of byte i >> 3 is set when byte i
+ *         holds `modal`; bits of padding bytes are clear
+ *   exc   the qualities whose bit is clear, read by read, in base order (padding excluded);
+ *         read r's exceptions start at exc[exc_off[r]], exc_off has n_reads + 1 entries                          */
+typedef struct hm_bq_compact {
+  const uint8_t* mask;
+  uint64_t mask_bytes;     /* bq_bytes / 8 */
+  const uint8_t* exc;
+  uint64_t exc_bytes;
+  const uint64_t* exc_off;
+  uint8_t modal;
+  uint8_t reserved[7];
+} hm_bq_compact;
+
 /* One unit of work = one element of the reference's chunkloci_lst (util.chunkloci,
  * src/himut/util.py:119-132) or, in --phase mode, one phase-set span
  * (vcflib.load_phased_hetsnps, src/himut/vcflib.py:655-662).  `read_lo..read_hi` is the
@@ -249,6 +266,12 @@ int hm_last_records(hm_ctx* ctx, hm_site_record* out, size_t cap, size_t* n_out)
 int hm_call_batch(hm_ctx* ctx, const hm_read_batch* batch, const hm_chunk* chunks,
                   size_t n_chunks, hm_site_record* out, size_t cap, size_t* n_out,
                   int64_t log[HM_CALL_LOG_LEN]);
+
+/* hm_upload_batch / hm_call_batch with the quality stream in compact form (hm_bq_compact above): batch->bq is
+ * ignored (may be NULL); batch->bq_off / bq_bytes still describe the expanded layout */
+int hm_upload_batch_compact(hm_ctx* ctx, const hm_read_batch* batch, const hm_bq_compact* bq);
+int hm_call_batch_compact(hm_ctx* ctx, const hm_read_batch* batch, const hm_bq_compact* bq, const hm_chunk* chunks,
+                          size_t n_chunks, hm_site_record* out, size_t cap, size_t* n_out, int64_t log[HM_CALL_LOG_LEN]);
 
 /* keep a contig's reference sequence (the `seq` argument of get_callable_tricounts,
  * normcounts.py:208) resident on the device; hm_normcounts_chunks then accepts refseq = NULL */

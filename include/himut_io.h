@@ -56,6 +56,13 @@ int hm_bam_window_qlens(hm_bam* b, int rid, int32_t start, int32_t end, int thre
 int hm_bam_write_batch(const char* path, const char* chrom, int32_t contig_len, const char* sample, const hm_read_batch* b,
                        int level, int threads);
 
+/* hm_bq_compact (himut_b200.h) of a packed batch, for the host -> device copy: `mask` (bq_bytes / 8 bytes) and
+ * `exc_off` (n_reads + 1 entries) are caller allocated, the exception bytes are allocated here (*exc_out, release
+ * with hm_bq_compact_free); *modal_out is the batch's most frequent quality */
+int hm_bq_compact_build(const hm_read_batch* b, int threads, uint8_t* mask, uint64_t* exc_off, uint8_t** exc_out,
+                        uint64_t* exc_bytes, uint8_t* modal_out);
+void hm_bq_compact_free(uint8_t* exc);
+
 /* query names are interned per handle: qname_id of a batch indexes this table, ids are stable
  * across hm_bam_read_batch calls (m.num_ccs counts distinct names per contig, caller.py:318-320) */
 uint32_t hm_bam_n_qnames(const hm_bam* b);
