@@ -20,7 +20,7 @@ def test_io_library_exports_every_declared_symbol():
     lib = C.CDLL(bamdec.lib_path())
     hdr = open(os.path.join(os.path.dirname(cases.GOLDEN_DIR), "..", "include", "himut_io.h")).read()
     import re
-    declared = set(re.findall(r"\b(hm_bam_\w+)\s*\(", hdr))
+    declared = set(re.findall(r"\b(hm_(?:bam|bq)_\w+)\s*\(", hdr))
     assert declared == set(bamdec.EXPORTS)
     for name in declared:
         assert hasattr(lib, name), name
