@@ -56,7 +56,7 @@ int hm_bam_window_qlens(hm_bam* b, int rid, int32_t start, int32_t end, int thre
 int hm_bam_write_batch(const char* path, const char* chrom, int32_t contig_len, const char* sample, const hm_read_batch* b,
                        int level, int threads);
 
-/* hm_bq_compact (himut_b200.h) of a packed batch, for the host -> device copy: `mask` (bq_bytes / 8 bytes) and
+/* compact quality stream of a packed batch (struct hm_bq_compact, himut_b200.h), for the host -> device copy: `mask` (bq_bytes / 8 bytes) and
  * `exc_off` (n_reads + 1 entries) are caller allocated, the exception bytes are allocated here (*exc_out, release
  * with hm_bq_compact_free); *modal_out is the batch's most frequent quality */
 int hm_bq_compact_build(const hm_read_batch* b, int threads, uint8_t* mask, uint64_t* exc_off, uint8_t** exc_out,
