@@ -196,6 +196,21 @@ def _call_basic():
                 chunks=chunkloci(0, 260_000), args=call_args())
 
 
+@case("call_config0_1mb")
+def _call_config0():
+    # BASELINE.json configs[0]: 1 Mb contig, 30x, the reference's own 200 kb chunking
+    d = _synth_case(1_000_000, 20260101)
+    return dict(kind="call", batch=d.batch, ref=d.ref.decode(), contig_len=1_000_000,
+                chunks=chunkloci(0, 1_000_000), args=call_args())
+
+
+@case("norm_config0_1mb")
+def _norm_config0():
+    d = _synth_case(1_000_000, 20260101)
+    return dict(kind="norm", batch=d.batch, ref=d.ref.decode(), contig_len=1_000_000,
+                chunks=chunkloci(0, 1_000_000), args=call_args())
+
+
 @case("call_sets")
 def _call_sets():
     d = _synth_case(230_000, 12, somatic_rate=2e-5)
