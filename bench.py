@@ -74,7 +74,7 @@ class ClockSampler:
         try:
             self.f = open(self.path, "w")
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+                                          "-lms", "200"], stdout=self.f, stderr=subprocess.DEVNULL)
         except OSError:
             self.proc = None
 
@@ -100,6 +100,23 @@ class ClockSampler:
         os.unlink(self.path)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
                 "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def bind_to_gpu_numa_node(gpu_index):
+    """one process per GPU: run it on the cores next to that GPU (NVML's ideal CPU set), so eight ranks do not
+    share cores or cross sockets for their pinned-memory copies"""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+        n_words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, n_words)
+        cpus = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (m >> b) & 1}
+        allowed = os.sched_getaffinity(0)
+        if cpus & allowed:
+            os.sched_setaffinity(0, cpus & allowed)
+    except Exception:
+        pass
 
 
 def measured_peak():
@@ -251,6 +268,7 @@ def main():
         raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    bind_to_gpu_numa_node(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # stdout carries the one JSON line only
@@ -278,14 +296,17 @@ def main():
         rec, log = ctx.call_chunks(chunks, view=True)
     sampler = ClockSampler(local_rank)
     barrier()
-    sampler.start()
+    if rank == 0:  # one sampler for the job: eight concurrent NVML pollers slow every rank's driver calls down
+        sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     k_ms = {}
     e0.record(stream)
     for _ in range(args.steps):
-        rec, log = ctx.call_chunks(chunks, view=True)
+        # the record copy of a step (20 MB, device -> pinned host) overlaps the next step's kernels
+        rec, log = ctx.call_chunks(chunks, view=True, wait=False)
         for name, ms in ctx.last_kernel_times():
             k_ms.setdefault(name, []).append(ms)
+    ctx.records_wait()  # every step's records are in host memory before the clock stops
     e1.record(stream)
     barrier()
     ms_total = e0.elapsed_time(e1)

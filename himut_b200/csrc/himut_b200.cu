@@ -8,6 +8,7 @@
 // Everything per base / per read / per site runs in the kernels of kernels.cuh and
 // normcounts.cuh.  There is no CPU fallback: without a CUDA device hm_create fails.
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -23,6 +24,9 @@
 #include "kernels.cuh"
 #include "normcounts.cuh"
 #include "normfast.cuh"
+
+#define HM_BOUNDARY_CAP_DEFAULT 65536   // boundary records the device list holds (HIMUT_B200_BOUNDARY_CAP overrides: tests)
+#define HM_BOUNDARY_FIRST 2048  // ... of which this many travel with the counters
 
 namespace {
 
@@ -70,7 +74,13 @@ struct hm_ctx {
   DevPhase dphase = {nullptr, nullptr, nullptr, nullptr, nullptr, 0};
   // work buffers
   DevBuf b_chunks, b_pair_off, b_pair_hap, b_qseen, b_keys, b_keys_sorted, b_cub, b_records, b_counters;
-  DevBuf b_ref, b_norm_out, b_lut, b_tile_off, b_agg, b_geom, b_bidx;
+  DevBuf b_ref, b_norm_out, b_lut, b_tile_off, b_agg, b_geom, b_bidx, b_brecs;
+  cudaStream_t copy_stream = nullptr;       // record read-back runs here so it can overlap the next call's kernels
+  cudaEvent_t ev_copy_done[2] = {nullptr, nullptr};
+  DevBuf b_records_alt;                     // second record buffer: calls alternate
+  int rec_parity = 0;
+  bool copy_pending = false;
+  unsigned long long* h_cnt_pin = nullptr; // pinned: counters + boundary indices + boundary records of a call
   DevLut dlut = {nullptr};
   // pinned staging for records coming back, final records of the last call
   hm_site_record* h_stage = nullptr;
@@ -245,6 +255,12 @@ int hm_create(int cuda_device, hm_ctx** out) {
     return HM_ERR_CUDA;
   }
   memset(&ctx->db, 0, sizeof(ctx->db));
+  if (cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&ctx->ev_copy_done[0], cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&ctx->ev_copy_done[1], cudaEventDisableTiming) != cudaSuccess) {
+    delete ctx;
+    return HM_ERR_CUDA;
+  }
   *out = ctx;
   return HM_OK;
 }
@@ -253,15 +269,19 @@ void hm_destroy(hm_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
+  if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
+  for (cudaEvent_t e : ctx->ev_copy_done) if (e) cudaEventDestroy(e);
+  ctx->b_records_alt.release();
   DevBuf* bufs[] = {&ctx->b_tstart, &ctx->b_tend, &ctx->b_qstart, &ctx->b_qlen, &ctx->b_mapq, &ctx->b_flags, &ctx->b_qname,
                     &ctx->b_seq_off, &ctx->b_bq_off, &ctx->b_op_off, &ctx->b_n_ops, &ctx->b_seq, &ctx->b_bq, &ctx->b_ops,
                     &ctx->b_op_t, &ctx->b_op_q, &ctx->b_mm, &ctx->b_bq_total, &ctx->b_n_match, &ctx->b_n_sub,
                     &ctx->b_ins_len, &ctx->b_del_len, &ctx->b_n_mm, &ctx->b_gate, &ctx->b_pmax, &ctx->b_tix_off, &ctx->b_tix, &ctx->b_common, &ctx->b_pon,
                     &ctx->b_hpos, &ctx->b_href, &ctx->b_halt, &ctx->b_hbit, &ctx->b_set_off, &ctx->b_chunks,
                     &ctx->b_pair_off, &ctx->b_pair_hap, &ctx->b_qseen, &ctx->b_keys, &ctx->b_keys_sorted, &ctx->b_cub,
-                    &ctx->b_records, &ctx->b_counters, &ctx->b_ref, &ctx->b_norm_out, &ctx->b_lut, &ctx->b_tile_off, &ctx->b_agg, &ctx->b_geom, &ctx->b_bidx, &ctx->b_sites, &ctx->b_koff, &ctx->b_tile_info, &ctx->b_edge_counts, &ctx->b_edge_hpos, &ctx->b_edge_href, &ctx->b_bqmask, &ctx->b_bqexc, &ctx->b_bqexc_off};
+                    &ctx->b_records, &ctx->b_counters, &ctx->b_ref, &ctx->b_norm_out, &ctx->b_lut, &ctx->b_tile_off, &ctx->b_agg, &ctx->b_geom, &ctx->b_bidx, &ctx->b_brecs, &ctx->b_sites, &ctx->b_koff, &ctx->b_tile_info, &ctx->b_edge_counts, &ctx->b_edge_hpos, &ctx->b_edge_href, &ctx->b_bqmask, &ctx->b_bqexc, &ctx->b_bqexc_off};
   for (DevBuf* b : bufs) b->release();
   if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+  if (ctx->h_cnt_pin) cudaFreeHost(ctx->h_cnt_pin);
   for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
   if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
@@ -445,12 +465,40 @@ static int upload_batch_impl(hm_ctx* ctx, const hm_read_batch* b, const hm_bq_co
   return HM_OK;
 }
 
+static int call_chunks_impl(hm_ctx* ctx, const hm_chunk* chunks, size_t n_chunks, hm_site_record* out, size_t cap, size_t* n_out,
+                           int64_t log[HM_CALL_LOG_LEN], bool async);
+
 int hm_call_chunks(hm_ctx* ctx, const hm_chunk* chunks, size_t n_chunks, hm_site_record* out, size_t cap, size_t* n_out,
                    int64_t log[HM_CALL_LOG_LEN]) {
+  return call_chunks_impl(ctx, chunks, n_chunks, out, cap, n_out, log, false);
+}
+
+/* hm_call_chunks that returns as soon as the counters are final: the record copy into `out` may still be in
+ * flight (on the context's copy stream) and overlaps whatever the caller enqueues next; hm_records_wait blocks
+ * until `out` is complete.  Two calls may be in flight: `out` must not be reused before the second next call. */
+int hm_call_chunks_async(hm_ctx* ctx, const hm_chunk* chunks, size_t n_chunks, hm_site_record* out, size_t cap, size_t* n_out,
+                         int64_t log[HM_CALL_LOG_LEN]) {
+  return call_chunks_impl(ctx, chunks, n_chunks, out, cap, n_out, log, true);
+}
+
+int hm_records_wait(hm_ctx* ctx) {
+  if (!ctx) return HM_ERR_ARG;
+  CU(cudaSetDevice(ctx->device));
+  if (ctx->copy_pending) { CU(cudaStreamSynchronize(ctx->copy_stream)); ctx->copy_pending = false; }
+  return HM_OK;
+}
+
+static int call_chunks_impl(hm_ctx* ctx, const hm_chunk* chunks, size_t n_chunks, hm_site_record* out, size_t cap, size_t* n_out,
+                            int64_t log[HM_CALL_LOG_LEN], bool async) {
   int rc = check_ready(ctx, chunks, n_chunks);
   if (rc) return rc;
   if (!log || !n_out) return fail(ctx, HM_ERR_ARG, "log / n_out is NULL");
   CU(cudaSetDevice(ctx->device));
+  // HIMUT_B200_HOST_TIMING=1: wall-clock of the host-visible phases of one call, to stderr (diagnostics)
+  static const bool host_timing = getenv("HIMUT_B200_HOST_TIMING") != nullptr;
+  auto tp0 = std::chrono::steady_clock::now();
+  double ht[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  auto lap = [&](int i) { auto t = std::chrono::steady_clock::now(); ht[i] += std::chrono::duration<double, std::milli>(t - tp0).count(); tp0 = t; };
   memset(log, 0, sizeof(int64_t) * HM_CALL_LOG_LEN);
   *n_out = 0;
   ctx->final_recs.clear();
@@ -487,8 +535,10 @@ int hm_call_chunks(hm_ctx* ctx, const hm_chunk* chunks, size_t n_chunks, hm_site
                                                   ctx->b_qseen.as<uint8_t>(), ctx->b_keys.as<unsigned long long>(), key_cap, d_cnt, pos_bits);
     t_end(ctx);
     CU(cudaGetLastError());
+    lap(0); // uploads + launches up to k_candidates
     CU(cudaMemcpyAsync(h_cnt, ctx->b_counters.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
+    lap(1); // sync 1: candidate count
     if (h_cnt[0] <= key_cap) break;
     key_cap = h_cnt[0];
   }
@@ -509,9 +559,14 @@ int hm_call_chunks(hm_ctx* ctx, const hm_chunk* chunks, size_t n_chunks, hm_site
   }
 
   size_t n_unique = 0, n_boundary = 0;
+  const int parity = ctx->rec_parity;
+  DevBuf& rec_buf = parity ? ctx->b_records_alt : ctx->b_records;
+  size_t HM_BOUNDARY_CAP = HM_BOUNDARY_CAP_DEFAULT;
+  if (const char* e = getenv("HIMUT_B200_BOUNDARY_CAP")) HM_BOUNDARY_CAP = (size_t)std::max(0ll, atoll(e));
   hm_site_record* recs = nullptr; // where the device records land on the host
   bool direct = false;
-  std::vector<uint32_t> bidx;
+  bool have_all = false; // the records are already on the host (fallback of the boundary replay)
+  std::vector<std::pair<uint32_t, hm_site_record>> border; // (index in key order, record) of the boundary records
   if (n_pairs) {
     if (n_keys) {
       // sort + unique of the candidate keys (library plumbing: cub), then the site kernels
@@ -532,15 +587,19 @@ int hm_call_chunks(hm_ctx* ctx, const hm_chunk* chunks, size_t n_chunks, hm_site
       t_end(ctx);
       CU(cudaMemcpyAsync(h_cnt + 1, d_cnt + 1, 8, cudaMemcpyDeviceToHost, ctx->stream));
       if ((rc = upload(ctx, ctx->b_geom, geom.data(), 2 * n_chunks))) return rc;
+      lap(2); // sort / unique launches
       CU(cudaStreamSynchronize(ctx->stream));
+      lap(3); // sync 2: distinct count
       n_unique = (size_t)h_cnt[1];
       const uint64_t stride = (n_unique + 31) & ~31ull;
       CU(ctx->b_agg.ensure(stride * HM_SITE_SLOTS * 4 + n_unique * 8));
       uint32_t* entries = ctx->b_agg.as<uint32_t>();
       uint32_t* site_lo = entries + stride * HM_SITE_SLOTS;
       uint32_t* site_n = site_lo + n_unique;
-      CU(ctx->b_records.ensure(n_unique * sizeof(hm_site_record)));
-      CU(ctx->b_bidx.ensure(n_unique * 4));
+      CU(rec_buf.ensure(n_unique * sizeof(hm_site_record)));
+      CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_copy_done[parity], 0)); // the copy that last read this buffer
+      CU(ctx->b_bidx.ensure((size_t)HM_BOUNDARY_CAP * 4 + HM_BOUNDARY_FIRST * 4));
+      CU(ctx->b_brecs.ensure(((size_t)HM_BOUNDARY_CAP + HM_BOUNDARY_FIRST) * sizeof(hm_site_record)));
       t_begin(ctx, "k_site_range");
       k_site_range<<<(unsigned)((n_unique + 255) / 256), 256, 0, ctx->stream>>>(ctx->db, ctx->b_chunks.as<hm_chunk>(), k_in, d_cnt + 1,
                                                                               site_lo, site_n);
@@ -568,8 +627,8 @@ int hm_call_chunks(hm_ctx* ctx, const hm_chunk* chunks, size_t n_chunks, hm_site
       k_site_reduce<<<(unsigned)((n_unique + 127) / 128), 128, 0, ctx->stream>>>(
           ctx->db, ctx->dp, ctx->dsets, ctx->dlut, ctx->b_chunks.as<hm_chunk>(), ctx->b_pair_off.as<uint64_t>(),
           ctx->b_pair_hap.as<uint8_t>(), ctx->b_geom.as<int32_t>(), ctx->b_geom.as<int32_t>() + n_chunks, k_in, d_cnt + 1, site_lo,
-          site_n, entries, stride, ctx->b_records.as<hm_site_record>(), d_cnt + 8, ctx->b_bidx.as<uint32_t>(), (uint32_t)n_unique,
-          d_cnt + 4, reinterpret_cast<int*>(d_cnt + 3));
+          site_n, entries, stride, rec_buf.as<hm_site_record>(), d_cnt + 8, ctx->b_bidx.as<uint32_t>(),
+          ctx->b_brecs.as<hm_site_record>(), (uint32_t)HM_BOUNDARY_CAP, d_cnt + 4, reinterpret_cast<int*>(d_cnt + 3));
       t_end(ctx);
       CU(cudaGetLastError());
     }
@@ -577,49 +636,77 @@ int hm_call_chunks(hm_ctx* ctx, const hm_chunk* chunks, size_t n_chunks, hm_site
     k_count_flags<<<148, 256, 0, ctx->stream>>>(ctx->b_qseen.as<uint8_t>(), (uint64_t)ctx->max_qname_id + 1, d_cnt + 2);
     t_end(ctx);
     CU(cudaGetLastError());
-    // records straight into the caller's buffer when it is large enough, else into pinned staging
+    // records go straight into the caller's buffer when it is large enough, else into pinned staging
     direct = out && cap >= n_unique;
-    if (n_unique) {
-      if (!direct) {
-        if (n_unique > ctx->h_stage_cap) {
-          if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
-          ctx->h_stage = nullptr; ctx->h_stage_cap = 0;
-          const size_t want = n_unique + n_unique / 4 + 1024;
-          CU(cudaHostAlloc((void**)&ctx->h_stage, want * sizeof(hm_site_record), cudaHostAllocDefault));
-          ctx->h_stage_cap = want;
-        }
-        recs = ctx->h_stage;
-      } else recs = out;
-      CU(cudaMemcpyAsync(recs, ctx->b_records.p, n_unique * sizeof(hm_site_record), cudaMemcpyDeviceToHost, ctx->stream));
+    if (n_unique && !direct) {
+      if (n_unique > ctx->h_stage_cap) {
+        if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+        ctx->h_stage = nullptr; ctx->h_stage_cap = 0;
+        const size_t want = n_unique + n_unique / 4 + 1024;
+        CU(cudaHostAlloc((void**)&ctx->h_stage, want * sizeof(hm_site_record), cudaHostAllocDefault));
+        ctx->h_stage_cap = want;
+      }
     }
-    CU(cudaMemcpyAsync(h_cnt, ctx->b_counters.p, CNT_BYTES, cudaMemcpyDeviceToHost, ctx->stream));
+    recs = n_unique ? (direct ? out : ctx->h_stage) : nullptr;
+    // First the small things: counters and the boundary records (the only ones the sequential som_seen replay
+    // looks at).  The big record copy follows the replay, so records a previous chunk already claimed are skipped
+    // by the copy itself instead of being squeezed out of 20 MB on the host.
+    if (!ctx->h_cnt_pin) CU(cudaHostAlloc((void**)&ctx->h_cnt_pin, CNT_BYTES + HM_BOUNDARY_FIRST * (4 + sizeof(hm_site_record)), cudaHostAllocDefault));
+    uint32_t* h_bidx = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(ctx->h_cnt_pin) + CNT_BYTES);
+    hm_site_record* h_brecs = reinterpret_cast<hm_site_record*>(h_bidx + HM_BOUNDARY_FIRST);
+    CU(cudaMemcpyAsync(ctx->h_cnt_pin, ctx->b_counters.p, CNT_BYTES, cudaMemcpyDeviceToHost, ctx->stream));
+    if (n_keys) {
+      CU(cudaMemcpyAsync(h_bidx, ctx->b_bidx.p, HM_BOUNDARY_FIRST * 4, cudaMemcpyDeviceToHost, ctx->stream));
+      CU(cudaMemcpyAsync(h_brecs, ctx->b_brecs.p, HM_BOUNDARY_FIRST * sizeof(hm_site_record), cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    lap(4); // site kernel launches enqueued
     CU(cudaStreamSynchronize(ctx->stream));
+    lap(5); // sync 3: site kernels
+    memcpy(h_cnt, ctx->h_cnt_pin, CNT_BYTES);
     if ((int)h_cnt[3] == HM_ERR_BQ_ZERO) return fail(ctx, HM_ERR_BQ_ZERO, "a base quality of 0 reached the genotype model (the reference raises ValueError: math.log10(0))");
     n_boundary = n_keys ? (size_t)h_cnt[4] : 0;
-    if (n_boundary) {
-      bidx.resize(n_boundary);
-      CU(cudaMemcpyAsync(bidx.data(), ctx->b_bidx.p, n_boundary * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (n_boundary > HM_BOUNDARY_CAP) {
+      // heavily overlapping region lists: more boundary records than the device list holds.  Fetch everything and
+      // find them on the host with the same test k_site_reduce applies.
+      CU(cudaMemcpyAsync(recs, rec_buf.p, n_unique * sizeof(hm_site_record), cudaMemcpyDeviceToHost, ctx->stream));
       CU(cudaStreamSynchronize(ctx->stream));
+      border.clear();
+      for (size_t i = 0; i < n_unique; i++)
+        if (recs[i].tpos <= prev_max_end[recs[i].chunk] || recs[i].tpos >= next_min_start[recs[i].chunk]) border.emplace_back((uint32_t)i, recs[i]);
+      n_boundary = border.size();
+      have_all = true;
+    } else if (n_boundary) {
+      border.resize(n_boundary);
+      if (n_boundary <= (size_t)HM_BOUNDARY_FIRST) {
+        for (size_t i = 0; i < n_boundary; i++) border[i] = std::make_pair(h_bidx[i], h_brecs[i]);
+      } else {
+        std::vector<uint32_t> bi(n_boundary);
+        std::vector<hm_site_record> br(n_boundary);
+        CU(cudaMemcpyAsync(bi.data(), ctx->b_bidx.p, n_boundary * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaMemcpyAsync(br.data(), ctx->b_brecs.p, n_boundary * sizeof(hm_site_record), cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        for (size_t i = 0; i < n_boundary; i++) border[i] = std::make_pair(bi[i], br[i]);
+      }
     }
   }
-  t_collect(ctx);
+  lap(6); // boundary list
 
   // sequential part: chunk order, som_seen carry (caller.py:324-347; bamlib.py:77), over the
   // boundary records only.  Indices are positions in the key order = (chunk, tpos, ref, alt).
   unsigned long long* hist = h_cnt + 8;
   std::vector<uint32_t> dropped;
   if (n_boundary) {
-    std::sort(bidx.begin(), bidx.end());
+    std::sort(border.begin(), border.end(), [](const std::pair<uint32_t, hm_site_record>& a, const std::pair<uint32_t, hm_site_record>& b) { return a.first < b.first; });
     std::unordered_set<int32_t> som_seen;
     std::vector<int32_t> adds;
     size_t i = 0;
     while (i < n_boundary) {
-      const int32_t chunk = recs[bidx[i]].chunk;
+      const int32_t chunk = border[i].second.chunk;
       adds.clear();
-      for (; i < n_boundary && recs[bidx[i]].chunk == chunk; i++) {
-        const hm_site_record& R = recs[bidx[i]];
+      for (; i < n_boundary && border[i].second.chunk == chunk; i++) {
+        const hm_site_record& R = border[i].second;
         if (R.tpos <= prev_max_end[chunk] && som_seen.count(R.tpos)) { // dropped in get_tsbs_candidates
-          dropped.push_back(bidx[i]);
+          dropped.push_back(border[i].first);
           hist[R.status]--;
           continue;
         }
@@ -629,6 +716,32 @@ int hm_call_chunks(hm_ctx* ctx, const hm_chunk* chunks, size_t n_chunks, hm_site
       for (int32_t t : adds) som_seen.insert(t);
     }
   }
+  // the records, minus the dropped ones (ascending indices): one copy per run between two dropped records
+  size_t n_final = 0;
+  if (n_unique && have_all) {
+    size_t from = 0;
+    for (size_t d = 0; d <= dropped.size(); d++) {
+      const size_t to = d < dropped.size() ? dropped[d] : n_unique;
+      if (to > from && n_final != from) memmove(recs + n_final, recs + from, (to - from) * sizeof(hm_site_record));
+      n_final += to - from;
+      from = to + 1;
+    }
+  } else if (n_unique) {
+    size_t from = 0;
+    for (size_t d = 0; d <= dropped.size(); d++) {
+      const size_t to = d < dropped.size() ? dropped[d] : n_unique;
+      if (to > from)
+        CU(cudaMemcpyAsync(recs + n_final, rec_buf.as<hm_site_record>() + from, (to - from) * sizeof(hm_site_record),
+                           cudaMemcpyDeviceToHost, ctx->copy_stream)); // the kernels are done: the main stream was synchronised above
+      n_final += to - from;
+      from = to + 1;
+    }
+    CU(cudaEventRecord(ctx->ev_copy_done[parity], ctx->copy_stream));
+    ctx->copy_pending = true;
+    ctx->rec_parity ^= 1;
+    if (!async || !direct) { CU(cudaStreamSynchronize(ctx->copy_stream)); ctx->copy_pending = false; }
+  }
+  t_collect(ctx);
   // chrom2tsbs_log (caller.py:625-641) from the status tallies
   {
     unsigned long long total = 0;
@@ -643,18 +756,11 @@ int hm_call_chunks(hm_ctx* ctx, const hm_chunk* chunks, size_t n_chunks, hm_site
     log[14] = (int64_t)(hist[HM_ST_PASS] + hist[HM_ST_UNPHASED]); // num_som is counted before the phase verdict
     log[6] = log[8] + log[9] + log[10] + log[11] + log[12] + log[13] + log[14];
   }
-  // squeeze the dropped records out (ascending indices)
-  size_t n_final = n_unique;
-  if (!dropped.empty() && recs) {
-    size_t w = dropped[0];
-    for (size_t d = 0; d < dropped.size(); d++) {
-      const size_t from = (size_t)dropped[d] + 1, to = d + 1 < dropped.size() ? dropped[d + 1] : n_unique;
-      memmove(recs + w, recs + from, (to - from) * sizeof(hm_site_record));
-      w += to - from;
-    }
-    n_final = w;
-  }
   *n_out = n_final;
+  lap(7); // host replay
+  if (host_timing)
+    fprintf(stderr, "[host timing, dev %d] enqueue %.3f | sync1 %.3f | sort enqueue %.3f | sync2 %.3f | sites enqueue %.3f | sync3 %.3f | boundary %.3f | replay %.3f ms\n",
+            ctx->device, ht[0], ht[1], ht[2], ht[3], ht[4], ht[5], ht[6], ht[7]);
   if (!direct && n_final) {
     if (out && cap >= n_final) memcpy(out, recs, n_final * sizeof(hm_site_record));
     else {

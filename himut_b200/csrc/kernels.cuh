@@ -707,7 +707,8 @@ __global__ void __launch_bounds__(128) k_site_reduce(DevBatch b, DevParams p, De
                                                      const unsigned long long* n_keys_dev, const uint32_t* site_lo,
                                                      const uint32_t* site_n, const uint32_t* entries, uint64_t stride,
                                                      hm_site_record* out, unsigned long long* status_hist, uint32_t* boundary_idx,
-                                                     uint32_t boundary_cap, unsigned long long* n_boundary, int* err_flag) {
+                                                     hm_site_record* boundary_recs, uint32_t boundary_cap,
+                                                     unsigned long long* n_boundary, int* err_flag) {
   __shared__ unsigned int s_hist[16];
   __shared__ double s_lut[3][256];
   for (int i = threadIdx.x; i < 768; i += blockDim.x) s_lut[i >> 8][i & 255] = __ldg(lut.lut + i);
@@ -814,7 +815,7 @@ __global__ void __launch_bounds__(128) k_site_reduce(DevBatch b, DevParams p, De
     atomicAdd(&s_hist[status], 1u);
     if (tpos <= prev_max_end[c] || tpos >= next_min_start[c]) {
       const unsigned long long at = atomicAdd(n_boundary, 1ull);
-      if (at < boundary_cap) boundary_idx[at] = (uint32_t)ki;
+      if (at < boundary_cap) { boundary_idx[at] = (uint32_t)ki; boundary_recs[at] = R; } // a copy for the host's som_seen replay
     }
   }
   __syncthreads();

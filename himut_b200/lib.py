@@ -20,7 +20,7 @@ EXPORTS = [
     "hm_set_phase_sets", "hm_upload_batch", "hm_call_chunks", "hm_call_batch", "hm_normcounts_chunks",
     "hm_read_stats", "hm_last_timing", "hm_last_kernel_times", "hm_set_stream", "hm_host_register",
     "hm_host_unregister", "hm_abi_sizeof", "hm_last_records", "hm_qname_seen", "hm_set_reference", "hm_ref_tricounts", "hm_last_norm_exact_sites",
-    "hm_phase_edges_begin", "hm_phase_edges_add", "hm_phase_edges_end", "hm_upload_batch_compact", "hm_call_batch_compact",
+    "hm_phase_edges_begin", "hm_phase_edges_add", "hm_phase_edges_end", "hm_upload_batch_compact", "hm_call_batch_compact", "hm_call_chunks_async", "hm_records_wait",
 ]
 
 
@@ -51,12 +51,14 @@ def load():
         lib.hm_set_phase_sets.argtypes = [vp, vp, vp, vp, vp, sz, vp, sz]
         lib.hm_upload_batch.argtypes = [vp, C.POINTER(abi.hm_read_batch)]
         lib.hm_call_chunks.argtypes = [vp, vp, sz, vp, sz, C.POINTER(sz), vp]
+        lib.hm_call_chunks_async.argtypes = [vp, vp, sz, vp, sz, C.POINTER(sz), vp]
         lib.hm_call_batch.argtypes = [vp, C.POINTER(abi.hm_read_batch), vp, sz, vp, sz, C.POINTER(sz), vp]
         lib.hm_normcounts_chunks.argtypes = [vp, vp, sz, vp, sz, vp, vp, vp, C.POINTER(C.c_int64)]
         lib.hm_read_stats.argtypes = [vp, vp, vp, vp, vp, vp, vp]
         lib.hm_last_timing.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_int)]
         lib.hm_last_kernel_times.argtypes = [vp, vp, vp, sz, C.POINTER(sz)]
         lib.hm_last_records.argtypes = [vp, vp, sz, C.POINTER(sz)]
+        lib.hm_records_wait.argtypes = [vp]
         lib.hm_qname_seen.argtypes = [vp, vp, sz, C.POINTER(sz)]
         lib.hm_set_reference.argtypes = [vp, vp, sz]
         lib.hm_ref_tricounts.argtypes = [vp, vp, sz, vp]
@@ -169,15 +171,22 @@ class Context:
                 del self._keep[id(a)]
 
     def _out_buffer(self, cap):
-        """persistent page-locked record buffer (records are copied device -> here directly)"""
-        buf = getattr(self, "_out", None)
+        """persistent page-locked record buffers (records are copied device -> here directly); two of them,
+        used alternately, so that an asynchronous call's records stay valid while the next call runs"""
+        bufs = getattr(self, "_outs", None)
+        if bufs is None:
+            bufs = self._outs = [None, None]
+            self._out_i = 0
+        self._out_i ^= 1
+        buf = bufs[self._out_i]
         if buf is None or buf.shape[0] < cap:
+            self._chk(self.lib.hm_records_wait(self.h))
             if buf is not None:
                 self.lib.hm_host_unregister(self.h, _p(buf))
             buf = np.empty(cap, dtype=abi.SITE_DTYPE)
             self._chk(self.lib.hm_host_register(self.h, _p(buf), buf.nbytes))
-            self._out = buf
-        return self._out
+            bufs[self._out_i] = buf
+        return buf
 
     def _call(self, fn, head, chunks, cap, view):
         chunks = np.ascontiguousarray(chunks, dtype=abi.CHUNK_DTYPE)
@@ -193,10 +202,17 @@ class Context:
         res = out[: n.value]
         return (res if view else res.copy()), log
 
-    def call_chunks(self, chunks, cap=None, view=False):
+    def call_chunks(self, chunks, cap=None, view=False, wait=True):
         """`himut call` over the resident batch -> (records, log[15]).
-        view=True returns a view of the context's pinned buffer, valid until the next call."""
-        return self._call(self.lib.hm_call_chunks, (), chunks, cap, view)
+        view=True returns a view of one of the context's two pinned buffers, valid until the second next call.
+        wait=False (needs view=True): the records may still be on their way when this returns — the copy overlaps
+        the next call's kernels; records_wait() completes them."""
+        if not wait and not view:
+            raise ValueError("wait=False needs view=True")
+        return self._call(self.lib.hm_call_chunks if wait else self.lib.hm_call_chunks_async, (), chunks, cap, view)
+
+    def records_wait(self):
+        self._chk(self.lib.hm_records_wait(self.h))
 
     def call_batch(self, batch, chunks, cap=None, view=False):
         """upload + call (host buffers in, records out): the end-to-end path"""

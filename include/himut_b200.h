@@ -258,6 +258,17 @@ int hm_call_chunks(hm_ctx* ctx, const hm_chunk* chunks, size_t n_chunks,
                    hm_site_record* out, size_t cap, size_t* n_out,
                    int64_t log[HM_CALL_LOG_LEN]);
 
+/* hm_call_chunks that returns as soon as the counters and *n_out are final: the copy of the records into `out` may
+ * still be in flight (on a copy stream of the context) and overlaps whatever the caller enqueues next — a worker
+ * that feeds a contig in several batches decodes / uploads / scans the next one meanwhile.  hm_records_wait blocks
+ * until the records of every earlier call are complete.  At most two calls may be in flight: an `out` buffer must
+ * not be reused before the second next call.  `out` must hold all records (HM_ERR_CAPACITY behaves as above, and
+ * then synchronously).                                                                                          */
+int hm_call_chunks_async(hm_ctx* ctx, const hm_chunk* chunks, size_t n_chunks,
+                         hm_site_record* out, size_t cap, size_t* n_out,
+                         int64_t log[HM_CALL_LOG_LEN]);
+int hm_records_wait(hm_ctx* ctx);
+
 /* after hm_call_chunks / hm_call_batch returned HM_ERR_CAPACITY: copy the records of that call
  * into a buffer of at least *n_out entries, without recomputing anything */
 int hm_last_records(hm_ctx* ctx, hm_site_record* out, size_t cap, size_t* n_out);

@@ -132,3 +132,30 @@ def test_malformed_batch_is_rejected(ctx):
     with pytest.raises(lib.HimutError) as e:
         ctx.upload(d.batch)
     assert e.value.code == abi.HM_ERR_ARG
+
+
+def test_async_record_copy_equals_synchronous(ctx):
+    """hm_call_chunks_async: the record copy overlaps the next call; after records_wait the buffers hold exactly
+    what the synchronous call returns, for several calls in flight"""
+    from himut_b200 import gtmodel, synth
+    d = synth.generate(400_000, seed=71)
+    p = gtmodel.make_params(**gtmodel.DEFAULT_CALL_ARGS)
+    loci = cases.chunkloci(0, 400_000)
+    tables = [d.batch.chunk_table(loci), d.batch.chunk_table(loci[:1]), d.batch.chunk_table(loci[1:])]
+    ctx.set_params(p)
+    ctx.set_site_sets()
+    ctx.upload(d.batch)
+    sync = [ctx.call_chunks(t) for t in tables]
+    for _ in range(2):
+        pend = []
+        for t in tables[:2]:
+            pend.append(ctx.call_chunks(t, view=True, wait=False))
+        ctx.records_wait()
+        for (rec, log), (srec, slog) in zip(pend, sync[:2]):
+            assert list(log) == list(slog)
+            ok, why = parity.records_equal(rec, srec)
+            assert ok, why
+    rec, log = ctx.call_chunks(tables[2], view=True, wait=False)
+    ctx.records_wait()
+    ok, why = parity.records_equal(rec, sync[2][0])
+    assert ok, why
