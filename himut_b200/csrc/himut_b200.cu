@@ -511,6 +511,7 @@ static int call_chunks_impl(hm_ctx* ctx, const hm_chunk* chunks, size_t n_chunks
   // counters (u64): [0] n_keys, [1] n_unique, [2] num_ccs, [3] error flag, [4] n_boundary, [8..23] status histogram
   const size_t CNT_BYTES = 256;
   CU(ctx->b_counters.ensure(CNT_BYTES));
+  if (!ctx->h_cnt_pin) CU(cudaHostAlloc((void**)&ctx->h_cnt_pin, CNT_BYTES + HM_BOUNDARY_FIRST * (4 + sizeof(hm_site_record)), cudaHostAllocMapped));
   CU(ctx->b_qseen.ensure((size_t)ctx->max_qname_id + 1));
   if (ctx->params.phase) CU(ctx->b_pair_hap.ensure(n_pairs + 16));
   unsigned long long h_cnt[32];
@@ -536,8 +537,9 @@ static int call_chunks_impl(hm_ctx* ctx, const hm_chunk* chunks, size_t n_chunks
     t_end(ctx);
     CU(cudaGetLastError());
     lap(0); // uploads + launches up to k_candidates
-    CU(cudaMemcpyAsync(h_cnt, ctx->b_counters.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    k_publish<<<1, 32, 0, ctx->stream>>>(reinterpret_cast<const uint32_t*>(d_cnt), reinterpret_cast<uint32_t*>(ctx->h_cnt_pin), 2);
     CU(cudaStreamSynchronize(ctx->stream));
+    h_cnt[0] = ctx->h_cnt_pin[0];
     lap(1); // sync 1: candidate count
     if (h_cnt[0] <= key_cap) break;
     key_cap = h_cnt[0];
@@ -585,10 +587,11 @@ static int call_chunks_impl(hm_ctx* ctx, const hm_chunk* chunks, size_t n_chunks
       CU(cub::DeviceSelect::Unique(ctx->b_cub.p, tmp_uniq, k_sorted, k_in, d_cnt + 1, (int64_t)n_keys, ctx->stream));
       k_expand_keys<<<(unsigned)((n_keys + 255) / 256), 256, 0, ctx->stream>>>(k_in, d_cnt + 1, ctx->b_chunks.as<hm_chunk>(), pos_bits);
       t_end(ctx);
-      CU(cudaMemcpyAsync(h_cnt + 1, d_cnt + 1, 8, cudaMemcpyDeviceToHost, ctx->stream));
+      k_publish<<<1, 32, 0, ctx->stream>>>(reinterpret_cast<const uint32_t*>(d_cnt + 1), reinterpret_cast<uint32_t*>(ctx->h_cnt_pin + 1), 2);
       if ((rc = upload(ctx, ctx->b_geom, geom.data(), 2 * n_chunks))) return rc;
       lap(2); // sort / unique launches
       CU(cudaStreamSynchronize(ctx->stream));
+      h_cnt[1] = ctx->h_cnt_pin[1];
       lap(3); // sync 2: distinct count
       n_unique = (size_t)h_cnt[1];
       const uint64_t stride = (n_unique + 31) & ~31ull;
@@ -651,14 +654,15 @@ static int call_chunks_impl(hm_ctx* ctx, const hm_chunk* chunks, size_t n_chunks
     // First the small things: counters and the boundary records (the only ones the sequential som_seen replay
     // looks at).  The big record copy follows the replay, so records a previous chunk already claimed are skipped
     // by the copy itself instead of being squeezed out of 20 MB on the host.
-    if (!ctx->h_cnt_pin) CU(cudaHostAlloc((void**)&ctx->h_cnt_pin, CNT_BYTES + HM_BOUNDARY_FIRST * (4 + sizeof(hm_site_record)), cudaHostAllocDefault));
     uint32_t* h_bidx = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(ctx->h_cnt_pin) + CNT_BYTES);
     hm_site_record* h_brecs = reinterpret_cast<hm_site_record*>(h_bidx + HM_BOUNDARY_FIRST);
-    CU(cudaMemcpyAsync(ctx->h_cnt_pin, ctx->b_counters.p, CNT_BYTES, cudaMemcpyDeviceToHost, ctx->stream));
+    k_publish<<<1, 64, 0, ctx->stream>>>(reinterpret_cast<const uint32_t*>(d_cnt), reinterpret_cast<uint32_t*>(ctx->h_cnt_pin), (uint32_t)(CNT_BYTES / 4));
     if (n_keys) {
-      CU(cudaMemcpyAsync(h_bidx, ctx->b_bidx.p, HM_BOUNDARY_FIRST * 4, cudaMemcpyDeviceToHost, ctx->stream));
-      CU(cudaMemcpyAsync(h_brecs, ctx->b_brecs.p, HM_BOUNDARY_FIRST * sizeof(hm_site_record), cudaMemcpyDeviceToHost, ctx->stream));
+      k_publish_items<<<4, 256, 0, ctx->stream>>>(ctx->b_bidx.as<uint32_t>(), h_bidx, 1u, (uint32_t)HM_BOUNDARY_FIRST, d_cnt + 4);
+      k_publish_items<<<8, 256, 0, ctx->stream>>>(ctx->b_brecs.as<uint32_t>(), reinterpret_cast<uint32_t*>(h_brecs),
+                                                  (uint32_t)(sizeof(hm_site_record) / 4), (uint32_t)HM_BOUNDARY_FIRST, d_cnt + 4);
     }
+    CU(cudaGetLastError());
     lap(4); // site kernel launches enqueued
     CU(cudaStreamSynchronize(ctx->stream));
     lap(5); // sync 3: site kernels

@@ -822,6 +822,21 @@ __global__ void __launch_bounds__(128) k_site_reduce(DevBatch b, DevParams p, De
   if (threadIdx.x < 16 && s_hist[threadIdx.x]) atomicAdd(status_hist + threadIdx.x, (unsigned long long)s_hist[threadIdx.x]);
 }
 
+// Small results go to the host through mapped pinned memory (plain stores over PCIe) instead of the copy engine,
+// where they would queue behind a previous call's 20 MB record copy.  words of 4 bytes; *n_src_limit (optional)
+// bounds how many `item_words`-sized items of src are worth sending.
+__global__ void k_publish(const uint32_t* src, uint32_t* mapped_dst, uint32_t n_words) {
+  for (uint32_t i = threadIdx.x; i < n_words; i += blockDim.x) mapped_dst[i] = src[i];
+  __threadfence_system();
+}
+__global__ void k_publish_items(const uint32_t* src, uint32_t* mapped_dst, uint32_t item_words, uint32_t max_items,
+                                const unsigned long long* n_items_dev) {
+  const unsigned long long n = min((unsigned long long)max_items, *n_items_dev);
+  const uint64_t total = n * item_words;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) mapped_dst[i] = src[i];
+  __threadfence_system();
+}
+
 // number of set bytes in flags[0..n)
 __global__ void k_count_flags(const uint8_t* flags, uint64_t n, unsigned long long* out) {
   unsigned long long c = 0;
