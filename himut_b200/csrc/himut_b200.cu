@@ -80,6 +80,10 @@ struct hm_ctx {
   DevBuf b_records_alt;                     // second record buffer: calls alternate
   int rec_parity = 0;
   bool copy_pending = false;
+  struct PendingCopy { void* dst; const void* src; size_t bytes; };
+  std::vector<PendingCopy> deferred;        // record copies of the last async call, not enqueued yet
+  int deferred_parity = 0;
+  cudaEvent_t ev_go = nullptr;              // recorded after k_read_scan: the deferred copies start behind it
   unsigned long long* h_cnt_pin = nullptr; // pinned: counters + boundary indices + boundary records of a call
   DevLut dlut = {nullptr};
   // pinned staging for records coming back, final records of the last call
@@ -190,6 +194,22 @@ void make_norm_cert(hm_ctx* ctx) {
   c.enabled = 1;
 }
 
+// The record copies of an asynchronous call are enqueued late, behind the *next* call's k_read_scan (the one
+// HBM-bound kernel of the path), so they overlap its latency-bound kernels instead; without a next call,
+// hm_records_wait enqueues them.  after_main: make the copy stream wait for what the main stream has queued so far.
+int flush_deferred(hm_ctx* ctx, bool after_main) {
+  if (ctx->deferred.empty()) return HM_OK;
+  if (after_main) {
+    CU(cudaEventRecord(ctx->ev_go, ctx->stream));
+    CU(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_go, 0));
+  }
+  for (const auto& c : ctx->deferred) CU(cudaMemcpyAsync(c.dst, c.src, c.bytes, cudaMemcpyDeviceToHost, ctx->copy_stream));
+  CU(cudaEventRecord(ctx->ev_copy_done[ctx->deferred_parity], ctx->copy_stream));
+  ctx->deferred.clear();
+  ctx->copy_pending = true;
+  return HM_OK;
+}
+
 int check_ready(hm_ctx* ctx, const hm_chunk* chunks, size_t n_chunks) {
   if (!ctx) return HM_ERR_ARG;
   if (!ctx->have_params) return fail(ctx, HM_ERR_STATE, "hm_set_params has not been called");
@@ -257,7 +277,8 @@ int hm_create(int cuda_device, hm_ctx** out) {
   memset(&ctx->db, 0, sizeof(ctx->db));
   if (cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaEventCreateWithFlags(&ctx->ev_copy_done[0], cudaEventDisableTiming) != cudaSuccess ||
-      cudaEventCreateWithFlags(&ctx->ev_copy_done[1], cudaEventDisableTiming) != cudaSuccess) {
+      cudaEventCreateWithFlags(&ctx->ev_copy_done[1], cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&ctx->ev_go, cudaEventDisableTiming) != cudaSuccess) {
     delete ctx;
     return HM_ERR_CUDA;
   }
@@ -271,6 +292,7 @@ void hm_destroy(hm_ctx* ctx) {
   cudaStreamSynchronize(ctx->stream);
   if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
   for (cudaEvent_t e : ctx->ev_copy_done) if (e) cudaEventDestroy(e);
+  if (ctx->ev_go) cudaEventDestroy(ctx->ev_go);
   ctx->b_records_alt.release();
   DevBuf* bufs[] = {&ctx->b_tstart, &ctx->b_tend, &ctx->b_qstart, &ctx->b_qlen, &ctx->b_mapq, &ctx->b_flags, &ctx->b_qname,
                     &ctx->b_seq_off, &ctx->b_bq_off, &ctx->b_op_off, &ctx->b_n_ops, &ctx->b_seq, &ctx->b_bq, &ctx->b_ops,
@@ -484,6 +506,8 @@ int hm_call_chunks_async(hm_ctx* ctx, const hm_chunk* chunks, size_t n_chunks, h
 int hm_records_wait(hm_ctx* ctx) {
   if (!ctx) return HM_ERR_ARG;
   CU(cudaSetDevice(ctx->device));
+  int rc = flush_deferred(ctx, false);
+  if (rc) return rc;
   if (ctx->copy_pending) { CU(cudaStreamSynchronize(ctx->copy_stream)); ctx->copy_pending = false; }
   return HM_OK;
 }
@@ -507,6 +531,7 @@ static int call_chunks_impl(hm_ctx* ctx, const hm_chunk* chunks, size_t n_chunks
   if ((rc = upload_chunks(ctx, chunks, n_chunks, pair_off))) return rc;
   const uint64_t n_pairs = pair_off.back();
   if ((rc = launch_read_scan(ctx))) return rc;
+  if ((rc = flush_deferred(ctx, true))) return rc;
 
   // counters (u64): [0] n_keys, [1] n_unique, [2] num_ccs, [3] error flag, [4] n_boundary, [8..23] status histogram
   const size_t CNT_BYTES = 256;
@@ -735,15 +760,17 @@ static int call_chunks_impl(hm_ctx* ctx, const hm_chunk* chunks, size_t n_chunks
     for (size_t d = 0; d <= dropped.size(); d++) {
       const size_t to = d < dropped.size() ? dropped[d] : n_unique;
       if (to > from)
-        CU(cudaMemcpyAsync(recs + n_final, rec_buf.as<hm_site_record>() + from, (to - from) * sizeof(hm_site_record),
-                           cudaMemcpyDeviceToHost, ctx->copy_stream)); // the kernels are done: the main stream was synchronised above
+        ctx->deferred.push_back(hm_ctx::PendingCopy{recs + n_final, rec_buf.as<hm_site_record>() + from, (to - from) * sizeof(hm_site_record)});
       n_final += to - from;
       from = to + 1;
     }
-    CU(cudaEventRecord(ctx->ev_copy_done[parity], ctx->copy_stream));
-    ctx->copy_pending = true;
+    ctx->deferred_parity = parity;
     ctx->rec_parity ^= 1;
-    if (!async || !direct) { CU(cudaStreamSynchronize(ctx->copy_stream)); ctx->copy_pending = false; }
+    if (!async || !direct) { // the kernels are done (the main stream was synchronised above): copy now
+      if ((rc = flush_deferred(ctx, false))) return rc;
+      CU(cudaStreamSynchronize(ctx->copy_stream));
+      ctx->copy_pending = false;
+    }
   }
   t_collect(ctx);
   // chrom2tsbs_log (caller.py:625-641) from the status tallies
