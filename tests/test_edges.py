@@ -66,3 +66,19 @@ def test_worker_mirror_matches_reference(ctx, tmp_path, monkeypatch, name):
     got = [[int(i), int(j)] + [int(v) for v in e2c[(i, j)]] for (i, j) in edge_lst]
     assert got == _expected(name)
     assert all(isinstance(v, np.ndarray) and v.dtype == np.float64 for v in e2c.values())
+
+
+@pytest.mark.gpu
+def test_cuda_matches_oracle_2mb(ctx):
+    """a contig-sized run: 4 000 reads, 2 000 hetSNPs, default `himut phase` thresholds"""
+    from himut_b200 import synth
+    d = synth.generate(2_000_000, seed=57)
+    het = d.germ["gt"] < 2
+    hpos = d.germ["pos"][het].astype(np.int32)
+    href = d.germ["ref"][het].astype(np.uint8)
+    ctx.upload(d.batch)
+    ctx.phase_edges_begin(hpos, href, 128)
+    assert ctx.phase_edges_add(20, 20) == 0
+    got = ctx.phase_edges_end()
+    exp, need = oracle.phase_edges(d.batch, hpos, href, 128, 20, 20)
+    assert need == 0 and np.array_equal(got, exp) and int(got.sum()) > 100_000
