@@ -159,3 +159,22 @@ def test_async_record_copy_equals_synchronous(ctx):
     ctx.records_wait()
     ok, why = parity.records_equal(rec, sync[2][0])
     assert ok, why
+
+
+def test_async_with_dropped_boundary_records(ctx):
+    """overlapping regions: records a previous chunk claimed are left out by the copy itself, also when it is deferred"""
+    c = cases.build_case("call_adversarial_b")
+    ctx.set_params(c["params"])
+    ctx.set_site_sets(c["common"], c["pon"])
+    ctx.upload(c["batch"])
+    srec, slog = ctx.call_chunks(c["chunk_table"])
+    o_rec, o_log = oracle.call_chunks(c["params"], c["batch"], c["chunk_table"], c["common"], c["pon"], c["phase"])
+    ok, why = parity.records_equal(srec, o_rec)
+    assert ok, why
+    a = ctx.call_chunks(c["chunk_table"], view=True, wait=False)
+    b = ctx.call_chunks(c["chunk_table"], view=True, wait=False)
+    ctx.records_wait()
+    for rec, log in (a, b):
+        ok, why = parity.records_equal(rec, srec)
+        assert ok, why
+        assert list(log) == list(slog)

@@ -78,3 +78,40 @@ def test_normcounts_additive_over_chunks(ctx):
     assert np.array_equal(whole[0], sum(x[0] for x in parts))
     assert np.array_equal(whole[1], sum(x[1] for x in parts))
     assert list(whole[2][1:]) == list(sum(x[2] for x in parts)[1:])  # num_ccs is a distinct count, not additive
+
+
+@pytest.mark.parametrize("over", [dict(min_gq=60), dict(min_gq=99), dict(min_gq=0, germline_snv_prior=0.3),
+                                  dict(min_bq=1, min_gq=35, md_threshold=25), dict(min_ref_count=40)])
+def test_normcounts_certification_edges(ctx, over):
+    """parameters that push many pure positions out of the certified domain (or make every one fail a gate):
+    whatever the fast pass cannot decide must come back through the exact pass with the oracle's answer"""
+    d = synth.generate(200_000, seed=33)
+    p = gtmodel.make_params(**cases.call_args(**over))
+    chunks = d.batch.chunk_table(cases.chunkloci(0, 200_000))
+    ctx.set_params(p)
+    ctx.set_site_sets()
+    ctx.upload(d.batch)
+    g = ctx.normcounts_chunks(d.ref, chunks)
+    o = oracle.normcounts_chunks(p, d.batch, d.ref, chunks)
+    assert np.array_equal(g[0], o[0]) and np.array_equal(g[1], o[1]) and list(g[2]) == list(o[2]) and g[3] == o[3]
+
+
+def test_normcounts_deep_pileup(ctx):
+    """400x: more than 255 reads per 2048-position tile (the packed 8-bit tallies of the fast pass would overflow:
+    the whole tile goes to the exact pass) and more than 64 reads per position (slots beyond the entry table)"""
+    d = synth.generate(30_000, seed=34, depth=400.0)
+    p = gtmodel.make_params(**cases.call_args(md_threshold=1000))
+    chunks = d.batch.chunk_table([(0, 12_345), (12_345, 30_000)])
+    ctx.set_params(p)
+    ctx.set_site_sets()
+    ctx.upload(d.batch)
+    g = ctx.normcounts_chunks(d.ref, chunks)
+    assert ctx.last_norm_exact_sites() > 25_000
+    o = oracle.normcounts_chunks(p, d.batch, d.ref, chunks)
+    assert np.array_equal(g[0], o[0]) and np.array_equal(g[1], o[1]) and list(g[2]) == list(o[2]) and g[3] == o[3]
+    # the same data through `call`: deep pileups there too
+    rec, log = ctx.call_chunks(chunks)
+    o_rec, o_log = oracle.call_chunks(p, d.batch, chunks)
+    ok, why = parity.records_equal(rec, o_rec)
+    assert ok, why
+    assert list(log) == list(o_log)
