@@ -530,6 +530,21 @@ static int call_chunks_impl(hm_ctx* ctx, const hm_chunk* chunks, size_t n_chunks
   std::vector<uint64_t> pair_off;
   if ((rc = upload_chunks(ctx, chunks, n_chunks, pair_off))) return rc;
   const uint64_t n_pairs = pair_off.back();
+  // chunk geometry for the som_seen carry: a position can only have been claimed by an earlier
+  // chunk if it lies at or below the largest chunk end seen so far, and only needs remembering if
+  // a later chunk starts at or below it.  With the reference's own chunking that is just the
+  // shared boundary position, so very few records ever reach the host replay.
+  std::vector<int32_t> geom(2 * n_chunks + 2);
+  int32_t* prev_max_end = geom.data();
+  int32_t* next_min_start = geom.data() + n_chunks;
+  {
+    int32_t m = INT32_MIN;
+    for (size_t i = 0; i < n_chunks; i++) { prev_max_end[i] = m; m = std::max(m, chunks[i].end); }
+    m = INT32_MAX;
+    for (size_t i = n_chunks; i-- > 0;) { next_min_start[i] = m; m = std::min(m, chunks[i].start); }
+  }
+
+  if (n_chunks && (rc = upload(ctx, ctx->b_geom, geom.data(), 2 * n_chunks))) return rc;
   if ((rc = launch_read_scan(ctx))) return rc;
   if ((rc = flush_deferred(ctx, true))) return rc;
 
@@ -549,8 +564,20 @@ static int call_chunks_impl(hm_ctx* ctx, const hm_chunk* chunks, size_t n_chunks
     const int64_t span = (int64_t)chunks[i].end - (int64_t)chunks[i].start;
     while (pos_bits < 32 && span >= (1ll << pos_bits)) pos_bits++;
   }
+  int end_bit = pos_bits + 4;
+  for (size_t c = n_chunks; c > 0; c >>= 1) end_bit++;
+  end_bit = std::min(end_bit, 64);
   for (int attempt = 0; attempt < 2 && n_pairs; attempt++) {
     CU(ctx->b_keys.ensure(key_cap * 8));
+    { // everything the sort needs that does not depend on the candidate count: done while the device works
+      CU(ctx->b_keys_sorted.ensure(key_cap * 8));
+      size_t tmp_sort = 0, tmp_uniq = 0;
+      unsigned long long* k_in = ctx->b_keys.as<unsigned long long>();
+      unsigned long long* k_sorted = ctx->b_keys_sorted.as<unsigned long long>();
+      CU(cub::DeviceRadixSort::SortKeys(nullptr, tmp_sort, k_in, k_sorted, (int64_t)key_cap, 0, end_bit, ctx->stream));
+      CU(cub::DeviceSelect::Unique(nullptr, tmp_uniq, k_sorted, k_in, ctx->b_counters.as<unsigned long long>() + 1, (int64_t)key_cap, ctx->stream));
+      CU(ctx->b_cub.ensure(std::max(tmp_sort, tmp_uniq)));
+    }
     CU(cudaMemsetAsync(ctx->b_counters.p, 0, CNT_BYTES, ctx->stream));
     CU(cudaMemsetAsync(ctx->b_qseen.p, 0, (size_t)ctx->max_qname_id + 1, ctx->stream));
     const unsigned blocks = (unsigned)((n_pairs * 32 + 255) / 256);
@@ -571,20 +598,6 @@ static int call_chunks_impl(hm_ctx* ctx, const hm_chunk* chunks, size_t n_chunks
   }
   const unsigned long long n_keys = h_cnt[0];
 
-  // chunk geometry for the som_seen carry: a position can only have been claimed by an earlier
-  // chunk if it lies at or below the largest chunk end seen so far, and only needs remembering if
-  // a later chunk starts at or below it.  With the reference's own chunking that is just the
-  // shared boundary position, so very few records ever reach the host replay.
-  std::vector<int32_t> geom(2 * n_chunks + 2);
-  int32_t* prev_max_end = geom.data();
-  int32_t* next_min_start = geom.data() + n_chunks;
-  {
-    int32_t m = INT32_MIN;
-    for (size_t i = 0; i < n_chunks; i++) { prev_max_end[i] = m; m = std::max(m, chunks[i].end); }
-    m = INT32_MAX;
-    for (size_t i = n_chunks; i-- > 0;) { next_min_start[i] = m; m = std::min(m, chunks[i].start); }
-  }
-
   size_t n_unique = 0, n_boundary = 0;
   const int parity = ctx->rec_parity;
   DevBuf& rec_buf = parity ? ctx->b_records_alt : ctx->b_records;
@@ -597,23 +610,15 @@ static int call_chunks_impl(hm_ctx* ctx, const hm_chunk* chunks, size_t n_chunks
   if (n_pairs) {
     if (n_keys) {
       // sort + unique of the candidate keys (library plumbing: cub), then the site kernels
-      CU(ctx->b_keys_sorted.ensure(n_keys * 8));
-      size_t tmp_sort = 0, tmp_uniq = 0;
-      int end_bit = pos_bits + 4;
-      for (size_t c = n_chunks; c > 0; c >>= 1) end_bit++;
-      end_bit = std::min(end_bit, 64);
+      size_t tmp_sort = ctx->b_cub.cap, tmp_uniq = ctx->b_cub.cap; // sized for key_cap >= n_keys above
       unsigned long long* k_in = ctx->b_keys.as<unsigned long long>();
       unsigned long long* k_sorted = ctx->b_keys_sorted.as<unsigned long long>();
-      CU(cub::DeviceRadixSort::SortKeys(nullptr, tmp_sort, k_in, k_sorted, (int64_t)n_keys, 0, end_bit, ctx->stream));
-      CU(cub::DeviceSelect::Unique(nullptr, tmp_uniq, k_sorted, k_in, d_cnt + 1, (int64_t)n_keys, ctx->stream));
-      CU(ctx->b_cub.ensure(std::max(tmp_sort, tmp_uniq)));
       t_begin(ctx, "cub_sort_unique_keys");
       CU(cub::DeviceRadixSort::SortKeys(ctx->b_cub.p, tmp_sort, k_in, k_sorted, (int64_t)n_keys, 0, end_bit, ctx->stream));
       CU(cub::DeviceSelect::Unique(ctx->b_cub.p, tmp_uniq, k_sorted, k_in, d_cnt + 1, (int64_t)n_keys, ctx->stream));
       k_expand_keys<<<(unsigned)((n_keys + 255) / 256), 256, 0, ctx->stream>>>(k_in, d_cnt + 1, ctx->b_chunks.as<hm_chunk>(), pos_bits);
       t_end(ctx);
       k_publish<<<1, 32, 0, ctx->stream>>>(reinterpret_cast<const uint32_t*>(d_cnt + 1), reinterpret_cast<uint32_t*>(ctx->h_cnt_pin + 1), 2);
-      if ((rc = upload(ctx, ctx->b_geom, geom.data(), 2 * n_chunks))) return rc;
       lap(2); // sort / unique launches
       CU(cudaStreamSynchronize(ctx->stream));
       h_cnt[1] = ctx->h_cnt_pin[1];

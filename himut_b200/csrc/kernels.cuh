@@ -358,30 +358,42 @@ __global__ void __launch_bounds__(256) k_candidates(DevBatch b, DevParams p, Dev
   const int32_t* mm = b.mm_pos + o0;
   const uint32_t nmm = (uint32_t)b.n_mm[r];
   const int w = p.mismatch_window;
+  uint32_t mm_seen = 0; // entries of the mismatch list that belong to ops before this batch
   for (uint32_t base = 0; base < nops; base += 32) {
     const uint32_t k = base + lane;
     bool emit = false;
     unsigned long long key = 0;
+    uint32_t op = 0, v = 0;
+    bool is_mm = false;
     if (k < nops) {
-      const uint32_t op = __ldg(b.ops + o0 + k);
-      const uint32_t v = op >> 2;
-      if ((op & 3u) == HM_OP_SUB && (v & 7u) != HM_BASE_N) {
-        const int32_t tpos = tstart + (int32_t)b.op_t[o0 + k] + 1;
-        const int32_t qpos = (int32_t)b.op_q[o0 + k];
-        if (ch.start <= tpos && tpos <= ch.end && !((double)qpos < trim_s) && !((double)qpos > trim_e)) {
-          // bamlib.get_mismatch_range
-          const int qs = qpos - w, qe = qpos + w;
-          int u, d;
-          if (qs < 0) { u = w + qs; d = w + (-qs); }
-          else if (qe > qlen) { u = w + (qe - qlen); d = qlen - qpos; }
-          else { u = w; d = w; }
-          const int cnt = (int)upper_bound_dev(mm, nmm, tpos + d) - (int)lower_bound_dev(mm, nmm, tpos - u) - 1;
-          if (!(cnt > p.max_mismatch_count)) {
-            emit = true;
-            // sort key: chunk | position inside the chunk | ref | alt, packed so the radix sort sees as few bits as
-            // possible; k_expand_keys turns it into chunk << 36 | tpos << 4 | ref << 2 | alt afterwards
-            key = ((unsigned long long)c << (pos_bits + 4)) | ((unsigned long long)(uint32_t)(tpos - ch.start) << 4) | ((v & 3u) << 2) | ((v >> 3) & 3u);
-          }
+      op = __ldg(b.ops + o0 + k);
+      v = op >> 2;
+      const uint32_t kind = op & 3u;
+      is_mm = (kind == HM_OP_SUB && (v & 7u) != HM_BASE_N) || kind == HM_OP_INS || kind == HM_OP_DEL; // cs2subindel's list
+    }
+    const uint32_t mbal = __ballot_sync(HM_FULL, is_mm);
+    const int rank = (int)(mm_seen + __popc(mbal & ((1u << lane) - 1u))); // this op's own entry in the mismatch list
+    mm_seen += __popc(mbal);
+    if (k < nops && (op & 3u) == HM_OP_SUB && (v & 7u) != HM_BASE_N) {
+      const int32_t tpos = tstart + (int32_t)b.op_t[o0 + k] + 1;
+      const int32_t qpos = (int32_t)b.op_q[o0 + k];
+      if (ch.start <= tpos && tpos <= ch.end && !((double)qpos < trim_s) && !((double)qpos > trim_e)) {
+        // bamlib.get_mismatch_range
+        const int qs = qpos - w, qe = qpos + w;
+        int u, d;
+        if (qs < 0) { u = w + qs; d = w + (-qs); }
+        else if (qe > qlen) { u = w + (qe - qlen); d = qlen - qpos; }
+        else { u = w; d = w; }
+        // mismatches with tpos - u <= x <= tpos + d, minus this one: walk outwards from the op's own entry
+        // (bisect_right - bisect_left - 1, bamlib.py:266-282; the list is sorted and mm[rank] == tpos)
+        int cnt = 0;
+        for (int j = rank + 1; j < (int)nmm && __ldg(mm + j) <= tpos + d; j++) cnt++;
+        for (int j = rank - 1; j >= 0 && __ldg(mm + j) >= tpos - u; j--) cnt++;
+        if (!(cnt > p.max_mismatch_count)) {
+          emit = true;
+          // sort key: chunk | position inside the chunk | ref | alt, packed so the radix sort sees as few bits as
+          // possible; k_expand_keys turns it into chunk << 36 | tpos << 4 | ref << 2 | alt afterwards
+          key = ((unsigned long long)c << (pos_bits + 4)) | ((unsigned long long)(uint32_t)(tpos - ch.start) << 4) | ((v & 3u) << 2) | ((v >> 3) & 3u);
         }
       }
     }
