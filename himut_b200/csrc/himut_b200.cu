@@ -194,8 +194,9 @@ void make_norm_cert(hm_ctx* ctx) {
   c.enabled = 1;
 }
 
-// The record copies of an asynchronous call are enqueued late, behind the *next* call's k_read_scan (the one
-// HBM-bound kernel of the path), so they overlap its latency-bound kernels instead; without a next call,
+// The record copies of an asynchronous call are enqueued late, behind the *next* call's sort (past k_read_scan, the
+// one HBM-bound kernel of the path, and past the latency-bound candidate / sort kernels a concurrent copy slows most),
+// so they overlap its site kernels; without a next call (or when it has no candidates),
 // hm_records_wait enqueues them.  after_main: make the copy stream wait for what the main stream has queued so far.
 int flush_deferred(hm_ctx* ctx, bool after_main) {
   if (ctx->deferred.empty()) return HM_OK;
@@ -546,7 +547,6 @@ static int call_chunks_impl(hm_ctx* ctx, const hm_chunk* chunks, size_t n_chunks
 
   if (n_chunks && (rc = upload(ctx, ctx->b_geom, geom.data(), 2 * n_chunks))) return rc;
   if ((rc = launch_read_scan(ctx))) return rc;
-  if ((rc = flush_deferred(ctx, true))) return rc;
 
   // counters (u64): [0] n_keys, [1] n_unique, [2] num_ccs, [3] error flag, [4] n_boundary, [8..23] status histogram
   const size_t CNT_BYTES = 256;
@@ -618,6 +618,7 @@ static int call_chunks_impl(hm_ctx* ctx, const hm_chunk* chunks, size_t n_chunks
       CU(cub::DeviceSelect::Unique(ctx->b_cub.p, tmp_uniq, k_sorted, k_in, d_cnt + 1, (int64_t)n_keys, ctx->stream));
       k_expand_keys<<<(unsigned)((n_keys + 255) / 256), 256, 0, ctx->stream>>>(k_in, d_cnt + 1, ctx->b_chunks.as<hm_chunk>(), pos_bits);
       t_end(ctx);
+      if ((rc = flush_deferred(ctx, true))) return rc; // the previous call's records start moving behind the sort
       k_publish<<<1, 32, 0, ctx->stream>>>(reinterpret_cast<const uint32_t*>(d_cnt + 1), reinterpret_cast<uint32_t*>(ctx->h_cnt_pin + 1), 2);
       lap(2); // sort / unique launches
       CU(cudaStreamSynchronize(ctx->stream));
@@ -751,6 +752,7 @@ static int call_chunks_impl(hm_ctx* ctx, const hm_chunk* chunks, size_t n_chunks
     }
   }
   // the records, minus the dropped ones (ascending indices): one copy per run between two dropped records
+  if ((rc = flush_deferred(ctx, false))) return rc; // an earlier call's copies, if this call had no sort to put them behind
   size_t n_final = 0;
   if (n_unique && have_all) {
     size_t from = 0;

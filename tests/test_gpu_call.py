@@ -178,3 +178,24 @@ def test_async_with_dropped_boundary_records(ctx):
         ok, why = parity.records_equal(rec, srec)
         assert ok, why
         assert list(log) == list(slog)
+
+
+def test_async_followed_by_a_call_without_candidates(ctx):
+    """the deferred record copy of an asynchronous call must not get lost when the next call has nothing to sort"""
+    from himut_b200 import gtmodel, synth
+    d = synth.generate(200_000, seed=72)
+    ctx.set_params(gtmodel.make_params(**gtmodel.DEFAULT_CALL_ARGS))
+    ctx.set_site_sets()
+    ctx.upload(d.batch)
+    full = d.batch.chunk_table(cases.chunkloci(0, 200_000))
+    srec, slog = ctx.call_chunks(full)
+    empty = d.batch.chunk_table([(5, 6)])          # a one-base window: no candidate
+    a = ctx.call_chunks(full, view=True, wait=False)
+    b = ctx.call_chunks(empty, view=True, wait=False)
+    c = ctx.call_chunks(full, view=True, wait=False)
+    ctx.records_wait()
+    assert b[0].size == 0
+    for rec, log in (a, c):
+        ok, why = parity.records_equal(rec, srec)
+        assert ok, why
+        assert list(log) == list(slog)
