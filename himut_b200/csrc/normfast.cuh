@@ -221,7 +221,7 @@ __device__ __forceinline__ void fast_fill_slot(const DevBatch& b, const DevParam
   const int32_t trim_s = (int32_t)floor(__dmul_rn(p.min_trim, (double)qlen));
   const int32_t trim_e = (int32_t)ceil(__dmul_rn(__dsub_rn(1.0, p.min_trim), (double)qlen));
   const int32_t W = HF_TW; // bits beyond the chunk's end land on positions the consumers never count
-  int32_t cur_delta = INT32_MIN, q_lo = 0, q_hi = 0;
+  int32_t cur_delta = INT32_MIN, q_lo = 0, q_hi = 0, last_bgroup = -1;
   bool have_q = false;
   // a matched base is not callable when a mismatch lies within the window of its block (normcounts.py:82-94).
   // For every block but those starting within `w` of a read end the window is (w, w): one range per mismatch,
@@ -244,7 +244,12 @@ __device__ __forceinline__ void fast_fill_slot(const DevBatch& b, const DevParam
             else {
               S->seg_start[nseg] = lo_p; S->seg_delta[nseg] = delta;
               if (nseg == 0) delta0 = delta;
-              else fmask_set(S->mask, 0, lo_p, (lo_p + 3) & ~3, &sp_touch); // rest of the 4-position group after an indel
+              else if (lo_p & 3) {
+                // a run that starts inside a 4-position group: the consumer blends the two offsets (one boundary per
+                // group); a second boundary in the same group sends the rest of the group to the exact pass
+                if (last_bgroup == (lo_p >> 2)) fmask_set(S->mask, 0, lo_p, (lo_p + 3) & ~3, &sp_touch);
+                last_bgroup = lo_p >> 2;
+              }
               nseg++; cur_delta = delta;
             }
           }
@@ -503,15 +508,28 @@ k_norm_fast(DevBatch b, DevParams p, NormCert cert, const hm_chunk* chunks, uint
         uint32_t good = cm & ~sp;
         int delta = (int)hd.w;
         const uint32_t nseg = fl >> 16;
-        for (uint32_t s = 1; s < nseg; s++)               // uniform trip count, almost always zero
-          if (p0 >= S->seg_start[s]) delta = S->seg_delta[s];
+        int delta2 = 0, b2 = 4;                           // a run that starts inside this group: its offset, its first position
+        for (uint32_t s = 1; s < nseg; s++) {             // uniform trip count, almost always zero
+          const int st = S->seg_start[s];
+          if (p0 >= st) delta = S->seg_delta[s];
+          else if (st <= p0 + 3 && b2 == 4) { b2 = st - p0; delta2 = S->seg_delta[s]; }
+        }
         // query position relative to the staged origin, + 64; clamped so special / uncovered groups stay inside the buffers
         const uint32_t qq = min((uint32_t)(p0 + delta - (int)hd.z + 64), (uint32_t)(HF_BQ_BUF - HF_PAD - 8 + 64));
         const uint32_t* bw = reinterpret_cast<const uint32_t*>(S->bq);
         const uint32_t bi = qq - 48u;                     // byte index into bq[] (HF_PAD = 16 in front)
-        const uint32_t w = __funnelshift_r(bw[bi >> 2], bw[(bi >> 2) + 1], (bi & 3u) * 8u);
+        uint32_t w = __funnelshift_r(bw[bi >> 2], bw[(bi >> 2) + 1], (bi & 3u) * 8u);
         const uint32_t* sw = reinterpret_cast<const uint32_t*>(S->seq);
-        const uint32_t s8 = __funnelshift_r(sw[qq >> 4], sw[(qq >> 4) + 1], (qq & 15u) * 2u) & 0xffu;
+        uint32_t s8 = __funnelshift_r(sw[qq >> 4], sw[(qq >> 4) + 1], (qq & 15u) * 2u) & 0xffu;
+        if (b2 < 4) { // positions b2.. of the group follow an indel: take them with the next run's offset
+          const uint32_t qq2 = min((uint32_t)(p0 + delta2 - (int)hd.z + 64), (uint32_t)(HF_BQ_BUF - HF_PAD - 8 + 64));
+          const uint32_t bj = qq2 - 48u;
+          const uint32_t w2 = __funnelshift_r(bw[bj >> 2], bw[(bj >> 2) + 1], (bj & 3u) * 8u);
+          const uint32_t t8 = __funnelshift_r(sw[qq2 >> 4], sw[(qq2 >> 4) + 1], (qq2 & 15u) * 2u) & 0xffu;
+          const uint32_t bm = 0xffffffffu << (8 * b2), sm = (0xffu << (2 * b2)) & 0xffu;
+          w = (w & ~bm) | (w2 & bm);
+          s8 = (s8 & ~sm) | (t8 & sm);
+        }
         const uint32_t mis = s8 ^ ref8;
         if (mis) { // special / uncovered / dead positions in the group, or a read base that differs from the FASTA under a cs match
           const uint32_t m2 = (mis | (mis >> 1)) & 0x55u;
