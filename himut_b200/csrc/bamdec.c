@@ -22,6 +22,7 @@
 #include <zlib.h>
 
 #include "../../include/himut_io.h"
+#include "inflate_fast.h"
 
 typedef struct {
   char* name;
@@ -152,6 +153,7 @@ typedef struct {
   size_t next;
   pthread_mutex_t mu;
   int error;
+  int zlib_only; /* HIMUT_B200_ZLIB_INFLATE=1: A/B against the library decoder */
 } inflate_job_t;
 
 static void* inflate_worker(void* arg) {
@@ -170,12 +172,20 @@ static void* inflate_worker(void* arg) {
       const uint8_t* src = j->comp + b->coff;
       uint16_t xlen = (uint16_t)(src[10] | (src[11] << 8));
       if (b->usize == 0) continue;
+      const uint8_t* payload = src + 12 + xlen;
+      const size_t payload_len = b->csize - 12 - xlen - 8;
+      const uint32_t want_crc = rd32(src + b->csize - 8);
+      uint8_t* dst = j->out + b->uoff;
+      /* own decoder first (inflate_fast.h); zlib when it declines or the CRC disagrees */
+      if (!j->zlib_only && hm_inflate_raw(payload, payload_len, dst, b->usize) == 0 &&
+          (uint32_t)crc32(crc32(0L, Z_NULL, 0), dst, b->usize) == want_crc)
+        continue;
       inflateReset(&zs);
-      zs.next_in = (Bytef*)(src + 12 + xlen);
-      zs.avail_in = b->csize - 12 - xlen - 8;
-      zs.next_out = j->out + b->uoff;
+      zs.next_in = (Bytef*)payload;
+      zs.avail_in = (uInt)payload_len;
+      zs.next_out = dst;
       zs.avail_out = b->usize;
-      if (inflate(&zs, Z_FINISH) != Z_STREAM_END) { j->error = 1; break; }
+      if (inflate(&zs, Z_FINISH) != Z_STREAM_END || (uint32_t)crc32(crc32(0L, Z_NULL, 0), dst, b->usize) != want_crc) { j->error = 1; break; }
     }
     if (j->error) break;
   }
@@ -245,6 +255,7 @@ static int stream_fill(stream_t* s) {
     inflate_job_t job;
     memset(&job, 0, sizeof(job));
     job.comp = comp; job.blocks = blocks; job.n_blocks = nb; job.out = s->buf + s->len;
+    job.zlib_only = getenv("HIMUT_B200_ZLIB_INFLATE") != NULL;
     pthread_mutex_init(&job.mu, NULL);
     int nt = s->threads < 1 ? 1 : (s->threads > 64 ? 64 : s->threads);
     if ((size_t)nt > (nb + 15) / 16) nt = (int)((nb + 15) / 16);
@@ -1034,4 +1045,7 @@ int hm_bq_compact_build(const hm_read_batch* b, int threads, uint8_t* mask, uint
   return HM_OK;
 }
 void hm_bq_compact_free(uint8_t* exc) { free(exc); }
+
+/* test hook: the raw DEFLATE decoder of inflate_fast.h on one stream (0 = ok) */
+int hm_inflate_raw_test(const uint8_t* in, size_t in_len, uint8_t* out, size_t out_len) { return hm_inflate_raw(in, in_len, out, out_len); }
 

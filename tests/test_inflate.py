@@ -1,0 +1,85 @@
+"""inflate_fast.h (the BGZF block decoder of the native BAM reader) against zlib: stored / fixed / dynamic blocks,
+long codes (subtables), overlapping and far matches, tiny and empty streams, truncated and corrupted input."""
+import ctypes as C
+import os
+import random
+import zlib
+
+import numpy as np
+import pytest
+
+from himut_b200 import bamdec
+
+
+def _inflate(comp, n):
+    lib = C.CDLL(bamdec.lib_path())
+    lib.hm_inflate_raw_test.argtypes = [C.c_char_p, C.c_size_t, C.c_void_p, C.c_size_t]
+    out = np.zeros(max(n, 1), np.uint8)
+    rc = lib.hm_inflate_raw_test(comp, len(comp), out.ctypes.data_as(C.c_void_p), n)
+    return rc, out[:n].tobytes()
+
+
+def _raw_deflate(data, level, strategy=zlib.Z_DEFAULT_STRATEGY):
+    c = zlib.compressobj(level, zlib.DEFLATED, -15, 9, strategy)
+    return c.compress(data) + c.flush()
+
+
+def _payloads():
+    rnd = random.Random(7)
+    yield b""
+    yield b"a"
+    yield b"abc" * 5
+    yield bytes(1000)                                        # dist-1 runs
+    yield bytes(rnd.randrange(256) for _ in range(70_000))   # incompressible: stored blocks / literal-only trees
+    yield bytes(rnd.choice(b"ACGT") for _ in range(65_000))  # 4-symbol alphabet: short codes
+    q = bytearray()
+    while len(q) < 64_000:                                    # quality-string like: long runs with exceptions
+        q += bytes([93]) * rnd.randrange(1, 60) + bytes([rnd.randrange(1, 93)])
+    yield bytes(q[:64_000])
+    words = [bytes(rnd.randrange(256) for _ in range(rnd.randrange(3, 40))) for _ in range(300)]
+    yield b"".join(rnd.choice(words) for _ in range(4000))[:65_280]   # many distinct lengths / distances
+    skew = bytes(min(255, int(rnd.expovariate(0.03))) for _ in range(65_000))  # skewed alphabet: codes longer than 10 bits
+    yield skew
+
+
+@pytest.mark.parametrize("level", [0, 1, 6, 9])
+@pytest.mark.parametrize("strategy", [zlib.Z_DEFAULT_STRATEGY, zlib.Z_FIXED, zlib.Z_HUFFMAN_ONLY, zlib.Z_RLE])
+def test_matches_zlib(level, strategy):
+    for data in _payloads():
+        comp = _raw_deflate(data, level, strategy)
+        assert zlib.decompress(comp, -15) == data
+        rc, got = _inflate(comp, len(data))
+        assert rc == 0 and got == data, (level, strategy, len(data))
+
+
+def test_rejects_bad_input():
+    data = bytes(random.Random(3).choice(b"ACGTN") for _ in range(20_000))
+    comp = _raw_deflate(data, 6)
+    assert _inflate(comp, len(data))[0] == 0
+    assert _inflate(comp, len(data) - 1)[0] != 0         # output size is part of the contract
+    assert _inflate(comp, len(data) + 1)[0] != 0
+    assert _inflate(comp[: len(comp) // 2], len(data))[0] != 0   # truncated
+    rnd = random.Random(4)
+    for _ in range(200):                                  # corrupted: must not crash; a wrong answer is caught by the CRC
+        bad = bytearray(comp)
+        bad[rnd.randrange(len(bad))] ^= 1 << rnd.randrange(8)
+        rc, got = _inflate(bytes(bad), len(data))
+        assert rc != 0 or len(got) == len(data)
+
+
+def test_bam_blocks_decode_identically_with_both_decoders(tmp_path, monkeypatch):
+    from himut_b200 import synth
+    import cases
+    d = synth.generate(400_000, seed=81)
+    digests = []
+    for level in (1, 6):
+        path = str(tmp_path / ("l%d.bam" % level))
+        bamdec.write_batch_bam(path, "chr1", 400_000, d.batch, level=level)
+        for zl in (False, True):
+            if zl:
+                monkeypatch.setenv("HIMUT_B200_ZLIB_INFLATE", "1")
+            else:
+                monkeypatch.delenv("HIMUT_B200_ZLIB_INFLATE", raising=False)
+            nb = bamdec.NativeBam(path, threads=2)
+            digests.append(cases.batch_digest(nb.read_batch("chr1", 0, 400_000)))
+    assert len(set(digests)) == 1 and digests[0] == cases.batch_digest(d.batch)
