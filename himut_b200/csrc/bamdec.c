@@ -19,6 +19,9 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <time.h>
 #include <zlib.h>
 
 #include "../../include/himut_io.h"
@@ -41,6 +44,8 @@ typedef struct {
 
 typedef struct hm_bam {
   FILE* f;
+  const uint8_t* map;  /* the whole file, mapped read-only (NULL: read() path) */
+  size_t map_len;
   char* path;
   char* header;
   int32_t n_ref;
@@ -145,6 +150,10 @@ static int read_block_header(FILE* f, uint64_t coff, blk_t* b) {
   return 0;
 }
 
+/* HIMUT_B200_DECODE_TIMING=1: seconds per phase of the last region decode, to stderr */
+static double g_phase[8];
+static inline double now_s(void) { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec; }
+
 typedef struct {
   const uint8_t* comp; /* compressed bytes of the span; blocks[i].coff is relative to it */
   const blk_t* blocks;
@@ -154,6 +163,7 @@ typedef struct {
   pthread_mutex_t mu;
   int error;
   int zlib_only; /* HIMUT_B200_ZLIB_INFLATE=1: A/B against the library decoder */
+  size_t grab;   /* blocks a worker takes at a time */
 } inflate_job_t;
 
 static void* inflate_worker(void* arg) {
@@ -164,10 +174,10 @@ static void* inflate_worker(void* arg) {
   for (;;) {
     pthread_mutex_lock(&j->mu);
     size_t i0 = j->next;
-    j->next += 16; /* a few blocks per grab */
+    j->next += j->grab; /* a few blocks per grab */
     pthread_mutex_unlock(&j->mu);
     if (i0 >= j->n_blocks) break;
-    for (size_t i = i0; i < i0 + 16 && i < j->n_blocks; i++) {
+    for (size_t i = i0; i < i0 + j->grab && i < j->n_blocks; i++) {
       const blk_t* b = &j->blocks[i];
       const uint8_t* src = j->comp + b->coff;
       uint16_t xlen = (uint16_t)(src[10] | (src[11] << 8));
@@ -208,15 +218,26 @@ static int stream_fill(stream_t* s) {
   if (s->eof) return 1;
   if (s->span == 0) s->span = 1u << 20;
   for (;;) {
-    uint8_t* comp = (uint8_t*)malloc(s->span);
-    if (!comp) return -1;
-    if (fseeko(s->b->f, (off_t)s->next_coff, SEEK_SET)) { free(comp); return -1; }
-    size_t got = fread(comp, 1, s->span, s->b->f);
-    if (got == 0) { free(comp); s->eof = 1; return 1; }
+    double t0 = now_s();
+    uint8_t* comp;
+    size_t got;
+    const int mapped = s->b->map != NULL;
+    if (mapped) { /* compressed bytes straight out of the page cache */
+      if (s->next_coff >= s->b->map_len) { s->eof = 1; return 1; }
+      comp = (uint8_t*)(s->b->map + s->next_coff);
+      got = s->b->map_len - s->next_coff < s->span ? s->b->map_len - s->next_coff : s->span;
+    } else {
+      comp = (uint8_t*)malloc(s->span);
+      if (!comp) return -1;
+      if (fseeko(s->b->f, (off_t)s->next_coff, SEEK_SET)) { free(comp); return -1; }
+      got = fread(comp, 1, s->span, s->b->f);
+      if (got == 0) { free(comp); s->eof = 1; return 1; }
+    }
+    g_phase[0] += now_s() - t0; t0 = now_s();
     size_t nb = 0, cap_b = got / 200 + 16, off = 0;
     uint64_t usum = 0;
     blk_t* blocks = (blk_t*)malloc(cap_b * sizeof(blk_t));
-    if (!blocks) { free(comp); return -1; }
+    if (!blocks) { if (!mapped) free(comp); return -1; }
     int bad = 0;
     while (off + 18 <= got) {
       const uint8_t* h = comp + off;
@@ -236,9 +257,9 @@ static int stream_fill(stream_t* s) {
       blocks[nb].coff = off; blocks[nb].csize = (uint32_t)csize; blocks[nb].usize = rd32(h + csize - 4); blocks[nb].uoff = usum;
       usum += blocks[nb].usize; off += csize; nb++;
     }
-    if (bad) { free(blocks); free(comp); return -1; }
+    if (bad) { free(blocks); if (!mapped) free(comp); return -1; }
     if (nb == 0) { /* a block larger than the span, or a truncated file */
-      free(blocks); free(comp);
+      free(blocks); if (!mapped) free(comp);
       if (got < s->span) return -1;
       s->span *= 2;
       continue;
@@ -249,22 +270,28 @@ static int stream_fill(stream_t* s) {
     if (s->len + usum > s->cap) {
       size_t nc = s->len + usum + (1 << 20);
       uint8_t* nbuf = (uint8_t*)realloc(s->buf, nc);
-      if (!nbuf) { free(blocks); free(comp); return -1; }
+      if (!nbuf) { free(blocks); if (!mapped) free(comp); return -1; }
       s->buf = nbuf; s->cap = nc;
     }
+    g_phase[1] += now_s() - t0; t0 = now_s();
     inflate_job_t job;
     memset(&job, 0, sizeof(job));
     job.comp = comp; job.blocks = blocks; job.n_blocks = nb; job.out = s->buf + s->len;
     job.zlib_only = getenv("HIMUT_B200_ZLIB_INFLATE") != NULL;
     pthread_mutex_init(&job.mu, NULL);
     int nt = s->threads < 1 ? 1 : (s->threads > 64 ? 64 : s->threads);
-    if ((size_t)nt > (nb + 15) / 16) nt = (int)((nb + 15) / 16);
+    job.grab = nb / ((size_t)nt * 8) + 1; /* about eight grabs per thread: balanced, few lock round trips */
+    if (job.grab > 16) job.grab = 16;
+    if ((size_t)nt > (nb + job.grab - 1) / job.grab) nt = (int)((nb + job.grab - 1) / job.grab);
     pthread_t th[64];
     for (int t = 1; t < nt; t++) pthread_create(&th[t], NULL, inflate_worker, &job);
     inflate_worker(&job);
     for (int t = 1; t < nt; t++) pthread_join(th[t], NULL);
     pthread_mutex_destroy(&job.mu);
-    free(comp); free(blocks);
+    g_phase[2] += now_s() - t0; t0 = now_s();
+    if (!mapped) free(comp);
+    free(blocks);
+    g_phase[3] += now_s() - t0;
     if (job.error) return -1;
     s->len += usum;
     s->next_coff += off;
@@ -323,6 +350,7 @@ static int load_bai(hm_bam* b) {
 
 void hm_bam_close(hm_bam* b) {
   if (!b) return;
+  if (b->map) munmap((void*)b->map, b->map_len);
   if (b->f) fclose(b->f);
   for (int32_t i = 0; i < b->n_ref; i++) { free(b->refs[i].name); free(b->refs[i].lin); }
   free(b->refs); free(b->header); free(b->path);
@@ -341,6 +369,13 @@ int hm_bam_open(const char* path, hm_bam** out) {
   b->path = strdup(path);
   b->f = fopen(path, "rb");
   if (!b->f) { hm_bam_close(b); return HM_ERR_ARG; }
+  {
+    struct stat st;
+    if (fstat(fileno(b->f), &st) == 0 && st.st_size > 0) {
+      void* m = mmap(NULL, (size_t)st.st_size, PROT_READ, MAP_PRIVATE, fileno(b->f), 0);
+      if (m != MAP_FAILED) { b->map = (const uint8_t*)m; b->map_len = (size_t)st.st_size; }
+    }
+  }
   stream_t s;
   memset(&s, 0, sizeof(s));
   s.b = b; s.threads = 1;
@@ -545,6 +580,11 @@ int hm_bam_read_batch(hm_bam* b, int rid, int32_t start, int32_t end, int thread
     stream_t s;
     memset(&s, 0, sizeof(s));
     s.b = b; s.threads = threads;
+    { /* first read sized for the region (about 8 compressed bytes per reference position at 30x), so that a large
+         region keeps every inflate thread busy from the start */
+      const uint64_t guess = (uint64_t)(end > start ? end - start : 0) * 8u;
+      s.span = guess < (1u << 20) ? (1u << 20) : (guess > (64u << 20) ? (64u << 20) : (size_t)guess);
+    }
     if (stream_seek(&s, voff) < 0) { free(s.buf); return fail(b, "cannot read BGZF blocks of %s (%ld)", b->path, 0); }
     rec_t* recs = NULL; size_t recs_cap = 0;
     int rc = HM_OK, done = 0;
@@ -559,6 +599,7 @@ int hm_bam_read_batch(hm_bam* b, int rid, int32_t start, int32_t end, int thread
         uint32_t bs0 = rd32(s.buf + s.pos);
         if (stream_need(&s, 4 + (size_t)bs0)) { rc = fail(b, "truncated BAM record in %s (%ld)", b->path, 0); break; }
       }
+      double tA = now_s();
       size_t nsel = 0, seg_ops = 0;
       const size_t first_read = n_reads;
       while (s.len - s.pos >= 4) {
@@ -638,6 +679,7 @@ int hm_bam_read_batch(hm_bam* b, int rid, int32_t start, int32_t end, int thread
         GROW(b->seq, b->cap_seq, n_seq + 16, uint8_t);
         GROW(b->bq, b->cap_bq, n_bq + 16, uint8_t);
         GROW(b->ops, b->cap_ops, n_ops + seg_ops + 4, uint32_t);
+        g_phase[4] += now_s() - tA; tA = now_s();
         /* phase B (parallel): bases, qualities, cs -> ops */
         decode_job_t job;
         memset(&job, 0, sizeof(job));
@@ -650,6 +692,7 @@ int hm_bam_read_batch(hm_bam* b, int rid, int32_t start, int32_t end, int thread
         decode_worker(&job);
         for (int t = 1; t < use; t++) pthread_join(th[t], NULL);
         pthread_mutex_destroy(&job.mu);
+        g_phase[5] += now_s() - tA; tA = now_s();
         /* serial tail: first error in file order, op compaction */
         for (size_t i = 0; i < nsel; i++) {
           rec_t* R = &recs[i];
@@ -661,6 +704,9 @@ int hm_bam_read_batch(hm_bam* b, int rid, int32_t start, int32_t end, int thread
         }
       }
     }
+    if (getenv("HIMUT_B200_DECODE_TIMING"))
+      fprintf(stderr, "[decode timing] read %.3f walk %.3f inflate %.3f free %.3f | scan+alloc %.3f decode %.3f s\n", g_phase[0], g_phase[1], g_phase[2], g_phase[3], g_phase[4], g_phase[5]);
+    memset(g_phase, 0, sizeof(g_phase));
     free(recs); free(s.buf);
     if (rc) return rc;
   }
