@@ -6,13 +6,25 @@ CLI, header, thresholds, natsort and writers stay the reference's own code.
 """
 
 
+def _scipy_compat():
+    """scipy >= 1.12 dropped scipy.stats.binom_test, which himut.phaselib imports at module level
+    (src/himut/phaselib.py:11); without it `himut.__main__` cannot be imported.  Same test, new name."""
+    import scipy.stats
+    if not hasattr(scipy.stats, "binom_test"):
+        def binom_test(x, n=None, p=0.5, alternative="two-sided"):
+            return scipy.stats.binomtest(int(x), int(n), p, alternative=alternative).pvalue
+        scipy.stats.binom_test = binom_test
+
+
 def install():
+    _scipy_compat()
+    import himut.bamlib
     import himut.caller
     import himut.normcounts
-    import himut.bamlib
+    import himut.phaselib
     import himut.reflib
 
-    from . import bamlib, caller, normcounts, reflib
+    from . import bamlib, caller, normcounts, phaselib, reflib
     himut.caller.get_somatic_substitutions = caller.get_somatic_substitutions
     himut.normcounts.get_callable_tricounts = normcounts.get_callable_tricounts
     himut.reflib.get_chrom_tricount = reflib.get_chrom_tricount  # reflib.py:42-52 starmap target
