@@ -19,6 +19,7 @@
 #include <vector>
 
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
 #include <cub/device/device_select.cuh>
 
 #include "kernels.cuh"
@@ -78,6 +79,8 @@ struct hm_ctx {
   cudaStream_t copy_stream = nullptr;       // record read-back runs here so it can overlap the next call's kernels
   cudaEvent_t ev_copy_done[2] = {nullptr, nullptr};
   DevBuf b_records_alt;                     // second record buffer: calls alternate
+  DevBuf b_compact[2], b_keep, b_kpos, b_bpos; // HM_OPT_OMIT_RESTATEMENTS: compacted records, keep flags, their scan
+  bool omit_restatements = false;
   int rec_parity = 0;
   bool copy_pending = false;
   struct PendingCopy { void* dst; const void* src; size_t bytes; };
@@ -295,6 +298,7 @@ void hm_destroy(hm_ctx* ctx) {
   for (cudaEvent_t e : ctx->ev_copy_done) if (e) cudaEventDestroy(e);
   if (ctx->ev_go) cudaEventDestroy(ctx->ev_go);
   ctx->b_records_alt.release();
+  ctx->b_compact[0].release(); ctx->b_compact[1].release(); ctx->b_keep.release(); ctx->b_kpos.release(); ctx->b_bpos.release();
   DevBuf* bufs[] = {&ctx->b_tstart, &ctx->b_tend, &ctx->b_qstart, &ctx->b_qlen, &ctx->b_mapq, &ctx->b_flags, &ctx->b_qname,
                     &ctx->b_seq_off, &ctx->b_bq_off, &ctx->b_op_off, &ctx->b_n_ops, &ctx->b_seq, &ctx->b_bq, &ctx->b_ops,
                     &ctx->b_op_t, &ctx->b_op_q, &ctx->b_mm, &ctx->b_bq_total, &ctx->b_n_match, &ctx->b_n_sub,
@@ -504,6 +508,12 @@ int hm_call_chunks_async(hm_ctx* ctx, const hm_chunk* chunks, size_t n_chunks, h
   return call_chunks_impl(ctx, chunks, n_chunks, out, cap, n_out, log, true);
 }
 
+int hm_set_option(hm_ctx* ctx, int option, int value) {
+  if (!ctx) return HM_ERR_ARG;
+  if (option == HM_OPT_OMIT_RESTATEMENTS) { ctx->omit_restatements = value != 0; return HM_OK; }
+  return fail(ctx, HM_ERR_ARG, "unknown option %d", option);
+}
+
 int hm_records_wait(hm_ctx* ctx) {
   if (!ctx) return HM_ERR_ARG;
   CU(cudaSetDevice(ctx->device));
@@ -551,7 +561,7 @@ static int call_chunks_impl(hm_ctx* ctx, const hm_chunk* chunks, size_t n_chunks
   // counters (u64): [0] n_keys, [1] n_unique, [2] num_ccs, [3] error flag, [4] n_boundary, [8..23] status histogram
   const size_t CNT_BYTES = 256;
   CU(ctx->b_counters.ensure(CNT_BYTES));
-  if (!ctx->h_cnt_pin) CU(cudaHostAlloc((void**)&ctx->h_cnt_pin, CNT_BYTES + HM_BOUNDARY_FIRST * (4 + sizeof(hm_site_record)), cudaHostAllocMapped));
+  if (!ctx->h_cnt_pin) CU(cudaHostAlloc((void**)&ctx->h_cnt_pin, CNT_BYTES + HM_BOUNDARY_FIRST * (8 + sizeof(hm_site_record)), cudaHostAllocMapped));
   CU(ctx->b_qseen.ensure((size_t)ctx->max_qname_id + 1));
   if (ctx->params.phase) CU(ctx->b_pair_hap.ensure(n_pairs + 16));
   unsigned long long h_cnt[32];
@@ -601,12 +611,14 @@ static int call_chunks_impl(hm_ctx* ctx, const hm_chunk* chunks, size_t n_chunks
   size_t n_unique = 0, n_boundary = 0;
   const int parity = ctx->rec_parity;
   DevBuf& rec_buf = parity ? ctx->b_records_alt : ctx->b_records;
+  const bool omit = ctx->omit_restatements;
   size_t HM_BOUNDARY_CAP = HM_BOUNDARY_CAP_DEFAULT;
   if (const char* e = getenv("HIMUT_B200_BOUNDARY_CAP")) HM_BOUNDARY_CAP = (size_t)std::max(0ll, atoll(e));
   hm_site_record* recs = nullptr; // where the device records land on the host
   bool direct = false;
   bool have_all = false; // the records are already on the host (fallback of the boundary replay)
-  std::vector<std::pair<uint32_t, hm_site_record>> border; // (index in key order, record) of the boundary records
+  struct Border { uint32_t idx, pos; hm_site_record rec; }; // index in key order, index among the kept records, the record
+  std::vector<Border> border;
   if (n_pairs) {
     if (n_keys) {
       // sort + unique of the candidate keys (library plumbing: cub), then the site kernels
@@ -663,6 +675,22 @@ static int call_chunks_impl(hm_ctx* ctx, const hm_chunk* chunks, size_t n_chunks
           ctx->b_pair_hap.as<uint8_t>(), ctx->b_geom.as<int32_t>(), ctx->b_geom.as<int32_t>() + n_chunks, k_in, d_cnt + 1, site_lo,
           site_n, entries, stride, rec_buf.as<hm_site_record>(), d_cnt + 8, ctx->b_bidx.as<uint32_t>(),
           ctx->b_brecs.as<hm_site_record>(), (uint32_t)HM_BOUNDARY_CAP, d_cnt + 4, reinterpret_cast<int*>(d_cnt + 3));
+      if (omit) { // records of germline restatements stay here: flags -> scan -> stable compaction
+        CU(ctx->b_keep.ensure(n_unique * 4 + 16)); CU(ctx->b_kpos.ensure(n_unique * 4 + 16));
+        CU(ctx->b_bpos.ensure(((size_t)HM_BOUNDARY_CAP + HM_BOUNDARY_FIRST) * 4));
+        CU(ctx->b_compact[parity].ensure(n_unique * sizeof(hm_site_record)));
+        const unsigned nb_ = (unsigned)((n_unique + 255) / 256);
+        k_keep_flags<<<nb_, 256, 0, ctx->stream>>>(rec_buf.as<hm_site_record>(), d_cnt + 1, ctx->b_keep.as<uint32_t>());
+        size_t tmp_scan = 0;
+        CU(cub::DeviceScan::ExclusiveSum(nullptr, tmp_scan, ctx->b_keep.as<uint32_t>(), ctx->b_kpos.as<uint32_t>(), (int64_t)n_unique, ctx->stream));
+        if (tmp_scan > ctx->b_cub.cap) CU(ctx->b_cub.ensure(tmp_scan)); // the sort has finished with it (same stream)
+        tmp_scan = ctx->b_cub.cap;
+        CU(cub::DeviceScan::ExclusiveSum(ctx->b_cub.p, tmp_scan, ctx->b_keep.as<uint32_t>(), ctx->b_kpos.as<uint32_t>(), (int64_t)n_unique, ctx->stream));
+        k_compact_records<<<nb_, 256, 0, ctx->stream>>>(rec_buf.as<hm_site_record>(), ctx->b_keep.as<uint32_t>(), ctx->b_kpos.as<uint32_t>(),
+                                                      d_cnt + 1, ctx->b_compact[parity].as<hm_site_record>());
+        k_gather_u32<<<8, 256, 0, ctx->stream>>>(ctx->b_kpos.as<uint32_t>(), ctx->b_bidx.as<uint32_t>(), d_cnt + 4, (uint32_t)HM_BOUNDARY_CAP,
+                                                ctx->b_bpos.as<uint32_t>());
+      }
       t_end(ctx);
       CU(cudaGetLastError());
     }
@@ -686,12 +714,14 @@ static int call_chunks_impl(hm_ctx* ctx, const hm_chunk* chunks, size_t n_chunks
     // looks at).  The big record copy follows the replay, so records a previous chunk already claimed are skipped
     // by the copy itself instead of being squeezed out of 20 MB on the host.
     uint32_t* h_bidx = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(ctx->h_cnt_pin) + CNT_BYTES);
-    hm_site_record* h_brecs = reinterpret_cast<hm_site_record*>(h_bidx + HM_BOUNDARY_FIRST);
+    uint32_t* h_bpos = h_bidx + HM_BOUNDARY_FIRST;
+    hm_site_record* h_brecs = reinterpret_cast<hm_site_record*>(h_bpos + HM_BOUNDARY_FIRST);
     k_publish<<<1, 64, 0, ctx->stream>>>(reinterpret_cast<const uint32_t*>(d_cnt), reinterpret_cast<uint32_t*>(ctx->h_cnt_pin), (uint32_t)(CNT_BYTES / 4));
     if (n_keys) {
       k_publish_items<<<4, 256, 0, ctx->stream>>>(ctx->b_bidx.as<uint32_t>(), h_bidx, 1u, (uint32_t)HM_BOUNDARY_FIRST, d_cnt + 4);
       k_publish_items<<<8, 256, 0, ctx->stream>>>(ctx->b_brecs.as<uint32_t>(), reinterpret_cast<uint32_t*>(h_brecs),
                                                   (uint32_t)(sizeof(hm_site_record) / 4), (uint32_t)HM_BOUNDARY_FIRST, d_cnt + 4);
+      if (omit) k_publish_items<<<4, 256, 0, ctx->stream>>>(ctx->b_bpos.as<uint32_t>(), h_bpos, 1u, (uint32_t)HM_BOUNDARY_FIRST, d_cnt + 4);
     }
     CU(cudaGetLastError());
     lap(4); // site kernel launches enqueued
@@ -707,20 +737,21 @@ static int call_chunks_impl(hm_ctx* ctx, const hm_chunk* chunks, size_t n_chunks
       CU(cudaStreamSynchronize(ctx->stream));
       border.clear();
       for (size_t i = 0; i < n_unique; i++)
-        if (recs[i].tpos <= prev_max_end[recs[i].chunk] || recs[i].tpos >= next_min_start[recs[i].chunk]) border.emplace_back((uint32_t)i, recs[i]);
+        if (recs[i].tpos <= prev_max_end[recs[i].chunk] || recs[i].tpos >= next_min_start[recs[i].chunk]) border.push_back(Border{(uint32_t)i, 0u, recs[i]});
       n_boundary = border.size();
       have_all = true;
     } else if (n_boundary) {
       border.resize(n_boundary);
       if (n_boundary <= (size_t)HM_BOUNDARY_FIRST) {
-        for (size_t i = 0; i < n_boundary; i++) border[i] = std::make_pair(h_bidx[i], h_brecs[i]);
+        for (size_t i = 0; i < n_boundary; i++) border[i] = Border{h_bidx[i], omit ? h_bpos[i] : 0u, h_brecs[i]};
       } else {
-        std::vector<uint32_t> bi(n_boundary);
+        std::vector<uint32_t> bi(n_boundary), bp(n_boundary, 0u);
         std::vector<hm_site_record> br(n_boundary);
         CU(cudaMemcpyAsync(bi.data(), ctx->b_bidx.p, n_boundary * 4, cudaMemcpyDeviceToHost, ctx->stream));
         CU(cudaMemcpyAsync(br.data(), ctx->b_brecs.p, n_boundary * sizeof(hm_site_record), cudaMemcpyDeviceToHost, ctx->stream));
+        if (omit) CU(cudaMemcpyAsync(bp.data(), ctx->b_bpos.p, n_boundary * 4, cudaMemcpyDeviceToHost, ctx->stream));
         CU(cudaStreamSynchronize(ctx->stream));
-        for (size_t i = 0; i < n_boundary; i++) border[i] = std::make_pair(bi[i], br[i]);
+        for (size_t i = 0; i < n_boundary; i++) border[i] = Border{bi[i], bp[i], br[i]};
       }
     }
   }
@@ -730,27 +761,33 @@ static int call_chunks_impl(hm_ctx* ctx, const hm_chunk* chunks, size_t n_chunks
   // boundary records only.  Indices are positions in the key order = (chunk, tpos, ref, alt).
   unsigned long long* hist = h_cnt + 8;
   std::vector<uint32_t> dropped;
+  // restatement records are counted before any of them is dropped by the replay
+  const size_t n_restate = (size_t)(hist[HM_ST_GERM_HET] + hist[HM_ST_GERM_HETALT] + hist[HM_ST_GERM_HOMALT] + hist[HM_ST_GERM_HOMREF]);
   if (n_boundary) {
-    std::sort(border.begin(), border.end(), [](const std::pair<uint32_t, hm_site_record>& a, const std::pair<uint32_t, hm_site_record>& b) { return a.first < b.first; });
+    std::sort(border.begin(), border.end(), [](const Border& a, const Border& b) { return a.idx < b.idx; });
     std::unordered_set<int32_t> som_seen;
     std::vector<int32_t> adds;
     size_t i = 0;
     while (i < n_boundary) {
-      const int32_t chunk = border[i].second.chunk;
+      const int32_t chunk = border[i].rec.chunk;
       adds.clear();
-      for (; i < n_boundary && border[i].second.chunk == chunk; i++) {
-        const hm_site_record& R = border[i].second;
+      for (; i < n_boundary && border[i].rec.chunk == chunk; i++) {
+        const hm_site_record& R = border[i].rec;
+        const bool restates = R.status >= HM_ST_GERM_HET && R.status <= HM_ST_GERM_HOMREF;
         if (R.tpos <= prev_max_end[chunk] && som_seen.count(R.tpos)) { // dropped in get_tsbs_candidates
-          dropped.push_back(border[i].first);
+          if (!(omit && !have_all && restates)) dropped.push_back((omit && !have_all) ? border[i].pos : border[i].idx);
           hist[R.status]--;
           continue;
         }
-        const bool restates = R.status >= HM_ST_GERM_HET && R.status <= HM_ST_GERM_HOMREF;
         if (!restates && R.tpos >= next_min_start[chunk]) adds.push_back(R.tpos); // som_seen.add(tpos), caller.py:347
       }
       for (int32_t t : adds) som_seen.insert(t);
     }
   }
+  // what the copy below walks over: every record, or (restatements omitted) the compacted ones
+  const bool from_compact = omit && !have_all;
+  const size_t n_source = from_compact ? n_unique - n_restate : n_unique;
+  const hm_site_record* d_source = from_compact ? ctx->b_compact[parity].as<hm_site_record>() : rec_buf.as<hm_site_record>();
   // the records, minus the dropped ones (ascending indices): one copy per run between two dropped records
   if ((rc = flush_deferred(ctx, false))) return rc; // an earlier call's copies, if this call had no sort to put them behind
   size_t n_final = 0;
@@ -762,19 +799,25 @@ static int call_chunks_impl(hm_ctx* ctx, const hm_chunk* chunks, size_t n_chunks
       n_final += to - from;
       from = to + 1;
     }
+    if (omit) { // the slow path has everything on the host: drop the restatements here
+      size_t w = 0;
+      for (size_t i = 0; i < n_final; i++)
+        if (!(recs[i].status >= HM_ST_GERM_HET && recs[i].status <= HM_ST_GERM_HOMREF)) { if (w != i) recs[w] = recs[i]; w++; }
+      n_final = w;
+    }
   } else if (n_unique) {
     size_t from = 0;
     for (size_t d = 0; d <= dropped.size(); d++) {
-      const size_t to = d < dropped.size() ? dropped[d] : n_unique;
+      const size_t to = d < dropped.size() ? dropped[d] : n_source;
       if (to > from)
-        ctx->deferred.push_back(hm_ctx::PendingCopy{recs + n_final, rec_buf.as<hm_site_record>() + from, (to - from) * sizeof(hm_site_record)});
+        ctx->deferred.push_back(hm_ctx::PendingCopy{recs + n_final, d_source + from, (to - from) * sizeof(hm_site_record)});
       n_final += to - from;
       from = to + 1;
     }
     ctx->deferred_parity = parity;
     ctx->rec_parity ^= 1;
-    if (!async || !direct) { // the kernels are done (the main stream was synchronised above): copy now
-      if ((rc = flush_deferred(ctx, false))) return rc;
+    if (!async || !direct) { // copy now, behind whatever the main stream still has queued
+      if ((rc = flush_deferred(ctx, true))) return rc;
       CU(cudaStreamSynchronize(ctx->copy_stream));
       ctx->copy_pending = false;
     }

@@ -849,6 +849,28 @@ __global__ void k_publish_items(const uint32_t* src, uint32_t* mapped_dst, uint3
   __threadfence_system();
 }
 
+// ---- records the reference never emits stay on the device (option HM_OPT_OMIT_RESTATEMENTS) ----------------
+// A candidate that merely restates the germline genotype is counted and dropped by the reference
+// (caller.py:338-345): its record is needed for the counters and the boundary replay only.  keep flags -> exclusive
+// scan (cub) -> stable compaction; the host copies the compact array.
+__global__ void k_keep_flags(const hm_site_record* rec, const unsigned long long* n_dev, uint32_t* flags) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= *n_dev) return;
+  const uint8_t st = rec[i].status;
+  flags[i] = (st >= HM_ST_GERM_HET && st <= HM_ST_GERM_HOMREF) ? 0u : 1u;
+}
+__global__ void k_compact_records(const hm_site_record* rec, const uint32_t* flags, const uint32_t* pos,
+                                  const unsigned long long* n_dev, hm_site_record* out) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= *n_dev) return;
+  if (flags[i]) out[pos[i]] = rec[i];
+}
+// dst[i] = src[idx[i]] for the first min(cap, *n_items_dev) entries
+__global__ void k_gather_u32(const uint32_t* src, const uint32_t* idx, const unsigned long long* n_items_dev, uint32_t cap, uint32_t* dst) {
+  const unsigned long long n = min((unsigned long long)cap, *n_items_dev);
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) dst[i] = src[idx[i]];
+}
+
 // number of set bytes in flags[0..n)
 __global__ void k_count_flags(const uint8_t* flags, uint64_t n, unsigned long long* out) {
   unsigned long long c = 0;

@@ -20,7 +20,7 @@ EXPORTS = [
     "hm_set_phase_sets", "hm_upload_batch", "hm_call_chunks", "hm_call_batch", "hm_normcounts_chunks",
     "hm_read_stats", "hm_last_timing", "hm_last_kernel_times", "hm_set_stream", "hm_host_register",
     "hm_host_unregister", "hm_abi_sizeof", "hm_last_records", "hm_qname_seen", "hm_set_reference", "hm_ref_tricounts", "hm_last_norm_exact_sites",
-    "hm_phase_edges_begin", "hm_phase_edges_add", "hm_phase_edges_end", "hm_upload_batch_compact", "hm_call_batch_compact", "hm_call_chunks_async", "hm_records_wait",
+    "hm_phase_edges_begin", "hm_phase_edges_add", "hm_phase_edges_end", "hm_upload_batch_compact", "hm_call_batch_compact", "hm_call_chunks_async", "hm_records_wait", "hm_set_option",
 ]
 
 
@@ -59,6 +59,7 @@ def load():
         lib.hm_last_kernel_times.argtypes = [vp, vp, vp, sz, C.POINTER(sz)]
         lib.hm_last_records.argtypes = [vp, vp, sz, C.POINTER(sz)]
         lib.hm_records_wait.argtypes = [vp]
+        lib.hm_set_option.argtypes = [vp, C.c_int, C.c_int]
         lib.hm_qname_seen.argtypes = [vp, vp, sz, C.POINTER(sz)]
         lib.hm_set_reference.argtypes = [vp, vp, sz]
         lib.hm_ref_tricounts.argtypes = [vp, vp, sz, vp]
@@ -210,6 +211,10 @@ class Context:
         if not wait and not view:
             raise ValueError("wait=False needs view=True")
         return self._call(self.lib.hm_call_chunks if wait else self.lib.hm_call_chunks_async, (), chunks, cap, view)
+
+    def omit_restatements(self, on=True):
+        """records of germline restatements (never emitted by the reference) stay on the device; counters unchanged"""
+        self._chk(self.lib.hm_set_option(self.h, 1, 1 if on else 0))
 
     def records_wait(self):
         self._chk(self.lib.hm_records_wait(self.h))

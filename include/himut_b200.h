@@ -269,6 +269,12 @@ int hm_call_chunks_async(hm_ctx* ctx, const hm_chunk* chunks, size_t n_chunks,
                          int64_t log[HM_CALL_LOG_LEN]);
 int hm_records_wait(hm_ctx* ctx);
 
+/* options of a context.  HM_OPT_OMIT_RESTATEMENTS (default 0): records whose status is one of HM_ST_GERM_* — a
+ * candidate that merely restates the germline genotype, which the reference counts and drops (caller.py:338-345) —
+ * are not copied to the host; they still count in log[2..4].  A third of the record bytes at 30x.                */
+#define HM_OPT_OMIT_RESTATEMENTS 1
+int hm_set_option(hm_ctx* ctx, int option, int value);
+
 /* after hm_call_chunks / hm_call_batch returned HM_ERR_CAPACITY: copy the records of that call
  * into a buffer of at least *n_out entries, without recomputing anything */
 int hm_last_records(hm_ctx* ctx, hm_site_record* out, size_t cap, size_t* n_out);

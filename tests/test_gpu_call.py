@@ -1,5 +1,7 @@
 """Parity of the CUDA `himut call` path (through the C ABI) with the CPU oracle and with the
 reference's own outputs (golden fixtures).  Needs a B200: `pytest -m gpu`."""
+import os
+
 import numpy as np
 import pytest
 
@@ -199,3 +201,41 @@ def test_async_followed_by_a_call_without_candidates(ctx):
         ok, why = parity.records_equal(rec, srec)
         assert ok, why
         assert list(log) == list(slog)
+
+
+@pytest.mark.parametrize("name", ["call_basic", "call_sets", "call_phase", "call_adversarial_a", "call_adversarial_b", "call_lowdepth"])
+def test_omit_restatements(ctx, name):
+    """HM_OPT_OMIT_RESTATEMENTS: the same records minus the germline restatements (which the reference never emits),
+    the same counters; synchronous, asynchronous, and through the host fallback of the boundary replay"""
+    c = cases.build_case(name)
+    ctx.set_params(c["params"])
+    ctx.set_site_sets(c["common"], c["pon"])
+    if c["phase"] is not None:
+        ctx.set_phase_sets(c["phase"])
+    ctx.upload(c["batch"])
+    full, flog = ctx.call_chunks(c["chunk_table"])
+    restates = np.isin(full["status"], [abi.ST_GERM_HET, abi.ST_GERM_HETALT, abi.ST_GERM_HOMALT, abi.ST_GERM_HOMREF])
+    want = full[~restates]
+    ctx.omit_restatements(True)
+    try:
+        rec, log = ctx.call_chunks(c["chunk_table"])
+        assert list(log) == list(flog)
+        ok, why = parity.records_equal(rec, want)
+        assert ok, why
+        a = ctx.call_chunks(c["chunk_table"], view=True, wait=False)
+        b = ctx.call_chunks(c["chunk_table"], view=True, wait=False)
+        ctx.records_wait()
+        for r, l in (a, b):
+            assert list(l) == list(flog)
+            ok, why = parity.records_equal(r, want)
+            assert ok, why
+        os.environ["HIMUT_B200_BOUNDARY_CAP"] = "2"
+        try:
+            rec, log = ctx.call_chunks(c["chunk_table"])
+        finally:
+            del os.environ["HIMUT_B200_BOUNDARY_CAP"]
+        assert list(log) == list(flog)
+        ok, why = parity.records_equal(rec, want)
+        assert ok, why
+    finally:
+        ctx.omit_restatements(False)
