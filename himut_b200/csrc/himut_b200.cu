@@ -698,18 +698,6 @@ static int call_chunks_impl(hm_ctx* ctx, const hm_chunk* chunks, size_t n_chunks
     k_count_flags<<<148, 256, 0, ctx->stream>>>(ctx->b_qseen.as<uint8_t>(), (uint64_t)ctx->max_qname_id + 1, d_cnt + 2);
     t_end(ctx);
     CU(cudaGetLastError());
-    // records go straight into the caller's buffer when it is large enough, else into pinned staging
-    direct = out && cap >= n_unique;
-    if (n_unique && !direct) {
-      if (n_unique > ctx->h_stage_cap) {
-        if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
-        ctx->h_stage = nullptr; ctx->h_stage_cap = 0;
-        const size_t want = n_unique + n_unique / 4 + 1024;
-        CU(cudaHostAlloc((void**)&ctx->h_stage, want * sizeof(hm_site_record), cudaHostAllocDefault));
-        ctx->h_stage_cap = want;
-      }
-    }
-    recs = n_unique ? (direct ? out : ctx->h_stage) : nullptr;
     // First the small things: counters and the boundary records (the only ones the sequential som_seen replay
     // looks at).  The big record copy follows the replay, so records a previous chunk already claimed are skipped
     // by the copy itself instead of being squeezed out of 20 MB on the host.
@@ -730,6 +718,23 @@ static int call_chunks_impl(hm_ctx* ctx, const hm_chunk* chunks, size_t n_chunks
     memcpy(h_cnt, ctx->h_cnt_pin, CNT_BYTES);
     if ((int)h_cnt[3] == HM_ERR_BQ_ZERO) return fail(ctx, HM_ERR_BQ_ZERO, "a base quality of 0 reached the genotype model (the reference raises ValueError: math.log10(0))");
     n_boundary = n_keys ? (size_t)h_cnt[4] : 0;
+    // records go straight into the caller's buffer when it is large enough, else into pinned staging
+    {
+      const unsigned long long* hh = h_cnt + 8;
+      const size_t n_ret = omit ? n_unique - (size_t)(hh[HM_ST_GERM_HET] + hh[HM_ST_GERM_HETALT] + hh[HM_ST_GERM_HOMALT] + hh[HM_ST_GERM_HOMREF]) : n_unique;
+      const size_t n_host = n_boundary > HM_BOUNDARY_CAP ? n_unique : n_ret; // the host fallback of the replay fetches everything
+      direct = out && cap >= n_host;
+      if (n_host && !direct) {
+        if (n_host > ctx->h_stage_cap) {
+          if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+          ctx->h_stage = nullptr; ctx->h_stage_cap = 0;
+          const size_t want = n_host + n_host / 4 + 1024;
+          CU(cudaHostAlloc((void**)&ctx->h_stage, want * sizeof(hm_site_record), cudaHostAllocDefault));
+          ctx->h_stage_cap = want;
+        }
+      }
+      recs = n_unique ? (direct ? out : ctx->h_stage) : nullptr;
+    }
     if (n_boundary > HM_BOUNDARY_CAP) {
       // heavily overlapping region lists: more boundary records than the device list holds.  Fetch everything and
       // find them on the host with the same test k_site_reduce applies.
