@@ -408,9 +408,9 @@ def main():
                           "h2d_bytes_per_step": int(batch.nbytes() + chunks.nbytes), "d2h_bytes_per_step": int(rec.nbytes + 32),
                           "ms_per_step": ms_e2e_plain / args.steps, "call": "hm_call_batch (one quality byte per base)"},
             # own kernels per resident step: k_read_scan, k_candidates, k_expand_keys, k_site_range, k_chunk_key_ranges,
-            # k_site_entries_by_read, k_site_reduce, k_count_flags, 3 x k_publish, 2 x k_publish_items (profiles/
-            # launches_call_r01.csv; the cub sort / unique launches are library code and not counted)
-            "gpu_launches": int(args.steps * 13),
+            # k_site_entries_by_read, k_site_reduce, k_keep_flags, k_compact_records, k_gather_u32, k_count_flags,
+            # 3 x k_publish, 3 x k_publish_items (the cub sort / unique / scan launches are library code, not counted)
+            "gpu_launches": int(args.steps * 17),
             "dominant_kernel": max(step_ms, key=step_ms.get),
             "library_launches_per_step": "cub::DeviceRadixSort (candidate keys)",
             "roofline": {"bound": "hbm", "kernel": "k_read_scan", "achieved": achieved, "peak": peak, "unit": "GB/s",
