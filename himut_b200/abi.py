@@ -159,6 +159,8 @@ class ReadBatch:
             s.n_reads = self.n_reads
             for name, _ in self._FIELDS:
                 setattr(s, name, _ptr(getattr(self, name)))
+            if self.n_reads and not self.seq.size:  # no base stream (see without_seq)
+                s.seq, s.seq_off = None, None
             s.seq_bytes = self.seq.size
             s.bq_bytes = self.bq.size
             s.n_ops_total = self.ops.size
@@ -167,6 +169,14 @@ class ReadBatch:
 
     def nbytes(self):
         return sum(getattr(self, n).nbytes for n, _ in self._FIELDS)
+
+    def without_seq(self):
+        """the same batch (arrays shared) without its base stream: hm_read_batch.seq = NULL.  `call` and the phase
+        edges take the bases of match runs from the site's reference allele then — which is what a cs match says
+        (src/himut/cslib.py:22-29) — so a worker need neither unpack nor upload them."""
+        kw = {name: getattr(self, name) for name, _ in self._FIELDS}
+        kw["seq"], kw["seq_off"] = np.zeros(0, np.uint8), np.zeros(0, np.uint64)
+        return ReadBatch(keepalive=(self, self.keepalive), **kw)
 
     # ---- chunk -> read index range --------------------------------------------------
     def chunk_table(self, chunkloci, phase_sets=None):

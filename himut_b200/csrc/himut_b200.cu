@@ -410,6 +410,12 @@ int hm_upload_batch_compact(hm_ctx* ctx, const hm_read_batch* b, const hm_bq_com
 static int upload_batch_impl(hm_ctx* ctx, const hm_read_batch* b, const hm_bq_compact* cq) {
   if (!ctx || !b) return HM_ERR_ARG;
   if (!cq && !b->bq) return fail(ctx, HM_ERR_ARG, "batch has no quality stream");
+  // seq == NULL: no base stream.  The bases of match runs are then the reference allele of the site that asks
+  // (what a cs match means, cslib.py:22-29); substituted bases travel in the ops.  `call` and the phase edges
+  // need nothing else; normcounts does (for now) and refuses such a batch.
+  const bool has_seq = b->seq != nullptr;
+  if (!has_seq && b->seq_bytes) return fail(ctx, HM_ERR_ARG, "seq is NULL but seq_bytes is not 0");
+  if (has_seq && !b->seq_off) return fail(ctx, HM_ERR_ARG, "seq without seq_off");
   if (cq) {
     if (!cq->mask || !cq->exc_off || (cq->exc_bytes && !cq->exc)) return fail(ctx, HM_ERR_ARG, "incomplete hm_bq_compact");
     if (cq->mask_bytes * 8 != b->bq_bytes) return fail(ctx, HM_ERR_ARG, "hm_bq_compact.mask_bytes must be bq_bytes / 8");
@@ -429,8 +435,8 @@ static int upload_batch_impl(hm_ctx* ctx, const hm_read_batch* b, const hm_bq_co
     if (r && b->tstart[r] < b->tstart[r - 1]) return fail(ctx, HM_ERR_ARG, "read %llu: batch is not sorted by reference_start", (unsigned long long)r);
     if (b->tend[r] < b->tstart[r] || b->qlen[r] <= 0 || b->qstart[r] < 0 || b->qstart[r] > b->qlen[r])
       return fail(ctx, HM_ERR_ARG, "read %llu: inconsistent coordinates", (unsigned long long)r);
-    if ((b->seq_off[r] & 15) || (b->bq_off[r] & 15)) return fail(ctx, HM_ERR_ARG, "read %llu: seq_off / bq_off not 16-byte aligned", (unsigned long long)r);
-    if (b->bq_off[r] + (uint64_t)b->qlen[r] > b->bq_bytes || b->seq_off[r] + ((uint64_t)b->qlen[r] + 3) / 4 > b->seq_bytes ||
+    if ((has_seq && (b->seq_off[r] & 15)) || (b->bq_off[r] & 15)) return fail(ctx, HM_ERR_ARG, "read %llu: seq_off / bq_off not 16-byte aligned", (unsigned long long)r);
+    if (b->bq_off[r] + (uint64_t)b->qlen[r] > b->bq_bytes || (has_seq && b->seq_off[r] + ((uint64_t)b->qlen[r] + 3) / 4 > b->seq_bytes) ||
         b->op_off[r] + b->n_ops[r] > b->n_ops_total)
       return fail(ctx, HM_ERR_ARG, "read %llu: offsets outside the buffers", (unsigned long long)r);
     if (b->tend[r] > run) run = b->tend[r];
@@ -444,8 +450,9 @@ static int upload_batch_impl(hm_ctx* ctx, const hm_read_batch* b, const hm_bq_co
 #define UP(buf, field, count) if ((rc = upload(ctx, ctx->buf, b->field, (size_t)(count)))) return rc
   UP(b_tstart, tstart, n); UP(b_tend, tend, n); UP(b_qstart, qstart, n); UP(b_qlen, qlen, n);
   UP(b_mapq, mapq, n); UP(b_flags, flags, n); UP(b_qname, qname_id, n);
-  UP(b_seq_off, seq_off, n); UP(b_bq_off, bq_off, n); UP(b_op_off, op_off, n); UP(b_n_ops, n_ops, n);
-  UP(b_seq, seq, b->seq_bytes); UP(b_ops, ops, b->n_ops_total);
+  UP(b_bq_off, bq_off, n); UP(b_op_off, op_off, n); UP(b_n_ops, n_ops, n);
+  if (has_seq) { UP(b_seq_off, seq_off, n); UP(b_seq, seq, b->seq_bytes); }
+  UP(b_ops, ops, b->n_ops_total);
   if (!cq) { UP(b_bq, bq, b->bq_bytes); }
   else {
     for (uint64_t r = 0; r < n; r++)
@@ -471,8 +478,8 @@ static int upload_batch_impl(hm_ctx* ctx, const hm_read_batch* b, const hm_bq_co
   d.n_reads = n;
   d.tstart = ctx->b_tstart.as<int32_t>(); d.tend = ctx->b_tend.as<int32_t>(); d.qstart = ctx->b_qstart.as<int32_t>();
   d.qlen = ctx->b_qlen.as<int32_t>(); d.mapq = ctx->b_mapq.as<uint8_t>(); d.flags = ctx->b_flags.as<uint8_t>();
-  d.qname_id = ctx->b_qname.as<uint32_t>(); d.seq_off = ctx->b_seq_off.as<uint64_t>(); d.bq_off = ctx->b_bq_off.as<uint64_t>();
-  d.op_off = ctx->b_op_off.as<uint64_t>(); d.n_ops = ctx->b_n_ops.as<uint32_t>(); d.seq = ctx->b_seq.as<uint8_t>();
+  d.qname_id = ctx->b_qname.as<uint32_t>(); d.seq_off = has_seq ? ctx->b_seq_off.as<uint64_t>() : nullptr; d.bq_off = ctx->b_bq_off.as<uint64_t>();
+  d.op_off = ctx->b_op_off.as<uint64_t>(); d.n_ops = ctx->b_n_ops.as<uint32_t>(); d.seq = has_seq ? ctx->b_seq.as<uint8_t>() : nullptr;
   d.bq = ctx->b_bq.as<uint8_t>(); d.ops = ctx->b_ops.as<uint32_t>();
   d.op_t = ctx->b_op_t.as<uint32_t>(); d.op_q = ctx->b_op_q.as<uint32_t>(); d.mm_pos = ctx->b_mm.as<int32_t>();
   d.bq_total = ctx->b_bq_total.as<unsigned long long>(); d.n_match = ctx->b_n_match.as<int32_t>();
@@ -1049,6 +1056,7 @@ static int hm_normcounts_impl(hm_ctx* ctx, const uint8_t* refseq, size_t ref_len
                               int64_t* ccs_tri, int64_t* ref_tri, int64_t* log, int64_t* n_alt_tie) {
   if (!ccs_tri || !ref_tri || !log) return fail(ctx, HM_ERR_ARG, "output pointer is NULL");
   if (!refseq && !ctx->ref_len) return fail(ctx, HM_ERR_STATE, "refseq is NULL and no reference was set with hm_set_reference");
+  if (ctx->have_batch && !ctx->db.seq) return fail(ctx, HM_ERR_STATE, "the resident batch was uploaded without a base stream (seq == NULL): normcounts needs it");
   if (!refseq) ref_len = ctx->ref_len;
   CU(cudaSetDevice(ctx->device));
   memset(ccs_tri, 0, sizeof(int64_t) * HM_TRI_BINS);

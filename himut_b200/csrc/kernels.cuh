@@ -250,7 +250,10 @@ __global__ void __launch_bounds__(256) k_bq_expand(DevBatch b, const uint8_t* ma
 // allele of read r at 0-based reference position rpos (tstart <= rpos <= tend):
 //   0..3 base, 5 deleted, -1 no base; *bq = quality of the base; *ins = insertions whose
 //   reference position is rpos (caller.update_allelecounts: counts[tpos][4] += 1).
-__device__ __forceinline__ int read_allele_at(const DevBatch& b, uint64_t r, int32_t rpos, int* bq, int* ins) {
+//   ref_base: the reference allele at rpos as the caller's site names it.  A batch uploaded without a base
+//   stream (hm_read_batch.seq == NULL) takes the bases of its match runs from there: by the meaning of a cs
+//   match (cslib.py:22-29) they are the reference's.
+__device__ __forceinline__ int read_allele_at(const DevBatch& b, uint64_t r, int32_t rpos, int ref_base, int* bq, int* ins) {
   const uint32_t n = b.n_ops[r];
   *bq = 0; *ins = 0;
   if (n == 0) return -1;
@@ -274,6 +277,7 @@ __device__ __forceinline__ int read_allele_at(const DevBatch& b, uint64_t r, int
   const uint32_t q = __ldg(b.op_q + o0 + k) + (kind == HM_OP_MATCH ? off - t0 : 0u);
   *bq = b.bq[b.bq_off[r] + q];
   if (kind == HM_OP_SUB) return (int)((v >> 3) & 7u);
+  if (!b.seq) return ref_base;
   return (b.seq[b.seq_off[r] + (q >> 2)] >> (2 * (q & 3u))) & 3;
 }
 
@@ -307,7 +311,7 @@ __device__ __forceinline__ int warp_read_hap(const DevBatch& b, uint64_t r, cons
   bool h0 = true, h1 = true;
   for (uint32_t k = idx + lane; k < jdx; k += 32) {
     int bq, ins;
-    const int a = read_allele_at(b, r, hp[k] - 1, &bq, &ins);
+    const int a = read_allele_at(b, r, hp[k] - 1, (int)ph.href[s0 + k], &bq, &ins);
     int bit = 2;
     if (a >= 0 && a < 4) {
       if (a == (int)ph.href[s0 + k]) bit = 0;
@@ -524,7 +528,7 @@ __device__ __forceinline__ uint32_t warp_count_below(const int32_t* a, uint32_t 
 }
 
 // read_allele_at with the 8-ary op search
-__device__ __forceinline__ int read_allele_fast(const DevBatch& b, uint32_t r, int32_t rpos, int32_t ts, int* bq, int* ins) {
+__device__ __forceinline__ int read_allele_fast(const DevBatch& b, uint32_t r, int32_t rpos, int32_t ts, int ref_base, int* bq, int* ins) {
   const uint32_t n = __ldg(b.n_ops + r);
   *bq = 0; *ins = 0;
   if (n == 0) return -1;
@@ -543,6 +547,7 @@ __device__ __forceinline__ int read_allele_fast(const DevBatch& b, uint32_t r, i
   const uint32_t q = __ldg(b.op_q + o0 + k) + (kind == HM_OP_MATCH ? off - t0 : 0u);
   *bq = b.bq[__ldg(b.bq_off + r) + q];
   if (kind == HM_OP_SUB) return (int)((v >> 3) & 7u);
+  if (!b.seq) return ref_base;
   return (b.seq[__ldg(b.seq_off + r) + (q >> 2)] >> (2 * (q & 3u))) & 3;
 }
 
@@ -566,13 +571,14 @@ __device__ __forceinline__ int read_allele_fast(const DevBatch& b, uint32_t r, i
 // entry: bits 0-2 allele (0-3 base, 5 deleted, 7 none), 3-10 BQ, 11-18 insertions at the site,
 //        19-20 haplotype (0, 1, 2 ".", 3 not fetched), 21 read also covers the next position
 __device__ __forceinline__ uint32_t site_entry(const DevBatch& b, const DevParams& p, const hm_chunk& ch, uint32_t c,
-                                               const uint64_t* pair_off, const uint8_t* pair_hap, uint32_t r, int32_t rpos) {
+                                               const uint64_t* pair_off, const uint8_t* pair_hap, uint32_t r, int32_t rpos,
+                                               int ref_base) {
   uint32_t e = HM_ENT_NONE;
   if (!(__ldg(b.flags + r) & HM_READ_SECONDARY)) {
     const int32_t ts = __ldg(b.tstart + r), te = __ldg(b.tend + r);
     if (ts < ch.end && te > ch.start && ts <= rpos && rpos <= te) {
       int bq, ins;
-      const int a = read_allele_fast(b, r, rpos, ts, &bq, &ins);
+      const int a = read_allele_fast(b, r, rpos, ts, ref_base, &bq, &ins);
       const uint32_t hap = p.phase ? pair_hap[pair_off[c] + (r - ch.read_lo)] : 2u;
       e = (a < 0 ? HM_ENT_NONE : (uint32_t)a) | ((uint32_t)bq << 3) | ((uint32_t)min(ins, 255) << 11) | ((hap & 3u) << 19) |
           ((te > rpos + 1) ? (1u << 21) : 0u); // overlaps [tpos, tpos + 1) (caller.py:558)
@@ -610,7 +616,7 @@ __global__ void __launch_bounds__(1024) k_site_entries(DevBatch b, DevParams p, 
   const uint32_t c = (uint32_t)(key >> 36);
   const int32_t rpos = (int32_t)((key >> 4) & 0xffffffffull) - 1;
   const hm_chunk ch = chunks[c];
-  entries[(uint64_t)slot * stride + ki] = site_entry(b, p, ch, c, pair_off, pair_hap, __ldg(site_lo + ki) + slot, rpos);
+  entries[(uint64_t)slot * stride + ki] = site_entry(b, p, ch, c, pair_off, pair_hap, __ldg(site_lo + ki) + slot, rpos, (int)((key >> 2) & 3));
 }
 
 // ---- gather by read ------------------------------------------------------------------------------
@@ -683,12 +689,14 @@ __global__ void __launch_bounds__(256) k_site_entries_by_read(DevBatch b, DevPar
     }
     __syncwarp();
   }
-  const uint64_t bq0 = __ldg(b.bq_off + r), sq0 = __ldg(b.seq_off + r);
+  const uint64_t bq0 = __ldg(b.bq_off + r), sq0 = b.seq ? __ldg(b.seq_off + r) : 0;
   const uint32_t hap = p.phase ? pair_hap[pr] : 2u;
   for (uint32_t ki = s_lo + lane; ki < s_hi; ki += 32) {
     const uint32_t slot = r - __ldg(site_lo + ki);
     if (slot >= HM_SITE_SLOTS || slot >= __ldg(site_n + ki)) continue; // deep pileups: k_site_reduce computes these itself
-    const int32_t rpos = (int32_t)((__ldg(keys + ki) >> 4) & 0xffffffffull) - 1;
+    const unsigned long long key = __ldg(keys + ki);
+    const int32_t rpos = (int32_t)((key >> 4) & 0xffffffffull) - 1;
+    const int ref_base = (int)((key >> 2) & 3);
     int a, bq = 0, ins = 0;
     if (staged) {
       const uint32_t off = (uint32_t)(rpos - ts);
@@ -703,10 +711,10 @@ __global__ void __launch_bounds__(256) k_site_entries_by_read(DevBatch b, DevPar
       else {
         const uint32_t q = s_q[wid][k] + (kind == HM_OP_MATCH ? off - t_op : 0u);
         bq = b.bq[bq0 + q];
-        a = kind == HM_OP_SUB ? (int)((v >> 3) & 7u) : (int)((b.seq[sq0 + (q >> 2)] >> (2 * (q & 3u))) & 3u);
+        a = kind == HM_OP_SUB ? (int)((v >> 3) & 7u) : !b.seq ? ref_base : (int)((b.seq[sq0 + (q >> 2)] >> (2 * (q & 3u))) & 3u);
       }
     } else {
-      a = read_allele_fast(b, r, rpos, ts, &bq, &ins);
+      a = read_allele_fast(b, r, rpos, ts, ref_base, &bq, &ins);
     }
     entries[(uint64_t)slot * stride + ki] = (a < 0 ? HM_ENT_NONE : (uint32_t)a) | ((uint32_t)bq << 3) | ((uint32_t)min(ins, 255) << 11) |
                                             ((hap & 3u) << 19) | ((te > rpos + 1) ? (1u << 21) : 0u);
@@ -743,7 +751,7 @@ __global__ void __launch_bounds__(128) k_site_reduce(DevBatch b, DevParams p, De
     for (int x = 0; x < 4; x++) { SS[x][0] = 0.0; SS[x][1] = 0.0; SS[x][2] = 0.0; }
     for (uint32_t s = 0; s < n; s++) {
       const uint32_t e = s < HM_SITE_SLOTS ? __ldg(entries + (uint64_t)s * stride + ki)
-                                           : site_entry(b, p, ch, c, pair_off, pair_hap, lo + s, tpos - 1); // very deep pileups
+                                           : site_entry(b, p, ch, c, pair_off, pair_hap, lo + s, tpos - 1, ref); // very deep pileups
       if (e == HM_ENT_UNWRITTEN) continue; // a read of the range that does not reach the site
       const uint32_t a = e & 7u;
       cnt[4] += (int)((e >> 11) & 255u);

@@ -972,7 +972,7 @@ __global__ void __launch_bounds__(128) k_phase_edges(DevBatch b, const int32_t* 
   if (k > HM_EDGE_MAX_SNPS) { if (lane == 0) atomicMax(need_band, 0xffffffffu); return; }
   for (uint32_t i = lane; i < k; i += 32) {
     int bq, ins;
-    const int a = read_allele_fast(b, (uint32_t)r, hpos[idx + i] - 1, ts, &bq, &ins);
+    const int a = read_allele_fast(b, (uint32_t)r, hpos[idx + i] - 1, ts, (int)href[idx + i], &bq, &ins);
     // tpos2qbase: deleted base ("-", 0); every covered position has an entry (cslib.py:153-170)
     uint8_t st = 2;                                      // 2: skipped (BQ below min_bq)
     if (!(bq < min_bq)) st = (a >= 0 && a < 4 && a == (int)href[idx + i]) ? 0 : 1;

@@ -86,6 +86,12 @@ typedef struct hm_read_batch {
   const uint32_t* n_ops;
   const uint8_t* seq;       /* 2-bit bases, 4 per byte, base i at bits 2*(i&3) of byte i>>2 */
   uint64_t seq_bytes;       /* padded to a multiple of 16                                   */
+                            /* seq may be NULL (seq_bytes 0, seq_off ignored): the batch then
+                             * carries no base stream.  Substituted bases travel in the ops; the
+                             * bases of match runs are, by the meaning of a cs match
+                             * (cslib.py:22-29), the reference allele of the site that asks.
+                             * hm_call_* and hm_phase_edges_* accept such a batch (a quarter of
+                             * the upload less); hm_normcounts_chunks returns HM_ERR_STATE.   */
   const uint8_t* bq;        /* one byte per base                                            */
   uint64_t bq_bytes;        /* padded to a multiple of 16                                   */
   const uint32_t* ops;
