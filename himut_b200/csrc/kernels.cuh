@@ -655,6 +655,8 @@ __global__ void k_chunk_key_ranges(const unsigned long long* keys, const unsigne
   koff[c] = (uint32_t)lo;
 }
 
+// kSeq: the batch has a base stream (false: match runs carry the site's reference allele, hm_read_batch.seq == NULL)
+template <bool kSeq>
 __global__ void __launch_bounds__(256) k_site_entries_by_read(DevBatch b, DevParams p, const hm_chunk* chunks, uint32_t n_chunks,
                                                               const uint64_t* pair_off, uint64_t n_pairs, const uint8_t* pair_hap,
                                                               const unsigned long long* keys, const uint32_t* koff,
@@ -689,7 +691,7 @@ __global__ void __launch_bounds__(256) k_site_entries_by_read(DevBatch b, DevPar
     }
     __syncwarp();
   }
-  const uint64_t bq0 = __ldg(b.bq_off + r), sq0 = b.seq ? __ldg(b.seq_off + r) : 0;
+  const uint64_t bq0 = __ldg(b.bq_off + r), sq0 = kSeq ? __ldg(b.seq_off + r) : 0;
   const uint32_t hap = p.phase ? pair_hap[pr] : 2u;
   for (uint32_t ki = s_lo + lane; ki < s_hi; ki += 32) {
     const uint32_t slot = r - __ldg(site_lo + ki);
@@ -711,7 +713,7 @@ __global__ void __launch_bounds__(256) k_site_entries_by_read(DevBatch b, DevPar
       else {
         const uint32_t q = s_q[wid][k] + (kind == HM_OP_MATCH ? off - t_op : 0u);
         bq = b.bq[bq0 + q];
-        a = kind == HM_OP_SUB ? (int)((v >> 3) & 7u) : !b.seq ? ref_base : (int)((b.seq[sq0 + (q >> 2)] >> (2 * (q & 3u))) & 3u);
+        a = kind == HM_OP_SUB ? (int)((v >> 3) & 7u) : !kSeq ? ref_base : (int)((b.seq[sq0 + (q >> 2)] >> (2 * (q & 3u))) & 3u);
       }
     } else {
       a = read_allele_fast(b, r, rpos, ts, ref_base, &bq, &ins);
