@@ -39,7 +39,7 @@ def get_edges(chrom, bam_file, min_bq, min_mapq, hpos_lst, hetsnp_lst, hetsnp2hi
                 hi = min(length, lo + worker.GROUP_SPAN)
                 batch, _ = src.batch(chrom, [(chrom, lo, hi)])
                 if batch.n_reads:
-                    ctx.upload(batch)
+                    ctx.upload(batch.without_seq())  # a cs match at a hetSNP carries its reference allele
                     need = ctx.phase_edges_add(min_bq, min_mapq, lo if lo else -2**31)
                 lo = hi
             if not need:

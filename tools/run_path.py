@@ -13,6 +13,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("path", choices=["call", "normcounts"])
 ap.add_argument("--contig-mb", type=int, default=8)
 ap.add_argument("--reps", type=int, default=3)
+ap.add_argument("--with-seq", action="store_true", help="call: upload the 2-bit base stream too (the worker mirror does not)")
 a = ap.parse_args()
 
 import cases  # noqa: E402
@@ -25,7 +26,7 @@ chunks = d.batch.chunk_table(cases.chunkloci(0, n))
 with lib.Context(0) as ctx:
     ctx.set_params(params)
     ctx.set_site_sets()
-    ctx.upload(d.batch)
+    ctx.upload(d.batch if (a.path == "normcounts" or a.with_seq) else d.batch.without_seq())
     for _ in range(a.reps):
         if a.path == "call":
             rec, log = ctx.call_chunks(chunks, view=True)
