@@ -204,12 +204,46 @@ def bam_to_records(ctx, params, contig_mb, seed):
             if best is None or t2 - t0 < best:
                 best, best_dec = t2 - t0, t1 - t0
         bam.close()
-        return {"value": d.aligned_bases / best, "unit": "bases/s", "contig_mb": contig_mb, "decode_threads": threads,
-                "seconds": best, "decode_seconds": best_dec, "bam_bytes": os.path.getsize(path), "bam_write_seconds": t_write,
-                "site_records": int(rec.size),
-                "note": "BAM (page cache) -> records: bounded by host BGZF inflate + record parse, not by the GPU"}
+        out = {"value": d.aligned_bases / best, "unit": "bases/s", "contig_mb": contig_mb, "decode_threads": threads,
+               "seconds": best, "decode_seconds": best_dec, "bam_bytes": os.path.getsize(path), "bam_write_seconds": t_write,
+               "site_records": int(rec.size),
+               "note": "BAM (page cache) -> records: bounded by host BGZF inflate + record parse, not by the GPU"}
+        try:
+            out["to_vcf"] = bam_to_vcf(path, n, d.aligned_bases, tmp)
+        except Exception as ex:  # a sub-measurement: never costs the line
+            out["to_vcf"] = {"error": repr(ex)}
+        return out
     finally:
         shutil.rmtree(tmp, ignore_errors=True)
+
+
+def bam_to_vcf(bam_path, contig_len, aligned_bases, tmp):
+    """SURVEY 8(d) timing (ii): BAM on disk -> VCF on disk through the worker mirror itself
+    (himut_b200.caller.get_somatic_substitutions: native decode, upload, device path, 12-tuples, natsort) and the
+    mirror of the reference's writer (vcfio.dump_sbs).  Its own hm_ctx, like a worker process."""
+    from himut_b200 import caller, gtmodel, vcfio
+    a = gtmodel.DEFAULT_CALL_ARGS
+    loci = [("chr1", s, e) for s, e in chunkloci(contig_len)]
+    header = "##fileformat=VCFv4.2\n#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\tsynth"
+    best = None
+    for _ in range(3):
+        lst, log = {}, {}
+        t0 = time.perf_counter()
+        caller.get_somatic_substitutions(
+            "chr1", bam_path, None, None, loci, {}, {}, {}, a["min_qv"], a["min_mapq"], a["qlen_lower_limit"],
+            a["qlen_upper_limit"], a["min_sequence_identity"], a["min_gq"], a["min_bq"], a["min_trim"], a["max_mismatch_count"],
+            a["mismatch_window"], a["md_threshold"], a["min_ref_count"], a["min_alt_count"], a["min_hap_count"], 1e-6,
+            a["germline_snv_prior"], 1e-4, False, True, False, lst, log)
+        t1 = time.perf_counter()
+        vcf = os.path.join(tmp, "out.vcf")
+        vcfio.dump_sbs(vcf, header, ["chr1"], lst)
+        t2 = time.perf_counter()
+        if best is None or t2 - t0 < best[0]:
+            best = (t2 - t0, t1 - t0, t2 - t1)
+    return {"value": aligned_bases / best[0], "unit": "bases/s", "seconds": best[0], "worker_seconds": best[1],
+            "writer_seconds": best[2], "rows": len(lst["chr1"]), "vcf_bytes": os.path.getsize(vcf),
+            "log": [int(v) for v in log["chr1"]],
+            "note": "non_human_sample = True (no common-SNP / PoN files), otherwise the defaults of the resident workload"}
 
 
 def run_reference(args, rank, world):

@@ -39,7 +39,46 @@ def record_to_tuple(chrom, r):
             read_depth, ref_count, alt_count, alt_vaf, phase_set)
 
 
+_EMITTED_CODES = np.array(sorted(_EMITTED), np.uint8)
+_NAME_BY_CODE = [abi.STATUS_NAME.get(c, "") for c in range(256)]
+
+
+def _sorted_rows(rows):
+    """natsorted(rows) for rows of one contig.  All rows share element 0, position keys are ("", int) and the
+    ref / alt strings hold no digits, so natsort's order is the plain order of (pos, ref, alt) whenever those
+    three are distinct from row to row; otherwise (the later, mixed-type fields decide) the general routine runs."""
+    out = sorted(rows, key=lambda r: (r[1], r[2], r[3]))
+    for a, b in zip(out, out[1:]):
+        if a[1] == b[1] and a[2] == b[2] and a[3] == b[3]:
+            return natsorted(rows)
+    return out
+
+
 def records_to_tsbs_lst(chrom, records):
-    """chrom2tsbs_lst[chrom] = natsorted(list(set(pass + filtered)))  (caller.py:622-624)"""
-    rows = [record_to_tuple(chrom, r) for r in records if int(r["status"]) in _EMITTED]
-    return natsorted(list(set(rows)))
+    """chrom2tsbs_lst[chrom] = natsorted(list(set(pass + filtered)))  (caller.py:622-624).
+    Column arithmetic is done on whole arrays (the expressions of record_to_tuple, same operand types: int32
+    counts as float64, int quality sums divided by float64 counts); HetAltSite rows, which carry formatted
+    strings, go through record_to_tuple one by one."""
+    rec = records[np.isin(records["status"], _EMITTED_CODES)]
+    n = rec.size
+    if n == 0:
+        return []
+    idx = np.arange(n)
+    ref_c, alt_c = rec["ref"].astype(np.intp), rec["alt"].astype(np.intp)
+    counts = rec["counts"].astype(np.float64)
+    depth = counts.sum(axis=1) - counts[:, 4]                 # bamlib.get_read_depth
+    n_ref, n_alt = counts[idx, ref_c], counts[idx, alt_c]
+    with np.errstate(divide="ignore", invalid="ignore"):
+        vaf = n_alt / depth                                   # bamlib.get_alt_counts
+        alt_bq = np.where(n_alt != 0, rec["bq_sum"][idx, alt_c].astype(np.int64) / n_alt, 0.0)
+    status = rec["status"]
+    ps = rec["phase_set"]
+    ps_txt = ["."] * n
+    for i in np.flatnonzero((status == abi.ST_PASS) & (ps >= 0)).tolist():
+        ps_txt[i] = str(int(ps[i]))
+    rows = list(zip([chrom] * n, rec["tpos"].tolist(), [abi.CODE2BASE[c] for c in ref_c.tolist()],
+                    [abi.CODE2BASE[c] for c in alt_c.tolist()], [_NAME_BY_CODE[c] for c in status.tolist()],
+                    rec["gq"].tolist(), alt_bq.tolist(), depth.tolist(), n_ref.tolist(), n_alt.tolist(), vaf.tolist(), ps_txt))
+    for i in np.flatnonzero(status == abi.ST_HETALT_SITE).tolist():
+        rows[i] = record_to_tuple(chrom, rec[i])
+    return _sorted_rows(list(set(rows)))

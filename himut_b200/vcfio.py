@@ -103,3 +103,39 @@ def phase_tables(chunkloci_lst, phase_set2hbit_lst, phase_set2hpos_lst, phase_se
     table = dict(hpos=np.asarray(hpos, np.int32), href=np.asarray(href, np.uint8), halt=np.asarray(halt, np.uint8),
                  hbit=np.asarray(hbit, np.uint8), set_off=np.asarray(set_off, np.uint64))
     return table, chunk_sets
+
+
+# ---- writers -----------------------------------------------------------------------------------
+# Text the reference's vcflib.dump_sbs / dump_phased_sbs (src/himut/vcflib.py:820-1021) produce from
+# chrom2tsbs_lst, reproduced so that "BAM on disk -> VCF on disk" can be run and timed without the reference
+# (bench.py); in a drop-in installation the reference's own writers stay in place.  Quirks kept: a HetAltSite row
+# carries pre-formatted strings and goes to the single-molecule file when int(ref_count) == 1 (every other row:
+# int(alt_count) == 1), and the phased main file names no PS key for a HetAltSite row although the sample has one.
+_COLS = "{}\t{}\t.\t{}\t{}\t.\t{}\t.\t{}\t{}\n"
+_KEYS = "GT:GQ:BQ:DP:AD:VAF"
+_SAMPLE_HETALT = "./.:{}:{}:{:0.0f}:{:0.0f},{}:{}"
+_SAMPLE_OTHER = "./.:{}:{:0.1f}:{:0.0f}:{:0.0f},{:0.0f}:{:.2f}"
+
+
+def dump_sbs(vcf_file, vcf_header, chrom_lst, chrom2tsbs_lst, phased=False):
+    """writes vcf_file and its .single_molecule_mutations.vcf twin; phased=True is dump_phased_sbs"""
+    if not vcf_file.endswith(".vcf"):
+        raise ValueError("VCF file must have .vcf suffix")
+    ps_key = ":PS" if phased else ""
+    with open(vcf_file, "w") as main, open(vcf_file.replace(".vcf", ".single_molecule_mutations.vcf"), "w") as single:
+        main.write("{}\n".format(vcf_header))
+        single.write("{}\n".format(vcf_header))
+        for chrom in chrom_lst:
+            for row in chrom2tsbs_lst[chrom]:
+                name, pos, ref, alt, status, gq, bq, depth, n_ref, n_alt, vaf, phase_set = row
+                hetalt = status == "HetAltSite"
+                sample = (_SAMPLE_HETALT if hetalt else _SAMPLE_OTHER).format(gq, bq, depth, n_ref, n_alt, vaf)
+                if phased:
+                    sample = "{}:{}".format(sample, phase_set)
+                main.write(_COLS.format(name, pos, ref, alt, status, _KEYS + ("" if hetalt else ps_key), sample))
+                if int(n_ref if hetalt else n_alt) == 1:
+                    single.write(_COLS.format(name, pos, ref, alt, status, _KEYS + ps_key, sample))
+
+
+def dump_phased_sbs(vcf_file, vcf_header, chrom_lst, chrom2tsbs_lst):
+    dump_sbs(vcf_file, vcf_header, chrom_lst, chrom2tsbs_lst, phased=True)

@@ -82,3 +82,32 @@ def test_group_chunks():
     assert worker.group_chunks(loci, span=450_000) == [[0, 1], [2, 3]]
     assert worker.group_chunks(loci, span=10) == [[0], [1], [2], [3]]
     assert worker.group_chunks(loci, span=10**9) == [[0, 1, 2, 3]]
+
+
+def _rows_one_by_one(chrom, recs):
+    from himut_b200 import records
+    rows = [records.record_to_tuple(chrom, r) for r in recs if int(r["status"]) in records._EMITTED]
+    return natsort_compat.natsorted(list(set(rows)))
+
+
+def test_rows_from_whole_arrays_equal_rows_one_by_one():
+    """records_to_tsbs_lst does the column arithmetic on arrays and sorts by (pos, ref, alt): same rows, same order
+    as record_to_tuple per record + natsorted (caller.py:622-624)"""
+    from himut_b200 import records
+    from oracle import oracle
+    for name in ("call_sets", "call_phase", "call_adversarial_a", "call_adversarial_b", "call_pon_params"):
+        c = cases.build_case(name)
+        rec, _ = oracle.call_chunks(c["params"], c["batch"], c["chunk_table"], c["common"], c["pon"], c["phase"])
+        got = records.records_to_tsbs_lst(cases.CHROM, rec)
+        assert got == _rows_one_by_one(cases.CHROM, rec), name
+    assert records.records_to_tsbs_lst(cases.CHROM, np.zeros(0, abi.SITE_DTYPE)) == []
+
+
+def test_row_order_falls_back_to_natsort_on_equal_sites():
+    from himut_b200 import records
+    a = ("chr1", 10, "A", "C", "LowBQ", 5, 20.0, 30.0, 28.0, 2.0, 0.07, ".")
+    b = ("chr1", 10, "A", "C", "LowGQ", 5, 20.0, 30.0, 28.0, 2.0, 0.07, ".")
+    c = ("chr1", 9, "T", "G", "PASS", 50, 93.0, 30.0, 29.0, 1.0, 0.03, ".")
+    d = ("chr1", 10, "A", "C,G", "HetAltSite", 50, "93.0,93.0", 30.0, 0.0, "15,15", "0.50,0.50", ".")
+    for rows in ([b, a, c], [d, b, c], [c, d, a, b]):
+        assert records._sorted_rows(list(rows)) == natsort_compat.natsorted(list(rows))
