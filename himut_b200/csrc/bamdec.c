@@ -26,6 +26,22 @@
 
 #include "../../include/himut_io.h"
 #include "inflate_fast.h"
+#include "crc32_clmul.h"
+
+/* crc32(0, p, n) of zlib: carry-less-multiply folding over the multiple-of-16 body when the CPU has it
+ * (crc32_clmul.h), zlib for the tail and everywhere else */
+static uint32_t block_crc(const uint8_t* p, size_t n) {
+#if HM_CRC32_CLMUL
+  if (n >= 64 && hm_crc32_available()) {
+    size_t used = 0;
+    const uint32_t state = hm_crc32_fold(0xffffffffu, p, n, &used);
+    return (uint32_t)crc32((uLong)(uint32_t)~state, p + used, (uInt)(n - used));
+  }
+#endif
+  return (uint32_t)crc32(crc32(0L, Z_NULL, 0), p, (uInt)n);
+}
+uint32_t hm_crc32_test(const uint8_t* p, size_t n) { return block_crc(p, n); }
+
 
 typedef struct {
   char* name;
@@ -188,14 +204,14 @@ static void* inflate_worker(void* arg) {
       uint8_t* dst = j->out + b->uoff;
       /* own decoder first (inflate_fast.h); zlib when it declines or the CRC disagrees */
       if (!j->zlib_only && hm_inflate_raw(payload, payload_len, dst, b->usize) == 0 &&
-          (uint32_t)crc32(crc32(0L, Z_NULL, 0), dst, b->usize) == want_crc)
+          block_crc(dst, b->usize) == want_crc)
         continue;
       inflateReset(&zs);
       zs.next_in = (Bytef*)payload;
       zs.avail_in = (uInt)payload_len;
       zs.next_out = dst;
       zs.avail_out = b->usize;
-      if (inflate(&zs, Z_FINISH) != Z_STREAM_END || (uint32_t)crc32(crc32(0L, Z_NULL, 0), dst, b->usize) != want_crc) { j->error = 1; break; }
+      if (inflate(&zs, Z_FINISH) != Z_STREAM_END || block_crc(dst, b->usize) != want_crc) { j->error = 1; break; }
     }
     if (j->error) break;
   }
@@ -852,7 +868,7 @@ static void* deflate_worker(void* arg) {
       deflateEnd(&zs);
       static const uint8_t head[16] = {0x1f, 0x8b, 8, 4, 0, 0, 0, 0, 0, 0xff, 6, 0, 'B', 'C', 2, 0};
       memcpy(o, head, 16); o[16] = (uint8_t)bsize; o[17] = (uint8_t)(bsize >> 8);
-      const uint32_t crc = (uint32_t)crc32(crc32(0L, Z_NULL, 0), j->src + off, (uInt)len);
+      const uint32_t crc = block_crc(j->src + off, len);
       uint8_t* t = o + 18 + clen;
       t[0] = (uint8_t)crc; t[1] = (uint8_t)(crc >> 8); t[2] = (uint8_t)(crc >> 16); t[3] = (uint8_t)(crc >> 24);
       t[4] = (uint8_t)len; t[5] = (uint8_t)(len >> 8); t[6] = (uint8_t)(len >> 16); t[7] = (uint8_t)(len >> 24);

@@ -83,3 +83,18 @@ def test_bam_blocks_decode_identically_with_both_decoders(tmp_path, monkeypatch)
             nb = bamdec.NativeBam(path, threads=2)
             digests.append(cases.batch_digest(nb.read_batch("chr1", 0, 400_000)))
     assert len(set(digests)) == 1 and digests[0] == cases.batch_digest(d.batch)
+
+
+def test_block_crc_equals_zlib():
+    """every inflated BGZF block is checked with block_crc (carry-less-multiply folding + zlib for the tail,
+    csrc/crc32_clmul.h): it must be zlib's crc32 for every length and content"""
+    lib = bamdec.load()
+    lib.hm_crc32_test.argtypes = [C.c_char_p, C.c_size_t]
+    lib.hm_crc32_test.restype = C.c_uint32
+    rnd = random.Random(5)
+    lengths = list(range(0, 200)) + [rnd.randrange(0, 70_000) for _ in range(200)] + [65536, 65280, 4096, 4097]
+    for n in lengths:
+        data = rnd.randbytes(n)
+        assert lib.hm_crc32_test(data, n) == zlib.crc32(data), n
+    for data in (b"\x00" * 1000, b"\xff" * 4097, bytes(range(256)) * 37):
+        assert lib.hm_crc32_test(data, len(data)) == zlib.crc32(data)
