@@ -519,7 +519,7 @@ def main():
             out["normcounts"] = norm
         if bam_leg is not None:
             out["bam_to_records"] = bam_leg
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:  # the CPU arm beside the one-GPU line only
             threads = host_threads()
             n = max(1, min(len(chunks) // threads, args.cpu_chunks))
             v1, bases1, dt1, _ = cpu_baseline(d, params, chunks, n, 1)
