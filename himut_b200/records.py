@@ -63,6 +63,13 @@ def records_to_tsbs_lst(chrom, records):
     n = rec.size
     if n == 0:
         return []
+    # rows in (pos, ref letter, alt letter) order up front: when no two records share a site the rows are distinct and
+    # already in natsort's order (see _sorted_rows), so neither the set nor the sort has anything left to do
+    letter = np.frombuffer(abi.CODE2BASE.encode(), np.uint8)
+    order = np.lexsort((letter[rec["alt"]], letter[rec["ref"]], rec["tpos"]))
+    rec = rec[order]
+    same_site = (rec["tpos"][1:] == rec["tpos"][:-1]) & (rec["ref"][1:] == rec["ref"][:-1]) & (rec["alt"][1:] == rec["alt"][:-1])
+    distinct = not bool(same_site.any()) and not bool((rec["status"] == abi.ST_HETALT_SITE).any())
     idx = np.arange(n)
     ref_c, alt_c = rec["ref"].astype(np.intp), rec["alt"].astype(np.intp)
     counts = rec["counts"].astype(np.float64)
@@ -81,4 +88,4 @@ def records_to_tsbs_lst(chrom, records):
                     rec["gq"].tolist(), alt_bq.tolist(), depth.tolist(), n_ref.tolist(), n_alt.tolist(), vaf.tolist(), ps_txt))
     for i in np.flatnonzero(status == abi.ST_HETALT_SITE).tolist():
         rows[i] = record_to_tuple(chrom, rec[i])
-    return _sorted_rows(list(set(rows)))
+    return rows if distinct else _sorted_rows(list(set(rows)))

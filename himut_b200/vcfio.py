@@ -111,30 +111,41 @@ def phase_tables(chunkloci_lst, phase_set2hbit_lst, phase_set2hpos_lst, phase_se
 # (bench.py); in a drop-in installation the reference's own writers stay in place.  Quirks kept: a HetAltSite row
 # carries pre-formatted strings and goes to the single-molecule file when int(ref_count) == 1 (every other row:
 # int(alt_count) == 1), and the phased main file names no PS key for a HetAltSite row although the sample has one.
-_COLS = "{}\t{}\t.\t{}\t{}\t.\t{}\t.\t{}\t{}\n"
 _KEYS = "GT:GQ:BQ:DP:AD:VAF"
-_SAMPLE_HETALT = "./.:{}:{}:{:0.0f}:{:0.0f},{}:{}"
-_SAMPLE_OTHER = "./.:{}:{:0.1f}:{:0.0f}:{:0.0f},{:0.0f}:{:.2f}"
+# one template per (row kind, with PS or not); %-formatting and str.format share the float conversion
+# (PyOS_double_to_string), "%s" of an int is "{}" of it
+_HEAD = "%s\t%s\t.\t%s\t%s\t.\t%s\t.\t"
+_OTHER = "\t./.:%s:%0.1f:%0.0f:%0.0f,%0.0f:%.2f"
+_HETALT = "\t./.:%s:%s:%0.0f:%0.0f,%s:%s"
 
 
 def dump_sbs(vcf_file, vcf_header, chrom_lst, chrom2tsbs_lst, phased=False):
     """writes vcf_file and its .single_molecule_mutations.vcf twin; phased=True is dump_phased_sbs"""
     if not vcf_file.endswith(".vcf"):
         raise ValueError("VCF file must have .vcf suffix")
-    ps_key = ":PS" if phased else ""
-    with open(vcf_file, "w") as main, open(vcf_file.replace(".vcf", ".single_molecule_mutations.vcf"), "w") as single:
-        main.write("{}\n".format(vcf_header))
-        single.write("{}\n".format(vcf_header))
-        for chrom in chrom_lst:
-            for row in chrom2tsbs_lst[chrom]:
-                name, pos, ref, alt, status, gq, bq, depth, n_ref, n_alt, vaf, phase_set = row
-                hetalt = status == "HetAltSite"
-                sample = (_SAMPLE_HETALT if hetalt else _SAMPLE_OTHER).format(gq, bq, depth, n_ref, n_alt, vaf)
-                if phased:
-                    sample = "{}:{}".format(sample, phase_set)
-                main.write(_COLS.format(name, pos, ref, alt, status, _KEYS + ("" if hetalt else ps_key), sample))
-                if int(n_ref if hetalt else n_alt) == 1:
-                    single.write(_COLS.format(name, pos, ref, alt, status, _KEYS + ps_key, sample))
+    ps_key, ps_val = (":PS", ":%s\n") if phased else ("", "\n")
+    t_other = _HEAD + _KEYS + ps_key + _OTHER + ps_val
+    t_hetalt_main = _HEAD + _KEYS + _HETALT + ps_val
+    t_hetalt_single = _HEAD + _KEYS + ps_key + _HETALT + ps_val
+    main, single = ["{}\n".format(vcf_header)], ["{}\n".format(vcf_header)]
+    for chrom in chrom_lst:
+        for row in chrom2tsbs_lst[chrom]:
+            vals = (row[0], row[1], row[2], row[3], row[4], row[5], row[6], row[7], row[8], row[9], row[10])
+            if phased:
+                vals += (row[11],)
+            if row[4] == "HetAltSite":
+                main.append(t_hetalt_main % vals)
+                if int(row[8]) == 1:
+                    single.append(t_hetalt_single % vals)
+            else:
+                line = t_other % vals
+                main.append(line)
+                if int(row[9]) == 1:
+                    single.append(line)
+    with open(vcf_file, "w") as f:
+        f.write("".join(main))
+    with open(vcf_file.replace(".vcf", ".single_molecule_mutations.vcf"), "w") as f:
+        f.write("".join(single))
 
 
 def dump_phased_sbs(vcf_file, vcf_header, chrom_lst, chrom2tsbs_lst):
