@@ -16,7 +16,7 @@ from . import abi, pack
 
 _LIB = None
 EXPORTS = ["hm_bam_open", "hm_bam_close", "hm_bam_error", "hm_bam_header_text", "hm_bam_n_refs", "hm_bam_ref_name",
-           "hm_bam_ref_len", "hm_bam_read_batch", "hm_bam_n_qnames", "hm_bam_qname", "hm_bam_window_qlens", "hm_bam_write_batch", "hm_bq_compact_build",
+           "hm_bam_ref_len", "hm_bam_read_batch", "hm_bam_set_option", "hm_bam_n_qnames", "hm_bam_qname", "hm_bam_window_qlens", "hm_bam_write_batch", "hm_bq_compact_build",
            "hm_bq_compact_free"]
 
 
@@ -44,6 +44,7 @@ def load():
         lib.hm_bam_ref_name.restype = C.c_char_p
         lib.hm_bam_ref_len.argtypes = [vp, C.c_int]
         lib.hm_bam_read_batch.argtypes = [vp, C.c_int, C.c_int32, C.c_int32, C.c_int, C.POINTER(abi.hm_read_batch)]
+        lib.hm_bam_set_option.argtypes = [vp, C.c_int, C.c_int]
         lib.hm_bam_window_qlens.argtypes = [vp, C.c_int, C.c_int32, C.c_int32, C.c_int, vp, C.c_size_t, C.POINTER(C.c_size_t)]
         lib.hm_bam_write_batch.argtypes = [C.c_char_p, C.c_char_p, C.c_int32, C.c_char_p, C.POINTER(abi.hm_read_batch), C.c_int, C.c_int]
         lib.hm_bq_compact_build.argtypes = [C.POINTER(abi.hm_read_batch), C.c_int, vp, vp, C.POINTER(vp), C.POINTER(C.c_uint64), C.POINTER(C.c_uint8)]
@@ -115,9 +116,13 @@ class NativeBam:
         self.lengths = [self.lib.hm_bam_ref_len(self.h, i) for i in range(len(self.references))]
         self.header_text = self.lib.hm_bam_header_text(self.h).decode()
 
-    def read_batch(self, chrom, start, end, copy=True):
+    def read_batch(self, chrom, start, end, copy=True, seq=True):
+        """seq=False: the batch comes without its 2-bit base stream (HM_BAM_OPT_NO_SEQ), as `call` and the phase
+        edges want it; the decoder still checks the bases against the cs tag"""
         if chrom not in self.references:
             raise KeyError(chrom)
+        if self.lib.hm_bam_set_option(self.h, 1, 0 if seq else 1) != 0:
+            raise RuntimeError(self.lib.hm_bam_error(self.h).decode())
         s = abi.hm_read_batch()
         rc = self.lib.hm_bam_read_batch(self.h, self.references.index(chrom), int(max(start, 0)), int(end), self.threads, C.byref(s))
         if rc != 0:

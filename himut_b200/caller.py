@@ -60,12 +60,13 @@ def get_somatic_substitutions(
     groups = worker.group_chunks(chunkloci_lst)
     for gi, idx in enumerate(groups):
         loci = [chunkloci_lst[i] for i in idx]
-        batch, table = src.batch(chrom, loci, None if chunk_sets is None else [chunk_sets[i] for i in idx])
+        batch, table = src.batch(chrom, loci, None if chunk_sets is None else [chunk_sets[i] for i in idx], seq=False)
         if batch.n_reads == 0:
             continue
         # `call` never needs the read bases as a stream: substituted bases are in the ops, and under a cs match the
-        # read carries the reference allele of the site (cslib.py:22-29) — a quarter of the upload less
-        ctx.upload(batch.without_seq())
+        # read carries the reference allele of the site (cslib.py:22-29) — the decoder does not unpack them
+        # (seq=False above) and a quarter of the upload goes away
+        ctx.upload(batch)
         rec, _log = ctx.call_chunks(table)
         tally.add(ctx.qname_seen())
         # som_seen carries across groups exactly as across chunks (caller.py:243,347; bamlib.py:77)

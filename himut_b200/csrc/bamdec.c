@@ -79,6 +79,7 @@ typedef struct hm_bam {
   uint8_t *seq, *bq;
   uint32_t* ops;
   size_t cap_reads, cap_seq, cap_bq, cap_ops;
+  int no_seq; /* HM_BAM_OPT_NO_SEQ: batches come without the 2-bit base stream */
 } hm_bam;
 
 static int fail(hm_bam* b, const char* fmt, const char* a, long x) {
@@ -485,6 +486,60 @@ typedef struct {
   pthread_mutex_t mu;
 } decode_job_t;
 
+/* BAM's 4-bit bases -> one code per byte (A0 T1 G2 C3, 0xff anything else); 32 bases per step with a byte shuffle */
+static void nib_to_codes_scalar(const uint8_t* seq4, int32_t i, int32_t l_seq, uint8_t* codes) {
+  if (i & 1) { codes[i] = (uint8_t)NIB2CODE[seq4[i >> 1] & 15]; i++; }
+  for (; i + 1 < l_seq; i += 2) { const uint8_t by = seq4[i >> 1]; codes[i] = (uint8_t)NIB2CODE[by >> 4]; codes[i + 1] = (uint8_t)NIB2CODE[by & 15]; }
+  if (i < l_seq) codes[i] = (uint8_t)NIB2CODE[seq4[i >> 1] >> 4];
+}
+/* codes -> 2-bit packed (base i at bits 2*(i&3) of byte i>>2); codes outside 0..3 (soft clips only: the caller has
+ * rejected them under a match) are stored as 0, like the Python packer */
+static void pack_codes_scalar(const uint8_t* codes, int32_t i, int32_t l_seq, uint8_t* dst) {
+  for (; i + 3 < l_seq; i += 4) {
+    uint8_t v = 0;
+    for (int k = 0; k < 4; k++) { const uint8_t c = codes[i + k]; v |= (uint8_t)((c > 3 ? 0 : c) << (2 * k)); }
+    dst[i >> 2] = v;
+  }
+  if (i < l_seq) { uint8_t v = 0; for (int32_t k = i; k < l_seq; k++) { const uint8_t c = codes[k]; v |= (uint8_t)((c > 3 ? 0 : c) << (2 * (k & 3))); } dst[i >> 2] = v; }
+}
+#if defined(__x86_64__) && defined(__GNUC__)
+#include <immintrin.h>
+static int have_ssse3(void) { static int k = -1; if (k < 0) k = __builtin_cpu_supports("ssse3") && __builtin_cpu_supports("sse4.1"); return k; }
+__attribute__((target("ssse3,sse4.1"))) static int32_t nib_to_codes_simd(const uint8_t* seq4, int32_t l_seq, uint8_t* codes) {
+  const __m128i lut = _mm_setr_epi8(-1, 0, 3, -1, 2, -1, -1, -1, 1, -1, -1, -1, -1, -1, -1, -1);
+  const __m128i low = _mm_set1_epi8(0x0f);
+  int32_t i = 0;
+  for (; i + 32 <= l_seq; i += 32) {
+    const __m128i v = _mm_loadu_si128((const __m128i*)(seq4 + (i >> 1)));
+    const __m128i first = _mm_shuffle_epi8(lut, _mm_and_si128(_mm_srli_epi16(v, 4), low)); /* high nibble = even base */
+    const __m128i second = _mm_shuffle_epi8(lut, _mm_and_si128(v, low));
+    _mm_storeu_si128((__m128i*)(codes + i), _mm_unpacklo_epi8(first, second));
+    _mm_storeu_si128((__m128i*)(codes + i + 16), _mm_unpackhi_epi8(first, second));
+  }
+  return i;
+}
+__attribute__((target("ssse3,sse4.1"))) static int32_t pack_codes_simd(const uint8_t* codes, int32_t l_seq, uint8_t* dst) {
+  const __m128i w8 = _mm_set1_epi16(0x0401);      /* c0 + 4 c1 per byte pair  */
+  const __m128i w16 = _mm_set1_epi32(0x00100001); /* p0 + 16 p1 per word pair */
+  const __m128i three = _mm_set1_epi8(3);
+  int32_t i = 0;
+  for (; i + 16 <= l_seq; i += 16) {
+    __m128i c = _mm_loadu_si128((const __m128i*)(codes + i));
+    c = _mm_and_si128(_mm_andnot_si128(_mm_cmplt_epi8(c, _mm_setzero_si128()), c), three); /* 0xff (negative) -> 0 */
+    const __m128i p = _mm_maddubs_epi16(c, w8);  /* 8 x (c0 | c1 << 2)            */
+    const __m128i q = _mm_madd_epi16(p, w16);    /* 4 x (p0 | p1 << 4) = one byte */
+    const __m128i b = _mm_packus_epi16(_mm_packus_epi32(q, q), _mm_setzero_si128());
+    const uint32_t out = (uint32_t)_mm_cvtsi128_si32(b);
+    memcpy(dst + (i >> 2), &out, 4);
+  }
+  return i;
+}
+#else
+static int have_ssse3(void) { return 0; }
+static int32_t nib_to_codes_simd(const uint8_t* seq4, int32_t l_seq, uint8_t* codes) { (void)seq4; (void)l_seq; (void)codes; return 0; }
+static int32_t pack_codes_simd(const uint8_t* codes, int32_t l_seq, uint8_t* dst) { (void)codes; (void)l_seq; (void)dst; return 0; }
+#endif
+
 /* phase B for one record: SEQ -> 2-bit, QUAL copy, cs -> ops (cslib.cs2lst grammar) with span and base checks */
 static void decode_record(hm_bam* b, rec_t* R, uint8_t** codes_p, size_t* codes_cap) {
   const uint8_t* r = R->rec;
@@ -499,8 +554,7 @@ static void decode_record(hm_bam* b, rec_t* R, uint8_t** codes_p, size_t* codes_
     *codes_p = np_; *codes_cap = nc;
   }
   uint8_t* codes = *codes_p;
-  for (int32_t i = 0; i + 1 < l_seq; i += 2) { const uint8_t by = seq4[i >> 1]; codes[i] = (uint8_t)NIB2CODE[by >> 4]; codes[i + 1] = (uint8_t)NIB2CODE[by & 15]; }
-  if (l_seq & 1) codes[l_seq - 1] = (uint8_t)NIB2CODE[seq4[(l_seq - 1) >> 1] >> 4];
+  nib_to_codes_scalar(seq4, have_ssse3() ? nib_to_codes_simd(seq4, l_seq, codes) : 0, l_seq, codes);
   uint32_t* ops = b->ops + R->op_slot;
   uint32_t n_ops = 0;
   int32_t q = R->lead, rspan = 0;
@@ -512,7 +566,7 @@ static void decode_record(hm_bam* b, rec_t* R, uint8_t** codes_p, size_t* codes_
       if (*c < '0' || *c > '9') { R->err = E_CS_TOKEN; R->err_arg = (long)(c - cs); return; }
       while (*c >= '0' && *c <= '9') n = n * 10 + (*c++ - '0');
       if (q + n > l_seq) { R->err = E_CS_PAST; R->err_arg = q + n; return; }
-      for (long k = 0; k < n; k++) if (codes[q + k] == 0xff) { R->err = E_N_MATCH; R->err_arg = q + k; return; }
+      if (n) { const uint8_t* bad = (const uint8_t*)memchr(codes + q, 0xff, (size_t)n); if (bad) { R->err = E_N_MATCH; R->err_arg = (long)(bad - codes); return; } }
       if (n) ops[n_ops++] = HM_MAKE_OP(HM_OP_MATCH, n);
       q += (int32_t)n; rspan += (int32_t)n;
     } else if (*c == '=') {
@@ -545,17 +599,11 @@ static void decode_record(hm_bam* b, rec_t* R, uint8_t** codes_p, size_t* codes_
   if (q - R->lead != l_seq - R->trail - R->lead) { R->err = E_SPAN_QRY; R->err_arg = q - R->lead; return; }
   R->n_ops = n_ops; R->rspan = rspan;
   const size_t sb = ((size_t)l_seq + 3) / 4, sb16 = (sb + 15) & ~(size_t)15, qb16 = ((size_t)l_seq + 15) & ~(size_t)15;
-  uint8_t* dst = b->seq + R->seq_off;
-  int32_t i = 0;
-  for (; i + 3 < l_seq; i += 4) {
-    const uint8_t c0 = codes[i] & 3, c1 = codes[i + 1] & 3, c2 = codes[i + 2] & 3, c3 = codes[i + 3] & 3; /* 0xff (N in a clip) -> 3; fixed below */
-    dst[i >> 2] = (uint8_t)(c0 | (c1 << 2) | (c2 << 4) | (c3 << 6));
+  if (!b->no_seq) {
+    uint8_t* dst = b->seq + R->seq_off;
+    pack_codes_scalar(codes, have_ssse3() ? pack_codes_simd(codes, l_seq, dst) : 0, l_seq, dst);
+    memset(dst + sb, 0, sb16 - sb);
   }
-  if (i < l_seq) { uint8_t v = 0; for (int32_t k = i; k < l_seq; k++) v |= (uint8_t)((codes[k] & 3) << (2 * (k & 3))); dst[i >> 2] = v; }
-  /* bases outside A/C/G/T (soft clips only, checked above) are stored as code 0, like the Python packer */
-  for (int32_t k = 0; k < R->lead; k++) if (codes[k] == 0xff) dst[k >> 2] &= (uint8_t)~(3u << (2 * (k & 3)));
-  for (int32_t k = l_seq - R->trail; k < l_seq; k++) if (codes[k] == 0xff) dst[k >> 2] &= (uint8_t)~(3u << (2 * (k & 3)));
-  memset(dst + sb, 0, sb16 - sb);
   memcpy(b->bq + R->bq_off, qual, (size_t)l_seq);
   memset(b->bq + R->bq_off + l_seq, 0, qb16 - (size_t)l_seq);
 }
@@ -573,6 +621,12 @@ static void* decode_worker(void* arg) {
   }
   free(codes);
   return NULL;
+}
+
+int hm_bam_set_option(hm_bam* b, int option, int value) {
+  if (!b) return HM_ERR_ARG;
+  if (option == HM_BAM_OPT_NO_SEQ) { b->no_seq = value != 0; return HM_OK; }
+  return fail(b, "unknown option%s (%ld)", NULL, (long)option);
 }
 
 int hm_bam_read_batch(hm_bam* b, int rid, int32_t start, int32_t end, int threads, hm_read_batch* out) {
@@ -688,11 +742,12 @@ int hm_bam_read_batch(hm_bam* b, int rid, int32_t start, int32_t end, int thread
         b->tstart[n_reads] = pos; b->qstart[n_reads] = lead; b->qlen[n_reads] = l_seq;
         b->mapq[n_reads] = (uint8_t)mapq; b->flags[n_reads] = 0; b->qname_id[n_reads] = (uint32_t)id;
         b->seq_off[n_reads] = n_seq; b->bq_off[n_reads] = n_bq;
-        n_seq += sb16; n_bq += qb16; seg_ops += strlen(cs) / 2 + 2; n_reads++;
+        if (!b->no_seq) n_seq += sb16;
+        n_bq += qb16; seg_ops += strlen(cs) / 2 + 2; n_reads++;
       }
       if (rc) break;
       if (nsel) {
-        GROW(b->seq, b->cap_seq, n_seq + 16, uint8_t);
+        if (!b->no_seq) GROW(b->seq, b->cap_seq, n_seq + 16, uint8_t);
         GROW(b->bq, b->cap_bq, n_bq + 16, uint8_t);
         GROW(b->ops, b->cap_ops, n_ops + seg_ops + 4, uint32_t);
         g_phase[4] += now_s() - tA; tA = now_s();
@@ -727,13 +782,14 @@ int hm_bam_read_batch(hm_bam* b, int rid, int32_t start, int32_t end, int thread
     if (rc) return rc;
   }
 finish:
-  if (n_seq == 0) { GROW(b->seq, b->cap_seq, 16, uint8_t); memset(b->seq, 0, 16); n_seq = 16; }
+  if (n_seq == 0 && !b->no_seq) { GROW(b->seq, b->cap_seq, 16, uint8_t); memset(b->seq, 0, 16); n_seq = 16; }
   if (n_bq == 0) { GROW(b->bq, b->cap_bq, 16, uint8_t); memset(b->bq, 0, 16); n_bq = 16; }
   out->n_reads = n_reads;
   out->tstart = b->tstart; out->tend = b->tend; out->qstart = b->qstart; out->qlen = b->qlen; out->mapq = b->mapq;
   out->flags = b->flags; out->qname_id = b->qname_id; out->seq_off = b->seq_off; out->bq_off = b->bq_off;
   out->op_off = b->op_off; out->n_ops = b->n_ops; out->seq = b->seq; out->seq_bytes = n_seq; out->bq = b->bq;
   out->bq_bytes = n_bq; out->ops = b->ops; out->n_ops_total = n_ops;
+  if (b->no_seq) { out->seq = NULL; out->seq_off = NULL; out->seq_bytes = 0; } /* himut_b200.h: a batch without a base stream */
   b->batch = *out;
   return HM_OK;
 }

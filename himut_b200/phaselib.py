@@ -37,9 +37,9 @@ def get_edges(chrom, bam_file, min_bq, min_mapq, hpos_lst, hetsnp_lst, hetsnp2hi
             need, lo = 0, 0
             while lo < length and not need:
                 hi = min(length, lo + worker.GROUP_SPAN)
-                batch, _ = src.batch(chrom, [(chrom, lo, hi)])
+                batch, _ = src.batch(chrom, [(chrom, lo, hi)], seq=False)  # a cs match at a hetSNP carries its reference allele
                 if batch.n_reads:
-                    ctx.upload(batch.without_seq())  # a cs match at a hetSNP carries its reference allele
+                    ctx.upload(batch)
                     need = ctx.phase_edges_add(min_bq, min_mapq, lo if lo else -2**31)
                 lo = hi
             if not need:

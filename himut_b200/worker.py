@@ -64,10 +64,11 @@ class RegionSource:
         # (num_ccs counts distinct names per contig)
         self.reader = bamdec.NativeBam(bam_file)
 
-    def batch(self, chrom, chunkloci, phase_sets=None):
+    def batch(self, chrom, chunkloci, phase_sets=None, seq=True):
+        """seq=False: without the 2-bit base stream (`call`, phase edges: ReadBatch.without_seq says why)"""
         lo = min(s for _, s, _e in chunkloci)
         hi = max(e for _, _s, e in chunkloci)
-        batch = self.reader.read_batch(chrom, lo, hi, copy=False)
+        batch = self.reader.read_batch(chrom, lo, hi, copy=False, seq=seq)
         table = batch.chunk_table([(s, e) for _, s, e in chunkloci], phase_sets)
         return batch, table
 

@@ -45,6 +45,12 @@ int hm_bam_ref_len(const hm_bam* b, int i);
  * substituted base, cs spans that disagree with the CIGAR.  `threads` = inflate threads. */
 int hm_bam_read_batch(hm_bam* b, int rid, int32_t start, int32_t end, int threads, hm_read_batch* out);
 
+/* HM_BAM_OPT_NO_SEQ = 1: batches come without the 2-bit base stream (seq = NULL, seq_off = NULL, seq_bytes = 0; see
+ * hm_read_batch in himut_b200.h) — `call` and the phase edges do not need it; every check on the bases (A/C/G/T under
+ * a cs match, long-form cs against SEQ) is still made.  Default 0. */
+#define HM_BAM_OPT_NO_SEQ 1
+int hm_bam_set_option(hm_bam* b, int option, int value);
+
 /* BAM pre-pass of bamlib.get_thresholds (reference src/himut/bamlib.py:137-178): len(query_sequence) of
  * every record of contig `rid` that overlaps [start, end) with mapping_quality > 0 and tp:A:P, in fetch
  * order (secondary / supplementary records included: the reference does not test the flag there).  Only

@@ -144,3 +144,48 @@ def test_native_writer_equals_python_writer(tmp_path):
         assert [key(r) for r in a.fetch("chr1", s, e)] == [key(r) for r in b.fetch("chr1", s, e)]
     nb = bamdec.NativeBam(p_c, threads=2)
     assert cases.batch_digest(nb.read_batch("chr1", 0, 150_000)) == cases.batch_digest(d.batch)
+
+
+def test_batch_without_base_stream(tmp_path):
+    """HM_BAM_OPT_NO_SEQ: everything but seq / seq_off is what the full decode gives, the base checks stay"""
+    d = synth.generate(200_000, seed=15, softclip_frac=0.2)
+    path = str(tmp_path / "t.bam")
+    bamio.write_batch_bam(path, "chr1", 200_000, d.batch)
+    nb = bamdec.NativeBam(path, threads=2)
+    full = nb.read_batch("chr1", 0, 200_000)
+    bare = nb.read_batch("chr1", 0, 200_000, seq=False)
+    assert bare.seq.size == 0 and bare.seq_off.size == 0
+    s = bare.as_struct()
+    assert s.seq is None and s.seq_off is None and s.seq_bytes == 0
+    for name, _ in full._FIELDS:
+        if name not in ("seq", "seq_off"):
+            assert np.array_equal(getattr(full, name), getattr(bare, name)), name
+    assert np.array_equal(nb.read_batch("chr1", 0, 200_000).seq, full.seq)  # and back
+    # a base outside A/C/G/T under a cs match is still refused
+    bad = str(tmp_path / "bad.bam")
+    _write(bad, [_rec(pos=10, cigar=((0, 6),), seq="ACNTAC", cs=":6", qname="n_under_match")])
+    nb2 = bamdec.NativeBam(bad, threads=1)
+    with pytest.raises(pack.BatchFormatError):
+        nb2.read_batch("chr1", 0, 1000, seq=False)
+
+
+def test_base_conversion_at_every_length(tmp_path):
+    """the decoder converts 4-bit bases 32 at a time and packs 2-bit codes 16 at a time with a scalar tail: records of
+    every length from 1 to 150 with N / IUPAC letters in their soft clips must pack like the Python packer"""
+    import random
+    rnd = random.Random(9)
+    recs = []
+    for n in range(1, 151):
+        lead, trail = rnd.randrange(0, 4), rnd.randrange(0, 4)
+        m = max(1, n - lead - trail)
+        clip = lambda k: "".join(rnd.choice("ACGTNRY") for _ in range(k))
+        body = "".join(rnd.choice("ACGT") for _ in range(m))
+        cigar = ([(4, lead)] if lead else []) + [(0, m)] + ([(4, trail)] if trail else [])
+        recs.append(_rec(pos=10 + n, cigar=cigar, seq=clip(lead) + body + clip(trail), cs=":%d" % m, qname="r%d" % n))
+    path = str(tmp_path / "len.bam")
+    _write(path, recs)
+    nb = bamdec.NativeBam(path, threads=2)
+    bb = pack.BatchBuilder()
+    got = nb.read_batch("chr1", 0, 1000)
+    _same(got, bamio.read_batch(bamio.BamReader(path), "chr1", 0, 1000, builder=bb))
+    assert got.n_reads == 150
