@@ -194,25 +194,50 @@ static void* inflate_worker(void* arg) {
     j->next += j->grab; /* a few blocks per grab */
     pthread_mutex_unlock(&j->mu);
     if (i0 >= j->n_blocks) break;
-    for (size_t i = i0; i < i0 + j->grab && i < j->n_blocks; i++) {
-      const blk_t* b = &j->blocks[i];
-      const uint8_t* src = j->comp + b->coff;
-      uint16_t xlen = (uint16_t)(src[10] | (src[11] << 8));
-      if (b->usize == 0) continue;
-      const uint8_t* payload = src + 12 + xlen;
-      const size_t payload_len = b->csize - 12 - xlen - 8;
-      const uint32_t want_crc = rd32(src + b->csize - 8);
-      uint8_t* dst = j->out + b->uoff;
-      /* own decoder first (inflate_fast.h); zlib when it declines or the CRC disagrees */
-      if (!j->zlib_only && hm_inflate_raw(payload, payload_len, dst, b->usize) == 0 &&
-          block_crc(dst, b->usize) == want_crc)
-        continue;
-      inflateReset(&zs);
-      zs.next_in = (Bytef*)payload;
-      zs.avail_in = (uInt)payload_len;
-      zs.next_out = dst;
-      zs.avail_out = b->usize;
-      if (inflate(&zs, Z_FINISH) != Z_STREAM_END || block_crc(dst, b->usize) != want_crc) { j->error = 1; break; }
+    /* own decoder first (inflate_fast.h), two blocks at a time so their dependency chains overlap; zlib when it
+     * declines a block or the CRC disagrees */
+    const size_t i_end = i0 + j->grab < j->n_blocks ? i0 + j->grab : j->n_blocks;
+    for (size_t i = i0; i < i_end; i += 2) {
+      const size_t n_here = i + 1 < i_end ? 2 : 1;
+      const uint8_t* payload[2] = {NULL, NULL};
+      size_t payload_len[2] = {0, 0};
+      uint8_t* dst[2] = {NULL, NULL};
+      uint32_t want_crc[2] = {0, 0};
+      int ok[2] = {0, 0};
+      for (size_t k = 0; k < n_here; k++) {
+        const blk_t* b = &j->blocks[i + k];
+        const uint8_t* src = j->comp + b->coff;
+        const uint16_t xlen = (uint16_t)(src[10] | (src[11] << 8));
+        payload[k] = src + 12 + xlen;
+        payload_len[k] = b->csize - 12 - xlen - 8;
+        want_crc[k] = rd32(src + b->csize - 8);
+        dst[k] = j->out + b->uoff;
+        if (b->usize == 0) ok[k] = 1; /* the empty end-of-file block */
+      }
+      if (!j->zlib_only) {
+        if (n_here == 2 && !ok[0] && !ok[1]) {
+          int rc[2];
+          hm_inflate_raw2(payload[0], payload_len[0], dst[0], j->blocks[i].usize, payload[1], payload_len[1], dst[1], j->blocks[i + 1].usize, rc);
+          ok[0] = rc[0] == 0; ok[1] = rc[1] == 0;
+        } else {
+          for (size_t k = 0; k < n_here; k++)
+            if (!ok[k]) ok[k] = hm_inflate_raw(payload[k], payload_len[k], dst[k], j->blocks[i + k].usize) == 0;
+        }
+        for (size_t k = 0; k < n_here; k++)
+          if (ok[k] && j->blocks[i + k].usize) ok[k] = block_crc(dst[k], j->blocks[i + k].usize) == want_crc[k];
+      }
+      for (size_t k = 0; k < n_here && !j->error; k++) {
+        if (ok[k]) continue;
+        const blk_t* b = &j->blocks[i + k];
+        if (b->usize == 0) continue;
+        inflateReset(&zs);
+        zs.next_in = (Bytef*)payload[k];
+        zs.avail_in = (uInt)payload_len[k];
+        zs.next_out = dst[k];
+        zs.avail_out = b->usize;
+        if (inflate(&zs, Z_FINISH) != Z_STREAM_END || block_crc(dst[k], b->usize) != want_crc[k]) j->error = 1;
+      }
+      if (j->error) break;
     }
     if (j->error) break;
   }
@@ -1166,4 +1191,10 @@ void hm_bq_compact_free(uint8_t* exc) { free(exc); }
 
 /* test hook: the raw DEFLATE decoder of inflate_fast.h on one stream (0 = ok) */
 int hm_inflate_raw_test(const uint8_t* in, size_t in_len, uint8_t* out, size_t out_len) { return hm_inflate_raw(in, in_len, out, out_len); }
+int hm_inflate_raw2_test(const uint8_t* in0, size_t in_len0, uint8_t* out0, size_t out_len0, const uint8_t* in1, size_t in_len1, uint8_t* out1,
+                         size_t out_len1) {
+  int rc[2];
+  hm_inflate_raw2(in0, in_len0, out0, out_len0, in1, in_len1, out1, out_len1, rc);
+  return (rc[0] ? 1 : 0) | (rc[1] ? 2 : 0);
+}
 

@@ -98,3 +98,41 @@ def test_block_crc_equals_zlib():
         assert lib.hm_crc32_test(data, n) == zlib.crc32(data), n
     for data in (b"\x00" * 1000, b"\xff" * 4097, bytes(range(256)) * 37):
         assert lib.hm_crc32_test(data, len(data)) == zlib.crc32(data)
+
+
+def _inflate2(c0, n0, c1, n1):
+    lib = C.CDLL(bamdec.lib_path())
+    vp = C.c_void_p
+    lib.hm_inflate_raw2_test.argtypes = [C.c_char_p, C.c_size_t, vp, C.c_size_t, C.c_char_p, C.c_size_t, vp, C.c_size_t]
+    o0, o1 = np.zeros(max(n0, 1), np.uint8), np.zeros(max(n1, 1), np.uint8)
+    rc = lib.hm_inflate_raw2_test(c0, len(c0), o0.ctypes.data_as(vp), n0, c1, len(c1), o1.ctypes.data_as(vp), n1)
+    return rc, o0[:n0].tobytes(), o1[:n1].tobytes()
+
+
+@pytest.mark.parametrize("level", [1, 6])
+def test_two_streams_in_one_loop_match_zlib(level):
+    """the BGZF workers inflate two blocks at a time (hm_inflate_raw2: both streams advance in one loop); every
+    pairing of the payload kinds, in both orders, so the streams end, stall on rare codes and leave their fast
+    regions at different times"""
+    items = [(d, _raw_deflate(d, level)) for d in _payloads()]
+    items.append((items[6][0], _raw_deflate(items[6][0], 6, zlib.Z_FIXED)))
+    for d0, c0 in items:
+        for d1, c1 in items:
+            rc, g0, g1 = _inflate2(c0, len(d0), c1, len(d1))
+            assert rc == 0 and g0 == d0 and g1 == d1, (len(d0), len(d1))
+
+
+def test_two_streams_fail_independently():
+    rnd = random.Random(8)
+    good = bytes(rnd.choice(b"ACGT") for _ in range(30_000))
+    other = bytes([93] * 10 + [20]) * 3000
+    cg, co = _raw_deflate(good, 6), _raw_deflate(other, 1)
+    assert _inflate2(cg, len(good), co, len(other) - 1)[0] == 2      # second stream: wrong size
+    assert _inflate2(cg[:100], len(good), co, len(other))[0] == 1    # first stream: truncated
+    rc, g0, g1 = _inflate2(cg, len(good), co[: len(co) // 2], len(other))
+    assert rc == 2 and g0 == good
+    for _ in range(200):                                              # corrupted: no crash; wrong bytes are the CRC's job
+        bad = bytearray(co)
+        bad[rnd.randrange(len(bad))] ^= 1 << rnd.randrange(8)
+        rc, g0, _ = _inflate2(cg, len(good), bytes(bad), len(other))
+        assert (rc & 1) == 0 and g0 == good
