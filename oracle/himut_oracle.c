@@ -376,11 +376,13 @@ static size_t fetch_reads(const hm_read_batch* b, const hm_chunk* c, uint64_t* F
 /* ---------------------------------------------------------------- `himut call` ------- */
 /* caller.get_somatic_substitutions (caller.py:243-641).  Emits one record per evaluated
  * candidate, germline restatements included (status HM_ST_GERM_*), in chunk order. */
-int orc_call_chunks(const hm_params* p, const hm_read_batch* b, const hm_chunk* chunks,
-                    size_t n_chunks, const uint64_t* common, size_t n_common,
-                    const uint64_t* pon, size_t n_pon, const orc_phase* ph,
-                    hm_site_record* out, size_t cap, size_t* n_out,
-                    int64_t log[HM_CALL_LOG_LEN]) {
+/* qseen (may be NULL): one flag per qname_id, set where a record with that id passed the read gates — the set
+ * m.num_ccs counts (caller.py:318-320), which a worker that feeds a contig in several batches has to carry */
+int orc_call_chunks_seen(const hm_params* p, const hm_read_batch* b, const hm_chunk* chunks,
+                         size_t n_chunks, const uint64_t* common, size_t n_common,
+                         const uint64_t* pon, size_t n_pon, const orc_phase* ph,
+                         hm_site_record* out, size_t cap, size_t* n_out,
+                         int64_t log[HM_CALL_LOG_LEN], uint8_t* qseen, size_t qseen_cap) {
   int rc = HM_OK, bq_zero = 0;
   size_t nrec = 0;
   memset(log, 0, sizeof(int64_t) * HM_CALL_LOG_LEN);
@@ -543,6 +545,8 @@ int orc_call_chunks(const hm_params* p, const hm_read_batch* b, const hm_chunk* 
     pile_free(&P);
   }
 done:
+  if (qseen)
+    for (size_t q = 0; q <= (size_t)max_qid && q < qseen_cap; q++) qseen[q] = (uint8_t)bitset_get(&ccs_seen, q);
   free(F); free(hap); free(mm); free(cand); free(pmax);
   free(som_seen.w); free(ccs_seen.w);
   if (n_out) *n_out = nrec;
@@ -550,6 +554,14 @@ done:
   if (bq_zero) return HM_ERR_BQ_ZERO;
   if (nrec > cap) return HM_ERR_CAPACITY;
   return HM_OK;
+}
+
+int orc_call_chunks(const hm_params* p, const hm_read_batch* b, const hm_chunk* chunks,
+                    size_t n_chunks, const uint64_t* common, size_t n_common,
+                    const uint64_t* pon, size_t n_pon, const orc_phase* ph,
+                    hm_site_record* out, size_t cap, size_t* n_out,
+                    int64_t log[HM_CALL_LOG_LEN]) {
+  return orc_call_chunks_seen(p, b, chunks, n_chunks, common, n_common, pon, n_pon, ph, out, cap, n_out, log, NULL, 0);
 }
 
 /* ---------------------------------------------------------------- `himut normcounts` - */
@@ -573,12 +585,12 @@ static inline int ascii2code(uint8_t ch) {
 
 /* alt_order[ref][0..2]: iteration order of list(base_set.difference(ref)) in the reference
  * (normcounts.py:370) — hash-seed dependent there; pass NULL for the canonical A,T,G,C order. */
-int orc_normcounts_chunks(const hm_params* p, const hm_read_batch* b, const uint8_t* refseq,
-                          size_t ref_len, const hm_chunk* chunks, size_t n_chunks,
-                          const uint64_t* common, size_t n_common, const uint64_t* pon,
-                          size_t n_pon, const orc_phase* ph, const uint8_t* alt_order,
-                          int64_t ccs_tri[HM_TRI_BINS], int64_t ref_tri[HM_TRI_BINS],
-                          int64_t log[HM_NORM_LOG_LEN], int64_t* n_alt_tie) {
+int orc_normcounts_chunks_seen(const hm_params* p, const hm_read_batch* b, const uint8_t* refseq,
+                               size_t ref_len, const hm_chunk* chunks, size_t n_chunks,
+                               const uint64_t* common, size_t n_common, const uint64_t* pon,
+                               size_t n_pon, const orc_phase* ph, const uint8_t* alt_order,
+                               int64_t ccs_tri[HM_TRI_BINS], int64_t ref_tri[HM_TRI_BINS],
+                               int64_t log[HM_NORM_LOG_LEN], int64_t* n_alt_tie, uint8_t* qseen, size_t qseen_cap) {
   int rc = HM_OK, bq_zero = 0;
   int64_t ties = 0;
   memset(ccs_tri, 0, sizeof(int64_t) * HM_TRI_BINS);
@@ -723,10 +735,22 @@ int orc_normcounts_chunks(const hm_params* p, const hm_read_batch* b, const uint
     pile_free(&P);
   }
 done:
+  if (qseen) /* as in orc_call_chunks_seen */
+    for (size_t q = 0; q <= (size_t)max_qid && q < qseen_cap; q++) qseen[q] = (uint8_t)bitset_get(&seen, q);
   free(F); free(hap); free(mm); free(seen.w);
   if (n_alt_tie) *n_alt_tie = ties;
   if (rc != HM_OK) return rc;
   return bq_zero ? HM_ERR_BQ_ZERO : HM_OK;
+}
+
+int orc_normcounts_chunks(const hm_params* p, const hm_read_batch* b, const uint8_t* refseq,
+                          size_t ref_len, const hm_chunk* chunks, size_t n_chunks,
+                          const uint64_t* common, size_t n_common, const uint64_t* pon,
+                          size_t n_pon, const orc_phase* ph, const uint8_t* alt_order,
+                          int64_t ccs_tri[HM_TRI_BINS], int64_t ref_tri[HM_TRI_BINS],
+                          int64_t log[HM_NORM_LOG_LEN], int64_t* n_alt_tie) {
+  return orc_normcounts_chunks_seen(p, b, refseq, ref_len, chunks, n_chunks, common, n_common, pon, n_pon, ph, alt_order,
+                                    ccs_tri, ref_tri, log, n_alt_tie, NULL, 0);
 }
 
 /* ---------------------------------------------------------------- reference tri counts */

@@ -57,8 +57,9 @@ def read_stats(batch):
     return out
 
 
-def call_chunks(params, batch, chunks, common=None, pon=None, phase=None, cap=None):
-    """-> (records: structured array abi.SITE_DTYPE, log[15]) ; raises on error"""
+def call_chunks(params, batch, chunks, common=None, pon=None, phase=None, cap=None, qseen=None):
+    """-> (records: structured array abi.SITE_DTYPE, log[15]) ; raises on error.
+    qseen: optional uint8 array, one flag per qname_id, filled with the query names that passed the read gates"""
     common = np.zeros(0, np.uint64) if common is None else np.ascontiguousarray(common, np.uint64)
     pon = np.zeros(0, np.uint64) if pon is None else np.ascontiguousarray(pon, np.uint64)
     chunks = np.ascontiguousarray(chunks, dtype=abi.CHUNK_DTYPE)
@@ -67,16 +68,17 @@ def call_chunks(params, batch, chunks, common=None, pon=None, phase=None, cap=No
     out = np.zeros(cap, dtype=abi.SITE_DTYPE)
     n_out = C.c_size_t(0)
     log = np.zeros(abi.CALL_LOG_LEN, np.int64)
-    rc = lib().orc_call_chunks(
+    rc = lib().orc_call_chunks_seen(
         C.byref(params), C.byref(batch.as_struct()), _p(chunks), C.c_size_t(len(chunks)),
         _p(common), C.c_size_t(common.size), _p(pon), C.c_size_t(pon.size),
-        C.byref(ph) if ph is not None else None, _p(out), C.c_size_t(cap), C.byref(n_out), _p(log))
+        C.byref(ph) if ph is not None else None, _p(out), C.c_size_t(cap), C.byref(n_out), _p(log),
+        None if qseen is None else _p(qseen), C.c_size_t(0 if qseen is None else qseen.size))
     if rc != 0:
         raise RuntimeError("orc_call_chunks failed: %d" % rc)
     return out[: n_out.value].copy(), log
 
 
-def normcounts_chunks(params, batch, refseq, chunks, common=None, pon=None, phase=None, alt_order=None):
+def normcounts_chunks(params, batch, refseq, chunks, common=None, pon=None, phase=None, alt_order=None, qseen=None):
     """-> (ccs_tri[33], ref_tri[33], log[14], n_alt_tie)"""
     common = np.zeros(0, np.uint64) if common is None else np.ascontiguousarray(common, np.uint64)
     pon = np.zeros(0, np.uint64) if pon is None else np.ascontiguousarray(pon, np.uint64)
@@ -88,10 +90,11 @@ def normcounts_chunks(params, batch, refseq, chunks, common=None, pon=None, phas
     rt = np.zeros(abi.TRI_BINS, np.int64)
     log = np.zeros(abi.NORM_LOG_LEN, np.int64)
     ties = C.c_int64(0)
-    rc = lib().orc_normcounts_chunks(
+    rc = lib().orc_normcounts_chunks_seen(
         C.byref(params), C.byref(batch.as_struct()), _p(ref), C.c_size_t(ref.size), _p(chunks),
         C.c_size_t(len(chunks)), _p(common), C.c_size_t(common.size), _p(pon), C.c_size_t(pon.size),
-        C.byref(ph) if ph is not None else None, _p(ao), _p(ccs), _p(rt), _p(log), C.byref(ties))
+        C.byref(ph) if ph is not None else None, _p(ao), _p(ccs), _p(rt), _p(log), C.byref(ties),
+        None if qseen is None else _p(qseen), C.c_size_t(0 if qseen is None else qseen.size))
     if rc != 0:
         raise RuntimeError("orc_normcounts_chunks failed: %d" % rc)
     return ccs, rt, log, ties.value

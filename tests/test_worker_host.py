@@ -1,0 +1,173 @@
+"""Host logic of the drop-in workers on the CPU: himut_b200.caller / normcounts / phaselib run here against a
+stand-in context whose device calls are answered by the oracle (test infrastructure only), through real BAM files
+and the native decoder, and must reproduce the reference's own outputs (tests/golden/).  What this pins without a
+GPU: chunk grouping, the som_seen and distinct-read carry across groups, the log vector, rows and their order, the
+tri-count dictionaries.  The same workers with the real context are tests/test_gpu_worker.py."""
+import importlib.util
+import os
+
+import numpy as np
+import pytest
+
+import cases
+import parity
+from himut_b200 import abi, bamio, caller, normcounts, phaselib, worker
+from oracle import oracle
+
+
+class OracleContext:
+    """the part of lib.Context the workers use, answered by the oracle"""
+
+    def __init__(self):
+        self.params = self.batch = self.phase = None
+        self.common = self.pon = None
+        self.uploads = 0
+
+    def set_params(self, p):
+        self.params = p
+
+    def set_site_sets(self, common=None, pon=None):
+        self.common, self.pon = common, pon
+
+    def set_phase_sets(self, table):
+        self.phase = table
+
+    def upload(self, batch):
+        assert batch.seq.size, "the oracle reads the bases: the test asks the decoder for them"
+        self.batch = batch
+        self.uploads += 1
+
+    def call_chunks(self, table):
+        self._seen = np.zeros(int(self.batch.qname_id.max()) + 1 if self.batch.n_reads else 1, np.uint8)
+        return oracle.call_chunks(self.params, self.batch, table, self.common, self.pon, self.phase, qseen=self._seen)
+
+    def qname_seen(self):
+        return self._seen
+
+    def normcounts_chunks(self, refseq, table):
+        self._seen = np.zeros(int(self.batch.qname_id.max()) + 1 if self.batch.n_reads else 1, np.uint8)
+        ref = refseq.encode() if isinstance(refseq, str) else refseq
+        return oracle.normcounts_chunks(self.params, self.batch, ref, table, self.common, self.pon, self.phase, qseen=self._seen)
+
+    def phase_edges_begin(self, hpos, href, band):
+        self._edges = (np.ascontiguousarray(hpos, np.int32), np.ascontiguousarray(href, np.uint8), int(band))
+        self._table = np.zeros((len(hpos), int(band), 4), np.uint32)
+
+    def phase_edges_add(self, min_bq, min_mapq, min_tstart=-2**31):
+        hpos, href, band = self._edges
+        counts, need = oracle.phase_edges(self.batch, hpos, href, band, min_bq, min_mapq, min_tstart)
+        if need:
+            return int(need)
+        self._table += counts
+        return 0
+
+    def phase_edges_end(self):
+        return self._table
+
+
+@pytest.fixture
+def octx(monkeypatch):
+    ctx = OracleContext()
+    monkeypatch.setattr(worker, "context", lambda: ctx)
+    plain = worker.RegionSource.batch
+    monkeypatch.setattr(worker.RegionSource, "batch",
+                        lambda self, chrom, loci, phase_sets=None, seq=True: plain(self, chrom, loci, phase_sets, seq=True))
+    return ctx
+
+
+def _inputs(c, tmp_path):
+    bam = str(tmp_path / (c["name"] + ".bam"))
+    bamio.write_batch_bam(bam, cases.CHROM, c["contig_len"], c["batch"])
+    common = pon = None
+    if c["common_vcf"].size:
+        common = str(tmp_path / "common.vcf.bgz")
+        cases.write_sites_vcf(common, cases.CHROM, c["common_vcf"])
+    if c["pon_vcf"].size:
+        pon = str(tmp_path / "pon.vcf.bgz")
+        cases.write_sites_vcf(pon, cases.CHROM, c["pon_vcf"])
+    return bam, common, pon
+
+
+def _run_call(c, tmp_path):
+    a = c["args"]
+    bam, common, pon = _inputs(c, tmp_path)
+    hbit, hpos, hetsnp = cases.phase_dicts(c)
+    lst, log = {}, {}
+    caller.get_somatic_substitutions(
+        cases.CHROM, bam, common, pon, [(cases.CHROM, s, e) for s, e in c["chunks"]], hbit, hpos, hetsnp,
+        a["min_qv"], a["min_mapq"], a["qlen_lower_limit"], a["qlen_upper_limit"], a["min_sequence_identity"],
+        a["min_gq"], a["min_bq"], a["min_trim"], a["max_mismatch_count"], a["mismatch_window"], a["md_threshold"],
+        a["min_ref_count"], a["min_alt_count"], a["min_hap_count"], 1e-6, a["germline_snv_prior"], 1e-4,
+        bool(a.get("phase")), bool(a.get("non_human_sample")), bool(a.get("create_panel_of_normals")), lst, log)
+    return lst[cases.CHROM], log[cases.CHROM]
+
+
+@pytest.mark.parametrize("name", ["call_basic", "call_sets", "call_pon_params", "call_phase", "call_adversarial_a"])
+def test_call_worker_host_logic(octx, name, tmp_path):
+    c = cases.build_case(name)
+    fx = parity.load_golden(name)
+    rows, log = _run_call(c, tmp_path)
+    gold = parity.golden_rows(fx)
+    assert parity.rows_equal(rows, gold), parity.first_diff(rows, gold)
+    assert log == fx["expected"]["log"]
+
+
+@pytest.mark.parametrize("span", [700, 1200, 2500])
+def test_call_worker_group_carry_on_cpu(octx, tmp_path, monkeypatch, span):
+    """a contig fed to the device in several batches: som_seen and the distinct-read count carry across them"""
+    monkeypatch.setattr(worker, "GROUP_SPAN", span)
+    for name in ("call_adversarial_a", "call_adversarial_b"):
+        c = cases.build_case(name)
+        fx = parity.load_golden(name)
+        before = octx.uploads
+        rows, log = _run_call(c, tmp_path)
+        assert octx.uploads - before > 1
+        gold = parity.golden_rows(fx)
+        assert parity.rows_equal(rows, gold), (name, parity.first_diff(rows, gold))
+        assert log == fx["expected"]["log"], name
+
+
+@pytest.mark.parametrize("name", ["norm_basic", "norm_phase", "norm_adversarial"])
+def test_normcounts_worker_host_logic(octx, name, tmp_path, monkeypatch):
+    if name == "norm_adversarial":
+        monkeypatch.setattr(worker, "GROUP_SPAN", 1200)
+    c = cases.build_case(name)
+    e = parity.load_golden(name)["expected"]
+    a = c["args"]
+    bam, common, pon = _inputs(c, tmp_path)
+    hbit, hpos, hetsnp = cases.phase_dicts(c)
+    ccs, rt, log = {}, {}, {}
+    ties = normcounts.get_callable_tricounts(
+        cases.CHROM, c["ref"], bam, common, pon, [(cases.CHROM, s, e2) for s, e2 in c["chunks"]], hbit, hpos, hetsnp,
+        a["min_qv"], a["min_mapq"], a["min_trim"], a["qlen_lower_limit"], a["qlen_upper_limit"],
+        a["min_sequence_identity"], a["min_gq"], a["min_bq"], a["mismatch_window"], a["max_mismatch_count"],
+        a["min_ref_count"], a["min_alt_count"], a["min_hap_count"], float(a["md_threshold"]), 1e-6,
+        a["germline_snv_prior"], 1e-4, bool(a.get("phase")), bool(a.get("non_human_sample")), ccs, rt, log)
+    if ties:
+        pytest.skip("%d alt ties: the reference's own result depends on PYTHONHASHSEED here" % ties)
+    for tri in normcounts.TRI_LST:
+        assert ccs[cases.CHROM][tri] == e["ccs_tri2count"].get(tri, 0), tri
+        assert rt[cases.CHROM][tri] == e["ref_tri2count"].get(tri, 0), tri
+    assert log[cases.CHROM] == e["log"]
+
+
+_spec = importlib.util.spec_from_file_location("mkedges_host", os.path.join(cases.GOLDEN_DIR, "make_golden_edges.py"))
+mk_edges = importlib.util.module_from_spec(_spec)
+_spec.loader.exec_module(mk_edges)
+
+
+@pytest.mark.parametrize("name", ["plain", "bq0_counts_deletions"])
+@pytest.mark.parametrize("span", [37_000, 10_000_000])
+def test_phase_edge_worker_host_logic(octx, tmp_path, monkeypatch, name, span):
+    """phaselib.get_edges over several decode windows (a read shared by two windows counts once) and the band
+    retry, against the reference's own get_edges output"""
+    import json
+    from himut_b200 import bamdec
+    batch, hetsnp_lst, h2i, n, min_bq, min_mapq = mk_edges.inputs(name)
+    path = str(tmp_path / "e.bam")
+    bamdec.write_batch_bam(path, "chr1", n, batch)
+    monkeypatch.setattr(worker, "GROUP_SPAN", span)
+    edge_lst, e2c = phaselib.get_edges("chr1", path, min_bq, min_mapq, [h[0] for h in hetsnp_lst], hetsnp_lst, h2i)
+    got = [[int(i), int(j)] + [int(v) for v in e2c[(i, j)]] for (i, j) in edge_lst]
+    assert got == json.load(open(os.path.join(cases.GOLDEN_DIR, "edges.json")))["expected"][name]
+    assert all(isinstance(v, np.ndarray) and v.dtype == np.float64 for v in e2c.values())
