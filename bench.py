@@ -447,7 +447,10 @@ def main():
     # ---------------- BAM on disk -> site records (decode included), rank 0, a separate 8 Mb contig ----------------
     bam_leg = None
     if rank == 0 and not args.no_bam_leg:
-        bam_leg = bam_to_records(ctx, params, args.bam_mb, args.seed)
+        try:
+            bam_leg = bam_to_records(ctx, params, args.bam_mb, args.seed)
+        except Exception as ex:  # a side measurement: never costs the line
+            bam_leg = {"error": repr(ex)}
 
     # ---------------- reduce over ranks ----------------
     t = torch.tensor([ms_total, ms_e2e, ms_e2e_plain, ms_e2e_ns], device=dev, dtype=torch.float64)

@@ -406,6 +406,7 @@ void hm_bam_close(hm_bam* b) {
 int hm_bam_open(const char* path, hm_bam** out) {
   if (!path || !out) return HM_ERR_ARG;
   *out = NULL;
+  (void)hi_use_run(); (void)hm_crc32_available(); /* one-time CPU probes and tables, before any worker thread exists */
   hm_bam* b = (hm_bam*)calloc(1, sizeof(hm_bam));
   if (!b) return HM_ERR_ARG;
   b->path = strdup(path);
