@@ -136,3 +136,19 @@ def test_two_streams_fail_independently():
         bad[rnd.randrange(len(bad))] ^= 1 << rnd.randrange(8)
         rc, g0, _ = _inflate2(cg, len(good), bytes(bad), len(other))
         assert (rc & 1) == 0 and g0 == good
+
+
+def test_sanitizer_fuzz_session(tmp_path):
+    """tools/fuzz_inflate.c under AddressSanitizer + UBSan: intact streams decode exactly (single and pair decoder),
+    damaged ones never touch memory outside their exact-size buffers"""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "fz")
+    cc = subprocess.run(["gcc", "-O1", "-g", "-std=c11", "-fsanitize=address,undefined", "-fno-sanitize-recover=undefined",
+                         "-I", os.path.join(root, "himut_b200", "csrc"), "-o", exe, os.path.join(root, "tools", "fuzz_inflate.c"), "-lz"],
+                        capture_output=True, text=True)
+    if cc.returncode != 0:
+        pytest.skip("no sanitizer runtime here: " + cc.stderr[-200:])
+    run = subprocess.run([exe, "400"], capture_output=True, text=True, timeout=300)
+    assert run.returncode == 0, run.stdout[-500:] + run.stderr[-2000:]
+    assert "iterations 3200" in run.stdout
