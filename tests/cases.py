@@ -324,3 +324,76 @@ def build_case(name):
     c["chunk_table"] = c["batch"].chunk_table(c["chunks"], c["phase_sets"])
     c["params"] = gtmodel.make_params(**c["args"])
     return c
+
+
+# ------------------------------------------------------------------------------------------
+# randomised sweep (tests/test_gpu_random.py: CUDA == oracle; tests/golden/make_golden_random.py +
+# tests/test_oracle_random.py: oracle == reference on the very same cases)
+# ------------------------------------------------------------------------------------------
+RANDOM_CALL_SEEDS = range(1000, 1030)
+RANDOM_NORM_SEEDS = range(2000, 2030)
+
+
+def random_setup(seed):
+    rnd = random.Random(seed)
+    n = rnd.choice([1500, 3000, 6000])
+    batch, ref = adversarial_batch(seed, contig_len=n, n_reads=rnd.choice([40, 120, 300]), max_len=rnd.choice([300, 900, 2000]))
+    args = call_args(
+        min_qv=rnd.choice([0, 20, 30]), min_mapq=rnd.choice([0, 20, 60]), qlen_lower_limit=rnd.choice([0, 30, 200]),
+        qlen_upper_limit=rnd.choice([500, 900, 5000]), min_sequence_identity=rnd.choice([0.0, 0.9, 0.99]),
+        min_gq=rnd.choice([0, 5, 20]), min_bq=rnd.choice([1, 30, 93]), min_trim=rnd.choice([0.0, 0.01, 0.1]),
+        max_mismatch_count=rnd.choice([0, 0, 1, 3]), mismatch_window=rnd.choice([0, 5, 20, 40]),
+        md_threshold=rnd.choice([10, 45, 1000]), min_ref_count=rnd.choice([0, 2, 5]), min_alt_count=rnd.choice([1, 2]),
+        min_hap_count=rnd.choice([0, 1, 3]), germline_snv_prior=rnd.choice([1e-3, 1e-2]))
+    # chunk list: sometimes the reference's own tiling, sometimes overlapping / unordered windows
+    if rnd.random() < 0.5:
+        cuts = sorted(rnd.sample(range(1, n), rnd.choice([1, 2, 4])))
+        edges = [0] + cuts + [n]
+        chunks = [(edges[i], edges[i + 1]) for i in range(len(edges) - 1)]
+    else:
+        chunks = []
+        for _ in range(rnd.choice([1, 3, 5])):
+            a = rnd.randrange(0, n - 10)
+            chunks.append((a, min(n, a + rnd.randrange(5, n))))
+    # site sets drawn from positions that exist
+    keys = [((rnd.randrange(1, n) << 4) | (rnd.randrange(4) << 2) | rnd.randrange(4)) for _ in range(n // 4)]
+    common = np.unique(np.array(keys[: len(keys) // 2], np.uint64))
+    pon = np.unique(np.array(keys[len(keys) // 2:], np.uint64))
+    return rnd, batch, ref, args, chunks, common, pon
+
+
+def random_phase(rnd, ref, chunks):
+    """one phase set per chunk: random hetSNPs inside the chunk's window (some with non-matching alleles)"""
+    hpos, href, halt, hbit, set_off, new_chunks = [], [], [], [], [0], []
+    for (s, e) in chunks:
+        cand = sorted(rnd.sample(range(max(s, 1), max(e, s + 2)), min(rnd.choice([2, 6, 20]), max(e - s - 1, 1))))
+        cand = [p for p in cand if ref[p - 1] in "ATGC"]
+        if len(cand) < 1:
+            continue
+        for p in cand:
+            r = "ATGC".index(ref[p - 1])
+            hpos.append(p); href.append(r); halt.append(rnd.choice([x for x in range(4) if x != r])); hbit.append(rnd.randrange(2))
+        set_off.append(len(hpos))
+        new_chunks.append((cand[0], cand[-1]))  # the reference's phase chunks: (first hpos, last hpos)
+    ph = dict(hpos=np.array(hpos, np.int32), href=np.array(href, np.uint8), halt=np.array(halt, np.uint8),
+              hbit=np.array(hbit, np.uint8), set_off=np.array(set_off, np.uint64))
+    return ph, new_chunks
+
+
+def random_case(kind, seed):
+    """the case dict (as build_case returns it) of one seed of the sweep, or None when the seed draws no phase set"""
+    rnd, batch, ref, args, chunks, common, pon = random_setup(seed)
+    if kind == "norm":
+        ref = "".join(c.lower() if rnd.random() < 0.02 else c for c in ref)
+    phase, sets = None, None
+    if seed % 3 == 0:
+        phase, chunks = random_phase(rnd, ref.upper(), chunks)
+        if not chunks:
+            return None
+        args["phase"] = True
+        sets = list(range(len(chunks)))
+    c = dict(name="rand_%s_%d" % (kind, seed), kind=kind, batch=batch, ref=ref, contig_len=len(ref), chunks=chunks,
+             args=args, common=common, pon=pon, common_vcf=common, pon_vcf=pon, phase=phase, phase_sets=sets)
+    c["chunk_table"] = batch.chunk_table(chunks, sets)
+    c["params"] = gtmodel.make_params(**args)
+    return c

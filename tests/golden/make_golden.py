@@ -40,9 +40,10 @@ write_sites_vcf = cases.write_sites_vcf
 phase_dicts = cases.phase_dicts
 
 
-def run_case(name, himut, tmp):
+def reference_outputs(c, himut, tmp):
+    """run the reference worker of case dict `c` (cases.build_case / cases.random_case) -> (expected dict, seconds)"""
     import pysam
-    c = cases.build_case(name)
+    name = c["name"]
     a = c["args"]
     bam = os.path.join(tmp, name + ".bam")
     pysam.register(bam, refshim.BatchProvider(cases.CHROM, c["contig_len"], c["batch"]))
@@ -84,7 +85,12 @@ def run_case(name, himut, tmp):
         exp["ref_tri2count"] = {k: int(v) for k, v in rt[cases.CHROM].items()}
         exp["log"] = [int(v) for v in log[cases.CHROM]]
         exp["alt_order"] = [[abi.BASE2CODE[x] for x in list(himut.util.base_set.difference(r))] for r in "ATGC"]
-    dt = time.time() - t0
+    return exp, time.time() - t0
+
+
+def run_case(name, himut, tmp):
+    c = cases.build_case(name)
+    exp, dt = reference_outputs(c, himut, tmp)
     fixture = dict(case=name, kind=c["kind"], batch_sha256=cases.batch_digest(c["batch"]),
                    n_reads=c["batch"].n_reads, aligned_bases=c["batch"].aligned_bases,
                    reference_seconds=round(dt, 2), expected=exp)

@@ -29,6 +29,23 @@ def rows_equal(a, b):
     return all(len(x) == len(y) and all(u == v for u, v in zip(x, y)) for x, y in zip(a, b))
 
 
+def rows_digest(rows):
+    """SHA-256 over the repr of every field of every row (repr of a float round-trips exactly; numpy scalars are
+    taken as the Python numbers they equal)"""
+    import hashlib
+    h = hashlib.sha256()
+    for row in rows:
+        plain = [float(v) if isinstance(v, (np.floating, float)) else int(v) if isinstance(v, (np.integer, int)) else v for v in row]
+        h.update(("\t".join(repr(v) for v in plain) + "\n").encode())
+    return h.hexdigest()
+
+
+def load_random_sweep():
+    """tests/golden/random_sweep.json: what the reference returned for every seed of cases.random_case"""
+    with open(os.path.join(cases.GOLDEN_DIR, "random_sweep.json")) as f:
+        return json.load(f)
+
+
 def first_diff(a, b):
     for i, (x, y) in enumerate(zip(a, b)):
         if not (len(x) == len(y) and all(u == v for u, v in zip(x, y))):
