@@ -397,3 +397,17 @@ def random_case(kind, seed):
     c["chunk_table"] = batch.chunk_table(chunks, sets)
     c["params"] = gtmodel.make_params(**args)
     return c
+
+
+# ------------------------------------------------------------------------------------------
+# the whole CLI (tests/test_cli_dropin.py): three contigs whose names only sort right naturally
+# ------------------------------------------------------------------------------------------
+CLI_CONTIGS = [("chr1", 230_000, 31), ("chr2", 90_000, 32), ("chr10", 40_000, 33)]
+
+
+def cli_dataset(phase_block=None):
+    """-> [(name, length, synth data)]: 30x CCS reads over a two-chunk contig and two short ones"""
+    over = dict(somatic_rate=2e-5)
+    if phase_block:
+        over["phase_block"] = phase_block
+    return [(name, n, synth.generate(n, seed=seed, **over)) for name, n, seed in CLI_CONTIGS]

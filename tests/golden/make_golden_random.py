@@ -77,23 +77,12 @@ def one(kind, seed, himut, tmp):
     return entry, why
 
 
-class _StableArgsortNumpy:
-    """numpy as gtlib sees it, with argsort as numpy 1.24 does it on short vectors (stable)"""
-
-    def __getattr__(self, name):
-        return getattr(np, name)
-
-    @staticmethod
-    def argsort(a, *args, **kw):
-        return np.argsort(a, kind="stable")
-
-
 def main():
     himut = refshim.import_reference()
     if "--native-argsort" in sys.argv:
         sys.argv.remove("--native-argsort")
     else:
-        himut.gtlib.np = _StableArgsortNumpy()
+        himut.gtlib.np = refshim.StableArgsortNumpy()
     extra = None
     if len(sys.argv) >= 4 and sys.argv[1] == "--extra":
         extra = range(int(sys.argv[2]), int(sys.argv[3]))

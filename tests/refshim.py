@@ -111,3 +111,32 @@ class BatchProvider:
                     break
                 continue
             yield self.segment(r)
+
+
+class ContigsProvider:
+    """several contigs' batches behind one pysam.AlignmentFile look-alike"""
+
+    def __init__(self, contigs, sample="synth"):
+        """contigs: [(name, length, ReadBatch)] in @SQ order"""
+        self.header_text = "@HD\tVN:1.6\tSO:coordinate\n" + "".join("@SQ\tSN:%s\tLN:%d\n" % (c, n) for c, n, _ in contigs) \
+                           + "@RG\tID:rg\tSM:%s\n" % sample
+        self._by_name = {c: BatchProvider(c, n, b, sample) for c, n, b in contigs}
+        self._order = [c for c, _, _ in contigs]
+
+    def fetch_records(self, chrom=None, start=None, end=None):
+        for c in ([chrom] if chrom is not None else self._order):
+            if c in self._by_name:
+                yield from self._by_name[c].fetch_records(c, start, end)
+
+
+class StableArgsortNumpy:
+    """numpy as the reference's gtlib should see it: np.argsort of a 10-vector is an insertion sort, hence stable, in the
+    reference's pinned numpy 1.24.4 (poetry.lock), while numpy >= 1.25 on AVX-512 hosts dispatches to an unstable SIMD
+    sort.  Install with `himut.gtlib.np = StableArgsortNumpy()`."""
+
+    def __getattr__(self, name):
+        return getattr(np, name)
+
+    @staticmethod
+    def argsort(a, *args, **kw):
+        return np.argsort(a, kind="stable")

@@ -1,0 +1,119 @@
+"""The drop-in claim end to end, on the CPU: the reference's own command line (`himut call`, /root/reference/src, run
+unmodified through the I/O look-alikes of tests/shims) once with its own workers and once after
+`himut_b200.patch.install()`, on the same three-contig BAM and VCF files — option parsing, the BAM pre-pass
+(get_thresholds mirror on the real BAM file through the native decoder), chunking, the fork of the worker pool with a
+lazily created context, the Manager-dict contract, natsort, header and writers all included.  The output VCF and
+himut.log must be byte-identical.  Without a GPU the device calls of the drop-in workers are answered by the oracle
+(tests/standin.py); what the device computes is pinned separately (tests/test_gpu_*.py).
+
+Build container only: the reference is not on the GPU box."""
+import gzip
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import cases
+import refshim
+from himut_b200 import bamio, synth
+
+pytestmark = pytest.mark.skipif(not refshim.have_reference(), reason="reference sources are not present")
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+VCF_HEAD = "##fileformat=VCFv4.2\n%s#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\tsynth\n"
+
+
+def _write_sites(path, per_contig, compress):
+    """per_contig: [(chrom, keys)] -> single-sample VCF of PASS SNVs"""
+    text = [VCF_HEAD % ""]
+    for chrom, keys in per_contig:
+        for k in keys.tolist():
+            text.append("%s\t%d\t.\t%s\t%s\t.\tPASS\t.\tGT\t0/1\n" % (chrom, k >> 4, "ATGC"[(k >> 2) & 3], "ATGC"[k & 3]))
+    data = "".join(text).encode()
+    with open(path, "wb") as f:
+        f.write(gzip.compress(data) if compress else data)
+    if compress:
+        open(path + ".tbi", "wb").write(b"placeholder: the tabix look-alike scans the file")
+
+
+def _write_phased(path, data, phase_block):
+    text = [VCF_HEAD % '##FORMAT=<ID=GT,Number=1,Type=String,Description="Genotype">\n##FORMAT=<ID=PS,Number=1,Type=Integer,Description="Phase set">\n']
+    for chrom, _n, d in data:
+        ph = synth.phase_table(d.germ, phase_block)
+        for s in range(ph["set_off"].size - 1):
+            a, b = int(ph["set_off"][s]), int(ph["set_off"][s + 1])
+            ps = int(ph["hpos"][a])
+            for i in range(a, b):
+                bit = int(ph["hbit"][i])
+                text.append("%s\t%d\t.\t%s\t%s\t.\tPASS\t.\tGT:PS\t%s:%d\n" % (
+                    chrom, int(ph["hpos"][i]), "ATGC"[int(ph["href"][i])], "ATGC"[int(ph["halt"][i])], "0|1" if bit == 0 else "1|0", ps))
+    with open(path, "w") as f:
+        f.write("".join(text))
+
+
+def _inputs(tmp, phase_block=None):
+    data = cases.cli_dataset(phase_block)
+    bam = os.path.join(tmp, "synth.bam")
+    bamio.write_batches_bam(bam, [(c, n, d.batch) for c, n, d in data])
+    sets = [(c,) + cases.site_sets_from_synth(d, 40 + i) for i, (c, _n, d) in enumerate(data)]
+    return data, bam, sets
+
+
+def _run(mode, tmp, phase_block, argv):
+    work = os.path.join(tmp, mode)
+    os.makedirs(work)
+    out = os.path.join(work, "out.vcf")
+    cmd = [sys.executable, os.path.join(HERE, "cli_runner.py"), mode, work, str(phase_block or 0)] + argv + ["-o", out]
+    env = dict(os.environ, PYTHONHASHSEED="0")
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=env, timeout=1500)
+    assert r.returncode == 0, r.stdout[-4000:]
+    assert os.path.exists(out), r.stdout[-4000:]
+    strip = lambda text: [l for l in text.split("\n") if not l.startswith("##fileDate")]
+    vcf = strip(open(out).read())
+    log = open(os.path.join(work, "himut.log")).read()
+    return vcf, log, r.stdout
+
+
+def _compare(tmp, phase_block, argv, expect_status):
+    ref_vcf, ref_log, ref_out = _run("reference", tmp, phase_block, argv)
+    our_vcf, our_log, our_out = _run("dropin", tmp, phase_block, argv)
+    # the header names the output path: the two runs write to different directories
+    fix = lambda lines, mode: [l.replace(os.path.join(tmp, mode), "<work>") for l in lines]
+    ref_vcf, our_vcf = fix(ref_vcf, "reference"), fix(our_vcf, "dropin")
+    rows = [l for l in ref_vcf if l and not l.startswith("#")]
+    assert len(rows) > 50, "the reference emitted almost nothing: not a test"
+    for s in expect_status:
+        assert any(("\t%s\t" % s) in l for l in rows), "no %s row in the reference's VCF" % s
+    assert our_vcf == ref_vcf, next((a, b) for a, b in zip(our_vcf + [None], ref_vcf + [None]) if a != b)
+    assert our_log == ref_log
+    chroms = [l.split("\t")[0] for l in rows]
+    assert chroms.index("chr10") > chroms.index("chr2") > chroms.index("chr1")  # natural order, not lexicographic
+    return rows
+
+
+def test_call_cli_is_a_drop_in(tmp_path):
+    """`himut call -i … --common_snps … --panel_of_normals … -t 3`: human-sample defaults, bgzip-style site files"""
+    tmp = str(tmp_path)
+    data, bam, sets = _inputs(tmp)
+    common, pon = os.path.join(tmp, "common.vcf.bgz"), os.path.join(tmp, "pon.vcf.bgz")
+    _write_sites(common, [(c, k) for c, k, _ in sets], compress=True)
+    _write_sites(pon, [(c, k) for c, _, k in sets], compress=True)
+    _compare(tmp, None, ["call", "-i", bam, "--common_snps", common, "--panel_of_normals", pon, "-t", "3"],
+             ["PASS", "ComSnp", "PanelOfNormal"])
+
+
+def test_call_cli_phase_is_a_drop_in(tmp_path):
+    """`himut call --phase --phased_vcf …` with plain-text site files (the `.vcf` common-SNP loader keeps the *other*
+    contigs' records, vcflib.py:434 — the drop-in must do the same) and non-default thresholds"""
+    tmp = str(tmp_path)
+    block = 50_000
+    data, bam, sets = _inputs(tmp, block)
+    common, pon, phased = os.path.join(tmp, "common.vcf"), os.path.join(tmp, "pon.vcf"), os.path.join(tmp, "germline.phased.vcf")
+    _write_sites(common, [(c, k) for c, k, _ in sets], compress=False)
+    _write_sites(pon, [(c, k) for c, _, k in sets], compress=False)
+    _write_phased(phased, data, block)
+    _compare(tmp, block, ["call", "-i", bam, "--phase", "--phased_vcf", phased, "--common_snps", common, "--panel_of_normals", pon,
+                          "--min_gq", "15", "--min_bq", "60", "--min_trim", "0.02", "--mismatch_window_size", "30", "-t", "2"],
+             ["PASS"])

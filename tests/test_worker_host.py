@@ -12,57 +12,7 @@ import pytest
 import cases
 import parity
 from himut_b200 import abi, bamio, caller, normcounts, phaselib, worker
-from oracle import oracle
-
-
-class OracleContext:
-    """the part of lib.Context the workers use, answered by the oracle"""
-
-    def __init__(self):
-        self.params = self.batch = self.phase = None
-        self.common = self.pon = None
-        self.uploads = 0
-
-    def set_params(self, p):
-        self.params = p
-
-    def set_site_sets(self, common=None, pon=None):
-        self.common, self.pon = common, pon
-
-    def set_phase_sets(self, table):
-        self.phase = table
-
-    def upload(self, batch):
-        assert batch.seq.size, "the oracle reads the bases: the test asks the decoder for them"
-        self.batch = batch
-        self.uploads += 1
-
-    def call_chunks(self, table):
-        self._seen = np.zeros(int(self.batch.qname_id.max()) + 1 if self.batch.n_reads else 1, np.uint8)
-        return oracle.call_chunks(self.params, self.batch, table, self.common, self.pon, self.phase, qseen=self._seen)
-
-    def qname_seen(self):
-        return self._seen
-
-    def normcounts_chunks(self, refseq, table):
-        self._seen = np.zeros(int(self.batch.qname_id.max()) + 1 if self.batch.n_reads else 1, np.uint8)
-        ref = refseq.encode() if isinstance(refseq, str) else refseq
-        return oracle.normcounts_chunks(self.params, self.batch, ref, table, self.common, self.pon, self.phase, qseen=self._seen)
-
-    def phase_edges_begin(self, hpos, href, band):
-        self._edges = (np.ascontiguousarray(hpos, np.int32), np.ascontiguousarray(href, np.uint8), int(band))
-        self._table = np.zeros((len(hpos), int(band), 4), np.uint32)
-
-    def phase_edges_add(self, min_bq, min_mapq, min_tstart=-2**31):
-        hpos, href, band = self._edges
-        counts, need = oracle.phase_edges(self.batch, hpos, href, band, min_bq, min_mapq, min_tstart)
-        if need:
-            return int(need)
-        self._table += counts
-        return 0
-
-    def phase_edges_end(self):
-        return self._table
+from standin import OracleContext
 
 
 @pytest.fixture
