@@ -29,7 +29,7 @@ def main():
     import refshim
     himut = refshim.import_reference()
     import pysam
-    bam = argv[argv.index("-i") + 1]
+    bam = argv[argv.index("-i" if "-i" in argv else "--bam") + 1]
     data = cases.cli_dataset(phase_block or None)
     pysam.register(bam, refshim.ContigsProvider([(c, n, d.batch) for c, n, d in data]))
     himut.gtlib.np = refshim.StableArgsortNumpy()

@@ -40,6 +40,9 @@ class OracleContext:
         ref = refseq.encode() if isinstance(refseq, str) else refseq
         return oracle.normcounts_chunks(self.params, self.batch, ref, table, self.common, self.pon, self.phase, qseen=self._seen)
 
+    def ref_tricounts(self, refseq):
+        return oracle.ref_tricounts(refseq.encode() if isinstance(refseq, str) else bytes(refseq))
+
     def phase_edges_begin(self, hpos, href, band):
         self._edges = (np.ascontiguousarray(hpos, np.int32), np.ascontiguousarray(href, np.uint8), int(band))
         self._table = np.zeros((len(hpos), int(band), 4), np.uint32)

@@ -61,10 +61,10 @@ def _inputs(tmp, phase_block=None):
     return data, bam, sets
 
 
-def _run(mode, tmp, phase_block, argv):
+def _run(mode, tmp, phase_block, argv, out_name="out.vcf", log_name="himut.log"):
     work = os.path.join(tmp, mode)
     os.makedirs(work)
-    out = os.path.join(work, "out.vcf")
+    out = os.path.join(work, out_name)
     cmd = [sys.executable, os.path.join(HERE, "cli_runner.py"), mode, work, str(phase_block or 0)] + argv + ["-o", out]
     env = dict(os.environ, PYTHONHASHSEED="0")
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=env, timeout=1500)
@@ -72,7 +72,7 @@ def _run(mode, tmp, phase_block, argv):
     assert os.path.exists(out), r.stdout[-4000:]
     strip = lambda text: [l for l in text.split("\n") if not l.startswith("##fileDate")]
     vcf = strip(open(out).read())
-    log = open(os.path.join(work, "himut.log")).read()
+    log = open(os.path.join(work, log_name)).read()
     return vcf, log, r.stdout
 
 
@@ -117,3 +117,35 @@ def test_call_cli_phase_is_a_drop_in(tmp_path):
     _compare(tmp, block, ["call", "-i", bam, "--phase", "--phased_vcf", phased, "--common_snps", common, "--panel_of_normals", pon,
                           "--min_gq", "15", "--min_bq", "60", "--min_trim", "0.02", "--mismatch_window_size", "30", "-t", "2"],
              ["PASS"])
+
+
+def test_normcounts_cli_is_a_drop_in(tmp_path):
+    """`himut normcounts --bam … --ref … --sbs <the VCF of himut call> --region_list …`: thresholds read back from the call
+    VCF's header, the callable-base workers, the reference tri-count workers (reflib.get_genome_tricounts' pool) and the
+    reference's own normalisation arithmetic and writers on top"""
+    tmp = str(tmp_path)
+    data, bam, sets = _inputs(tmp)
+    common, pon = os.path.join(tmp, "common.vcf.bgz"), os.path.join(tmp, "pon.vcf.bgz")
+    _write_sites(common, [(c, k) for c, k, _ in sets], compress=True)
+    _write_sites(pon, [(c, k) for c, _, k in sets], compress=True)
+    fasta = os.path.join(tmp, "ref.fa")
+    with open(fasta, "w") as f:
+        for c, _n, d in data:
+            seq = d.ref.decode()
+            f.write(">%s\n" % c + "\n".join(seq[i:i + 60] for i in range(0, len(seq), 60)) + "\n")
+    # the --sbs input: the VCF `himut call` writes (identical from either side, test_call_cli_is_a_drop_in)
+    os.makedirs(os.path.join(tmp, "call"))
+    call_vcf, _log, _out = _run("dropin", os.path.join(tmp, "call"), None,
+                                ["call", "-i", bam, "--common_snps", common, "--panel_of_normals", pon, "-t", "3"])
+    sbs = os.path.join(tmp, "call", "dropin", "out.vcf")
+    regions = os.path.join(tmp, "regions.txt")
+    open(regions, "w").write("chr2\nchr10\n")  # the two short contigs: the reference needs 7 us per aligned base here
+    argv = ["normcounts", "--bam", bam, "--ref", fasta, "--sbs", sbs, "--common_snps", common, "--panel_of_normals", pon,
+            "--region_list", regions, "-t", "2"]
+    ref_tsv, ref_log, _ = _run("reference", tmp, None, argv, "out.normcounts.tsv", "norm.log")
+    our_tsv, our_log, _ = _run("dropin", tmp, None, argv, "out.normcounts.tsv", "norm.log")
+    fix = lambda lines, mode: [l.replace(os.path.join(tmp, mode), "<work>") for l in lines]
+    assert fix(our_tsv, "dropin") == fix(ref_tsv, "reference")
+    assert our_log == ref_log
+    body = [l for l in ref_tsv if l and not l.startswith("#")]
+    assert len(body) >= 96
