@@ -1,9 +1,9 @@
-"""The drop-in claim end to end, on the CPU: the reference's own command line (`himut call`, /root/reference/src, run
-unmodified through the I/O look-alikes of tests/shims) once with its own workers and once after
+"""The drop-in claim end to end, on the CPU: the reference's own command line (`himut call`, `himut normcounts`,
+`himut phase`; /root/reference/src, run unmodified through the I/O look-alikes of tests/shims) once with its own workers and once after
 `himut_b200.patch.install()`, on the same three-contig BAM and VCF files — option parsing, the BAM pre-pass
 (get_thresholds mirror on the real BAM file through the native decoder), chunking, the fork of the worker pool with a
-lazily created context, the Manager-dict contract, natsort, header and writers all included.  The output VCF and
-himut.log must be byte-identical.  Without a GPU the device calls of the drop-in workers are answered by the oracle
+lazily created context, the Manager-dict contract, natsort, header and writers all included.  The output files (VCF,
+normcounts TSV, phased VCF) and himut.log / norm.log must be byte-identical.  Without a GPU the device calls of the drop-in workers are answered by the oracle
 (tests/standin.py); what the device computes is pinned separately (tests/test_gpu_*.py).
 
 Build container only: the reference is not on the GPU box."""
@@ -149,3 +149,24 @@ def test_normcounts_cli_is_a_drop_in(tmp_path):
     assert our_log == ref_log
     body = [l for l in ref_tsv if l and not l.startswith("#")]
     assert len(body) >= 96
+
+
+def test_phase_cli_is_a_drop_in(tmp_path):
+    """`himut phase --bam … --vcf <germline> -o x.phased.vcf`: the hetSNP pair tables come from the phase-edge mirror
+    (phaselib.get_edges), the binomial tests, the graph search and the writer stay the reference's"""
+    tmp = str(tmp_path)
+    data, bam, _sets = _inputs(tmp)
+    germline = os.path.join(tmp, "germline.vcf")
+    text = [VCF_HEAD % ""]
+    for chrom, _n, d in data:
+        g = d.germ
+        for p, r, a, gt in zip(g["pos"].tolist(), g["ref"].tolist(), g["alt"].tolist(), g["gt"].tolist()):
+            text.append("%s\t%d\t.\t%s\t%s\t50\tPASS\t.\tGT\t%s\n" % (chrom, p, "ATGC"[r], "ATGC"[a], "0/1" if gt < 2 else "1/1"))
+    open(germline, "w").write("".join(text))
+    argv = ["phase", "--bam", bam, "--vcf", germline, "-t", "2"]
+    ref_vcf, _l, ref_out = _run("reference", tmp, None, argv, "out.phased.vcf", "out.phased.vcf")
+    our_vcf, _l, our_out = _run("dropin", tmp, None, argv, "out.phased.vcf", "out.phased.vcf")
+    fix = lambda lines, mode: [l.replace(os.path.join(tmp, mode), "<work>") for l in lines]
+    assert fix(our_vcf, "dropin") == fix(ref_vcf, "reference")
+    phased = [l for l in ref_vcf if l and not l.startswith("#")]
+    assert len(phased) > 100 and any("0|1" in l for l in phased) and any("1|0" in l for l in phased)
