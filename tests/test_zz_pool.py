@@ -1,0 +1,69 @@
+"""The deployment model of the drop-in: the reference driver forks `--threads` pool workers, one task per contig, each
+creating its context lazily in the child (src/himut/caller.py:766-810; INTEGRATION.md "Process model").
+tests/pool_runner.py reproduces that model around himut_b200.caller.get_somatic_substitutions in a fresh process; its
+output must equal what the reference's own `himut call` wrote for the same three-contig BAM and site files
+(tests/golden/cli_call.json, from tests/golden/make_golden_cli.py): the BAM pre-pass thresholds, the log vector of
+every contig and every VCF body line.  On the GPU box the workers use the CUDA library (three processes sharing the
+device); on the CPU the oracle stand-in pins the host side.  Runs last (file name) because it spawns processes."""
+import gzip
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+import cases
+from himut_b200 import bamio
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLD = json.load(open(os.path.join(cases.GOLDEN_DIR, "cli_call.json")))
+PHASE_BLOCK = 50_000
+PHASE_OVERRIDES = ["min_gq=15", "min_bq=60", "min_trim=0.02", "mismatch_window=30"]
+
+
+def _write_sites(path, per_contig):
+    text = ["##fileformat=VCFv4.2\n#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\tsynth\n"]
+    for chrom, keys in per_contig:
+        for k in keys.tolist():
+            text.append("%s\t%d\t.\t%s\t%s\t.\tPASS\t.\tGT\t0/1\n" % (chrom, k >> 4, "ATGC"[(k >> 2) & 3], "ATGC"[k & 3]))
+    with open(path, "wb") as f:
+        f.write(gzip.compress("".join(text).encode()))
+
+
+def _run(tmp, name, real):
+    block = PHASE_BLOCK if name == "phase" else 0
+    data = cases.cli_dataset(block or None)
+    bam = os.path.join(tmp, "synth.bam")
+    bamio.write_batches_bam(bam, [(c, n, d.batch) for c, n, d in data])
+    sets = [(c,) + cases.site_sets_from_synth(d, 40 + i) for i, (c, _n, d) in enumerate(data)]
+    common, pon = os.path.join(tmp, "common.vcf.bgz"), os.path.join(tmp, "pon.vcf.bgz")
+    _write_sites(common, [(c, k) for c, k, _ in sets])
+    _write_sites(pon, [(c, k) for c, _, k in sets])
+    cmd = [sys.executable, os.path.join(HERE, "pool_runner.py"), tmp, bam, common, pon, "3", str(block)] + (PHASE_OVERRIDES if block else [])
+    env = dict(os.environ)
+    env.pop("HIMUT_B200_DEVICE", None)
+    env.pop("LOCAL_RANK", None)  # device = pool worker index modulo visible GPUs, as in a plain `himut call`
+    env["HIMUT_B200_CLI_REAL_CONTEXT"] = "1" if real else "0"
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, env=env, timeout=1500)
+    assert r.returncode == 0, (r.stdout[-2000:], r.stderr[-4000:])
+    return json.loads(r.stdout.strip().split("\n")[-1])
+
+
+def _check(got, name):
+    exp = GOLD[name]
+    assert got["thresholds"] == exp["thresholds"]
+    assert got["log"] == exp["log"]
+    assert len(got["body"]) == len(exp["body"])
+    assert got["body"] == exp["body"], next((a, b) for a, b in zip(got["body"], exp["body"]) if a != b)
+
+
+@pytest.mark.parametrize("name", ["plain", "phase"])
+def test_forked_pool_matches_reference_cli_cpu(tmp_path, name):
+    _check(_run(str(tmp_path), name, real=False), name)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["plain", "phase"])
+def test_forked_pool_matches_reference_cli_gpu(tmp_path, name):
+    _check(_run(str(tmp_path), name, real=True), name)
