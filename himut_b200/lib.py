@@ -53,6 +53,9 @@ def load():
         lib.hm_call_chunks.argtypes = [vp, vp, sz, vp, sz, C.POINTER(sz), vp]
         lib.hm_call_chunks_async.argtypes = [vp, vp, sz, vp, sz, C.POINTER(sz), vp]
         lib.hm_call_batch.argtypes = [vp, C.POINTER(abi.hm_read_batch), vp, sz, vp, sz, C.POINTER(sz), vp]
+        lib.hm_upload_batch_compact.argtypes = [vp, C.POINTER(abi.hm_read_batch), C.POINTER(abi.hm_bq_compact)]
+        lib.hm_call_batch_compact.argtypes = [vp, C.POINTER(abi.hm_read_batch), C.POINTER(abi.hm_bq_compact), vp, sz, vp, sz,
+                                              C.POINTER(sz), vp]
         lib.hm_normcounts_chunks.argtypes = [vp, vp, sz, vp, sz, vp, vp, vp, C.POINTER(C.c_int64)]
         lib.hm_read_stats.argtypes = [vp, vp, vp, vp, vp, vp, vp]
         lib.hm_last_timing.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_int)]
