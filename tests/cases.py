@@ -255,6 +255,25 @@ def _call_phase_shallow():
                 chunks=chunks, phase_sets=sets, phase=ph, args=call_args(phase=True, md_threshold=30))
 
 
+@case("call_config3_phase_sets")
+def _call_config3():
+    # BASELINE.json configs[3] in small: --phase with a phased germline table AND common-SNP AND panel-of-normals sets
+    d = _synth_case(240_000, 17, somatic_rate=4e-5, sub_err_rate=3e-4, phase_block=60_000)
+    ph, chunks, sets = phase_case(d, 60_000)
+    common, pon = site_sets_from_synth(d, 17)
+    return dict(kind="call", batch=d.batch, ref=d.ref.decode(), contig_len=240_000,
+                chunks=chunks, phase_sets=sets, phase=ph, args=call_args(phase=True), common=common, pon=pon)
+
+
+@case("norm_config3_phase_sets")
+def _norm_config3():
+    d = _synth_case(60_000, 24, sub_err_rate=1e-3, somatic_rate=1e-4, phase_block=20_000)
+    ph, chunks, sets = phase_case(d, 20_000)
+    common, pon = site_sets_from_synth(d, 24)
+    return dict(kind="norm", batch=d.batch, ref=d.ref.decode(), contig_len=60_000,
+                chunks=chunks, phase_sets=sets, phase=ph, args=call_args(phase=True), common=common, pon=pon)
+
+
 def _adv(seed, **over):
     batch, ref = adversarial_batch(seed)
     args = call_args(min_qv=20, min_mapq=20, qlen_lower_limit=30, qlen_upper_limit=900,
