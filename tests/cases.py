@@ -353,13 +353,26 @@ RANDOM_CALL_SEEDS = range(1000, 1030)
 RANDOM_NORM_SEEDS = range(2000, 2030)
 
 
+# a second family: dirty reads several 2048-position tiles long on a 30 kb contig (seeds >= LONG_SEED_BASE)
+LONG_SEED_BASE = 4000
+RANDOM_LONG_CALL_SEEDS = range(4000, 4010)
+RANDOM_LONG_NORM_SEEDS = range(5000, 5008)
+
+
 def random_setup(seed):
     rnd = random.Random(seed)
-    n = rnd.choice([1500, 3000, 6000])
-    batch, ref = adversarial_batch(seed, contig_len=n, n_reads=rnd.choice([40, 120, 300]), max_len=rnd.choice([300, 900, 2000]))
+    long_reads = seed >= LONG_SEED_BASE
+    if long_reads:
+        n = rnd.choice([20_000, 30_000])
+        batch, ref = adversarial_batch(seed, contig_len=n, n_reads=rnd.choice([60, 150, 220]), max_len=rnd.choice([2500, 5000, 9000]))
+    else:
+        n = rnd.choice([1500, 3000, 6000])
+        batch, ref = adversarial_batch(seed, contig_len=n, n_reads=rnd.choice([40, 120, 300]), max_len=rnd.choice([300, 900, 2000]))
     args = call_args(
-        min_qv=rnd.choice([0, 20, 30]), min_mapq=rnd.choice([0, 20, 60]), qlen_lower_limit=rnd.choice([0, 30, 200]),
-        qlen_upper_limit=rnd.choice([500, 900, 5000]), min_sequence_identity=rnd.choice([0.0, 0.9, 0.99]),
+        min_qv=rnd.choice([0, 20, 30]), min_mapq=rnd.choice([0, 20, 60]),
+        qlen_lower_limit=rnd.choice([0, 30, 2000] if long_reads else [0, 30, 200]),
+        qlen_upper_limit=rnd.choice([4000, 12000, 100000] if long_reads else [500, 900, 5000]),
+        min_sequence_identity=rnd.choice([0.0, 0.9, 0.99]),
         min_gq=rnd.choice([0, 5, 20]), min_bq=rnd.choice([1, 30, 93]), min_trim=rnd.choice([0.0, 0.01, 0.1]),
         max_mismatch_count=rnd.choice([0, 0, 1, 3]), mismatch_window=rnd.choice([0, 5, 20, 40]),
         md_threshold=rnd.choice([10, 45, 1000]), min_ref_count=rnd.choice([0, 2, 5]), min_alt_count=rnd.choice([1, 2]),

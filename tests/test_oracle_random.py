@@ -1,6 +1,7 @@
 """The CPU oracle against the unmodified reference on the randomised sweep (tests/golden/random_sweep.json, written by
 tests/golden/make_golden_random.py in the build container): the same 60 dirty batches x random parameters that
-tests/test_gpu_random.py runs through the CUDA path, so reference == oracle == CUDA on every one of them.  CPU only."""
+tests/test_gpu_random.py runs through the CUDA path, so reference == oracle == CUDA on every one of them — plus a
+second family of dirty reads several 2048-position tiles long (tests/test_zz_gpu_random_long.py on the GPU).  CPU only."""
 import numpy as np
 import pytest
 
@@ -12,7 +13,7 @@ from oracle import oracle
 SWEEP = parity.load_random_sweep()
 
 
-@pytest.mark.parametrize("seed", cases.RANDOM_CALL_SEEDS)
+@pytest.mark.parametrize("seed", list(cases.RANDOM_CALL_SEEDS) + list(cases.RANDOM_LONG_CALL_SEEDS))
 def test_call_matches_reference(seed):
     c = cases.random_case("call", seed)
     if c is None:
@@ -27,7 +28,7 @@ def test_call_matches_reference(seed):
     assert [int(v) for v in log] == fx["log"]
 
 
-@pytest.mark.parametrize("seed", cases.RANDOM_NORM_SEEDS)
+@pytest.mark.parametrize("seed", list(cases.RANDOM_NORM_SEEDS) + list(cases.RANDOM_LONG_NORM_SEEDS))
 def test_normcounts_matches_reference(seed):
     c = cases.random_case("norm", seed)
     if c is None:
