@@ -151,6 +151,60 @@ def test_normcounts_cli_is_a_drop_in(tmp_path):
     assert len(body) >= 96
 
 
+def _write_germline(path, data):
+    text = [VCF_HEAD % ""]
+    for chrom, _n, d in data:
+        g = d.germ
+        for p, r, a, gt in zip(g["pos"].tolist(), g["ref"].tolist(), g["alt"].tolist(), g["gt"].tolist()):
+            text.append("%s\t%d\t.\t%s\t%s\t50\tPASS\t.\tGT\t%s\n" % (chrom, p, "ATGC"[r], "ATGC"[a], "0/1" if gt < 2 else "1/1"))
+        # a few germline indels: with none the reference's get_truncated_float(0.0) raises (util.py:539-544)
+        for i, p in enumerate((1000, 2000, 3000, 4000)):
+            text.append("%s\t%d\t.\tA\t%s\t50\tPASS\t.\tGT\t%s\n" % (chrom, p, "AT" if i % 2 else "ATT", "0/1" if i < 3 else "1/1"))
+    open(path, "w").write("".join(text))
+
+
+def _write_fasta(path, data):
+    with open(path, "w") as f:
+        for c, _n, d in data:
+            seq = d.ref.decode()
+            f.write(">%s\n" % c + "\n".join(seq[i:i + 60] for i in range(0, len(seq), 60)) + "\n")
+
+
+def test_call_cli_non_human_sample_is_a_drop_in(tmp_path):
+    """`himut call --non_human_sample --ref … --vcf …`: the germline priors come from the sample's own VCF (truncated
+    floats, vcflib.get_germline_priors), no common-SNP / panel-of-normals sets are loaded, a --region_list restricts
+    the run to two contigs"""
+    tmp = str(tmp_path)
+    data, bam, _sets = _inputs(tmp)
+    germline, fasta, regions = os.path.join(tmp, "germline.vcf"), os.path.join(tmp, "ref.fa"), os.path.join(tmp, "regions.txt")
+    _write_germline(germline, data)
+    _write_fasta(fasta, data)
+    open(regions, "w").write("chr10\nchr2\n")
+    ref_vcf, ref_log, _ = _run("reference", tmp, None, ["call", "-i", bam, "--non_human_sample", "--ref", fasta, "--vcf", germline,
+                                                       "--region_list", regions, "-t", "2"])
+    our_vcf, our_log, _ = _run("dropin", tmp, None, ["call", "-i", bam, "--non_human_sample", "--ref", fasta, "--vcf", germline,
+                                                     "--region_list", regions, "-t", "2"])
+    fix = lambda lines, mode: [l.replace(os.path.join(tmp, mode), "<work>") for l in lines]
+    assert fix(our_vcf, "dropin") == fix(ref_vcf, "reference")
+    assert our_log == ref_log
+    cmd = next(l for l in ref_vcf if l.startswith("##himut_command"))
+    assert "--germline_snv_prior 0.001 " not in cmd  # a prior measured from the VCF, not the default
+    assert sum(1 for l in ref_vcf if l and not l.startswith("#")) > 30
+
+
+def test_call_cli_create_panel_of_normal_is_a_drop_in(tmp_path):
+    """`himut call --create_panel_of_normal`: the preset of util.load_pon_params replaces the thresholds"""
+    tmp = str(tmp_path)
+    data, bam, _sets = _inputs(tmp)
+    argv = ["call", "-i", bam, "--create_panel_of_normal", "--region", "chr2", "-t", "1"]
+    ref_vcf, ref_log, _ = _run("reference", tmp, None, argv)
+    our_vcf, our_log, _ = _run("dropin", tmp, None, argv)
+    fix = lambda lines, mode: [l.replace(os.path.join(tmp, mode), "<work>") for l in lines]
+    assert fix(our_vcf, "dropin") == fix(ref_vcf, "reference")
+    assert our_log == ref_log
+    assert sum(1 for l in ref_vcf if l and not l.startswith("#")) > 30
+
+
 def test_phase_cli_is_a_drop_in(tmp_path):
     """`himut phase --bam … --vcf <germline> -o x.phased.vcf`: the hetSNP pair tables come from the phase-edge mirror
     (phaselib.get_edges), the binomial tests, the graph search and the writer stay the reference's"""
