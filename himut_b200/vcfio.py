@@ -10,6 +10,9 @@ Mirrors the reference's loaders, quirks included (src/himut/vcflib.py:356-459):
     bi-allelic SNP.
 """
 import gzip
+import os
+import struct
+import zlib
 
 import numpy as np
 
@@ -20,6 +23,89 @@ def _open_text(path):
     with open(path, "rb") as f:
         magic = f.read(2)
     return gzip.open(path, "rt") if magic == b"\x1f\x8b" else open(path, "rt")
+
+
+# ---- tabix ---------------------------------------------------------------------------------------
+# The reference reads `.bgz` site files through pytabix region queries (vcflib.py:381,417,449,640), so a genome-wide
+# common-SNP file costs it only the records of the region.  The workers here want one contig's records at a time:
+# the `.tbi` index names the BGZF range that holds them, and only that range is inflated.  Without a usable index
+# the file is scanned from the top (same result, slower on genome-wide files).
+_TBI_PSEUDO_BIN = 37450
+
+
+def tabix_contig_range(tbi_path, chrom):
+    """-> (begin, end) BGZF virtual offsets of `chrom`'s records per the .tbi index, None when the index does not
+    list the contig, raises ValueError on anything that is not a tabix index"""
+    with open(tbi_path, "rb") as f:
+        raw = gzip.decompress(f.read())
+    if raw[:4] != b"TBI\x01":
+        raise ValueError("not a tabix index")
+    n_ref, _fmt, _cs, _cb, _ce, _meta, _skip, l_nm = struct.unpack_from("<8i", raw, 4)
+    p = 36
+    names = raw[p:p + l_nm].split(b"\0")[:n_ref]
+    p += l_nm
+    want = chrom.encode()
+    for r in range(n_ref):
+        n_bin = struct.unpack_from("<i", raw, p)[0]
+        p += 4
+        lo, hi, pseudo = None, None, None
+        for _ in range(n_bin):
+            bin_id, n_chunk = struct.unpack_from("<Ii", raw, p)
+            p += 8
+            chunks = struct.unpack_from("<%dQ" % (2 * n_chunk), raw, p)
+            p += 16 * n_chunk
+            if names[r] != want:
+                continue
+            if bin_id == _TBI_PSEUDO_BIN:   # (first, last) offsets of the contig + record counts
+                if n_chunk >= 1:
+                    pseudo = (chunks[0], chunks[1])
+                continue
+            for i in range(n_chunk):
+                lo = chunks[2 * i] if lo is None else min(lo, chunks[2 * i])
+                hi = chunks[2 * i + 1] if hi is None else max(hi, chunks[2 * i + 1])
+        n_intv = struct.unpack_from("<i", raw, p)[0]
+        p += 4 + 8 * n_intv
+        if names[r] == want:
+            if lo is not None:
+                return lo, hi
+            return pseudo
+    return None
+
+
+def _bgzf_lines(path, begin, end):
+    """text lines of the BGZF file between two virtual offsets"""
+    from .bamio import _read_block
+    out = []
+    with open(path, "rb") as f:
+        coff, skip = begin >> 16, begin & 0xFFFF
+        end_coff, end_uoff = end >> 16, end & 0xFFFF
+        f.seek(coff)
+        while coff <= end_coff:
+            size, data = _read_block(f)
+            if size == 0:
+                break
+            if coff == end_coff:
+                data = data[:end_uoff]
+            out.append(data[skip:] if skip else data)
+            skip = 0
+            coff += size
+    return b"".join(out).decode().split("\n")
+
+
+def _contig_lines(path, chrom):
+    """the lines of a site file that can belong to `chrom`: through the tabix index when there is one"""
+    tbi = path + ".tbi"
+    if path.endswith(".bgz") and os.path.exists(tbi):
+        try:
+            rng = tabix_contig_range(tbi, chrom)
+        except (ValueError, OSError, struct.error, EOFError, zlib.error):
+            rng = False  # not a readable index (the tests' placeholder, a csi index, a truncated file): scan instead
+        if rng is None:
+            return []
+        if rng:
+            return _bgzf_lines(path, rng[0], rng[1])
+    with _open_text(path) as f:
+        return f.read().split("\n")
 
 
 def _key(pos, ref, alt):
@@ -39,23 +125,27 @@ def load_common_snps(chrom, path):
         return np.zeros(0, np.uint64)
     plain = path.endswith(".vcf")
     keys = []
-    with _open_text(path) as f:
-        for line in f:
-            if line.startswith("#"):
-                continue
-            arr = line.strip().split()
-            if len(arr) < 7:
-                continue
-            same = arr[0] == chrom
-            if plain and same:      # vcflib.py:434 keeps `chrom != arr[0]`
-                continue
-            if not plain and not same:
-                continue
-            alts = arr[4].split(",")
-            if arr[6] == "PASS" and len(alts) == 1 and len(arr[3]) == 1 and len(alts[0]) == 1:
-                k = _key(arr[1], arr[3], alts[0])
-                if k is not None:
-                    keys.append(k)
+    if plain:
+        with _open_text(path) as f:
+            lines = f.read().split("\n")
+    else:
+        lines = _contig_lines(path, chrom)
+    for line in lines:
+        if line.startswith("#"):
+            continue
+        arr = line.strip().split()
+        if len(arr) < 7:
+            continue
+        same = arr[0] == chrom
+        if plain and same:      # vcflib.py:434 keeps `chrom != arr[0]`
+            continue
+        if not plain and not same:
+            continue
+        alts = arr[4].split(",")
+        if arr[6] == "PASS" and len(alts) == 1 and len(arr[3]) == 1 and len(alts[0]) == 1:
+            k = _key(arr[1], arr[3], alts[0])
+            if k is not None:
+                keys.append(k)
     return _finish(keys)
 
 
@@ -64,18 +154,17 @@ def load_pon(chrom, path):
     if path is None:
         return np.zeros(0, np.uint64)
     keys = []
-    with _open_text(path) as f:
-        for line in f:
-            if line.startswith("#"):
-                continue
-            arr = line.strip().split()
-            if len(arr) < 7 or arr[0] != chrom:
-                continue
-            alts = arr[4].split(",")
-            if arr[6] == "PASS" and len(alts) == 1 and len(arr[3]) == 1 and len(alts[0]) == 1:
-                k = _key(arr[1], arr[3], alts[0])
-                if k is not None:
-                    keys.append(k)
+    for line in _contig_lines(path, chrom):
+        if line.startswith("#"):
+            continue
+        arr = line.strip().split()
+        if len(arr) < 7 or arr[0] != chrom:
+            continue
+        alts = arr[4].split(",")
+        if arr[6] == "PASS" and len(alts) == 1 and len(arr[3]) == 1 and len(alts[0]) == 1:
+            k = _key(arr[1], arr[3], alts[0])
+            if k is not None:
+                keys.append(k)
     return _finish(keys)
 
 

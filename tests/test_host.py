@@ -111,3 +111,38 @@ def test_row_order_falls_back_to_natsort_on_equal_sites():
     d = ("chr1", 10, "A", "C,G", "HetAltSite", 50, "93.0,93.0", 30.0, 0.0, "15,15", "0.50,0.50", ".")
     for rows in ([b, a, c], [d, b, c], [c, d, a, b]):
         assert records._sorted_rows(list(rows)) == natsort_compat.natsorted(list(rows))
+
+
+def test_site_files_are_read_through_the_tabix_index(tmp_path, monkeypatch):
+    """`.bgz` + `.tbi`: only the contig's BGZF range is inflated, and the keys equal those of a scan from the top"""
+    import random
+    import tbi
+    from himut_b200 import vcfio
+    rnd = random.Random(11)
+    header = "##fileformat=VCFv4.2\n#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\n"
+    records = []
+    for chrom, n in (("chr1", 3_000_000), ("chr2", 40_000), ("chrX", 900_000)):
+        for pos in sorted(rnd.sample(range(1, n), 1500)):
+            ref = rnd.choice(["A", "T", "G", "C", "AT"])
+            alt = rnd.choice(["A", "T", "G", "C", "A,T", "GC"])
+            flt = rnd.choice(["PASS", "PASS", "PASS", "q10"])
+            records.append((chrom, pos, ref, "%s\t%d\t.\t%s\t%s\t.\t%s\t." % (chrom, pos, ref, alt, flt)))
+    path = str(tmp_path / "sites.vcf.bgz")
+    tbi.write_vcf_bgz_tbi(path, header, records)
+    assert vcfio.tabix_contig_range(path + ".tbi", "chr9") is None
+    lo1, hi1 = vcfio.tabix_contig_range(path + ".tbi", "chr1")
+    lo2, hi2 = vcfio.tabix_contig_range(path + ".tbi", "chr2")
+    assert lo1 < hi1 <= lo2 < hi2
+    indexed = {c: (vcfio.load_common_snps(c, path), vcfio.load_pon(c, path)) for c in ("chr1", "chr2", "chrX", "chr9")}
+    # the index really was the way in: a scan from the top is not allowed here
+    monkeypatch.setattr(vcfio, "_open_text", lambda p: (_ for _ in ()).throw(AssertionError("scanned")))
+    again = vcfio.load_common_snps("chr2", path)
+    monkeypatch.undo()
+    assert np.array_equal(again, indexed["chr2"][0])
+    os.rename(path + ".tbi", path + ".tbi.away")      # no index: scan
+    for c, (common, pon) in indexed.items():
+        assert np.array_equal(common, vcfio.load_common_snps(c, path)), c
+        assert np.array_equal(pon, vcfio.load_pon(c, path)), c
+    assert indexed["chr1"][0].size > 300 and indexed["chr9"][0].size == 0
+    open(path + ".tbi", "wb").write(b"not an index")    # unreadable index: scan, same keys
+    assert np.array_equal(indexed["chrX"][0], vcfio.load_common_snps("chrX", path))
