@@ -26,16 +26,20 @@ VCF_HEAD = "##fileformat=VCFv4.2\n%s#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINF
 
 
 def _write_sites(path, per_contig, compress):
-    """per_contig: [(chrom, keys)] -> single-sample VCF of PASS SNVs"""
-    text = [VCF_HEAD % ""]
+    """per_contig: [(chrom, keys)] -> single-sample VCF of PASS SNVs; compress: BGZF + a real tabix index, which the
+    drop-in's loaders use (the reference side goes through the pytabix look-alike, which scans the file)"""
+    import tbi
+    head = VCF_HEAD % ""
+    rows = []
     for chrom, keys in per_contig:
         for k in keys.tolist():
-            text.append("%s\t%d\t.\t%s\t%s\t.\tPASS\t.\tGT\t0/1\n" % (chrom, k >> 4, "ATGC"[(k >> 2) & 3], "ATGC"[k & 3]))
-    data = "".join(text).encode()
-    with open(path, "wb") as f:
-        f.write(gzip.compress(data) if compress else data)
+            ref = "ATGC"[(k >> 2) & 3]
+            rows.append((chrom, k >> 4, ref, "%s\t%d\t.\t%s\t%s\t.\tPASS\t.\tGT\t0/1" % (chrom, k >> 4, ref, "ATGC"[k & 3])))
     if compress:
-        open(path + ".tbi", "wb").write(b"placeholder: the tabix look-alike scans the file")
+        tbi.write_vcf_bgz_tbi(path, head, rows)
+    else:
+        with open(path, "w") as f:
+            f.write(head + "".join(r[3] + "\n" for r in rows))
 
 
 def _write_phased(path, data, phase_block):
