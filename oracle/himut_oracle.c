@@ -454,7 +454,7 @@ int orc_call_chunks_seen(const hm_params* p, const hm_read_batch* b, const hm_ch
       }
     }
     /* set(somatic_tsbs_candidate_lst) */
-    qsort(cand, ncand, sizeof(uint64_t), cmp_u64);
+    if (ncand) qsort(cand, ncand, sizeof(uint64_t), cmp_u64);
     size_t nu = 0;
     for (size_t i = 0; i < ncand; i++) if (i == 0 || cand[i] != cand[i - 1]) cand[nu++] = cand[i];
 
