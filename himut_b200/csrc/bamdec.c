@@ -403,10 +403,17 @@ void hm_bam_close(hm_bam* b) {
   free(b);
 }
 
+#if defined(__x86_64__) && defined(__GNUC__)
+static int have_ssse3(void); /* probed once in hm_bam_open, read by the record-decode threads */
+#endif
+
 int hm_bam_open(const char* path, hm_bam** out) {
   if (!path || !out) return HM_ERR_ARG;
   *out = NULL;
   (void)hi_use_run(); (void)hm_crc32_available(); /* one-time CPU probes and tables, before any worker thread exists */
+#if defined(__x86_64__) && defined(__GNUC__)
+  (void)have_ssse3();
+#endif
   hm_bam* b = (hm_bam*)calloc(1, sizeof(hm_bam));
   if (!b) return HM_ERR_ARG;
   b->path = strdup(path);
@@ -963,6 +970,7 @@ static void* deflate_worker(void* arg) {
 int hm_bam_write_batch(const char* path, const char* chrom, int32_t contig_len, const char* sample, const hm_read_batch* b,
                        int level, int threads) {
   if (!path || !chrom || !b) return HM_ERR_ARG;
+  (void)hm_crc32_available(); /* probed before the deflate threads exist */
   wbuf_t w; memset(&w, 0, sizeof(w));
   char text[1024];
   int ltext = snprintf(text, sizeof(text), "@HD\tVN:1.6\tSO:coordinate\n@SQ\tSN:%s\tLN:%d\n@RG\tID:rg\tSM:%s\n", chrom, contig_len, sample ? sample : "synth");
