@@ -357,6 +357,9 @@ RANDOM_NORM_SEEDS = range(2000, 2030)
 LONG_SEED_BASE = 4000
 RANDOM_LONG_CALL_SEEDS = range(4000, 4010)
 RANDOM_LONG_NORM_SEEDS = range(5000, 5008)
+# long-read --phase seeds where two records sharing a query name disagree at a phase-checked site: the reference
+# classifies the re-fetched records by query name (caller.py:556-567), DESIGN.md §7 says what the kernels do today
+RANDOM_DUPNAME_CALL_SEEDS = (6081, 6090, 6123)
 
 
 def random_setup(seed):

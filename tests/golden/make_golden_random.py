@@ -89,7 +89,7 @@ def main():
     sweep = {"call": {}, "norm": {}}
     bad = []
     with tempfile.TemporaryDirectory() as tmp:
-        for kind, seeds in (("call", extra or list(cases.RANDOM_CALL_SEEDS) + list(cases.RANDOM_LONG_CALL_SEEDS)),
+        for kind, seeds in (("call", extra or list(cases.RANDOM_CALL_SEEDS) + list(cases.RANDOM_LONG_CALL_SEEDS) + list(cases.RANDOM_DUPNAME_CALL_SEEDS)),
                             ("norm", extra or list(cases.RANDOM_NORM_SEEDS) + list(cases.RANDOM_LONG_NORM_SEEDS))):
             for seed in seeds:
                 try:

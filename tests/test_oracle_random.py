@@ -13,7 +13,7 @@ from oracle import oracle
 SWEEP = parity.load_random_sweep()
 
 
-@pytest.mark.parametrize("seed", list(cases.RANDOM_CALL_SEEDS) + list(cases.RANDOM_LONG_CALL_SEEDS))
+@pytest.mark.parametrize("seed", list(cases.RANDOM_CALL_SEEDS) + list(cases.RANDOM_LONG_CALL_SEEDS) + list(cases.RANDOM_DUPNAME_CALL_SEEDS))
 def test_call_matches_reference(seed):
     c = cases.random_case("call", seed)
     if c is None:
