@@ -62,6 +62,24 @@ def test_call_worker_host_logic(octx, name, tmp_path):
     assert log == fx["expected"]["log"]
 
 
+def test_duplicate_query_names_are_flagged_in_phase_mode(octx, tmp_path):
+    """records sharing a query name make the phase check of the kernels differ from the reference's:
+    the worker says so instead of deviating silently; clean inputs stay quiet"""
+    import warnings
+    c = cases.random_case("call", cases.RANDOM_DUPNAME_CALL_SEEDS[0])
+    c["name"] = "dupnames"
+    fx = parity.load_random_sweep()["call"][str(cases.RANDOM_DUPNAME_CALL_SEEDS[0])]
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        rows, log = _run_call(c, tmp_path)
+    assert any(issubclass(x.category, RuntimeWarning) and "share query names" in str(x.message) for x in w)
+    assert parity.rows_digest(rows) == fx["rows_sha256"] and log == fx["log"]  # the stand-in is the oracle: the reference's rows
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        _run_call(cases.build_case("call_phase"), tmp_path)
+    assert not [x for x in w if "share query names" in str(x.message)]
+
+
 @pytest.mark.parametrize("span", [700, 1200, 2500])
 def test_call_worker_group_carry_on_cpu(octx, tmp_path, monkeypatch, span):
     """a contig fed to the device in several batches: som_seen and the distinct-read count carry across them"""
