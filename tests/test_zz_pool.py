@@ -31,6 +31,20 @@ def _write_sites(path, per_contig):
         f.write(gzip.compress("".join(text).encode()))
 
 
+def _run_group(cmd, env, timeout):
+    """subprocess.run, but the runner and the pool workers it forks form one process group that is killed as a whole
+    when the time is up: nothing is left behind holding the device"""
+    import signal
+    p = subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, env=env, start_new_session=True)
+    try:
+        out, err = p.communicate(timeout=timeout)
+    except subprocess.TimeoutExpired:
+        os.killpg(p.pid, signal.SIGKILL)
+        out, err = p.communicate()
+        pytest.fail("pool runner did not finish within %d s\n%s\n%s" % (timeout, out[-2000:], err[-4000:]))
+    return subprocess.CompletedProcess(cmd, p.returncode, out, err)
+
+
 def _run(tmp, name, real):
     block = PHASE_BLOCK if name == "phase" else 0
     data = cases.cli_dataset(block or None)
@@ -45,7 +59,7 @@ def _run(tmp, name, real):
     env.pop("HIMUT_B200_DEVICE", None)
     env.pop("LOCAL_RANK", None)  # device = pool worker index modulo visible GPUs, as in a plain `himut call`
     env["HIMUT_B200_CLI_REAL_CONTEXT"] = "1" if real else "0"
-    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, env=env, timeout=1500)
+    r = _run_group(cmd, env, timeout=600)
     if real and r.returncode != 0 and "hm_create(device=" in (r.stdout + r.stderr):
         # the workers could not open the device although this process has it open: exclusive-process compute mode
         pytest.skip("a second process cannot open the GPU while pytest holds a context (exclusive-process mode)")
