@@ -189,3 +189,31 @@ def test_base_conversion_at_every_length(tmp_path):
     got = nb.read_batch("chr1", 0, 1000)
     _same(got, bamio.read_batch(bamio.BamReader(path), "chr1", 0, 1000, builder=bb))
     assert got.n_reads == 150
+
+
+@pytest.mark.parametrize("threads", [1, 3])
+def test_compact_quality_stream_is_lossless_on_the_cpu(threads):
+    """hm_bq_compact_build (host) against the format include/himut_b200.h specifies, expanded here with numpy the way
+    k_bq_expand does on the device: bit set = modal value, clear bits take the exceptions read by read in base order"""
+    from himut_b200 import synth
+    import cases
+    for batch in (synth.generate(300_000, seed=61).batch, cases.adversarial_batch(5, contig_len=6000, n_reads=300, max_len=2000)[0]):
+        cq = bamdec.compact_bq(batch, threads=threads)
+        assert cq.mask.size * 8 == batch.bq.size and cq.exc_off.size == batch.n_reads + 1
+        bits = np.unpackbits(cq.mask, bitorder="little").astype(bool)
+        vals, counts = np.unique(batch.bq[np.concatenate([np.arange(int(o), int(o) + int(l)) for o, l in zip(batch.bq_off, batch.qlen)])],
+                                 return_counts=True)
+        assert cq.modal == int(vals[np.argmax(counts)])
+        out = np.zeros(batch.bq.size, np.uint8)
+        for r in range(batch.n_reads):
+            o, l = int(batch.bq_off[r]), int(batch.qlen[r])
+            m = bits[o:o + l]
+            seg = np.full(l, cq.modal, np.uint8)
+            e0, e1 = int(cq.exc_off[r]), int(cq.exc_off[r + 1])
+            assert e1 - e0 == int((~m).sum())
+            seg[~m] = cq.exc[e0:e1]
+            out[o:o + l] = seg
+            pad_end = int(batch.bq_off[r + 1]) if r + 1 < batch.n_reads else batch.bq.size
+            assert not bits[o + l:pad_end].any()      # padding bits are clear
+            assert np.array_equal(seg, batch.bq[o:o + l])
+        assert int(cq.exc_off[-1]) == cq.n_exc
