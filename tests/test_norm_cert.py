@@ -96,3 +96,19 @@ def test_thirty_reads_at_q93_are_certified_by_default():
     assert certified(make_cert(1e-3, 20), [93])            # the prior alone puts het 30 above hom-ref
     assert not certified(make_cert(1e-3, 60), [93] * 5)    # 5 reads: 15 + 30 < 60
     assert make_cert(1e-3, 20, min_bq=200) is None           # outside the certified domain: exact pass only
+
+
+def test_every_table_entry_is_the_references_value():
+    """the per-BQ terms and priors the kernels add are the reference's own functions' values, bit for bit, over the whole
+    table (tests/test_kat.py pins four entries without the reference)"""
+    himut = refshim.import_reference()
+    hom, het, err = gtmodel.bq_tables()
+    for bq in range(1, 256):
+        assert hom[bq] == himut.gtlib.get_log10_one_minus_epsilon(bq)
+        assert het[bq] == himut.gtlib.get_log10_one_half_minus_epsilon(bq)
+        assert err[bq] == himut.gtlib.get_log10_epsilon(bq / 3)
+    for prior in (1e-3, 1e-2, 5e-4, 0.3, 0.00123):
+        himut.gtlib.init(prior)
+        ours = gtmodel.germline_priors(prior)
+        for state, v in zip(("homref", "het", "hetalt", "homalt"), ours):
+            assert math.log10(v) == himut.gtlib.get_log10_germ_gt_prior(state), (prior, state)
