@@ -34,7 +34,7 @@
  * run in the build container through I/O shims: tests/golden/make_golden.py generates the
  * fixtures in tests/golden/, tests/test_oracle_golden.py checks this file against them;
  * tests/golden/make_golden_random.py does the same for a randomised sweep of dirty batches x
- * random parameters (81 committed seeds, tests/test_oracle_random.py; 1 300 more compared in
+ * random parameters (81 committed seeds, tests/test_oracle_random.py; 3 400 more compared in
  * fuzzing sessions without a mismatch).
  *
  * Build: see oracle/Makefile (gcc -O2 -ffp-contract=off -shared).
