@@ -201,10 +201,13 @@ def test_call_cli_non_human_sample_is_a_drop_in(tmp_path):
 
 
 def test_call_cli_create_panel_of_normal_is_a_drop_in(tmp_path):
-    """`himut call --create_panel_of_normal`: the preset of util.load_pon_params replaces the thresholds"""
+    """`himut call --create_panel_of_normal --region_list <chrom start end>`: the preset of util.load_pon_params replaces
+    the thresholds; arbitrary, overlapping windows (the som_seen carry between them) through the whole CLI"""
     tmp = str(tmp_path)
     data, bam, _sets = _inputs(tmp)
-    argv = ["call", "-i", bam, "--create_panel_of_normal", "--region", "chr2", "-t", "1"]
+    regions = os.path.join(tmp, "regions.txt")
+    open(regions, "w").write("chr2\t1000\t60000\nchr2\t55000\t90000\nchr10\t0\t40000\n")  # windows, two of them overlapping
+    argv = ["call", "-i", bam, "--create_panel_of_normal", "--region_list", regions, "-t", "2"]
     ref_vcf, ref_log, _ = _run("reference", tmp, None, argv)
     our_vcf, our_log, _ = _run("dropin", tmp, None, argv)
     fix = lambda lines, mode: [l.replace(os.path.join(tmp, mode), "<work>") for l in lines]
