@@ -437,12 +437,13 @@ def random_case(kind, seed):
 # ------------------------------------------------------------------------------------------
 # the whole CLI (tests/test_cli_dropin.py): three contigs whose names only sort right naturally
 # ------------------------------------------------------------------------------------------
-CLI_CONTIGS = [("chr1", 230_000, 31), ("chr2", 90_000, 32), ("chr10", 40_000, 33)]
+CLI_CONTIGS = [("chr1", 205_000, 31), ("chr2", 70_000, 32), ("chr10", 30_000, 33)]
+CLI_DEPTH = 22.0  # the reference needs 2 - 8 us per aligned base: sized so that the CLI tests stay a minute or two in all
 
 
 def cli_dataset(phase_block=None):
-    """-> [(name, length, synth data)]: 30x CCS reads over a two-chunk contig and two short ones"""
-    over = dict(somatic_rate=2e-5)
+    """-> [(name, length, synth data)]: 22x CCS reads over a two-chunk contig and two short ones"""
+    over = dict(somatic_rate=2e-5, depth=CLI_DEPTH)
     if phase_block:
         over["phase_block"] = phase_block
     return [(name, n, synth.generate(n, seed=seed, **over)) for name, n, seed in CLI_CONTIGS]

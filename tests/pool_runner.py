@@ -47,7 +47,7 @@ def main():
     hbit, hpos, hetsnp, loci = {}, {}, {}, {}
     for c, n, seed in cases.CLI_CONTIGS:
         if block:
-            d = synth.generate(n, seed=seed, somatic_rate=2e-5, phase_block=block)
+            d = synth.generate(n, seed=seed, somatic_rate=2e-5, depth=cases.CLI_DEPTH, phase_block=block)
             ph = synth.phase_table(d.germ, block)
             hbit[c], hpos[c], hetsnp[c] = cases.phase_dicts({"phase": ph})
             loci[c] = [(c, v[0], v[-1]) for v in hpos[c].values()]  # vcflib.py:655-662

@@ -65,24 +65,43 @@ def _inputs(tmp, phase_block=None):
     return data, bam, sets
 
 
-def _run(mode, tmp, phase_block, argv, out_name="out.vcf", log_name="himut.log"):
+def _start(mode, tmp, phase_block, argv, out_name):
     work = os.path.join(tmp, mode)
     os.makedirs(work)
     out = os.path.join(work, out_name)
     cmd = [sys.executable, os.path.join(HERE, "cli_runner.py"), mode, work, str(phase_block or 0)] + argv + ["-o", out]
     env = dict(os.environ, PYTHONHASHSEED="0")
-    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=env, timeout=1500)
-    assert r.returncode == 0, r.stdout[-4000:]
-    assert os.path.exists(out), r.stdout[-4000:]
+    return subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=env), work, out
+
+
+def _finish(started, log_name):
+    p, work, out = started
+    try:
+        stdout, _ = p.communicate(timeout=1500)
+    except subprocess.TimeoutExpired:
+        p.kill()
+        raise
+    assert p.returncode == 0, stdout[-4000:]
+    assert os.path.exists(out), stdout[-4000:]
     strip = lambda text: [l for l in text.split("\n") if not l.startswith("##fileDate")]
     vcf = strip(open(out).read())
     log = open(os.path.join(work, log_name)).read()
-    return vcf, log, r.stdout
+    return vcf, log, stdout
+
+
+def _run(mode, tmp, phase_block, argv, out_name="out.vcf", log_name="himut.log"):
+    return _finish(_start(mode, tmp, phase_block, argv, out_name), log_name)
+
+
+def _run_both(tmp, phase_block, argv, out_name="out.vcf", log_name="himut.log"):
+    """the unmodified run and the drop-in run side by side -> ((vcf, log, stdout) of the reference, of the drop-in)"""
+    a = _start("reference", tmp, phase_block, argv, out_name)
+    b = _start("dropin", tmp, phase_block, argv, out_name)
+    return _finish(a, log_name), _finish(b, log_name)
 
 
 def _compare(tmp, phase_block, argv, expect_status, contigs=("chr1", "chr2", "chr10")):
-    ref_vcf, ref_log, ref_out = _run("reference", tmp, phase_block, argv)
-    our_vcf, our_log, our_out = _run("dropin", tmp, phase_block, argv)
+    (ref_vcf, ref_log, ref_out), (our_vcf, our_log, our_out) = _run_both(tmp, phase_block, argv)
     # the header names the output path: the two runs write to different directories
     fix = lambda lines, mode: [l.replace(os.path.join(tmp, mode), "<work>") for l in lines]
     ref_vcf, our_vcf = fix(ref_vcf, "reference"), fix(our_vcf, "dropin")
@@ -150,8 +169,7 @@ def test_normcounts_cli_is_a_drop_in(tmp_path):
     open(regions, "w").write("chr2\nchr10\n")  # the two short contigs: the reference needs 7 us per aligned base here
     argv = ["normcounts", "--bam", bam, "--ref", fasta, "--sbs", sbs, "--common_snps", common, "--panel_of_normals", pon,
             "--region_list", regions, "-t", "2"]
-    ref_tsv, ref_log, _ = _run("reference", tmp, None, argv, "out.normcounts.tsv", "norm.log")
-    our_tsv, our_log, _ = _run("dropin", tmp, None, argv, "out.normcounts.tsv", "norm.log")
+    (ref_tsv, ref_log, _), (our_tsv, our_log, _) = _run_both(tmp, None, argv, "out.normcounts.tsv", "norm.log")
     fix = lambda lines, mode: [l.replace(os.path.join(tmp, mode), "<work>") for l in lines]
     assert fix(our_tsv, "dropin") == fix(ref_tsv, "reference")
     assert our_log == ref_log
@@ -188,10 +206,8 @@ def test_call_cli_non_human_sample_is_a_drop_in(tmp_path):
     _write_germline(germline, data)
     _write_fasta(fasta, data)
     open(regions, "w").write("chr10\nchr2\n")
-    ref_vcf, ref_log, _ = _run("reference", tmp, None, ["call", "-i", bam, "--non_human_sample", "--ref", fasta, "--vcf", germline,
-                                                       "--region_list", regions, "-t", "2"])
-    our_vcf, our_log, _ = _run("dropin", tmp, None, ["call", "-i", bam, "--non_human_sample", "--ref", fasta, "--vcf", germline,
-                                                     "--region_list", regions, "-t", "2"])
+    (ref_vcf, ref_log, _), (our_vcf, our_log, _) = _run_both(tmp, None, ["call", "-i", bam, "--non_human_sample", "--ref", fasta, "--vcf", germline,
+                                                                        "--region_list", regions, "-t", "2"])
     fix = lambda lines, mode: [l.replace(os.path.join(tmp, mode), "<work>") for l in lines]
     assert fix(our_vcf, "dropin") == fix(ref_vcf, "reference")
     assert our_log == ref_log
@@ -208,8 +224,7 @@ def test_call_cli_create_panel_of_normal_is_a_drop_in(tmp_path):
     regions = os.path.join(tmp, "regions.txt")
     open(regions, "w").write("chr2\t1000\t60000\nchr2\t55000\t90000\nchr10\t0\t40000\n")  # windows, two of them overlapping
     argv = ["call", "-i", bam, "--create_panel_of_normal", "--region_list", regions, "-t", "2"]
-    ref_vcf, ref_log, _ = _run("reference", tmp, None, argv)
-    our_vcf, our_log, _ = _run("dropin", tmp, None, argv)
+    (ref_vcf, ref_log, _), (our_vcf, our_log, _) = _run_both(tmp, None, argv)
     fix = lambda lines, mode: [l.replace(os.path.join(tmp, mode), "<work>") for l in lines]
     assert fix(our_vcf, "dropin") == fix(ref_vcf, "reference")
     assert our_log == ref_log
@@ -229,8 +244,7 @@ def test_phase_cli_is_a_drop_in(tmp_path):
             text.append("%s\t%d\t.\t%s\t%s\t50\tPASS\t.\tGT\t%s\n" % (chrom, p, "ATGC"[r], "ATGC"[a], "0/1" if gt < 2 else "1/1"))
     open(germline, "w").write("".join(text))
     argv = ["phase", "--bam", bam, "--vcf", germline, "-t", "2"]
-    ref_vcf, _l, ref_out = _run("reference", tmp, None, argv, "out.phased.vcf", "out.phased.vcf")
-    our_vcf, _l, our_out = _run("dropin", tmp, None, argv, "out.phased.vcf", "out.phased.vcf")
+    (ref_vcf, _l, ref_out), (our_vcf, _l2, our_out) = _run_both(tmp, None, argv, "out.phased.vcf", "out.phased.vcf")
     fix = lambda lines, mode: [l.replace(os.path.join(tmp, mode), "<work>") for l in lines]
     assert fix(our_vcf, "dropin") == fix(ref_vcf, "reference")
     phased = [l for l in ref_vcf if l and not l.startswith("#")]
