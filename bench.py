@@ -504,7 +504,8 @@ def main():
             "dominant_kernel": max(step_ms, key=step_ms.get),
             "library_launches_per_step": "cub::DeviceRadixSort (candidate keys)",
             "roofline": {"bound": "hbm", "kernel": "k_read_scan", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": ncu_traffic(alg), "peak_source": peak_src,
+                         "frac": achieved / peak, "frac_of_nominal_8000_gbs": achieved / 8000.0,  # north_star's ~8 TB/s
+                         "traffic": ncu_traffic(alg), "peak_source": peak_src,
                          "alg_bytes_per_launch": alg, "kernel_ms": scan_ms,
                          "share_of_step_device_time": scan_ms / dev_ms if dev_ms else None},
             "roofline_step": {"formula": "SURVEY 8(d): 1.25*N_base + 4*N_op + 40*N_read + 48*N_cand", "bytes": survey_bytes,
