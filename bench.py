@@ -479,7 +479,8 @@ def main():
         else:
             e2e_best = dict(e2e_with, note_without_bases=noseq_note or "not counted on some rank")
         alg, n_base, n_op, n_read = kernel_alg_bytes(batch)
-        scan_ms = float(np.mean(k_ms["k_read_scan"]))
+        scan_name = "k_call_scan" if "k_call_scan" in k_ms else "k_read_scan"
+        scan_ms = float(np.mean(k_ms[scan_name]))
         peak, peak_src = measured_peak()
         achieved = alg / (scan_ms * 1e-3) / 1e9
         step_ms = {k: float(np.mean(v)) for k, v in k_ms.items()}
@@ -503,7 +504,7 @@ def main():
             "gpu_launches": int(args.steps * 17),
             "dominant_kernel": max(step_ms, key=step_ms.get),
             "library_launches_per_step": "cub::DeviceRadixSort (candidate keys)",
-            "roofline": {"bound": "hbm", "kernel": "k_read_scan", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "roofline": {"bound": "hbm", "kernel": scan_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "frac_of_nominal_8000_gbs": achieved / 8000.0,  # north_star's ~8 TB/s
                          "traffic": ncu_traffic(alg), "peak_source": peak_src,
                          "alg_bytes_per_launch": alg, "kernel_ms": scan_ms,

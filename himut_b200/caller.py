@@ -4,19 +4,11 @@ Same positional signature, same contract as the reference worker (src/himut/call
 it fills chrom2tsbs_lst[chrom] with the natsorted 12-tuples and chrom2tsbs_log[chrom] with the
 15 counters.  Install with himut_b200.patch.install().
 """
-import warnings
-
 import numpy as np
 
 from . import abi, gtmodel, records, vcfio, worker
 
 _RESTATES = (abi.ST_GERM_HET, abi.ST_GERM_HETALT, abi.ST_GERM_HOMALT, abi.ST_GERM_HOMREF)
-
-
-def _has_duplicate_names(batch):
-    """do two primary records of the batch carry the same query name?"""
-    ids = batch.qname_id[(batch.flags & abi.READ_SECONDARY) == 0]
-    return ids.size != np.unique(ids).size
 
 
 def _log_from_records(rec, num_ccs):
@@ -64,7 +56,6 @@ def get_somatic_substitutions(
     src = worker.RegionSource(bam_file)
     tally = worker.QnameTally()
     kept, som_seen = [], set()
-    dup_warned = False
     starts = [s for _, s, _e in chunkloci_lst]
     groups = worker.group_chunks(chunkloci_lst)
     for gi, idx in enumerate(groups):
@@ -75,12 +66,6 @@ def get_somatic_substitutions(
         # `call` never needs the read bases as a stream: substituted bases are in the ops, and under a cs match the
         # read carries the reference allele of the site (cslib.py:22-29) — the decoder does not unpack them
         # (seq=False above) and a quarter of the upload goes away
-        if phase and not dup_warned and _has_duplicate_names(batch):
-            # flagged, not guessed: the reference classifies the records re-fetched at a phase-checked site by query
-            # name (caller.py:556-567), the kernels by record; the two agree unless records share a name
-            warnings.warn("%s: primary records share query names; at phase-checked sites they are classified by record, "
-                          "not by name as the reference does (pre-filter with -F 0x900)" % chrom, RuntimeWarning)
-            dup_warned = True
         ctx.upload(batch)
         rec, _log = ctx.call_chunks(table)
         tally.add(ctx.qname_seen())

@@ -25,6 +25,7 @@
 #include "kernels.cuh"
 #include "normcounts.cuh"
 #include "normfast.cuh"
+#include "callfused.cuh"
 
 #define HM_BOUNDARY_CAP_DEFAULT 65536   // boundary records the device list holds (HIMUT_B200_BOUNDARY_CAP overrides: tests)
 #define HM_BOUNDARY_FIRST 2048  // ... of which this many travel with the counters
@@ -105,6 +106,14 @@ struct hm_ctx {
   DevBuf b_sites, b_koff, b_tile_info, b_edge_counts, b_edge_hpos, b_edge_href, b_bqmask, b_bqexc, b_bqexc_off;
   uint64_t edge_n = 0;
   uint32_t edge_band = 0;
+  // fused call path
+  std::vector<uint64_t> h_ops_prefix;       // ops of the reads before read r (candidate slots a chunk can need)
+  bool dup_names = false;                   // two primary records of the resident batch share a query name
+  int call_path = 0;                        // hm_last_call_path
+  uint64_t site_cap_hint = 0;               // high-water mark of distinct sites per call
+  char* h_geom_pin = nullptr;
+  size_t h_geom_cap = 0;
+  DevBuf b_cgeom, b_seg_keys, b_seg_read, b_key_site, b_keys_tmp, b_gscratch, b_czero, b_first_pair, b_tiles, b_site_valid;
 };
 
 namespace {
@@ -305,10 +314,12 @@ void hm_destroy(hm_ctx* ctx) {
                     &ctx->b_ins_len, &ctx->b_del_len, &ctx->b_n_mm, &ctx->b_gate, &ctx->b_pmax, &ctx->b_tix_off, &ctx->b_tix, &ctx->b_common, &ctx->b_pon,
                     &ctx->b_hpos, &ctx->b_href, &ctx->b_halt, &ctx->b_hbit, &ctx->b_set_off, &ctx->b_chunks,
                     &ctx->b_pair_off, &ctx->b_pair_hap, &ctx->b_qseen, &ctx->b_keys, &ctx->b_keys_sorted, &ctx->b_cub,
-                    &ctx->b_records, &ctx->b_counters, &ctx->b_ref, &ctx->b_norm_out, &ctx->b_lut, &ctx->b_tile_off, &ctx->b_agg, &ctx->b_geom, &ctx->b_bidx, &ctx->b_brecs, &ctx->b_sites, &ctx->b_koff, &ctx->b_tile_info, &ctx->b_edge_counts, &ctx->b_edge_hpos, &ctx->b_edge_href, &ctx->b_bqmask, &ctx->b_bqexc, &ctx->b_bqexc_off};
+                    &ctx->b_records, &ctx->b_counters, &ctx->b_ref, &ctx->b_norm_out, &ctx->b_lut, &ctx->b_tile_off, &ctx->b_agg, &ctx->b_geom, &ctx->b_bidx, &ctx->b_brecs, &ctx->b_sites, &ctx->b_koff, &ctx->b_tile_info, &ctx->b_edge_counts, &ctx->b_edge_hpos, &ctx->b_edge_href, &ctx->b_bqmask, &ctx->b_bqexc, &ctx->b_bqexc_off,
+                    &ctx->b_cgeom, &ctx->b_seg_keys, &ctx->b_seg_read, &ctx->b_key_site, &ctx->b_keys_tmp, &ctx->b_gscratch, &ctx->b_czero, &ctx->b_first_pair, &ctx->b_tiles, &ctx->b_site_valid};
   for (DevBuf* b : bufs) b->release();
   if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
   if (ctx->h_cnt_pin) cudaFreeHost(ctx->h_cnt_pin);
+  if (ctx->h_geom_pin) cudaFreeHost(ctx->h_geom_pin);
   for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
   if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
@@ -446,6 +457,20 @@ static int upload_batch_impl(hm_ctx* ctx, const hm_read_batch* b, const hm_bq_co
     if (b->qname_id[r] > max_q) max_q = b->qname_id[r];
   }
   ctx->max_qname_id = max_q;
+  // candidate slots a chunk can need = ops of the reads it fetches; shared query names among primary records
+  // (the phase check of a site then goes by name, caller.py:556-567)
+  ctx->h_ops_prefix.resize(n + 1);
+  ctx->h_ops_prefix[0] = 0;
+  ctx->dup_names = false;
+  {
+    std::vector<uint8_t> named((size_t)max_q + 1, 0);
+    for (uint64_t r = 0; r < n; r++) {
+      ctx->h_ops_prefix[r + 1] = ctx->h_ops_prefix[r] + b->n_ops[r];
+      if (b->flags[r] & HM_READ_SECONDARY) continue;
+      if (named[b->qname_id[r]]) ctx->dup_names = true;
+      named[b->qname_id[r]] = 1;
+    }
+  }
   int rc;
 #define UP(buf, field, count) if ((rc = upload(ctx, ctx->buf, b->field, (size_t)(count)))) return rc
   UP(b_tstart, tstart, n); UP(b_tend, tend, n); UP(b_qstart, qstart, n); UP(b_qlen, qlen, n);
@@ -530,6 +555,188 @@ int hm_records_wait(hm_ctx* ctx) {
   return HM_OK;
 }
 
+// ---- the fused path (callfused.cuh): everything between the uploads and the one synchronisation of a call ----
+namespace {
+
+inline size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
+
+// can the fused path run this call?  (else the first version does: chunk spans of 2^28 positions and more, more than
+// 2^32 (chunk, read) pairs or candidate slots — nothing a reference-style chunk list produces)
+bool fused_eligible(hm_ctx* ctx, const hm_chunk* chunks, size_t n_chunks, uint64_t n_pairs, uint64_t* total_cap, uint64_t* n_tiles) {
+  const bool force_v1 = getenv("HIMUT_B200_CALL_V1") != nullptr; // read per call: tests switch it
+  if (force_v1 || n_pairs == 0 || n_pairs >= 0xffffffffull) return false;
+  uint64_t cap = 0, tiles = 0;
+  for (size_t i = 0; i < n_chunks; i++) {
+    const int64_t span = (int64_t)chunks[i].end - (int64_t)chunks[i].start;
+    if (span >= (1ll << HC_KEY_POS_BITS)) return false;
+    cap += ctx->h_ops_prefix[chunks[i].read_hi] - ctx->h_ops_prefix[chunks[i].read_lo];
+    if (span >= 0) tiles += (uint64_t)(span >> HC_TILE_BITS) + 1;
+  }
+  if (cap >= 0xffffffffull || tiles >= (1ull << 31)) return false;
+  *total_cap = cap; *n_tiles = tiles;
+  return true;
+}
+
+struct FusedGeom { // device pointers into the one geometry block of a call
+  const hm_chunk* chunks; const uint64_t* pair_off; const uint64_t* seg_off; const uint32_t* tile_off; const int32_t* geom;
+  const uint32_t* tile_chunk;
+};
+
+// enqueue the fused path on ctx->stream.  *site_cap: distinct sites the buffers hold (k_tile_scan flags an overflow).
+int fused_enqueue(hm_ctx* ctx, const hm_chunk* chunks, size_t n_chunks, const std::vector<uint64_t>& pair_off, const int32_t* geom,
+                  uint64_t total_cap, uint64_t n_tiles, uint64_t site_cap, int parity, bool omit, size_t boundary_cap, FusedGeom* G_out) {
+  const uint64_t n_pairs = pair_off.back();
+  const size_t n_reads = (size_t)ctx->n_reads;
+  // ---- geometry: one pinned block, one copy ----
+  const size_t o_chunks = 0, o_pair = align16(o_chunks + n_chunks * sizeof(hm_chunk)), o_seg = align16(o_pair + (n_chunks + 1) * 8),
+               o_tile = align16(o_seg + (n_chunks + 1) * 8), o_geom = align16(o_tile + (n_chunks + 1) * 4),
+               o_tchunk = align16(o_geom + 2 * n_chunks * 4 + 16), g_bytes = align16(o_tchunk + (size_t)n_tiles * 4 + 16);
+  if (g_bytes > ctx->h_geom_cap) {
+    if (ctx->h_geom_pin) cudaFreeHost(ctx->h_geom_pin);
+    ctx->h_geom_pin = nullptr; ctx->h_geom_cap = 0;
+    CU(cudaHostAlloc((void**)&ctx->h_geom_pin, g_bytes + g_bytes / 4, cudaHostAllocDefault));
+    ctx->h_geom_cap = g_bytes + g_bytes / 4;
+  }
+  char* hp = ctx->h_geom_pin;
+  memcpy(hp + o_chunks, chunks, n_chunks * sizeof(hm_chunk));
+  memcpy(hp + o_pair, pair_off.data(), (n_chunks + 1) * 8);
+  uint64_t* h_seg = reinterpret_cast<uint64_t*>(hp + o_seg);
+  uint32_t* h_tile = reinterpret_cast<uint32_t*>(hp + o_tile);
+  uint32_t* h_tchunk = reinterpret_cast<uint32_t*>(hp + o_tchunk);
+  h_seg[0] = 0; h_tile[0] = 0;
+  for (size_t i = 0; i < n_chunks; i++) {
+    const int64_t span = (int64_t)chunks[i].end - (int64_t)chunks[i].start;
+    const uint32_t nt = span >= 0 ? (uint32_t)(span >> HC_TILE_BITS) + 1u : 0u;
+    h_seg[i + 1] = h_seg[i] + (ctx->h_ops_prefix[chunks[i].read_hi] - ctx->h_ops_prefix[chunks[i].read_lo]);
+    for (uint32_t k = 0; k < nt; k++) h_tchunk[h_tile[i] + k] = (uint32_t)i;
+    h_tile[i + 1] = h_tile[i] + nt;
+  }
+  memcpy(hp + o_geom, geom, 2 * n_chunks * 4);
+  CU(ctx->b_cgeom.ensure(g_bytes));
+  CU(cudaMemcpyAsync(ctx->b_cgeom.p, hp, g_bytes, cudaMemcpyHostToDevice, ctx->stream));
+  char* dp = ctx->b_cgeom.as<char>();
+  FusedGeom G = {reinterpret_cast<const hm_chunk*>(dp + o_chunks), reinterpret_cast<const uint64_t*>(dp + o_pair),
+                 reinterpret_cast<const uint64_t*>(dp + o_seg), reinterpret_cast<const uint32_t*>(dp + o_tile),
+                 reinterpret_cast<const int32_t*>(dp + o_geom), reinterpret_cast<const uint32_t*>(dp + o_tchunk)};
+  *G_out = G;
+
+  // ---- buffers ----
+  const size_t capk = (size_t)std::max<uint64_t>(total_cap, 1);
+  CU(ctx->b_seg_keys.ensure(capk * 4 + 16)); CU(ctx->b_seg_read.ensure(capk * 4 + 16)); CU(ctx->b_key_site.ensure(capk * 4 + 16));
+  CU(ctx->b_keys_tmp.ensure(capk * 4 + 16)); CU(ctx->b_gscratch.ensure(capk * 8 + 16));
+  const size_t z_cnt = 0, z_cur = z_cnt + n_chunks * 4, z_cur2 = z_cur + n_chunks * 4, z_counted = align16(z_cur2 + n_chunks * 4),
+               z_qvfail = align16(z_counted + n_reads), z_bytes = align16(z_qvfail + n_reads) + 16;
+  CU(ctx->b_czero.ensure(z_bytes));
+  CU(ctx->b_first_pair.ensure(n_reads * 4 + 16));
+  CU(ctx->b_tiles.ensure(((size_t)n_tiles * 3 + 4) * 4));
+  const uint64_t stride = (site_cap + 31) & ~31ull;
+  CU(ctx->b_keys.ensure(site_cap * 8 + 16));
+  CU(ctx->b_agg.ensure(stride * HM_SITE_SLOTS * 4 + site_cap * 8 + 16));
+  CU(ctx->b_site_valid.ensure(site_cap + 16));
+  DevBuf& rec_buf = parity ? ctx->b_records_alt : ctx->b_records;
+  CU(rec_buf.ensure(site_cap * sizeof(hm_site_record)));
+  CU(ctx->b_compact[parity].ensure(site_cap * sizeof(hm_site_record)));
+  CU(ctx->b_kpos.ensure(site_cap * 4 + 16));
+  const unsigned n_red = (unsigned)((site_cap + 127) / 128);
+  CU(ctx->b_keep.ensure((size_t)n_red * 4 + 16));
+  CU(ctx->b_bidx.ensure(boundary_cap * 4 + HM_BOUNDARY_FIRST * 4));
+  CU(ctx->b_brecs.ensure((boundary_cap + HM_BOUNDARY_FIRST) * sizeof(hm_site_record)));
+  CU(ctx->b_bpos.ensure((boundary_cap + HM_BOUNDARY_FIRST) * 4));
+  CU(ctx->b_qseen.ensure((size_t)ctx->max_qname_id + 1));
+  if (ctx->params.phase) CU(ctx->b_pair_hap.ensure(n_pairs + 16));
+
+  char* z = ctx->b_czero.as<char>();
+  uint32_t* seg_cnt = reinterpret_cast<uint32_t*>(z + z_cnt);
+  uint32_t* cursor = reinterpret_cast<uint32_t*>(z + z_cur);
+  uint32_t* cursor2 = reinterpret_cast<uint32_t*>(z + z_cur2);
+  uint8_t* read_counted = reinterpret_cast<uint8_t*>(z + z_counted);
+  uint8_t* qv_fail_read = reinterpret_cast<uint8_t*>(z + z_qvfail);
+  uint32_t* tile_src = ctx->b_tiles.as<uint32_t>();
+  uint32_t* tile_cnt = tile_src + n_tiles;
+  uint32_t* tile_dst = tile_cnt + n_tiles; // n_tiles + 1 entries
+  unsigned long long* d_cnt = ctx->b_counters.as<unsigned long long>();
+  unsigned long long* keys = ctx->b_keys.as<unsigned long long>();
+  uint32_t* entries = ctx->b_agg.as<uint32_t>();
+  uint32_t* site_lo = entries + stride * HM_SITE_SLOTS;
+  uint32_t* site_n = site_lo + site_cap;
+  uint8_t* pair_hap = ctx->params.phase ? ctx->b_pair_hap.as<uint8_t>() : nullptr;
+  const bool has_seq = ctx->db.seq != nullptr;
+
+  static bool attr_set = false;
+  const size_t sort_smem = (2 * (size_t)HC_TILE_WORDS + 2 * (size_t)HC_CAPD) * 4;
+  const size_t scan_smem = sizeof(ScanWarp) * HC_WARPS;
+  if (!attr_set) {
+    CU(cudaFuncSetAttribute(k_site_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sort_smem));
+    CU(cudaFuncSetAttribute(k_call_scan<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scan_smem));
+    CU(cudaFuncSetAttribute(k_call_scan<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scan_smem));
+    attr_set = true;
+  }
+
+  CU(cudaMemsetAsync(ctx->b_counters.p, 0, 256, ctx->stream));
+  CU(cudaMemsetAsync(ctx->b_qseen.p, 0, (size_t)ctx->max_qname_id + 1, ctx->stream));
+  CU(cudaMemsetAsync(ctx->b_czero.p, 0, z_bytes, ctx->stream));
+  CU(cudaMemsetAsync(ctx->b_first_pair.p, 0xff, n_reads * 4, ctx->stream));
+  const unsigned pair_blocks = (unsigned)((n_pairs + HC_WARPS - 1) / HC_WARPS);
+  t_begin(ctx, "k_call_pairs");
+  if (has_seq)
+    k_call_pairs<true><<<pair_blocks, 32 * HC_WARPS, 0, ctx->stream>>>(ctx->db, ctx->dp, ctx->dphase, G.chunks, (uint32_t)n_chunks, G.pair_off, n_pairs, pair_hap,
+                                                                      read_counted, ctx->b_first_pair.as<uint32_t>(), G.seg_off, seg_cnt,
+                                                                      ctx->b_seg_keys.as<uint32_t>(), ctx->b_seg_read.as<uint32_t>());
+  else
+    k_call_pairs<false><<<pair_blocks, 32 * HC_WARPS, 0, ctx->stream>>>(ctx->db, ctx->dp, ctx->dphase, G.chunks, (uint32_t)n_chunks, G.pair_off, n_pairs, pair_hap,
+                                                                       read_counted, ctx->b_first_pair.as<uint32_t>(), G.seg_off, seg_cnt,
+                                                                       ctx->b_seg_keys.as<uint32_t>(), ctx->b_seg_read.as<uint32_t>());
+  t_end(ctx);
+  CU(cudaGetLastError());
+  t_begin(ctx, "k_site_sort");
+  if (n_tiles)
+    k_site_sort<<<(unsigned)n_tiles, HC_SORT_THREADS, sort_smem, ctx->stream>>>(G.tile_chunk, G.tile_off, G.seg_off, seg_cnt, ctx->b_seg_keys.as<uint32_t>(),
+                                                                               cursor, cursor2, ctx->b_gscratch.as<uint32_t>(), ctx->b_keys_tmp.as<uint32_t>(),
+                                                                               ctx->b_key_site.as<uint32_t>(), tile_src, tile_cnt);
+  k_tile_scan<<<1, 1024, 0, ctx->stream>>>(tile_cnt, (uint32_t)n_tiles, tile_dst, (unsigned long long)site_cap, d_cnt);
+  k_site_range2<<<(unsigned)((site_cap + 255) / 256), 256, 0, ctx->stream>>>(ctx->db, G.chunks, G.tile_chunk, tile_src, tile_dst, (uint32_t)n_tiles,
+                                                                            ctx->b_keys_tmp.as<uint32_t>(), d_cnt + 1, keys, site_lo, site_n, entries, stride,
+                                                                            ctx->b_site_valid.as<uint8_t>());
+  t_end(ctx);
+  CU(cudaGetLastError());
+  int rc = flush_deferred(ctx, true); // the previous call's records start moving now, under the quality scan
+  if (rc) return rc;
+  unsigned int* qv_any = reinterpret_cast<unsigned int*>(d_cnt + 7);
+  t_begin(ctx, "k_call_scan");
+  if (has_seq)
+    k_call_scan<true><<<pair_blocks, 32 * HC_WARPS, scan_smem, ctx->stream>>>(ctx->db, ctx->dp, G.chunks, (uint32_t)n_chunks, G.pair_off, n_pairs, pair_hap,
+                                                                             read_counted, ctx->b_first_pair.as<uint32_t>(), G.tile_off, tile_dst, keys,
+                                                                             site_lo, site_n, entries, stride, qv_fail_read, qv_any,
+                                                                             ctx->b_qseen.as<uint8_t>(), d_cnt + 1);
+  else
+    k_call_scan<false><<<pair_blocks, 32 * HC_WARPS, scan_smem, ctx->stream>>>(ctx->db, ctx->dp, G.chunks, (uint32_t)n_chunks, G.pair_off, n_pairs, pair_hap,
+                                                                              read_counted, ctx->b_first_pair.as<uint32_t>(), G.tile_off, tile_dst, keys,
+                                                                              site_lo, site_n, entries, stride, qv_fail_read, qv_any,
+                                                                              ctx->b_qseen.as<uint8_t>(), d_cnt + 1);
+  t_end(ctx);
+  CU(cudaGetLastError());
+  CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_copy_done[parity], 0)); // the copy that last read these record buffers
+  t_begin(ctx, "k_site_reduce");
+  if (n_chunks)
+    k_site_valid<<<(unsigned)n_chunks, 256, 0, ctx->stream>>>(qv_any, qv_fail_read, G.seg_off, seg_cnt, ctx->b_seg_keys.as<uint32_t>(),
+                                                            ctx->b_seg_read.as<uint32_t>(), ctx->b_key_site.as<uint32_t>(), G.tile_off, tile_dst,
+                                                            d_cnt + 1, ctx->b_site_valid.as<uint8_t>());
+  k_site_reduce<<<n_red, 128, 0, ctx->stream>>>(ctx->db, ctx->dp, ctx->dsets, ctx->dlut, ctx->dphase, ctx->dup_names ? 1 : 0, G.chunks, G.pair_off, pair_hap,
+                                                G.geom, G.geom + n_chunks, keys, d_cnt + 1, site_lo, site_n, entries, stride,
+                                                rec_buf.as<hm_site_record>(), d_cnt + 8, ctx->b_bidx.as<uint32_t>(), ctx->b_brecs.as<hm_site_record>(),
+                                                (uint32_t)boundary_cap, d_cnt + 4, reinterpret_cast<int*>(d_cnt + 3), ctx->b_site_valid.as<uint8_t>(),
+                                                qv_any, ctx->b_keep.as<uint32_t>(), omit ? 1 : 0);
+  k_compact_sites<<<(unsigned)std::max<uint64_t>(1, (site_cap + 1023) / 1024), 1024, 0, ctx->stream>>>(
+      rec_buf.as<hm_site_record>(), d_cnt + 1, ctx->b_keep.as<uint32_t>(), omit ? 1 : 0, ctx->b_compact[parity].as<hm_site_record>(),
+      ctx->b_kpos.as<uint32_t>(), d_cnt + 6);
+  k_gather_u32<<<8, 256, 0, ctx->stream>>>(ctx->b_kpos.as<uint32_t>(), ctx->b_bidx.as<uint32_t>(), d_cnt + 4, (uint32_t)boundary_cap, ctx->b_bpos.as<uint32_t>());
+  t_end(ctx);
+  CU(cudaGetLastError());
+  return HM_OK;
+}
+
+}  // namespace
+
 static int call_chunks_impl(hm_ctx* ctx, const hm_chunk* chunks, size_t n_chunks, hm_site_record* out, size_t cap, size_t* n_out,
                             int64_t log[HM_CALL_LOG_LEN], bool async) {
   int rc = check_ready(ctx, chunks, n_chunks);
@@ -545,9 +752,16 @@ static int call_chunks_impl(hm_ctx* ctx, const hm_chunk* chunks, size_t n_chunks
   *n_out = 0;
   ctx->final_recs.clear();
   t_reset(ctx);
-  std::vector<uint64_t> pair_off;
-  if ((rc = upload_chunks(ctx, chunks, n_chunks, pair_off))) return rc;
+  std::vector<uint64_t> pair_off(n_chunks + 1, 0);
+  for (size_t i = 0; i < n_chunks; i++) pair_off[i + 1] = pair_off[i] + (chunks[i].read_hi - chunks[i].read_lo);
   const uint64_t n_pairs = pair_off.back();
+  uint64_t total_cap = 0, n_tiles = 0;
+  const bool fused = fused_eligible(ctx, chunks, n_chunks, n_pairs, &total_cap, &n_tiles);
+  ctx->call_path = fused ? 2 : 1;
+  if (!fused) {
+    if ((rc = upload(ctx, ctx->b_chunks, chunks, n_chunks))) return rc;
+    if ((rc = upload(ctx, ctx->b_pair_off, pair_off.data(), pair_off.size()))) return rc;
+  }
   // chunk geometry for the som_seen carry: a position can only have been claimed by an earlier
   // chunk if it lies at or below the largest chunk end seen so far, and only needs remembering if
   // a later chunk starts at or below it.  With the reference's own chunking that is just the
@@ -562,18 +776,58 @@ static int call_chunks_impl(hm_ctx* ctx, const hm_chunk* chunks, size_t n_chunks
     for (size_t i = n_chunks; i-- > 0;) { next_min_start[i] = m; m = std::min(m, chunks[i].start); }
   }
 
-  if (n_chunks && (rc = upload(ctx, ctx->b_geom, geom.data(), 2 * n_chunks))) return rc;
-  if ((rc = launch_read_scan(ctx))) return rc;
-
-  // counters (u64): [0] n_keys, [1] n_unique, [2] num_ccs, [3] error flag, [4] n_boundary, [8..23] status histogram
+  // counters (u64): [0] n_keys (first version), [1] n_unique, [2] num_ccs, [3] error flag, [4] n_boundary,
+  // [5] sites needed when the fused path's site buffers overflowed, [6] records kept by k_compact_sites,
+  // [7] some read failed the QV gate, [8..23] status histogram
   const size_t CNT_BYTES = 256;
   CU(ctx->b_counters.ensure(CNT_BYTES));
   if (!ctx->h_cnt_pin) CU(cudaHostAlloc((void**)&ctx->h_cnt_pin, CNT_BYTES + HM_BOUNDARY_FIRST * (8 + sizeof(hm_site_record)), cudaHostAllocMapped));
-  CU(ctx->b_qseen.ensure((size_t)ctx->max_qname_id + 1));
-  if (ctx->params.phase) CU(ctx->b_pair_hap.ensure(n_pairs + 16));
   unsigned long long h_cnt[32];
   memset(h_cnt, 0, sizeof(h_cnt));
   unsigned long long* d_cnt = ctx->b_counters.as<unsigned long long>();
+  const int parity = ctx->rec_parity;
+  DevBuf& rec_buf = parity ? ctx->b_records_alt : ctx->b_records;
+  const bool omit = ctx->omit_restatements;
+  size_t HM_BOUNDARY_CAP = HM_BOUNDARY_CAP_DEFAULT;
+  if (const char* e = getenv("HIMUT_B200_BOUNDARY_CAP")) HM_BOUNDARY_CAP = (size_t)std::max(0ll, atoll(e));
+  uint32_t* h_bidx = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(ctx->h_cnt_pin) + CNT_BYTES);
+  uint32_t* h_bpos = h_bidx + HM_BOUNDARY_FIRST;
+  hm_site_record* h_brecs = reinterpret_cast<hm_site_record*>(h_bpos + HM_BOUNDARY_FIRST);
+  unsigned long long n_keys = 0;
+
+  if (fused) {
+    uint64_t site_cap = std::max<uint64_t>(std::max<uint64_t>(ctx->site_cap_hint, ctx->n_ops_total / 8), 4096);
+    if (const char* e = getenv("HIMUT_B200_SITE_CAP")) site_cap = (uint64_t)std::max(1ll, atoll(e)); // tests: force the overflow retry
+    site_cap = std::min<uint64_t>(site_cap, std::max<uint64_t>(total_cap, 1));
+    for (int attempt = 0;; attempt++) {
+      t_reset(ctx);
+      FusedGeom G;
+      if ((rc = fused_enqueue(ctx, chunks, n_chunks, pair_off, geom.data(), total_cap, n_tiles, site_cap, parity, omit, HM_BOUNDARY_CAP, &G))) return rc;
+      t_begin(ctx, "k_count_flags");
+      k_count_flags<<<148, 256, 0, ctx->stream>>>(ctx->b_qseen.as<uint8_t>(), (uint64_t)ctx->max_qname_id + 1, d_cnt + 2);
+      t_end(ctx);
+      k_publish<<<1, 64, 0, ctx->stream>>>(reinterpret_cast<const uint32_t*>(d_cnt), reinterpret_cast<uint32_t*>(ctx->h_cnt_pin), (uint32_t)(CNT_BYTES / 4));
+      k_publish_items<<<4, 256, 0, ctx->stream>>>(ctx->b_bidx.as<uint32_t>(), h_bidx, 1u, (uint32_t)HM_BOUNDARY_FIRST, d_cnt + 4);
+      k_publish_items<<<8, 256, 0, ctx->stream>>>(ctx->b_brecs.as<uint32_t>(), reinterpret_cast<uint32_t*>(h_brecs),
+                                                  (uint32_t)(sizeof(hm_site_record) / 4), (uint32_t)HM_BOUNDARY_FIRST, d_cnt + 4);
+      k_publish_items<<<4, 256, 0, ctx->stream>>>(ctx->b_bpos.as<uint32_t>(), h_bpos, 1u, (uint32_t)HM_BOUNDARY_FIRST, d_cnt + 4);
+      CU(cudaGetLastError());
+      lap(4);
+      CU(cudaStreamSynchronize(ctx->stream)); // the one synchronisation of the call
+      lap(5);
+      memcpy(h_cnt, ctx->h_cnt_pin, CNT_BYTES);
+      if (!h_cnt[5]) break;
+      if (attempt >= 2) return fail(ctx, HM_ERR_STATE, "site buffers overflowed twice (%llu sites)", h_cnt[5]);
+      site_cap = std::min<uint64_t>(h_cnt[5] + h_cnt[5] / 8 + 1024, std::max<uint64_t>(total_cap, 1)); // the list overflowed: run again with room
+      memset(h_cnt, 0, sizeof(h_cnt));
+    }
+    ctx->site_cap_hint = std::max<uint64_t>(ctx->site_cap_hint, h_cnt[1] + h_cnt[1] / 4);
+    n_keys = h_cnt[1];
+  } else {
+  if (n_chunks && (rc = upload(ctx, ctx->b_geom, geom.data(), 2 * n_chunks))) return rc;
+  if ((rc = launch_read_scan(ctx))) return rc;
+  CU(ctx->b_qseen.ensure((size_t)ctx->max_qname_id + 1));
+  if (ctx->params.phase) CU(ctx->b_pair_hap.ensure(n_pairs + 16));
   unsigned long long key_cap = std::max<unsigned long long>(ctx->n_ops_total, 1024);
   // bits of (tpos - chunk.start): candidates satisfy start <= tpos <= end (is_chunk, caller.py:325)
   int pos_bits = 1;
@@ -613,19 +867,8 @@ static int call_chunks_impl(hm_ctx* ctx, const hm_chunk* chunks, size_t n_chunks
     if (h_cnt[0] <= key_cap) break;
     key_cap = h_cnt[0];
   }
-  const unsigned long long n_keys = h_cnt[0];
+  n_keys = h_cnt[0];
 
-  size_t n_unique = 0, n_boundary = 0;
-  const int parity = ctx->rec_parity;
-  DevBuf& rec_buf = parity ? ctx->b_records_alt : ctx->b_records;
-  const bool omit = ctx->omit_restatements;
-  size_t HM_BOUNDARY_CAP = HM_BOUNDARY_CAP_DEFAULT;
-  if (const char* e = getenv("HIMUT_B200_BOUNDARY_CAP")) HM_BOUNDARY_CAP = (size_t)std::max(0ll, atoll(e));
-  hm_site_record* recs = nullptr; // where the device records land on the host
-  bool direct = false;
-  bool have_all = false; // the records are already on the host (fallback of the boundary replay)
-  struct Border { uint32_t idx, pos; hm_site_record rec; }; // index in key order, index among the kept records, the record
-  std::vector<Border> border;
   if (n_pairs) {
     if (n_keys) {
       // sort + unique of the candidate keys (library plumbing: cub), then the site kernels
@@ -643,7 +886,7 @@ static int call_chunks_impl(hm_ctx* ctx, const hm_chunk* chunks, size_t n_chunks
       CU(cudaStreamSynchronize(ctx->stream));
       h_cnt[1] = ctx->h_cnt_pin[1];
       lap(3); // sync 2: distinct count
-      n_unique = (size_t)h_cnt[1];
+      const size_t n_unique = (size_t)h_cnt[1];
       const uint64_t stride = (n_unique + 31) & ~31ull;
       CU(ctx->b_agg.ensure(stride * HM_SITE_SLOTS * 4 + n_unique * 8));
       uint32_t* entries = ctx->b_agg.as<uint32_t>();
@@ -679,10 +922,10 @@ static int call_chunks_impl(hm_ctx* ctx, const hm_chunk* chunks, size_t n_chunks
       CU(cudaGetLastError());
       t_begin(ctx, "k_site_reduce");
       k_site_reduce<<<(unsigned)((n_unique + 127) / 128), 128, 0, ctx->stream>>>(
-          ctx->db, ctx->dp, ctx->dsets, ctx->dlut, ctx->b_chunks.as<hm_chunk>(), ctx->b_pair_off.as<uint64_t>(),
+          ctx->db, ctx->dp, ctx->dsets, ctx->dlut, ctx->dphase, ctx->dup_names ? 1 : 0, ctx->b_chunks.as<hm_chunk>(), ctx->b_pair_off.as<uint64_t>(),
           ctx->b_pair_hap.as<uint8_t>(), ctx->b_geom.as<int32_t>(), ctx->b_geom.as<int32_t>() + n_chunks, k_in, d_cnt + 1, site_lo,
           site_n, entries, stride, rec_buf.as<hm_site_record>(), d_cnt + 8, ctx->b_bidx.as<uint32_t>(),
-          ctx->b_brecs.as<hm_site_record>(), (uint32_t)HM_BOUNDARY_CAP, d_cnt + 4, reinterpret_cast<int*>(d_cnt + 3));
+          ctx->b_brecs.as<hm_site_record>(), (uint32_t)HM_BOUNDARY_CAP, d_cnt + 4, reinterpret_cast<int*>(d_cnt + 3), nullptr, nullptr, nullptr, 0);
       if (omit) { // records of germline restatements stay here: flags -> scan -> stable compaction
         CU(ctx->b_keep.ensure(n_unique * 4 + 16)); CU(ctx->b_kpos.ensure(n_unique * 4 + 16));
         CU(ctx->b_bpos.ensure(((size_t)HM_BOUNDARY_CAP + HM_BOUNDARY_FIRST) * 4));
@@ -709,9 +952,6 @@ static int call_chunks_impl(hm_ctx* ctx, const hm_chunk* chunks, size_t n_chunks
     // First the small things: counters and the boundary records (the only ones the sequential som_seen replay
     // looks at).  The big record copy follows the replay, so records a previous chunk already claimed are skipped
     // by the copy itself instead of being squeezed out of 20 MB on the host.
-    uint32_t* h_bidx = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(ctx->h_cnt_pin) + CNT_BYTES);
-    uint32_t* h_bpos = h_bidx + HM_BOUNDARY_FIRST;
-    hm_site_record* h_brecs = reinterpret_cast<hm_site_record*>(h_bpos + HM_BOUNDARY_FIRST);
     k_publish<<<1, 64, 0, ctx->stream>>>(reinterpret_cast<const uint32_t*>(d_cnt), reinterpret_cast<uint32_t*>(ctx->h_cnt_pin), (uint32_t)(CNT_BYTES / 4));
     if (n_keys) {
       k_publish_items<<<4, 256, 0, ctx->stream>>>(ctx->b_bidx.as<uint32_t>(), h_bidx, 1u, (uint32_t)HM_BOUNDARY_FIRST, d_cnt + 4);
@@ -724,12 +964,28 @@ static int call_chunks_impl(hm_ctx* ctx, const hm_chunk* chunks, size_t n_chunks
     CU(cudaStreamSynchronize(ctx->stream));
     lap(5); // sync 3: site kernels
     memcpy(h_cnt, ctx->h_cnt_pin, CNT_BYTES);
+  }
+  } // first version
+
+  // ---- from here on both versions: counters are on the host, records still on the device ----
+  size_t n_unique = (size_t)h_cnt[1], n_boundary = 0;
+  // compacted: the records the host copies sit in b_compact (germline restatements left out when asked; the fused
+  // path always compacts, it may have dropped speculative sites); boundary records are addressed through their
+  // position there (h_bpos)
+  const bool compacted = fused || omit;
+  hm_site_record* recs = nullptr; // where the device records land on the host
+  bool direct = false;
+  bool have_all = false; // the records are already on the host (fallback of the boundary replay)
+  struct Border { uint32_t idx, pos; hm_site_record rec; }; // index in key order, index among the kept records, the record
+  std::vector<Border> border;
+  unsigned long long* hist = h_cnt + 8;
+  const size_t n_restate0 = (size_t)(hist[HM_ST_GERM_HET] + hist[HM_ST_GERM_HETALT] + hist[HM_ST_GERM_HOMALT] + hist[HM_ST_GERM_HOMREF]);
+  if (n_pairs) {
     if ((int)h_cnt[3] == HM_ERR_BQ_ZERO) return fail(ctx, HM_ERR_BQ_ZERO, "a base quality of 0 reached the genotype model (the reference raises ValueError: math.log10(0))");
     n_boundary = n_keys ? (size_t)h_cnt[4] : 0;
     // records go straight into the caller's buffer when it is large enough, else into pinned staging
     {
-      const unsigned long long* hh = h_cnt + 8;
-      const size_t n_ret = omit ? n_unique - (size_t)(hh[HM_ST_GERM_HET] + hh[HM_ST_GERM_HETALT] + hh[HM_ST_GERM_HOMALT] + hh[HM_ST_GERM_HOMREF]) : n_unique;
+      const size_t n_ret = fused ? (size_t)h_cnt[6] : (omit ? n_unique - n_restate0 : n_unique);
       const size_t n_host = n_boundary > HM_BOUNDARY_CAP ? n_unique : n_ret; // the host fallback of the replay fetches everything
       direct = out && cap >= n_host;
       if (n_host && !direct) {
@@ -750,19 +1006,20 @@ static int call_chunks_impl(hm_ctx* ctx, const hm_chunk* chunks, size_t n_chunks
       CU(cudaStreamSynchronize(ctx->stream));
       border.clear();
       for (size_t i = 0; i < n_unique; i++)
-        if (recs[i].tpos <= prev_max_end[recs[i].chunk] || recs[i].tpos >= next_min_start[recs[i].chunk]) border.push_back(Border{(uint32_t)i, 0u, recs[i]});
+        if (recs[i].status != HM_ST_INTERNAL_DROPPED &&
+            (recs[i].tpos <= prev_max_end[recs[i].chunk] || recs[i].tpos >= next_min_start[recs[i].chunk])) border.push_back(Border{(uint32_t)i, 0u, recs[i]});
       n_boundary = border.size();
       have_all = true;
     } else if (n_boundary) {
       border.resize(n_boundary);
       if (n_boundary <= (size_t)HM_BOUNDARY_FIRST) {
-        for (size_t i = 0; i < n_boundary; i++) border[i] = Border{h_bidx[i], omit ? h_bpos[i] : 0u, h_brecs[i]};
+        for (size_t i = 0; i < n_boundary; i++) border[i] = Border{h_bidx[i], compacted ? h_bpos[i] : 0u, h_brecs[i]};
       } else {
         std::vector<uint32_t> bi(n_boundary), bp(n_boundary, 0u);
         std::vector<hm_site_record> br(n_boundary);
         CU(cudaMemcpyAsync(bi.data(), ctx->b_bidx.p, n_boundary * 4, cudaMemcpyDeviceToHost, ctx->stream));
         CU(cudaMemcpyAsync(br.data(), ctx->b_brecs.p, n_boundary * sizeof(hm_site_record), cudaMemcpyDeviceToHost, ctx->stream));
-        if (omit) CU(cudaMemcpyAsync(bp.data(), ctx->b_bpos.p, n_boundary * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        if (compacted) CU(cudaMemcpyAsync(bp.data(), ctx->b_bpos.p, n_boundary * 4, cudaMemcpyDeviceToHost, ctx->stream));
         CU(cudaStreamSynchronize(ctx->stream));
         for (size_t i = 0; i < n_boundary; i++) border[i] = Border{bi[i], bp[i], br[i]};
       }
@@ -772,10 +1029,10 @@ static int call_chunks_impl(hm_ctx* ctx, const hm_chunk* chunks, size_t n_chunks
 
   // sequential part: chunk order, som_seen carry (caller.py:324-347; bamlib.py:77), over the
   // boundary records only.  Indices are positions in the key order = (chunk, tpos, ref, alt).
-  unsigned long long* hist = h_cnt + 8;
   std::vector<uint32_t> dropped;
   // restatement records are counted before any of them is dropped by the replay
-  const size_t n_restate = (size_t)(hist[HM_ST_GERM_HET] + hist[HM_ST_GERM_HETALT] + hist[HM_ST_GERM_HOMALT] + hist[HM_ST_GERM_HOMREF]);
+  const size_t n_restate = n_restate0;
+  const bool in_compact = compacted && !have_all; // the copy below reads b_compact
   if (n_boundary) {
     std::sort(border.begin(), border.end(), [](const Border& a, const Border& b) { return a.idx < b.idx; });
     std::unordered_set<int32_t> som_seen;
@@ -788,7 +1045,7 @@ static int call_chunks_impl(hm_ctx* ctx, const hm_chunk* chunks, size_t n_chunks
         const hm_site_record& R = border[i].rec;
         const bool restates = R.status >= HM_ST_GERM_HET && R.status <= HM_ST_GERM_HOMREF;
         if (R.tpos <= prev_max_end[chunk] && som_seen.count(R.tpos)) { // dropped in get_tsbs_candidates
-          if (!(omit && !have_all && restates)) dropped.push_back((omit && !have_all) ? border[i].pos : border[i].idx);
+          if (!(in_compact && omit && restates)) dropped.push_back(in_compact ? border[i].pos : border[i].idx);
           hist[R.status]--;
           continue;
         }
@@ -796,11 +1053,11 @@ static int call_chunks_impl(hm_ctx* ctx, const hm_chunk* chunks, size_t n_chunks
       }
       for (int32_t t : adds) som_seen.insert(t);
     }
+    std::sort(dropped.begin(), dropped.end());
   }
-  // what the copy below walks over: every record, or (restatements omitted) the compacted ones
-  const bool from_compact = omit && !have_all;
-  const size_t n_source = from_compact ? n_unique - n_restate : n_unique;
-  const hm_site_record* d_source = from_compact ? ctx->b_compact[parity].as<hm_site_record>() : rec_buf.as<hm_site_record>();
+  // what the copy below walks over: every record, or the compacted ones
+  const size_t n_source = !in_compact ? n_unique : (fused ? (size_t)h_cnt[6] : n_unique - n_restate);
+  const hm_site_record* d_source = in_compact ? ctx->b_compact[parity].as<hm_site_record>() : rec_buf.as<hm_site_record>();
   // the records, minus the dropped ones (ascending indices): one copy per run between two dropped records
   if ((rc = flush_deferred(ctx, false))) return rc; // an earlier call's copies, if this call had no sort to put them behind
   size_t n_final = 0;
@@ -812,10 +1069,14 @@ static int call_chunks_impl(hm_ctx* ctx, const hm_chunk* chunks, size_t n_chunks
       n_final += to - from;
       from = to + 1;
     }
-    if (omit) { // the slow path has everything on the host: drop the restatements here
+    if (omit || fused) { // the slow path has everything on the host: drop here what the compaction would have
       size_t w = 0;
-      for (size_t i = 0; i < n_final; i++)
-        if (!(recs[i].status >= HM_ST_GERM_HET && recs[i].status <= HM_ST_GERM_HOMREF)) { if (w != i) recs[w] = recs[i]; w++; }
+      for (size_t i = 0; i < n_final; i++) {
+        const uint8_t st = recs[i].status;
+        if (st == HM_ST_INTERNAL_DROPPED || (omit && st >= HM_ST_GERM_HET && st <= HM_ST_GERM_HOMREF)) continue;
+        if (w != i) recs[w] = recs[i];
+        w++;
+      }
       n_final = w;
     }
   } else if (n_unique) {
@@ -853,8 +1114,8 @@ static int call_chunks_impl(hm_ctx* ctx, const hm_chunk* chunks, size_t n_chunks
   *n_out = n_final;
   lap(7); // host replay
   if (host_timing)
-    fprintf(stderr, "[host timing, dev %d] enqueue %.3f | sync1 %.3f | sort enqueue %.3f | sync2 %.3f | sites enqueue %.3f | sync3 %.3f | boundary %.3f | replay %.3f ms\n",
-            ctx->device, ht[0], ht[1], ht[2], ht[3], ht[4], ht[5], ht[6], ht[7]);
+    fprintf(stderr, "[host timing, dev %d, %s] enqueue %.3f | sync1 %.3f | sort enqueue %.3f | sync2 %.3f | sites enqueue %.3f | sync3 %.3f | boundary %.3f | replay %.3f ms\n",
+            ctx->device, fused ? "fused" : "first version", ht[0], ht[1], ht[2], ht[3], ht[4], ht[5], ht[6], ht[7]);
   if (!direct && n_final) {
     if (out && cap >= n_final) memcpy(out, recs, n_final * sizeof(hm_site_record));
     else {
@@ -1039,6 +1300,8 @@ int hm_last_timing(hm_ctx* ctx, float* total_ms, int* n_launches) {
   if (n_launches) *n_launches = ctx->last_launches;
   return HM_OK;
 }
+
+int hm_last_call_path(hm_ctx* ctx) { return !ctx ? 0 : (ctx->call_path); }
 
 int hm_last_kernel_times(hm_ctx* ctx, const char** names, float* ms, size_t cap, size_t* n) {
   if (!ctx || !n) return HM_ERR_ARG;

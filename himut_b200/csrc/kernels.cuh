@@ -299,6 +299,10 @@ __device__ __forceinline__ bool key_in_dev(const uint64_t* a, uint64_t n, uint64
   return lo < n && __ldg(a + lo) == key;
 }
 
+// the match-run base a batch without a base stream takes at a phased hetSNP (hm_set_phase_sets): href 0..3 is the
+// reference base itself; 16 + c says "REF has several bases (never equal to a read base), its first base is c"
+__device__ __forceinline__ int href_match_base(int hr) { return hr < 4 ? hr : ((hr & 0xf0) == 0x10 ? (hr & 3) : 4); }
+
 // haplib.get_ccs_hap (haplib.py:61-83) for a whole warp: 0 / 1 / 2 (".")
 __device__ __forceinline__ int warp_read_hap(const DevBatch& b, uint64_t r, const DevPhase& ph, int set, int lane) {
   if (set < 0 || (uint32_t)set >= ph.n_sets) return 2;
@@ -311,7 +315,7 @@ __device__ __forceinline__ int warp_read_hap(const DevBatch& b, uint64_t r, cons
   bool h0 = true, h1 = true;
   for (uint32_t k = idx + lane; k < jdx; k += 32) {
     int bq, ins;
-    const int a = read_allele_at(b, r, hp[k] - 1, (int)ph.href[s0 + k], &bq, &ins);
+    const int a = read_allele_at(b, r, hp[k] - 1, href_match_base((int)ph.href[s0 + k]), &bq, &ins);
     int bit = 2;
     if (a >= 0 && a < 4) {
       if (a == (int)ph.href[s0 + k]) bit = 0;
@@ -323,6 +327,51 @@ __device__ __forceinline__ int warp_read_hap(const DevBatch& b, uint64_t r, cons
   }
   h0 = __all_sync(HM_FULL, h0);
   h1 = __all_sync(HM_FULL, h1);
+  return h0 ? 0 : (h1 ? 1 : 2);
+}
+
+// haplib.get_ccs_hap for one thread: the read's ops walked once, merged with the phase set's hetSNPs in position
+// order.  Needs nothing k_read_scan derives (no op prefix arrays).  Used where a record has no (chunk, read) pair of
+// its own: the records the reference re-fetches at a phase-checked site (caller.py:558) that share a query name with
+// a read of the site's pileup.
+__device__ __noinline__ int thread_read_hap_walk(const DevBatch& b, uint64_t r, const DevPhase& ph, int set) {
+  if (set < 0 || (uint32_t)set >= ph.n_sets) return 2;
+  const uint64_t s0 = ph.set_off[set];
+  const uint32_t n = (uint32_t)(ph.set_off[set + 1] - s0);
+  const int32_t* hp = ph.hpos + s0;
+  const int32_t ts = b.tstart[r];
+  const uint32_t idx = upper_bound_dev(hp, n, ts);
+  const uint32_t jdx = upper_bound_dev(hp, n, b.tend[r]);
+  if (jdx - idx < 2) return 2;
+  const uint64_t o0 = b.op_off[r];
+  const uint32_t nops = b.n_ops[r];
+  uint32_t k = 0, t0 = 0, q0 = (uint32_t)b.qstart[r];
+  bool h0 = true, h1 = true;
+  for (uint32_t i = idx; i < jdx; i++) {
+    const uint32_t off = (uint32_t)(hp[i] - 1 - ts);
+    int a = -1;
+    while (k < nops) { // the op that holds reference offset `off`
+      const uint32_t w = __ldg(b.ops + o0 + k);
+      const uint32_t rl = (uint32_t)op_ref_len(w);
+      if (rl && off < t0 + rl) {
+        const uint32_t kind = w & 3u, v = w >> 2;
+        if (kind == HM_OP_DEL) a = 5;
+        else if (kind == HM_OP_SUB) a = (int)((v >> 3) & 7u);
+        else if (!b.seq) a = href_match_base((int)ph.href[s0 + i]);
+        else { const uint32_t q = q0 + (off - t0); a = (b.seq[b.seq_off[r] + (q >> 2)] >> (2 * (q & 3u))) & 3; }
+        break;
+      }
+      t0 += rl; q0 += (uint32_t)op_qry_len(w); k++;
+    }
+    int bit = 2;
+    if (a >= 0 && a < 4) {
+      if (a == (int)ph.href[s0 + i]) bit = 0;
+      else if (a == (int)ph.halt[s0 + i]) bit = 1;
+    }
+    const int hb = ph.hbit[s0 + i];
+    if (bit != hb) h0 = false;
+    if (bit != 1 - hb) h1 = false;
+  }
   return h0 ? 0 : (h1 ? 1 : 2);
 }
 
@@ -723,21 +772,43 @@ __global__ void __launch_bounds__(256) k_site_entries_by_read(DevBatch b, DevPar
   }
 }
 
-__global__ void __launch_bounds__(128) k_site_reduce(DevBatch b, DevParams p, DevSets sets, DevLut lut, const hm_chunk* chunks,
+// status of a record that is not one: a speculative candidate none of whose supporting reads passed the QV gate
+// (fused path, callfused.cuh); never leaves the device
+#define HM_ST_INTERNAL_DROPPED 31
+
+// ph / dup_names: two primary records of the batch share a query name.  The reference classifies the records it
+//   re-fetches at a phase-checked site by *name* (wt_ccs_set / alt_ccs_set, caller.py:556-567); with unique names
+//   that is the record's own allele (the entries' haplotype tallies), with shared names the exact walk below.
+// site_valid / qv_fail (fused path, else NULL): *qv_fail != 0 -> only sites with site_valid[ki] exist.
+// keep_cnt (fused path, else NULL): per block, the number of records the host wants (not dropped; not a germline
+//   restatement when omit != 0).
+__global__ void __launch_bounds__(128) k_site_reduce(DevBatch b, DevParams p, DevSets sets, DevLut lut, DevPhase ph, int dup_names,
+                                                     const hm_chunk* chunks,
                                                      const uint64_t* pair_off, const uint8_t* pair_hap, const int32_t* prev_max_end,
                                                      const int32_t* next_min_start, const unsigned long long* keys,
                                                      const unsigned long long* n_keys_dev, const uint32_t* site_lo,
                                                      const uint32_t* site_n, const uint32_t* entries, uint64_t stride,
                                                      hm_site_record* out, unsigned long long* status_hist, uint32_t* boundary_idx,
                                                      hm_site_record* boundary_recs, uint32_t boundary_cap,
-                                                     unsigned long long* n_boundary, int* err_flag) {
+                                                     unsigned long long* n_boundary, int* err_flag,
+                                                     const uint8_t* site_valid, const unsigned int* qv_fail, uint32_t* keep_cnt, int omit) {
   __shared__ unsigned int s_hist[16];
+  __shared__ unsigned int s_keep;
   __shared__ double s_lut[3][256];
   for (int i = threadIdx.x; i < 768; i += blockDim.x) s_lut[i >> 8][i & 255] = __ldg(lut.lut + i);
   if (threadIdx.x < 16) s_hist[threadIdx.x] = 0;
+  if (threadIdx.x == 0) s_keep = 0;
   __syncthreads();
   const uint64_t ki = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (ki < *n_keys_dev) {
+  const uint64_t n_keys = *n_keys_dev;
+  if (ki < n_keys && site_valid && *qv_fail && !site_valid[ki]) {
+    hm_site_record R;
+    memset(&R, 0, sizeof(R));
+    R.tpos = (int32_t)((keys[ki] >> 4) & 0xffffffffull);
+    R.chunk = (int32_t)(keys[ki] >> 36);
+    R.status = HM_ST_INTERNAL_DROPPED; // k_compact_sites skips it; not tallied, not a boundary record
+    out[ki] = R;
+  } else if (ki < n_keys) {
     const unsigned long long key = keys[ki];
     const uint32_t c = (uint32_t)(key >> 36);
     const int32_t tpos = (int32_t)((key >> 4) & 0xffffffffull);
@@ -751,14 +822,12 @@ __global__ void __launch_bounds__(128) k_site_reduce(DevBatch b, DevParams p, De
     double SS[4][3];
 #pragma unroll
     for (int x = 0; x < 4; x++) { SS[x][0] = 0.0; SS[x][1] = 0.0; SS[x][2] = 0.0; }
-    for (uint32_t s = 0; s < n; s++) {
-      const uint32_t e = s < HM_SITE_SLOTS ? __ldg(entries + (uint64_t)s * stride + ki)
-                                           : site_entry(b, p, ch, c, pair_off, pair_hap, lo + s, tpos - 1, ref); // very deep pileups
-      if (e == HM_ENT_UNWRITTEN) continue; // a read of the range that does not reach the site
+    auto acc = [&](uint32_t e) {
+      if (e == HM_ENT_UNWRITTEN) return; // a read of the range that does not reach the site
       const uint32_t a = e & 7u;
       cnt[4] += (int)((e >> 11) & 255u);
-      if (a == HM_ENT_NONE) continue;
-      if (a == 5u) { cnt[5]++; continue; }
+      if (a == HM_ENT_NONE) return;
+      if (a == 5u) { cnt[5]++; return; }
       const int bq = (int)((e >> 3) & 255u);
       const uint32_t hap = (e >> 19) & 3u;
       const bool next_cov = (e >> 21) & 1u;
@@ -776,7 +845,18 @@ __global__ void __launch_bounds__(128) k_site_reduce(DevBatch b, DevParams p, De
         if ((int)a == ref) { h0 += (hap == 0u); h1 += (hap == 1u); }
         else if ((int)a == alt) { if (hap == 0u) som_mask |= 1; else if (hap == 1u) som_mask |= 2; }
       }
+    };
+    // slots in file order: the first HM_SITE_SLOTS from the gathered entries (eight independent loads at a time),
+    // deeper pileups computed here
+    const uint32_t n_slot = min(n, (uint32_t)HM_SITE_SLOTS);
+    for (uint32_t s0 = 0; s0 < n_slot; s0 += 8) {
+      uint32_t ev[8];
+#pragma unroll
+      for (int j = 0; j < 8; j++) ev[j] = (s0 + j < n_slot) ? __ldg(entries + (uint64_t)(s0 + j) * stride + ki) : HM_ENT_UNWRITTEN;
+#pragma unroll
+      for (int j = 0; j < 8; j++) acc(ev[j]);
     }
+    for (uint32_t s = HM_SITE_SLOTS; s < n; s++) acc(site_entry(b, p, ch, c, pair_off, pair_hap, lo + s, tpos - 1, ref));
     if (bq_zero) *err_flag = HM_ERR_BQ_ZERO;
 
     double pl[10];
@@ -815,6 +895,33 @@ __global__ void __launch_bounds__(128) k_site_reduce(DevBatch b, DevParams p, De
       else {
         status = HM_ST_PASS;
         if (p.phase) { // caller.py:552-603
+          if (dup_names) {
+            // Query names are shared: do what the reference does.  Every primary record of the file that overlaps
+            // [tpos, tpos + 1) (alignments.fetch(chrom, tpos, tpos + 1)) is classified by whether its *name* is
+            // among the names of the pileup's ref-allele reads, else of its alt-allele reads; its own haplotype counts.
+            h0 = 0; h1 = 0; som_mask = 0;
+            const uint32_t r_lo = count_le_kary_i32(b.pmax_tend, (uint32_t)b.n_reads, tpos); // first read with running max(tend) > tpos
+            for (uint32_t r = r_lo; r < (uint32_t)b.n_reads && __ldg(b.tstart + r) < tpos + 1; r++) {
+              if (!(__ldg(b.tend + r) > tpos) || (__ldg(b.flags + r) & HM_READ_SECONDARY)) continue;
+              const uint32_t q = __ldg(b.qname_id + r);
+              bool in_wt = false, in_alt = false;
+              for (uint32_t s = 0; s < n; s++) {
+                if (__ldg(b.qname_id + lo + s) != q) continue;
+                const uint32_t e = s < HM_SITE_SLOTS ? __ldg(entries + (uint64_t)s * stride + ki)
+                                                     : site_entry(b, p, ch, c, pair_off, pair_hap, lo + s, tpos - 1, ref);
+                if (e == HM_ENT_UNWRITTEN) continue;
+                const int a = (int)(e & 7u);
+                if (a == ref) { in_wt = true; break; }
+                if (a == alt) in_alt = true;
+              }
+              if (!in_wt && !in_alt) continue;
+              int hap = 3;
+              if (r >= ch.read_lo && r < ch.read_hi) hap = pair_hap[pair_off[c] + (r - ch.read_lo)];
+              if (hap == 3) hap = thread_read_hap_walk(b, r, ph, ch.phase_set); // not fetched by this chunk
+              if (in_wt) { h0 += (hap == 0); h1 += (hap == 1); }
+              else if (hap < 2) som_mask |= 1 << hap;
+            }
+          }
           if (h0 >= p.min_hap_count && h1 >= p.min_hap_count && (som_mask == 1 || som_mask == 2)) phase_set = ch.start;
           else status = HM_ST_UNPHASED;
         }
@@ -835,6 +942,7 @@ __global__ void __launch_bounds__(128) k_site_reduce(DevBatch b, DevParams p, De
     R.phase_set = phase_set;
     out[ki] = R;
     atomicAdd(&s_hist[status], 1u);
+    if (!(omit && status >= HM_ST_GERM_HET && status <= HM_ST_GERM_HOMREF)) atomicAdd(&s_keep, 1u);
     if (tpos <= prev_max_end[c] || tpos >= next_min_start[c]) {
       const unsigned long long at = atomicAdd(n_boundary, 1ull);
       if (at < boundary_cap) { boundary_idx[at] = (uint32_t)ki; boundary_recs[at] = R; } // a copy for the host's som_seen replay
@@ -842,6 +950,7 @@ __global__ void __launch_bounds__(128) k_site_reduce(DevBatch b, DevParams p, De
   }
   __syncthreads();
   if (threadIdx.x < 16 && s_hist[threadIdx.x]) atomicAdd(status_hist + threadIdx.x, (unsigned long long)s_hist[threadIdx.x]);
+  if (keep_cnt && threadIdx.x == 0) keep_cnt[blockIdx.x] = s_keep;
 }
 
 // Small results go to the host through mapped pinned memory (plain stores over PCIe) instead of the copy engine,

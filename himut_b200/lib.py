@@ -20,7 +20,7 @@ EXPORTS = [
     "hm_set_phase_sets", "hm_upload_batch", "hm_call_chunks", "hm_call_batch", "hm_normcounts_chunks",
     "hm_read_stats", "hm_last_timing", "hm_last_kernel_times", "hm_set_stream", "hm_host_register",
     "hm_host_unregister", "hm_abi_sizeof", "hm_last_records", "hm_qname_seen", "hm_set_reference", "hm_ref_tricounts", "hm_last_norm_exact_sites",
-    "hm_phase_edges_begin", "hm_phase_edges_add", "hm_phase_edges_end", "hm_upload_batch_compact", "hm_call_batch_compact", "hm_call_chunks_async", "hm_records_wait", "hm_set_option",
+    "hm_phase_edges_begin", "hm_phase_edges_add", "hm_phase_edges_end", "hm_upload_batch_compact", "hm_call_batch_compact", "hm_call_chunks_async", "hm_records_wait", "hm_set_option", "hm_last_call_path",
 ]
 
 
@@ -71,6 +71,8 @@ def load():
         lib.hm_phase_edges_add.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_uint32)]
         lib.hm_phase_edges_end.argtypes = [vp, vp, sz]
         lib.hm_set_stream.argtypes = [vp, vp]
+        lib.hm_last_call_path.argtypes = [vp]
+        lib.hm_last_call_path.restype = C.c_int
         lib.hm_host_register.argtypes = [vp, vp, sz]
         lib.hm_host_unregister.argtypes = [vp, vp]
         _LIB = lib
@@ -293,6 +295,10 @@ class Context:
         out = np.zeros(n.value, np.uint8)
         self._chk(self.lib.hm_qname_seen(self.h, _p(out), out.size, C.byref(n)))
         return out
+
+    def last_call_path(self):
+        """2: the last call_chunks ran the fused device path, 1: the first version, 0: none yet"""
+        return int(self.lib.hm_last_call_path(self.h))
 
     def last_timing(self):
         ms, n = C.c_float(0), C.c_int(0)

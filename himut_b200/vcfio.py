@@ -183,8 +183,16 @@ def phase_tables(chunkloci_lst, phase_set2hbit_lst, phase_set2hpos_lst, phase_se
             index[key] = len(set_off) - 1
             for p, s, b in zip(pos, snp, bits):
                 hpos.append(int(p))
-                # multi-base (indel) alleles can never equal a read base: code 255
-                href.append(abi.BASE2CODE.get(s[1], 255) if len(s[1]) == 1 else 255)
+                # the reference compares the read's one-letter base with the REF / ALT *strings*
+                # (haplib.get_ccs_hbit, haplib.py:46-58): an indel allele (or a lower-case one) never equals it: 255.
+                # A batch without its base stream (`call`) takes the base of a cs match run from the table: the
+                # contig's base at hpos is REF's first letter, so a REF that can never be equal is stored as
+                # 16 + code(REF[0]) — "never equal, but this is what a matching read shows" (the ALT test then sees
+                # the real base, e.g. REF=AT ALT=A gives bit 1 for every read that matches at the anchor)
+                ref_code = abi.BASE2CODE.get(s[1], 255) if len(s[1]) == 1 else 255
+                if ref_code == 255 and s[1][:1].upper() in abi.BASE2CODE:
+                    ref_code = 16 + abi.BASE2CODE[s[1][:1].upper()]
+                href.append(ref_code)
                 halt.append(abi.BASE2CODE.get(s[2], 255) if len(s[2]) == 1 else 255)
                 hbit.append(int(b) if b in ("0", "1") else 2)
             set_off.append(len(hpos))

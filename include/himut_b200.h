@@ -248,7 +248,10 @@ int hm_set_site_sets(hm_ctx* ctx, const uint64_t* common_sorted, size_t n_common
 
 /* phased hetSNPs of the current contig (vcflib.load_phased_hetsnps): phase set s owns
  * entries set_off[s] .. set_off[s+1]; hpos is 1-based and ascending inside a set; hbit is
- * the h0 bit (0/1); set_id[s] is the set's chunk_start (the reference's phase_set key).    */
+ * the h0 bit (0/1); set_id[s] is the set's chunk_start (the reference's phase_set key).
+ * href / halt: base codes 0..3; 255 = an allele no read base can equal (an indel allele: the reference compares
+ * the read's one-letter base with the allele string, haplib.py:46-58); href 16 + c = REF can never be equal but its
+ * first base is c — what a batch without a base stream shows in a cs match run at that position.               */
 int hm_set_phase_sets(hm_ctx* ctx, const int32_t* hpos, const uint8_t* href,
                       const uint8_t* halt, const uint8_t* hbit, size_t n_hetsnp,
                       const uint64_t* set_off, size_t n_sets);
@@ -350,6 +353,10 @@ int hm_read_stats(hm_ctx* ctx, int64_t* bq_total, int32_t* n_match, int32_t* n_s
  * events): total device milliseconds and the launch count.  names/ms give per-kernel
  * figures for up to `cap` kernels; returns how many were written in *n.                    */
 int hm_last_timing(hm_ctx* ctx, float* total_ms, int* n_launches);
+/* which device path the last hm_call_chunks took: 2 the fused one (one pass over the quality stream, no library
+ * sort, one synchronisation), 1 the first version (chunk spans of 2^28 positions and more, or HIMUT_B200_CALL_V1 set),
+ * 0 none yet.  Same records either way; for tests and bench.py.                                              */
+int hm_last_call_path(hm_ctx* ctx);
 int hm_last_kernel_times(hm_ctx* ctx, const char** names, float* ms, size_t cap, size_t* n);
 
 #ifdef __cplusplus
