@@ -600,6 +600,37 @@ __device__ __forceinline__ int read_allele_fast(const DevBatch& b, uint32_t r, i
   return (b.seq[__ldg(b.seq_off + r) + (q >> 2)] >> (2 * (q & 3u))) & 3;
 }
 
+// read_allele_fast without the op prefix arrays (the fused path does not keep them in HBM): one walk over the read's
+// ops.  Only the slots past HM_SITE_SLOTS of very deep pileups are answered this way.
+__device__ __noinline__ int read_allele_walk(const DevBatch& b, uint32_t r, int32_t rpos, int32_t ts, int ref_base, int* bq, int* ins) {
+  const uint32_t n = __ldg(b.n_ops + r);
+  *bq = 0; *ins = 0;
+  const uint64_t o0 = __ldg(b.op_off + r);
+  const uint32_t off = (uint32_t)(rpos - ts);
+  uint32_t t = 0, q = (uint32_t)__ldg(b.qstart + r);
+  uint32_t lw = 0, lt = 0, lq = 0;
+  bool have = false;
+  int cnt = 0;
+  for (uint32_t k = 0; k < n; k++) { // the last op that starts at or before `off`; insertions that start at it
+    const uint32_t w = __ldg(b.ops + o0 + k);
+    if (t > off) break;
+    if (t == off && (w & 3u) == HM_OP_INS) cnt++;
+    lw = w; lt = t; lq = q; have = true;
+    t += (uint32_t)op_ref_len(w); q += (uint32_t)op_qry_len(w);
+  }
+  *ins = cnt;
+  if (!have) return -1;
+  const uint32_t kind = lw & 3u, v = lw >> 2;
+  const uint32_t rl = (uint32_t)op_ref_len(lw);
+  if (rl == 0 || off >= lt + rl) return -1;
+  if (kind == HM_OP_DEL) return 5;
+  const uint32_t qq = lq + (kind == HM_OP_MATCH ? off - lt : 0u);
+  *bq = b.bq[__ldg(b.bq_off + r) + qq];
+  if (kind == HM_OP_SUB) return (int)((v >> 3) & 7u);
+  if (!b.seq) return ref_base;
+  return (b.seq[__ldg(b.seq_off + r) + (qq >> 2)] >> (2 * (qq & 3u))) & 3;
+}
+
 // ============================================================================ site kernels
 // The pileup column of a candidate site is gathered in three steps so every thread has work and
 // the order-sensitive part stays sequential per site:
@@ -619,15 +650,16 @@ __device__ __forceinline__ int read_allele_fast(const DevBatch& b, uint32_t r, i
 
 // entry: bits 0-2 allele (0-3 base, 5 deleted, 7 none), 3-10 BQ, 11-18 insertions at the site,
 //        19-20 haplotype (0, 1, 2 ".", 3 not fetched), 21 read also covers the next position
+// walk: the batch's op prefix arrays are not filled (fused path)
 __device__ __forceinline__ uint32_t site_entry(const DevBatch& b, const DevParams& p, const hm_chunk& ch, uint32_t c,
                                                const uint64_t* pair_off, const uint8_t* pair_hap, uint32_t r, int32_t rpos,
-                                               int ref_base) {
+                                               int ref_base, bool walk = false) {
   uint32_t e = HM_ENT_NONE;
   if (!(__ldg(b.flags + r) & HM_READ_SECONDARY)) {
     const int32_t ts = __ldg(b.tstart + r), te = __ldg(b.tend + r);
     if (ts < ch.end && te > ch.start && ts <= rpos && rpos <= te) {
       int bq, ins;
-      const int a = read_allele_fast(b, r, rpos, ts, ref_base, &bq, &ins);
+      const int a = walk ? read_allele_walk(b, r, rpos, ts, ref_base, &bq, &ins) : read_allele_fast(b, r, rpos, ts, ref_base, &bq, &ins);
       const uint32_t hap = p.phase ? pair_hap[pair_off[c] + (r - ch.read_lo)] : 2u;
       e = (a < 0 ? HM_ENT_NONE : (uint32_t)a) | ((uint32_t)bq << 3) | ((uint32_t)min(ins, 255) << 11) | ((hap & 3u) << 19) |
           ((te > rpos + 1) ? (1u << 21) : 0u); // overlaps [tpos, tpos + 1) (caller.py:558)
@@ -801,6 +833,7 @@ __global__ void __launch_bounds__(128) k_site_reduce(DevBatch b, DevParams p, De
   __syncthreads();
   const uint64_t ki = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const uint64_t n_keys = *n_keys_dev;
+  const bool fused = site_valid != nullptr; // no op prefix arrays in HBM then
   if (ki < n_keys && site_valid && *qv_fail && !site_valid[ki]) {
     hm_site_record R;
     memset(&R, 0, sizeof(R));
@@ -856,7 +889,7 @@ __global__ void __launch_bounds__(128) k_site_reduce(DevBatch b, DevParams p, De
 #pragma unroll
       for (int j = 0; j < 8; j++) acc(ev[j]);
     }
-    for (uint32_t s = HM_SITE_SLOTS; s < n; s++) acc(site_entry(b, p, ch, c, pair_off, pair_hap, lo + s, tpos - 1, ref));
+    for (uint32_t s = HM_SITE_SLOTS; s < n; s++) acc(site_entry(b, p, ch, c, pair_off, pair_hap, lo + s, tpos - 1, ref, fused));
     if (bq_zero) *err_flag = HM_ERR_BQ_ZERO;
 
     double pl[10];
@@ -908,7 +941,7 @@ __global__ void __launch_bounds__(128) k_site_reduce(DevBatch b, DevParams p, De
               for (uint32_t s = 0; s < n; s++) {
                 if (__ldg(b.qname_id + lo + s) != q) continue;
                 const uint32_t e = s < HM_SITE_SLOTS ? __ldg(entries + (uint64_t)s * stride + ki)
-                                                     : site_entry(b, p, ch, c, pair_off, pair_hap, lo + s, tpos - 1, ref);
+                                                     : site_entry(b, p, ch, c, pair_off, pair_hap, lo + s, tpos - 1, ref, fused);
                 if (e == HM_ENT_UNWRITTEN) continue;
                 const int a = (int)(e & 7u);
                 if (a == ref) { in_wt = true; break; }

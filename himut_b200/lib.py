@@ -97,9 +97,14 @@ class Context:
 
     def close(self):
         if getattr(self, "h", None):
-            if getattr(self, "_out", None) is not None:
-                self.lib.hm_host_unregister(self.h, _p(self._out))
-                self._out = None
+            for buf in getattr(self, "_outs", None) or ():  # the two page-locked record buffers
+                if buf is not None:
+                    self.lib.hm_records_wait(self.h)
+                    self.lib.hm_host_unregister(self.h, _p(buf))
+            self._outs = None
+            for a in list(self._keep.values()):
+                self.lib.hm_host_unregister(self.h, _p(a))
+            self._keep = {}
             self.lib.hm_destroy(self.h)
             self.h = None
 

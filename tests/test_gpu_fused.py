@@ -15,14 +15,15 @@ pytestmark = pytest.mark.gpu
 CALL_CASES = [n for n in cases.CASES if n.startswith("call_")]
 
 
-def _same_as_oracle(ctx, p, batch, chunks, common=None, pon=None, phase=None, path=2):
+def _same_as_oracle(ctx, p, batch, chunks, common=None, pon=None, phase=None, path=2, full=None):
+    """full: the batch with its base stream when `batch` comes without (the oracle reads the bases)"""
     ctx.set_params(p)
     ctx.set_site_sets(common, pon)
     if phase is not None:
         ctx.set_phase_sets(phase)
     rec, log = ctx.call_batch(batch, chunks)
     assert ctx.last_call_path() == path
-    o_rec, o_log = oracle.call_chunks(p, batch, chunks, common, pon, phase)
+    o_rec, o_log = oracle.call_chunks(p, full if full is not None else batch, chunks, common, pon, phase)
     ok, why = parity.records_equal(rec, o_rec)
     assert ok, why
     assert list(log) == list(o_log)
@@ -49,7 +50,7 @@ def test_one_chunk_of_several_tiles(ctx):
     d = synth.generate(600_000, seed=31)
     p = gtmodel.make_params(**gtmodel.DEFAULT_CALL_ARGS)
     _same_as_oracle(ctx, p, d.batch, d.batch.chunk_table([(0, 600_000)]))
-    _same_as_oracle(ctx, p, d.batch.without_seq(), d.batch.chunk_table([(0, 600_000)]))
+    _same_as_oracle(ctx, p, d.batch.without_seq(), d.batch.chunk_table([(0, 600_000)]), full=d.batch)
 
 
 def test_site_buffer_overflow_retries(ctx, monkeypatch):
@@ -69,7 +70,7 @@ def test_dense_candidates(ctx):
     p = gtmodel.make_params(**a)
     rec, log = _same_as_oracle(ctx, p, d.batch, d.batch.chunk_table([(0, 150_000)]))
     assert rec.size > 100_000
-    _same_as_oracle(ctx, p, d.batch.without_seq(), d.batch.chunk_table([(0, 75_000), (75_000, 150_000)]))
+    _same_as_oracle(ctx, p, d.batch.without_seq(), d.batch.chunk_table([(0, 75_000), (75_000, 150_000)]), full=d.batch)
 
 
 def test_reads_that_fail_the_qv_gate_take_their_candidates_with_them(ctx):
