@@ -29,16 +29,16 @@
 #include "kernels.cuh"
 #include "normcounts.cuh" // mbarrier / cp.async.bulk helpers
 
-#define HC_MAX_OPS 192                 // ops of a read staged per warp; longer lists use the batch's global op_t / op_q
+#define HC_MAX_OPS 128                 // ops of a read staged per warp; longer lists use the batch's global op_t / op_q
 #define HC_TILE_BITS 17
 #define HC_TILE (1u << HC_TILE_BITS)   // positions per sort tile
 #define HC_TILE_WORDS (HC_TILE / 32u)
-#define HC_CAPD 8192u                  // distinct positions of a tile kept in shared memory (more: global scratch)
+#define HC_CAPD 4096u                  // distinct positions of a tile kept in shared memory (more: global scratch)
 #define HC_SORT_THREADS 512
 #define HC_BLK 2048u                   // bytes per quality stage
-#define HC_NS 3                        // stages per warp
+#define HC_NS 2                        // stages per warp
 #define HC_WARPS 8                     // warps per CTA of k_call_pairs / k_call_scan
-#define HC_KEY_POS_BITS 28             // a chunk may span < 2^28 positions on this path (else the first version runs)
+#define HC_KEY_POS_BITS 27             // a chunk may span < 2^27 positions on this path (else the first version runs)
 
 struct OpView { const uint32_t* w; const uint32_t* t; const uint32_t* q; uint32_t n; };
 
@@ -110,142 +110,266 @@ __device__ __forceinline__ int warp_read_hap_ops(const DevBatch& b, uint32_t r, 
 }
 
 // ============================================================================ k_call_pairs
-// pair_hap (--phase only): 0 / 1 / 2 ("."), 3 = the chunk does not fetch the read.
+// One THREAD per (chunk, read) pair: a 15 kb CCS read is ~40 cs ops, a warp per pair leaves most lanes idle and the
+// kernel is pure latency; with a thread per pair every pair of a 64 Mb contig is resident at once (one wave).
+//
+// pair_c[pr]: the pair's chunk, or 0xffffffff when the chunk does not fetch the read (k_call_scan starts from it).
+// pair_hap (--phase only): 0 / 1 / 2 ("."), 3 = not fetched.
 // read_counted[r] = 1: some chunk fetched r, r passed the MAPQ / identity / length gates there and (--phase) got a
 //   haplotype: if its QV gate passes too (k_call_scan) it counts in num_ccs and its candidates are real.
 // first_pair[r]: the lowest pair index that fetches r; that pair's warp streams the read's qualities in k_call_scan.
-template <bool kSeq>
-__global__ void __launch_bounds__(32 * HC_WARPS) k_call_pairs(DevBatch b, DevParams p, DevPhase ph, const hm_chunk* chunks, uint32_t n_chunks,
-                                                              const uint64_t* pair_off, uint64_t n_pairs, uint8_t* pair_hap,
-                                                              uint8_t* read_counted, uint32_t* first_pair, const uint64_t* seg_off,
-                                                              uint32_t* seg_cnt, uint32_t* seg_keys, uint32_t* seg_read) {
-  __shared__ uint32_t s_w[HC_WARPS][HC_MAX_OPS], s_t[HC_WARPS][HC_MAX_OPS], s_q[HC_WARPS][HC_MAX_OPS];
-  __shared__ int32_t s_mm[HC_WARPS][HC_MAX_OPS];
-  const uint64_t pr = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  if (pr >= n_pairs) return;
-  const uint32_t c = warp_find_chunk(pair_off, n_chunks, pr, lane);
-  const hm_chunk ch = chunks[c];
-  const uint32_t r = ch.read_lo + (uint32_t)(pr - __ldg(pair_off + c));
-  if (p.phase && lane == 0) pair_hap[pr] = 3;
-  if (__ldg(b.flags + r) & HM_READ_SECONDARY) return;
-  const int32_t ts = __ldg(b.tstart + r), te = __ldg(b.tend + r);
-  if (!(ts < ch.end && te > ch.start)) return;
-  if (lane == 0) atomicMin(first_pair + r, (uint32_t)pr);
-  const uint32_t n = __ldg(b.n_ops + r);
-  const uint64_t o0 = __ldg(b.op_off + r);
-  const int32_t qlen = __ldg(b.qlen + r);
-  const bool staged = n <= HC_MAX_OPS;
-  uint32_t* Tw = staged ? s_t[wid] : b.op_t + o0;
-  uint32_t* Qw = staged ? s_q[wid] : b.op_q + o0;
-  int32_t* Mw = staged ? s_mm[wid] : b.mm_pos + o0;
-  const uint32_t* Wr = staged ? s_w[wid] : b.ops + o0;
+// Candidates: the thread reserves one slot per substitution of its read in the chunk's segment (one atomic), fills
+//   the slots of the substitutions that pass and marks the others as holes (HC_KEY_HOLE).
+#define HC_KEY_HOLE 0xffffffffu
 
-  // sweep 1: prefix scan of (reference, query) lengths, mismatch list, identity tallies (cslib.cs2subindel,
-  // bamlib.get_blast_sequence_identity); pairs of one read write the same values where the arrays are global
-  uint32_t t_carry = 0, q_carry = (uint32_t)__ldg(b.qstart + r);
-  int mm_base = 0, nm = 0, ns = 0, il = 0, dl = 0;
-  for (uint32_t base = 0; base < n; base += 32) {
-    const uint32_t k = base + lane;
-    const bool valid = k < n;
-    const uint32_t w = valid ? __ldg(b.ops + o0 + k) : 0u;
-    const uint32_t kind = w & 3u, v = w >> 2;
-    const uint32_t rl = (uint32_t)op_ref_len(w), al = (uint32_t)op_qry_len(w);
-    uint32_t rs = rl, qs = al;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      const uint32_t a = __shfl_up_sync(HM_FULL, rs, d), e = __shfl_up_sync(HM_FULL, qs, d);
-      if (lane >= d) { rs += a; qs += e; }
+// haplib.get_ccs_hap for one thread over the read's ops (as thread_read_hap_walk, kernels.cuh), kSeq at compile time
+template <bool kSeq>
+__device__ __forceinline__ int thread_read_hap(const DevBatch& b, uint32_t r, int32_t ts, int32_t te, const uint32_t* ops, uint32_t nops,
+                                               uint32_t qstart, const DevPhase& ph, int set) {
+  if (set < 0 || (uint32_t)set >= ph.n_sets) return 2;
+  const uint64_t s0 = ph.set_off[set];
+  const uint32_t n = (uint32_t)(ph.set_off[set + 1] - s0);
+  const int32_t* hp = ph.hpos + s0;
+  const uint32_t idx = upper_bound_dev(hp, n, ts);
+  const uint32_t jdx = upper_bound_dev(hp, n, te);
+  if (jdx - idx < 2) return 2;
+  uint32_t k = 0, t0 = 0, q0 = qstart;
+  bool h0 = true, h1 = true;
+  for (uint32_t i = idx; i < jdx; i++) {
+    const uint32_t off = (uint32_t)(__ldg(hp + i) - 1 - ts);
+    const int hr = (int)ph.href[s0 + i];
+    int a = -1;
+    while (k < nops) { // the op that holds reference offset `off`
+      const uint32_t w = ops[k];
+      const uint32_t rl = (uint32_t)op_ref_len(w);
+      if (rl && off < t0 + rl) {
+        const uint32_t kind = w & 3u, v = w >> 2;
+        if (kind == HM_OP_DEL) a = 5;
+        else if (kind == HM_OP_SUB) a = (int)((v >> 3) & 7u);
+        else if (!kSeq) a = href_match_base(hr);
+        else { const uint32_t q = q0 + (off - t0); a = (b.seq[__ldg(b.seq_off + r) + (q >> 2)] >> (2 * (q & 3u))) & 3; }
+        break;
+      }
+      t0 += rl; q0 += (uint32_t)op_qry_len(w); k++;
     }
-    const uint32_t t_ex = t_carry + rs - rl, q_ex = q_carry + qs - al;
-    if (valid) { if (staged) s_w[wid][k] = w; Tw[k] = t_ex; Qw[k] = q_ex; }
-    const bool is_mm = valid && ((kind == HM_OP_SUB && (v & 7u) != HM_BASE_N) || kind == HM_OP_INS || kind == HM_OP_DEL);
-    const uint32_t bal = __ballot_sync(HM_FULL, is_mm);
-    if (is_mm) Mw[mm_base + __popc(bal & ((1u << lane) - 1u))] = ts + (int32_t)t_ex + 1;
-    mm_base += __popc(bal);
-    if (valid) {
-      if (kind == HM_OP_MATCH) nm += (int)v;
-      else if (kind == HM_OP_SUB) ns += 1;
-      else if (kind == HM_OP_INS) il += (int)v;
-      else dl += (int)v;
+    int bit = 2;
+    if (a >= 0 && a < 4) {
+      if (a == hr) bit = 0;
+      else if (a == (int)ph.halt[s0 + i]) bit = 1;
     }
-    t_carry += __shfl_sync(HM_FULL, rs, 31);
-    q_carry += __shfl_sync(HM_FULL, qs, 31);
+    const int hb = ph.hbit[s0 + i];
+    if (bit != hb) h0 = false;
+    if (bit != 1 - hb) h1 = false;
   }
-  __syncwarp();
-  nm = __reduce_add_sync(HM_FULL, nm);
-  ns = __reduce_add_sync(HM_FULL, ns);
-  il = __reduce_add_sync(HM_FULL, il);
-  dl = __reduce_add_sync(HM_FULL, dl);
-  const int nmm = mm_base;
+  return h0 ? 0 : (h1 ? 1 : 2);
+}
+
+#define HC_A_CAP 6144u // op words of a CTA's 128 reads staged in shared memory
+
+// is op word w an entry of cs2subindel's mismatch list (cslib.py:47-64)?
+__device__ __forceinline__ bool op_is_mismatch(uint32_t w) {
+  const uint32_t kind = w & 3u;
+  return kind == HM_OP_INS || kind == HM_OP_DEL || (kind == HM_OP_SUB && ((w >> 2) & 7u) != HM_BASE_N);
+}
+
+// largest c with off[c] <= x (off: n + 1 ascending entries, off[0] <= x < off[n]); 8-ary: three rounds of independent
+// loads for a few hundred chunks instead of nine dependent ones
+__device__ __forceinline__ uint32_t find_chunk_kary(const uint64_t* off, uint32_t n, uint64_t x) {
+  uint32_t lo = 0, len = n + 1;
+  while (len > 8) {
+    const uint32_t step = (len + 7) >> 3, end = lo + len;
+    uint32_t c = 0;
+#pragma unroll
+    for (uint32_t i = 1; i < 8; i++) {
+      const uint32_t idx = lo + step * i - 1;
+      if (idx < end) c += (__ldg(off + idx) <= x);
+    }
+    lo += c * step;
+    len = min(step, end - lo);
+  }
+  uint32_t c = 0;
+#pragma unroll
+  for (uint32_t i = 0; i < 8; i++)
+    if (i < len) c += (__ldg(off + lo + i) <= x);
+  return lo + c - 1;
+}
+
+// the per-pair work of k_call_pairs once the read's ops are at hand; kShared: `ops` points into shared memory (the
+// common case; a generic pointer would cost every load of the two walks an address-space check)
+template <bool kSeq, bool kShared>
+__device__ __forceinline__ void call_pair_body(const DevBatch& b, const DevParams& p, const DevPhase& ph, const uint32_t* ops_any,
+                                               const hm_chunk& ch, uint32_t c, uint32_t r, uint64_t pr, uint32_t n, uint64_t o0,
+                                               int32_t ts, int32_t te, int32_t qlen, uint32_t qstart, int mapq, uint8_t* pair_hap,
+                                               uint8_t* read_counted, const uint64_t* seg_off, uint32_t* seg_cnt, uint32_t* seg_keys,
+                                               uint32_t* seg_read) {
+  struct Ops { // address-space-specific loads
+    const uint32_t* p;
+    __device__ __forceinline__ uint32_t operator[](uint32_t k) const {
+      if (kShared) { uint32_t v; asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"((uint32_t)__cvta_generic_to_shared(p + k))); return v; }
+      return __ldg(p + k);
+    }
+  };
+  const Ops ops = {ops_any};
+
+  // walk 1, branch-free per op: identity tallies (bamlib.get_blast_sequence_identity), substitutions inside the chunk;
+  // op prefixes to HBM for the op lists k_call_scan does not stage itself
+  uint32_t t = 0;
+  int nm = 0, ns = 0, il = 0, dl = 0, n_sub_in = 0;
+  const bool long_ops = n > HC_MAX_OPS;
+  uint32_t qq = qstart;
+  const int32_t lo_t = ch.start - ts - 1, hi_t = ch.end - ts - 1; // candidate <=> lo_t <= t <= hi_t (tpos = ts + t + 1)
+  for (uint32_t k = 0; k < n; k++) {
+    const uint32_t w = ops[k];
+    const uint32_t kind = w & 3u, v = w >> 2;
+    if (long_ops) { b.op_t[o0 + k] = t; b.op_q[o0 + k] = qq; qq += (uint32_t)op_qry_len(w); }
+    const bool is_m = kind == HM_OP_MATCH, is_s = kind == HM_OP_SUB, is_i = kind == HM_OP_INS, is_d = kind == HM_OP_DEL;
+    nm += is_m ? (int)v : 0; ns += is_s; il += is_i ? (int)v : 0; dl += is_d ? (int)v : 0;
+    n_sub_in += (is_s && (v & 7u) != HM_BASE_N && (int32_t)t >= lo_t && (int32_t)t <= hi_t);
+    t += (is_m || is_d) ? v : (uint32_t)is_s;
+  }
 
   // read gates of caller.py:310-317 except the QV gate (k_call_scan has the quality sum), same order of evaluation
   bool pre_ok = true;
-  if ((int)__ldg(b.mapq + r) < p.min_mapq) pre_ok = false;
+  if (mapq < p.min_mapq) pre_ok = false;
   const double ident = __ddiv_rn((double)nm, (double)(nm + ns + il + dl));
   if (ident < p.min_sequence_identity) pre_ok = false;
   if (!(p.qlen_lower_limit < qlen && qlen < p.qlen_upper_limit)) pre_ok = false;
-
-  const OpView view = {Wr, Tw, Qw, n};
   if (p.phase) {
-    const int hap = warp_read_hap_ops<kSeq>(b, r, ts, te, view, ph, ch.phase_set, lane);
-    if (lane == 0) pair_hap[pr] = (uint8_t)hap;
+    const int hap = thread_read_hap<kSeq>(b, r, ts, te, ops_any, n, qstart, ph, ch.phase_set);
+    pair_hap[pr] = (uint8_t)hap;
     if (hap > 1) return;
   }
   if (!pre_ok) return;
-  if (lane == 0) read_counted[r] = 1;
+  read_counted[r] = 1;
+  if (n_sub_in == 0) return;
 
-  // sweep 2: bamlib.get_tsbs_candidates (bamlib.py:69-86) for every substitution of the read that lies in the chunk
+  // walk 2: bamlib.get_tsbs_candidates (bamlib.py:69-86) for every substitution of the read that lies in the chunk.
+  // A lane first runs ahead to its next such substitution (a short loop), then the lanes of the warp test theirs
+  // together.  The mismatch-window count (bamlib.py:266-282: entries of the sorted mismatch list inside
+  // [tpos - u, tpos + d], minus the substitution itself) is taken from the neighbouring ops directly — every non-match
+  // op is one entry of that list (cs2subindel), at the reference position the walk has reached — and stops as soon
+  // as it exceeds max_mismatch_count.
+  const uint64_t slot0 = __ldg(seg_off + c) + atomicAdd(seg_cnt + c, (uint32_t)n_sub_in);
   const double trim_s = floor(__dmul_rn(p.min_trim, (double)qlen));
   const double trim_e = ceil(__dmul_rn(__dsub_rn(1.0, p.min_trim), (double)qlen));
-  const int wsz = p.mismatch_window;
-  const uint64_t seg0 = __ldg(seg_off + c);
-  uint32_t mm_seen = 0;
-  for (uint32_t base = 0; base < n; base += 32) {
-    const uint32_t k = base + lane;
-    uint32_t op = 0, v = 0;
-    bool is_mm = false;
-    if (k < n) {
-      op = Wr[k];
-      v = op >> 2;
-      const uint32_t kind = op & 3u;
-      is_mm = (kind == HM_OP_SUB && (v & 7u) != HM_BASE_N) || kind == HM_OP_INS || kind == HM_OP_DEL;
+  const int wsz = p.mismatch_window, max_mm = p.max_mismatch_count;
+  uint32_t q = qstart, k = 0;
+  t = 0;
+  for (int used = 0; used < n_sub_in; used++) {
+    uint32_t w = 0;
+    for (; k < n; k++) { // to the next substitution inside the chunk
+      w = ops[k];
+      const uint32_t kind = w & 3u, v = w >> 2;
+      if (kind == HM_OP_SUB && (v & 7u) != HM_BASE_N && (int32_t)t >= lo_t && (int32_t)t <= hi_t) break;
+      t += (kind == HM_OP_MATCH || kind == HM_OP_DEL) ? v : (uint32_t)(kind == HM_OP_SUB);
+      q += (kind == HM_OP_MATCH || kind == HM_OP_INS) ? v : (uint32_t)(kind == HM_OP_SUB);
     }
-    const uint32_t mbal = __ballot_sync(HM_FULL, is_mm);
-    const int rank = (int)(mm_seen + __popc(mbal & ((1u << lane) - 1u))); // this op's own entry in the mismatch list
-    mm_seen += __popc(mbal);
-    bool emit = false;
-    uint32_t key = 0;
-    if (k < n && (op & 3u) == HM_OP_SUB && (v & 7u) != HM_BASE_N) {
-      const int32_t tpos = ts + (int32_t)Tw[k] + 1;
-      const int32_t qpos = (int32_t)Qw[k];
-      if (ch.start <= tpos && tpos <= ch.end && !((double)qpos < trim_s) && !((double)qpos > trim_e)) {
-        const int qs = qpos - wsz, qe = qpos + wsz; // bamlib.get_mismatch_range
-        int u, d;
-        if (qs < 0) { u = wsz + qs; d = wsz + (-qs); }
-        else if (qe > qlen) { u = wsz + (qe - qlen); d = qlen - qpos; }
-        else { u = wsz; d = wsz; }
-        int cnt = 0; // mismatches in [tpos - u, tpos + d] other than this one (bamlib.py:266-282)
-        for (int j = rank + 1; j < nmm && Mw[j] <= tpos + d; j++) cnt++;
-        for (int j = rank - 1; j >= 0 && Mw[j] >= tpos - u; j--) cnt++;
-        if (!(cnt > p.max_mismatch_count)) {
-          emit = true;
-          key = ((uint32_t)(tpos - ch.start) << 4) | ((v & 3u) << 2) | ((v >> 3) & 3u);
-        }
+    if (k >= n) break; // cannot happen: walk 1 counted n_sub_in of them
+    const uint32_t v = w >> 2;
+    const int32_t tpos = ts + (int32_t)t + 1;
+    const int32_t qpos = (int32_t)q;
+    uint32_t key = HC_KEY_HOLE;
+    if (!((double)qpos < trim_s) && !((double)qpos > trim_e)) {
+      const int qs = qpos - wsz, qe = qpos + wsz; // bamlib.get_mismatch_range
+      int u, d;
+      if (qs < 0) { u = wsz + qs; d = wsz + (-qs); }
+      else if (qe > qlen) { u = wsz + (qe - qlen); d = qlen - qpos; }
+      else { u = wsz; d = wsz; }
+      int cnt = 0;
+      uint32_t tj = t + 1; // reference offset at the start of op k + 1
+      for (uint32_t j = k + 1; j < n && cnt <= max_mm; j++) { // later entries of the list, ascending positions
+        const uint32_t wj = ops[j];
+        if (ts + (int32_t)tj + 1 > tpos + d) break; // nothing from here on can be inside the window
+        cnt += op_is_mismatch(wj);
+        tj += (uint32_t)op_ref_len(wj);
       }
+      tj = t; // reference offset at the start of op k
+      for (uint32_t j = k; j-- > 0 && cnt <= max_mm;) { // earlier entries, descending positions
+        const uint32_t wj = ops[j];
+        tj -= (uint32_t)op_ref_len(wj); // offset at the start of op j
+        if (op_is_mismatch(wj)) {
+          if (ts + (int32_t)tj + 1 < tpos - u) break;
+          cnt++;
+        } else if (ts + (int32_t)tj + 1 < tpos - u) break; // a match run that starts before the window: nothing earlier counts
+      }
+      if (!(cnt > max_mm)) key = ((uint32_t)(tpos - ch.start) << 4) | ((v & 3u) << 2) | ((v >> 3) & 3u);
     }
-    const uint32_t bal = __ballot_sync(HM_FULL, emit);
-    if (bal) {
-      uint32_t at = 0;
-      if (lane == 0) at = atomicAdd(seg_cnt + c, (uint32_t)__popc(bal));
-      at = __shfl_sync(HM_FULL, at, 0);
-      if (emit) {
-        const uint64_t slot = seg0 + at + __popc(bal & ((1u << lane) - 1u));
-        seg_keys[slot] = key;
-        seg_read[slot] = r;
-      }
+    seg_keys[slot0 + used] = key;
+    seg_read[slot0 + used] = r;
+    t += 1; q += 1; k++;
+  }
+}
+
+template <bool kSeq>
+__global__ void __launch_bounds__(128) k_call_pairs(DevBatch b, DevParams p, DevPhase ph, const hm_chunk* chunks, uint32_t n_chunks,
+                                                    const uint64_t* pair_off, uint64_t n_pairs, uint32_t* pair_c, uint8_t* pair_hap,
+                                                    uint8_t* read_counted, uint32_t* first_pair, const uint64_t* seg_off,
+                                                    uint32_t* seg_cnt, uint32_t* seg_keys, uint32_t* seg_read) {
+  extern __shared__ uint32_t s_ops[]; // HC_A_CAP
+  __shared__ unsigned long long s_span[2];
+  if (threadIdx.x == 0) { s_span[0] = ~0ull; s_span[1] = 0ull; }
+  __syncthreads();
+  const uint64_t pr = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  bool active = pr < n_pairs;
+  uint32_t c = 0, r = 0, n = 0, qstart = 0;
+  hm_chunk ch = {0, 0, 0, 0, 0, 0};
+  int32_t ts = 0, te = 0, qlen = 0;
+  uint64_t o0 = 0;
+  int mapq = 0;
+  if (active) {
+    c = find_chunk_kary(pair_off, n_chunks, pr);
+    ch = chunks[c];
+    r = ch.read_lo + (uint32_t)(pr - __ldg(pair_off + c));
+    // everything the pair needs from the read, loaded together
+    const uint32_t flags = __ldg(b.flags + r);
+    ts = __ldg(b.tstart + r); te = __ldg(b.tend + r);
+    n = __ldg(b.n_ops + r);
+    o0 = __ldg(b.op_off + r);
+    qlen = __ldg(b.qlen + r);
+    qstart = (uint32_t)__ldg(b.qstart + r);
+    mapq = (int)__ldg(b.mapq + r);
+    if ((flags & HM_READ_SECONDARY) || !(ts < ch.end && te > ch.start)) {
+      pair_c[pr] = 0xffffffffu;
+      if (p.phase) pair_hap[pr] = 3;
+      active = false;
+    } else {
+      pair_c[pr] = c;
+      atomicMin(first_pair + r, (uint32_t)pr);
     }
   }
+  { // the run of the op stream this CTA's reads span: warp reduction, one shared atomic per warp
+    unsigned long long lo = (active && n) ? (unsigned long long)o0 : ~0ull, hi = (active && n) ? (unsigned long long)(o0 + n) : 0ull;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+      const unsigned long long a = __shfl_xor_sync(HM_FULL, lo, d), e = __shfl_xor_sync(HM_FULL, hi, d);
+      lo = min(lo, a); hi = max(hi, e);
+    }
+    if ((threadIdx.x & 31) == 0) { atomicMin(&s_span[0], lo); atomicMax(&s_span[1], hi); }
+  }
+  __syncthreads();
+  // the CTA's reads are neighbours in the file, so their ops are one short run of the op stream: staged with
+  // coalesced loads (a thread walking its own ops in global memory costs one L1 wavefront per lane and load)
+  const unsigned long long sp_lo = s_span[0], sp_hi = s_span[1];
+  const bool staged = sp_hi > sp_lo && sp_hi - sp_lo <= HC_A_CAP;
+  if (staged) { // eight independent loads per thread and round: the run is ~40 words per thread, one round trip each otherwise
+    const uint32_t nw = (uint32_t)(sp_hi - sp_lo);
+    const uint32_t* src = b.ops + sp_lo;
+    for (uint32_t i0 = threadIdx.x; i0 < nw; i0 += 8 * blockDim.x) {
+      uint32_t v[8];
+#pragma unroll
+      for (int u = 0; u < 8; u++) { const uint32_t i = i0 + u * blockDim.x; v[u] = i < nw ? __ldg(src + i) : 0u; }
+#pragma unroll
+      for (int u = 0; u < 8; u++) { const uint32_t i = i0 + u * blockDim.x; if (i < nw) s_ops[i] = v[u]; }
+    }
+  }
+  __syncthreads();
+  if (!active) return;
+  if (staged)
+    call_pair_body<kSeq, true>(b, p, ph, s_ops + (o0 - sp_lo), ch, c, r, pr, n, o0, ts, te, qlen, qstart, mapq, pair_hap, read_counted, seg_off,
+                               seg_cnt, seg_keys, seg_read);
+  else
+    call_pair_body<kSeq, false>(b, p, ph, b.ops + o0, ch, c, r, pr, n, o0, ts, te, qlen, qstart, mapq, pair_hap, read_counted, seg_off, seg_cnt,
+                                seg_keys, seg_read);
 }
 
 // ============================================================================ k_site_sort
@@ -271,19 +395,23 @@ __device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t* s_warp
 }
 
 // One CTA per tile.  tile_chunk[t] = chunk of tile t, tile_off[c] = first tile of chunk c (host).  Outputs: the
-// tile's sorted distinct keys (chunk-relative: rel << 4 | ref << 2 | alt) at keys_tmp[tile_src[t] ...), tile_cnt[t],
-// and for every emitted key its rank among the tile's distinct keys (key_site).
+// tile's sorted distinct keys (chunk-relative: rel << 4 | ref << 2 | alt) at keys_tmp[tile_src[t] ...) and tile_cnt[t].
+// The tile's own keys are staged in shared memory once (the chunk's segment is read a single time, coalesced); a tile
+// with more keys than the stage holds walks the segment in global memory instead.
+#define HC_STAGE 8192u
 __global__ void __launch_bounds__(HC_SORT_THREADS) k_site_sort(const uint32_t* tile_chunk, const uint32_t* tile_off, const uint64_t* seg_off,
                                                                const uint32_t* seg_cnt, const uint32_t* seg_keys, uint32_t* chunk_cursor,
                                                                uint32_t* chunk_cursor2, uint32_t* gscratch, uint32_t* keys_tmp,
-                                                               uint32_t* key_site, uint32_t* tile_src, uint32_t* tile_cnt) {
+                                                               uint32_t* tile_src, uint32_t* tile_cnt) {
   extern __shared__ uint32_t sm[];
   uint32_t* s_bits = sm;                          // HC_TILE_WORDS
   uint32_t* s_wpre = s_bits + HC_TILE_WORDS;      // HC_TILE_WORDS: distinct positions before each word
   uint32_t* s_mask = s_wpre + HC_TILE_WORDS;      // HC_CAPD: (ref, alt) combinations seen at the rank-th distinct position
   uint32_t* s_off = s_mask + HC_CAPD;             // HC_CAPD: distinct keys before the rank-th distinct position
+  uint32_t* s_keys = s_off + HC_CAPD;             // HC_STAGE: the tile's keys
   __shared__ uint32_t s_warp[33];
   __shared__ uint32_t s_base[2];
+  __shared__ uint32_t s_nstaged;
   const uint32_t t = blockIdx.x, tid = threadIdx.x;
   const uint32_t c = tile_chunk[t];
   const uint32_t tile_in_chunk = t - tile_off[c];
@@ -292,12 +420,25 @@ __global__ void __launch_bounds__(HC_SORT_THREADS) k_site_sort(const uint32_t* t
   const uint32_t* keys = seg_keys + seg0;
 
   for (uint32_t i = tid; i < HC_TILE_WORDS; i += blockDim.x) s_bits[i] = 0u;
+  if (tid == 0) s_nstaged = 0;
   __syncthreads();
-  for (uint32_t j = tid; j < nk; j += blockDim.x) {
-    const uint32_t rel = __ldg(keys + j) >> 4;
-    if ((rel >> HC_TILE_BITS) == tile_in_chunk) atomicOr(&s_bits[(rel & (HC_TILE - 1u)) >> 5], 1u << (rel & 31u));
+  // position bitmap; the tile's keys go to the stage as long as they fit (holes: slots of substitutions that failed)
+  for (uint32_t j0 = 0; j0 < nk; j0 += 4 * blockDim.x) {
+    uint32_t kv[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) { const uint32_t j = j0 + u * blockDim.x + tid; kv[u] = j < nk ? __ldg(keys + j) : HC_KEY_HOLE; }
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const uint32_t rel = kv[u] >> 4;
+      if (kv[u] == HC_KEY_HOLE || (rel >> HC_TILE_BITS) != tile_in_chunk) continue;
+      atomicOr(&s_bits[(rel & (HC_TILE - 1u)) >> 5], 1u << (rel & 31u));
+      const uint32_t at = atomicAdd(&s_nstaged, 1u);
+      if (at < HC_STAGE) s_keys[at] = kv[u];
+    }
   }
   __syncthreads();
+  const uint32_t n_own = s_nstaged;
+  const bool staged = n_own <= HC_STAGE;
   // distinct positions before each bitmap word: each thread owns HC_TILE_WORDS / blockDim.x consecutive words
   constexpr uint32_t WPT = HC_TILE_WORDS / HC_SORT_THREADS;
   uint32_t local = 0;
@@ -315,9 +456,11 @@ __global__ void __launch_bounds__(HC_SORT_THREADS) k_site_sort(const uint32_t* t
   uint32_t* off = in_smem ? s_off : mask + n_dist;
   for (uint32_t i = tid; i < n_dist; i += blockDim.x) mask[i] = 0u;
   __syncthreads();
-  for (uint32_t j = tid; j < nk; j += blockDim.x) {
-    const uint32_t key = __ldg(keys + j), rel = key >> 4;
-    if ((rel >> HC_TILE_BITS) != tile_in_chunk) continue;
+  const uint32_t n_walk = staged ? n_own : nk;
+  const uint32_t* walk = staged ? s_keys : keys;
+  for (uint32_t j = tid; j < n_walk; j += blockDim.x) {
+    const uint32_t key = walk[j], rel = key >> 4;
+    if (key == HC_KEY_HOLE || (rel >> HC_TILE_BITS) != tile_in_chunk) continue;
     const uint32_t p = rel & (HC_TILE - 1u);
     const uint32_t rank = s_wpre[p >> 5] + __popc(s_bits[p >> 5] & ((1u << (p & 31u)) - 1u));
     atomicOr(&mask[rank], 1u << (key & 15u));
@@ -353,14 +496,6 @@ __global__ void __launch_bounds__(HC_SORT_THREADS) k_site_sort(const uint32_t* t
       while (m) { const uint32_t cb = __ffs(m) - 1; m &= m - 1; dst[o++] = (rel << 4) | cb; }
       rank++;
     }
-  }
-  // where each emitted key went (k_site_valid needs it when a read fails the QV gate)
-  for (uint32_t j = tid; j < nk; j += blockDim.x) {
-    const uint32_t key = __ldg(keys + j), rel = key >> 4;
-    if ((rel >> HC_TILE_BITS) != tile_in_chunk) continue;
-    const uint32_t p = rel & (HC_TILE - 1u);
-    const uint32_t rank = s_wpre[p >> 5] + __popc(s_bits[p >> 5] & ((1u << (p & 31u)) - 1u));
-    key_site[seg0 + j] = off[rank] + __popc(mask[rank] & ((1u << (key & 15u)) - 1u));
   }
 }
 
@@ -414,10 +549,16 @@ __global__ void __launch_bounds__(256) k_site_range2(DevBatch b, const hm_chunk*
 }
 
 // ============================================================================ k_call_scan
-// One warp per (chunk, read) pair.  Shared memory per warp: the read's ops with their prefixes, HC_NS quality stages,
-// HC_NS mbarriers.  The pair that owns the read (first_pair) and whose read can still count (read_counted) streams the
-// read's qualities: lane 0 keeps HC_NS bulk copies in flight; every block is summed from shared memory and then serves
-// the sites whose query position lies in it.  Other pairs fetch their few quality bytes directly.
+// One warp per (chunk, read) pair, four warps per CTA.  Shared memory per warp: HC_NS quality stages with their
+// mbarriers, the read's ops with their prefixes, and the pair's site list (query position, entry without its quality,
+// entry address).  The pair that owns the read (first_pair) and whose read can still count (read_counted) streams the
+// read's qualities: lane 0 issues the first bulk copies as soon as the read is known — the site searches, the op scan
+// and the site list are built while they fly — and keeps HC_NS copies in flight; every block is summed from shared
+// memory and then serves the listed sites whose query position lies in it.  Other pairs fetch their few quality bytes
+// directly.
+#define HC_SCAN_WARPS 4
+#define HC_SITES 96 // sites of a pair kept in the list (a 15 kb read at 30x sees ~70); the rest go the direct way
+
 struct __align__(16) ScanWarp {
   uint8_t bq[HC_NS][HC_BLK];
   uint32_t w[HC_MAX_OPS], t[HC_MAX_OPS], q[HC_MAX_OPS];
@@ -426,42 +567,64 @@ struct __align__(16) ScanWarp {
 };
 
 template <bool kSeq>
-__global__ void __launch_bounds__(32 * HC_WARPS) k_call_scan(DevBatch b, DevParams p, const hm_chunk* chunks, uint32_t n_chunks,
-                                                             const uint64_t* pair_off, uint64_t n_pairs, const uint8_t* pair_hap,
-                                                             const uint8_t* read_counted, const uint32_t* first_pair,
-                                                             const uint32_t* tile_off, const uint32_t* tile_dst,
-                                                             const unsigned long long* keys, const uint32_t* site_lo, const uint32_t* site_n,
-                                                             uint32_t* entries, uint64_t stride, uint8_t* qv_fail_read,
-                                                             unsigned int* qv_fail_any, uint8_t* qname_seen,
-                                                             const unsigned long long* n_keys_dev) {
+__global__ void __launch_bounds__(32 * HC_SCAN_WARPS) k_call_scan(DevBatch b, DevParams p, const hm_chunk* chunks, const uint64_t* pair_off,
+                                                                  uint64_t n_pairs, const uint32_t* pair_c, const uint8_t* pair_hap,
+                                                                  const uint8_t* read_counted, const uint32_t* first_pair,
+                                                                  const uint32_t* tile_off, const uint32_t* tile_dst,
+                                                                  const unsigned long long* keys, const uint32_t* site_lo,
+                                                                  const uint32_t* site_n, uint32_t* entries, uint32_t stride,
+                                                                  uint8_t* qv_fail_read, unsigned int* qv_fail_any, uint32_t* qname_seen32,
+                                                                  unsigned long long* num_ccs, const unsigned long long* n_keys_dev) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   const uint64_t pr = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   if (pr >= n_pairs) return;
+  const uint32_t c = __ldg(pair_c + pr);
+  if (c == 0xffffffffu) return; // the chunk does not fetch the read
   ScanWarp* S = reinterpret_cast<ScanWarp*>(smem_raw) + wid;
-  const uint32_t c = warp_find_chunk(pair_off, n_chunks, pr, lane);
-  const hm_chunk ch = chunks[c];
-  const uint32_t r = ch.read_lo + (uint32_t)(pr - __ldg(pair_off + c));
-  if (__ldg(b.flags + r) & HM_READ_SECONDARY) return;
+  const int32_t ch_read_lo = (int32_t)__ldg(&chunks[c].read_lo);
+  const uint32_t to0 = __ldg(tile_off + c), to1 = __ldg(tile_off + c + 1);
+  const uint32_t r = (uint32_t)ch_read_lo + (uint32_t)(pr - __ldg(pair_off + c));
   const int32_t ts = __ldg(b.tstart + r), te = __ldg(b.tend + r);
-  if (!(ts < ch.end && te > ch.start)) return;
-  const bool owner = __ldg(first_pair + r) == (uint32_t)pr && __ldg(read_counted + r) != 0;
   const uint32_t n = __ldg(b.n_ops + r);
+  const uint64_t o0 = __ldg(b.op_off + r);
+  const uint64_t bq0 = __ldg(b.bq_off + r);
+  const uint32_t qlen = (uint32_t)__ldg(b.qlen + r);
+  const uint32_t qstart = (uint32_t)__ldg(b.qstart + r);
+  const bool owner = __ldg(first_pair + r) == (uint32_t)pr && __ldg(read_counted + r) != 0;
+  const uint32_t hap = p.phase ? (uint32_t)__ldg(pair_hap + pr) : 2u;
+  const uint32_t k_lo = __ldg(tile_dst + to0), k_hi = __ldg(tile_dst + to1);
+  const bool have_sites = *n_keys_dev != 0; // 0 also when the site list overflowed its buffers: the host runs the call again
+  const uint8_t* bqg = b.bq + bq0;
+  const uint32_t nbytes = (qlen + 15u) & ~15u; // the stream is padded to 16 bytes per read
+  const uint32_t nblk = owner ? (nbytes + HC_BLK - 1u) / HC_BLK : 0u;
+
+  // the first copies leave before anything else is looked at
+  if (owner) {
+    if (lane == 0) {
+#pragma unroll
+      for (int s = 0; s < HC_NS; s++) mbar_init(&S->bar[s], 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      for (uint32_t s = 0; s < (uint32_t)HC_NS && s < nblk; s++) {
+        const uint32_t bytes = min(HC_BLK, nbytes - s * HC_BLK);
+        mbar_arrive_expect_tx(&S->bar[s], bytes);
+        bulk_g2s(S->bq[s], bqg + (size_t)s * HC_BLK, bytes, &S->bar[s]);
+      }
+    }
+    __syncwarp();
+  }
+
   // the chunk's sites the read can touch: rpos in [ts, te], i.e. tpos in [ts + 1, te + 1]
   uint32_t s_lo = 0, s_hi = 0;
-  if (n && *n_keys_dev) { // 0 also when the site list overflowed its buffers (k_tile_scan): the host runs the call again
-    const uint32_t k_lo = __ldg(tile_dst + __ldg(tile_off + c)), k_hi = __ldg(tile_dst + __ldg(tile_off + c + 1));
-    if (k_lo < k_hi) {
-      const unsigned long long kb = (unsigned long long)c << 36;
-      s_lo = warp_lower_bound_u64(keys, k_lo, k_hi, kb | ((unsigned long long)(uint32_t)(ts + 1) << 4), lane);
-      s_hi = warp_lower_bound_u64(keys, s_lo, k_hi, kb | ((unsigned long long)(uint32_t)(te + 2) << 4), lane);
-    }
+  if (n && have_sites && k_lo < k_hi) {
+    const unsigned long long kb = (unsigned long long)c << 36;
+    s_lo = warp_lower_bound_u64(keys, k_lo, k_hi, kb | ((unsigned long long)(uint32_t)(ts + 1) << 4), lane);
+    s_hi = warp_lower_bound_u64(keys, s_lo, k_hi, kb | ((unsigned long long)(uint32_t)(te + 2) << 4), lane);
   }
   if (!owner && s_lo >= s_hi) return;
-  const uint64_t o0 = __ldg(b.op_off + r);
   const bool staged = n <= HC_MAX_OPS;
   if (staged && s_lo < s_hi) { // the prefix scan again (registers only): cheaper than keeping 8 B per op in HBM
-    uint32_t t_carry = 0, q_carry = (uint32_t)__ldg(b.qstart + r);
+    uint32_t t_carry = 0, q_carry = qstart;
     for (uint32_t base = 0; base < n; base += 32) {
       const uint32_t k = base + lane;
       const uint32_t w = k < n ? __ldg(b.ops + o0 + k) : 0u;
@@ -479,21 +642,12 @@ __global__ void __launch_bounds__(32 * HC_WARPS) k_call_scan(DevBatch b, DevPara
     __syncwarp();
   }
   const OpView view = {staged ? S->w : b.ops + o0, staged ? S->t : b.op_t + o0, staged ? S->q : b.op_q + o0, n};
-  const uint64_t bq0 = __ldg(b.bq_off + r);
-  const uint8_t* bqg = b.bq + bq0;
   const uint64_t sq0 = kSeq ? __ldg(b.seq_off + r) : 0;
-  const uint32_t hap = p.phase ? (uint32_t)pair_hap[pr] : 2u;
-  const uint32_t qlen = (uint32_t)__ldg(b.qlen + r);
 
-  // site groups: 32 consecutive sites, one per lane.  pending: the lane's site waits for the quality byte at my_q.
-  uint32_t g_next = s_lo;
-  bool pending = false;
-  uint32_t my_q = 0, my_e = 0;
-  uint64_t my_at = 0;
-  auto load_group = [&]() {
-    const uint32_t ki = g_next + (uint32_t)lane;
-    g_next += 32;
-    if (ki >= s_hi) return;
+  // one site: entry without its quality, the query position of the base (0xffffffff: the site needs no quality byte
+  // of this read, its entry is written at once), the entry's address
+  auto site = [&](uint32_t ki, uint32_t* q_out, uint32_t* e_out, uint32_t* at_out) {
+    *q_out = 0xffffffffu; *e_out = 0; *at_out = 0;
     const uint32_t slot = r - __ldg(site_lo + ki);
     if (slot >= HM_SITE_SLOTS || slot >= __ldg(site_n + ki)) return; // deep pileups: k_site_reduce computes these itself
     const unsigned long long key = __ldg(keys + ki);
@@ -504,27 +658,22 @@ __global__ void __launch_bounds__(32 * HC_WARPS) k_call_scan(DevBatch b, DevPara
     if (a == 8) a = kSeq ? (int)((b.seq[sq0 + (q >> 2)] >> (2 * (q & 3u))) & 3u) : (int)((key >> 2) & 3);
     const uint32_t e = (a < 0 ? HM_ENT_NONE : (uint32_t)a) | ((uint32_t)min(ins, 255) << 11) | ((hap & 3u) << 19) |
                        ((te > rpos + 1) ? (1u << 21) : 0u);
-    const uint64_t at = (uint64_t)slot * stride + ki;
-    if (has_base) { pending = true; my_q = q; my_e = e; my_at = at; }
+    const uint32_t at = slot * stride + ki;
+    if (has_base) { *q_out = q; *e_out = e; *at_out = at; }
     else entries[at] = e;
   };
 
-  if (owner) {
-    const uint32_t nbytes = (qlen + 15u) & ~15u; // the stream is padded to 16 bytes per read
-    const uint32_t nblk = (nbytes + HC_BLK - 1u) / HC_BLK;
-    if (lane == 0) {
+  // the pair's site list (the first HC_SITES sites), HC_SITES / 32 per lane, in registers
+  const uint32_t n_list = min(s_hi - s_lo, (uint32_t)HC_SITES);
+  uint32_t lq[HC_SITES / 32], le[HC_SITES / 32], la[HC_SITES / 32];
 #pragma unroll
-      for (int s = 0; s < HC_NS; s++) mbar_init(&S->bar[s], 1);
-      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncwarp();
-    if (lane == 0) {
-      for (uint32_t s = 0; s < (uint32_t)HC_NS && s < nblk; s++) {
-        const uint32_t bytes = min(HC_BLK, nbytes - s * HC_BLK);
-        mbar_arrive_expect_tx(&S->bar[s], bytes);
-        bulk_g2s(S->bq[s], bqg + (size_t)s * HC_BLK, bytes, &S->bar[s]);
-      }
-    }
+  for (uint32_t g = 0; g < HC_SITES / 32; g++) {
+    const uint32_t i = g * 32 + (uint32_t)lane;
+    lq[g] = 0xffffffffu; le[g] = 0; la[g] = 0;
+    if (i < n_list) site(s_lo + i, &lq[g], &le[g], &la[g]);
+  }
+
+  if (owner) {
     uint32_t acc = 0;
     for (uint32_t blk = 0; blk < nblk; blk++) {
       const uint32_t st = blk % HC_NS, parity = (blk / HC_NS) & 1u;
@@ -532,33 +681,35 @@ __global__ void __launch_bounds__(32 * HC_WARPS) k_call_scan(DevBatch b, DevPara
       const uint32_t blk0 = blk * HC_BLK;
       const uint32_t bytes = min(HC_BLK, nbytes - blk0);
       const uint4* s4 = reinterpret_cast<const uint4*>(S->bq[st]);
-      for (uint32_t i = lane; i < (bytes >> 4); i += 32) {
-        uint4 v = s4[i];
-        const uint32_t g0 = blk0 + (i << 4); // bytes past the read's length are padding: not part of the sum
-        if (g0 + 16u > qlen) {
-          const uint32_t keep = qlen - g0; // 1 .. 15
-          uint32_t wv[4] = {v.x, v.y, v.z, v.w};
+      if (bytes == HC_BLK && blk0 + HC_BLK <= qlen) { // a full block inside the read: four words per lane, no edge to mind
+        const uint4 v0 = s4[lane], v1 = s4[lane + 32], v2 = s4[lane + 64], v3 = s4[lane + 96];
+        acc = sum4(v0.x, acc); acc = sum4(v0.y, acc); acc = sum4(v0.z, acc); acc = sum4(v0.w, acc);
+        acc = sum4(v1.x, acc); acc = sum4(v1.y, acc); acc = sum4(v1.z, acc); acc = sum4(v1.w, acc);
+        acc = sum4(v2.x, acc); acc = sum4(v2.y, acc); acc = sum4(v2.z, acc); acc = sum4(v2.w, acc);
+        acc = sum4(v3.x, acc); acc = sum4(v3.y, acc); acc = sum4(v3.z, acc); acc = sum4(v3.w, acc);
+      } else {
+        for (uint32_t i = lane; i < (bytes >> 4); i += 32) {
+          uint4 v = s4[i];
+          const uint32_t g0 = blk0 + (i << 4); // bytes past the read's length are padding: not part of the sum
+          if (g0 + 16u > qlen) {
+            const uint32_t keep = qlen - g0; // 1 .. 15
+            uint32_t wv[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-          for (int j = 0; j < 4; j++) {
-            const int kb = (int)keep - 4 * j;
-            wv[j] = kb >= 4 ? wv[j] : kb <= 0 ? 0u : (wv[j] & ((1u << (8 * kb)) - 1u));
+            for (int j = 0; j < 4; j++) {
+              const int kb = (int)keep - 4 * j;
+              wv[j] = kb >= 4 ? wv[j] : kb <= 0 ? 0u : (wv[j] & ((1u << (8 * kb)) - 1u));
+            }
+            v = make_uint4(wv[0], wv[1], wv[2], wv[3]);
           }
-          v = make_uint4(wv[0], wv[1], wv[2], wv[3]);
+          acc = sum4(v.x, acc); acc = sum4(v.y, acc); acc = sum4(v.z, acc); acc = sum4(v.w, acc);
         }
-        acc = sum4(v.x, acc); acc = sum4(v.y, acc); acc = sum4(v.z, acc); acc = sum4(v.w, acc);
       }
-      // sites whose quality byte is in this block (query positions ascend with the sites)
-      for (;;) {
-        if (!__any_sync(HM_FULL, pending)) {
-          if (g_next >= s_hi) break;
-          load_group();
-          continue;
-        }
-        if (pending && my_q >= blk0 && my_q < blk0 + bytes) {
-          entries[my_at] = my_e | ((uint32_t)S->bq[st][my_q - blk0] << 3);
-          pending = false;
-        }
-        if (__any_sync(HM_FULL, pending)) break; // the rest waits for a later block
+      // listed sites whose quality byte is in this block (0xffffffff — no byte wanted — and earlier blocks wrap to
+      // large values)
+#pragma unroll
+      for (uint32_t g = 0; g < HC_SITES / 32; g++) {
+        const uint32_t rel = lq[g] - blk0;
+        if (rel < bytes && lq[g] != 0xffffffffu) entries[la[g]] = le[g] | ((uint32_t)S->bq[st][rel] << 3);
       }
       __syncwarp(); // every lane is done with this stage
       if (lane == 0 && blk + HC_NS < nblk) {
@@ -576,69 +727,65 @@ __global__ void __launch_bounds__(32 * HC_WARPS) k_call_scan(DevBatch b, DevPara
     if (lane == 0) {
       const double qv = __ddiv_rn((double)tot, (double)qlen);
       if (qv < (double)p.min_qv) { qv_fail_read[r] = 1; *qv_fail_any = 1u; }
-      else qname_seen[__ldg(b.qname_id + r)] = 1; // m.num_ccs counts it (caller.py:318-320)
+      else { // m.num_ccs counts distinct query names (caller.py:318-320): one byte per name, the first setter counts
+        const uint32_t qn = __ldg(b.qname_id + r);
+        const uint32_t bit = 1u << (8u * (qn & 3u));
+        if (!(atomicOr(qname_seen32 + (qn >> 2), bit) & bit)) atomicAdd(num_ccs + (r & 7u), 1ull);
+      }
     }
+    // a listed site whose query position lies past the read's end (malformed ops) never met a block
+#pragma unroll
+    for (uint32_t g = 0; g < HC_SITES / 32; g++)
+      if (lq[g] != 0xffffffffu && lq[g] >= nbytes) entries[la[g]] = le[g];
+  } else {
+#pragma unroll
+    for (uint32_t g = 0; g < HC_SITES / 32; g++)
+      if (lq[g] != 0xffffffffu) entries[la[g]] = le[g] | ((uint32_t)(lq[g] < qlen ? bqg[lq[g]] : 0) << 3);
   }
-  // what is left: every site of a pair that does not stream; nothing, normally, of one that does
-  for (;;) {
-    if (pending) { entries[my_at] = my_e | ((uint32_t)(my_q < qlen ? bqg[my_q] : 0) << 3); pending = false; }
-    if (g_next >= s_hi) break;
-    load_group();
+  // sites past the list: the direct way
+  for (uint32_t k0 = s_lo + HC_SITES; k0 < s_hi; k0 += 32) {
+    const uint32_t ki = k0 + (uint32_t)lane;
+    if (ki >= s_hi) continue;
+    uint32_t q, e, at;
+    site(ki, &q, &e, &at);
+    if (q != 0xffffffffu) entries[at] = e | ((uint32_t)(q < qlen ? bqg[q] : 0) << 3);
   }
 }
 
-// sites keep only the candidates of reads that passed the QV gate; runs only when some read failed it
-__global__ void __launch_bounds__(256) k_site_valid(const unsigned int* qv_fail_any, const uint8_t* qv_fail_read, const uint64_t* seg_off,
-                                                    const uint32_t* seg_cnt, const uint32_t* seg_keys, const uint32_t* seg_read,
-                                                    const uint32_t* key_site, const uint32_t* tile_off, const uint32_t* tile_dst,
-                                                    const unsigned long long* n_keys_dev, uint8_t* site_valid) {
-  if (!*qv_fail_any) return;
+// sites keep only the candidates of reads that passed the QV gate; does something only when some read failed it
+// (then every emitted key looks its site up in the sorted key array)
+__global__ void __launch_bounds__(256) k_site_valid(const unsigned int* qv_fail_any, const uint8_t* qv_fail_read, const hm_chunk* chunks,
+                                                    const uint64_t* seg_off, const uint32_t* seg_cnt, const uint32_t* seg_keys,
+                                                    const uint32_t* seg_read, const uint32_t* tile_off, const uint32_t* tile_dst,
+                                                    const unsigned long long* keys, const unsigned long long* n_keys_dev,
+                                                    uint8_t* site_valid) {
+  if (!*qv_fail_any || !*n_keys_dev) return;
   const uint32_t c = blockIdx.x;
   const uint64_t seg0 = seg_off[c];
   const uint32_t nk = seg_cnt[c];
-  const unsigned long long n_keys = *n_keys_dev;
+  const uint32_t k_lo = tile_dst[tile_off[c]], k_hi = tile_dst[tile_off[c + 1]];
+  const int32_t start = chunks[c].start;
   for (uint32_t j = threadIdx.x; j < nk; j += blockDim.x) {
-    if (qv_fail_read[seg_read[seg0 + j]]) continue;
-    const uint32_t rel = seg_keys[seg0 + j] >> 4;
-    const uint64_t site = (uint64_t)tile_dst[tile_off[c] + (rel >> HC_TILE_BITS)] + key_site[seg0 + j];
-    if (site < n_keys) site_valid[site] = 1;
+    const uint32_t k32 = seg_keys[seg0 + j];
+    if (k32 == HC_KEY_HOLE || qv_fail_read[seg_read[seg0 + j]]) continue;
+    const unsigned long long want = ((unsigned long long)c << 36) | ((unsigned long long)(uint32_t)(start + (int32_t)(k32 >> 4)) << 4) | (k32 & 15u);
+    uint32_t lo = k_lo, hi = k_hi;
+    while (lo < hi) { const uint32_t m = (lo + hi) >> 1; if (__ldg(keys + m) < want) lo = m + 1; else hi = m; }
+    if (lo < k_hi && __ldg(keys + lo) == want) site_valid[lo] = 1;
   }
 }
 
-// ============================================================================ k_compact_sites
-// Stable compaction of the records the host wants.  keep_cnt[j] = kept records of k_site_reduce's block j (128 sites);
-// a CTA here covers 8 of them.  kpos[i] = where record i went (boundary records are looked up through it).
-__global__ void __launch_bounds__(1024) k_compact_sites(const hm_site_record* rec, const unsigned long long* n_dev, const uint32_t* keep_cnt,
-                                                        int omit, hm_site_record* out, uint32_t* kpos, unsigned long long* n_kept) {
-  __shared__ uint32_t s_warp[33];
-  const uint64_t n = *n_dev;
-  const uint64_t i0 = (uint64_t)blockIdx.x * 1024;
-  if (i0 >= n && blockIdx.x != 0) return;
-  const uint32_t n_red = (uint32_t)((n + 127) / 128);
-  // records kept before this CTA (and, in CTA 0, in total)
-  const uint32_t before = min(blockIdx.x * 8u, n_red);
-  uint32_t part = 0, all = 0;
-  for (uint32_t j = threadIdx.x; j < (blockIdx.x == 0 ? n_red : before); j += blockDim.x) {
-    const uint32_t v = keep_cnt[j];
-    all += v;
-    if (j < before) part += v;
-  }
-  uint32_t tot_before, tot_all;
-  block_excl_scan(part, s_warp, &tot_before);
-  if (blockIdx.x == 0) {
-    block_excl_scan(all, s_warp, &tot_all);
-    if (threadIdx.x == 0) *n_kept = tot_all;
-  }
-  const uint64_t i = i0 + threadIdx.x;
-  bool keep = false;
-  if (i < n) {
-    const uint8_t st = rec[i].status;
-    keep = st != HM_ST_INTERNAL_DROPPED && !(omit && st >= HM_ST_GERM_HET && st <= HM_ST_GERM_HOMREF);
-  }
-  uint32_t total;
-  const uint32_t ex = block_excl_scan(keep ? 1u : 0u, s_warp, &total);
-  if (i < n) {
-    kpos[i] = tot_before + ex;
-    if (keep) out[tot_before + ex] = rec[i];
-  }
+// ============================================================================ k_publish_call
+// Everything the host reads at the one synchronisation of a call, in one launch, into mapped pinned memory:
+// the counters and the first boundary records (index in key order, position among the kept records, the record).
+__global__ void __launch_bounds__(256) k_publish_call(const uint32_t* cnt, uint32_t cnt_words, const uint32_t* bidx, const uint32_t* bpos,
+                                                      const uint32_t* brecs, uint32_t max_items, const unsigned long long* n_items_dev,
+                                                      uint32_t* m_cnt, uint32_t* m_bidx, uint32_t* m_bpos, uint32_t* m_brecs) {
+  const uint32_t n = (uint32_t)min((unsigned long long)max_items, *n_items_dev);
+  const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+  for (uint32_t i = tid; i < cnt_words; i += nth) m_cnt[i] = cnt[i];
+  for (uint32_t i = tid; i < n; i += nth) { m_bidx[i] = bidx[i]; m_bpos[i] = bpos[i]; }
+  const uint32_t rw = (uint32_t)(sizeof(hm_site_record) / 4);
+  for (uint32_t i = tid; i < n * rw; i += nth) m_brecs[i] = brecs[i];
+  __threadfence_system();
 }

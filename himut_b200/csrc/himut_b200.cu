@@ -113,7 +113,7 @@ struct hm_ctx {
   uint64_t site_cap_hint = 0;               // high-water mark of distinct sites per call
   char* h_geom_pin = nullptr;
   size_t h_geom_cap = 0;
-  DevBuf b_cgeom, b_seg_keys, b_seg_read, b_key_site, b_keys_tmp, b_gscratch, b_czero, b_first_pair, b_tiles, b_site_valid;
+  DevBuf b_cgeom, b_seg_keys, b_seg_read, b_keys_tmp, b_gscratch, b_czero, b_first_pair, b_tiles, b_site_valid, b_pair_c;
 };
 
 namespace {
@@ -315,7 +315,7 @@ void hm_destroy(hm_ctx* ctx) {
                     &ctx->b_hpos, &ctx->b_href, &ctx->b_halt, &ctx->b_hbit, &ctx->b_set_off, &ctx->b_chunks,
                     &ctx->b_pair_off, &ctx->b_pair_hap, &ctx->b_qseen, &ctx->b_keys, &ctx->b_keys_sorted, &ctx->b_cub,
                     &ctx->b_records, &ctx->b_counters, &ctx->b_ref, &ctx->b_norm_out, &ctx->b_lut, &ctx->b_tile_off, &ctx->b_agg, &ctx->b_geom, &ctx->b_bidx, &ctx->b_brecs, &ctx->b_sites, &ctx->b_koff, &ctx->b_tile_info, &ctx->b_edge_counts, &ctx->b_edge_hpos, &ctx->b_edge_href, &ctx->b_bqmask, &ctx->b_bqexc, &ctx->b_bqexc_off,
-                    &ctx->b_cgeom, &ctx->b_seg_keys, &ctx->b_seg_read, &ctx->b_key_site, &ctx->b_keys_tmp, &ctx->b_gscratch, &ctx->b_czero, &ctx->b_first_pair, &ctx->b_tiles, &ctx->b_site_valid};
+                    &ctx->b_cgeom, &ctx->b_seg_keys, &ctx->b_seg_read, &ctx->b_keys_tmp, &ctx->b_gscratch, &ctx->b_czero, &ctx->b_first_pair, &ctx->b_tiles, &ctx->b_site_valid, &ctx->b_pair_c};
   for (DevBuf* b : bufs) b->release();
   if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
   if (ctx->h_cnt_pin) cudaFreeHost(ctx->h_cnt_pin);
@@ -622,27 +622,26 @@ int fused_enqueue(hm_ctx* ctx, const hm_chunk* chunks, size_t n_chunks, const st
 
   // ---- buffers ----
   const size_t capk = (size_t)std::max<uint64_t>(total_cap, 1);
-  CU(ctx->b_seg_keys.ensure(capk * 4 + 16)); CU(ctx->b_seg_read.ensure(capk * 4 + 16)); CU(ctx->b_key_site.ensure(capk * 4 + 16));
+  CU(ctx->b_seg_keys.ensure(capk * 4 + 16)); CU(ctx->b_seg_read.ensure(capk * 4 + 16));
   CU(ctx->b_keys_tmp.ensure(capk * 4 + 16)); CU(ctx->b_gscratch.ensure(capk * 8 + 16));
   const size_t z_cnt = 0, z_cur = z_cnt + n_chunks * 4, z_cur2 = z_cur + n_chunks * 4, z_counted = align16(z_cur2 + n_chunks * 4),
                z_qvfail = align16(z_counted + n_reads), z_bytes = align16(z_qvfail + n_reads) + 16;
   CU(ctx->b_czero.ensure(z_bytes));
   CU(ctx->b_first_pair.ensure(n_reads * 4 + 16));
+  CU(ctx->b_pair_c.ensure((size_t)n_pairs * 4 + 16));
   CU(ctx->b_tiles.ensure(((size_t)n_tiles * 3 + 4) * 4));
   const uint64_t stride = (site_cap + 31) & ~31ull;
+  if (stride * HM_SITE_SLOTS + site_cap >= (1ull << 32)) return fail(ctx, HM_ERR_ARG, "%llu candidate sites in one call: split the chunk list", (unsigned long long)site_cap);
   CU(ctx->b_keys.ensure(site_cap * 8 + 16));
   CU(ctx->b_agg.ensure(stride * HM_SITE_SLOTS * 4 + site_cap * 8 + 16));
   CU(ctx->b_site_valid.ensure(site_cap + 16));
-  DevBuf& rec_buf = parity ? ctx->b_records_alt : ctx->b_records;
-  CU(rec_buf.ensure(site_cap * sizeof(hm_site_record)));
   CU(ctx->b_compact[parity].ensure(site_cap * sizeof(hm_site_record)));
-  CU(ctx->b_kpos.ensure(site_cap * 4 + 16));
   const unsigned n_red = (unsigned)((site_cap + 127) / 128);
-  CU(ctx->b_keep.ensure((size_t)n_red * 4 + 16));
   CU(ctx->b_bidx.ensure(boundary_cap * 4 + HM_BOUNDARY_FIRST * 4));
   CU(ctx->b_brecs.ensure((boundary_cap + HM_BOUNDARY_FIRST) * sizeof(hm_site_record)));
   CU(ctx->b_bpos.ensure((boundary_cap + HM_BOUNDARY_FIRST) * 4));
-  CU(ctx->b_qseen.ensure((size_t)ctx->max_qname_id + 1));
+  const size_t qseen_bytes = ((size_t)ctx->max_qname_id + 4) & ~(size_t)3; // one byte per query name, set through 32-bit atomics
+  CU(ctx->b_qseen.ensure(qseen_bytes + 16));
   if (ctx->params.phase) CU(ctx->b_pair_hap.ensure(n_pairs + 16));
 
   char* z = ctx->b_czero.as<char>();
@@ -660,39 +659,43 @@ int fused_enqueue(hm_ctx* ctx, const hm_chunk* chunks, size_t n_chunks, const st
   uint32_t* site_lo = entries + stride * HM_SITE_SLOTS;
   uint32_t* site_n = site_lo + site_cap;
   uint8_t* pair_hap = ctx->params.phase ? ctx->b_pair_hap.as<uint8_t>() : nullptr;
+  uint32_t* pair_c = ctx->b_pair_c.as<uint32_t>();
   const bool has_seq = ctx->db.seq != nullptr;
 
   static bool attr_set = false;
-  const size_t sort_smem = (2 * (size_t)HC_TILE_WORDS + 2 * (size_t)HC_CAPD) * 4;
-  const size_t scan_smem = sizeof(ScanWarp) * HC_WARPS;
+  const size_t sort_smem = (2 * (size_t)HC_TILE_WORDS + 2 * (size_t)HC_CAPD + (size_t)HC_STAGE) * 4;
+  const size_t scan_smem = sizeof(ScanWarp) * HC_SCAN_WARPS;
+  const size_t pairs_smem = (size_t)HC_A_CAP * 4;
   if (!attr_set) {
     CU(cudaFuncSetAttribute(k_site_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sort_smem));
+    CU(cudaFuncSetAttribute(k_call_pairs<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pairs_smem));
+    CU(cudaFuncSetAttribute(k_call_pairs<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pairs_smem));
     CU(cudaFuncSetAttribute(k_call_scan<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scan_smem));
     CU(cudaFuncSetAttribute(k_call_scan<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scan_smem));
     attr_set = true;
   }
 
   CU(cudaMemsetAsync(ctx->b_counters.p, 0, 256, ctx->stream));
-  CU(cudaMemsetAsync(ctx->b_qseen.p, 0, (size_t)ctx->max_qname_id + 1, ctx->stream));
+  CU(cudaMemsetAsync(ctx->b_qseen.p, 0, qseen_bytes, ctx->stream));
   CU(cudaMemsetAsync(ctx->b_czero.p, 0, z_bytes, ctx->stream));
   CU(cudaMemsetAsync(ctx->b_first_pair.p, 0xff, n_reads * 4, ctx->stream));
-  const unsigned pair_blocks = (unsigned)((n_pairs + HC_WARPS - 1) / HC_WARPS);
+  const unsigned pair_blocks_a = (unsigned)((n_pairs + 127) / 128);
   t_begin(ctx, "k_call_pairs");
   if (has_seq)
-    k_call_pairs<true><<<pair_blocks, 32 * HC_WARPS, 0, ctx->stream>>>(ctx->db, ctx->dp, ctx->dphase, G.chunks, (uint32_t)n_chunks, G.pair_off, n_pairs, pair_hap,
-                                                                      read_counted, ctx->b_first_pair.as<uint32_t>(), G.seg_off, seg_cnt,
-                                                                      ctx->b_seg_keys.as<uint32_t>(), ctx->b_seg_read.as<uint32_t>());
+    k_call_pairs<true><<<pair_blocks_a, 128, pairs_smem, ctx->stream>>>(ctx->db, ctx->dp, ctx->dphase, G.chunks, (uint32_t)n_chunks, G.pair_off, n_pairs, pair_c, pair_hap,
+                                                              read_counted, ctx->b_first_pair.as<uint32_t>(), G.seg_off, seg_cnt,
+                                                              ctx->b_seg_keys.as<uint32_t>(), ctx->b_seg_read.as<uint32_t>());
   else
-    k_call_pairs<false><<<pair_blocks, 32 * HC_WARPS, 0, ctx->stream>>>(ctx->db, ctx->dp, ctx->dphase, G.chunks, (uint32_t)n_chunks, G.pair_off, n_pairs, pair_hap,
-                                                                       read_counted, ctx->b_first_pair.as<uint32_t>(), G.seg_off, seg_cnt,
-                                                                       ctx->b_seg_keys.as<uint32_t>(), ctx->b_seg_read.as<uint32_t>());
+    k_call_pairs<false><<<pair_blocks_a, 128, pairs_smem, ctx->stream>>>(ctx->db, ctx->dp, ctx->dphase, G.chunks, (uint32_t)n_chunks, G.pair_off, n_pairs, pair_c, pair_hap,
+                                                               read_counted, ctx->b_first_pair.as<uint32_t>(), G.seg_off, seg_cnt,
+                                                               ctx->b_seg_keys.as<uint32_t>(), ctx->b_seg_read.as<uint32_t>());
   t_end(ctx);
   CU(cudaGetLastError());
   t_begin(ctx, "k_site_sort");
   if (n_tiles)
     k_site_sort<<<(unsigned)n_tiles, HC_SORT_THREADS, sort_smem, ctx->stream>>>(G.tile_chunk, G.tile_off, G.seg_off, seg_cnt, ctx->b_seg_keys.as<uint32_t>(),
                                                                                cursor, cursor2, ctx->b_gscratch.as<uint32_t>(), ctx->b_keys_tmp.as<uint32_t>(),
-                                                                               ctx->b_key_site.as<uint32_t>(), tile_src, tile_cnt);
+                                                                               tile_src, tile_cnt);
   k_tile_scan<<<1, 1024, 0, ctx->stream>>>(tile_cnt, (uint32_t)n_tiles, tile_dst, (unsigned long long)site_cap, d_cnt);
   k_site_range2<<<(unsigned)((site_cap + 255) / 256), 256, 0, ctx->stream>>>(ctx->db, G.chunks, G.tile_chunk, tile_src, tile_dst, (uint32_t)n_tiles,
                                                                             ctx->b_keys_tmp.as<uint32_t>(), d_cnt + 1, keys, site_lo, site_n, entries, stride,
@@ -702,34 +705,31 @@ int fused_enqueue(hm_ctx* ctx, const hm_chunk* chunks, size_t n_chunks, const st
   int rc = flush_deferred(ctx, true); // the previous call's records start moving now, under the quality scan
   if (rc) return rc;
   unsigned int* qv_any = reinterpret_cast<unsigned int*>(d_cnt + 7);
+  const unsigned pair_blocks_b = (unsigned)((n_pairs + HC_SCAN_WARPS - 1) / HC_SCAN_WARPS);
   t_begin(ctx, "k_call_scan");
   if (has_seq)
-    k_call_scan<true><<<pair_blocks, 32 * HC_WARPS, scan_smem, ctx->stream>>>(ctx->db, ctx->dp, G.chunks, (uint32_t)n_chunks, G.pair_off, n_pairs, pair_hap,
-                                                                             read_counted, ctx->b_first_pair.as<uint32_t>(), G.tile_off, tile_dst, keys,
-                                                                             site_lo, site_n, entries, stride, qv_fail_read, qv_any,
-                                                                             ctx->b_qseen.as<uint8_t>(), d_cnt + 1);
+    k_call_scan<true><<<pair_blocks_b, 32 * HC_SCAN_WARPS, scan_smem, ctx->stream>>>(ctx->db, ctx->dp, G.chunks, G.pair_off, n_pairs, pair_c, pair_hap, read_counted,
+                                                                                    ctx->b_first_pair.as<uint32_t>(), G.tile_off, tile_dst, keys, site_lo, site_n,
+                                                                                    entries, (uint32_t)stride, qv_fail_read, qv_any, ctx->b_qseen.as<uint32_t>(),
+                                                                                    d_cnt + 24, d_cnt + 1);
   else
-    k_call_scan<false><<<pair_blocks, 32 * HC_WARPS, scan_smem, ctx->stream>>>(ctx->db, ctx->dp, G.chunks, (uint32_t)n_chunks, G.pair_off, n_pairs, pair_hap,
-                                                                              read_counted, ctx->b_first_pair.as<uint32_t>(), G.tile_off, tile_dst, keys,
-                                                                              site_lo, site_n, entries, stride, qv_fail_read, qv_any,
-                                                                              ctx->b_qseen.as<uint8_t>(), d_cnt + 1);
+    k_call_scan<false><<<pair_blocks_b, 32 * HC_SCAN_WARPS, scan_smem, ctx->stream>>>(ctx->db, ctx->dp, G.chunks, G.pair_off, n_pairs, pair_c, pair_hap, read_counted,
+                                                                                     ctx->b_first_pair.as<uint32_t>(), G.tile_off, tile_dst, keys, site_lo, site_n,
+                                                                                     entries, (uint32_t)stride, qv_fail_read, qv_any, ctx->b_qseen.as<uint32_t>(),
+                                                                                     d_cnt + 24, d_cnt + 1);
   t_end(ctx);
   CU(cudaGetLastError());
-  CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_copy_done[parity], 0)); // the copy that last read these record buffers
+  CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_copy_done[parity], 0)); // the copy that last read this record buffer
   t_begin(ctx, "k_site_reduce");
   if (n_chunks)
-    k_site_valid<<<(unsigned)n_chunks, 256, 0, ctx->stream>>>(qv_any, qv_fail_read, G.seg_off, seg_cnt, ctx->b_seg_keys.as<uint32_t>(),
-                                                            ctx->b_seg_read.as<uint32_t>(), ctx->b_key_site.as<uint32_t>(), G.tile_off, tile_dst,
-                                                            d_cnt + 1, ctx->b_site_valid.as<uint8_t>());
+    k_site_valid<<<(unsigned)n_chunks, 256, 0, ctx->stream>>>(qv_any, qv_fail_read, G.chunks, G.seg_off, seg_cnt, ctx->b_seg_keys.as<uint32_t>(),
+                                                            ctx->b_seg_read.as<uint32_t>(), G.tile_off, tile_dst, keys, d_cnt + 1,
+                                                            ctx->b_site_valid.as<uint8_t>());
   k_site_reduce<<<n_red, 128, 0, ctx->stream>>>(ctx->db, ctx->dp, ctx->dsets, ctx->dlut, ctx->dphase, ctx->dup_names ? 1 : 0, G.chunks, G.pair_off, pair_hap,
                                                 G.geom, G.geom + n_chunks, keys, d_cnt + 1, site_lo, site_n, entries, stride,
-                                                rec_buf.as<hm_site_record>(), d_cnt + 8, ctx->b_bidx.as<uint32_t>(), ctx->b_brecs.as<hm_site_record>(),
+                                                nullptr, d_cnt + 8, ctx->b_bidx.as<uint32_t>(), ctx->b_brecs.as<hm_site_record>(),
                                                 (uint32_t)boundary_cap, d_cnt + 4, reinterpret_cast<int*>(d_cnt + 3), ctx->b_site_valid.as<uint8_t>(),
-                                                qv_any, ctx->b_keep.as<uint32_t>(), omit ? 1 : 0);
-  k_compact_sites<<<(unsigned)std::max<uint64_t>(1, (site_cap + 1023) / 1024), 1024, 0, ctx->stream>>>(
-      rec_buf.as<hm_site_record>(), d_cnt + 1, ctx->b_keep.as<uint32_t>(), omit ? 1 : 0, ctx->b_compact[parity].as<hm_site_record>(),
-      ctx->b_kpos.as<uint32_t>(), d_cnt + 6);
-  k_gather_u32<<<8, 256, 0, ctx->stream>>>(ctx->b_kpos.as<uint32_t>(), ctx->b_bidx.as<uint32_t>(), d_cnt + 4, (uint32_t)boundary_cap, ctx->b_bpos.as<uint32_t>());
+                                                qv_any, ctx->b_compact[parity].as<hm_site_record>(), d_cnt + 6, ctx->b_bpos.as<uint32_t>(), omit ? 1 : 0);
   t_end(ctx);
   CU(cudaGetLastError());
   return HM_OK;
@@ -799,28 +799,30 @@ static int call_chunks_impl(hm_ctx* ctx, const hm_chunk* chunks, size_t n_chunks
     uint64_t site_cap = std::max<uint64_t>(std::max<uint64_t>(ctx->site_cap_hint, ctx->n_ops_total / 8), 4096);
     if (const char* e = getenv("HIMUT_B200_SITE_CAP")) site_cap = (uint64_t)std::max(1ll, atoll(e)); // tests: force the overflow retry
     site_cap = std::min<uint64_t>(site_cap, std::max<uint64_t>(total_cap, 1));
+    size_t bcap = HM_BOUNDARY_CAP;
     for (int attempt = 0;; attempt++) {
       t_reset(ctx);
       FusedGeom G;
-      if ((rc = fused_enqueue(ctx, chunks, n_chunks, pair_off, geom.data(), total_cap, n_tiles, site_cap, parity, omit, HM_BOUNDARY_CAP, &G))) return rc;
-      t_begin(ctx, "k_count_flags");
-      k_count_flags<<<148, 256, 0, ctx->stream>>>(ctx->b_qseen.as<uint8_t>(), (uint64_t)ctx->max_qname_id + 1, d_cnt + 2);
-      t_end(ctx);
-      k_publish<<<1, 64, 0, ctx->stream>>>(reinterpret_cast<const uint32_t*>(d_cnt), reinterpret_cast<uint32_t*>(ctx->h_cnt_pin), (uint32_t)(CNT_BYTES / 4));
-      k_publish_items<<<4, 256, 0, ctx->stream>>>(ctx->b_bidx.as<uint32_t>(), h_bidx, 1u, (uint32_t)HM_BOUNDARY_FIRST, d_cnt + 4);
-      k_publish_items<<<8, 256, 0, ctx->stream>>>(ctx->b_brecs.as<uint32_t>(), reinterpret_cast<uint32_t*>(h_brecs),
-                                                  (uint32_t)(sizeof(hm_site_record) / 4), (uint32_t)HM_BOUNDARY_FIRST, d_cnt + 4);
-      k_publish_items<<<4, 256, 0, ctx->stream>>>(ctx->b_bpos.as<uint32_t>(), h_bpos, 1u, (uint32_t)HM_BOUNDARY_FIRST, d_cnt + 4);
+      if ((rc = fused_enqueue(ctx, chunks, n_chunks, pair_off, geom.data(), total_cap, n_tiles, site_cap, parity, omit, bcap, &G))) return rc;
+      k_publish_call<<<8, 256, 0, ctx->stream>>>(reinterpret_cast<const uint32_t*>(d_cnt), (uint32_t)(CNT_BYTES / 4), ctx->b_bidx.as<uint32_t>(),
+                                                 ctx->b_bpos.as<uint32_t>(), ctx->b_brecs.as<uint32_t>(), (uint32_t)std::min<size_t>(HM_BOUNDARY_FIRST, bcap),
+                                                 d_cnt + 4, reinterpret_cast<uint32_t*>(ctx->h_cnt_pin), h_bidx, h_bpos, reinterpret_cast<uint32_t*>(h_brecs));
       CU(cudaGetLastError());
       lap(4);
       CU(cudaStreamSynchronize(ctx->stream)); // the one synchronisation of the call
       lap(5);
       memcpy(h_cnt, ctx->h_cnt_pin, CNT_BYTES);
-      if (!h_cnt[5]) break;
-      if (attempt >= 2) return fail(ctx, HM_ERR_STATE, "site buffers overflowed twice (%llu sites)", h_cnt[5]);
-      site_cap = std::min<uint64_t>(h_cnt[5] + h_cnt[5] / 8 + 1024, std::max<uint64_t>(total_cap, 1)); // the list overflowed: run again with room
+      const bool more_sites = h_cnt[5] != 0, more_boundary = h_cnt[4] > bcap;
+      if (!more_sites && !more_boundary) break;
+      if (attempt >= 3) return fail(ctx, HM_ERR_STATE, "site / boundary buffers overflowed repeatedly (%llu sites, %llu boundary records)", h_cnt[5], h_cnt[4]);
+      // a list overflowed: run again with room (the counts are exact now)
+      if (more_sites) site_cap = std::min<uint64_t>(h_cnt[5] + h_cnt[5] / 8 + 1024, std::max<uint64_t>(total_cap, 1));
+      if (more_boundary) bcap = (size_t)h_cnt[4] + 1024;
       memset(h_cnt, 0, sizeof(h_cnt));
     }
+    HM_BOUNDARY_CAP = bcap;
+    h_cnt[2] = 0;
+    for (int k = 24; k < 32; k++) h_cnt[2] += h_cnt[k]; // num_ccs: distinct query names, counted in eight slots
     ctx->site_cap_hint = std::max<uint64_t>(ctx->site_cap_hint, h_cnt[1] + h_cnt[1] / 4);
     n_keys = h_cnt[1];
   } else {
@@ -925,7 +927,7 @@ static int call_chunks_impl(hm_ctx* ctx, const hm_chunk* chunks, size_t n_chunks
           ctx->db, ctx->dp, ctx->dsets, ctx->dlut, ctx->dphase, ctx->dup_names ? 1 : 0, ctx->b_chunks.as<hm_chunk>(), ctx->b_pair_off.as<uint64_t>(),
           ctx->b_pair_hap.as<uint8_t>(), ctx->b_geom.as<int32_t>(), ctx->b_geom.as<int32_t>() + n_chunks, k_in, d_cnt + 1, site_lo,
           site_n, entries, stride, rec_buf.as<hm_site_record>(), d_cnt + 8, ctx->b_bidx.as<uint32_t>(),
-          ctx->b_brecs.as<hm_site_record>(), (uint32_t)HM_BOUNDARY_CAP, d_cnt + 4, reinterpret_cast<int*>(d_cnt + 3), nullptr, nullptr, nullptr, 0);
+          ctx->b_brecs.as<hm_site_record>(), (uint32_t)HM_BOUNDARY_CAP, d_cnt + 4, reinterpret_cast<int*>(d_cnt + 3), nullptr, nullptr, nullptr, nullptr, nullptr, 0);
       if (omit) { // records of germline restatements stay here: flags -> scan -> stable compaction
         CU(ctx->b_keep.ensure(n_unique * 4 + 16)); CU(ctx->b_kpos.ensure(n_unique * 4 + 16));
         CU(ctx->b_bpos.ensure(((size_t)HM_BOUNDARY_CAP + HM_BOUNDARY_FIRST) * 4));

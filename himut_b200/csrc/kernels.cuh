@@ -812,8 +812,10 @@ __global__ void __launch_bounds__(256) k_site_entries_by_read(DevBatch b, DevPar
 //   re-fetches at a phase-checked site by *name* (wt_ccs_set / alt_ccs_set, caller.py:556-567); with unique names
 //   that is the record's own allele (the entries' haplotype tallies), with shared names the exact walk below.
 // site_valid / qv_fail (fused path, else NULL): *qv_fail != 0 -> only sites with site_valid[ki] exist.
-// keep_cnt (fused path, else NULL): per block, the number of records the host wants (not dropped; not a germline
-//   restatement when omit != 0).
+// compact_out / n_kept / boundary_pos (fused path, else NULL): the records the host wants (not dropped; not a germline
+//   restatement when omit != 0) are written to compact_out only — a block reserves its range with one atomic on
+//   *n_kept, inside the block the order is the key order — and a boundary record carries its position there
+//   (0xffffffff: not kept).  `out` is not written then.
 __global__ void __launch_bounds__(128) k_site_reduce(DevBatch b, DevParams p, DevSets sets, DevLut lut, DevPhase ph, int dup_names,
                                                      const hm_chunk* chunks,
                                                      const uint64_t* pair_off, const uint8_t* pair_hap, const int32_t* prev_max_end,
@@ -823,24 +825,21 @@ __global__ void __launch_bounds__(128) k_site_reduce(DevBatch b, DevParams p, De
                                                      hm_site_record* out, unsigned long long* status_hist, uint32_t* boundary_idx,
                                                      hm_site_record* boundary_recs, uint32_t boundary_cap,
                                                      unsigned long long* n_boundary, int* err_flag,
-                                                     const uint8_t* site_valid, const unsigned int* qv_fail, uint32_t* keep_cnt, int omit) {
+                                                     const uint8_t* site_valid, const unsigned int* qv_fail, hm_site_record* compact_out,
+                                                     unsigned long long* n_kept, uint32_t* boundary_pos, int omit) {
   __shared__ unsigned int s_hist[16];
-  __shared__ unsigned int s_keep;
+  __shared__ unsigned int s_wkeep[4], s_kbase;
   __shared__ double s_lut[3][256];
   for (int i = threadIdx.x; i < 768; i += blockDim.x) s_lut[i >> 8][i & 255] = __ldg(lut.lut + i);
   if (threadIdx.x < 16) s_hist[threadIdx.x] = 0;
-  if (threadIdx.x == 0) s_keep = 0;
   __syncthreads();
+  hm_site_record R;
+  bool have_rec = false, keep = false, bnd = false;
   const uint64_t ki = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const uint64_t n_keys = *n_keys_dev;
   const bool fused = site_valid != nullptr; // no op prefix arrays in HBM then
   if (ki < n_keys && site_valid && *qv_fail && !site_valid[ki]) {
-    hm_site_record R;
-    memset(&R, 0, sizeof(R));
-    R.tpos = (int32_t)((keys[ki] >> 4) & 0xffffffffull);
-    R.chunk = (int32_t)(keys[ki] >> 36);
-    R.status = HM_ST_INTERNAL_DROPPED; // k_compact_sites skips it; not tallied, not a boundary record
-    out[ki] = R;
+    // a speculative site none of whose supporting reads passed the QV gate: no record, no tally
   } else if (ki < n_keys) {
     const unsigned long long key = keys[ki];
     const uint32_t c = (uint32_t)(key >> 36);
@@ -960,7 +959,6 @@ __global__ void __launch_bounds__(128) k_site_reduce(DevBatch b, DevParams p, De
         }
       }
     }
-    hm_site_record R;
     R.tpos = tpos; R.ref = (uint8_t)ref; R.alt = (uint8_t)alt; R.status = (uint8_t)status;
     R.flags = tie ? HM_SITE_PL_TIE : 0;
     R.chunk = (int32_t)c; R.gq = gq;
@@ -973,17 +971,34 @@ __global__ void __launch_bounds__(128) k_site_reduce(DevBatch b, DevParams p, De
     R.hap_count[0] = ph_eval ? h0 : 0; R.hap_count[1] = ph_eval ? h1 : 0;
     R.som_hap_mask = ph_eval ? som_mask : 0;
     R.phase_set = phase_set;
-    out[ki] = R;
+    have_rec = true;
+    keep = !(omit && status >= HM_ST_GERM_HET && status <= HM_ST_GERM_HOMREF);
+    bnd = tpos <= prev_max_end[c] || tpos >= next_min_start[c];
     atomicAdd(&s_hist[status], 1u);
-    if (!(omit && status >= HM_ST_GERM_HET && status <= HM_ST_GERM_HOMREF)) atomicAdd(&s_keep, 1u);
-    if (tpos <= prev_max_end[c] || tpos >= next_min_start[c]) {
-      const unsigned long long at = atomicAdd(n_boundary, 1ull);
-      if (at < boundary_cap) { boundary_idx[at] = (uint32_t)ki; boundary_recs[at] = R; } // a copy for the host's som_seen replay
+  }
+  uint32_t pos = 0xffffffffu;
+  if (compact_out) { // block-stable compaction: ballot rank inside the warp, warp totals, one atomic per block
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const uint32_t bal = __ballot_sync(HM_FULL, keep);
+    if (lane == 0) s_wkeep[wid] = __popc(bal);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const unsigned int tot = s_wkeep[0] + s_wkeep[1] + s_wkeep[2] + s_wkeep[3];
+      s_kbase = tot ? (unsigned int)atomicAdd(n_kept, (unsigned long long)tot) : 0u;
     }
+    __syncthreads();
+    uint32_t before = 0;
+    for (int w = 0; w < wid; w++) before += s_wkeep[w];
+    if (keep) { pos = s_kbase + before + __popc(bal & ((1u << lane) - 1u)); compact_out[pos] = R; }
+  } else if (have_rec) {
+    out[ki] = R;
+  }
+  if (bnd) { // a copy for the host's som_seen replay
+    const unsigned long long at = atomicAdd(n_boundary, 1ull);
+    if (at < boundary_cap) { boundary_idx[at] = (uint32_t)ki; boundary_recs[at] = R; if (boundary_pos) boundary_pos[at] = pos; }
   }
   __syncthreads();
   if (threadIdx.x < 16 && s_hist[threadIdx.x]) atomicAdd(status_hist + threadIdx.x, (unsigned long long)s_hist[threadIdx.x]);
-  if (keep_cnt && threadIdx.x == 0) keep_cnt[blockIdx.x] = s_keep;
 }
 
 // Small results go to the host through mapped pinned memory (plain stores over PCIe) instead of the copy engine,

@@ -30,7 +30,7 @@ def test_call_full_size_equals_oracle(ctx, big):
     # structural properties that hold at any size
     assert rec.size == int(log[1])
     key = (rec["chunk"].astype(np.int64) << 36) | (rec["tpos"].astype(np.int64) << 4) | (rec["ref"] << 2) | rec["alt"]
-    assert np.all(np.diff(key) > 0), "records are sorted by (chunk, tpos, ref, alt) and distinct"
+    assert np.all(np.diff(np.sort(key)) > 0), "records are distinct in (chunk, tpos, ref, alt); they come back in no particular order"
     assert np.all((rec["tpos"] >= chunks["start"][rec["chunk"]]) & (rec["tpos"] <= chunks["end"][rec["chunk"]]))
     assert int(log[6]) == int(log[8:15].sum())
     assert int(log[1]) == int(log[2:8].sum()) + int((rec["status"] == abi.ST_GERM_HOMREF).sum())
