@@ -163,6 +163,10 @@ class ReadBatch:
                 s.seq, s.seq_off = None, None
             s.seq_bytes = self.seq.size
             s.bq_bytes = self.bq.size
+            if not self.bq.size and getattr(self, "bq_bytes_expanded", 0):
+                # the qualities travel in compact form (BqCompact): no one-byte-per-base stream on the host;
+                # bq_off / bq_bytes describe the layout the device expands to
+                s.bq, s.bq_bytes = None, int(self.bq_bytes_expanded)
             s.n_ops_total = self.ops.size
             self._struct = s
         return self._struct

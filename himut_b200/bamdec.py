@@ -16,7 +16,7 @@ from . import abi, pack
 
 _LIB = None
 EXPORTS = ["hm_bam_open", "hm_bam_close", "hm_bam_error", "hm_bam_header_text", "hm_bam_n_refs", "hm_bam_ref_name",
-           "hm_bam_ref_len", "hm_bam_read_batch", "hm_bam_set_option", "hm_bam_n_qnames", "hm_bam_qname", "hm_bam_window_qlens", "hm_bam_write_batch", "hm_bq_compact_build",
+           "hm_bam_ref_len", "hm_bam_read_batch", "hm_bam_set_option", "hm_bam_last_compact", "hm_bam_n_qnames", "hm_bam_qname", "hm_bam_window_qlens", "hm_bam_write_batch", "hm_bq_compact_build",
            "hm_bq_compact_free"]
 
 
@@ -45,6 +45,7 @@ def load():
         lib.hm_bam_ref_len.argtypes = [vp, C.c_int]
         lib.hm_bam_read_batch.argtypes = [vp, C.c_int, C.c_int32, C.c_int32, C.c_int, C.POINTER(abi.hm_read_batch)]
         lib.hm_bam_set_option.argtypes = [vp, C.c_int, C.c_int]
+        lib.hm_bam_last_compact.argtypes = [vp, C.POINTER(abi.hm_bq_compact)]
         lib.hm_bam_window_qlens.argtypes = [vp, C.c_int, C.c_int32, C.c_int32, C.c_int, vp, C.c_size_t, C.POINTER(C.c_size_t)]
         lib.hm_bam_write_batch.argtypes = [C.c_char_p, C.c_char_p, C.c_int32, C.c_char_p, C.POINTER(abi.hm_read_batch), C.c_int, C.c_int]
         lib.hm_bq_compact_build.argtypes = [C.POINTER(abi.hm_read_batch), C.c_int, vp, vp, C.POINTER(vp), C.POINTER(C.c_uint64), C.POINTER(C.c_uint8)]
@@ -116,24 +117,41 @@ class NativeBam:
         self.lengths = [self.lib.hm_bam_ref_len(self.h, i) for i in range(len(self.references))]
         self.header_text = self.lib.hm_bam_header_text(self.h).decode()
 
-    def read_batch(self, chrom, start, end, copy=True, seq=True):
+    def read_batch(self, chrom, start, end, copy=True, seq=True, compact=False, buffer_set=0):
         """seq=False: the batch comes without its 2-bit base stream (HM_BAM_OPT_NO_SEQ), as `call` and the phase
-        edges want it; the decoder still checks the bases against the cs tag"""
+        edges want it; the decoder still checks the bases against the cs tag.
+        compact=True: the qualities come as modal bitmap + exceptions, written by the record-parse pass itself
+        (HM_BAM_OPT_COMPACT_BQ); returns (batch, abi.BqCompact) for Context.upload_compact — no one-byte-per-base
+        stream exists on the host then (batch.bq is empty).
+        buffer_set (copy=False): which of the handle's two buffer sets receives the batch; a batch stays valid until
+        the next one decoded into the same set, so one can be uploaded while the next is decoded."""
         if chrom not in self.references:
             raise KeyError(chrom)
-        if self.lib.hm_bam_set_option(self.h, 1, 0 if seq else 1) != 0:
-            raise RuntimeError(self.lib.hm_bam_error(self.h).decode())
+        for opt, val in ((1, 0 if seq else 1), (2, 1 if compact else 0), (3, int(buffer_set))):
+            if self.lib.hm_bam_set_option(self.h, opt, val) != 0:
+                raise RuntimeError(self.lib.hm_bam_error(self.h).decode())
         s = abi.hm_read_batch()
         rc = self.lib.hm_bam_read_batch(self.h, self.references.index(chrom), int(max(start, 0)), int(end), self.threads, C.byref(s))
         if rc != 0:
             raise pack.BatchFormatError(self.lib.hm_bam_error(self.h).decode())
         n = int(s.n_reads)
         cp = (lambda a: a.copy()) if copy else (lambda a: a)
-        sizes = {"seq": int(s.seq_bytes), "bq": int(s.bq_bytes), "ops": int(s.n_ops_total)}
+        sizes = {"seq": int(s.seq_bytes), "bq": 0 if compact else int(s.bq_bytes), "ops": int(s.n_ops_total)}
         arrays = {}
         for name, dt in abi.ReadBatch._FIELDS:
             arrays[name] = cp(_view(getattr(s, name), sizes.get(name, n), dt))
-        return abi.ReadBatch(keepalive=None if copy else self, **arrays)
+        batch = abi.ReadBatch(keepalive=None if copy else self, **arrays)
+        if not compact:
+            return batch
+        batch.bq_bytes_expanded = int(s.bq_bytes)
+        q = abi.hm_bq_compact()
+        if self.lib.hm_bam_last_compact(self.h, C.byref(q)) != 0:
+            raise RuntimeError(self.lib.hm_bam_error(self.h).decode())
+        n_exc = int(q.exc_bytes)
+        mask = cp(_view(q.mask, int(q.mask_bytes), np.uint8))
+        exc = cp(_view(q.exc, (n_exc + 31) & ~15, np.uint8))  # the decoder keeps 32 readable bytes past the last exception
+        exc_off = cp(_view(q.exc_off, n + 1, np.uint64))
+        return batch, abi.BqCompact(mask, exc, exc_off, int(q.modal), n_exc)
 
     def window_qlens(self, chrom, start, end):
         """len(query_sequence) of the records overlapping [start, end) with MAPQ > 0 and tp:A:P, fetch order

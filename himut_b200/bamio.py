@@ -298,8 +298,8 @@ def read_batch(reader, chrom, start, end, builder=None):
             continue
         if "cs" not in r.tags:
             raise pack.BatchFormatError("%s has no cs:Z tag (the reference raises KeyError in BAM.__init__)" % r.query_name)
-        if r.hard_clipped:
-            raise pack.BatchFormatError("%s is hard clipped: cs / SEQ indexing breaks in the reference (pre-filter with -F 0x900)" % r.query_name)
+        # hard clips: pysam's query_sequence / query_alignment_start leave the clipped bases out (SEQ does not hold
+        # them), so cs2tuple indexes consistently and the reference processes such records; so do we
         q = r.query_qualities
         if q is None:
             raise pack.BatchFormatError("%s has no base qualities" % r.query_name)

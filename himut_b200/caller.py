@@ -58,25 +58,35 @@ def get_somatic_substitutions(
     kept, som_seen = [], set()
     starts = [s for _, s, _e in chunkloci_lst]
     groups = worker.group_chunks(chunkloci_lst)
-    for gi, idx in enumerate(groups):
-        loci = [chunkloci_lst[i] for i in idx]
-        batch, table = src.batch(chrom, loci, None if chunk_sets is None else [chunk_sets[i] for i in idx], seq=False)
-        if batch.n_reads == 0:
-            continue
-        # `call` never needs the read bases as a stream: substituted bases are in the ops, and under a cs match the
-        # read carries the reference allele of the site (cslib.py:22-29) — the decoder does not unpack them
-        # (seq=False above) and a quarter of the upload goes away
-        ctx.upload(batch)
-        rec, _log = ctx.call_chunks(table)
-        tally.add(ctx.qname_seen())
-        # som_seen carries across groups exactly as across chunks (caller.py:243,347; bamlib.py:77)
-        if som_seen and rec.size:
-            rec = rec[~np.isin(rec["tpos"], np.fromiter(som_seen, np.int32, len(som_seen)))]
-        later = min(starts[idx[-1] + 1:], default=None)
-        if later is not None and rec.size:
-            claim = rec[(~np.isin(rec["status"], _RESTATES)) & (rec["tpos"] >= later)]
-            som_seen.update(int(t) for t in claim["tpos"])
-        kept.append(rec)
+    pins = worker.PinCache(ctx, enabled=len(groups) > 1)
+    # `call` never needs the read bases as a stream: substituted bases are in the ops, and under a cs match the read
+    # carries the reference allele of the site (cslib.py:22-29) — the decoder does not unpack them (seq=False) — and the
+    # qualities travel as the decoder's parse pass leaves them: bitmap of the modal quality + exceptions, expanded on the
+    # device (upload_compact).  Group k + 1 is decoded while group k is uploaded and called.
+    # --phase: the reference re-fetches [tpos, tpos + 1) at a site (caller.py:558), one position past a chunk that ends
+    # at tpos: decode that position too, so a record that starts there is in the batch (it can only matter through a
+    # shared query name)
+    try:
+        for idx, batch, cq, table, release in worker.pipelined_groups(src, chrom, chunkloci_lst, groups, chunk_sets, seq=False,
+                                                                      pad=1 if phase else 0):
+            if batch.n_reads == 0:
+                release()
+                continue
+            pins.pin([cq.mask, cq.exc, batch.ops])
+            ctx.upload_compact(batch, cq)
+            release()  # everything is on the device: the decoder may reuse the buffers
+            rec, _log = ctx.call_chunks(table)
+            tally.add(ctx.qname_seen())
+            # som_seen carries across groups exactly as across chunks (caller.py:243,347; bamlib.py:77)
+            if som_seen and rec.size:
+                rec = rec[~np.isin(rec["tpos"], np.fromiter(som_seen, np.int32, len(som_seen)))]
+            later = min(starts[idx[-1] + 1:], default=None)
+            if later is not None and rec.size:
+                claim = rec[(~np.isin(rec["status"], _RESTATES)) & (rec["tpos"] >= later)]
+                som_seen.update(int(t) for t in claim["tpos"])
+            kept.append(rec)
+    finally:
+        pins.close()
     src.close()
     rec = np.concatenate(kept) if kept else np.zeros(0, abi.SITE_DTYPE)
     chrom2tsbs_lst[chrom] = records.records_to_tsbs_lst(chrom, rec)

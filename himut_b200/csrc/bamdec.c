@@ -23,6 +23,9 @@
 #include <sys/stat.h>
 #include <time.h>
 #include <zlib.h>
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
 
 #include "../../include/himut_io.h"
 #include "inflate_fast.h"
@@ -79,8 +82,40 @@ typedef struct hm_bam {
   uint8_t *seq, *bq;
   uint32_t* ops;
   size_t cap_reads, cap_seq, cap_bq, cap_ops;
-  int no_seq; /* HM_BAM_OPT_NO_SEQ: batches come without the 2-bit base stream */
+  /* compact quality stream of the last batch (HM_BAM_OPT_COMPACT_BQ): hm_bq_compact of himut_b200.h */
+  uint8_t *qmask, *qexc;
+  uint64_t* qexc_off;
+  size_t cap_qmask, cap_qexc, cap_qexc_off;
+  uint64_t n_qexc;
+  int no_seq;     /* HM_BAM_OPT_NO_SEQ: batches come without the 2-bit base stream */
+  int compact_bq; /* HM_BAM_OPT_COMPACT_BQ: qualities come as modal bitmap + exceptions, built while records are parsed */
+  int modal;      /* the modal quality of the handle's compact streams (0: not chosen yet) */
+  /* HM_BAM_OPT_BUFFER_SET: two sets of output buffers, so that one batch can be uploaded while the next is decoded */
+  struct hm_bufset {
+    int32_t *tstart, *tend, *qstart, *qlen;
+    uint8_t *mapq, *flags;
+    uint32_t *qname_id, *n_ops;
+    uint64_t *seq_off, *bq_off, *op_off;
+    uint8_t *seq, *bq;
+    uint32_t* ops;
+    size_t cap_reads, cap_seq, cap_bq, cap_ops;
+    uint8_t *qmask, *qexc;
+    uint64_t* qexc_off;
+    size_t cap_qmask, cap_qexc, cap_qexc_off;
+    uint64_t n_qexc;
+  } other; /* the set that is not active */
+  int cur_set;
 } hm_bam;
+
+/* swap the active output buffers with the parked set */
+static void swap_bufset(hm_bam* b) {
+  struct hm_bufset t;
+#define SW(f) t.f = b->f; b->f = b->other.f; b->other.f = t.f
+  SW(tstart); SW(tend); SW(qstart); SW(qlen); SW(mapq); SW(flags); SW(qname_id); SW(n_ops); SW(seq_off); SW(bq_off); SW(op_off);
+  SW(seq); SW(bq); SW(ops); SW(cap_reads); SW(cap_seq); SW(cap_bq); SW(cap_ops); SW(qmask); SW(qexc); SW(qexc_off);
+  SW(cap_qmask); SW(cap_qexc); SW(cap_qexc_off); SW(n_qexc);
+#undef SW
+}
 
 static int fail(hm_bam* b, const char* fmt, const char* a, long x) {
   snprintf(b->err, sizeof(b->err), fmt, a ? a : "", x);
@@ -398,8 +433,12 @@ void hm_bam_close(hm_bam* b) {
   free(b->refs); free(b->header); free(b->path);
   for (uint32_t i = 0; i < b->qt.n; i++) free(b->qt.names[i]);
   free(b->qt.names); free(b->qt.keys_hash); free(b->qt.ids);
-  free(b->tstart); free(b->tend); free(b->qstart); free(b->qlen); free(b->mapq); free(b->flags); free(b->qname_id);
-  free(b->n_ops); free(b->seq_off); free(b->bq_off); free(b->op_off); free(b->seq); free(b->bq); free(b->ops);
+  for (int k = 0; k < 2; k++) { /* both buffer sets */
+    free(b->tstart); free(b->tend); free(b->qstart); free(b->qlen); free(b->mapq); free(b->flags); free(b->qname_id);
+    free(b->n_ops); free(b->seq_off); free(b->bq_off); free(b->op_off); free(b->seq); free(b->bq); free(b->ops);
+    free(b->qmask); free(b->qexc); free(b->qexc_off);
+    swap_bufset(b);
+  }
   free(b);
 }
 
@@ -498,7 +537,8 @@ typedef struct {
   const char* cs;
   int32_t pos, l_seq, lead, trail, ref_span;
   size_t seq_off, bq_off, op_slot; /* where its outputs go; op_slot is an upper-bound slot, compacted afterwards */
-  uint32_t n_ops;
+  size_t exc_slot;                 /* compact qualities: upper-bound slot of the exceptions, compacted afterwards */
+  uint32_t n_ops, n_exc;
   int32_t rspan;
   int err;              /* 0 ok, else index into the message table below */
   long err_arg;
@@ -597,7 +637,7 @@ static void decode_record(hm_bam* b, rec_t* R, uint8_t** codes_p, size_t* codes_
     if (*c == ':') {
       long n = 0; c++;
       if (*c < '0' || *c > '9') { R->err = E_CS_TOKEN; R->err_arg = (long)(c - cs); return; }
-      while (*c >= '0' && *c <= '9') n = n * 10 + (*c++ - '0');
+      while (*c >= '0' && *c <= '9') { n = n * 10 + (*c++ - '0'); if (n > l_seq) { R->err = E_CS_PAST; R->err_arg = n; return; } }
       if (q + n > l_seq) { R->err = E_CS_PAST; R->err_arg = q + n; return; }
       if (n) { const uint8_t* bad = (const uint8_t*)memchr(codes + q, 0xff, (size_t)n); if (bad) { R->err = E_N_MATCH; R->err_arg = (long)(bad - codes); return; } }
       if (n) ops[n_ops++] = HM_MAKE_OP(HM_OP_MATCH, n);
@@ -637,8 +677,34 @@ static void decode_record(hm_bam* b, rec_t* R, uint8_t** codes_p, size_t* codes_
     pack_codes_scalar(codes, have_ssse3() ? pack_codes_simd(codes, l_seq, dst) : 0, l_seq, dst);
     memset(dst + sb, 0, sb16 - sb);
   }
-  memcpy(b->bq + R->bq_off, qual, (size_t)l_seq);
-  memset(b->bq + R->bq_off + l_seq, 0, qb16 - (size_t)l_seq);
+  if (!b->compact_bq) {
+    memcpy(b->bq + R->bq_off, qual, (size_t)l_seq);
+    memset(b->bq + R->bq_off + l_seq, 0, qb16 - (size_t)l_seq);
+  } else {
+    /* hm_bq_compact: one bit per byte of the expanded stream (set: the modal quality; padding bits clear), the other
+     * qualities in base order.  16 qualities per step. */
+    uint8_t* m = b->qmask + (R->bq_off >> 3);
+    uint8_t* e = b->qexc + R->exc_slot;
+    const uint8_t modal = (uint8_t)b->modal;
+    uint32_t ne = 0;
+    int32_t i = 0;
+#if defined(__SSE2__)
+    const __m128i vm = _mm_set1_epi8((char)modal);
+    for (; i + 16 <= l_seq; i += 16) {
+      const uint32_t eq = (uint32_t)_mm_movemask_epi8(_mm_cmpeq_epi8(_mm_loadu_si128((const __m128i*)(qual + i)), vm));
+      m[i >> 3] = (uint8_t)eq; m[(i >> 3) + 1] = (uint8_t)(eq >> 8);
+      uint32_t z = ~eq & 0xffffu;
+      while (z) { const int k = __builtin_ctz(z); z &= z - 1; e[ne++] = qual[i + k]; }
+    }
+#endif
+    for (; i < l_seq; i += 16) { /* the last, partial group (every group without SSE2) */
+      uint32_t eq = 0;
+      const int32_t lim = l_seq - i < 16 ? l_seq - i : 16;
+      for (int32_t k = 0; k < lim; k++) { if (qual[i + k] == modal) eq |= 1u << k; else e[ne++] = qual[i + k]; }
+      m[i >> 3] = (uint8_t)eq; m[(i >> 3) + 1] = (uint8_t)(eq >> 8);
+    }
+    R->n_exc = ne;
+  }
 }
 
 static void* decode_worker(void* arg) {
@@ -659,6 +725,12 @@ static void* decode_worker(void* arg) {
 int hm_bam_set_option(hm_bam* b, int option, int value) {
   if (!b) return HM_ERR_ARG;
   if (option == HM_BAM_OPT_NO_SEQ) { b->no_seq = value != 0; return HM_OK; }
+  if (option == HM_BAM_OPT_COMPACT_BQ) { b->compact_bq = value != 0; return HM_OK; }
+  if (option == HM_BAM_OPT_BUFFER_SET) {
+    if (value != 0 && value != 1) return fail(b, "buffer set must be 0 or 1%s (%ld)", NULL, (long)value);
+    if (value != b->cur_set) { swap_bufset(b); b->cur_set = value; }
+    return HM_OK;
+  }
   return fail(b, "unknown option%s (%ld)", NULL, (long)option);
 }
 
@@ -668,7 +740,9 @@ int hm_bam_read_batch(hm_bam* b, int rid, int32_t start, int32_t end, int thread
   if (start < 0) start = 0;
   if (end > b->refs[rid].len) end = b->refs[rid].len;
   size_t n_reads = 0, n_seq = 0, n_bq = 0, n_ops = 0;
+  uint64_t n_exc = 0;
   memset(out, 0, sizeof(*out));
+  b->n_qexc = 0;
   uint64_t voff = b->first_record;
   if (b->have_bai) {
     const bam_ref_t* R = &b->refs[rid];
@@ -703,7 +777,7 @@ int hm_bam_read_batch(hm_bam* b, int rid, int32_t start, int32_t end, int thread
         if (stream_need(&s, 4 + (size_t)bs0)) { rc = fail(b, "truncated BAM record in %s (%ld)", b->path, 0); break; }
       }
       double tA = now_s();
-      size_t nsel = 0, seg_ops = 0;
+      size_t nsel = 0, seg_ops = 0, seg_exc = 0;
       const size_t first_read = n_reads;
       while (s.len - s.pos >= 4) {
         uint32_t bs = rd32(s.buf + s.pos);
@@ -713,16 +787,21 @@ int hm_bam_read_batch(hm_bam* b, int rid, int32_t start, int32_t end, int thread
         int32_t ref_id = (int32_t)rd32(r), pos = (int32_t)rd32(r + 4);
         if (ref_id != rid) { if (ref_id > rid || ref_id < 0) { done = 1; break; } continue; }
         if (pos >= end) { done = 1; break; }
+        if (bs < 32) { rc = fail(b, "malformed BAM record in %s: block_size %ld", b->path, (long)bs); break; }
         uint32_t l_name = r[8], mapq = r[9], n_cig = r[12] | (r[13] << 8), flag = r[14] | (r[15] << 8);
         int32_t l_seq = (int32_t)rd32(r + 16);
+        /* the fixed part, name, CIGAR, SEQ and QUAL must lie inside the record before any of them is touched */
+        if (l_seq < 0 || l_name == 0 || 32 + (uint64_t)l_name + 4 * (uint64_t)n_cig + ((uint64_t)l_seq + 1) / 2 + (uint64_t)l_seq > (uint64_t)bs ||
+            r[32 + l_name - 1] != 0) {
+          rc = fail(b, "malformed BAM record in %s: fields run past block_size %ld", b->path, (long)bs);
+          break;
+        }
         const char* qname = (const char*)(r + 32);
         const uint8_t* cig = r + 32 + l_name;
         int32_t ref_span = 0, lead = 0, trail = 0;
-        int hard = 0;
         for (uint32_t k = 0; k < n_cig; k++) {
           uint32_t c = rd32(cig + 4 * k), op = c & 15, ln = c >> 4;
           if (op == 0 || op == 2 || op == 3 || op == 7 || op == 8) ref_span += (int32_t)ln;
-          if (op == 5) hard = 1;
         }
         for (uint32_t k = 0; k < n_cig; k++) { uint32_t c = rd32(cig + 4 * k), op = c & 15; if (op == 4) lead += (int32_t)(c >> 4); else if (op != 5) break; }
         for (uint32_t k = n_cig; k-- > 0;) { uint32_t c = rd32(cig + 4 * k), op = c & 15; if (op == 4) trail += (int32_t)(c >> 4); else if (op != 5) break; }
@@ -737,18 +816,31 @@ int hm_bam_read_batch(hm_bam* b, int rid, int32_t start, int32_t end, int thread
         while (tag + 3 <= rec_end) {
           char ty = (char)tag[2];
           const uint8_t* v = tag + 3;
+          const size_t left = (size_t)(rec_end - v);
           size_t adv;
-          if (ty == 'Z' || ty == 'H') { adv = strlen((const char*)v) + 1; if (tag[0] == 'c' && tag[1] == 's' && ty == 'Z') cs = (const char*)v; }
+          if (ty == 'Z' || ty == 'H') {
+            const void* z = memchr(v, 0, left); /* the string must end inside the record */
+            if (!z) { rc = fail(b, "malformed BAM record %s: unterminated %ld tag", qname, (long)ty); break; }
+            adv = (size_t)((const uint8_t*)z - v) + 1;
+            if (tag[0] == 'c' && tag[1] == 's' && ty == 'Z') cs = (const char*)v;
+          }
           else if (ty == 'A' || ty == 'c' || ty == 'C') adv = 1;
           else if (ty == 's' || ty == 'S') adv = 2;
           else if (ty == 'i' || ty == 'I' || ty == 'f') adv = 4;
-          else if (ty == 'B') { char sub = (char)v[0]; uint32_t cnt = rd32(v + 1); adv = 5 + (size_t)cnt * ((sub == 'c' || sub == 'C') ? 1 : (sub == 's' || sub == 'S') ? 2 : 4); }
+          else if (ty == 'B') {
+            if (left < 5) { rc = fail(b, "malformed BAM record %s: truncated B tag (%ld)", qname, (long)left); break; }
+            char sub = (char)v[0]; uint32_t cnt = rd32(v + 1);
+            adv = 5 + (size_t)cnt * ((sub == 'c' || sub == 'C') ? 1 : (sub == 's' || sub == 'S') ? 2 : 4);
+          }
           else { rc = fail(b, "unknown tag type in record %s (%ld)", qname, ty); break; }
+          if (adv > left) { rc = fail(b, "malformed BAM record %s: a tag runs past the record (%ld)", qname, (long)adv); break; }
           tag = v + adv;
         }
         if (rc) break;
         if (!cs) { rc = fail(b, "%s has no cs:Z tag (the reference raises KeyError in BAM.__init__) (%ld)", qname, 0); break; }
-        if (hard) { rc = fail(b, "%s is hard clipped: cs / SEQ indexing breaks in the reference (pre-filter with -F 0x900) (%ld)", qname, 0); break; }
+        /* hard clips: pysam's query_sequence and query_alignment_start leave them out (SEQ holds no hard-clipped base),
+         * so cs2tuple indexes consistently and the reference processes such records (minimap2 writes them for
+         * supplementary alignments without -Y); lead / trail above count soft clips only */
         if (l_seq <= 0 || qual[0] == 0xff) { rc = fail(b, "%s has no base qualities (%ld)", qname, 0); break; }
         if (nsel == recs_cap) {
           size_t nc = recs_cap ? recs_cap * 2 : 8192;
@@ -772,6 +864,17 @@ int hm_bam_read_batch(hm_bam* b, int rid, int32_t start, int32_t end, int thread
         rec_t* R = &recs[nsel++];
         R->rec = r; R->cs = cs; R->pos = pos; R->l_seq = l_seq; R->lead = lead; R->trail = trail; R->ref_span = ref_span;
         R->seq_off = n_seq; R->bq_off = n_bq; R->op_slot = n_ops + seg_ops; R->n_ops = 0; R->rspan = 0; R->err = 0; R->err_arg = 0;
+        R->exc_slot = (size_t)n_exc + seg_exc; R->n_exc = 0;
+        if (b->compact_bq) {
+          if (!b->modal) { /* the handle's modal quality: the most frequent one of the first record it compacts */
+            uint32_t hist[256]; memset(hist, 0, sizeof(hist));
+            for (int32_t k = 0; k < l_seq; k++) hist[qual[k]]++;
+            int mo = 1;
+            for (int v_ = 1; v_ < 255; v_++) if (hist[v_] > hist[mo]) mo = v_;
+            b->modal = mo;
+          }
+          seg_exc += (size_t)l_seq;
+        }
         b->tstart[n_reads] = pos; b->qstart[n_reads] = lead; b->qlen[n_reads] = l_seq;
         b->mapq[n_reads] = (uint8_t)mapq; b->flags[n_reads] = 0; b->qname_id[n_reads] = (uint32_t)id;
         b->seq_off[n_reads] = n_seq; b->bq_off[n_reads] = n_bq;
@@ -781,7 +884,12 @@ int hm_bam_read_batch(hm_bam* b, int rid, int32_t start, int32_t end, int thread
       if (rc) break;
       if (nsel) {
         if (!b->no_seq) GROW(b->seq, b->cap_seq, n_seq + 16, uint8_t);
-        GROW(b->bq, b->cap_bq, n_bq + 16, uint8_t);
+        if (!b->compact_bq) GROW(b->bq, b->cap_bq, n_bq + 16, uint8_t);
+        else {
+          GROW(b->qmask, b->cap_qmask, (n_bq >> 3) + 16, uint8_t);
+          GROW(b->qexc, b->cap_qexc, (size_t)n_exc + seg_exc + 32, uint8_t);
+          GROW(b->qexc_off, b->cap_qexc_off, n_reads + 2, uint64_t);
+        }
         GROW(b->ops, b->cap_ops, n_ops + seg_ops + 4, uint32_t);
         g_phase[4] += now_s() - tA; tA = now_s();
         /* phase B (parallel): bases, qualities, cs -> ops */
@@ -805,6 +913,11 @@ int hm_bam_read_batch(hm_bam* b, int rid, int32_t start, int32_t end, int thread
           if (R->op_slot != n_ops) memmove(b->ops + n_ops, b->ops + R->op_slot, (size_t)R->n_ops * sizeof(uint32_t));
           b->op_off[rd] = n_ops; b->n_ops[rd] = R->n_ops; b->tend[rd] = R->pos + R->rspan;
           n_ops += R->n_ops;
+          if (b->compact_bq) {
+            if (R->exc_slot != n_exc) memmove(b->qexc + n_exc, b->qexc + R->exc_slot, (size_t)R->n_exc);
+            b->qexc_off[rd] = n_exc;
+            n_exc += R->n_exc;
+          }
         }
       }
     }
@@ -816,14 +929,37 @@ int hm_bam_read_batch(hm_bam* b, int rid, int32_t start, int32_t end, int thread
   }
 finish:
   if (n_seq == 0 && !b->no_seq) { GROW(b->seq, b->cap_seq, 16, uint8_t); memset(b->seq, 0, 16); n_seq = 16; }
-  if (n_bq == 0) { GROW(b->bq, b->cap_bq, 16, uint8_t); memset(b->bq, 0, 16); n_bq = 16; }
+  if (n_bq == 0) {
+    if (!b->compact_bq) { GROW(b->bq, b->cap_bq, 16, uint8_t); memset(b->bq, 0, 16); }
+    else { GROW(b->qmask, b->cap_qmask, 16, uint8_t); memset(b->qmask, 0, 16); }
+    n_bq = 16;
+  }
+  if (b->compact_bq) {
+    GROW(b->qexc_off, b->cap_qexc_off, n_reads + 2, uint64_t);
+    GROW(b->qexc, b->cap_qexc, (size_t)n_exc + 32, uint8_t);
+    b->qexc_off[n_reads] = n_exc;
+    memset(b->qexc + n_exc, 0, 32); /* the expansion kernel may read a few bytes past the last exception */
+    b->n_qexc = n_exc;
+    if (!b->modal) b->modal = 93;
+  }
   out->n_reads = n_reads;
   out->tstart = b->tstart; out->tend = b->tend; out->qstart = b->qstart; out->qlen = b->qlen; out->mapq = b->mapq;
   out->flags = b->flags; out->qname_id = b->qname_id; out->seq_off = b->seq_off; out->bq_off = b->bq_off;
   out->op_off = b->op_off; out->n_ops = b->n_ops; out->seq = b->seq; out->seq_bytes = n_seq; out->bq = b->bq;
   out->bq_bytes = n_bq; out->ops = b->ops; out->n_ops_total = n_ops;
   if (b->no_seq) { out->seq = NULL; out->seq_off = NULL; out->seq_bytes = 0; } /* himut_b200.h: a batch without a base stream */
+  if (b->compact_bq) out->bq = NULL; /* the qualities are in hm_bam_last_compact; bq_off / bq_bytes describe the expanded layout */
   b->batch = *out;
+  return HM_OK;
+}
+
+int hm_bam_last_compact(hm_bam* b, hm_bq_compact* out) {
+  if (!b || !out) return HM_ERR_ARG;
+  if (!b->compact_bq || !b->qmask) return fail(b, "the last batch was not decoded with HM_BAM_OPT_COMPACT_BQ%s (%ld)", NULL, 0);
+  memset(out, 0, sizeof(*out));
+  out->mask = b->qmask; out->mask_bytes = b->batch.bq_bytes >> 3;
+  out->exc = b->qexc; out->exc_bytes = b->n_qexc; out->exc_off = b->qexc_off;
+  out->modal = (uint8_t)b->modal;
   return HM_OK;
 }
 
@@ -867,8 +1003,14 @@ int hm_bam_window_qlens(hm_bam* b, int rid, int32_t start, int32_t end, int thre
     int32_t ref_id = (int32_t)rd32(r), pos = (int32_t)rd32(r + 4);
     if (ref_id != rid) { if (ref_id > rid || ref_id < 0) break; continue; }
     if (pos >= end) break;
+    if (bs < 32) { rc = fail(b, "malformed BAM record in %s: block_size %ld", b->path, (long)bs); break; }
     uint32_t l_name = r[8], mapq = r[9], n_cig = r[12] | (r[13] << 8);
     int32_t l_seq = (int32_t)rd32(r + 16);
+    if (l_seq < 0 || l_name == 0 || 32 + (uint64_t)l_name + 4 * (uint64_t)n_cig + ((uint64_t)l_seq + 1) / 2 + (uint64_t)l_seq > (uint64_t)bs ||
+        r[32 + l_name - 1] != 0) {
+      rc = fail(b, "malformed BAM record in %s: fields run past block_size %ld", b->path, (long)bs);
+      break;
+    }
     const uint8_t* cig = r + 32 + l_name;
     int32_t ref_span = 0;
     for (uint32_t k = 0; k < n_cig; k++) {
@@ -883,13 +1025,23 @@ int hm_bam_window_qlens(hm_bam* b, int rid, int32_t start, int32_t end, int thre
     while (tag + 3 <= rec_end) {
       char ty = (char)tag[2];
       const uint8_t* v = tag + 3;
+      const size_t left = (size_t)(rec_end - v);
       size_t adv;
-      if (ty == 'Z' || ty == 'H') adv = strlen((const char*)v) + 1;
-      else if (ty == 'A' || ty == 'c' || ty == 'C') { adv = 1; if (tag[0] == 't' && tag[1] == 'p' && ty == 'A') tp_primary = (v[0] == 'P'); }
+      if (ty == 'Z' || ty == 'H') {
+        const void* z = memchr(v, 0, left);
+        if (!z) { rc = fail(b, "malformed BAM record %s: unterminated %ld tag", (const char*)(r + 32), (long)ty); break; }
+        adv = (size_t)((const uint8_t*)z - v) + 1;
+      }
+      else if (ty == 'A' || ty == 'c' || ty == 'C') { adv = 1; if (left >= 1 && tag[0] == 't' && tag[1] == 'p' && ty == 'A') tp_primary = (v[0] == 'P'); }
       else if (ty == 's' || ty == 'S') adv = 2;
       else if (ty == 'i' || ty == 'I' || ty == 'f') adv = 4;
-      else if (ty == 'B') { char sub = (char)v[0]; uint32_t cnt = rd32(v + 1); adv = 5 + (size_t)cnt * ((sub == 'c' || sub == 'C') ? 1 : (sub == 's' || sub == 'S') ? 2 : 4); }
+      else if (ty == 'B') {
+        if (left < 5) { rc = fail(b, "malformed BAM record %s: truncated B tag (%ld)", (const char*)(r + 32), (long)left); break; }
+        char sub = (char)v[0]; uint32_t cnt = rd32(v + 1);
+        adv = 5 + (size_t)cnt * ((sub == 'c' || sub == 'C') ? 1 : (sub == 's' || sub == 'S') ? 2 : 4);
+      }
       else { rc = fail(b, "unknown tag type in record %s (%ld)", (const char*)(r + 32), ty); break; }
+      if (adv > left) { rc = fail(b, "malformed BAM record %s: a tag runs past the record (%ld)", (const char*)(r + 32), (long)adv); break; }
       tag = v + adv;
     }
     if (rc) break;

@@ -42,15 +42,22 @@ def get_callable_tricounts(
     ref = np.zeros(abi.TRI_BINS, np.int64)
     log = np.zeros(abi.NORM_LOG_LEN, np.int64)
     ties = 0
-    for idx in worker.group_chunks(chunkloci_lst):
-        loci = [chunkloci_lst[i] for i in idx]
-        batch, table = src.batch(chrom, loci, None if chunk_sets is None else [chunk_sets[i] for i in idx])
-        if batch.n_reads == 0:
-            continue
-        ctx.upload(batch)
-        c, r, l, t = ctx.normcounts_chunks(refseq, table)
-        tally.add(ctx.qname_seen())
-        ccs += c; ref += r; log += l; ties += t
+    groups = worker.group_chunks(chunkloci_lst)
+    pins = worker.PinCache(ctx, enabled=len(groups) > 1)
+    try:
+        # qualities in the decoder's compact form, bases as a stream (the tile kernel reads them), decode one group ahead
+        for _idx, batch, cq, table, release in worker.pipelined_groups(src, chrom, chunkloci_lst, groups, chunk_sets, seq=True):
+            if batch.n_reads == 0:
+                release()
+                continue
+            pins.pin([cq.mask, cq.exc, batch.ops, batch.seq])
+            ctx.upload_compact(batch, cq)
+            release()
+            c, r, l, t = ctx.normcounts_chunks(refseq, table)
+            tally.add(ctx.qname_seen())
+            ccs += c; ref += r; log += l; ties += t
+    finally:
+        pins.close()
     src.close()
     log[0] = tally.count()
     ccs_d = {tri: int(ccs[i]) for i, tri in enumerate(TRI_LST)}

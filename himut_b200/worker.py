@@ -9,8 +9,9 @@ from . import abi, bamdec, lib
 _CTX = None
 _CTX_PID = None
 
-# upper bound of reference span decoded into one batch (30x -> ~1.5 GB of packed reads)
-GROUP_SPAN = int(os.environ.get("HIMUT_B200_GROUP_SPAN", 40_000_000))
+# upper bound of reference span decoded into one batch (30x, compact qualities -> ~0.12 GB per 16 Mb); a contig longer
+# than this is fed in several groups, decoded one ahead of the device (pipelined_groups)
+GROUP_SPAN = int(os.environ.get("HIMUT_B200_GROUP_SPAN", 16_000_000))
 
 
 def context():
@@ -64,16 +65,97 @@ class RegionSource:
         # (num_ccs counts distinct names per contig)
         self.reader = bamdec.NativeBam(bam_file)
 
-    def batch(self, chrom, chunkloci, phase_sets=None, seq=True):
-        """seq=False: without the 2-bit base stream (`call`, phase edges: ReadBatch.without_seq says why)"""
+    def batch(self, chrom, chunkloci, phase_sets=None, seq=True, compact=False, buffer_set=0, pad=0):
+        """seq=False: without the 2-bit base stream (`call`, phase edges: ReadBatch.without_seq says why).
+        compact=True: -> (batch, abi.BqCompact, table), the qualities as the decoder's parse pass writes them for the
+        upload (bitmap + exceptions).  pad: decode that many positions past the last chunk end (`call --phase`
+        re-fetches [tpos, tpos + 1) at a site, which reaches one position past a chunk that ends at tpos)."""
         lo = min(s for _, s, _e in chunkloci)
-        hi = max(e for _, _s, e in chunkloci)
-        batch = self.reader.read_batch(chrom, lo, hi, copy=False, seq=seq)
+        hi = max(e for _, _s, e in chunkloci) + pad
+        got = self.reader.read_batch(chrom, lo, hi, copy=False, seq=seq, compact=compact, buffer_set=buffer_set)
+        batch, cq = got if compact else (got, None)
         table = batch.chunk_table([(s, e) for _, s, e in chunkloci], phase_sets)
-        return batch, table
+        return (batch, cq, table) if compact else (batch, table)
 
     def close(self):
         self.reader.close()
+
+
+def pipelined_groups(src, chrom, chunkloci_lst, groups, chunk_sets, seq, pad=0):
+    """the groups of a contig, decoded one ahead of the consumer on a thread of their own (the decoder's C calls drop
+    the GIL): decode(k + 1) runs while group k is uploaded and called.  The decoder's two buffer sets alternate; the
+    consumer hands a set back with release() as soon as its upload has returned (hm_upload_batch* copies everything).
+    Yields (idx, batch, cq, table, release)."""
+    import queue
+    import threading
+    if len(groups) == 1:  # nothing to overlap
+        idx = groups[0]
+        b, cq, t = src.batch(chrom, [chunkloci_lst[i] for i in idx], None if chunk_sets is None else [chunk_sets[i] for i in idx],
+                             seq=seq, compact=True, pad=pad)
+        yield idx, b, cq, t, (lambda: None)
+        return
+    free, ready = queue.Queue(), queue.Queue()
+    free.put(0); free.put(1)
+    stop = threading.Event()
+
+    def work():
+        try:
+            for idx in groups:
+                s = free.get()
+                if stop.is_set():
+                    return
+                loci = [chunkloci_lst[i] for i in idx]
+                b, cq, t = src.batch(chrom, loci, None if chunk_sets is None else [chunk_sets[i] for i in idx],
+                                     seq=seq, compact=True, buffer_set=s, pad=pad)
+                ready.put((idx, b, cq, t, s))
+            ready.put(None)
+        except BaseException as ex:  # delivered to the consumer
+            ready.put(ex)
+
+    th = threading.Thread(target=work, name="himut-b200-decode", daemon=True)
+    th.start()
+    try:
+        while True:
+            item = ready.get()
+            if item is None:
+                break
+            if isinstance(item, BaseException):
+                raise item
+            idx, b, cq, t, s = item
+            yield idx, b, cq, t, (lambda s=s: free.put(s))
+    finally:
+        stop.set()
+        free.put(0)  # unblock a decoder waiting for a set
+        th.join()
+
+
+class PinCache:
+    """page-locks the decoder's big output buffers once per (address, size): they are reused from group to group, so
+    the H2D copies of every group but the first run at PCIe speed.  Off for single-group contigs (locking pages costs
+    about what one pageable copy does)."""
+
+    def __init__(self, ctx, enabled):
+        self.ctx, self.enabled, self.held = ctx, enabled, {}
+
+    def pin(self, arrays):
+        if not self.enabled:
+            return
+        for a in arrays:
+            if a is None or a.nbytes < (1 << 22):
+                continue
+            key = a.ctypes.data
+            old = self.held.get(key)
+            if old is not None and old.nbytes >= a.nbytes:
+                continue
+            if old is not None:
+                self.ctx.unpin_arrays([old])
+            self.ctx.pin_arrays([a])
+            self.held[key] = a
+
+    def close(self):
+        if self.held:
+            self.ctx.unpin_arrays(list(self.held.values()))
+            self.held = {}
 
 
 class QnameTally:

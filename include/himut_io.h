@@ -41,15 +41,29 @@ int hm_bam_ref_len(const hm_bam* b, int i);
  * order, each once (pysam fetch semantics, caller.py:299); secondary records (0x100) are
  * dropped as bamlib.BAM.__init__ drops them (bamlib.py:17), supplementary ones are kept.
  * Inputs the reference would crash on are rejected with HM_ERR_ARG and a message: no cs:Z tag,
- * missing qualities, hard clips, a read base outside A/C/G/T under a cs match or as the
- * substituted base, cs spans that disagree with the CIGAR.  `threads` = inflate threads. */
+ * missing qualities, a read base outside A/C/G/T under a cs match or as the substituted base, cs spans that
+ * disagree with the CIGAR, records whose fields run past their block_size.  Hard-clipped records are decoded as pysam
+ * presents them (SEQ holds no hard-clipped base; lead / trail count soft clips only).  `threads` = inflate threads. */
 int hm_bam_read_batch(hm_bam* b, int rid, int32_t start, int32_t end, int threads, hm_read_batch* out);
 
 /* HM_BAM_OPT_NO_SEQ = 1: batches come without the 2-bit base stream (seq = NULL, seq_off = NULL, seq_bytes = 0; see
  * hm_read_batch in himut_b200.h) — `call` and the phase edges do not need it; every check on the bases (A/C/G/T under
  * a cs match, long-form cs against SEQ) is still made.  Default 0. */
 #define HM_BAM_OPT_NO_SEQ 1
+/* HM_BAM_OPT_COMPACT_BQ = 1: the qualities of a batch come in the compact form of struct hm_bq_compact [himut_b200.h]: a bitmap
+ * of the handle's modal quality + the other qualities in read order), written by the record-parse pass itself — no
+ * one-byte-per-base stream is produced and no second pass is made; hm_read_batch.bq is NULL, bq_off / bq_bytes
+ * describe the layout the device expands to.  hm_bam_last_compact fills the struct for hm_upload_batch_compact /
+ * hm_call_batch_compact.  Default 0. */
+#define HM_BAM_OPT_COMPACT_BQ 2
+/* HM_BAM_OPT_BUFFER_SET = 0 | 1: which of the handle's two sets of output buffers the next hm_bam_read_batch fills.
+ * The arrays of a batch stay valid until the next batch decoded into the same set, so a worker can upload one batch
+ * while the next is decoded (query-name ids stay global: the name table is the handle's).  Default 0. */
+#define HM_BAM_OPT_BUFFER_SET 3
 int hm_bam_set_option(hm_bam* b, int option, int value);
+/* the compact quality stream of the last batch decoded with HM_BAM_OPT_COMPACT_BQ (pointers into the handle's
+ * buffers of the active set) */
+int hm_bam_last_compact(hm_bam* b, hm_bq_compact* out);
 
 /* BAM pre-pass of bamlib.get_thresholds (reference src/himut/bamlib.py:137-178): len(query_sequence) of
  * every record of contig `rid` that overlaps [start, end) with mapping_quality > 0 and tp:A:P, in fetch

@@ -42,7 +42,7 @@ def main():
             ctx = standin.OracleContext()
             worker.context = lambda: ctx  # inherited by the pool workers (fork)
             plain = worker.RegionSource.batch  # the oracle reads the bases: ask the decoder for them
-            worker.RegionSource.batch = lambda self, chrom, loci, phase_sets=None, seq=True: plain(self, chrom, loci, phase_sets, seq=True)
+            worker.RegionSource.batch = lambda self, chrom, loci, phase_sets=None, seq=True, **kw: plain(self, chrom, loci, phase_sets, seq=True, **kw)
     else:
         patch._scipy_compat()  # himut.__main__ imports phaselib, which needs scipy.stats.binom_test (removed in scipy 1.12)
     os.chdir(workdir)  # himut.log / norm.log are written to the working directory

@@ -36,7 +36,7 @@ def main():
         ctx = standin.OracleContext()
         worker.context = lambda: ctx
         plain = worker.RegionSource.batch
-        worker.RegionSource.batch = lambda self, chrom, loci, phase_sets=None, seq=True: plain(self, chrom, loci, phase_sets, seq=True)
+        worker.RegionSource.batch = lambda self, chrom, loci, phase_sets=None, seq=True, **kw: plain(self, chrom, loci, phase_sets, seq=True, **kw)
 
     a = dict(gtmodel.DEFAULT_CALL_ARGS)
     for k, v in over.items():

@@ -28,6 +28,30 @@ class OracleContext:
         self.batch = batch
         self.uploads += 1
 
+    def upload_compact(self, batch, cq):
+        """qualities as the decoder's parse pass leaves them (bitmap + exceptions): expanded here as k_bq_expand does on
+        the device, then the oracle sees the same one-byte-per-base stream"""
+        from himut_b200 import abi
+        bits = np.unpackbits(cq.mask, bitorder="little").astype(bool)
+        valid = np.zeros(bits.size, bool)
+        for o, n in zip(batch.bq_off.tolist(), batch.qlen.tolist()):
+            valid[o:o + n] = True
+        bq = np.where(bits & valid, np.uint8(cq.modal), np.uint8(0)).astype(np.uint8)
+        zero = ~bits & valid
+        assert int(zero.sum()) == cq.n_exc
+        bq[zero] = cq.exc[:cq.n_exc]  # exceptions are stored read by read, base by base: the stream's own order
+        # copies: like the device upload, nothing may point into the decoder's buffers once this returns (the worker
+        # hands them back to the decode thread right after)
+        kw = {name: np.array(getattr(batch, name)) for name, _ in abi.ReadBatch._FIELDS}
+        kw["bq"] = bq
+        self.upload(abi.ReadBatch(**kw))
+
+    def pin_arrays(self, arrays):
+        pass
+
+    def unpin_arrays(self, arrays):
+        pass
+
     def call_chunks(self, table):
         self._seen = np.zeros(int(self.batch.qname_id.max()) + 1 if self.batch.n_reads else 1, np.uint8)
         return oracle.call_chunks(self.params, self.batch, table, self.common, self.pon, self.phase, qseen=self._seen)

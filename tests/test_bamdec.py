@@ -99,7 +99,6 @@ def test_soft_clips_secondary_supplementary_and_contigs(tmp_path):
 
 @pytest.mark.parametrize("bad", [
     dict(cs=None),                                      # KeyError in BAM.__init__
-    dict(cigar=((5, 3), (0, 8))),                       # hard clip
     dict(seq="ACNTACGT"),                               # N under a match
     dict(cs=":2*an:5"),                                 # substitution to N
     dict(cs=":9"),                                      # cs longer than the read
@@ -217,3 +216,129 @@ def test_compact_quality_stream_is_lossless_on_the_cpu(threads):
             assert not bits[o + l:pad_end].any()      # padding bits are clear
             assert np.array_equal(seg, batch.bq[o:o + l])
         assert int(cq.exc_off[-1]) == cq.n_exc
+
+
+def test_hard_clipped_records_are_decoded_as_pysam_presents_them(tmp_path):
+    """SEQ holds no hard-clipped base; query_alignment_start counts soft clips only: the reference processes such
+    records (minimap2 writes them for supplementary alignments), native decoder and specification agree"""
+    path = str(tmp_path / "h.bam")
+    _write(path, [
+        _rec(pos=10, cigar=((5, 3), (0, 8)), qname="hard5"),
+        _rec(pos=12, cigar=((5, 4), (4, 2), (0, 5), (4, 1), (5, 7)), seq="NNACGTAN", cs=":5", qname="hard_soft"),
+    ])
+    nb = bamdec.NativeBam(path, threads=1)
+    rd = bamio.BamReader(path)
+    bb = pack.BatchBuilder()
+    got = nb.read_batch("chr1", 0, 1000)
+    _same(got, bamio.read_batch(rd, "chr1", 0, 1000, builder=bb))
+    assert got.qstart.tolist() == [0, 2] and got.qlen.tolist() == [8, 8] and got.tend.tolist() == [18, 17]
+
+
+def _expand(batch, cq):
+    """hm_bq_compact -> the one-byte-per-base stream (what k_bq_expand does on the device)"""
+    out = np.zeros(batch.bq_bytes_expanded, np.uint8)
+    bits = np.unpackbits(cq.mask, bitorder="little")
+    for r in range(batch.n_reads):
+        o, n = int(batch.bq_off[r]), int(batch.qlen[r])
+        m = bits[o:o + n].astype(bool)
+        q = np.full(n, cq.modal, np.uint8)
+        e0, e1 = int(cq.exc_off[r]), int(cq.exc_off[r + 1])
+        assert e1 - e0 == int((~m).sum())
+        q[~m] = cq.exc[e0:e1]
+        out[o:o + n] = q
+        assert not bits[o + n:o + ((n + 15) & ~15)].any()  # padding bits are clear
+    return out
+
+
+@pytest.mark.parametrize("threads", [1, 4])
+def test_compact_qualities_from_the_parse_pass(tmp_path, threads):
+    """HM_BAM_OPT_COMPACT_BQ: the decoder writes bitmap + exceptions while it parses the records; expanded, they are
+    the plain stream byte for byte; everything else in the batch is unchanged"""
+    d = synth.generate(300_000, seed=21)
+    path = str(tmp_path / "c.bam")
+    bamio.write_batch_bam(path, "chr1", 300_000, d.batch)
+    nb = bamdec.NativeBam(path, threads=threads)
+    for s, e in [(0, 300_000), (120_000, 180_000), (299_990, 300_000)]:
+        plain = nb.read_batch("chr1", s, e, seq=False)
+        batch, cq = nb.read_batch("chr1", s, e, seq=False, compact=True)
+        assert batch.bq.size == 0 and batch.bq_bytes_expanded == plain.bq.size
+        assert np.array_equal(_expand(batch, cq), plain.bq)
+        for name in ("tstart", "tend", "qstart", "qlen", "mapq", "flags", "qname_id", "bq_off", "op_off", "n_ops", "ops"):
+            assert np.array_equal(getattr(batch, name), getattr(plain, name)), name
+        assert cq.n_exc == int(cq.exc_off[-1]) and cq.mask.size * 8 == plain.bq.size
+    nb.close()
+
+
+def test_two_buffer_sets(tmp_path):
+    """a batch decoded into one buffer set stays valid while the next is decoded into the other"""
+    d = synth.generate(200_000, seed=22)
+    path = str(tmp_path / "s.bam")
+    bamio.write_batch_bam(path, "chr1", 200_000, d.batch)
+    nb = bamdec.NativeBam(path, threads=2)
+    want_a = nb.read_batch("chr1", 0, 100_000)
+    want_b = nb.read_batch("chr1", 100_000, 200_000)
+    a = nb.read_batch("chr1", 0, 100_000, copy=False, buffer_set=0)
+    b = nb.read_batch("chr1", 100_000, 200_000, copy=False, buffer_set=1)
+    assert cases.batch_digest(a) == cases.batch_digest(want_a)  # not overwritten by the second decode
+    assert cases.batch_digest(b) == cases.batch_digest(want_b)
+    a2, cq = nb.read_batch("chr1", 0, 100_000, copy=False, seq=False, compact=True, buffer_set=0)
+    assert cases.batch_digest(b) == cases.batch_digest(want_b)
+    assert np.array_equal(_expand(a2, cq), want_a.bq)
+    nb.close()
+
+
+def test_malformed_records_are_rejected_not_read_past(tmp_path):
+    """fields taken from the file are checked against block_size before they are used: a corrupt record gives a
+    BatchFormatError, never an out-of-bounds read (run under ASan by tools/sanitize_host.sh)"""
+    import gzip
+    import struct
+    import zlib
+    path = str(tmp_path / "ok.bam")
+    _write(path, [_rec(pos=10, qname="first"), _rec(pos=20, qname="second", extra=[("xb", "B", ("c", [1, 2, 3]))] if False else [])])
+    raw = bytearray(gzip.open(path, "rb").read())  # BGZF members are gzip members
+    first = raw.find(b"first\x00") - 36  # block_size field of the first record
+    assert first > 0
+    bs = struct.unpack_from("<I", raw, first)[0]
+    rng = np.random.default_rng(5)
+
+    def rewrite(mut, name):
+        out = str(tmp_path / name)
+        blocks = []
+        for i in range(0, len(mut), 60000):
+            piece = bytes(mut[i:i + 60000])
+            c = zlib.compressobj(6, zlib.DEFLATED, -15)
+            comp = c.compress(piece) + c.flush()
+            blocks.append(b"\x1f\x8b\x08\x04\x00\x00\x00\x00\x00\xff\x06\x00BC\x02\x00" + struct.pack("<H", len(comp) + 25) + comp +
+                          struct.pack("<II", zlib.crc32(piece) & 0xffffffff, len(piece)))
+        blocks.append(bytes.fromhex("1f8b08040000000000ff0600424302001b0003000000000000000000"))
+        with open(out, "wb") as f:
+            f.write(b"".join(blocks))
+        return out
+
+    cases_ = []
+    m = bytearray(raw); struct.pack_into("<i", m, first + 4 + 16, 1 << 20); cases_.append(m)       # l_seq far past the record
+    m = bytearray(raw); m[first + 4 + 8] = 255; cases_.append(m)                                    # l_name past the record
+    m = bytearray(raw); struct.pack_into("<H", m, first + 4 + 12, 60000); cases_.append(m)          # n_cigar_op past the record
+    m = bytearray(raw); struct.pack_into("<I", m, first, 16); cases_.append(m)                      # block_size below the fixed part
+    m = bytearray(raw); m[first + 4 + bs - 1] = 65; cases_.append(m)                                # last tag string unterminated
+    for k in range(40):                                                                             # random byte damage inside the record
+        m = bytearray(raw)
+        for _ in range(3):
+            m[first + 4 + int(rng.integers(0, bs))] = int(rng.integers(0, 256))
+        cases_.append(m)
+    n_bad = 0
+    for i, m in enumerate(cases_):
+        p = rewrite(m, "mut%d.bam" % i)
+        try:
+            nb = bamdec.NativeBam(p, threads=1)
+        except IOError:
+            n_bad += 1
+            continue
+        try:
+            nb.read_batch("chr1", 0, 1000)
+            nb.read_batch("chr1", 0, 1000, seq=False, compact=True)
+            nb.window_qlens("chr1", 0, 1000)
+        except pack.BatchFormatError:
+            n_bad += 1
+        nb.close()
+    assert n_bad >= 5  # the five structural mutations at least

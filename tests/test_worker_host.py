@@ -21,7 +21,7 @@ def octx(monkeypatch):
     monkeypatch.setattr(worker, "context", lambda: ctx)
     plain = worker.RegionSource.batch
     monkeypatch.setattr(worker.RegionSource, "batch",
-                        lambda self, chrom, loci, phase_sets=None, seq=True: plain(self, chrom, loci, phase_sets, seq=True))
+                        lambda self, chrom, loci, phase_sets=None, seq=True, **kw: plain(self, chrom, loci, phase_sets, seq=True, **kw))
     return ctx
 
 
