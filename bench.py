@@ -1,23 +1,26 @@
 #!/usr/bin/env python
 """bench.py — `himut call` hot-path throughput on synthetic 30x CCS data (BASELINE.json).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--contig-mb M]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--contig-mb M] [--genome-mb G]
 
-A step is one pass of the whole `himut call` device path (k_read_scan -> k_candidates -> sort ->
-k_site_range|entries|reduce -> host som_seen replay) over one contig's packed read batch.
+A step is one pass of the whole `himut call` device path (k_call_pairs -> k_site_sort -> k_call_scan -> k_site_reduce,
+one host synchronisation, host som_seen replay) over the workload's packed read batches.
 
-  value   aligned CCS bases/s with the batch already resident in HBM (hm_call_chunks),
-          CUDA events on the launching stream, barrier + synchronize on both sides, max over ranks
-  e2e     the same metric through the C-ABI call a worker makes with HOST buffers
-          (hm_call_batch: pinned host -> device copies, kernels, records back)
-  roofline  dominant kernel (k_read_scan): algorithmic bytes / its CUDA-event duration vs the
-          measured HBM copy bandwidth of MEASURED_PEAKS.json
-  cpu_baseline  the CPU oracle port (oracle/himut_oracle.c, one thread per host core, each like a reference worker on a
-          single contig) on a bounded sample of the same workload, rank 0 only
-
-N > 1 (torchrun, one rank per GPU): every rank owns one contig of the same size (different
-seed) — the genome shards by contig with no data-path collective; the 15 log counters are
-all-reduced over NCCL and record counts gathered at the end.  Weak scaling.
+N = 1 (the driver's BENCH run): BASELINE configs[1], one 64 Mb contig at 30x.
+  value   aligned CCS bases/s with the batch already resident in HBM (hm_call_chunks), CUDA events on the launching
+          stream, barrier + synchronize on both sides
+  e2e     the same metric through the C-ABI call the worker mirrors make (himut_b200/caller.py: hm_upload_batch_compact
+          + hm_call_chunks = hm_call_batch_compact) with HOST buffers exactly as the native BAM decoder leaves them
+          (the contig is written to a BAM and decoded back, outside the timed region): pinned host -> device copies,
+          quality expansion, the whole path and the records back, all inside the timed region
+  bam_to_vcf  BAM on disk (page cache) -> VCF on disk through the worker mirror itself (decode included)
+  roofline  dominant kernel (k_call_scan) against the measured HBM copy bandwidth, and the whole step (`frac_step`)
+  genome  BASELINE configs[2] scaled to --genome-mb: 24 contigs with human length ratios, chunk runs sharded by
+          himut_b200.genome.plan_runs — on one GPU here, so that the N > 1 lines have their strong-scaling base
+  cpu_baseline  the CPU oracle port on the host cores, a bounded sample of the same contig
+N > 1 (torchrun, one rank per GPU): the genome workload is the headline, STRONG scaling: the same genome for every N,
+  chunk runs of long contigs on different GPUs, no data-path collective (the 15 log counters are all-reduced over
+  NCCL); value = the genome's aligned bases x steps / the slowest rank's time; `imbalance` = max / mean bases per rank.
 """
 import argparse
 import json
@@ -32,6 +35,10 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 import numpy as np  # noqa: E402
+
+METRIC = "aligned CCS bases/sec (himut call, 30x synthetic)"
+# chr1 .. chr22, X, Y in Mb (GRCh38, rounded): the length ratios of BASELINE configs[2]'s 3.1 Gb genome
+HUMAN_MB = [248, 242, 198, 190, 181, 171, 159, 145, 138, 133, 135, 133, 114, 107, 102, 90, 83, 80, 58, 64, 46, 50, 156, 57]
 
 
 def chunkloci(end):
@@ -51,14 +58,16 @@ def make_workload(contig_len, seed):
     return d, params, chunks
 
 
-def kernel_alg_bytes(batch):
-    """algorithmic bytes of one k_read_scan launch: every quality byte once,
-    every op word once, per-read metadata once; outputs: two u32 prefix words + one mismatch
-    position per op at most, 29 B of per-read results"""
-    n_base = int(batch.qlen.astype(np.int64).sum())
-    n_op = int(batch.ops.size)
-    n_read = int(batch.n_reads)
-    return 1.0 * n_base + 4.0 * n_op + 33.0 * n_read + 12.0 * n_op + 29.0 * n_read, n_base, n_op, n_read
+def batch_counts(batch):
+    return int(batch.qlen.astype(np.int64).sum()), int(batch.ops.size), int(batch.n_reads)
+
+
+def scan_alg_bytes(batch):
+    """algorithmic bytes of one k_call_scan launch: every quality byte once, every op word once (the
+    prefix scan is redone in registers), 40 B of per-read metadata; the entries it writes (4 B per (site, covering
+    read)) are left out, so the figure is a lower bound of what the kernel must move"""
+    n_base, n_op, n_read = batch_counts(batch)
+    return 1.0 * n_base + 4.0 * n_op + 40.0 * n_read
 
 
 class ClockSampler:
@@ -130,11 +139,11 @@ def measured_peak():
 
 
 def ncu_traffic(alg_bytes):
-    """DRAM bytes per k_read_scan launch: dram/algorithmic ratio of the committed ncu capture
-    (profiles/traffic.json, taken on a 16 Mb contig) applied to this launch's algorithmic bytes"""
+    """DRAM bytes per k_call_scan launch: the dram / algorithmic ratio of the committed `ncu --set full` capture
+    (profiles/traffic.json, 64 Mb contig) applied to this launch's algorithmic bytes — not measured in this run"""
     p = os.path.join(ROOT, "profiles", "traffic.json")
     try:
-        return float(json.load(open(p))["k_read_scan_dram_over_alg"]) * alg_bytes
+        return float(json.load(open(p))["k_call_scan_dram_over_alg"]) * alg_bytes
     except Exception:
         return None
 
@@ -146,11 +155,11 @@ def host_threads():
         return max(1, os.cpu_count() or 1)
 
 
+# ------------------------------------------------------------------------------------------------ CPU arm
 def cpu_baseline(d, params, chunks, n_chunks, threads=1):
     """oracle port on `threads` host threads, each over its own run of n_chunks consecutive chunks of the contig
-    (the reference's own parallelism is one worker per contig, `caller.py:593-618`: a thread here stands for
-    one such worker; ctypes drops the GIL for the duration of the C call)
-    -> (bases/s, bases, seconds, threads used)"""
+    (the reference's own parallelism is one worker per contig, caller.py:766-810: a thread here stands for one such
+    worker; ctypes drops the GIL for the duration of the C call) -> (bases/s, bases, seconds, threads used)"""
     from concurrent.futures import ThreadPoolExecutor
     from oracle import oracle
     b = d.batch
@@ -161,7 +170,6 @@ def cpu_baseline(d, params, chunks, n_chunks, threads=1):
     per_read = np.add.reduceat(qspan, b.op_off.astype(np.int64))
     bases = 0
     for sub in groups:
-        # distinct reads fetched by the group's chunks = reads [lo, hi) that overlap [start0, endN)
         lo, hi = int(sub["read_lo"].min()), int(sub["read_hi"].max())
         ov = (b.tstart[lo:hi] < int(sub["end"][-1])) & (b.tend[lo:hi] > int(sub["start"][0]))
         bases += int(per_read[lo:hi][ov].sum())
@@ -176,52 +184,254 @@ def cpu_baseline(d, params, chunks, n_chunks, threads=1):
     return bases / dt, bases, dt, threads
 
 
-def bam_to_records(ctx, params, contig_mb, seed):
-    """what a worker does per contig, from a BAM file in the page cache: native decode (threaded BGZF inflate +
-    record parse + cs -> ops, csrc/bamdec.c) -> pinned-less host batch -> hm_call_batch.  Host bound by design."""
-    import shutil
-    from himut_b200 import bamdec, synth
-    n = contig_mb * 1_000_000
-    d = synth.generate(n, seed=seed + 1, copy=False)
-    tmp = tempfile.mkdtemp(prefix="himut_b200_bench_")
-    try:
-        path = os.path.join(tmp, "synth.bam")
-        t0 = time.perf_counter()
-        bamdec.write_batch_bam(path, "chr1", n, d.batch)
-        t_write = time.perf_counter() - t0
-        threads = bamdec.default_threads()
-        bam = bamdec.NativeBam(path, threads=threads)
-        chunks = None
-        best, best_dec = None, None
-        for _ in range(3):
-            t0 = time.perf_counter()
-            batch = bam.read_batch("chr1", 0, n, copy=False, seq=False)  # as the worker mirror does (caller.py):
-            t1 = time.perf_counter()                                    # `call` needs no base stream
-            if chunks is None:
-                chunks = batch.chunk_table(chunkloci(n))
-            rec, log = ctx.call_batch(batch, chunks, view=True)
-            t2 = time.perf_counter()
-            if best is None or t2 - t0 < best:
-                best, best_dec = t2 - t0, t1 - t0
-        bam.close()
-        out = {"value": d.aligned_bases / best, "unit": "bases/s", "contig_mb": contig_mb, "decode_threads": threads,
-               "seconds": best, "decode_seconds": best_dec, "bam_bytes": os.path.getsize(path), "bam_write_seconds": t_write,
-               "site_records": int(rec.size),
-               "note": "BAM (page cache) -> records: bounded by host BGZF inflate + record parse, not by the GPU"}
-        try:
-            out["to_vcf"] = bam_to_vcf(path, n, d.aligned_bases, tmp)
-        except Exception as ex:  # a sub-measurement: never costs the line
-            out["to_vcf"] = {"error": repr(ex)}
-        return out
-    finally:
-        shutil.rmtree(tmp, ignore_errors=True)
+PY_REF_NOTE = ("the reference itself is pure Python and its I/O dependencies (pysam, natsort, pytabix) are not on this box: the arm times "
+               "oracle/himut_oracle.c, a C restatement pinned to the reference's outputs (tests/golden); the unmodified Python "
+               "reference ran at 5.0e5 (`call`) and 1.5e5 (`normcounts`) aligned bases/s on one core of the build container "
+               "(tests/golden/*_config0_1mb.json: reference_seconds), i.e. the C port is ~300x faster per core than what it stands for")
 
 
-def bam_to_vcf(bam_path, contig_len, aligned_bases, tmp):
-    """SURVEY 8(d) timing (ii): BAM on disk -> VCF on disk through the worker mirror itself
-    (himut_b200.caller.get_somatic_substitutions: native decode, upload, device path, 12-tuples, natsort) and the
-    mirror of the reference's writer (vcfio.dump_sbs).  Its own hm_ctx, like a worker process."""
-    from himut_b200 import caller, gtmodel, vcfio
+def run_reference(args, rank, world):
+    """--impl reference: the CPU implementation of the path, one thread per host core, on a bounded sample of the
+    N = 1 workload.  Nothing of the product is loaded: only the oracle library and the data generator."""
+    if rank != 0:
+        return
+    contig_len = args.contig_mb * 1_000_000
+    d, params, chunks = make_workload(contig_len, args.seed)
+    threads = host_threads()
+    n = max(1, min(len(chunks) // threads, args.cpu_chunks))
+    for _ in range(args.warmup):
+        cpu_baseline(d, params, chunks, n, threads)
+    tot, el = 0, 0.0
+    for _ in range(args.steps):
+        v, bases, dt, used = cpu_baseline(d, params, chunks, n, threads)
+        tot += bases
+        el += dt
+    value = tot / el
+    sample = "%d threads x %d consecutive chunks = %d of %d chunks (%.1f Mb, %d aligned bases) of the %d Mb 30x contig per step" % (
+        used, n, used * n, len(chunks), used * n * 0.2, bases, args.contig_mb)
+    loaded = [ln.split()[-1] for ln in open("/proc/self/maps") if "libhimut" in ln and ln.rstrip().endswith(".so")]
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "bases/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * el / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/f64", "data": "synthetic",
+        "config": workload_config(args, 1),
+        "cpu_baseline": {"value": value, "unit": "bases/s", "cores": used, "kind": "port", "sample": sample, "note": PY_REF_NOTE},
+        "e2e": {"value": value, "unit": "bases/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "native_libraries_mapped": sorted(set(os.path.basename(p) for p in loaded)),
+    }))
+
+
+def workload_config(args, world):
+    if world == 1:
+        return {"workload": "himut call on a %d Mb synthetic contig at 30x CCS (15 kb reads, cs tags), %d x 200 kb chunks"
+                            % (args.contig_mb, len(chunkloci(args.contig_mb * 1_000_000))),
+                "baseline_config": "configs[1]" if args.contig_mb == 64 else "custom",
+                "contig_mb": args.contig_mb, "depth": 30, "parallelism": "one GPU",
+                "l2": "inputs (>= 2 GB per step) are larger than the 126 MB L2; no explicit flush"}
+    return {"workload": "himut call on a %d Mb synthetic genome at 30x CCS: 24 contigs with the length ratios of GRCh38 (BASELINE "
+                        "configs[2] at 1/%.0f scale: the 3.1 Gb genome is 116 GB of packed reads and cannot be generated inside the "
+                        "bench's time budget), 200 kb chunks, chunk runs sharded over %d GPUs by himut_b200.genome.plan_runs"
+                        % (args.genome_mb, 3100.0 / args.genome_mb, world),
+            "baseline_config": "configs[2] (scaled)", "genome_mb": args.genome_mb, "depth": 30,
+            "parallelism": "chunk runs, contiguous equal-weight partition x%d" % world,
+            "l2": "every rank's inputs are larger than the 126 MB L2; no explicit flush"}
+
+
+# ------------------------------------------------------------------------------------------------ helpers
+def slice_batch(batch, lo, hi):
+    """reads [lo, hi) of a batch as a batch of their own (array views, offsets rebased); without a base stream"""
+    from himut_b200 import abi
+    if hi <= lo:
+        lo = hi = 0
+    b0 = int(batch.bq_off[lo]) if hi > lo else 0
+    b1 = (int(batch.bq_off[hi - 1]) + ((int(batch.qlen[hi - 1]) + 15) & ~15)) if hi > lo else 16
+    o0 = int(batch.op_off[lo]) if hi > lo else 0
+    o1 = (int(batch.op_off[hi - 1]) + int(batch.n_ops[hi - 1])) if hi > lo else 0
+    skip = ("seq", "bq", "ops", "seq_off", "bq_off", "op_off")
+    kw = {name: getattr(batch, name)[lo:hi] for name, _ in abi.ReadBatch._FIELDS if name not in skip}
+    kw["bq_off"] = batch.bq_off[lo:hi] - np.uint64(b0)
+    kw["op_off"] = batch.op_off[lo:hi] - np.uint64(o0)
+    kw["bq"], kw["ops"] = batch.bq[b0:b1], batch.ops[o0:o1]
+    kw["seq"], kw["seq_off"] = np.zeros(0, np.uint8), np.zeros(0, np.uint64)
+    return abi.ReadBatch(keepalive=batch, **kw)
+
+
+def aligned_per_read(batch):
+    kind, val = batch.ops & 3, (batch.ops >> 2).astype(np.int64)
+    qspan = np.where(kind == 0, val, 0) + (kind == 1) + np.where(kind == 2, val, 0)
+    return np.add.reduceat(qspan, batch.op_off.astype(np.int64)) if batch.n_reads else np.zeros(0, np.int64)
+
+
+class Timer:
+    """CUDA events on the launching stream, barrier + synchronize on both sides"""
+
+    def __init__(self, torch, dist, world, stream):
+        self.torch, self.dist, self.world, self.stream = torch, dist, world, stream
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def run(self, fn, steps, after=None):
+        self.barrier()
+        e0, e1 = self.torch.cuda.Event(enable_timing=True), self.torch.cuda.Event(enable_timing=True)
+        e0.record(self.stream)
+        for _ in range(steps):
+            fn()
+        if after:
+            after()
+        e1.record(self.stream)
+        self.barrier()
+        return e0.elapsed_time(e1)
+
+
+def kernel_breakdown(ctx, fn, reps=3):
+    """per-kernel CUDA-event times and the launch count of a call, measured outside the timed loops"""
+    ctx.kernel_timing(True)
+    acc, launches = {}, 0
+    for _ in range(reps):
+        fn()
+        for name, ms in ctx.last_kernel_times():
+            acc.setdefault(name, []).append(ms)
+        launches = ctx.last_timing()[1]
+    ctx.kernel_timing(False)
+    return {k: float(np.mean(v)) for k, v in acc.items()}, launches
+
+
+# ------------------------------------------------------------------------------------------------ N = 1: configs[1]
+def leg_contig(args, T, ctx, d, params, chunks, tmpdir):
+    """the 64 Mb contig on one GPU: resident, end to end from the decoder's buffers, kernel breakdown"""
+    from himut_b200 import bamdec
+    batch = d.batch
+    aligned = d.aligned_bases
+    ctx.set_params(params)
+    ctx.set_site_sets()
+    ctx.omit_restatements(True)  # germline restatements are counted on the device and not copied back (caller.py:338-345)
+    ctx.kernel_timing(False)
+    # ---- resident ----
+    ctx.upload(batch.without_seq())
+    state = {}
+
+    def step():
+        state["rec"], state["log"] = ctx.call_chunks(chunks, view=True, wait=False)
+
+    for _ in range(args.warmup):
+        step()
+    ms_total = T.run(step, args.steps, after=ctx.records_wait)
+    rec, log = state["rec"].copy(), state["log"]
+    assert ctx.last_call_path() == 2, "the fused device path did not run"
+    k_ms, launches = kernel_breakdown(ctx, step)
+    ctx.records_wait()
+    # ---- end to end: the worker's call on the decoder's own buffers ----
+    bam = os.path.join(tmpdir, "contig.bam")
+    t0 = time.perf_counter()
+    bamdec.write_batch_bam(bam, "chr1", len(d.ref), batch)
+    t_write = time.perf_counter() - t0
+    nb = bamdec.NativeBam(bam)
+    t0 = time.perf_counter()
+    dbatch, cq = nb.read_batch("chr1", 0, len(d.ref), copy=False, seq=False, compact=True)
+    t_decode = time.perf_counter() - t0
+    dchunks = dbatch.chunk_table(chunkloci(len(d.ref)))
+    small = [getattr(dbatch, n) for n, _ in dbatch._FIELDS if n not in ("seq", "bq", "ops", "seq_off")]
+    pinned = [cq.mask, cq.exc, cq.exc_off, dbatch.ops] + small
+    ctx.pin_arrays(pinned)
+
+    def step_e2e():
+        state["rec_e"], state["log_e"] = ctx.call_batch_compact(dbatch, cq, dchunks, view=True)
+
+    for _ in range(2):
+        step_e2e()
+    ms_e2e = T.run(step_e2e, args.steps)
+    assert list(state["log_e"]) == list(log), "the decoded batch gives other counters than the generated one"
+    srt = lambda a: np.sort(a, order=["chunk", "tpos", "ref", "alt"]).tobytes()  # records come back in no particular order
+    assert srt(state["rec_e"]) == srt(rec), "end-to-end records differ from the resident call's"
+    h2d = int(cq.nbytes() + dbatch.ops.nbytes + sum(a.nbytes for a in small) + dchunks.nbytes)
+    # the same call with one quality byte per base and the 2-bit bases (what round 1's workers uploaded)
+    ctx.pin(batch)
+
+    def step_plain():
+        ctx.call_batch(batch, chunks, view=True)
+
+    step_plain()
+    n_plain = max(2, args.steps // 3)
+    ms_plain = T.run(step_plain, n_plain) / n_plain
+    ctx.unpin(batch)
+    ctx.unpin_arrays(pinned)
+    nb.close()
+    n_base, n_op, n_read = batch_counts(batch)
+    alg = scan_alg_bytes(batch)
+    peak, peak_src = measured_peak()
+    scan_ms = k_ms.get("k_call_scan", float("nan"))
+    dev_ms = float(sum(k_ms.values()))
+    step_ms = ms_total / args.steps
+    survey_bytes = 1.25 * n_base + 4.0 * n_op + 40.0 * n_read + 48.0 * rec.size
+    out = {
+        "value": aligned * args.steps / (ms_total * 1e-3), "ms_per_step": step_ms,
+        "e2e": {"value": aligned * args.steps / (ms_e2e * 1e-3), "unit": "bases/s", "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": int(rec.nbytes + 256), "ms_per_step": ms_e2e / args.steps,
+                "call": "hm_call_batch_compact = hm_upload_batch_compact + hm_call_chunks, what himut_b200/caller.py:call_region does per "
+                        "decode group; host buffers exactly as csrc/bamdec.c leaves them (no base stream, qualities as modal bitmap + "
+                        "exceptions written by its record-parse pass), page-locked once before the loop; records byte-identical to the "
+                        "resident call's",
+                "decode_seconds_outside_timed_region": t_decode, "bam_write_seconds": t_write},
+        "e2e_plain": {"value": aligned / (ms_plain * 1e-3), "unit": "bases/s", "h2d_bytes_per_step": int(batch.nbytes() + chunks.nbytes),
+                      "ms_per_step": ms_plain, "call": "hm_call_batch: one quality byte per base + 2-bit bases (round 1's upload)"},
+        "gpu_launches": int(launches * args.steps),
+        "gpu_launches_per_step": int(launches),
+        "library_launches_per_step": 0,
+        "roofline": {"bound": "hbm", "kernel": "k_call_scan", "achieved": alg / (scan_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                     "frac": alg / (scan_ms * 1e-3) / 1e9 / peak, "frac_of_nominal_8000_gbs": alg / (scan_ms * 1e-3) / 1e9 / 8000.0,
+                     "traffic": ncu_traffic(alg),
+                     "traffic_source": "profiles/traffic.json (ncu --set full, 64 Mb contig): ratio applied, not measured in this run",
+                     "peak_source": peak_src, "alg_bytes_per_launch": alg, "kernel_ms": scan_ms,
+                     "share_of_step_device_time": scan_ms / dev_ms if dev_ms else None,
+                     # the whole step: SURVEY 8(d)'s bytes over the driver-comparable wall time of a step, and over its kernels alone
+                     "frac_step": survey_bytes / (step_ms * 1e-3) / 1e9 / peak,
+                     "frac_step_kernels_only": survey_bytes / (dev_ms * 1e-3) / 1e9 / peak if dev_ms else None,
+                     "step_bytes_formula": "SURVEY 8(d): 1.25*N_base + 4*N_op + 40*N_read + 48*N_cand (the 0.25 B per base of the 2-bit "
+                                           "stream is counted although `call` does not read it)",
+                     "step_bytes": survey_bytes},
+        "kernel_ms_per_step": k_ms, "kernel_ms_note": "CUDA events per kernel group, taken in 3 extra steps outside the timed loop",
+        "aligned_bases_per_step": int(aligned), "site_records_per_step": int(rec.size),
+        "records": "every record the reference emits (PASS + filtered sites) reaches host memory each step; germline restatements are "
+                   "counted in the log on the device (HM_OPT_OMIT_RESTATEMENTS)",
+        "log_counters": [int(v) for v in log],
+    }
+    return out, bam
+
+
+def leg_normcounts(args, T, ctx, d, chunks):
+    batch = d.batch
+    ctx.upload(batch)
+    ctx.normcounts_chunks(d.ref, chunks)
+    state = {}
+
+    def step():
+        state["r"] = ctx.normcounts_chunks(d.ref, chunks)
+
+    n_norm = max(2, args.steps // 3)
+    ms = T.run(step, n_norm) / n_norm
+    ccs_tri, ref_tri, nlog, nties = state["r"]
+    ctx.kernel_timing(True)
+    step()
+    nk = {k: v for k, v in ctx.last_kernel_times()}
+    ctx.kernel_timing(False)
+    n_base, n_op, n_read = batch_counts(batch)
+    peak, _ = measured_peak()
+    nbytes = 1.25 * n_base + 4.0 * n_op + 40.0 * n_read + 1.0 * len(d.ref)
+    return {"value": d.aligned_bases / (ms * 1e-3), "unit": "bases/s", "ms_per_step": ms, "steps": n_norm, "kernel_ms_per_step": nk,
+            "frac_step": nbytes / (ms * 1e-3) / 1e9 / peak,
+            "callable_bases": int(nlog[13]), "callable_positions": int(ref_tri.sum()), "alt_ties_flagged": int(nties),
+            "positions_evaluated_exactly": ctx.last_norm_exact_sites(), "positions": int(len(d.ref)),
+            "bound": "instruction issue (integer pass over every aligned base) + the exact fp64 pass over the listed positions, see DESIGN.md"}
+
+
+def leg_bam_to_vcf(bam_path, contig_len, aligned_bases, tmp):
+    """SURVEY 8(d) timing (ii): BAM on disk (page cache) -> VCF on disk through the worker mirror itself
+    (himut_b200.caller.get_somatic_substitutions: native decode one group ahead, compact upload, device path, 12-tuples,
+    natsort) and the mirror of the reference's writer (vcfio.dump_sbs).  Its own hm_ctx, like a worker process."""
+    from himut_b200 import bamdec, caller, gtmodel, vcfio, worker
     a = gtmodel.DEFAULT_CALL_ARGS
     loci = [("chr1", s, e) for s, e in chunkloci(contig_len)]
     header = "##fileformat=VCFv4.2\n#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\tsynth"
@@ -241,50 +451,129 @@ def bam_to_vcf(bam_path, contig_len, aligned_bases, tmp):
         if best is None or t2 - t0 < best[0]:
             best = (t2 - t0, t1 - t0, t2 - t1)
     return {"value": aligned_bases / best[0], "unit": "bases/s", "seconds": best[0], "worker_seconds": best[1],
-            "writer_seconds": best[2], "rows": len(lst["chr1"]), "vcf_bytes": os.path.getsize(vcf),
-            "log": [int(v) for v in log["chr1"]],
-            "note": "non_human_sample = True (no common-SNP / PoN files), otherwise the defaults of the resident workload"}
+            "writer_seconds": best[2], "rows": len(lst["chr1"]), "vcf_bytes": os.path.getsize(vcf), "contig_mb": contig_len // 1_000_000,
+            "decode_threads": bamdec.default_threads(), "decode_group_mb": worker.GROUP_SPAN // 1_000_000,
+            "bam_bytes": os.path.getsize(bam_path), "log": [int(v) for v in log["chr1"]],
+            "note": "host bound: BGZF inflate + record parse on the host cores take most of it (decode of group k + 1 overlaps upload "
+                    "and kernels of group k); non_human_sample = True (no common-SNP / PoN files)"}
 
 
-def run_reference(args, rank, world):
-    """--impl reference: the CPU implementation of the path (the oracle port: the reference is
-    pure Python and is not on this box), one thread per host core, on a bounded sample of the workload."""
-    if rank != 0:
-        return
-    contig_len = args.contig_mb * 1_000_000
-    d, params, chunks = make_workload(contig_len, args.seed)
-    threads = host_threads()
-    n = max(1, min(len(chunks) // threads, args.cpu_chunks))
+# ------------------------------------------------------------------------------------------------ configs[2] (scaled)
+def genome_contigs(genome_mb):
+    scale = genome_mb / float(sum(HUMAN_MB))
+    names = ["chr%d" % (i + 1) for i in range(22)] + ["chrX", "chrY"]
+    return [(n, max(400_000, int(round(mb * scale * 5)) * 200_000)) for n, mb in zip(names, HUMAN_MB)]
+
+
+def leg_genome(args, T, lib, torch, rank, world, local_rank, stream):
+    """chunk runs of the scaled genome on this rank: resident and end-to-end timing, the 15 counters summed over ranks"""
+    from concurrent.futures import ThreadPoolExecutor
+    from himut_b200 import bamdec, genome, gtmodel, synth
+    contigs = genome_contigs(args.genome_mb)
+    loci = {c: genome.chunkloci(c, n) for c, n in contigs}
+    runs = genome.plan_runs(loci, world)
+    mine = [r for r in runs if r.rank == rank]
+    order = [c for c, _ in contigs]
+    need = sorted({r.chrom for r in mine}, key=order.index)
+    length = dict(contigs)
+    seed_of = {c: args.seed + 1009 * i for i, (c, _) in enumerate(contigs)}
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(max(1, min(len(need), host_threads()))) as ex:
+        data = dict(zip(need, ex.map(lambda c: synth.generate(length[c], seed=seed_of[c], copy=False), need)))
+    t_gen = time.perf_counter() - t0
+    params = gtmodel.make_params(**gtmodel.DEFAULT_CALL_ARGS)
+    items, my_bases = [], 0
+    for r in mine:
+        d = data[r.chrom]
+        chunks_r = [(s, e) for _c, s, e in loci[r.chrom][r.lo:r.hi]]
+        table_full = d.batch.chunk_table(chunks_r)
+        lo, hi = int(table_full["read_lo"].min()), int(table_full["read_hi"].max())
+        sub = slice_batch(d.batch, lo, hi)
+        table = sub.chunk_table(chunks_r)
+        cq = bamdec.compact_bq(sub)
+        # aligned bases of the reads that START in the run: every read of the genome is counted once over all ranks
+        a0 = -1 if r.lo == 0 else chunks_r[0][0]
+        a1 = (1 << 31) - 1 if r.hi == len(loci[r.chrom]) else chunks_r[-1][1]
+        per = aligned_per_read(sub)
+        my_bases += int(per[(sub.tstart >= a0) & (sub.tstart < a1)].sum())
+        ctx = lib.Context(local_rank)
+        ctx.set_stream(stream.cuda_stream)
+        ctx.set_params(params)
+        ctx.set_site_sets()
+        ctx.omit_restatements(True)
+        ctx.kernel_timing(False)
+        small = [getattr(sub, n) for n, _ in sub._FIELDS if n not in ("seq", "bq", "ops", "seq_off")]
+        pinned = [cq.mask, cq.exc, cq.exc_off, sub.ops] + small
+        ctx.pin_arrays(pinned)
+        ctx.upload_compact(sub, cq)
+        items.append(dict(ctx=ctx, sub=sub, cq=cq, table=table, pinned=pinned, small=small, run=r))
+    state = {"log": np.zeros(15, np.int64), "recs": 0}
+
+    def step():
+        log, recs = np.zeros(15, np.int64), 0
+        for it in items:
+            rec, l = it["ctx"].call_chunks(it["table"], view=True, wait=False)
+            log += l
+            recs += rec.size
+        state["log"], state["recs"] = log, recs
+
+    def wait_all():
+        for it in items:
+            it["ctx"].records_wait()
+
     for _ in range(args.warmup):
-        cpu_baseline(d, params, chunks, n, threads)
-    tot, el = 0, 0.0
-    for _ in range(args.steps):
-        v, bases, dt, used = cpu_baseline(d, params, chunks, n, threads)  # dt: the oracle calls only
-        tot += bases
-        el += dt
-    value = tot / el
-    sample = "%d threads x %d consecutive chunks = %d of %d chunks (%.1f Mb, %d aligned bases) of the %d Mb 30x contig per step" % (
-        used, n, used * n, len(chunks), used * n * 0.2, bases, args.contig_mb)
-    print(json.dumps({
-        "impl": "reference", "metric": "aligned CCS bases/sec (himut call, 30x synthetic)", "value": value, "unit": "bases/s",
-        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * el / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/f64", "data": "synthetic",
-        "config": workload_config(args, world),
-        "cpu_baseline": {"value": value, "unit": "bases/s", "cores": used, "kind": "port", "sample": sample,
-                         "note": "C restatement of the pure-Python reference (oracle/himut_oracle.c); the reference itself ran "
-                                 "at 3e5-6e5 bases/s/core in the build container (tests/golden/*.json reference_seconds)"},
-        "e2e": {"value": value, "unit": "bases/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }))
+        step()
+    wait_all()
+    ms_res = T.run(step, args.steps, after=wait_all)
+
+    def step_e2e():
+        for it in items:
+            it["ctx"].call_batch_compact(it["sub"], it["cq"], it["table"], view=True)
+
+    step_e2e()
+    ms_e2e = T.run(step_e2e, args.steps)
+    h2d = sum(int(it["cq"].nbytes() + it["sub"].ops.nbytes + sum(a.nbytes for a in it["small"]) + it["table"].nbytes) for it in items)
+    d2h = int(state["recs"]) * 76 + 256 * len(items)
+    for it in items:
+        it["ctx"].kernel_timing(True)
+    step()
+    wait_all()
+    launches = sum(it["ctx"].last_timing()[1] for it in items)
+    for it in items:
+        assert it["ctx"].last_call_path() == 2
+        it["ctx"].unpin_arrays(it["pinned"])
+        it["ctx"].close()
+    dev = torch.device("cuda", local_rank)
+    t = torch.tensor([ms_res, ms_e2e], device=dev, dtype=torch.float64)
+    s = torch.tensor([float(my_bases), float(state["recs"]), float(h2d), float(d2h), float(launches), float(len(items))], device=dev,
+                     dtype=torch.float64)
+    mx = torch.tensor([float(my_bases)], device=dev, dtype=torch.float64)
+    logt = torch.tensor(state["log"], device=dev)
+    if world > 1:
+        T.dist.all_reduce(t, op=T.dist.ReduceOp.MAX)
+        T.dist.all_reduce(s, op=T.dist.ReduceOp.SUM)
+        T.dist.all_reduce(mx, op=T.dist.ReduceOp.MAX)
+        T.dist.all_reduce(logt, op=T.dist.ReduceOp.SUM)  # the only cross-GPU step of the path: 15 counters
+    bases = float(s[0])
+    return {
+        "value": bases * args.steps / (float(t[0]) * 1e-3), "ms_per_step": float(t[0]) / args.steps,
+        "e2e": {"value": bases * args.steps / (float(t[1]) * 1e-3), "unit": "bases/s", "ms_per_step": float(t[1]) / args.steps,
+                "h2d_bytes_per_step": int(s[2]), "d2h_bytes_per_step": int(s[3]),
+                "call": "hm_call_batch_compact per chunk run, host buffers in the decoder's layout (no base stream, qualities as modal "
+                        "bitmap + exceptions — here built by hm_bq_compact_build from the generated batch, the same bytes the decoder's "
+                        "parse pass writes: tests/test_bamdec.py), page-locked before the loop"},
+        "aligned_bases_per_step": int(bases), "site_records_per_step": int(s[1]), "runs": len(runs), "runs_this_rank": len(items),
+        "split_contigs": sum(1 for c in loci if sum(1 for r in runs if r.chrom == c) > 1),
+        "imbalance": {"max_over_mean_bases_per_rank": float(mx[0]) / (bases / world) if bases else None,
+                      "planned_max_over_mean_weight": genome.imbalance(runs, world)},
+        "gpu_launches_per_step": int(s[4]), "contexts": int(s[5]), "generate_seconds_this_rank": t_gen,
+        "log_counters_sum": [int(v) for v in logt.tolist()],
+        "log_note": "summed over runs: a candidate on the one position two runs of a split contig share is counted by both (the "
+                    "product path, himut_b200/genome.py, replays som_seen over it at the merge; tests/test_zz_gpu_genome.py)",
+    }
 
 
-def workload_config(args, world):
-    return {"workload": "himut call on a %d Mb synthetic contig at 30x CCS (15 kb reads, cs tags), %d x 200 kb chunks%s"
-                        % (args.contig_mb, len(chunkloci(args.contig_mb * 1_000_000)), " per GPU" if world > 1 else ""),
-            "baseline_config": "configs[1]" if args.contig_mb == 64 else "custom",
-            "contig_mb": args.contig_mb, "depth": 30, "parallelism": "contig-sharded x%d" % world,
-            "l2": "inputs (>= 2 GB per step) are larger than the 126 MB L2; no explicit flush"}
-
-
+# ------------------------------------------------------------------------------------------------ main
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -292,12 +581,13 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--contig-mb", type=int, default=64)
+    ap.add_argument("--genome-mb", type=int, default=388, help="size of the scaled configs[2] genome (3.1 Gb / 8)")
     ap.add_argument("--seed", type=int, default=20260101)
     ap.add_argument("--cpu-chunks", type=int, default=25)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-normcounts", action="store_true")
     ap.add_argument("--no-bam-leg", action="store_true")
-    ap.add_argument("--bam-mb", type=int, default=8)
+    ap.add_argument("--no-genome", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -306,10 +596,10 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
 
     import __graft_entry__ as g
-    g.build()
-
     if args.impl == "reference":
+        g.build(load=False)  # the CPU arm: nothing of the product is loaded
         return run_reference(args, rank, world)
+    g.build()
 
     import torch
     import torch.distributed as dist
@@ -324,222 +614,70 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # stdout carries the one JSON line only
         dist.init_process_group("nccl", device_id=dev)
-
-    contig_len = args.contig_mb * 1_000_000
-    d, params, chunks = make_workload(contig_len, args.seed + 7919 * rank)
-    batch = d.batch
-    ctx = lib.Context(local_rank)
     stream = torch.cuda.current_stream()
-    ctx.set_stream(stream.cuda_stream)
-    ctx.set_params(params)
-    ctx.set_site_sets()
-    # records of candidates that merely restate the germline genotype are counted on the device and not copied back:
-    # the reference drops them too (caller.py:338-345)
-    ctx.omit_restatements(True)
-    ctx.pin(batch)
-    aligned = d.aligned_bases
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    # ---------------- resident (HBM) timing ----------------
-    # resident as the worker mirror leaves it (caller.py): no base stream — `call` takes the bases of match runs from
-    # the site's reference allele; the end-to-end legs below check those records byte for byte against a batch with bases
-    ctx.upload(batch.without_seq())
-    for _ in range(args.warmup):
-        rec, log = ctx.call_chunks(chunks, view=True)
+    T = Timer(torch, dist, world, stream)
     sampler = ClockSampler(local_rank)
-    barrier()
-    if rank == 0:  # one sampler for the job: eight concurrent NVML pollers slow every rank's driver calls down
-        sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    k_ms = {}
-    e0.record(stream)
-    for _ in range(args.steps):
-        # the record copy of a step (20 MB, device -> pinned host) overlaps the next step's kernels
-        rec, log = ctx.call_chunks(chunks, view=True, wait=False)
-        for name, ms in ctx.last_kernel_times():
-            k_ms.setdefault(name, []).append(ms)
-    ctx.records_wait()  # every step's records are in host memory before the clock stops
-    e1.record(stream)
-    barrier()
-    ms_total = e0.elapsed_time(e1)
-
-    # ---------------- end to end (host buffers through the C ABI) ----------------
-    # e2e: hm_call_batch_compact — the batch in pinned host memory with its quality stream as modal-value bitmap +
-    # exceptions (lossless, built once when the batch is produced, expanded on the device inside the timed region);
-    # e2e_plain: hm_call_batch with one quality byte per base.
-    from himut_b200 import bamdec
-    cq = bamdec.compact_bq(batch)
-    small = [getattr(batch, n) for n, _ in batch._FIELDS if n not in ("seq", "bq", "ops")]
-    ctx.pin_arrays([cq.mask, cq.exc, cq.exc_off] + small)
-    for _ in range(2):
-        ctx.call_batch(batch, chunks, view=True)
-        ctx.call_batch_compact(batch, cq, chunks, view=True)
-    barrier()
-    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    f0.record(stream)
-    for _ in range(args.steps):
-        rec_e, log_e = ctx.call_batch_compact(batch, cq, chunks, view=True)
-    f1.record(stream)
-    barrier()
-    ms_e2e = f0.elapsed_time(f1)
-    assert list(log_e) == list(log)
-    # the same call for a batch without its base stream (hm_read_batch.seq = NULL): the bases of match runs are the
-    # site's reference allele by the meaning of a cs match, so a worker need not ship them.  Counted as the
-    # end-to-end figure only if its records are byte for byte those of the call with bases.
-    ms_e2e_ns, noseq_note = float("inf"), None
+    tmpdir = tempfile.mkdtemp(prefix="himut_b200_bench_")
+    out = None
     try:
-        rec_with = rec_e.copy()
-        batch_ns = batch.without_seq()
-        for _ in range(2):
-            ctx.call_batch_compact(batch_ns, cq, chunks, view=True)
-        barrier()
-        n0, n1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        n0.record(stream)
-        for _ in range(args.steps):
-            rec_n, log_n = ctx.call_batch_compact(batch_ns, cq, chunks, view=True)
-        n1.record(stream)
-        barrier()
-        srt = lambda a: np.sort(a, order=["chunk", "tpos", "ref", "alt"]).tobytes()  # records come back in no particular order
-        if list(log_n) == list(log) and srt(rec_n) == srt(rec_with):
-            ms_e2e_ns = n0.elapsed_time(n1)
+        if world == 1:
+            contig_len = args.contig_mb * 1_000_000
+            d, params, chunks = make_workload(contig_len, args.seed)
+            ctx = lib.Context(local_rank)
+            ctx.set_stream(stream.cuda_stream)
+            sampler.start()
+            res, bam = leg_contig(args, T, ctx, d, params, chunks, tmpdir)
+            clocks = sampler.stop()  # sampled over the resident and the end-to-end loops of the headline
+            out = {"metric": METRIC, "value": res.pop("value"), "unit": "bases/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+                   "ms_per_step": res.pop("ms_per_step"), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                   "dtype": "u8/f64", "data": "synthetic", "config": workload_config(args, 1), "clocks": clocks}
+            out.update(res)
+            if not args.no_normcounts:
+                out["normcounts"] = leg_normcounts(args, T, ctx, d, chunks)
+            ctx.close()
+            if not args.no_bam_leg:
+                try:
+                    out["bam_to_vcf"] = leg_bam_to_vcf(bam, contig_len, d.aligned_bases, tmpdir)
+                except Exception as ex:  # a side measurement: never costs the line
+                    out["bam_to_vcf"] = {"error": repr(ex)}
+            if not args.no_cpu_baseline:
+                threads = host_threads()
+                n = max(1, min(len(chunks) // threads, args.cpu_chunks))
+                v1, bases1, dt1, _ = cpu_baseline(d, params, chunks, n, 1)
+                v, bases, dt, used = cpu_baseline(d, params, chunks, n, threads)
+                out["cpu_baseline"] = {"value": v, "unit": "bases/s", "cores": used, "kind": "port",
+                                       "sample": "%d threads x %d consecutive chunks of %d (%d aligned bases, %.1f s) of the same contig"
+                                                 % (used, n, len(chunks), bases, dt),
+                                       "one_core": {"value": v1, "bases": bases1, "seconds": dt1}, "note": PY_REF_NOTE}
+            del d
+            if not args.no_genome:
+                try:
+                    out["genome"] = leg_genome(args, T, lib, torch, rank, world, local_rank, stream)
+                    out["genome"]["workload"] = workload_config(args, 2)["workload"].replace("sharded over 2 GPUs", "planned for N GPUs (here: all on this one)")
+                    out["genome"]["note"] = ("strong-scaling base of the N > 1 lines (whose headline is this workload): efficiency(N) = "
+                                             "value(N) / (N x this value)")
+                except Exception as ex:
+                    out["genome"] = {"error": repr(ex)}
         else:
-            noseq_note = "records differ from the call with bases: not counted"
-        del rec_with
-    except Exception as ex:  # keep the line: the leg with bases stands
-        noseq_note = "failed: %r" % (ex,)
-    h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    h0.record(stream)
-    for _ in range(args.steps):
-        rec_p, log_p = ctx.call_batch(batch, chunks, view=True)
-    h1.record(stream)
-    barrier()
-    ms_e2e_plain = h0.elapsed_time(h1)
-    assert list(log_p) == list(log)
-    clocks = sampler.stop()  # sampled from the first timed resident step to the last end-to-end step
-    h2d_compact = int(batch.nbytes() - batch.bq.nbytes + cq.nbytes() + chunks.nbytes)
-
-    # ---------------- callable-base half of `himut normcounts` on the same resident batch ----------------
-    norm = None
-    if not args.no_normcounts:
-        ctx.upload(batch)
-        ctx.normcounts_chunks(d.ref, chunks)
-        barrier()
-        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        n_norm = max(2, args.steps // 3)
-        nk = {}
-        g0.record(stream)
-        for _ in range(n_norm):
-            ccs_tri, ref_tri, nlog, nties = ctx.normcounts_chunks(d.ref, chunks)
-            for name, ms in ctx.last_kernel_times():
-                nk.setdefault(name, []).append(ms)
-        g1.record(stream)
-        barrier()
-        ms_norm = g0.elapsed_time(g1) / n_norm
-        norm = {"value": aligned / (ms_norm * 1e-3), "unit": "bases/s", "ms_per_step": ms_norm, "steps": n_norm,
-                "kernel_ms_per_step": {k: float(np.mean(v)) for k, v in nk.items()},
-                "callable_bases": int(nlog[13]), "callable_positions": int(ref_tri.sum()), "alt_ties_flagged": int(nties),
-                "positions_evaluated_exactly": ctx.last_norm_exact_sites(), "positions": int(contig_len),
-                "bound": "instruction issue (integer pass over every aligned base) + the exact fp64 pass over the listed positions, see DESIGN.md"}
-
-    # ---------------- BAM on disk -> site records (decode included), rank 0, a separate 8 Mb contig ----------------
-    bam_leg = None
-    if rank == 0 and not args.no_bam_leg:
-        try:
-            bam_leg = bam_to_records(ctx, params, args.bam_mb, args.seed)
-        except Exception as ex:  # a side measurement: never costs the line
-            bam_leg = {"error": repr(ex)}
-
-    # ---------------- reduce over ranks ----------------
-    t = torch.tensor([ms_total, ms_e2e, ms_e2e_plain, ms_e2e_ns], device=dev, dtype=torch.float64)
-    tot = torch.tensor([float(aligned), float(rec.size)], device=dev, dtype=torch.float64)
-    logt = torch.tensor(np.asarray(log, np.int64), device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
-        dist.all_reduce(logt, op=dist.ReduceOp.SUM)  # the only cross-GPU step of the path: 15 counters
-    ms_total, ms_e2e, ms_e2e_plain, ms_e2e_ns = float(t[0]), float(t[1]), float(t[2]), float(t[3])
-    all_bases, all_recs = float(tot[0]), int(tot[1])
-
-    if rank == 0:
-        value = all_bases * args.steps / (ms_total * 1e-3)
-        e2e = all_bases * args.steps / (ms_e2e * 1e-3)
-        e2e_with = {"value": e2e, "unit": "bases/s", "h2d_bytes_per_step": h2d_compact,
-                    "d2h_bytes_per_step": int(rec.nbytes + 32), "ms_per_step": ms_e2e / args.steps,
-                    "call": "hm_call_batch_compact (quality stream as modal bitmap + exceptions, expanded on the device)"}
-        if np.isfinite(ms_e2e_ns):
-            e2e_best = {"value": all_bases * args.steps / (ms_e2e_ns * 1e-3), "unit": "bases/s",
-                        "h2d_bytes_per_step": int(h2d_compact - batch.seq.nbytes - batch.seq_off.nbytes),
-                        "d2h_bytes_per_step": int(rec.nbytes + 32), "ms_per_step": ms_e2e_ns / args.steps,
-                        "call": "hm_call_batch_compact, batch without a base stream (seq = NULL: match runs carry the reference's "
-                                "bases by the meaning of cs; substituted bases are in the ops) and the quality stream as modal "
-                                "bitmap + exceptions; records byte-identical to the call with bases"}
-        else:
-            e2e_best = dict(e2e_with, note_without_bases=noseq_note or "not counted on some rank")
-        alg, n_base, n_op, n_read = kernel_alg_bytes(batch)
-        scan_name = "k_call_scan" if "k_call_scan" in k_ms else "k_read_scan"
-        scan_ms = float(np.mean(k_ms[scan_name]))
-        peak, peak_src = measured_peak()
-        achieved = alg / (scan_ms * 1e-3) / 1e9
-        step_ms = {k: float(np.mean(v)) for k, v in k_ms.items()}
-        dev_ms = sum(step_ms.values())
-        # whole-step figure with SURVEY.md §8(d)'s formula (1.25 B per shipped base + ops + reads + records)
-        survey_bytes = 1.25 * n_base + 4.0 * n_op + 40.0 * n_read + 48.0 * rec.size
-        out = {
-            "metric": "aligned CCS bases/sec (himut call, 30x synthetic)", "value": value, "unit": "bases/s",
-            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/f64", "data": "synthetic",
-            "config": workload_config(args, world),
-            "clocks": clocks,
-            "e2e": e2e_best,
-            "e2e_with_bases": e2e_with,
-            "e2e_plain": {"value": all_bases * args.steps / (ms_e2e_plain * 1e-3), "unit": "bases/s",
-                          "h2d_bytes_per_step": int(batch.nbytes() + chunks.nbytes), "d2h_bytes_per_step": int(rec.nbytes + 32),
-                          "ms_per_step": ms_e2e_plain / args.steps, "call": "hm_call_batch (one quality byte per base)"},
-            # own kernels per resident step: k_read_scan, k_candidates, k_expand_keys, k_site_range, k_chunk_key_ranges,
-            # k_site_entries_by_read, k_site_reduce, k_keep_flags, k_compact_records, k_gather_u32, k_count_flags,
-            # 3 x k_publish, 3 x k_publish_items (the cub sort / unique / scan launches are library code, not counted)
-            "gpu_launches": int(args.steps * 17),
-            "dominant_kernel": max(step_ms, key=step_ms.get),
-            "library_launches_per_step": "cub::DeviceRadixSort (candidate keys)",
-            "roofline": {"bound": "hbm", "kernel": scan_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "frac_of_nominal_8000_gbs": achieved / 8000.0,  # north_star's ~8 TB/s
-                         "traffic": ncu_traffic(alg), "peak_source": peak_src,
-                         "alg_bytes_per_launch": alg, "kernel_ms": scan_ms,
-                         "share_of_step_device_time": scan_ms / dev_ms if dev_ms else None},
-            "roofline_step": {"formula": "SURVEY 8(d): 1.25*N_base + 4*N_op + 40*N_read + 48*N_cand", "bytes": survey_bytes,
-                              "note": "the formula's 0.25 B per base is the 2-bit base stream, which this resident batch does not carry: "
-                                      "by bytes actually needed the fraction is lower by 1.0/1.25 on that term",
-                              "device_ms": dev_ms, "achieved_gbs": survey_bytes / (dev_ms * 1e-3) / 1e9,
-                              "frac_of_peak": survey_bytes / (dev_ms * 1e-3) / 1e9 / peak},
-            "kernel_ms_per_step": step_ms,
-            "aligned_bases_per_step": int(all_bases), "site_records_per_step": all_recs,
-            "records": "every record the reference emits (PASS + filtered sites) reaches host memory each step; germline "
-                       "restatements are counted in the log on the device (HM_OPT_OMIT_RESTATEMENTS)",
-            "log_counters_sum": [int(v) for v in logt.tolist()],
-        }
-        if norm is not None:
-            out["normcounts"] = norm
-        if bam_leg is not None:
-            out["bam_to_records"] = bam_leg
-        if not args.no_cpu_baseline and world == 1:  # the CPU arm beside the one-GPU line only
-            threads = host_threads()
-            n = max(1, min(len(chunks) // threads, args.cpu_chunks))
-            v1, bases1, dt1, _ = cpu_baseline(d, params, chunks, n, 1)
-            v, bases, dt, used = cpu_baseline(d, params, chunks, n, threads)
-            out["cpu_baseline"] = {"value": v, "unit": "bases/s", "cores": used, "kind": "port",
-                                   "sample": "%d threads x %d consecutive chunks of %d (%d aligned bases, %.1f s) of the same contig"
-                                             % (used, n, len(chunks), bases, dt),
-                                   "one_core": {"value": v1, "bases": bases1, "seconds": dt1}}
-        print(json.dumps(out))
-    ctx.unpin(batch)
-    ctx.unpin_arrays([cq.mask, cq.exc, cq.exc_off] + small)
-    ctx.close()
-    if world > 1:
-        dist.destroy_process_group()
+            if rank == 0:
+                sampler.start()  # one sampler for the job: eight concurrent NVML pollers slow every rank's driver calls down
+            res = leg_genome(args, T, lib, torch, rank, world, local_rank, stream)
+            clocks = sampler.stop() if rank == 0 else None
+            if rank == 0:
+                out = {"metric": METRIC, "value": res.pop("value"), "unit": "bases/s", "n_gpus": world, "steps": args.steps,
+                       "warmup": args.warmup, "ms_per_step": res.pop("ms_per_step"), "higher_is_better": True, "scaling": "strong",
+                       "vs_baseline": None, "dtype": "u8/f64", "data": "synthetic", "config": workload_config(args, world), "clocks": clocks,
+                       "gpu_launches": int(res["gpu_launches_per_step"] * args.steps)}
+                out.update(res)
+                out["scaling_note"] = ("strong scaling: the same %d Mb genome for every N > 1; its one-GPU base is the `genome` object of "
+                                       "the N = 1 line (whose headline is BASELINE configs[1], a different workload)" % args.genome_mb)
+        if rank == 0 and out is not None:
+            print(json.dumps(out))
+    finally:
+        import shutil
+        shutil.rmtree(tmpdir, ignore_errors=True)
+        if world > 1:
+            dist.destroy_process_group()
 
 
 if __name__ == "__main__":

@@ -16,7 +16,7 @@ from . import abi, pack
 
 _LIB = None
 EXPORTS = ["hm_bam_open", "hm_bam_close", "hm_bam_error", "hm_bam_header_text", "hm_bam_n_refs", "hm_bam_ref_name",
-           "hm_bam_ref_len", "hm_bam_read_batch", "hm_bam_set_option", "hm_bam_last_compact", "hm_bam_n_qnames", "hm_bam_qname", "hm_bam_window_qlens", "hm_bam_write_batch", "hm_bq_compact_build",
+           "hm_bam_ref_len", "hm_bam_read_batch", "hm_bam_set_option", "hm_bam_last_compact", "hm_bam_qnames_blob", "hm_bam_n_qnames", "hm_bam_qname", "hm_bam_window_qlens", "hm_bam_write_batch", "hm_bq_compact_build",
            "hm_bq_compact_free"]
 
 
@@ -51,6 +51,7 @@ def load():
         lib.hm_bq_compact_build.argtypes = [C.POINTER(abi.hm_read_batch), C.c_int, vp, vp, C.POINTER(vp), C.POINTER(C.c_uint64), C.POINTER(C.c_uint8)]
         lib.hm_bq_compact_free.argtypes = [vp]
         lib.hm_bq_compact_free.restype = None
+        lib.hm_bam_qnames_blob.argtypes = [vp, vp, C.c_size_t, vp, C.c_size_t, C.POINTER(C.c_size_t)]
         lib.hm_bam_n_qnames.argtypes = [vp]
         lib.hm_bam_n_qnames.restype = C.c_uint32
         lib.hm_bam_qname.argtypes = [vp, C.c_uint32]
@@ -175,6 +176,17 @@ class NativeBam:
     def qname(self, i):
         v = self.lib.hm_bam_qname(self.h, i)
         return None if v is None else v.decode()
+
+    def qnames_blob(self, flags):
+        """b"name\\n..." of the ids whose flag is set (flags: uint8 per qname id, as Context.qname_seen / QnameTally keep them)"""
+        flags = np.ascontiguousarray(flags, np.uint8)
+        need = C.c_size_t(0)
+        self.lib.hm_bam_qnames_blob(self.h, flags.ctypes.data_as(C.c_void_p), flags.size, None, 0, C.byref(need))
+        buf = C.create_string_buffer(max(int(need.value), 1))
+        rc = self.lib.hm_bam_qnames_blob(self.h, flags.ctypes.data_as(C.c_void_p), flags.size, buf, int(need.value), C.byref(need))
+        if rc != 0 and need.value:
+            raise RuntimeError("hm_bam_qnames_blob failed: %d" % rc)
+        return buf.raw[: int(need.value)]
 
     def close(self):
         if self.h:

@@ -27,14 +27,11 @@ def _log_from_records(rec, num_ccs):
     return log
 
 
-def get_somatic_substitutions(
-    chrom, bam_file, common_snps, panel_of_normals, chunkloci_lst, phase_set2hbit_lst, phase_set2hpos_lst,
-    phase_set2hetsnp_lst, min_qv, min_mapq, qlen_lower_limit, qlen_upper_limit, min_sequence_identity, min_gq,
-    min_bq, min_trim, max_mismatch_count, mismatch_window_size, md_threshold, min_ref_count, min_alt_count,
-    min_hap_count, somatic_snv_prior, germline_snv_prior, germline_indel_prior, phase, non_human_sample,
-    create_panel_of_normals, chrom2tsbs_lst, chrom2tsbs_log,
-):
-    ctx = worker.context()
+def configure(ctx, chrom, common_snps, panel_of_normals, chunkloci_lst, phase_set2hbit_lst, phase_set2hpos_lst, phase_set2hetsnp_lst,
+              min_qv, min_mapq, qlen_lower_limit, qlen_upper_limit, min_sequence_identity, min_gq, min_bq, min_trim,
+              max_mismatch_count, mismatch_window_size, md_threshold, min_ref_count, min_alt_count, min_hap_count,
+              germline_snv_prior, phase, non_human_sample, create_panel_of_normals):
+    """worker arguments -> context state (parameters, site sets, phase table); returns the phase-set index per chunk"""
     params = gtmodel.make_params(
         min_qv=min_qv, min_mapq=min_mapq, qlen_lower_limit=qlen_lower_limit, qlen_upper_limit=qlen_upper_limit,
         min_sequence_identity=min_sequence_identity, min_gq=min_gq, min_bq=min_bq, min_trim=min_trim,
@@ -52,10 +49,33 @@ def get_somatic_substitutions(
     if phase:
         table, chunk_sets = vcfio.phase_tables(chunkloci_lst, phase_set2hbit_lst, phase_set2hpos_lst, phase_set2hetsnp_lst)
         ctx.set_phase_sets(table)
+    return chunk_sets
 
+
+def carry_som_seen(parts, later_starts):
+    """som_seen across consecutive pieces of one contig's chunk list (groups of a worker, runs of a sharded job), as it
+    carries across chunks (caller.py:243,347; bamlib.py:77): a candidate whose position an earlier piece claimed is
+    dropped, a piece claims the positions of its records that are not germline restatements.
+    parts: record arrays in chunk order; later_starts[i]: the smallest chunk start after piece i (None: nothing
+    follows) — only positions at or past it can matter later.  Returns the filtered arrays."""
+    som_seen, out = set(), []
+    for rec, later in zip(parts, later_starts):
+        if som_seen and rec.size:
+            rec = rec[~np.isin(rec["tpos"], np.fromiter(som_seen, np.int32, len(som_seen)))]
+        if later is not None and rec.size:
+            claim = rec[(~np.isin(rec["status"], _RESTATES)) & (rec["tpos"] >= later)]
+            som_seen.update(int(t) for t in claim["tpos"])
+        out.append(rec)
+    return out
+
+
+def call_region(ctx, bam_file, chrom, chunkloci_lst, chunk_sets, phase, want_names=False):
+    """the device path over a contig's chunk list (or a run of it): decode one group ahead, upload, call.
+    -> (records incl. germline restatements, number of distinct query names that passed the read gates,
+        names blob (want_names) or None)"""
     src = worker.RegionSource(bam_file)
     tally = worker.QnameTally()
-    kept, som_seen = [], set()
+    kept, laters = [], []
     starts = [s for _, s, _e in chunkloci_lst]
     groups = worker.group_chunks(chunkloci_lst)
     pins = worker.PinCache(ctx, enabled=len(groups) > 1)
@@ -77,18 +97,30 @@ def get_somatic_substitutions(
             release()  # everything is on the device: the decoder may reuse the buffers
             rec, _log = ctx.call_chunks(table)
             tally.add(ctx.qname_seen())
-            # som_seen carries across groups exactly as across chunks (caller.py:243,347; bamlib.py:77)
-            if som_seen and rec.size:
-                rec = rec[~np.isin(rec["tpos"], np.fromiter(som_seen, np.int32, len(som_seen)))]
-            later = min(starts[idx[-1] + 1:], default=None)
-            if later is not None and rec.size:
-                claim = rec[(~np.isin(rec["status"], _RESTATES)) & (rec["tpos"] >= later)]
-                som_seen.update(int(t) for t in claim["tpos"])
             kept.append(rec)
+            laters.append(min(starts[idx[-1] + 1:], default=None))
+        names = src.reader.qnames_blob(tally.seen) if want_names else None
     finally:
         pins.close()
-    src.close()
+        src.close()
+    kept = carry_som_seen(kept, laters)
     rec = np.concatenate(kept) if kept else np.zeros(0, abi.SITE_DTYPE)
+    return rec, tally.count(), names
+
+
+def get_somatic_substitutions(
+    chrom, bam_file, common_snps, panel_of_normals, chunkloci_lst, phase_set2hbit_lst, phase_set2hpos_lst,
+    phase_set2hetsnp_lst, min_qv, min_mapq, qlen_lower_limit, qlen_upper_limit, min_sequence_identity, min_gq,
+    min_bq, min_trim, max_mismatch_count, mismatch_window_size, md_threshold, min_ref_count, min_alt_count,
+    min_hap_count, somatic_snv_prior, germline_snv_prior, germline_indel_prior, phase, non_human_sample,
+    create_panel_of_normals, chrom2tsbs_lst, chrom2tsbs_log,
+):
+    ctx = worker.context()
+    chunk_sets = configure(ctx, chrom, common_snps, panel_of_normals, chunkloci_lst, phase_set2hbit_lst, phase_set2hpos_lst,
+                           phase_set2hetsnp_lst, min_qv, min_mapq, qlen_lower_limit, qlen_upper_limit, min_sequence_identity,
+                           min_gq, min_bq, min_trim, max_mismatch_count, mismatch_window_size, md_threshold, min_ref_count,
+                           min_alt_count, min_hap_count, germline_snv_prior, phase, non_human_sample, create_panel_of_normals)
+    rec, num_ccs, _ = call_region(ctx, bam_file, chrom, chunkloci_lst, chunk_sets, phase)
     chrom2tsbs_lst[chrom] = records.records_to_tsbs_lst(chrom, rec)
-    chrom2tsbs_log[chrom] = [int(v) for v in _log_from_records(rec, tally.count())]
+    chrom2tsbs_log[chrom] = [int(v) for v in _log_from_records(rec, num_ccs)]
     return int((rec["flags"] & abi.SITE_PL_TIE).astype(bool).sum())

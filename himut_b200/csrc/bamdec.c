@@ -513,6 +513,21 @@ const char* hm_bam_ref_name(const hm_bam* b, int i) { return (i >= 0 && i < b->n
 int hm_bam_ref_len(const hm_bam* b, int i) { return (i >= 0 && i < b->n_ref) ? b->refs[i].len : -1; }
 uint32_t hm_bam_n_qnames(const hm_bam* b) { return b->qt.n; }
 const char* hm_bam_qname(const hm_bam* b, uint32_t id) { return id < b->qt.n ? b->qt.names[id] : NULL; }
+/* the names whose flag is set, each followed by '\n', in id order: what a worker that owns only a run of a contig's
+ * chunks hands to the merge, which counts distinct names per contig (m.num_ccs, caller.py:318-320) across runs */
+int hm_bam_qnames_blob(const hm_bam* b, const uint8_t* flags, size_t n_flags, char* out, size_t cap, size_t* need) {
+  if (!b || !need || (n_flags && !flags)) return HM_ERR_ARG;
+  size_t n = 0;
+  const size_t lim = n_flags < b->qt.n ? n_flags : b->qt.n;
+  for (size_t i = 0; i < lim; i++) {
+    if (!flags[i]) continue;
+    const size_t l = strlen(b->qt.names[i]);
+    if (out && n + l + 1 <= cap) { memcpy(out + n, b->qt.names[i], l); out[n + l] = '\n'; }
+    n += l + 1;
+  }
+  *need = n;
+  return (out && n <= cap) ? HM_OK : HM_ERR_CAPACITY;
+}
 
 /* ------------------------------------------------------------------ decode */
 #define GROW(ptr, cap, need, type)                                    \

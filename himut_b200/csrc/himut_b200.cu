@@ -110,6 +110,8 @@ struct hm_ctx {
   std::vector<uint64_t> h_ops_prefix;       // ops of the reads before read r (candidate slots a chunk can need)
   bool dup_names = false;                   // two primary records of the resident batch share a query name
   int call_path = 0;                        // hm_last_call_path
+  bool ktiming = true;                      // HM_OPT_KERNEL_TIMING: CUDA events around the kernels of a call
+  bool own_launch_count = false;            // last_launches was counted launch by launch (fused path)
   uint64_t site_cap_hint = 0;               // high-water mark of distinct sites per call
   char* h_geom_pin = nullptr;
   size_t h_geom_cap = 0;
@@ -142,15 +144,16 @@ cudaEvent_t next_event(hm_ctx* ctx) {
   return ctx->ev_pool[ctx->ev_used++];
 }
 void t_begin(hm_ctx* ctx, const char* name) {
+  if (!ctx->ktiming) return;
   KTime k{name, next_event(ctx), next_event(ctx), 0.f};
   cudaEventRecord(k.a, ctx->stream);
   ctx->ktimes.push_back(k);
 }
-void t_end(hm_ctx* ctx) { cudaEventRecord(ctx->ktimes.back().b, ctx->stream); }
+void t_end(hm_ctx* ctx) { if (ctx->ktiming) cudaEventRecord(ctx->ktimes.back().b, ctx->stream); }
 void t_reset(hm_ctx* ctx) { ctx->ktimes.clear(); ctx->ev_used = 0; }
 void t_collect(hm_ctx* ctx) {
   ctx->last_total_ms = 0.f;
-  ctx->last_launches = (int)ctx->ktimes.size();
+  if (!ctx->own_launch_count) ctx->last_launches = (int)ctx->ktimes.size();
   for (auto& k : ctx->ktimes) cudaEventElapsedTime(&k.ms, k.a, k.b);
   if (!ctx->ktimes.empty()) cudaEventElapsedTime(&ctx->last_total_ms, ctx->ktimes.front().a, ctx->ktimes.back().b);
 }
@@ -543,6 +546,7 @@ int hm_call_chunks_async(hm_ctx* ctx, const hm_chunk* chunks, size_t n_chunks, h
 int hm_set_option(hm_ctx* ctx, int option, int value) {
   if (!ctx) return HM_ERR_ARG;
   if (option == HM_OPT_OMIT_RESTATEMENTS) { ctx->omit_restatements = value != 0; return HM_OK; }
+  if (option == HM_OPT_KERNEL_TIMING) { ctx->ktiming = value != 0; return HM_OK; }
   return fail(ctx, HM_ERR_ARG, "unknown option %d", option);
 }
 
@@ -758,6 +762,7 @@ static int call_chunks_impl(hm_ctx* ctx, const hm_chunk* chunks, size_t n_chunks
   uint64_t total_cap = 0, n_tiles = 0;
   const bool fused = fused_eligible(ctx, chunks, n_chunks, n_pairs, &total_cap, &n_tiles);
   ctx->call_path = fused ? 2 : 1;
+  ctx->own_launch_count = false;
   if (!fused) {
     if ((rc = upload(ctx, ctx->b_chunks, chunks, n_chunks))) return rc;
     if ((rc = upload(ctx, ctx->b_pair_off, pair_off.data(), pair_off.size()))) return rc;
@@ -800,6 +805,7 @@ static int call_chunks_impl(hm_ctx* ctx, const hm_chunk* chunks, size_t n_chunks
     if (const char* e = getenv("HIMUT_B200_SITE_CAP")) site_cap = (uint64_t)std::max(1ll, atoll(e)); // tests: force the overflow retry
     site_cap = std::min<uint64_t>(site_cap, std::max<uint64_t>(total_cap, 1));
     size_t bcap = HM_BOUNDARY_CAP;
+    int n_launched = 0;
     for (int attempt = 0;; attempt++) {
       t_reset(ctx);
       FusedGeom G;
@@ -808,6 +814,9 @@ static int call_chunks_impl(hm_ctx* ctx, const hm_chunk* chunks, size_t n_chunks
                                                  ctx->b_bpos.as<uint32_t>(), ctx->b_brecs.as<uint32_t>(), (uint32_t)std::min<size_t>(HM_BOUNDARY_FIRST, bcap),
                                                  d_cnt + 4, reinterpret_cast<uint32_t*>(ctx->h_cnt_pin), h_bidx, h_bpos, reinterpret_cast<uint32_t*>(h_brecs));
       CU(cudaGetLastError());
+      // own kernels launched by this attempt: k_call_pairs, k_site_sort, k_tile_scan, k_site_range2, k_call_scan, k_site_valid,
+      // k_site_reduce, k_publish_call (+ k_bq_expand when the batch came compact, counted by the upload)
+      n_launched += 6 + (n_tiles ? 1 : 0) + (n_chunks ? 1 : 0);
       lap(4);
       CU(cudaStreamSynchronize(ctx->stream)); // the one synchronisation of the call
       lap(5);
@@ -821,6 +830,8 @@ static int call_chunks_impl(hm_ctx* ctx, const hm_chunk* chunks, size_t n_chunks
       memset(h_cnt, 0, sizeof(h_cnt));
     }
     HM_BOUNDARY_CAP = bcap;
+    ctx->own_launch_count = true;
+    ctx->last_launches = n_launched;
     h_cnt[2] = 0;
     for (int k = 24; k < 32; k++) h_cnt[2] += h_cnt[k]; // num_ccs: distinct query names, counted in eight slots
     ctx->site_cap_hint = std::max<uint64_t>(ctx->site_cap_hint, h_cnt[1] + h_cnt[1] / 4);

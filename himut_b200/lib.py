@@ -226,6 +226,10 @@ class Context:
         """records of germline restatements (never emitted by the reference) stay on the device; counters unchanged"""
         self._chk(self.lib.hm_set_option(self.h, 1, 1 if on else 0))
 
+    def kernel_timing(self, on=True):
+        """CUDA events around the kernels of a call (last_kernel_times); off saves a dozen driver calls per call"""
+        self._chk(self.lib.hm_set_option(self.h, 2, 1 if on else 0))
+
     def records_wait(self):
         self._chk(self.lib.hm_records_wait(self.h))
 

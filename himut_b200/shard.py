@@ -1,7 +1,7 @@
-"""Contig sharding across ranks and the final reduction.
+"""Sharding across ranks and the final reduction; used by genome.py (chunk runs -> ranks) and bench.py.
 
-The path has no data-path collective: a contig (with all its chunks, so the som_seen carry never
-crosses a rank) is owned by exactly one rank.  What crosses ranks at the end is tiny: the 15 / 14
+The path has no data-path collective: a run of consecutive chunks of a contig is owned by exactly one rank (the
+som_seen carry inside it is the worker's; between runs it is replayed at the merge, genome.py).  What crosses ranks at the end is tiny: the 15 / 14
 log counters and 2 x 33 trinucleotide bins (all-reduce, sum) and the site records (gathered on
 rank 0 for the reference's natsort + writers).  Backend agnostic: NCCL on GPUs, gloo in tests.
 """
@@ -33,6 +33,17 @@ def all_reduce_sum(vec, device=None):
         return np.asarray(vec, np.int64)
     t = torch.as_tensor(np.asarray(vec, np.int64), device=device)
     dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return t.cpu().numpy()
+
+
+def all_reduce_max(vec, device=None):
+    """element-wise maximum of an int64 vector over ranks (identity without a process group)"""
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()):
+        return np.asarray(vec, np.int64)
+    t = torch.as_tensor(np.asarray(vec, np.int64), device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
     return t.cpu().numpy()
 
 

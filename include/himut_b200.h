@@ -282,6 +282,9 @@ int hm_records_wait(hm_ctx* ctx);
  * candidate that merely restates the germline genotype, which the reference counts and drops (caller.py:338-345) —
  * are not copied to the host; they still count in log[2..4].  A third of the record bytes at 30x.                */
 #define HM_OPT_OMIT_RESTATEMENTS 1
+/* HM_OPT_KERNEL_TIMING (default 1): CUDA events around the kernels of a call, read back by hm_last_timing /
+ * hm_last_kernel_times.  0 saves the event records (a dozen driver calls per call); the figures are then not updated. */
+#define HM_OPT_KERNEL_TIMING 2
 int hm_set_option(hm_ctx* ctx, int option, int value);
 
 /* after hm_call_chunks / hm_call_batch returned HM_ERR_CAPACITY: copy the records of that call
@@ -350,7 +353,8 @@ int hm_read_stats(hm_ctx* ctx, int64_t* bq_total, int32_t* n_match, int32_t* n_s
                   int32_t* ins_len, int32_t* del_len, int32_t* n_mismatch);
 
 /* timing of the last hm_call_chunks / hm_normcounts_chunks on the context's stream (CUDA
- * events): total device milliseconds and the launch count.  names/ms give per-kernel
+ * events): total device milliseconds and the number of own kernels the call launched (fused `call` path: counted
+ * launch by launch; elsewhere: the number of timed kernel groups).  names/ms give per-kernel
  * figures for up to `cap` kernels; returns how many were written in *n.                    */
 int hm_last_timing(hm_ctx* ctx, float* total_ms, int* n_launches);
 /* which device path the last hm_call_chunks took: 2 the fused one (one pass over the quality stream, no library

@@ -87,6 +87,10 @@ void hm_bq_compact_free(uint8_t* exc);
  * across hm_bam_read_batch calls (m.num_ccs counts distinct names per contig, caller.py:318-320) */
 uint32_t hm_bam_n_qnames(const hm_bam* b);
 const char* hm_bam_qname(const hm_bam* b, uint32_t id);
+/* the names of the ids whose flag byte is set (flags as hm_qname_seen returns them), each followed by '\n', in id order;
+ * HM_ERR_CAPACITY with *need = bytes wanted when `out` is NULL or too small.  For workers that own a run of a contig's
+ * chunks: the merge counts distinct names per contig across runs (genome.py) */
+int hm_bam_qnames_blob(const hm_bam* b, const uint8_t* flags, size_t n_flags, char* out, size_t cap, size_t* need);
 
 #ifdef __cplusplus
 }
