@@ -496,8 +496,11 @@ def leg_genome(args, T, lib, torch, rank, world, local_rank, stream):
         a1 = (1 << 31) - 1 if r.hi == len(loci[r.chrom]) else chunks_r[-1][1]
         per = aligned_per_read(sub)
         my_bases += int(per[(sub.tstart >= a0) & (sub.tstart < a1)].sum())
+        # every run has a context of its own with its private stream: collecting run k waits for run k only, so its host
+        # part (counters, som_seen replay, record copy) overlaps the kernels of the runs behind it.  The timing events
+        # are device timestamps on the bench's stream: the first before anything is enqueued, the second after every
+        # context has been collected (T.run), barrier + synchronize on both sides.
         ctx = lib.Context(local_rank)
-        ctx.set_stream(stream.cuda_stream)
         ctx.set_params(params)
         ctx.set_site_sets()
         ctx.omit_restatements(True)
@@ -510,9 +513,12 @@ def leg_genome(args, T, lib, torch, rank, world, local_rank, stream):
     state = {"log": np.zeros(15, np.int64), "recs": 0}
 
     def step():
+        # every run's device path is enqueued before the first is waited for: the GPU goes from run to run without the host
         log, recs = np.zeros(15, np.int64), 0
         for it in items:
-            rec, l = it["ctx"].call_chunks(it["table"], view=True, wait=False)
+            it["ctx"].call_chunks_submit(it["table"])
+        for it in items:
+            rec, l = it["ctx"].call_chunks_collect(view=True)
             log += l
             recs += rec.size
         state["log"], state["recs"] = log, recs
@@ -610,9 +616,14 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     bind_to_gpu_numa_node(local_rank)
+    saved_stdout = None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # stdout carries the one JSON line only
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        # stdout carries the one JSON line only: NCCL prints its version banner there when the first communicator comes up
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=dev)
     stream = torch.cuda.current_stream()
     T = Timer(torch, dist, world, stream)
@@ -671,8 +682,14 @@ def main():
                 out.update(res)
                 out["scaling_note"] = ("strong scaling: the same %d Mb genome for every N > 1; its one-GPU base is the `genome` object of "
                                        "the N = 1 line (whose headline is BASELINE configs[1], a different workload)" % args.genome_mb)
+        if saved_stdout is not None:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
+            saved_stdout = None
         if rank == 0 and out is not None:
             print(json.dumps(out))
+            sys.stdout.flush()
     finally:
         import shutil
         shutil.rmtree(tmpdir, ignore_errors=True)

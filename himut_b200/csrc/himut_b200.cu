@@ -115,6 +115,7 @@ struct hm_ctx {
   uint64_t site_cap_hint = 0;               // high-water mark of distinct sites per call
   char* h_geom_pin = nullptr;
   size_t h_geom_cap = 0;
+  struct Pending { bool active = false; std::vector<hm_chunk> chunks; uint64_t site_cap = 0; size_t bcap = 0; int n_launched = 0, parity = 0; bool omit = false; } pend;
   DevBuf b_cgeom, b_seg_keys, b_seg_read, b_keys_tmp, b_gscratch, b_czero, b_first_pair, b_tiles, b_site_valid, b_pair_c;
 };
 
@@ -527,12 +528,30 @@ static int upload_batch_impl(hm_ctx* ctx, const hm_read_batch* b, const hm_bq_co
   return HM_OK;
 }
 
+// stage: 0 the whole call, 1 enqueue only (hm_call_chunks_submit), 2 everything after the enqueue (hm_call_chunks_collect)
 static int call_chunks_impl(hm_ctx* ctx, const hm_chunk* chunks, size_t n_chunks, hm_site_record* out, size_t cap, size_t* n_out,
-                           int64_t log[HM_CALL_LOG_LEN], bool async);
+                           int64_t log[HM_CALL_LOG_LEN], bool async, int stage = 0);
 
 int hm_call_chunks(hm_ctx* ctx, const hm_chunk* chunks, size_t n_chunks, hm_site_record* out, size_t cap, size_t* n_out,
                    int64_t log[HM_CALL_LOG_LEN]) {
   return call_chunks_impl(ctx, chunks, n_chunks, out, cap, n_out, log, false);
+}
+
+/* hm_call_chunks in two halves, so that a host that drives several contexts (the chunk runs of a genome on one GPU) keeps
+ * the device busy: submit enqueues the whole device path of the call and returns at once; collect waits for it and
+ * does what hm_call_chunks_async does after its synchronisation (counters, som_seen replay, record copy).  One call
+ * may be pending per context; nothing else may be asked of the context in between. */
+int hm_call_chunks_submit(hm_ctx* ctx, const hm_chunk* chunks, size_t n_chunks) {
+  if (ctx && ctx->pend.active) return fail(ctx, HM_ERR_STATE, "a submitted call is still pending: collect it first");
+  size_t n_out = 0;
+  int64_t log[HM_CALL_LOG_LEN];
+  return call_chunks_impl(ctx, chunks, n_chunks, nullptr, 0, &n_out, log, true, 1);
+}
+int hm_call_chunks_collect(hm_ctx* ctx, hm_site_record* out, size_t cap, size_t* n_out, int64_t log[HM_CALL_LOG_LEN]) {
+  if (!ctx) return HM_ERR_ARG;
+  if (!ctx->pend.active) return fail(ctx, HM_ERR_STATE, "no submitted call is pending");
+  ctx->pend.active = false;
+  return call_chunks_impl(ctx, ctx->pend.chunks.data(), ctx->pend.chunks.size(), out, cap, n_out, log, true, 2);
 }
 
 /* hm_call_chunks that returns as soon as the counters are final: the record copy into `out` may still be in
@@ -742,9 +761,10 @@ int fused_enqueue(hm_ctx* ctx, const hm_chunk* chunks, size_t n_chunks, const st
 }  // namespace
 
 static int call_chunks_impl(hm_ctx* ctx, const hm_chunk* chunks, size_t n_chunks, hm_site_record* out, size_t cap, size_t* n_out,
-                            int64_t log[HM_CALL_LOG_LEN], bool async) {
+                            int64_t log[HM_CALL_LOG_LEN], bool async, int stage) {
   int rc = check_ready(ctx, chunks, n_chunks);
   if (rc) return rc;
+  if (stage != 2 && ctx->pend.active) return fail(ctx, HM_ERR_STATE, "a submitted call is still pending: collect it first");
   if (!log || !n_out) return fail(ctx, HM_ERR_ARG, "log / n_out is NULL");
   CU(cudaSetDevice(ctx->device));
   // HIMUT_B200_HOST_TIMING=1: wall-clock of the host-visible phases of one call, to stderr (diagnostics)
@@ -755,7 +775,7 @@ static int call_chunks_impl(hm_ctx* ctx, const hm_chunk* chunks, size_t n_chunks
   memset(log, 0, sizeof(int64_t) * HM_CALL_LOG_LEN);
   *n_out = 0;
   ctx->final_recs.clear();
-  t_reset(ctx);
+  if (stage != 2) t_reset(ctx);
   std::vector<uint64_t> pair_off(n_chunks + 1, 0);
   for (size_t i = 0; i < n_chunks; i++) pair_off[i + 1] = pair_off[i] + (chunks[i].read_hi - chunks[i].read_lo);
   const uint64_t n_pairs = pair_off.back();
@@ -790,11 +810,17 @@ static int call_chunks_impl(hm_ctx* ctx, const hm_chunk* chunks, size_t n_chunks
   unsigned long long h_cnt[32];
   memset(h_cnt, 0, sizeof(h_cnt));
   unsigned long long* d_cnt = ctx->b_counters.as<unsigned long long>();
-  const int parity = ctx->rec_parity;
+  const int parity = stage == 2 ? ctx->pend.parity : ctx->rec_parity;
   DevBuf& rec_buf = parity ? ctx->b_records_alt : ctx->b_records;
-  const bool omit = ctx->omit_restatements;
+  const bool omit = stage == 2 ? ctx->pend.omit : ctx->omit_restatements;
   size_t HM_BOUNDARY_CAP = HM_BOUNDARY_CAP_DEFAULT;
   if (const char* e = getenv("HIMUT_B200_BOUNDARY_CAP")) HM_BOUNDARY_CAP = (size_t)std::max(0ll, atoll(e));
+  if (stage == 1 && !fused) { // the first version synchronises in the middle: everything happens at collect
+    ctx->pend.active = true;
+    ctx->pend.chunks.assign(chunks, chunks + n_chunks);
+    ctx->pend.parity = parity; ctx->pend.omit = omit;
+    return HM_OK;
+  }
   uint32_t* h_bidx = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(ctx->h_cnt_pin) + CNT_BYTES);
   uint32_t* h_bpos = h_bidx + HM_BOUNDARY_FIRST;
   hm_site_record* h_brecs = reinterpret_cast<hm_site_record*>(h_bpos + HM_BOUNDARY_FIRST);
@@ -806,17 +832,27 @@ static int call_chunks_impl(hm_ctx* ctx, const hm_chunk* chunks, size_t n_chunks
     site_cap = std::min<uint64_t>(site_cap, std::max<uint64_t>(total_cap, 1));
     size_t bcap = HM_BOUNDARY_CAP;
     int n_launched = 0;
+    if (stage == 2) { site_cap = ctx->pend.site_cap; bcap = ctx->pend.bcap; n_launched = ctx->pend.n_launched; }
     for (int attempt = 0;; attempt++) {
-      t_reset(ctx);
-      FusedGeom G;
-      if ((rc = fused_enqueue(ctx, chunks, n_chunks, pair_off, geom.data(), total_cap, n_tiles, site_cap, parity, omit, bcap, &G))) return rc;
-      k_publish_call<<<8, 256, 0, ctx->stream>>>(reinterpret_cast<const uint32_t*>(d_cnt), (uint32_t)(CNT_BYTES / 4), ctx->b_bidx.as<uint32_t>(),
-                                                 ctx->b_bpos.as<uint32_t>(), ctx->b_brecs.as<uint32_t>(), (uint32_t)std::min<size_t>(HM_BOUNDARY_FIRST, bcap),
-                                                 d_cnt + 4, reinterpret_cast<uint32_t*>(ctx->h_cnt_pin), h_bidx, h_bpos, reinterpret_cast<uint32_t*>(h_brecs));
-      CU(cudaGetLastError());
-      // own kernels launched by this attempt: k_call_pairs, k_site_sort, k_tile_scan, k_site_range2, k_call_scan, k_site_valid,
-      // k_site_reduce, k_publish_call (+ k_bq_expand when the batch came compact, counted by the upload)
-      n_launched += 6 + (n_tiles ? 1 : 0) + (n_chunks ? 1 : 0);
+      if (!(stage == 2 && attempt == 0)) { // collect: the first attempt was enqueued by submit
+        t_reset(ctx);
+        FusedGeom G;
+        if ((rc = fused_enqueue(ctx, chunks, n_chunks, pair_off, geom.data(), total_cap, n_tiles, site_cap, parity, omit, bcap, &G))) return rc;
+        k_publish_call<<<8, 256, 0, ctx->stream>>>(reinterpret_cast<const uint32_t*>(d_cnt), (uint32_t)(CNT_BYTES / 4), ctx->b_bidx.as<uint32_t>(),
+                                                   ctx->b_bpos.as<uint32_t>(), ctx->b_brecs.as<uint32_t>(), (uint32_t)std::min<size_t>(HM_BOUNDARY_FIRST, bcap),
+                                                   d_cnt + 4, reinterpret_cast<uint32_t*>(ctx->h_cnt_pin), h_bidx, h_bpos, reinterpret_cast<uint32_t*>(h_brecs));
+        CU(cudaGetLastError());
+        // own kernels launched by this attempt: k_call_pairs, k_site_sort, k_tile_scan, k_site_range2, k_call_scan, k_site_valid,
+        // k_site_reduce, k_publish_call (+ k_bq_expand when the batch came compact, counted by the upload)
+        n_launched += 6 + (n_tiles ? 1 : 0) + (n_chunks ? 1 : 0);
+      }
+      if (stage == 1) { // submitted: the rest happens at collect
+        ctx->pend.active = true;
+        ctx->pend.chunks.assign(chunks, chunks + n_chunks);
+        ctx->pend.site_cap = site_cap; ctx->pend.bcap = bcap; ctx->pend.n_launched = n_launched;
+        ctx->pend.parity = parity; ctx->pend.omit = omit;
+        return HM_OK;
+      }
       lap(4);
       CU(cudaStreamSynchronize(ctx->stream)); // the one synchronisation of the call
       lap(5);

@@ -20,7 +20,7 @@ EXPORTS = [
     "hm_set_phase_sets", "hm_upload_batch", "hm_call_chunks", "hm_call_batch", "hm_normcounts_chunks",
     "hm_read_stats", "hm_last_timing", "hm_last_kernel_times", "hm_set_stream", "hm_host_register",
     "hm_host_unregister", "hm_abi_sizeof", "hm_last_records", "hm_qname_seen", "hm_set_reference", "hm_ref_tricounts", "hm_last_norm_exact_sites",
-    "hm_phase_edges_begin", "hm_phase_edges_add", "hm_phase_edges_end", "hm_upload_batch_compact", "hm_call_batch_compact", "hm_call_chunks_async", "hm_records_wait", "hm_set_option", "hm_last_call_path",
+    "hm_phase_edges_begin", "hm_phase_edges_add", "hm_phase_edges_end", "hm_upload_batch_compact", "hm_call_batch_compact", "hm_call_chunks_async", "hm_records_wait", "hm_set_option", "hm_last_call_path", "hm_call_chunks_submit", "hm_call_chunks_collect",
 ]
 
 
@@ -62,6 +62,8 @@ def load():
         lib.hm_last_kernel_times.argtypes = [vp, vp, vp, sz, C.POINTER(sz)]
         lib.hm_last_records.argtypes = [vp, vp, sz, C.POINTER(sz)]
         lib.hm_records_wait.argtypes = [vp]
+        lib.hm_call_chunks_submit.argtypes = [vp, vp, sz]
+        lib.hm_call_chunks_collect.argtypes = [vp, vp, sz, C.POINTER(sz), vp]
         lib.hm_set_option.argtypes = [vp, C.c_int, C.c_int]
         lib.hm_qname_seen.argtypes = [vp, vp, sz, C.POINTER(sz)]
         lib.hm_set_reference.argtypes = [vp, vp, sz]
@@ -221,6 +223,27 @@ class Context:
         if not wait and not view:
             raise ValueError("wait=False needs view=True")
         return self._call(self.lib.hm_call_chunks if wait else self.lib.hm_call_chunks_async, (), chunks, cap, view)
+
+    def call_chunks_submit(self, chunks):
+        """enqueue the device path of a call and return at once (call_chunks_collect finishes it): several contexts
+        on one GPU are submitted back to back so the device never waits for the host between them"""
+        chunks = np.ascontiguousarray(chunks, dtype=abi.CHUNK_DTYPE)
+        self._chk(self.lib.hm_call_chunks_submit(self.h, _p(chunks), len(chunks)))
+
+    def call_chunks_collect(self, cap=None, view=True):
+        """-> (records, log[15]) of the submitted call; view=True: a view of one of the two pinned buffers whose copy
+        may still be in flight (records_wait)"""
+        out = self._out_buffer(int(cap or getattr(self, "_cap", 65536)))
+        n = C.c_size_t(0)
+        log = np.zeros(abi.CALL_LOG_LEN, np.int64)
+        rc = self.lib.hm_call_chunks_collect(self.h, _p(out), out.shape[0], C.byref(n), _p(log))
+        if rc == abi.HM_ERR_CAPACITY:
+            self._cap = int(n.value) + int(n.value) // 4 + 1024
+            out = self._out_buffer(self._cap)
+            rc = self.lib.hm_last_records(self.h, _p(out), out.shape[0], C.byref(n))
+        self._chk(rc)
+        res = out[: n.value]
+        return (res if view else res.copy()), log
 
     def omit_restatements(self, on=True):
         """records of germline restatements (never emitted by the reference) stay on the device; counters unchanged"""

@@ -278,6 +278,15 @@ int hm_call_chunks_async(hm_ctx* ctx, const hm_chunk* chunks, size_t n_chunks,
                          int64_t log[HM_CALL_LOG_LEN]);
 int hm_records_wait(hm_ctx* ctx);
 
+/* hm_call_chunks_async in two halves, for a host that drives several contexts on one GPU (the chunk runs of a genome,
+ * himut_b200/genome.py): submit enqueues the whole device path of the call on the context's stream and returns at once
+ * (the fused path synchronises nowhere in between); collect waits for it and does the rest (counters, som_seen replay,
+ * record copy, with hm_call_chunks_async's rules for `out`).  Submitting the calls of all contexts before collecting
+ * the first keeps the device busy across them.  One call may be pending per context and nothing else may be asked
+ * of the context until it is collected. */
+int hm_call_chunks_submit(hm_ctx* ctx, const hm_chunk* chunks, size_t n_chunks);
+int hm_call_chunks_collect(hm_ctx* ctx, hm_site_record* out, size_t cap, size_t* n_out, int64_t log[HM_CALL_LOG_LEN]);
+
 /* options of a context.  HM_OPT_OMIT_RESTATEMENTS (default 0): records whose status is one of HM_ST_GERM_* — a
  * candidate that merely restates the germline genotype, which the reference counts and drops (caller.py:338-345) —
  * are not copied to the host; they still count in log[2..4].  A third of the record bytes at 30x.                */

@@ -10,7 +10,7 @@ import sys
 import pytest
 
 import parity
-from himut_b200 import bamdec, genome, gtmodel, synth, worker
+from himut_b200 import bamio, genome, gtmodel, synth, worker
 
 pytestmark = pytest.mark.gpu
 CONTIGS = [("chr1", 1_400_000, 61), ("chr2", 700_000, 62), ("chr10", 300_000, 63), ("chrX", 150_000, 64)]
@@ -30,7 +30,7 @@ def job(tmp_path_factory):
     tmp = tmp_path_factory.mktemp("genome")
     bam = str(tmp / "g.bam")
     parts = [(c, n, synth.generate(n, seed=s, copy=False).batch) for c, n, s in CONTIGS]
-    bamdec.write_batches_bam(bam, parts) if hasattr(bamdec, "write_batches_bam") else __import__("himut_b200.bamio", fromlist=["x"]).write_batches_bam(bam, parts)
+    bamio.write_batches_bam(bam, parts)
     cj = str(tmp / "contigs.json")
     json.dump([[c, n] for c, n, _ in CONTIGS], open(cj, "w"))
     return tmp, bam, cj
