@@ -69,8 +69,11 @@ def carry_som_seen(parts, later_starts):
     return out
 
 
-def call_region(ctx, bam_file, chrom, chunkloci_lst, chunk_sets, phase, want_names=False):
-    """the device path over a contig's chunk list (or a run of it): decode one group ahead, upload, call.
+def call_region(ctx, bam_file, chrom, chunkloci_lst, chunk_sets, phase, want_names=False, ctx2=None):
+    """the device path over a contig's chunk list (or a run of it), pipelined: group k + 1 is decoded on a thread of its
+    own while group k is uploaded; with a second context (configured like the first) the two alternate from group to
+    group, so upload(k + 1) also overlaps kernels(k) and the record copy of k - 1:
+        decode(k + 1) || H2D(k + 1) || kernels(k) || D2H(k - 1).
     -> (records incl. germline restatements, number of distinct query names that passed the read gates,
         names blob (want_names) or None)"""
     src = worker.RegionSource(bam_file)
@@ -78,27 +81,45 @@ def call_region(ctx, bam_file, chrom, chunkloci_lst, chunk_sets, phase, want_nam
     kept, laters = [], []
     starts = [s for _, s, _e in chunkloci_lst]
     groups = worker.group_chunks(chunkloci_lst)
+    ctxs = [ctx] if (ctx2 is None or len(groups) == 1 or not hasattr(ctx, "call_chunks_submit")) else [ctx, ctx2]
     pins = worker.PinCache(ctx, enabled=len(groups) > 1)
     # `call` never needs the read bases as a stream: substituted bases are in the ops, and under a cs match the read
     # carries the reference allele of the site (cslib.py:22-29) — the decoder does not unpack them (seq=False) — and the
     # qualities travel as the decoder's parse pass leaves them: bitmap of the modal quality + exceptions, expanded on the
-    # device (upload_compact).  Group k + 1 is decoded while group k is uploaded and called.
+    # device (upload_compact).
     # --phase: the reference re-fetches [tpos, tpos + 1) at a site (caller.py:558), one position past a chunk that ends
     # at tpos: decode that position too, so a record that starts there is in the batch (it can only matter through a
     # shared query name)
+    pending = None  # (context, chunk indices) of the call that is enqueued but not collected
+
+    def finish(p):
+        c, idx = p[0], p[1]
+        rec, _log = c.call_chunks_collect(view=False) if len(ctxs) > 1 else p[2]
+        tally.add(c.qname_seen())
+        kept.append(rec)
+        laters.append(min(starts[idx[-1] + 1:], default=None))
+
     try:
+        k = 0
         for idx, batch, cq, table, release in worker.pipelined_groups(src, chrom, chunkloci_lst, groups, chunk_sets, seq=False,
                                                                       pad=1 if phase else 0):
             if batch.n_reads == 0:
                 release()
                 continue
+            c = ctxs[k % len(ctxs)]
+            k += 1
             pins.pin([cq.mask, cq.exc, batch.ops])
-            ctx.upload_compact(batch, cq)
+            c.upload_compact(batch, cq)
             release()  # everything is on the device: the decoder may reuse the buffers
-            rec, _log = ctx.call_chunks(table)
-            tally.add(ctx.qname_seen())
-            kept.append(rec)
-            laters.append(min(starts[idx[-1] + 1:], default=None))
+            if len(ctxs) > 1:
+                c.call_chunks_submit(table)
+                if pending is not None:
+                    finish(pending)
+                pending = (c, idx)
+            else:
+                finish((c, idx, c.call_chunks(table)))
+        if pending is not None:
+            finish(pending)
         names = src.reader.qnames_blob(tally.seen) if want_names else None
     finally:
         pins.close()
@@ -116,11 +137,16 @@ def get_somatic_substitutions(
     create_panel_of_normals, chrom2tsbs_lst, chrom2tsbs_log,
 ):
     ctx = worker.context()
-    chunk_sets = configure(ctx, chrom, common_snps, panel_of_normals, chunkloci_lst, phase_set2hbit_lst, phase_set2hpos_lst,
-                           phase_set2hetsnp_lst, min_qv, min_mapq, qlen_lower_limit, qlen_upper_limit, min_sequence_identity,
-                           min_gq, min_bq, min_trim, max_mismatch_count, mismatch_window_size, md_threshold, min_ref_count,
-                           min_alt_count, min_hap_count, germline_snv_prior, phase, non_human_sample, create_panel_of_normals)
-    rec, num_ccs, _ = call_region(ctx, bam_file, chrom, chunkloci_lst, chunk_sets, phase)
+    conf = (chrom, common_snps, panel_of_normals, chunkloci_lst, phase_set2hbit_lst, phase_set2hpos_lst,
+            phase_set2hetsnp_lst, min_qv, min_mapq, qlen_lower_limit, qlen_upper_limit, min_sequence_identity,
+            min_gq, min_bq, min_trim, max_mismatch_count, mismatch_window_size, md_threshold, min_ref_count,
+            min_alt_count, min_hap_count, germline_snv_prior, phase, non_human_sample, create_panel_of_normals)
+    chunk_sets = configure(ctx, *conf)
+    ctx2 = None
+    if len(worker.group_chunks(chunkloci_lst)) > 1 and hasattr(ctx, "call_chunks_submit"):
+        ctx2 = worker.second_context()  # long contigs: two contexts alternate between decode groups
+        configure(ctx2, *conf)
+    rec, num_ccs, _ = call_region(ctx, bam_file, chrom, chunkloci_lst, chunk_sets, phase, ctx2=ctx2)
     chrom2tsbs_lst[chrom] = records.records_to_tsbs_lst(chrom, rec)
     chrom2tsbs_log[chrom] = [int(v) for v in _log_from_records(rec, num_ccs)]
     return int((rec["flags"] & abi.SITE_PL_TIE).astype(bool).sum())

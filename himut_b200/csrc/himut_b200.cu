@@ -268,6 +268,11 @@ extern "C" {
 
 int hm_abi_version(void) { return HM_ABI_VERSION; }
 
+int hm_device_count(void) {
+  int n = 0;
+  return cudaGetDeviceCount(&n) == cudaSuccess ? n : 0;
+}
+
 size_t hm_abi_sizeof(int which) {
   switch (which) {
     case 0: return sizeof(hm_read_batch);

@@ -129,6 +129,7 @@ def call_genome(bam_file, chrom2chunkloci, args, phase_tables=None, common_snps=
     per_contig = {}
     for r in runs:
         per_contig.setdefault(r.chrom, []).append(r)
+    own_ctx = ctx is None
     ctx = ctx or worker.context()
     phase = bool(args.get("phase"))
     local, t0, my_weight = [], time.perf_counter(), 0
@@ -137,14 +138,18 @@ def call_genome(bam_file, chrom2chunkloci, args, phase_tables=None, common_snps=
             continue
         chunks = chrom2chunkloci[r.chrom][r.lo:r.hi]
         hbit, hpos, hetsnp = (phase_tables or {}).get(r.chrom, ({}, {}, {}))
-        chunk_sets = caller.configure(
-            ctx, r.chrom, common_snps, panel_of_normals, chunks, hbit, hpos, hetsnp, args["min_qv"], args["min_mapq"],
-            args["qlen_lower_limit"], args["qlen_upper_limit"], args["min_sequence_identity"], args["min_gq"], args["min_bq"],
-            args["min_trim"], args["max_mismatch_count"], args["mismatch_window"], args["md_threshold"], args["min_ref_count"],
-            args["min_alt_count"], args["min_hap_count"], args["germline_snv_prior"], phase, bool(args.get("non_human_sample")),
-            bool(args.get("create_panel_of_normals")))
+        conf = (r.chrom, common_snps, panel_of_normals, chunks, hbit, hpos, hetsnp, args["min_qv"], args["min_mapq"],
+                args["qlen_lower_limit"], args["qlen_upper_limit"], args["min_sequence_identity"], args["min_gq"], args["min_bq"],
+                args["min_trim"], args["max_mismatch_count"], args["mismatch_window"], args["md_threshold"], args["min_ref_count"],
+                args["min_alt_count"], args["min_hap_count"], args["germline_snv_prior"], phase, bool(args.get("non_human_sample")),
+                bool(args.get("create_panel_of_normals")))
+        chunk_sets = caller.configure(ctx, *conf)
+        ctx2 = None
+        if own_ctx and len(worker.group_chunks(chunks)) > 1:  # long runs: two contexts alternate between decode groups
+            ctx2 = worker.second_context()
+            caller.configure(ctx2, *conf)
         split = len(per_contig[r.chrom]) > 1
-        rec, num_ccs, names = caller.call_region(ctx, bam_file, r.chrom, chunks, chunk_sets, phase, want_names=split)
+        rec, num_ccs, names = caller.call_region(ctx, bam_file, r.chrom, chunks, chunk_sets, phase, want_names=split, ctx2=ctx2)
         local.append((r.index, rec, num_ccs, names))
         my_weight += r.weight
     seconds = time.perf_counter() - t0

@@ -20,7 +20,7 @@ EXPORTS = [
     "hm_set_phase_sets", "hm_upload_batch", "hm_call_chunks", "hm_call_batch", "hm_normcounts_chunks",
     "hm_read_stats", "hm_last_timing", "hm_last_kernel_times", "hm_set_stream", "hm_host_register",
     "hm_host_unregister", "hm_abi_sizeof", "hm_last_records", "hm_qname_seen", "hm_set_reference", "hm_ref_tricounts", "hm_last_norm_exact_sites",
-    "hm_phase_edges_begin", "hm_phase_edges_add", "hm_phase_edges_end", "hm_upload_batch_compact", "hm_call_batch_compact", "hm_call_chunks_async", "hm_records_wait", "hm_set_option", "hm_last_call_path", "hm_call_chunks_submit", "hm_call_chunks_collect",
+    "hm_phase_edges_begin", "hm_phase_edges_add", "hm_phase_edges_end", "hm_upload_batch_compact", "hm_call_batch_compact", "hm_call_chunks_async", "hm_records_wait", "hm_set_option", "hm_last_call_path", "hm_call_chunks_submit", "hm_call_chunks_collect", "hm_device_count",
 ]
 
 
@@ -39,6 +39,7 @@ def load():
         lib = C.CDLL(LIB_PATH)
         vp, sz = C.c_void_p, C.c_size_t
         lib.hm_abi_version.restype = C.c_int
+        lib.hm_device_count.restype = C.c_int
         lib.hm_abi_sizeof.restype = sz
         lib.hm_abi_sizeof.argtypes = [C.c_int]
         lib.hm_create.argtypes = [C.c_int, C.POINTER(vp)]
@@ -85,6 +86,11 @@ def _p(a):
     return a.ctypes.data_as(C.c_void_p) if a is not None and a.size else None
 
 
+def device_count():
+    """cudaGetDeviceCount through the library (0 when no driver / device)"""
+    return int(load().hm_device_count())
+
+
 class Context:
     """one hm_ctx: single-threaded, bound to one GPU; create it inside the worker process"""
 
@@ -95,6 +101,7 @@ class Context:
         if rc != 0:
             raise HimutError(rc, "hm_create(device=%d) failed: no usable CUDA device (there is no CPU fallback)" % device)
         self.h = h
+        self.device = int(device)
         self._keep = {}
 
     def close(self):

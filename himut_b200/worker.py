@@ -28,15 +28,28 @@ def context():
             dev = dev % max(n, 1)
         _CTX = lib.Context(int(dev))
         _CTX_PID = os.getpid()
+        if os.environ.get("HIMUT_B200_VERBOSE"):
+            import sys
+            print("himut_b200: worker %d uses CUDA device %d" % (os.getpid(), int(dev)), file=sys.stderr)
     return _CTX
 
 
+_CTX2 = None
+
+
+def second_context():
+    """a second hm_ctx on the process's device: the worker mirrors alternate between the two from decode group to
+    decode group, so the upload of group k + 1 overlaps the kernels of group k (each context has its own stream)"""
+    global _CTX2
+    first = context()
+    if _CTX2 is None or _CTX2[0] != os.getpid() or _CTX2[2] is not first:
+        _CTX2 = (os.getpid(), lib.Context(first.device), first)
+    return _CTX2[1]
+
+
 def _device_count():
-    try:
-        import torch
-        return torch.cuda.device_count()
-    except Exception:
-        return 1
+    """visible CUDA devices, asked of the library itself (cudaGetDeviceCount): no torch import in a pool worker"""
+    return max(1, lib.device_count())
 
 
 def group_chunks(chunkloci_lst, span=None):

@@ -220,6 +220,8 @@ typedef struct hm_site_record {
 typedef struct hm_ctx hm_ctx;
 
 int hm_abi_version(void);
+/* visible CUDA devices (cudaGetDeviceCount; 0 without a driver or a device): pool workers place themselves with it */
+int hm_device_count(void);
 /* sizeof of the ABI structs as the library was compiled: 0 hm_read_batch, 1 hm_chunk,
  * 2 hm_params, 3 hm_site_record (bindings check their own layout against it) */
 size_t hm_abi_sizeof(int which);
