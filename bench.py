@@ -401,6 +401,41 @@ def leg_contig(args, T, ctx, d, params, chunks, tmpdir):
     return out, bam
 
 
+def leg_phase(args, T, ctx, d):
+    """BASELINE configs[3] on the same contig: `himut call --phase` with a phased germline table (phase sets of
+    ~200 kb, chunks = their spans) and common-SNP + panel-of-normals sets, resident"""
+    import cases
+    from himut_b200 import gtmodel
+    ph, spans, sets = cases.phase_case(d, 200_000)
+    common, pon = cases.site_sets_from_synth(d, 3)
+    p = gtmodel.make_params(**dict(gtmodel.DEFAULT_CALL_ARGS, phase=True))
+    chunks = d.batch.chunk_table(spans, sets)
+    ctx.set_params(p)
+    ctx.set_site_sets(common, pon)
+    ctx.set_phase_sets(ph)
+    ctx.upload(d.batch.without_seq())
+    state = {}
+
+    def step():
+        state["rec"], state["log"] = ctx.call_chunks(chunks, view=True, wait=False)
+
+    for _ in range(2):
+        step()
+    n = max(3, args.steps // 2)
+    ms = T.run(step, n, after=ctx.records_wait) / n
+    k_ms, launches = kernel_breakdown(ctx, step)
+    ctx.records_wait()
+    rec, log = state["rec"], state["log"]
+    out = {"value": d.aligned_bases / (ms * 1e-3), "unit": "bases/s", "ms_per_step": ms, "steps": n, "kernel_ms_per_step": k_ms,
+           "phase_sets": len(spans), "hetsnps": int(ph["hpos"].size), "common_snps": int(common.size), "panel_of_normals": int(pon.size),
+           "site_records_per_step": int(rec.size), "log_counters": [int(v) for v in log],
+           "workload": "himut call --phase, phased germline table (phase sets of ~200 kb) + common-SNP + PoN sets, same 64 Mb contig"}
+    # back to the plain configuration for the legs that follow
+    ctx.set_params(gtmodel.make_params(**gtmodel.DEFAULT_CALL_ARGS))
+    ctx.set_site_sets()
+    return out
+
+
 def leg_normcounts(args, T, ctx, d, chunks):
     batch = d.batch
     ctx.upload(batch)
@@ -594,6 +629,7 @@ def main():
     ap.add_argument("--no-normcounts", action="store_true")
     ap.add_argument("--no-bam-leg", action="store_true")
     ap.add_argument("--no-genome", action="store_true")
+    ap.add_argument("--no-phase", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -643,6 +679,11 @@ def main():
                    "ms_per_step": res.pop("ms_per_step"), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                    "dtype": "u8/f64", "data": "synthetic", "config": workload_config(args, 1), "clocks": clocks}
             out.update(res)
+            if not args.no_phase:
+                try:
+                    out["phase"] = leg_phase(args, T, ctx, d)
+                except Exception as ex:
+                    out["phase"] = {"error": repr(ex)}
             if not args.no_normcounts:
                 out["normcounts"] = leg_normcounts(args, T, ctx, d, chunks)
             ctx.close()

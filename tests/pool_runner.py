@@ -38,6 +38,11 @@ def main():
         plain = worker.RegionSource.batch
         worker.RegionSource.batch = lambda self, chrom, loci, phase_sets=None, seq=True, **kw: plain(self, chrom, loci, phase_sets, seq=True, **kw)
 
+    mode = over.pop("mode", "call")
+    if mode == "normcounts":
+        return run_normcounts(work, bam, common, pon, threads, over)
+    if mode == "phase_edges":
+        return run_phase_edges(bam, threads)
     a = dict(gtmodel.DEFAULT_CALL_ARGS)
     for k, v in over.items():
         a[k] = type(a[k])(v)
@@ -69,6 +74,53 @@ def main():
     (vcfio.dump_phased_sbs if block else vcfio.dump_sbs)(out, HEADER, chrom_lst, lst)
     body = [l for l in open(out).read().split("\n") if l and not l.startswith("#")]
     print(json.dumps({"thresholds": [int(qlo), int(qhi), int(md)], "log": {c: [int(v) for v in log[c]] for c in chrom_lst}, "body": body}))
+
+
+def run_normcounts(work, bam, common, pon, threads, over):
+    """the process model of `himut normcounts` around the callable-base worker (normcounts.py:494-538): one starmap task
+    per contig of the region list, the contig's sequence pickled into the task, Manager dicts for the results; the
+    thresholds are the ones the reference read back from the call VCF's header (given as qlo= qhi= md=)"""
+    import cases
+    from himut_b200 import gtmodel, normcounts
+    a = dict(gtmodel.DEFAULT_CALL_ARGS)
+    qlo, qhi, md = int(over["qlo"]), int(over["qhi"]), float(over["md"])
+    contigs = over["contigs"].split(",")
+    data = {c: (n, d) for c, n, d in cases.cli_dataset()}
+    pool = mp.Pool(threads)
+    manager = mp.Manager()
+    ccs, rt, log = manager.dict(), manager.dict(), manager.dict()
+    pool.starmap(normcounts.get_callable_tricounts, [
+        (c, data[c][1].ref.decode(), bam, common, pon, [(c, s, e) for s, e in cases.chunkloci(0, data[c][0])], {}, {}, {},
+         a["min_qv"], a["min_mapq"], a["min_trim"], qlo, qhi, a["min_sequence_identity"], a["min_gq"], a["min_bq"], a["mismatch_window"],
+         a["max_mismatch_count"], a["min_ref_count"], a["min_alt_count"], a["min_hap_count"], md, 1 / (10 ** 6), a["germline_snv_prior"],
+         1 / (10 ** 4), False, False, ccs, rt, log) for c in contigs])
+    pool.close()
+    pool.join()
+    tri = {}
+    for t in normcounts.TRI_LST:  # mutlib.get_cumsum_tricounts: summed over the contigs
+        tri[t] = [sum(int(rt[c][t]) for c in contigs), sum(int(ccs[c][t]) for c in contigs)]
+    print(json.dumps({"tri": tri, "log": {c: [int(v) for v in log[c]] for c in contigs}}))
+
+
+def _edges_task(c, n, seed, bam):
+    import cases
+    from himut_b200 import phaselib, synth
+    d = synth.generate(n, seed=seed, somatic_rate=2e-5, depth=cases.CLI_DEPTH)
+    het = d.germ["gt"] < 2
+    hetsnp_lst = [(int(p), "ATGC"[r], "ATGC"[al]) for p, r, al in zip(d.germ["pos"][het], d.germ["ref"][het], d.germ["alt"][het])]
+    h2i = {h: i for i, h in enumerate(hetsnp_lst)}
+    edge_lst, e2c = phaselib.get_edges(c, bam, 20, 20, [h[0] for h in hetsnp_lst], hetsnp_lst, h2i)
+    return c, [[int(i), int(j)] + [int(v) for v in e2c[(i, j)]] for (i, j) in edge_lst]
+
+
+def run_phase_edges(bam, threads):
+    """`himut phase` forks one task per contig (phaselib.py:280-300), each calling get_edges: the same around the mirror"""
+    import cases
+    pool = mp.Pool(threads)
+    res = pool.starmap(_edges_task, [(c, n, seed, bam) for c, n, seed in cases.CLI_CONTIGS])
+    pool.close()
+    pool.join()
+    print(json.dumps({"edges": dict(res)}))
 
 
 if __name__ == "__main__":

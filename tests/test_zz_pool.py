@@ -84,3 +84,59 @@ def test_forked_pool_matches_reference_cli_cpu(tmp_path, name):
 @pytest.mark.parametrize("name", ["plain", "phase"])
 def test_forked_pool_matches_reference_cli_gpu(tmp_path, name):
     _check(_run(str(tmp_path), name, real=True), name)
+
+
+# ---- `himut normcounts` and `himut phase` workers in the same process model -------------------------------------
+GOLD2 = json.load(open(os.path.join(cases.GOLDEN_DIR, "cli_norm_phase.json")))
+
+
+def _run_mode(tmp, real, extra):
+    data = cases.cli_dataset(None)
+    bam = os.path.join(tmp, "synth.bam")
+    bamio.write_batches_bam(bam, [(c, n, d.batch) for c, n, d in data])
+    sets = [(c,) + cases.site_sets_from_synth(d, 40 + i) for i, (c, _n, d) in enumerate(data)]
+    common, pon = os.path.join(tmp, "common.vcf.bgz"), os.path.join(tmp, "pon.vcf.bgz")
+    _write_sites(common, [(c, k) for c, k, _ in sets])
+    _write_sites(pon, [(c, k) for c, _, k in sets])
+    cmd = [sys.executable, os.path.join(HERE, "pool_runner.py"), tmp, bam, common, pon, "2", "0"] + extra
+    env = dict(os.environ)
+    env.pop("HIMUT_B200_DEVICE", None)
+    env.pop("LOCAL_RANK", None)
+    env["HIMUT_B200_CLI_REAL_CONTEXT"] = "1" if real else "0"
+    r = _run_group(cmd, env, timeout=900)
+    if real and r.returncode != 0 and "hm_create(device=" in (r.stdout + r.stderr):
+        pytest.skip("a second process cannot open the GPU while pytest holds a context (exclusive-process mode)")
+    assert r.returncode == 0, (r.stdout[-2000:], r.stderr[-4000:])
+    return json.loads(r.stdout.strip().split("\n")[-1])
+
+
+def _check_normcounts(got):
+    exp = GOLD2["normcounts"]
+    assert got["log"] == exp["log"]
+    assert got["tri"] == {k: v for k, v in exp["tri"].items()}
+
+
+def _norm_args():
+    qlo, qhi, md = GOLD2["normcounts"]["thresholds"]
+    return ["mode=normcounts", "qlo=%d" % qlo, "qhi=%d" % qhi, "md=%r" % md, "contigs=" + ",".join(GOLD2["normcounts"]["contigs"])]
+
+
+def test_normcounts_pool_matches_reference_cli_cpu(tmp_path):
+    """the callable-base workers in `himut normcounts`' process model == the TSV columns and norm.log the reference's
+    own command line wrote (tests/golden/make_golden_cli2.py)"""
+    _check_normcounts(_run_mode(str(tmp_path), False, _norm_args()))
+
+
+@pytest.mark.gpu
+def test_normcounts_pool_matches_reference_cli_gpu(tmp_path):
+    _check_normcounts(_run_mode(str(tmp_path), True, _norm_args()))
+
+
+def test_phase_edge_pool_matches_reference_cpu(tmp_path):
+    """the phase-edge workers in `himut phase`'s process model == the reference's own get_edges per contig"""
+    assert _run_mode(str(tmp_path), False, ["mode=phase_edges"])["edges"] == GOLD2["phase_edges"]
+
+
+@pytest.mark.gpu
+def test_phase_edge_pool_matches_reference_gpu(tmp_path):
+    assert _run_mode(str(tmp_path), True, ["mode=phase_edges"])["edges"] == GOLD2["phase_edges"]
