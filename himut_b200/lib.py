@@ -249,6 +249,8 @@ class Context:
             out = self._out_buffer(self._cap)
             rc = self.lib.hm_last_records(self.h, _p(out), out.shape[0], C.byref(n))
         self._chk(rc)
+        if not view:  # the record copy of a collected call may still be in flight: a private copy needs it finished
+            self.records_wait()
         res = out[: n.value]
         return (res if view else res.copy()), log
 
