@@ -273,14 +273,23 @@ class Timer:
             self.dist.barrier()
         self.torch.cuda.synchronize()
 
-    def run(self, fn, steps, after=None):
+    def run(self, fn, steps, after=None, streams=()):
+        """streams: the CUDA streams the timed work is launched on when it is not the bench's own (contexts with a stream
+        each): they wait for the opening event and the closing event waits for them, so the two events bracket the work
+        on the device whatever stream it ran on"""
         self.barrier()
         e0, e1 = self.torch.cuda.Event(enable_timing=True), self.torch.cuda.Event(enable_timing=True)
         e0.record(self.stream)
+        for st in streams:
+            st.wait_event(e0)
         for _ in range(steps):
             fn()
         if after:
             after()
+        for st in streams:
+            ev = self.torch.cuda.Event()
+            ev.record(st)
+            self.stream.wait_event(ev)
         e1.record(self.stream)
         self.barrier()
         return e0.elapsed_time(e1)
@@ -310,19 +319,55 @@ def leg_contig(args, T, ctx, d, params, chunks, tmpdir):
     ctx.omit_restatements(True)  # germline restatements are counted on the device and not copied back (caller.py:338-345)
     ctx.kernel_timing(False)
     # ---- resident ----
-    ctx.upload(batch.without_seq())
-    state = {}
+    # As the worker drives the device (himut_b200/caller.py:call_region): two contexts of the process alternate from
+    # call to call, the next call is enqueued before the previous one is collected, so the device goes from one to the
+    # other without waiting for the host.  Both hold the batch; each has a stream of its own.
+    from himut_b200 import lib as _lib
+    ctx_b = _lib.Context(ctx.device)
+    pair, streams = [ctx, ctx_b], [T.torch.cuda.Stream(), T.torch.cuda.Stream()]
+    for c, st in zip(pair, streams):
+        c.set_stream(st.cuda_stream)
+        c.set_params(params)
+        c.set_site_sets()
+        c.omit_restatements(True)
+        c.kernel_timing(False)
+        c.upload(batch.without_seq())
+    state = {"k": 0, "pending": None}
 
     def step():
-        state["rec"], state["log"] = ctx.call_chunks(chunks, view=True, wait=False)
+        c = pair[state["k"] % 2]
+        state["k"] += 1
+        c.call_chunks_submit(chunks)
+        if state["pending"] is not None:
+            state["rec"], state["log"] = state["pending"].call_chunks_collect(view=True)
+        state["pending"] = c
+
+    def drain():
+        if state["pending"] is not None:
+            state["rec"], state["log"] = state["pending"].call_chunks_collect(view=True)
+            state["pending"] = None
+        for c in pair:
+            c.records_wait()
 
     for _ in range(args.warmup):
         step()
-    ms_total = T.run(step, args.steps, after=ctx.records_wait)
+    drain()
+    ms_total = T.run(step, args.steps, after=drain, streams=streams)
     rec, log = state["rec"].copy(), state["log"]
     assert ctx.last_call_path() == 2, "the fused device path did not run"
-    k_ms, launches = kernel_breakdown(ctx, step)
+    # the same call, one context, each call collected before the next is enqueued (what hm_call_chunks alone gives)
+    sync_state = {}
+
+    def step_sync():
+        sync_state["rec"], sync_state["log"] = ctx.call_chunks(chunks, view=True, wait=False)
+
+    step_sync()
+    ms_sync = T.run(step_sync, args.steps, after=ctx.records_wait, streams=streams[:1]) / args.steps
+    assert list(sync_state["log"]) == list(log)
+    k_ms, launches = kernel_breakdown(ctx, step_sync)
     ctx.records_wait()
+    ctx_b.close()
+    ctx.set_stream(T.stream.cuda_stream)
     # ---- end to end: the worker's call on the decoder's own buffers ----
     bam = os.path.join(tmpdir, "contig.bam")
     t0 = time.perf_counter()
@@ -375,6 +420,10 @@ def leg_contig(args, T, ctx, d, params, chunks, tmpdir):
                         "exceptions written by its record-parse pass), page-locked once before the loop; records byte-identical to the "
                         "resident call's",
                 "decode_seconds_outside_timed_region": t_decode, "bam_write_seconds": t_write},
+        "value_one_context": {"value": aligned / (ms_sync * 1e-3), "unit": "bases/s", "ms_per_step": ms_sync,
+                              "call": "hm_call_chunks on one context, every call collected before the next is enqueued"},
+        "value_call": "hm_call_chunks_submit / hm_call_chunks_collect on two contexts that alternate, the next call enqueued before the "
+                      "previous is collected: how himut_b200/caller.py:call_region drives the device from decode group to decode group",
         "e2e_plain": {"value": aligned / (ms_plain * 1e-3), "unit": "bases/s", "h2d_bytes_per_step": int(batch.nbytes() + chunks.nbytes),
                       "ms_per_step": ms_plain, "call": "hm_call_batch: one quality byte per base + 2-bit bases (round 1's upload)"},
         "gpu_launches": int(launches * args.steps),
@@ -517,7 +566,7 @@ def leg_genome(args, T, lib, torch, rank, world, local_rank, stream):
         data = dict(zip(need, ex.map(lambda c: synth.generate(length[c], seed=seed_of[c], copy=False), need)))
     t_gen = time.perf_counter() - t0
     params = gtmodel.make_params(**gtmodel.DEFAULT_CALL_ARGS)
-    items, my_bases = [], 0
+    items, my_bases, streams = [], 0, []
     for r in mine:
         d = data[r.chrom]
         chunks_r = [(s, e) for _c, s, e in loci[r.chrom][r.lo:r.hi]]
@@ -531,11 +580,14 @@ def leg_genome(args, T, lib, torch, rank, world, local_rank, stream):
         a1 = (1 << 31) - 1 if r.hi == len(loci[r.chrom]) else chunks_r[-1][1]
         per = aligned_per_read(sub)
         my_bases += int(per[(sub.tstart >= a0) & (sub.tstart < a1)].sum())
-        # every run has a context of its own with its private stream: collecting run k waits for run k only, so its host
+        # every run has a context of its own with a stream of its own: collecting run k waits for run k only, so its host
         # part (counters, som_seen replay, record copy) overlaps the kernels of the runs behind it.  The timing events
-        # are device timestamps on the bench's stream: the first before anything is enqueued, the second after every
-        # context has been collected (T.run), barrier + synchronize on both sides.
+        # bracket all of them on the device (Timer.run: the streams wait for the opening event, the closing event waits
+        # for the streams), barrier + synchronize on both sides.
         ctx = lib.Context(local_rank)
+        st = torch.cuda.Stream()
+        ctx.set_stream(st.cuda_stream)
+        streams.append(st)
         ctx.set_params(params)
         ctx.set_site_sets()
         ctx.omit_restatements(True)
@@ -565,14 +617,14 @@ def leg_genome(args, T, lib, torch, rank, world, local_rank, stream):
     for _ in range(args.warmup):
         step()
     wait_all()
-    ms_res = T.run(step, args.steps, after=wait_all)
+    ms_res = T.run(step, args.steps, after=wait_all, streams=streams)
 
     def step_e2e():
         for it in items:
             it["ctx"].call_batch_compact(it["sub"], it["cq"], it["table"], view=True)
 
     step_e2e()
-    ms_e2e = T.run(step_e2e, args.steps)
+    ms_e2e = T.run(step_e2e, args.steps, streams=streams)
     h2d = sum(int(it["cq"].nbytes() + it["sub"].ops.nbytes + sum(a.nbytes for a in it["small"]) + it["table"].nbytes) for it in items)
     d2h = int(state["recs"]) * 76 + 256 * len(items)
     for it in items:
