@@ -349,7 +349,7 @@ def leg_contig(args, T, ctx, d, params, chunks, tmpdir):
         for c in pair:
             c.records_wait()
 
-    for _ in range(args.warmup):
+    for _ in range(2 * args.warmup + 4):  # each context sizes and page-locks its two record buffers in its first calls
         step()
     drain()
     ms_total = T.run(step, args.steps, after=drain, streams=streams)
