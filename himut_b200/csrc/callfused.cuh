@@ -202,14 +202,15 @@ __device__ __forceinline__ void call_pair_body(const DevBatch& b, const DevParam
                                                int32_t ts, int32_t te, int32_t qlen, uint32_t qstart, int mapq, uint8_t* pair_hap,
                                                uint8_t* read_counted, const uint64_t* seg_off, uint32_t* seg_cnt, uint32_t* seg_keys,
                                                uint32_t* seg_read) {
-  struct Ops { // address-space-specific loads
+  struct Ops { // address-space-specific loads; the shared window address is taken once
     const uint32_t* p;
+    uint32_t sbase;
     __device__ __forceinline__ uint32_t operator[](uint32_t k) const {
-      if (kShared) { uint32_t v; asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"((uint32_t)__cvta_generic_to_shared(p + k))); return v; }
+      if (kShared) { uint32_t v; asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(sbase + 4u * k)); return v; }
       return __ldg(p + k);
     }
   };
-  const Ops ops = {ops_any};
+  const Ops ops = {ops_any, kShared ? (uint32_t)__cvta_generic_to_shared(ops_any) : 0u};
 
   // walk 1, branch-free per op: identity tallies (bamlib.get_blast_sequence_identity), substitutions inside the chunk;
   // op prefixes to HBM for the op lists k_call_scan does not stage itself
@@ -218,14 +219,20 @@ __device__ __forceinline__ void call_pair_body(const DevBatch& b, const DevParam
   const bool long_ops = n > HC_MAX_OPS;
   uint32_t qq = qstart;
   const int32_t lo_t = ch.start - ts - 1, hi_t = ch.end - ts - 1; // candidate <=> lo_t <= t <= hi_t (tpos = ts + t + 1)
-  for (uint32_t k = 0; k < n; k++) {
-    const uint32_t w = ops[k];
-    const uint32_t kind = w & 3u, v = w >> 2;
-    if (long_ops) { b.op_t[o0 + k] = t; b.op_q[o0 + k] = qq; qq += (uint32_t)op_qry_len(w); }
-    const bool is_m = kind == HM_OP_MATCH, is_s = kind == HM_OP_SUB, is_i = kind == HM_OP_INS, is_d = kind == HM_OP_DEL;
-    nm += is_m ? (int)v : 0; ns += is_s; il += is_i ? (int)v : 0; dl += is_d ? (int)v : 0;
-    n_sub_in += (is_s && (v & 7u) != HM_BASE_N && (int32_t)t >= lo_t && (int32_t)t <= hi_t);
-    t += (is_m || is_d) ? v : (uint32_t)is_s;
+  for (uint32_t k0 = 0; k0 < n; k0 += 4) { // four ops per round: their loads go out together (a zero word is an empty match run)
+    uint32_t w4[4];
+#pragma unroll
+    for (uint32_t u = 0; u < 4; u++) w4[u] = k0 + u < n ? ops[k0 + u] : 0u;
+#pragma unroll
+    for (uint32_t u = 0; u < 4; u++) {
+      const uint32_t w = w4[u];
+      const uint32_t kind = w & 3u, v = w >> 2;
+      if (long_ops && k0 + u < n) { b.op_t[o0 + k0 + u] = t; b.op_q[o0 + k0 + u] = qq; qq += (uint32_t)op_qry_len(w); }
+      const bool is_m = kind == HM_OP_MATCH, is_s = kind == HM_OP_SUB, is_i = kind == HM_OP_INS, is_d = kind == HM_OP_DEL;
+      nm += is_m ? (int)v : 0; ns += is_s; il += is_i ? (int)v : 0; dl += is_d ? (int)v : 0;
+      n_sub_in += (is_s && (v & 7u) != HM_BASE_N && (int32_t)t >= lo_t && (int32_t)t <= hi_t);
+      t += (is_m || is_d) ? v : (uint32_t)is_s;
+    }
   }
 
   // read gates of caller.py:310-317 except the QV gate (k_call_scan has the quality sum), same order of evaluation
