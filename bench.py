@@ -580,48 +580,76 @@ def leg_genome(args, T, lib, torch, rank, world, local_rank, stream):
         a1 = (1 << 31) - 1 if r.hi == len(loci[r.chrom]) else chunks_r[-1][1]
         per = aligned_per_read(sub)
         my_bases += int(per[(sub.tstart >= a0) & (sub.tstart < a1)].sum())
-        # every run has a context of its own with a stream of its own: collecting run k waits for run k only, so its host
-        # part (counters, som_seen replay, record copy) overlaps the kernels of the runs behind it.  The timing events
-        # bracket all of them on the device (Timer.run: the streams wait for the opening event, the closing event waits
-        # for the streams), barrier + synchronize on both sides.
-        ctx = lib.Context(local_rank)
-        st = torch.cuda.Stream()
-        ctx.set_stream(st.cuda_stream)
-        streams.append(st)
-        ctx.set_params(params)
-        ctx.set_site_sets()
-        ctx.omit_restatements(True)
-        ctx.kernel_timing(False)
+        # every run has two contexts of its own (each with its stream and the run's batch resident): they alternate from
+        # step to step and the next step is enqueued before the previous one is collected, as himut_b200/caller.py drives
+        # a worker's two contexts from decode group to decode group — so the device goes from run to run and from step
+        # to step without waiting for the host, and collecting run k overlaps the kernels of the runs behind it.  The
+        # timing events bracket all of it on the device (Timer.run: the streams wait for the opening event, the closing
+        # event waits for the streams), barrier + synchronize on both sides.
         small = [getattr(sub, n) for n, _ in sub._FIELDS if n not in ("seq", "bq", "ops", "seq_off")]
         pinned = [cq.mask, cq.exc, cq.exc_off, sub.ops] + small
-        ctx.pin_arrays(pinned)
-        ctx.upload_compact(sub, cq)
-        items.append(dict(ctx=ctx, sub=sub, cq=cq, table=table, pinned=pinned, small=small, run=r))
-    state = {"log": np.zeros(15, np.int64), "recs": 0}
+        pair = []
+        for _k in range(2):
+            ctx = lib.Context(local_rank)
+            st = torch.cuda.Stream()
+            ctx.set_stream(st.cuda_stream)
+            streams.append(st)
+            ctx.set_params(params)
+            ctx.set_site_sets()
+            ctx.omit_restatements(True)
+            ctx.kernel_timing(False)
+            if not pair:
+                ctx.pin_arrays(pinned)
+            ctx.upload_compact(sub, cq)
+            pair.append(ctx)
+        items.append(dict(ctx=pair[0], pair=pair, sub=sub, cq=cq, table=table, pinned=pinned, small=small, run=r))
+    state = {"log": np.zeros(15, np.int64), "recs": 0, "k": 0, "pending": None}
 
-    def step():
-        # every run's device path is enqueued before the first is waited for: the GPU goes from run to run without the host
+    def collect(which):
         log, recs = np.zeros(15, np.int64), 0
         for it in items:
-            it["ctx"].call_chunks_submit(it["table"])
-        for it in items:
-            rec, l = it["ctx"].call_chunks_collect(view=True)
+            rec, l = it["pair"][which].call_chunks_collect(view=True)
             log += l
             recs += rec.size
         state["log"], state["recs"] = log, recs
 
-    def wait_all():
+    def step():
+        which = state["k"] % 2
+        state["k"] += 1
         for it in items:
-            it["ctx"].records_wait()
+            it["pair"][which].call_chunks_submit(it["table"])
+        if state["pending"] is not None:
+            collect(state["pending"])
+        state["pending"] = which
 
-    for _ in range(args.warmup):
+    def wait_all():
+        if state["pending"] is not None:
+            collect(state["pending"])
+            state["pending"] = None
+        for it in items:
+            for c in it["pair"]:
+                c.records_wait()
+
+    for _ in range(2 * args.warmup + 4):
         step()
     wait_all()
     ms_res = T.run(step, args.steps, after=wait_all, streams=streams)
 
     def step_e2e():
+        # host buffers -> device -> records, run by run; a run's kernels overlap the next run's upload (each run has its
+        # own context and stream), every step ends with all records of the step in host memory
+        prev = None
         for it in items:
-            it["ctx"].call_batch_compact(it["sub"], it["cq"], it["table"], view=True)
+            c = it["pair"][0]
+            c.upload_compact(it["sub"], it["cq"])
+            c.call_chunks_submit(it["table"])
+            if prev is not None:
+                prev.call_chunks_collect(view=True)
+            prev = c
+        if prev is not None:
+            prev.call_chunks_collect(view=True)
+        for it in items:
+            it["pair"][0].records_wait()
 
     step_e2e()
     ms_e2e = T.run(step_e2e, args.steps, streams=streams)
@@ -629,13 +657,15 @@ def leg_genome(args, T, lib, torch, rank, world, local_rank, stream):
     d2h = int(state["recs"]) * 76 + 256 * len(items)
     for it in items:
         it["ctx"].kernel_timing(True)
+    state["k"] = 0
     step()
     wait_all()
     launches = sum(it["ctx"].last_timing()[1] for it in items)
     for it in items:
         assert it["ctx"].last_call_path() == 2
         it["ctx"].unpin_arrays(it["pinned"])
-        it["ctx"].close()
+        for c in it["pair"]:
+            c.close()
     dev = torch.device("cuda", local_rank)
     t = torch.tensor([ms_res, ms_e2e], device=dev, dtype=torch.float64)
     s = torch.tensor([float(my_bases), float(state["recs"]), float(h2d), float(d2h), float(launches), float(len(items))], device=dev,
@@ -652,7 +682,8 @@ def leg_genome(args, T, lib, torch, rank, world, local_rank, stream):
         "value": bases * args.steps / (float(t[0]) * 1e-3), "ms_per_step": float(t[0]) / args.steps,
         "e2e": {"value": bases * args.steps / (float(t[1]) * 1e-3), "unit": "bases/s", "ms_per_step": float(t[1]) / args.steps,
                 "h2d_bytes_per_step": int(s[2]), "d2h_bytes_per_step": int(s[3]),
-                "call": "hm_call_batch_compact per chunk run, host buffers in the decoder's layout (no base stream, qualities as modal "
+                "call": "hm_upload_batch_compact + hm_call_chunks_submit / collect per chunk run (a run's kernels overlap the next run's "
+                        "upload), host buffers in the decoder's layout (no base stream, qualities as modal "
                         "bitmap + exceptions — here built by hm_bq_compact_build from the generated batch, the same bytes the decoder's "
                         "parse pass writes: tests/test_bamdec.py), page-locked before the loop"},
         "aligned_bases_per_step": int(bases), "site_records_per_step": int(s[1]), "runs": len(runs), "runs_this_rank": len(items),
