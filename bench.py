@@ -705,7 +705,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--contig-mb", type=int, default=64)
-    ap.add_argument("--genome-mb", type=int, default=388, help="size of the scaled configs[2] genome (3.1 Gb / 8)")
+    ap.add_argument("--genome-mb", type=int, default=776, help="size of the scaled configs[2] genome (3.1 Gb / 4)")
     ap.add_argument("--seed", type=int, default=20260101)
     ap.add_argument("--cpu-chunks", type=int, default=25)
     ap.add_argument("--no-cpu-baseline", action="store_true")
