@@ -672,7 +672,12 @@ def leg_genome(args, T, lib, torch, rank, world, local_rank, stream):
                      dtype=torch.float64)
     mx = torch.tensor([float(my_bases)], device=dev, dtype=torch.float64)
     logt = torch.tensor(state["log"], device=dev)
+    per_rank = [[ms_res / args.steps, ms_e2e / args.steps, float(my_bases), float(state["recs"]) * 76.0]]
     if world > 1:
+        mine_t = torch.tensor(per_rank[0], device=dev, dtype=torch.float64)
+        allt = [torch.zeros_like(mine_t) for _ in range(world)]
+        T.dist.all_gather(allt, mine_t)
+        per_rank = [[float(v) for v in x.tolist()] for x in allt]
         T.dist.all_reduce(t, op=T.dist.ReduceOp.MAX)
         T.dist.all_reduce(s, op=T.dist.ReduceOp.SUM)
         T.dist.all_reduce(mx, op=T.dist.ReduceOp.MAX)
@@ -691,6 +696,9 @@ def leg_genome(args, T, lib, torch, rank, world, local_rank, stream):
         "imbalance": {"max_over_mean_bases_per_rank": float(mx[0]) / (bases / world) if bases else None,
                       "planned_max_over_mean_weight": genome.imbalance(runs, world)},
         "gpu_launches_per_step": int(s[4]), "contexts": int(s[5]), "generate_seconds_this_rank": t_gen,
+        "per_rank": {"ms_per_step": [round(x[0], 4) for x in per_rank], "e2e_ms_per_step": [round(x[1], 4) for x in per_rank],
+                     "aligned_bases": [int(x[2]) for x in per_rank], "record_bytes_d2h_per_step": [int(x[3]) for x in per_rank],
+                     "record_d2h_gbs_if_it_were_the_only_limit": [round(x[3] / (x[0] * 1e-3) / 1e9, 2) if x[0] else None for x in per_rank]},
         "log_counters_sum": [int(v) for v in logt.tolist()],
         "log_note": "summed over runs: a candidate on the one position two runs of a split contig share is counted by both (the "
                     "product path, himut_b200/genome.py, replays som_seen over it at the merge; tests/test_zz_gpu_genome.py)",
