@@ -26,6 +26,7 @@
 #include "normcounts.cuh"
 #include "normfast.cuh"
 #include "callfused.cuh"
+#include "normbits.cuh"
 
 #define HM_BOUNDARY_CAP_DEFAULT 65536   // boundary records the device list holds (HIMUT_B200_BOUNDARY_CAP overrides: tests)
 #define HM_BOUNDARY_FIRST 2048  // ... of which this many travel with the counters
@@ -117,6 +118,12 @@ struct hm_ctx {
   size_t h_geom_cap = 0;
   struct Pending { bool active = false; std::vector<hm_chunk> chunks; uint64_t site_cap = 0; size_t bcap = 0; int n_launched = 0, parity = 0; bool omit = false; } pend;
   DevBuf b_cgeom, b_seg_keys, b_seg_read, b_keys_tmp, b_gscratch, b_czero, b_first_pair, b_tiles, b_site_valid, b_pair_c;
+  // bit-vector normcounts path (normbits.cuh)
+  std::vector<uint32_t> h_cw_off;           // per read: first word of its cal bit vector
+  uint64_t n_cw = 0;                        // words of all cal bit vectors (>= 2^32: the path is not used)
+  uint16_t cert_thr[256];                   // smallest callable count that certifies a pure position of depth n (0xffff: none)
+  uint64_t packed_pos = 0;                  // positions b_ref2 / b_tri8 cover for the reference now in b_ref (0: not packed)
+  DevBuf b_cw_off, b_calw, b_impure, b_ref2, b_tri8, b_thr, b_span_off;
 };
 
 namespace {
@@ -184,6 +191,7 @@ void make_norm_cert(hm_ctx* ctx) {
   const hm_params& p = ctx->params;
   NormCert& c = ctx->cert;
   memset(&c, 0, sizeof(c));
+  for (int n = 0; n < 256; n++) ctx->cert_thr[n] = 0xffff;
   const double L2 = 0.30102999566398119521; // log10(2)
   const double f1 = -p.lut_hom[1];
   bool ok = p.min_bq >= 1 && p.min_bq <= 128 && p.min_gq <= 99 && f1 > 0.0 && f1 < 1.0;
@@ -208,6 +216,24 @@ void make_norm_cert(hm_ctx* ctx) {
   c.ia_x = (long long)ceil(c.a_x * 1048576.0);
   c.i_need = (long long)ceil((c.need - c.c_oth) * 1048576.0);
   c.enabled = 1;
+  // The bit-vector pass (normbits.cuh) knows the depth n and the callable count cal of a pure position, not the sum of
+  // its qualities; every callable base has BQ >= min_bq and every other base BQ >= 1, so s1 >= min_bq cal + (n - cal),
+  // and the left side of the test above only grows with s1.  thr[n] = the smallest cal that passes it, made
+  // non-decreasing in n because the kernel looks it up with an upper bound of n.
+  uint16_t run = 0;
+  for (int n = 0; n < 256; n++) {
+    uint16_t t = 0xffff;
+    if (n >= c.n_min) {
+      for (int cal = 0; cal <= n; cal++) {
+        const long long s1 = (long long)p.min_bq * cal + (n - cal);
+        const long long x = std::min(254ll * n, 255ll * n - s1);
+        if (s1 * c.ia_bq - x * c.ia_x >= c.i_need) { t = (uint16_t)cal; break; }
+      }
+      if (t < run) t = run;
+      run = t;
+    }
+    ctx->cert_thr[n] = t;
+  }
 }
 
 // The record copies of an asynchronous call are enqueued late, behind the *next* call's sort (past k_read_scan, the
@@ -324,7 +350,8 @@ void hm_destroy(hm_ctx* ctx) {
                     &ctx->b_hpos, &ctx->b_href, &ctx->b_halt, &ctx->b_hbit, &ctx->b_set_off, &ctx->b_chunks,
                     &ctx->b_pair_off, &ctx->b_pair_hap, &ctx->b_qseen, &ctx->b_keys, &ctx->b_keys_sorted, &ctx->b_cub,
                     &ctx->b_records, &ctx->b_counters, &ctx->b_ref, &ctx->b_norm_out, &ctx->b_lut, &ctx->b_tile_off, &ctx->b_agg, &ctx->b_geom, &ctx->b_bidx, &ctx->b_brecs, &ctx->b_sites, &ctx->b_koff, &ctx->b_tile_info, &ctx->b_edge_counts, &ctx->b_edge_hpos, &ctx->b_edge_href, &ctx->b_bqmask, &ctx->b_bqexc, &ctx->b_bqexc_off,
-                    &ctx->b_cgeom, &ctx->b_seg_keys, &ctx->b_seg_read, &ctx->b_keys_tmp, &ctx->b_gscratch, &ctx->b_czero, &ctx->b_first_pair, &ctx->b_tiles, &ctx->b_site_valid, &ctx->b_pair_c};
+                    &ctx->b_cgeom, &ctx->b_seg_keys, &ctx->b_seg_read, &ctx->b_keys_tmp, &ctx->b_gscratch, &ctx->b_czero, &ctx->b_first_pair, &ctx->b_tiles, &ctx->b_site_valid, &ctx->b_pair_c,
+                    &ctx->b_cw_off, &ctx->b_calw, &ctx->b_impure, &ctx->b_ref2, &ctx->b_tri8, &ctx->b_thr, &ctx->b_span_off};
   for (DevBuf* b : bufs) b->release();
   if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
   if (ctx->h_cnt_pin) cudaFreeHost(ctx->h_cnt_pin);
@@ -448,7 +475,8 @@ static int upload_batch_impl(hm_ctx* ctx, const hm_read_batch* b, const hm_bq_co
   // structural validation (cheap, O(reads)); the kernels binary-search on these invariants
   ctx->h_pmax.resize(n);
   ctx->h_tix_off.resize(n + 1);
-  uint64_t n_tix = 0;
+  ctx->h_cw_off.resize(n + 1);
+  uint64_t n_tix = 0, n_cw = 0;
   int32_t run = INT32_MIN;
   uint32_t max_q = 0;
   for (uint64_t r = 0; r < n; r++) {
@@ -463,6 +491,8 @@ static int upload_batch_impl(hm_ctx* ctx, const hm_read_batch* b, const hm_bq_co
     ctx->h_pmax[r] = run;
     ctx->h_tix_off[r] = (uint32_t)n_tix;
     n_tix += (uint64_t)((b->tend[r] >> 11) - (b->tstart[r] >> 11) + 1);
+    ctx->h_cw_off[r] = (uint32_t)n_cw;
+    if (b->tend[r] > b->tstart[r] && b->tstart[r] >= 0) n_cw += (uint64_t)(((b->tend[r] - 1) >> 5) - (b->tstart[r] >> 5) + 1);
     if (b->qname_id[r] > max_q) max_q = b->qname_id[r];
   }
   ctx->max_qname_id = max_q;
@@ -503,6 +533,9 @@ static int upload_batch_impl(hm_ctx* ctx, const hm_read_batch* b, const hm_bq_co
   ctx->n_tix = n_tix;
   if ((rc = upload(ctx, ctx->b_pmax, ctx->h_pmax.data(), n))) return rc;
   if ((rc = upload(ctx, ctx->b_tix_off, ctx->h_tix_off.data(), n + 1))) return rc;
+  ctx->h_cw_off[n] = (uint32_t)n_cw;
+  ctx->n_cw = n_cw;
+  if (n_cw < (1ull << 32) && (rc = upload(ctx, ctx->b_cw_off, ctx->h_cw_off.data(), n + 1))) return rc;
   const size_t no = (size_t)b->n_ops_total;
   CU(ctx->b_op_t.ensure(no * 4 + 16)); CU(ctx->b_op_q.ensure(no * 4 + 16)); CU(ctx->b_mm.ensure(no * 4 + 16));
   CU(ctx->b_bq_total.ensure(n * 8 + 16)); CU(ctx->b_n_match.ensure(n * 4 + 16)); CU(ctx->b_n_sub.ensure(n * 4 + 16));
@@ -1250,6 +1283,7 @@ int hm_set_reference(hm_ctx* ctx, const uint8_t* refseq, size_t ref_len) {
   if (!ctx || (!refseq && ref_len)) return HM_ERR_ARG;
   CU(cudaSetDevice(ctx->device));
   ctx->ref_len = 0;
+  ctx->packed_pos = 0;
   int rc = upload(ctx, ctx->b_ref, refseq, ref_len);
   if (rc) return rc;
   CU(cudaStreamSynchronize(ctx->stream));
@@ -1265,6 +1299,7 @@ int hm_ref_tricounts(hm_ctx* ctx, const uint8_t* refseq, size_t ref_len, int64_t
   t_reset(ctx);
   int rc = upload(ctx, ctx->b_ref, refseq, ref_len);
   ctx->ref_len = 0;
+  ctx->packed_pos = 0;
   if (rc) return rc;
   CU(ctx->b_norm_out.ensure(sizeof(NormOut)));
   CU(cudaMemsetAsync(ctx->b_norm_out.p, 0, sizeof(NormOut), ctx->stream));
@@ -1405,8 +1440,49 @@ static int hm_normcounts_impl(hm_ctx* ctx, const uint8_t* refseq, size_t ref_len
   if (refseq) { // per-call reference: replaces whatever hm_set_reference left
     if ((rc = upload(ctx, ctx->b_ref, refseq, ref_len))) return rc;
     ctx->ref_len = 0;
+    ctx->packed_pos = 0;
   }
-  if ((rc = launch_read_scan(ctx))) return rc;
+  // which pass runs in front of the exact pass: bit vectors (normbits.cuh) unless the parameters are outside the
+  // certified domain or an earlier kernel is asked for (A/B: HIMUT_B200_NORM_V1 / _V2 single pass, _V3 byte tiles)
+  const bool use_v1 = getenv("HIMUT_B200_NORM_V1") != nullptr;
+  const bool use_v2 = getenv("HIMUT_B200_NORM_V2") != nullptr;
+  const bool use_v3 = getenv("HIMUT_B200_NORM_V3") != nullptr;
+  bool use_bits = !use_v1 && !use_v2 && !use_v3 && ctx->cert.enabled && ctx->n_reads > 0 && ctx->n_cw < (1ull << 32) && n_pairs > 0;
+  std::vector<uint64_t> span_off(n_chunks + 1, 0);
+  int64_t max_end = 0;
+  for (size_t i = 0; i < n_chunks; i++) {
+    const int64_t span = (int64_t)chunks[i].end - (int64_t)chunks[i].start;
+    if (chunks[i].start < 0) use_bits = false;
+    span_off[i + 1] = span_off[i] + (span > 0 && chunks[i].start >= 0 ? (uint64_t)(((chunks[i].end - 1) >> 10) - (chunks[i].start >> 10) + 1) : 0);
+    max_end = std::max<int64_t>(max_end, chunks[i].end);
+  }
+  const uint64_t n_spans = span_off[n_chunks];
+  uint64_t imp_words = 0;
+  if (use_bits) {
+    const uint64_t need_pos = std::max<uint64_t>(std::max<uint64_t>((uint64_t)ref_len, (uint64_t)std::max(ctx->h_pmax.back(), 0) + 2), (uint64_t)max_end);
+    const uint64_t n_pos = (need_pos + 1023) / 1024 * 1024 + 1024;
+    if (ctx->packed_pos < n_pos) {
+      CU(ctx->b_ref2.ensure(n_pos / 4 + 16));
+      CU(ctx->b_tri8.ensure(n_pos + 16));
+      t_begin(ctx, "k_ref_pack");
+      k_ref_pack<<<(unsigned)((n_pos / 16 + 255) / 256), 256, 0, ctx->stream>>>(ctx->b_ref.as<uint8_t>(), (uint64_t)ref_len, n_pos, ctx->b_ref2.as<uint32_t>(),
+                                                                             ctx->b_tri8.as<uint8_t>());
+      t_end(ctx);
+      CU(cudaGetLastError());
+      ctx->packed_pos = refseq ? 0 : n_pos; // a per-call reference is packed per call
+    }
+    imp_words = n_pos / 32;
+    CU(ctx->b_impure.ensure(imp_words * 4 + 16));
+    CU(cudaMemsetAsync(ctx->b_impure.p, 0, imp_words * 4, ctx->stream));
+    CU(ctx->b_calw.ensure((size_t)ctx->n_cw * 4 + 16));
+    if ((rc = upload(ctx, ctx->b_thr, ctx->cert_thr, 256))) return rc;
+    if ((rc = upload(ctx, ctx->b_span_off, span_off.data(), span_off.size()))) return rc;
+    t_begin(ctx, "k_norm_prep");
+    k_norm_prep<<<(unsigned)((ctx->n_reads + NB_PREP_WARPS - 1) / NB_PREP_WARPS), 32 * NB_PREP_WARPS, sizeof(PrepWarp) * NB_PREP_WARPS, ctx->stream>>>(
+        ctx->db, ctx->dp, ctx->b_ref2.as<uint32_t>(), ctx->b_cw_off.as<uint32_t>(), ctx->b_calw.as<uint32_t>(), ctx->b_impure.as<uint32_t>(), imp_words);
+    t_end(ctx);
+    CU(cudaGetLastError());
+  } else if ((rc = launch_read_scan(ctx))) return rc;
   CU(ctx->b_norm_out.ensure(sizeof(NormOut)));
   CU(ctx->b_counters.ensure(64));
   CU(ctx->b_qseen.ensure((size_t)ctx->max_qname_id + 1));
@@ -1425,8 +1501,6 @@ static int hm_normcounts_impl(hm_ctx* ctx, const uint8_t* refseq, size_t ref_len
                                                  ctx->b_qseen.as<uint8_t>());
     t_end(ctx);
     CU(cudaGetLastError());
-    const bool use_v1 = getenv("HIMUT_B200_NORM_V1") != nullptr;
-    const bool use_v2 = getenv("HIMUT_B200_NORM_V2") != nullptr;
     int n_sm = 148;
     cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, ctx->device);
     if (use_v1) {
@@ -1466,6 +1540,30 @@ static int hm_normcounts_impl(hm_ctx* ctx, const uint8_t* refseq, size_t ref_len
       unsigned long long site_cap = std::max<unsigned long long>(1ull << 16, total_span / 16);
       if (const char* g = getenv("HIMUT_B200_NORM_SITE_CAP")) site_cap = std::max(1ll, atoll(g));
       unsigned long long n_sites = 0;
+      if (use_bits) {
+        const double md = ctx->params.md_threshold;
+        const int md_k = !(md == md) ? 256 : md < 0.0 ? 0 : md >= 255.0 ? 256 : (int)floor(md) + 1; // depth >= md_k <=> depth > md_threshold
+        const unsigned bgrid = (unsigned)std::min<uint64_t>((n_spans + NB_BITS_WARPS - 1) / NB_BITS_WARPS, (uint64_t)n_sm * 8);
+        for (int attempt = 0; attempt < 2 && n_spans; attempt++) {
+          CU(ctx->b_sites.ensure(site_cap * 8));
+          if (attempt) { // the list overflowed: start over with the exact size
+            CU(cudaMemsetAsync(ctx->b_norm_out.p, 0, sizeof(NormOut), ctx->stream));
+            CU(cudaMemsetAsync(d_nsites, 0, 8, ctx->stream));
+          }
+          t_begin(ctx, "k_norm_bits");
+          k_norm_bits<<<bgrid, 32 * NB_BITS_WARPS, 0, ctx->stream>>>(
+              ctx->db, ctx->dp, ctx->b_thr.as<uint16_t>(), (int)ctx->cert.n_min, md_k, ctx->b_chunks.as<hm_chunk>(), (uint32_t)n_chunks,
+              ctx->b_pair_off.as<uint64_t>(), ctx->b_pair_hap.as<uint8_t>(), ctx->b_span_off.as<uint64_t>(), n_spans, ctx->b_cw_off.as<uint32_t>(),
+              ctx->b_calw.as<uint32_t>(), ctx->b_impure.as<uint32_t>(), ctx->b_tri8.as<uint8_t>(), ctx->b_norm_out.as<NormOut>(),
+              ctx->b_sites.as<unsigned long long>(), site_cap, d_nsites);
+          t_end(ctx);
+          CU(cudaGetLastError());
+          CU(cudaMemcpyAsync(&n_sites, d_nsites, 8, cudaMemcpyDeviceToHost, ctx->stream));
+          CU(cudaStreamSynchronize(ctx->stream));
+          if (n_sites <= site_cap) break;
+          site_cap = n_sites;
+        }
+      } else {
       CU(ctx->b_tix.ensure((size_t)ctx->n_tix * 16 + 16));
       CU(ctx->b_tile_info.ensure((size_t)n_tiles_fast * 16 + 16));
       t_begin(ctx, "k_tile_index");
@@ -1494,6 +1592,7 @@ static int hm_normcounts_impl(hm_ctx* ctx, const uint8_t* refseq, size_t ref_len
         CU(cudaStreamSynchronize(ctx->stream));
         if (n_sites <= site_cap) break;
         site_cap = n_sites;
+      }
       }
       ctx->last_norm_sites = n_sites;
       const bool by_site = getenv("HIMUT_B200_ENTRIES_BY_SITE") != nullptr; // thread-per-(site, read) gather (A/B)

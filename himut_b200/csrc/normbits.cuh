@@ -1,0 +1,522 @@
+// normbits.cuh — the callable-base half of `himut normcounts` as bit vectors (sm_100a); replaces the byte-per-base tile
+// kernel k_norm_fast (normfast.cuh) as the integer pass in front of the exact pass.
+//
+// The reference asks two things of every aligned base (normcounts.py:65-110, 292-314): "does this read count here"
+// (matched base, BQ >= min_bq, no mismatch within the window of its block, not trimmed) and "what does the pileup
+// column look like" (gtlib.get_germ_gt over every base of the column).  At a *pure* position — every primary read that
+// covers it shows the FASTA base through a plain cs match — the second question has a certified answer that needs the
+// depth n and a lower bound of the column's quality sum only (NormCert, normfast.cuh).  And a lower bound is at hand
+// without touching a single quality byte again: every counted base has BQ >= min_bq, every other base has BQ >= 1, so
+//     sum BQ  >=  min_bq * callable + (n - callable).
+// So each read is turned ONCE, by the warp that streams its qualities anyway, into one bit per reference position
+// ("this read counts here"), and the per-position work becomes adding bit vectors:
+//
+//   k_ref_pack    the contig as 2-bit codes + the trinucleotide bin of every position (once per reference).
+//   k_norm_prep   one warp per read (replaces k_read_scan on this path and does all it does): cs op prefix scan,
+//                 mismatch list, identity / QV gates, the whole-read quality sum — and, from the same 16-byte quality
+//                 words, the bit "BQ >= min_bq" per query base.  Then per 32 reference positions of the read: the
+//                 bits of the match runs moved to reference coordinates, minus trimmed and window-blocked positions
+//                 (get_trimmed_range / get_mismatch_range, bamlib.py:222-258) -> cal[read][word].  Positions where the
+//                 read is anything but a plain match of the FASTA base (substitution, deletion, the base an insertion
+//                 precedes, a match run base that differs from the FASTA, BQ 0, op lists too long to stage) are set in
+//                 a per-contig `impure` bitmap.
+//   k_norm_bits   one warp per 1024 reference positions, lane = 32 positions.  The covering reads in file order: the
+//                 coverage word and the cal word of each are added into bit-sliced counters (carry-save adders, three
+//                 logic ops per read and counter); depth, callable count and haplotype tallies of all 32 positions of
+//                 a lane never leave 8 + 8 (+ 16) registers.  Then, bit-parallel: certified -> the cascade's depth /
+//                 ref-count gates and the 33-bin tallies (normcounts.py:317-400); impure or not certified -> the site
+//                 list of the exact pass (k_norm_entries_by_read / k_norm_reduce, normfast.cuh), which evaluates the
+//                 position with the reference's own ordered fp64 arithmetic.  Both passes add into the same tallies.
+//
+// The verdict at a certified position is the exact verdict (tests/test_norm_cert.py holds the bound against the
+// reference's gtlib); everything else is evaluated exactly, so the result is bit-identical to genotyping every column.
+#pragma once
+#include "normfast.cuh"
+
+#define NB_OPS 160u                 // ops of a read staged in shared memory (more: the read's span goes to the exact pass)
+#define NB_QWORDS 1024u             // 32 768 query bases of "BQ >= min_bq" bits per warp (longer reads: exact pass)
+#define NB_PREP_WARPS 4
+#define NB_SPAN 1024                // reference positions per warp of k_norm_bits
+#define NB_BITS_WARPS 4
+
+struct __align__(16) PrepWarp {
+  uint32_t qg[NB_QWORDS + 4];       // bit q: BQ of query base q >= min_bq
+  uint32_t w[NB_OPS], t[NB_OPS], q[NB_OPS];
+  int32_t mm[NB_OPS];
+};
+
+// ============================================================================ k_ref_pack
+// ref2: 16 positions per word, HM base codes (A 0, T 1, G 2, C 3; anything else 0); tri8: get_tri_context bin
+// (normcounts.py:49-62) of a position whose base is upper-case A/C/G/T, else 255 (normcounts.py:320 skips it).
+// Both cover n_pos >= ref_len positions (multiple of 32); past the reference: 0 / 255.
+__global__ void __launch_bounds__(256) k_ref_pack(const uint8_t* refseq, uint64_t ref_len, uint64_t n_pos, uint32_t* ref2, uint8_t* tri8) {
+  const uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; // one thread per 16 positions
+  if (w * 16 >= n_pos) return;
+  uint32_t code = 0;
+  uint32_t tb[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
+#pragma unroll
+  for (int k = 0; k < 16; k++) {
+    const uint64_t pos = w * 16 + k;
+    if (pos >= ref_len) continue;
+    const uint8_t ch = __ldg(refseq + pos);
+    const int c = ch == 'A' ? 0 : ch == 'T' ? 1 : ch == 'G' ? 2 : ch == 'C' ? 3 : -1;
+    if (c < 0) continue;
+    code |= (uint32_t)c << (2 * k);
+    const uint32_t tri = (uint32_t)tri_bin_dev(refseq, ref_len, (int64_t)pos);
+    tb[k >> 2] = (tb[k >> 2] & ~(0xffu << (8 * (k & 3)))) | (tri << (8 * (k & 3)));
+  }
+  ref2[w] = code;
+  reinterpret_cast<uint4*>(tri8)[w] = make_uint4(tb[0], tb[1], tb[2], tb[3]);
+}
+
+__device__ __forceinline__ uint32_t low_mask(int k) { return k >= 32 ? 0xffffffffu : (k <= 0 ? 0u : ((1u << k) - 1u)); }
+__device__ __forceinline__ void mark_impure(uint32_t* impure, uint64_t imp_words, int64_t pos) {
+  if (pos >= 0 && (uint64_t)(pos >> 5) < imp_words) atomicOr(impure + (pos >> 5), 1u << (pos & 31));
+}
+__device__ __forceinline__ void mark_impure_range(uint32_t* impure, uint64_t imp_words, int64_t lo, int64_t hi) { // [lo, hi)
+  if (lo < 0) lo = 0;
+  while (lo < hi) {
+    const int64_t wi = lo >> 5;
+    const int b0 = (int)(lo & 31), n = (int)min((int64_t)(32 - b0), hi - lo);
+    if ((uint64_t)wi < imp_words) atomicOr(impure + wi, low_mask(n) << b0);
+    lo += n;
+  }
+}
+
+// ============================================================================ k_norm_prep
+// One warp per read.  Writes everything k_read_scan writes (op_t, op_q, mm_pos, the totals, the gate byte), plus the
+// read's cal words at calw[cw_off[r] ...) — word j holds reference positions 32 * ((tstart >> 5) + j) ... + 31 — and
+// the read's contribution to the impure bitmap.  Secondary records are skipped by every consumer: they get neither.
+__global__ void __launch_bounds__(32 * NB_PREP_WARPS) k_norm_prep(DevBatch b, DevParams p, const uint32_t* ref2, const uint32_t* cw_off,
+                                                                   uint32_t* calw, uint32_t* impure, uint64_t imp_words) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  const uint64_t r = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (r >= b.n_reads) return;
+  PrepWarp* S = reinterpret_cast<PrepWarp*>(smem_raw) + (threadIdx.x >> 5);
+  const uint64_t o0 = __ldg(b.op_off + r);
+  const uint32_t nops = __ldg(b.n_ops + r);
+  const int32_t ts = __ldg(b.tstart + r), te = __ldg(b.tend + r);
+  const int32_t qlen = __ldg(b.qlen + r);
+  const uint32_t qstart = (uint32_t)__ldg(b.qstart + r);
+  const bool primary = !(__ldg(b.flags + r) & HM_READ_SECONDARY);
+  const uint8_t* bq = b.bq + __ldg(b.bq_off + r);
+
+  // ---- phase 1: op prefix scan (k_read_scan), ops staged, non-match ops -> impure
+  uint32_t t_carry = 0, q_carry = qstart;
+  int mm_base = 0, nm = 0, ns = 0, il = 0, dl = 0;
+  for (uint32_t base = 0; base < nops; base += 32) {
+    const uint32_t k = base + lane;
+    const bool valid = k < nops;
+    const uint32_t w = valid ? __ldg(b.ops + o0 + k) : 0u;
+    const uint32_t kind = w & 3u, v = w >> 2;
+    const uint32_t rl = (uint32_t)op_ref_len(w), al = (uint32_t)op_qry_len(w);
+    uint32_t rs = rl, qs = al;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t a = __shfl_up_sync(HM_FULL, rs, d), c = __shfl_up_sync(HM_FULL, qs, d);
+      if (lane >= d) { rs += a; qs += c; }
+    }
+    const uint32_t t_ex = t_carry + rs - rl, q_ex = q_carry + qs - al;
+    if (valid) {
+      b.op_t[o0 + k] = t_ex; b.op_q[o0 + k] = q_ex;
+      if (k < NB_OPS) { S->w[k] = w; S->t[k] = t_ex; S->q[k] = q_ex; }
+    }
+    const bool is_mm = valid && ((kind == HM_OP_SUB && (v & 7u) != HM_BASE_N) || kind == HM_OP_INS || kind == HM_OP_DEL);
+    const uint32_t bal = __ballot_sync(HM_FULL, is_mm);
+    if (is_mm) {
+      const uint32_t at = (uint32_t)mm_base + __popc(bal & ((1u << lane) - 1u));
+      b.mm_pos[o0 + at] = ts + (int32_t)t_ex + 1;
+      if (at < NB_OPS) S->mm[at] = (int32_t)t_ex + 1; // read-relative, 1-based as the list is
+    }
+    mm_base += __popc(bal);
+    if (valid) {
+      if (kind == HM_OP_MATCH) nm += (int)v;
+      else if (kind == HM_OP_SUB) ns += 1;
+      else if (kind == HM_OP_INS) il += (int)v;
+      else dl += (int)v;
+      if (primary && kind != HM_OP_MATCH) { // update_allelecounts: a substituted / deleted base, or the base an insertion precedes
+        const int64_t at = (int64_t)ts + t_ex;
+        if (kind == HM_OP_DEL) mark_impure_range(impure, imp_words, at, at + v);
+        else mark_impure(impure, imp_words, at);
+      }
+    }
+    t_carry += __shfl_sync(HM_FULL, rs, 31);
+    q_carry += __shfl_sync(HM_FULL, qs, 31);
+  }
+  nm = __reduce_add_sync(HM_FULL, nm);
+  ns = __reduce_add_sync(HM_FULL, ns);
+  il = __reduce_add_sync(HM_FULL, il);
+  dl = __reduce_add_sync(HM_FULL, dl);
+
+  // ---- phase 2: the quality stream once — whole-read sum (np.mean is an exact integer sum divided once) and one
+  // bit per base: BQ >= min_bq
+  const bool fits = (uint32_t)qlen <= NB_QWORDS * 32u;
+  const uint32_t kge = (uint32_t)(128 - p.min_bq) * 0x01010101u; // byte >= min_bq  <=>  bit 7 of ((byte & 0x7f) + 128 - min_bq) | byte
+  const uint4* q4 = reinterpret_cast<const uint4*>(bq);
+  const uint32_t n16 = ((uint32_t)qlen + 15u) >> 4;
+  uint16_t* qg16 = reinterpret_cast<uint16_t*>(S->qg);
+  uint32_t acc = 0, zacc = 0;
+  auto one_word = [&](uint4 v, uint32_t i) {
+    uint32_t wv[4] = {v.x, v.y, v.z, v.w};
+    const uint32_t g0 = i << 4;
+    uint32_t live = 0xffffu;
+    if (g0 + 16u > (uint32_t)qlen) { // padding bytes are not part of the read
+      const uint32_t keep = (uint32_t)qlen - g0; // 1 .. 15
+      live = (1u << keep) - 1u;
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const int kb = (int)keep - 4 * j;
+        wv[j] = kb >= 4 ? wv[j] : kb <= 0 ? 0u : (wv[j] & ((1u << (8 * kb)) - 1u));
+      }
+    }
+    uint32_t bits = 0, zero = 0;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      acc = sum4(wv[j], acc);
+      const uint32_t ge = ((((wv[j] & 0x7f7f7f7fu) + kge) | wv[j]) >> 7) & 0x01010101u;
+      bits |= (((ge * 0x00204081u) >> 21) & 15u) << (4 * j);
+      const uint32_t nz = ((((wv[j] & 0x7f7f7f7fu) + 0x7f7f7f7fu) | wv[j]) >> 7) & 0x01010101u; // byte != 0
+      zero |= ((((nz ^ 0x01010101u) * 0x00204081u) >> 21) & 15u) << (4 * j);
+    }
+    zacc |= zero & live;
+    if (fits) qg16[i] = (uint16_t)(bits & live);
+  };
+  {
+    uint32_t i = (uint32_t)lane;
+    for (; i + 96 < n16; i += 128) {
+      const uint4 a0 = ldg_stream16(q4 + i), a1 = ldg_stream16(q4 + i + 32), a2 = ldg_stream16(q4 + i + 64), a3 = ldg_stream16(q4 + i + 96);
+      one_word(a0, i); one_word(a1, i + 32); one_word(a2, i + 64); one_word(a3, i + 96);
+    }
+    for (; i < n16; i += 32) one_word(ldg_stream16(q4 + i), i);
+  }
+  if (fits) { // the words the funnel shifts below may touch past the last base
+    const uint32_t h0 = n16, h1 = min(((n16 + 1u) & ~1u) + 4u, (NB_QWORDS + 4u) * 2u);
+    for (uint32_t i = h0 + (uint32_t)lane; i < h1; i += 32) qg16[i] = 0;
+  }
+  unsigned long long tot = acc;
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) tot += __shfl_xor_sync(HM_FULL, tot, d);
+  const bool has_zero = __any_sync(HM_FULL, zacc != 0u);
+  if (lane == 0) {
+    b.bq_total[r] = tot;
+    b.n_match[r] = nm; b.n_sub[r] = ns; b.ins_len[r] = il; b.del_len[r] = dl; b.n_mm[r] = mm_base;
+    bool ok = true; // caller.py:310-317 / normcounts.py:302-309, in order
+    const double qv = __ddiv_rn((double)tot, (double)qlen);
+    if (qv < (double)p.min_qv) ok = false;
+    if ((int)__ldg(b.mapq + r) < p.min_mapq) ok = false;
+    const double ident = __ddiv_rn((double)nm, (double)(nm + ns + il + dl));
+    if (ident < p.min_sequence_identity) ok = false;
+    if (!(p.qlen_lower_limit < qlen && qlen < p.qlen_upper_limit)) ok = false;
+    b.gate[r] = ok ? 1 : 0;
+  }
+  if (!primary || te <= ts) return;
+  __syncwarp();
+
+  // ---- phase 3: cal words in reference coordinates
+  const uint32_t nw = (uint32_t)(((te - 1) >> 5) - (ts >> 5) + 1);
+  uint32_t* out = calw + __ldg(cw_off + r);
+  // a read this kernel cannot stage, whose ops do not add up to its span, or with a quality of 0 (the reference raises
+  // there): every position of its span is evaluated by the exact pass
+  if (nops == 0 || nops > NB_OPS || !fits || has_zero || t_carry != (uint32_t)(te - ts)) {
+    for (uint32_t j = (uint32_t)lane; j < nw; j += 32) out[j] = 0u;
+    const int64_t per = ((int64_t)(te - ts) + 31) / 32; // every lane a piece of [ts, te)
+    mark_impure_range(impure, imp_words, (int64_t)ts + per * lane, min((int64_t)te, (int64_t)ts + per * (lane + 1)));
+    return;
+  }
+  const int32_t trim_s = (int32_t)floor(__dmul_rn(p.min_trim, (double)qlen));
+  const int32_t trim_e = (int32_t)ceil(__dmul_rn(__dsub_rn(1.0, p.min_trim), (double)qlen));
+  const int wsz = p.mismatch_window, max_mm = p.max_mismatch_count;
+  const uint32_t nmm = (uint32_t)mm_base;
+  const uint32_t* seq32 = reinterpret_cast<const uint32_t*>(b.seq + __ldg(b.seq_off + r));
+  const int32_t ts_lo = ts & 31;
+  uint32_t kp = 0, mp = 0; // first op / mismatch that can matter for the current span of 32 words (both only advance)
+  for (uint32_t jb = 0; jb < nw; jb += 32) {
+    const int32_t A0 = (int32_t)(jb * 32u) - ts_lo, A1 = A0 + 32 * 32; // the span in read offsets (reference position - ts)
+    while (kp < nops && (int32_t)(S->t[kp] + (uint32_t)op_ref_len(S->w[kp])) <= max(A0, 0)) kp++;
+    while (mp < nmm && S->mm[mp] - 1 < A0 - 2 * wsz - 1) mp++;
+    const uint32_t j = jb + (uint32_t)lane;
+    const int32_t a = (int32_t)(j * 32u) - ts_lo; // read offset of this lane's first position
+    uint32_t cal = 0;
+    for (uint32_t k = kp; k < nops; k++) {
+      const uint32_t wd = S->w[k];
+      const int32_t tk = (int32_t)S->t[k];
+      if (tk >= A1) break;
+      if ((wd & 3u) != HM_OP_MATCH) continue;
+      const int32_t len = (int32_t)(wd >> 2);
+      const int32_t lo = max(tk, a), hi = min(tk + len, a + 32);
+      if (j >= nw || lo >= hi) continue;
+      const int nb = hi - lo, sh = lo - a;
+      const int32_t qk = (int32_t)S->q[k];
+      const int32_t qb = qk + (lo - tk); // query position of the first base
+      uint32_t g = __funnelshift_r(S->qg[qb >> 5], S->qg[(qb >> 5) + 1], (uint32_t)(qb & 31)) & low_mask(nb);
+      // get_trimmed_range / is_trimmed (bamlib.py:222-242): q < trim_s or q > trim_e does not count
+      if (qb < trim_s) g &= ~low_mask(trim_s - qb);
+      if (qb + nb - 1 > trim_e) g &= low_mask(trim_e - qb + 1);
+      // get_mismatch_range anchored at the block start (normcounts.py:82, bamlib.py:245-258)
+      if (g) {
+        const int qs = qk - wsz, qe = qk + wsz;
+        int u, d;
+        if (qs < 0) { u = wsz + qs; d = wsz + (-qs); }
+        else if (qe > qlen) { u = wsz + (qe - qlen); d = qlen - qk; }
+        else { u = wsz; d = wsz; }
+        // list entry x1 = (read offset of the mismatch) + 1; the base at read offset o counts the entries with
+        // o - u <= x1 <= o + d (normcounts.py:84-87: 0-based position against the 1-based list)
+        if (max_mm == 0) {
+          for (uint32_t m = mp; m < nmm; m++) {
+            const int32_t x1 = S->mm[m];
+            if (x1 - d >= hi) break;           // ascending: nothing further reaches this lane's bases
+            const int32_t blo = max(x1 - d, lo), bhi = min(x1 + u + 1, hi); // o in [x1 - d, x1 + u]
+            if (blo < bhi) g &= ~(low_mask(bhi - lo) & ~low_mask(blo - lo));
+          }
+        } else {
+          uint32_t todo = g;
+          while (todo) {
+            const int bit = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const int32_t o = lo + bit;
+            int cnt = 0;
+            for (uint32_t m = mp; m < nmm; m++) {
+              const int32_t x1 = S->mm[m];
+              if (x1 > o + d) break;
+              cnt += (x1 >= o - u);
+            }
+            if (cnt > max_mm) g &= ~(1u << bit);
+          }
+        }
+      }
+      cal |= g << sh;
+      // the bases of the run against the FASTA (a cs match that is not the FASTA's base makes the column impure)
+      {
+        const uint32_t s = (uint32_t)qb >> 4, bsh = 2u * ((uint32_t)qb & 15u);
+        const uint32_t need = bsh + 2u * (uint32_t)nb; // bits of the stream from word s on
+        const uint32_t w0 = __ldg(seq32 + s), w1 = need > 32u ? __ldg(seq32 + s + 1) : 0u, w2 = need > 64u ? __ldg(seq32 + s + 2) : 0u;
+        const unsigned long long rd = (unsigned long long)__funnelshift_r(w0, w1, bsh) | ((unsigned long long)__funnelshift_r(w1, w2, bsh) << 32);
+        const uint64_t W = (uint64_t)(ts >> 5) + j;
+        const uint2 rf = __ldg(reinterpret_cast<const uint2*>(ref2) + W);
+        const unsigned long long rf64 = (unsigned long long)rf.x | ((unsigned long long)rf.y << 32);
+        unsigned long long rng = nb >= 32 ? ~0ull : ((1ull << (2 * nb)) - 1ull);
+        unsigned long long x = ((rd & rng) << (2 * sh)) ^ (rf64 & (rng << (2 * sh)));
+        if (x) {
+          unsigned long long dd = (x | (x >> 1)) & 0x5555555555555555ull;
+          while (dd) {
+            const int bit = __ffsll((long long)dd) - 1;
+            dd &= dd - 1;
+            mark_impure(impure, imp_words, (int64_t)(W << 5) + (bit >> 1));
+          }
+        }
+      }
+    }
+    if (j < nw) out[j] = cal;
+  }
+}
+
+// ============================================================================ k_norm_bits
+// carry-save adder: (h, l) = a + b + c per bit
+#define NB_CSA(h, l, a, b, c) do { const uint32_t u_ = (a) ^ (b); (h) = ((a) & (b)) | (u_ & (c)); (l) = u_ ^ (c); } while (0)
+
+// eight one-bit-per-position words added into the bit-sliced counter P (P[k] = bit k of the 32 counts): 7 carry-save
+// adders and one ripple of the weight-8 word
+__device__ __forceinline__ void bits_add8(uint32_t (&P)[8], const uint32_t (&x)[8]) {
+  uint32_t tA, tB, fA, fB, e;
+  NB_CSA(tA, P[0], P[0], x[0], x[1]);
+  NB_CSA(tB, P[0], P[0], x[2], x[3]);
+  NB_CSA(fA, P[1], P[1], tA, tB);
+  NB_CSA(tA, P[0], P[0], x[4], x[5]);
+  NB_CSA(tB, P[0], P[0], x[6], x[7]);
+  NB_CSA(fB, P[1], P[1], tA, tB);
+  NB_CSA(e, P[2], P[2], fA, fB);
+#pragma unroll
+  for (int k = 3; k < 8; k++) { const uint32_t t = P[k] & e; P[k] ^= e; e = t; }
+}
+// positions whose count is >= k
+__device__ __forceinline__ uint32_t bits_ge(const uint32_t (&P)[8], int k) {
+  if (k <= 0) return 0xffffffffu;
+  if (k > 255) return 0u;
+  uint32_t gt = 0u, eq = 0xffffffffu;
+#pragma unroll
+  for (int bq = 7; bq >= 0; bq--) {
+    const uint32_t kb = ((k >> bq) & 1) ? 0xffffffffu : 0u;
+    gt |= eq & P[bq] & ~kb;
+    eq &= ~(P[bq] ^ kb);
+  }
+  return gt | eq;
+}
+// sum of the counts over the positions of mask m
+__device__ __forceinline__ uint32_t bits_sum(const uint32_t (&P)[8], uint32_t m) {
+  uint32_t s = 0;
+#pragma unroll
+  for (int k = 0; k < 8; k++) s += (uint32_t)__popc(P[k] & m) << k;
+  return s;
+}
+
+// thr[n]: the smallest callable count that certifies a pure position of depth n (host, make_norm_cert), 0xffff: none.
+// md_k: depth >= md_k is "read_depth > md_threshold" (256: never).
+__global__ void __launch_bounds__(32 * NB_BITS_WARPS) k_norm_bits(DevBatch b, DevParams p, const uint16_t* thr, int n_min, int md_k, const hm_chunk* chunks,
+                                                                   uint32_t n_chunks, const uint64_t* pair_off, const uint8_t* pair_flag,
+                                                                   const uint64_t* span_off, uint64_t n_spans, const uint32_t* cw_off,
+                                                                   const uint32_t* calw, const uint32_t* impure, const uint8_t* tri8,
+                                                                   NormOut* out, unsigned long long* sites, unsigned long long site_cap,
+                                                                   unsigned long long* n_sites) {
+  __shared__ unsigned long long s_ccs[HM_TRI_BINS], s_ref[HM_TRI_BINS], s_log[HM_NORM_LOG_LEN];
+  __shared__ unsigned int s_wccs[NB_BITS_WARPS][HM_TRI_BINS + 1], s_wref[NB_BITS_WARPS][HM_TRI_BINS + 1];
+  __shared__ uint16_t s_thr[256];
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  for (int i = tid; i < NB_BITS_WARPS * (HM_TRI_BINS + 1); i += blockDim.x) { (&s_wccs[0][0])[i] = 0; (&s_wref[0][0])[i] = 0; }
+  if (tid < HM_TRI_BINS) { s_ccs[tid] = 0; s_ref[tid] = 0; }
+  if (tid < HM_NORM_LOG_LEN) s_log[tid] = 0;
+  for (int i = tid; i < 256; i += blockDim.x) s_thr[i] = thr[i];
+  __syncthreads();
+
+  for (uint64_t span = (uint64_t)blockIdx.x * NB_BITS_WARPS + wid; span < n_spans; span += (uint64_t)gridDim.x * NB_BITS_WARPS) {
+    const uint32_t c = upper_bound_dev(span_off, n_chunks + 1, span) - 1;
+    const hm_chunk ch = chunks[c];
+    const int32_t s0 = (int32_t)(((uint32_t)(ch.start >> 10) + (uint32_t)(span - __ldg(span_off + c))) << 10);
+    const int32_t lo_pos = max(s0, ch.start), hi_pos = min(s0 + NB_SPAN, ch.end);
+    const uint32_t n_in = ch.read_hi - ch.read_lo;
+    // reads that cover a position of [lo_pos, hi_pos): running-max(tend) > lo_pos, tstart < hi_pos
+    const uint32_t r_lo = ch.read_lo + count_le_kary_i32(b.pmax_tend + ch.read_lo, n_in, lo_pos);
+    const uint32_t r_hi = ch.read_lo + count_le_kary_i32(b.tstart + ch.read_lo, n_in, hi_pos - 1);
+    const bool deep = r_hi > r_lo && r_hi - r_lo > 255u; // the 8-bit counters would overflow: every position to the exact pass
+    const uint64_t pbase = __ldg(pair_off + c);
+    const int32_t P0 = s0 + 32 * lane;
+    const uint32_t W = (uint32_t)P0 >> 5;
+    uint32_t N[8] = {0, 0, 0, 0, 0, 0, 0, 0}, C[8] = {0, 0, 0, 0, 0, 0, 0, 0}, H0[8] = {0, 0, 0, 0, 0, 0, 0, 0}, H1[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    uint32_t n_touch = 0; // reads that cover at least one of this lane's positions: an upper bound of every depth here
+    if (!deep) {
+      for (uint32_t base = r_lo; base < r_hi; base += 32) {
+        const uint32_t rr = base + (uint32_t)lane;
+        int32_t l_ts = 0, l_te = 0;
+        uint32_t l_off = 0, l_pf = 0;
+        if (rr < r_hi) {
+          l_pf = pair_flag[pbase + (rr - ch.read_lo)];
+          l_ts = __ldg(b.tstart + rr); l_te = __ldg(b.tend + rr);
+          l_off = __ldg(cw_off + rr);
+          if (!(l_pf & HM_PF_FETCHED)) l_te = l_ts; // covers nothing
+        }
+        const uint32_t cnt = min(32u, r_hi - base);
+        for (uint32_t i0 = 0; i0 < cnt; i0 += 8) {
+          uint32_t xm[8], xc[8], x0[8], x1[8];
+#pragma unroll
+          for (uint32_t u = 0; u < 8; u++) {
+            const int32_t ts = __shfl_sync(HM_FULL, l_ts, (int)(i0 + u)), te = __shfl_sync(HM_FULL, l_te, (int)(i0 + u));
+            const uint32_t off = __shfl_sync(HM_FULL, l_off, (int)(i0 + u)), pf = __shfl_sync(HM_FULL, l_pf, (int)(i0 + u));
+            const uint32_t m = low_mask(te - P0) & ~low_mask(ts - P0); // lanes past cnt hold ts = te = 0: nothing
+            uint32_t cw = 0;
+            if (m && (pf & HM_PF_PASS)) cw = __ldg(calw + off + (W - ((uint32_t)ts >> 5))) & m;
+            xm[u] = m; xc[u] = cw;
+            n_touch += (m != 0u);
+            if (p.phase) {
+              const uint32_t hap = (pf >> HM_PF_HAP_SHIFT) & 3u;
+              x0[u] = hap == 0u ? m : 0u; x1[u] = hap == 1u ? m : 0u;
+            }
+          }
+          bits_add8(N, xm);
+          bits_add8(C, xc);
+          if (p.phase) { bits_add8(H0, x0); bits_add8(H1, x1); }
+        }
+      }
+    }
+
+    // ---- per position, bit-parallel (normcounts.py:317-400)
+    const uint4 ta = __ldg(reinterpret_cast<const uint4*>(tri8 + P0)), tb = __ldg(reinterpret_cast<const uint4*>(tri8 + P0) + 1);
+    const uint32_t tw[8] = {ta.x, ta.y, ta.z, ta.w, tb.x, tb.y, tb.z, tb.w};
+    uint32_t alive = 0;
+#pragma unroll
+    for (int g = 0; g < 8; g++) { // a byte of 255: not an upper-case A/C/G/T (or past the contig)
+      const uint32_t y = ~tw[g];
+      const uint32_t nz = ((((y & 0x7f7f7f7fu) + 0x7f7f7f7fu) | y) >> 7) & 0x01010101u;
+      alive |= (((nz * 0x00204081u) >> 21) & 15u) << (4 * g);
+    }
+    alive &= low_mask(hi_pos - P0) & ~low_mask(lo_pos - P0);
+    const uint32_t imp = __ldg(impure + W);
+    uint32_t push = deep ? alive : (alive & imp);
+    uint32_t ok = 0;
+    if (!deep) {
+      const uint32_t calpos = C[0] | C[1] | C[2] | C[3] | C[4] | C[5] | C[6] | C[7];
+      uint32_t rest = alive & ~imp & calpos; // tri_sum != 0 at a pure position
+      unsigned t1 = 0, t2 = 0, t8 = 0, t9 = 0;
+      if (p.phase) {
+        const uint32_t unph = rest & ~(bits_ge(H0, p.min_hap_count) & bits_ge(H1, p.min_hap_count));
+        const unsigned v = bits_sum(C, unph);
+        t1 += v; t2 += v;
+        rest &= ~unph;
+      }
+      const uint32_t cert = rest & bits_ge(N, n_min) & bits_ge(C, (int)s_thr[min(n_touch, 255u)]);
+      push |= rest & ~cert;
+      const uint32_t md = cert & bits_ge(N, md_k);
+      const uint32_t low = cert & ~md & ~bits_ge(N, p.min_ref_count);
+      ok = cert & ~md & ~low;
+      const unsigned v_cert = bits_sum(C, cert);
+      t1 += v_cert;
+      t8 = bits_sum(C, md);
+      t9 = bits_sum(C, low);
+      const unsigned t13 = v_cert - t8 - t9;
+      unsigned v;
+      v = __reduce_add_sync(HM_FULL, t1); if (lane == 0 && v) atomicAdd(&s_log[1], (unsigned long long)v);
+      v = __reduce_add_sync(HM_FULL, t2); if (lane == 0 && v) atomicAdd(&s_log[2], (unsigned long long)v);
+      v = __reduce_add_sync(HM_FULL, v_cert); if (lane == 0 && v) atomicAdd(&s_log[6], (unsigned long long)v);
+      v = __reduce_add_sync(HM_FULL, t8); if (lane == 0 && v) atomicAdd(&s_log[8], (unsigned long long)v);
+      v = __reduce_add_sync(HM_FULL, t9); if (lane == 0 && v) atomicAdd(&s_log[9], (unsigned long long)v);
+      v = __reduce_add_sync(HM_FULL, t13); if (lane == 0 && v) atomicAdd(&s_log[13], (unsigned long long)v);
+    }
+    // the 33-bin tallies of the counted positions: the callable counts transposed out of the bit planes, four at a time
+    if (__any_sync(HM_FULL, ok != 0u)) {
+#pragma unroll
+      for (int g = 0; g < 8; g++) {
+        const uint32_t o4 = (ok >> (4 * g)) & 15u;
+        if (!o4) continue;
+        uint32_t cw = 0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) cw += spread4((C[k] >> (4 * g)) & 15u) << k;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          if (!((o4 >> k) & 1u)) continue;
+          const uint32_t tri = (tw[g] >> (8 * k)) & 255u;
+          atomicAdd(&s_wref[wid][tri], 1u);
+          atomicAdd(&s_wccs[wid][tri], (cw >> (8 * k)) & 255u);
+        }
+      }
+    }
+    // the site list of the exact pass
+    {
+      const uint32_t np = (uint32_t)__popc(push);
+      uint32_t incl = np;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(HM_FULL, incl, d); if (lane >= d) incl += t; }
+      const uint32_t total = __shfl_sync(HM_FULL, incl, 31);
+      if (total) {
+        unsigned long long at = 0;
+        if (lane == 0) at = atomicAdd(n_sites, (unsigned long long)total);
+        at = __shfl_sync(HM_FULL, at, 0) + (incl - np);
+        uint32_t todo = push;
+        while (todo) {
+          const int bit = __ffs(todo) - 1;
+          todo &= todo - 1;
+          if (at < site_cap) sites[at] = ((unsigned long long)c << 36) | ((unsigned long long)(uint32_t)(P0 + bit + 1) << 4);
+          at++;
+        }
+      }
+    }
+    // the warp's 32-bit bins into the CTA's 64-bit ones before they can overflow
+    __syncwarp();
+    for (int i = lane; i < HM_TRI_BINS; i += 32) {
+      if (s_wccs[wid][i] > 0x40000000u) {
+        atomicAdd(&s_ccs[i], (unsigned long long)atomicExch(&s_wccs[wid][i], 0u));
+        atomicAdd(&s_ref[i], (unsigned long long)atomicExch(&s_wref[wid][i], 0u));
+      }
+    }
+    __syncwarp();
+  }
+  __syncwarp();
+  for (int i = lane; i < HM_TRI_BINS; i += 32) {
+    if (s_wccs[wid][i]) atomicAdd(&s_ccs[i], (unsigned long long)s_wccs[wid][i]);
+    if (s_wref[wid][i]) atomicAdd(&s_ref[i], (unsigned long long)s_wref[wid][i]);
+  }
+  __syncthreads();
+  if (tid < HM_TRI_BINS) {
+    if (s_ccs[tid]) atomicAdd(&out->ccs_tri[tid], s_ccs[tid]);
+    if (s_ref[tid]) atomicAdd(&out->ref_tri[tid], s_ref[tid]);
+  }
+  if (tid < HM_NORM_LOG_LEN && s_log[tid]) atomicAdd(&out->log[tid], s_log[tid]);
+}
