@@ -1543,7 +1543,7 @@ static int hm_normcounts_impl(hm_ctx* ctx, const uint8_t* refseq, size_t ref_len
       if (use_bits) {
         const double md = ctx->params.md_threshold;
         const int md_k = !(md == md) ? 256 : md < 0.0 ? 0 : md >= 255.0 ? 256 : (int)floor(md) + 1; // depth >= md_k <=> depth > md_threshold
-        const unsigned bgrid = (unsigned)std::min<uint64_t>((n_spans + NB_BITS_WARPS - 1) / NB_BITS_WARPS, (uint64_t)n_sm * 8);
+        const unsigned bgrid = (unsigned)std::min<uint64_t>((n_spans + NB_BITS_WARPS - 1) / NB_BITS_WARPS, (uint64_t)n_sm * (ctx->params.phase ? 4 : 6));
         for (int attempt = 0; attempt < 2 && n_spans; attempt++) {
           CU(ctx->b_sites.ensure(site_cap * 8));
           if (attempt) { // the list overflowed: start over with the exact size
@@ -1551,7 +1551,7 @@ static int hm_normcounts_impl(hm_ctx* ctx, const uint8_t* refseq, size_t ref_len
             CU(cudaMemsetAsync(d_nsites, 0, 8, ctx->stream));
           }
           t_begin(ctx, "k_norm_bits");
-          k_norm_bits<<<bgrid, 32 * NB_BITS_WARPS, 0, ctx->stream>>>(
+          (ctx->params.phase ? k_norm_bits<true> : k_norm_bits<false>)<<<bgrid, 32 * NB_BITS_WARPS, 0, ctx->stream>>>(
               ctx->db, ctx->dp, ctx->b_thr.as<uint16_t>(), (int)ctx->cert.n_min, md_k, ctx->b_chunks.as<hm_chunk>(), (uint32_t)n_chunks,
               ctx->b_pair_off.as<uint64_t>(), ctx->b_pair_hap.as<uint8_t>(), ctx->b_span_off.as<uint64_t>(), n_spans, ctx->b_cw_off.as<uint32_t>(),
               ctx->b_calw.as<uint32_t>(), ctx->b_impure.as<uint32_t>(), ctx->b_tri8.as<uint8_t>(), ctx->b_norm_out.as<NormOut>(),

@@ -87,6 +87,11 @@ __device__ __forceinline__ void mark_impure_range(uint32_t* impure, uint64_t imp
 // One warp per read.  Writes everything k_read_scan writes (op_t, op_q, mm_pos, the totals, the gate byte), plus the
 // read's cal words at calw[cw_off[r] ...) — word j holds reference positions 32 * ((tstart >> 5) + j) ... + 31 — and
 // the read's contribution to the impure bitmap.  Secondary records are skipped by every consumer: they get neither.
+//
+// The bits live in QUERY coordinates as long as possible: "BQ >= min_bq" comes out of the quality words in query
+// order; the trimmed ends are two masks; the mismatch window of a block (get_mismatch_range is anchored at the block's
+// first base, so the window of a mismatch differs from block to block) clears, per (mismatch, nearby block), one range
+// of query positions.  What is left is moved to reference coordinates run by run: a funnel shift per 32 positions.
 __global__ void __launch_bounds__(32 * NB_PREP_WARPS) k_norm_prep(DevBatch b, DevParams p, const uint32_t* ref2, const uint32_t* cw_off,
                                                                    uint32_t* calw, uint32_t* impure, uint64_t imp_words) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
@@ -127,7 +132,7 @@ __global__ void __launch_bounds__(32 * NB_PREP_WARPS) k_norm_prep(DevBatch b, De
     if (is_mm) {
       const uint32_t at = (uint32_t)mm_base + __popc(bal & ((1u << lane) - 1u));
       b.mm_pos[o0 + at] = ts + (int32_t)t_ex + 1;
-      if (at < NB_OPS) S->mm[at] = (int32_t)t_ex + 1; // read-relative, 1-based as the list is
+      if (at < NB_OPS) S->mm[at] = (int32_t)k; // the op that is this entry of the list
     }
     mm_base += __popc(bal);
     if (valid) {
@@ -158,28 +163,28 @@ __global__ void __launch_bounds__(32 * NB_PREP_WARPS) k_norm_prep(DevBatch b, De
   uint16_t* qg16 = reinterpret_cast<uint16_t*>(S->qg);
   uint32_t acc = 0, zacc = 0;
   auto one_word = [&](uint4 v, uint32_t i) {
-    uint32_t wv[4] = {v.x, v.y, v.z, v.w};
+    uint32_t wv[4] = {v.x, v.y, v.z, v.w}, zw[4] = {v.x, v.y, v.z, v.w};
     const uint32_t g0 = i << 4;
     uint32_t live = 0xffffu;
-    if (g0 + 16u > (uint32_t)qlen) { // padding bytes are not part of the read
+    if (g0 + 16u > (uint32_t)qlen) { // padding bytes are not part of the read: 0 for the sum, non-zero for the zero test
       const uint32_t keep = (uint32_t)qlen - g0; // 1 .. 15
       live = (1u << keep) - 1u;
 #pragma unroll
       for (int j = 0; j < 4; j++) {
         const int kb = (int)keep - 4 * j;
-        wv[j] = kb >= 4 ? wv[j] : kb <= 0 ? 0u : (wv[j] & ((1u << (8 * kb)) - 1u));
+        const uint32_t mk = kb >= 4 ? 0xffffffffu : kb <= 0 ? 0u : ((1u << (8 * kb)) - 1u);
+        wv[j] &= mk;
+        zw[j] = wv[j] | ~mk;
       }
     }
-    uint32_t bits = 0, zero = 0;
+    uint32_t bits = 0;
 #pragma unroll
     for (int j = 0; j < 4; j++) {
       acc = sum4(wv[j], acc);
-      const uint32_t ge = ((((wv[j] & 0x7f7f7f7fu) + kge) | wv[j]) >> 7) & 0x01010101u;
-      bits |= (((ge * 0x00204081u) >> 21) & 15u) << (4 * j);
-      const uint32_t nz = ((((wv[j] & 0x7f7f7f7fu) + 0x7f7f7f7fu) | wv[j]) >> 7) & 0x01010101u; // byte != 0
-      zero |= ((((nz ^ 0x01010101u) * 0x00204081u) >> 21) & 15u) << (4 * j);
+      const uint32_t ge = (((wv[j] & 0x7f7f7f7fu) + kge) | wv[j]) & 0x80808080u; // bit 7 of each byte: BQ >= min_bq
+      bits |= ((ge * 0x00204081u) >> 28) << (4 * j);                               // bits 7, 15, 23, 31 -> a nibble
+      zacc |= (zw[j] - 0x01010101u) & ~zw[j];                                      // bit 7 of some byte set iff a byte of the word is 0
     }
-    zacc |= zero & live;
     if (fits) qg16[i] = (uint16_t)(bits & live);
   };
   {
@@ -197,7 +202,7 @@ __global__ void __launch_bounds__(32 * NB_PREP_WARPS) k_norm_prep(DevBatch b, De
   unsigned long long tot = acc;
 #pragma unroll
   for (int d = 16; d > 0; d >>= 1) tot += __shfl_xor_sync(HM_FULL, tot, d);
-  const bool has_zero = __any_sync(HM_FULL, zacc != 0u);
+  const bool has_zero = __any_sync(HM_FULL, (zacc & 0x80808080u) != 0u);
   if (lane == 0) {
     b.bq_total[r] = tot;
     b.n_match[r] = nm; b.n_sub[r] = ns; b.ins_len[r] = il; b.del_len[r] = dl; b.n_mm[r] = mm_base;
@@ -213,7 +218,6 @@ __global__ void __launch_bounds__(32 * NB_PREP_WARPS) k_norm_prep(DevBatch b, De
   if (!primary || te <= ts) return;
   __syncwarp();
 
-  // ---- phase 3: cal words in reference coordinates
   const uint32_t nw = (uint32_t)(((te - 1) >> 5) - (ts >> 5) + 1);
   uint32_t* out = calw + __ldg(cw_off + r);
   // a read this kernel cannot stage, whose ops do not add up to its span, or with a quality of 0 (the reference raises
@@ -224,20 +228,76 @@ __global__ void __launch_bounds__(32 * NB_PREP_WARPS) k_norm_prep(DevBatch b, De
     mark_impure_range(impure, imp_words, (int64_t)ts + per * lane, min((int64_t)te, (int64_t)ts + per * (lane + 1)));
     return;
   }
+
+  // ---- phase 2b, still in query coordinates: trimmed ends and mismatch windows
   const int32_t trim_s = (int32_t)floor(__dmul_rn(p.min_trim, (double)qlen));
   const int32_t trim_e = (int32_t)ceil(__dmul_rn(__dsub_rn(1.0, p.min_trim), (double)qlen));
   const int wsz = p.mismatch_window, max_mm = p.max_mismatch_count;
   const uint32_t nmm = (uint32_t)mm_base;
+  { // get_trimmed_range / is_trimmed (bamlib.py:222-242): q < trim_s or q > trim_e does not count
+    const uint32_t nqw = ((uint32_t)qlen + 31u) >> 5;
+    for (uint32_t wi = (uint32_t)lane; wi < nqw; wi += 32) {
+      const uint32_t keep = low_mask(trim_e + 1 - (int32_t)(wi * 32u)) & ~low_mask(trim_s - (int32_t)(wi * 32u));
+      if (keep != 0xffffffffu) S->qg[wi] &= keep;
+    }
+  }
+  __syncwarp();
+  // get_mismatch_range(rpos, qpos, qlen, window) with (rpos, qpos) the block's first base (normcounts.py:82,
+  // bamlib.py:245-258) gives the block its (u, d); a base at read offset o counts the list entries x1 (1-based read
+  // offsets) with o - u <= x1 <= o + d (normcounts.py:84-87), and with max_mismatch_count = 0 a single one blocks it:
+  // lane = one entry of the list, which clears o in [x1 - d, x1 + u] in the blocks around it
+  auto block_ud = [&](int32_t qk, int* u, int* d) {
+    const int qs = qk - wsz, qe = qk + wsz;
+    if (qs < 0) { *u = wsz + qs; *d = wsz + (-qs); }
+    else if (qe > qlen) { *u = wsz + (qe - qlen); *d = qlen - qk; }
+    else { *u = wsz; *d = wsz; }
+  };
+  if (max_mm == 0) {
+    for (uint32_t m = (uint32_t)lane; m < nmm; m += 32) {
+      const int32_t km = S->mm[m];
+      const int32_t x1 = (int32_t)S->t[km] + 1;
+      auto clear_in_block = [&](int32_t kk) {
+        const uint32_t wd = S->w[kk];
+        const int32_t tk = (int32_t)S->t[kk], len = (int32_t)(wd >> 2), qk = (int32_t)S->q[kk];
+        int u, d;
+        block_ud(qk, &u, &d);
+        const int32_t lo = max(x1 - d, tk), hi = min(x1 + u, tk + len - 1); // inclusive
+        if (lo > hi) return;
+        int32_t q0 = qk + (lo - tk);
+        const int32_t q1 = qk + (hi - tk);
+        while (q0 <= q1) {
+          const int32_t wi = q0 >> 5, b0 = q0 & 31, n = min(32 - b0, q1 - q0 + 1);
+          atomicAnd(&S->qg[wi], ~(low_mask(n) << b0));
+          q0 += n;
+        }
+      };
+      for (int32_t kk = km + 1; kk < (int32_t)nops; kk++) { // blocks after the entry: they start at or after x1 - 1
+        if ((int32_t)S->t[kk] > x1 + 2 * wsz) break;
+        if ((S->w[kk] & 3u) == HM_OP_MATCH) clear_in_block(kk);
+      }
+      for (int32_t kk = km - 1; kk >= 0; kk--) {            // blocks before it
+        const uint32_t wd = S->w[kk];
+        if ((int32_t)S->t[kk] + op_ref_len(wd) - 1 < x1 - 2 * wsz) break;
+        if ((wd & 3u) == HM_OP_MATCH) clear_in_block(kk);
+      }
+    }
+    __syncwarp();
+  }
+
+  // ---- phase 3: the bits of the match runs to reference coordinates; the bases of the runs against the FASTA
   const uint32_t* seq32 = reinterpret_cast<const uint32_t*>(b.seq + __ldg(b.seq_off + r));
   const int32_t ts_lo = ts & 31;
-  uint32_t kp = 0, mp = 0; // first op / mismatch that can matter for the current span of 32 words (both only advance)
+  uint32_t kp = 0; // first op that can matter for the current span of 32 words (only advances)
   for (uint32_t jb = 0; jb < nw; jb += 32) {
     const int32_t A0 = (int32_t)(jb * 32u) - ts_lo, A1 = A0 + 32 * 32; // the span in read offsets (reference position - ts)
-    while (kp < nops && (int32_t)(S->t[kp] + (uint32_t)op_ref_len(S->w[kp])) <= max(A0, 0)) kp++;
-    while (mp < nmm && S->mm[mp] - 1 < A0 - 2 * wsz - 1) mp++;
+    while (kp < nops && (int32_t)S->t[kp] + op_ref_len(S->w[kp]) <= max(A0, 0)) kp++;
     const uint32_t j = jb + (uint32_t)lane;
     const int32_t a = (int32_t)(j * 32u) - ts_lo; // read offset of this lane's first position
+    const uint64_t W = (uint64_t)(ts >> 5) + j;
     uint32_t cal = 0;
+    uint2 rf = make_uint2(0u, 0u);
+    if (j < nw) rf = __ldg(reinterpret_cast<const uint2*>(ref2) + W);
+    const unsigned long long rf64 = (unsigned long long)rf.x | ((unsigned long long)rf.y << 32);
     for (uint32_t k = kp; k < nops; k++) {
       const uint32_t wd = S->w[k];
       const int32_t tk = (int32_t)S->t[k];
@@ -250,53 +310,31 @@ __global__ void __launch_bounds__(32 * NB_PREP_WARPS) k_norm_prep(DevBatch b, De
       const int32_t qk = (int32_t)S->q[k];
       const int32_t qb = qk + (lo - tk); // query position of the first base
       uint32_t g = __funnelshift_r(S->qg[qb >> 5], S->qg[(qb >> 5) + 1], (uint32_t)(qb & 31)) & low_mask(nb);
-      // get_trimmed_range / is_trimmed (bamlib.py:222-242): q < trim_s or q > trim_e does not count
-      if (qb < trim_s) g &= ~low_mask(trim_s - qb);
-      if (qb + nb - 1 > trim_e) g &= low_mask(trim_e - qb + 1);
-      // get_mismatch_range anchored at the block start (normcounts.py:82, bamlib.py:245-258)
-      if (g) {
-        const int qs = qk - wsz, qe = qk + wsz;
+      if (max_mm != 0 && g) { // general threshold: count the list entries in the window of every candidate base
         int u, d;
-        if (qs < 0) { u = wsz + qs; d = wsz + (-qs); }
-        else if (qe > qlen) { u = wsz + (qe - qlen); d = qlen - qk; }
-        else { u = wsz; d = wsz; }
-        // list entry x1 = (read offset of the mismatch) + 1; the base at read offset o counts the entries with
-        // o - u <= x1 <= o + d (normcounts.py:84-87: 0-based position against the 1-based list)
-        if (max_mm == 0) {
-          for (uint32_t m = mp; m < nmm; m++) {
-            const int32_t x1 = S->mm[m];
-            if (x1 - d >= hi) break;           // ascending: nothing further reaches this lane's bases
-            const int32_t blo = max(x1 - d, lo), bhi = min(x1 + u + 1, hi); // o in [x1 - d, x1 + u]
-            if (blo < bhi) g &= ~(low_mask(bhi - lo) & ~low_mask(blo - lo));
+        block_ud(qk, &u, &d);
+        uint32_t todo = g;
+        while (todo) {
+          const int bit = __ffs(todo) - 1;
+          todo &= todo - 1;
+          const int32_t o = lo + bit;
+          int cnt = 0;
+          for (uint32_t m = 0; m < nmm; m++) {
+            const int32_t x1 = (int32_t)S->t[S->mm[m]] + 1;
+            if (x1 > o + d) break;
+            cnt += (x1 >= o - u);
           }
-        } else {
-          uint32_t todo = g;
-          while (todo) {
-            const int bit = __ffs(todo) - 1;
-            todo &= todo - 1;
-            const int32_t o = lo + bit;
-            int cnt = 0;
-            for (uint32_t m = mp; m < nmm; m++) {
-              const int32_t x1 = S->mm[m];
-              if (x1 > o + d) break;
-              cnt += (x1 >= o - u);
-            }
-            if (cnt > max_mm) g &= ~(1u << bit);
-          }
+          if (cnt > max_mm) g &= ~(1u << bit);
         }
       }
       cal |= g << sh;
-      // the bases of the run against the FASTA (a cs match that is not the FASTA's base makes the column impure)
-      {
+      { // a cs match that is not the FASTA's base makes the column impure
         const uint32_t s = (uint32_t)qb >> 4, bsh = 2u * ((uint32_t)qb & 15u);
         const uint32_t need = bsh + 2u * (uint32_t)nb; // bits of the stream from word s on
         const uint32_t w0 = __ldg(seq32 + s), w1 = need > 32u ? __ldg(seq32 + s + 1) : 0u, w2 = need > 64u ? __ldg(seq32 + s + 2) : 0u;
         const unsigned long long rd = (unsigned long long)__funnelshift_r(w0, w1, bsh) | ((unsigned long long)__funnelshift_r(w1, w2, bsh) << 32);
-        const uint64_t W = (uint64_t)(ts >> 5) + j;
-        const uint2 rf = __ldg(reinterpret_cast<const uint2*>(ref2) + W);
-        const unsigned long long rf64 = (unsigned long long)rf.x | ((unsigned long long)rf.y << 32);
-        unsigned long long rng = nb >= 32 ? ~0ull : ((1ull << (2 * nb)) - 1ull);
-        unsigned long long x = ((rd & rng) << (2 * sh)) ^ (rf64 & (rng << (2 * sh)));
+        const unsigned long long rng = (nb >= 32 ? ~0ull : ((1ull << (2 * nb)) - 1ull)) << (2 * sh);
+        const unsigned long long x = ((rd << (2 * sh)) ^ rf64) & rng;
         if (x) {
           unsigned long long dd = (x | (x >> 1)) & 0x5555555555555555ull;
           while (dd) {
@@ -352,7 +390,8 @@ __device__ __forceinline__ uint32_t bits_sum(const uint32_t (&P)[8], uint32_t m)
 
 // thr[n]: the smallest callable count that certifies a pure position of depth n (host, make_norm_cert), 0xffff: none.
 // md_k: depth >= md_k is "read_depth > md_threshold" (256: never).
-__global__ void __launch_bounds__(32 * NB_BITS_WARPS) k_norm_bits(DevBatch b, DevParams p, const uint16_t* thr, int n_min, int md_k, const hm_chunk* chunks,
+template <bool kPhase>
+__global__ void __launch_bounds__(32 * NB_BITS_WARPS, kPhase ? 3 : 5) k_norm_bits(DevBatch b, DevParams p, const uint16_t* thr, int n_min, int md_k, const hm_chunk* chunks,
                                                                    uint32_t n_chunks, const uint64_t* pair_off, const uint8_t* pair_flag,
                                                                    const uint64_t* span_off, uint64_t n_spans, const uint32_t* cw_off,
                                                                    const uint32_t* calw, const uint32_t* impure, const uint8_t* tri8,
@@ -381,7 +420,8 @@ __global__ void __launch_bounds__(32 * NB_BITS_WARPS) k_norm_bits(DevBatch b, De
     const uint64_t pbase = __ldg(pair_off + c);
     const int32_t P0 = s0 + 32 * lane;
     const uint32_t W = (uint32_t)P0 >> 5;
-    uint32_t N[8] = {0, 0, 0, 0, 0, 0, 0, 0}, C[8] = {0, 0, 0, 0, 0, 0, 0, 0}, H0[8] = {0, 0, 0, 0, 0, 0, 0, 0}, H1[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    uint32_t N[8] = {0, 0, 0, 0, 0, 0, 0, 0}, C[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    uint32_t H0[8] = {0, 0, 0, 0, 0, 0, 0, 0}, H1[8] = {0, 0, 0, 0, 0, 0, 0, 0}; // kPhase only
     uint32_t n_touch = 0; // reads that cover at least one of this lane's positions: an upper bound of every depth here
     if (!deep) {
       for (uint32_t base = r_lo; base < r_hi; base += 32) {
@@ -396,7 +436,7 @@ __global__ void __launch_bounds__(32 * NB_BITS_WARPS) k_norm_bits(DevBatch b, De
         }
         const uint32_t cnt = min(32u, r_hi - base);
         for (uint32_t i0 = 0; i0 < cnt; i0 += 8) {
-          uint32_t xm[8], xc[8], x0[8], x1[8];
+          uint32_t xm[8], xc[8], x0[8], x1[8]; // x0 / x1: kPhase only
 #pragma unroll
           for (uint32_t u = 0; u < 8; u++) {
             const int32_t ts = __shfl_sync(HM_FULL, l_ts, (int)(i0 + u)), te = __shfl_sync(HM_FULL, l_te, (int)(i0 + u));
@@ -406,14 +446,14 @@ __global__ void __launch_bounds__(32 * NB_BITS_WARPS) k_norm_bits(DevBatch b, De
             if (m && (pf & HM_PF_PASS)) cw = __ldg(calw + off + (W - ((uint32_t)ts >> 5))) & m;
             xm[u] = m; xc[u] = cw;
             n_touch += (m != 0u);
-            if (p.phase) {
+            if constexpr (kPhase) {
               const uint32_t hap = (pf >> HM_PF_HAP_SHIFT) & 3u;
               x0[u] = hap == 0u ? m : 0u; x1[u] = hap == 1u ? m : 0u;
             }
           }
           bits_add8(N, xm);
           bits_add8(C, xc);
-          if (p.phase) { bits_add8(H0, x0); bits_add8(H1, x1); }
+          if constexpr (kPhase) { bits_add8(H0, x0); bits_add8(H1, x1); }
         }
       }
     }
@@ -436,7 +476,7 @@ __global__ void __launch_bounds__(32 * NB_BITS_WARPS) k_norm_bits(DevBatch b, De
       const uint32_t calpos = C[0] | C[1] | C[2] | C[3] | C[4] | C[5] | C[6] | C[7];
       uint32_t rest = alive & ~imp & calpos; // tri_sum != 0 at a pure position
       unsigned t1 = 0, t2 = 0, t8 = 0, t9 = 0;
-      if (p.phase) {
+      if constexpr (kPhase) {
         const uint32_t unph = rest & ~(bits_ge(H0, p.min_hap_count) & bits_ge(H1, p.min_hap_count));
         const unsigned v = bits_sum(C, unph);
         t1 += v; t2 += v;
