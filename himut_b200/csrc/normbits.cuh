@@ -33,16 +33,17 @@
 #pragma once
 #include "normfast.cuh"
 
-#define NB_OPS 160u                 // ops of a read staged in shared memory (more: the read's span goes to the exact pass)
-#define NB_QWORDS 1024u             // 32 768 query bases of "BQ >= min_bq" bits per warp (longer reads: exact pass)
+#define NB_OPS 192u                 // ops of a read staged in shared memory (more: the read's span goes to the exact pass)
+#define NB_SEG 8192u                // query bases a warp holds in shared memory at a time (a read is walked segment by segment)
 #define NB_PREP_WARPS 4
 #define NB_SPAN 1024                // reference positions per warp of k_norm_bits
 #define NB_BITS_WARPS 4
 
 struct __align__(16) PrepWarp {
-  uint32_t qg[NB_QWORDS + 4];       // bit q: BQ of query base q >= min_bq
-  uint32_t w[NB_OPS], t[NB_OPS], q[NB_OPS];
-  int32_t mm[NB_OPS];
+  uint32_t qg[NB_SEG / 32 + 4];     // bit q: BQ of the segment's query base q >= min_bq (then: "counts")
+  uint32_t sq[NB_SEG / 16 + 4];     // the segment's 2-bit bases
+  uint32_t w[NB_OPS], t[NB_OPS + 1], q[NB_OPS + 1]; // t / q[k + 1] = where op k ends (t / q[nops]: the read's totals)
+  int32_t mm[NB_OPS];               // op index of every entry of the mismatch list
 };
 
 // ============================================================================ k_ref_pack
@@ -153,51 +154,222 @@ __global__ void __launch_bounds__(32 * NB_PREP_WARPS) k_norm_prep(DevBatch b, De
   ns = __reduce_add_sync(HM_FULL, ns);
   il = __reduce_add_sync(HM_FULL, il);
   dl = __reduce_add_sync(HM_FULL, dl);
+  if (lane == 0 && nops <= NB_OPS) { S->t[nops] = t_carry; S->q[nops] = q_carry; }
+  __syncwarp();
 
-  // ---- phase 2: the quality stream once — whole-read sum (np.mean is an exact integer sum divided once) and one
-  // bit per base: BQ >= min_bq
-  const bool fits = (uint32_t)qlen <= NB_QWORDS * 32u;
+  // ---- phases 2 and 3, one segment of NB_SEG query bases after the other (shared memory holds one segment)
+  const uint32_t nw = (primary && te > ts) ? (uint32_t)(((te - 1) >> 5) - (ts >> 5) + 1) : 0u;
+  uint32_t* out = calw + __ldg(cw_off + r);
+  // a read whose ops this kernel cannot stage, or do not add up to its span: every position of the span is evaluated
+  // by the exact pass (so is a read with a quality of 0, found below: the reference raises there)
+  const bool staged = nops != 0 && nops <= NB_OPS && t_carry == (uint32_t)(te - ts);
+  const bool do_bits = nw != 0 && staged;
   const uint32_t kge = (uint32_t)(128 - p.min_bq) * 0x01010101u; // byte >= min_bq  <=>  bit 7 of ((byte & 0x7f) + 128 - min_bq) | byte
   const uint4* q4 = reinterpret_cast<const uint4*>(bq);
-  const uint32_t n16 = ((uint32_t)qlen + 15u) >> 4;
+  const uint32_t* seq32 = reinterpret_cast<const uint32_t*>(b.seq + __ldg(b.seq_off + r));
   uint16_t* qg16 = reinterpret_cast<uint16_t*>(S->qg);
+  const int32_t trim_s = (int32_t)floor(__dmul_rn(p.min_trim, (double)qlen));
+  const int32_t trim_e = (int32_t)ceil(__dmul_rn(__dsub_rn(1.0, p.min_trim), (double)qlen));
+  const int wsz = p.mismatch_window, max_mm = p.max_mismatch_count;
+  const uint32_t nmm = (uint32_t)mm_base;
+  const int32_t ts_lo = ts & 31;
+  // get_mismatch_range(rpos, qpos, qlen, window) with (rpos, qpos) the block's first base (normcounts.py:82,
+  // bamlib.py:245-258) gives the block its (u, d); a base at read offset o counts the list entries x1 (1-based read
+  // offsets) with o - u <= x1 <= o + d (normcounts.py:84-87)
+  auto block_ud = [&](int32_t qk, int* u, int* d) {
+    const int qs = qk - wsz, qe = qk + wsz;
+    if (qs < 0) { *u = wsz + qs; *d = wsz + (-qs); }
+    else if (qe > qlen) { *u = wsz + (qe - qlen); *d = qlen - qk; }
+    else { *u = wsz; *d = wsz; }
+  };
   uint32_t acc = 0, zacc = 0;
-  auto one_word = [&](uint4 v, uint32_t i) {
-    uint32_t wv[4] = {v.x, v.y, v.z, v.w}, zw[4] = {v.x, v.y, v.z, v.w};
-    const uint32_t g0 = i << 4;
-    uint32_t live = 0xffffu;
-    if (g0 + 16u > (uint32_t)qlen) { // padding bytes are not part of the read: 0 for the sum, non-zero for the zero test
-      const uint32_t keep = (uint32_t)qlen - g0; // 1 .. 15
-      live = (1u << keep) - 1u;
+  uint32_t ks = 0;                 // first op whose query bases reach into the current segment
+  int32_t o_seg = 0;               // read offset at which the current segment's reference positions begin
+  uint32_t carry = 0;              // the bits an earlier segment left in word carry_j
+  int32_t carry_j = -1;
+  for (int32_t seg0 = 0; seg0 < qlen; seg0 += (int32_t)NB_SEG) {
+    const int32_t seg1 = min(seg0 + (int32_t)NB_SEG, qlen);
+    // -- phase 2: the segment's quality words once — whole-read sum (np.mean is an exact integer sum divided once),
+    // one bit per base "BQ >= min_bq"; the segment's bases staged next to them
+    const uint32_t i0 = (uint32_t)seg0 >> 4, i1 = ((uint32_t)seg1 + 15u) >> 4;
+    auto one_word = [&](uint4 v, uint32_t i) {
+      uint32_t wv[4] = {v.x, v.y, v.z, v.w}, zw[4] = {v.x, v.y, v.z, v.w};
+      const uint32_t g0 = i << 4;
+      uint32_t live = 0xffffu;
+      if (g0 + 16u > (uint32_t)qlen) { // padding bytes are not part of the read: 0 for the sum, non-zero for the zero test
+        const uint32_t keep = (uint32_t)qlen - g0; // 1 .. 15
+        live = (1u << keep) - 1u;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          const int kb = (int)keep - 4 * j;
+          const uint32_t mk = kb >= 4 ? 0xffffffffu : kb <= 0 ? 0u : ((1u << (8 * kb)) - 1u);
+          wv[j] &= mk;
+          zw[j] = wv[j] | ~mk;
+        }
+      }
+      uint32_t bits = 0;
 #pragma unroll
       for (int j = 0; j < 4; j++) {
-        const int kb = (int)keep - 4 * j;
-        const uint32_t mk = kb >= 4 ? 0xffffffffu : kb <= 0 ? 0u : ((1u << (8 * kb)) - 1u);
-        wv[j] &= mk;
-        zw[j] = wv[j] | ~mk;
+        acc = sum4(wv[j], acc);
+        const uint32_t ge = (((wv[j] & 0x7f7f7f7fu) + kge) | wv[j]) & 0x80808080u; // bit 7 of each byte: BQ >= min_bq
+        bits |= ((ge * 0x00204081u) >> 28) << (4 * j);                               // bits 7, 15, 23, 31 -> a nibble
+        zacc |= (zw[j] - 0x01010101u) & ~zw[j];                                      // bit 7 of some byte set iff a byte of the word is 0
+      }
+      if (do_bits) qg16[i - i0] = (uint16_t)(bits & live);
+    };
+    {
+      uint32_t i = i0 + (uint32_t)lane;
+      for (; i + 96 < i1; i += 128) {
+        const uint4 a0 = ldg_stream16(q4 + i), a1 = ldg_stream16(q4 + i + 32), a2 = ldg_stream16(q4 + i + 64), a3 = ldg_stream16(q4 + i + 96);
+        uint32_t s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+        if (do_bits) { s0 = __ldg(seq32 + i); s1 = __ldg(seq32 + i + 32); s2 = __ldg(seq32 + i + 64); s3 = __ldg(seq32 + i + 96); }
+        one_word(a0, i); one_word(a1, i + 32); one_word(a2, i + 64); one_word(a3, i + 96);
+        if (do_bits) { S->sq[i - i0] = s0; S->sq[i - i0 + 32] = s1; S->sq[i - i0 + 64] = s2; S->sq[i - i0 + 96] = s3; }
+      }
+      for (; i < i1; i += 32) {
+        const uint4 a0 = ldg_stream16(q4 + i);
+        if (do_bits) S->sq[i - i0] = __ldg(seq32 + i);
+        one_word(a0, i);
       }
     }
-    uint32_t bits = 0;
-#pragma unroll
-    for (int j = 0; j < 4; j++) {
-      acc = sum4(wv[j], acc);
-      const uint32_t ge = (((wv[j] & 0x7f7f7f7fu) + kge) | wv[j]) & 0x80808080u; // bit 7 of each byte: BQ >= min_bq
-      bits |= ((ge * 0x00204081u) >> 28) << (4 * j);                               // bits 7, 15, 23, 31 -> a nibble
-      zacc |= (zw[j] - 0x01010101u) & ~zw[j];                                      // bit 7 of some byte set iff a byte of the word is 0
+    if (!do_bits) continue;
+    { // the words the funnel shifts below may touch past the segment's last base
+      const uint32_t n16 = i1 - i0;
+      for (uint32_t i = n16 + (uint32_t)lane; i < ((n16 + 1u) & ~1u) + 4u; i += 32) qg16[i] = 0;
+      for (uint32_t i = n16 + (uint32_t)lane; i < n16 + 3u; i += 32) S->sq[i] = 0;
     }
-    if (fits) qg16[i] = (uint16_t)(bits & live);
-  };
-  {
-    uint32_t i = (uint32_t)lane;
-    for (; i + 96 < n16; i += 128) {
-      const uint4 a0 = ldg_stream16(q4 + i), a1 = ldg_stream16(q4 + i + 32), a2 = ldg_stream16(q4 + i + 64), a3 = ldg_stream16(q4 + i + 96);
-      one_word(a0, i); one_word(a1, i + 32); one_word(a2, i + 64); one_word(a3, i + 96);
+    __syncwarp();
+
+    // -- phase 2b, still in query coordinates: trimmed ends and mismatch windows
+    { // get_trimmed_range / is_trimmed (bamlib.py:222-242): q < trim_s or q > trim_e does not count
+      const uint32_t nqw = ((uint32_t)(seg1 - seg0) + 31u) >> 5;
+      for (uint32_t wi = (uint32_t)lane; wi < nqw; wi += 32) {
+        const int32_t q0 = seg0 + (int32_t)(wi * 32u);
+        const uint32_t keep = low_mask(trim_e + 1 - q0) & ~low_mask(trim_s - q0);
+        if (keep != 0xffffffffu) S->qg[wi] &= keep;
+      }
     }
-    for (; i < n16; i += 32) one_word(ldg_stream16(q4 + i), i);
-  }
-  if (fits) { // the words the funnel shifts below may touch past the last base
-    const uint32_t h0 = n16, h1 = min(((n16 + 1u) & ~1u) + 4u, (NB_QWORDS + 4u) * 2u);
-    for (uint32_t i = h0 + (uint32_t)lane; i < h1; i += 32) qg16[i] = 0;
+    __syncwarp();
+    // with max_mismatch_count = 0 a single list entry in its window blocks a base: lane = one entry of the list,
+    // which clears o in [x1 - d, x1 + u] in the blocks around it (the part that lies in this segment)
+    if (max_mm == 0) {
+      for (uint32_t m = (uint32_t)lane; m < nmm; m += 32) {
+        const int32_t km = S->mm[m];
+        const int32_t x1 = (int32_t)S->t[km] + 1;
+        auto clear_in_block = [&](int32_t kk) {
+          const uint32_t wd = S->w[kk];
+          const int32_t tk = (int32_t)S->t[kk], len = (int32_t)(wd >> 2), qk = (int32_t)S->q[kk];
+          if (qk >= seg1 || qk + len <= seg0) return;
+          int u, d;
+          block_ud(qk, &u, &d);
+          const int32_t lo = max(x1 - d, tk), hi = min(x1 + u, tk + len - 1); // inclusive
+          if (lo > hi) return;
+          int32_t q0 = max(qk + (lo - tk), seg0) - seg0;
+          const int32_t q1 = min(qk + (hi - tk), seg1 - 1) - seg0;
+          while (q0 <= q1) {
+            const int32_t wi = q0 >> 5, b0 = q0 & 31, n = min(32 - b0, q1 - q0 + 1);
+            atomicAnd(&S->qg[wi], ~(low_mask(n) << b0));
+            q0 += n;
+          }
+        };
+        for (int32_t kk = km + 1; kk < (int32_t)nops; kk++) { // blocks after the entry
+          if ((int32_t)S->t[kk] > x1 + 2 * wsz) break;
+          if ((S->w[kk] & 3u) == HM_OP_MATCH) clear_in_block(kk);
+        }
+        for (int32_t kk = km - 1; kk >= 0; kk--) {            // blocks before it
+          const uint32_t wd = S->w[kk];
+          if ((int32_t)S->t[kk + 1] - 1 < x1 - 2 * wsz) break;
+          if ((wd & 3u) == HM_OP_MATCH) clear_in_block(kk);
+        }
+      }
+      __syncwarp();
+    }
+
+    // -- phase 3: the bits of the match runs to reference coordinates; the bases of the runs against the FASTA.
+    // The segment owns the read offsets [o_seg, o_next): o_next = where the next segment's first base lies.
+    // ks / ke: the first op that ends past query position seg0 / seg1 (op ends ascend: a count is an index)
+    uint32_t ke = 0;
+    {
+      uint32_t c0 = 0, c1 = 0;
+      for (uint32_t base = 0; base < nops; base += 32) {
+        const uint32_t k = base + (uint32_t)lane;
+        const int32_t qe = k < nops ? (int32_t)S->q[k + 1] : INT32_MAX;
+        c0 += __popc(__ballot_sync(HM_FULL, qe <= seg0));
+        c1 += __popc(__ballot_sync(HM_FULL, qe <= seg1));
+      }
+      ks = c0; ke = c1;
+    }
+    int32_t o_next = te - ts;
+    if (seg1 < qlen && ke < nops) {
+      const uint32_t wd = S->w[ke];
+      o_next = (int32_t)S->t[ke] + ((wd & 3u) == HM_OP_MATCH ? max(seg1 - (int32_t)S->q[ke], 0) : 0);
+    }
+    const uint32_t jA = (uint32_t)(o_seg + ts_lo) >> 5;
+    const uint32_t jB = o_next > o_seg ? (uint32_t)(o_next - 1 + ts_lo) >> 5 : jA; // last word with a position of the segment
+    uint32_t kl = ks; // this lane's op pointer: its words ascend, so it only advances
+    uint32_t last_cal = 0;
+    for (uint32_t jb = jA; jb <= jB && o_next > o_seg; jb += 32) {
+      const uint32_t j = jb + (uint32_t)lane;
+      uint32_t cal = (int32_t)j == carry_j ? carry : 0u;
+      if (j <= jB) {
+        const int32_t a = (int32_t)(j * 32u) - ts_lo; // read offset of this lane's first position
+        const int32_t lo_w = max(a, o_seg), hi_w = min(a + 32, o_next); // the word's positions this segment owns
+        const uint64_t W = (uint64_t)(ts >> 5) + j;
+        const uint2 rf = __ldg(reinterpret_cast<const uint2*>(ref2) + W);
+        const unsigned long long rf64 = (unsigned long long)rf.x | ((unsigned long long)rf.y << 32);
+        while (kl < nops && (int32_t)S->t[kl + 1] <= lo_w) kl++;
+        for (uint32_t k = kl; k < nops; k++) {
+          const int32_t tk = (int32_t)S->t[k];
+          if (tk >= hi_w) break;
+          const uint32_t wd = S->w[k];
+          if ((wd & 3u) != HM_OP_MATCH) continue;
+          const int32_t lo = max(tk, lo_w), hi = min((int32_t)S->t[k + 1], hi_w);
+          if (lo >= hi) continue;
+          const int nb = hi - lo, sh = lo - a;
+          const int32_t qk = (int32_t)S->q[k];
+          const int32_t qb = qk + (lo - tk) - seg0; // query position of the first base, in the segment
+          uint32_t g = __funnelshift_r(S->qg[qb >> 5], S->qg[(qb >> 5) + 1], (uint32_t)(qb & 31)) & low_mask(nb);
+          if (max_mm != 0 && g) { // general threshold: count the list entries in the window of every candidate base
+            int u, d;
+            block_ud(qk, &u, &d);
+            uint32_t todo = g;
+            while (todo) {
+              const int bit = __ffs(todo) - 1;
+              todo &= todo - 1;
+              const int32_t o = lo + bit;
+              int cnt = 0;
+              for (uint32_t m = 0; m < nmm; m++) {
+                const int32_t x1 = (int32_t)S->t[S->mm[m]] + 1;
+                if (x1 > o + d) break;
+                cnt += (x1 >= o - u);
+              }
+              if (cnt > max_mm) g &= ~(1u << bit);
+            }
+          }
+          cal |= g << sh;
+          { // a cs match that is not the FASTA's base makes the column impure
+            const uint32_t s = (uint32_t)qb >> 4, bsh = 2u * ((uint32_t)qb & 15u);
+            const uint32_t w0 = S->sq[s], w1 = S->sq[s + 1], w2 = S->sq[s + 2];
+            const unsigned long long rd = (unsigned long long)__funnelshift_r(w0, w1, bsh) | ((unsigned long long)__funnelshift_r(w1, w2, bsh) << 32);
+            const unsigned long long rng = (nb >= 32 ? ~0ull : ((1ull << (2 * nb)) - 1ull)) << (2 * sh);
+            const unsigned long long x = ((rd << (2 * sh)) ^ rf64) & rng;
+            if (x) {
+              unsigned long long dd = (x | (x >> 1)) & 0x5555555555555555ull;
+              while (dd) {
+                const int bit = __ffsll((long long)dd) - 1;
+                dd &= dd - 1;
+                mark_impure(impure, imp_words, (int64_t)(W << 5) + (bit >> 1));
+              }
+            }
+          }
+        }
+        out[j] = cal;
+      }
+      if (jb + 32 > jB) last_cal = __shfl_sync(HM_FULL, cal, (int)(jB - jb)); // the segment's last word: the next segment may add to it
+    }
+    if (o_next > o_seg) { carry = last_cal; carry_j = (int32_t)jB; }
+    o_seg = o_next;
+    __syncwarp(); // the stores of this segment's last word precede the next segment's
   }
   unsigned long long tot = acc;
 #pragma unroll
@@ -215,137 +387,10 @@ __global__ void __launch_bounds__(32 * NB_PREP_WARPS) k_norm_prep(DevBatch b, De
     if (!(p.qlen_lower_limit < qlen && qlen < p.qlen_upper_limit)) ok = false;
     b.gate[r] = ok ? 1 : 0;
   }
-  if (!primary || te <= ts) return;
-  __syncwarp();
-
-  const uint32_t nw = (uint32_t)(((te - 1) >> 5) - (ts >> 5) + 1);
-  uint32_t* out = calw + __ldg(cw_off + r);
-  // a read this kernel cannot stage, whose ops do not add up to its span, or with a quality of 0 (the reference raises
-  // there): every position of its span is evaluated by the exact pass
-  if (nops == 0 || nops > NB_OPS || !fits || has_zero || t_carry != (uint32_t)(te - ts)) {
-    for (uint32_t j = (uint32_t)lane; j < nw; j += 32) out[j] = 0u;
+  if (nw != 0 && (!staged || has_zero)) {
+    if (!staged) for (uint32_t j = (uint32_t)lane; j < nw; j += 32) out[j] = 0u;
     const int64_t per = ((int64_t)(te - ts) + 31) / 32; // every lane a piece of [ts, te)
     mark_impure_range(impure, imp_words, (int64_t)ts + per * lane, min((int64_t)te, (int64_t)ts + per * (lane + 1)));
-    return;
-  }
-
-  // ---- phase 2b, still in query coordinates: trimmed ends and mismatch windows
-  const int32_t trim_s = (int32_t)floor(__dmul_rn(p.min_trim, (double)qlen));
-  const int32_t trim_e = (int32_t)ceil(__dmul_rn(__dsub_rn(1.0, p.min_trim), (double)qlen));
-  const int wsz = p.mismatch_window, max_mm = p.max_mismatch_count;
-  const uint32_t nmm = (uint32_t)mm_base;
-  { // get_trimmed_range / is_trimmed (bamlib.py:222-242): q < trim_s or q > trim_e does not count
-    const uint32_t nqw = ((uint32_t)qlen + 31u) >> 5;
-    for (uint32_t wi = (uint32_t)lane; wi < nqw; wi += 32) {
-      const uint32_t keep = low_mask(trim_e + 1 - (int32_t)(wi * 32u)) & ~low_mask(trim_s - (int32_t)(wi * 32u));
-      if (keep != 0xffffffffu) S->qg[wi] &= keep;
-    }
-  }
-  __syncwarp();
-  // get_mismatch_range(rpos, qpos, qlen, window) with (rpos, qpos) the block's first base (normcounts.py:82,
-  // bamlib.py:245-258) gives the block its (u, d); a base at read offset o counts the list entries x1 (1-based read
-  // offsets) with o - u <= x1 <= o + d (normcounts.py:84-87), and with max_mismatch_count = 0 a single one blocks it:
-  // lane = one entry of the list, which clears o in [x1 - d, x1 + u] in the blocks around it
-  auto block_ud = [&](int32_t qk, int* u, int* d) {
-    const int qs = qk - wsz, qe = qk + wsz;
-    if (qs < 0) { *u = wsz + qs; *d = wsz + (-qs); }
-    else if (qe > qlen) { *u = wsz + (qe - qlen); *d = qlen - qk; }
-    else { *u = wsz; *d = wsz; }
-  };
-  if (max_mm == 0) {
-    for (uint32_t m = (uint32_t)lane; m < nmm; m += 32) {
-      const int32_t km = S->mm[m];
-      const int32_t x1 = (int32_t)S->t[km] + 1;
-      auto clear_in_block = [&](int32_t kk) {
-        const uint32_t wd = S->w[kk];
-        const int32_t tk = (int32_t)S->t[kk], len = (int32_t)(wd >> 2), qk = (int32_t)S->q[kk];
-        int u, d;
-        block_ud(qk, &u, &d);
-        const int32_t lo = max(x1 - d, tk), hi = min(x1 + u, tk + len - 1); // inclusive
-        if (lo > hi) return;
-        int32_t q0 = qk + (lo - tk);
-        const int32_t q1 = qk + (hi - tk);
-        while (q0 <= q1) {
-          const int32_t wi = q0 >> 5, b0 = q0 & 31, n = min(32 - b0, q1 - q0 + 1);
-          atomicAnd(&S->qg[wi], ~(low_mask(n) << b0));
-          q0 += n;
-        }
-      };
-      for (int32_t kk = km + 1; kk < (int32_t)nops; kk++) { // blocks after the entry: they start at or after x1 - 1
-        if ((int32_t)S->t[kk] > x1 + 2 * wsz) break;
-        if ((S->w[kk] & 3u) == HM_OP_MATCH) clear_in_block(kk);
-      }
-      for (int32_t kk = km - 1; kk >= 0; kk--) {            // blocks before it
-        const uint32_t wd = S->w[kk];
-        if ((int32_t)S->t[kk] + op_ref_len(wd) - 1 < x1 - 2 * wsz) break;
-        if ((wd & 3u) == HM_OP_MATCH) clear_in_block(kk);
-      }
-    }
-    __syncwarp();
-  }
-
-  // ---- phase 3: the bits of the match runs to reference coordinates; the bases of the runs against the FASTA
-  const uint32_t* seq32 = reinterpret_cast<const uint32_t*>(b.seq + __ldg(b.seq_off + r));
-  const int32_t ts_lo = ts & 31;
-  uint32_t kp = 0; // first op that can matter for the current span of 32 words (only advances)
-  for (uint32_t jb = 0; jb < nw; jb += 32) {
-    const int32_t A0 = (int32_t)(jb * 32u) - ts_lo, A1 = A0 + 32 * 32; // the span in read offsets (reference position - ts)
-    while (kp < nops && (int32_t)S->t[kp] + op_ref_len(S->w[kp]) <= max(A0, 0)) kp++;
-    const uint32_t j = jb + (uint32_t)lane;
-    const int32_t a = (int32_t)(j * 32u) - ts_lo; // read offset of this lane's first position
-    const uint64_t W = (uint64_t)(ts >> 5) + j;
-    uint32_t cal = 0;
-    uint2 rf = make_uint2(0u, 0u);
-    if (j < nw) rf = __ldg(reinterpret_cast<const uint2*>(ref2) + W);
-    const unsigned long long rf64 = (unsigned long long)rf.x | ((unsigned long long)rf.y << 32);
-    for (uint32_t k = kp; k < nops; k++) {
-      const uint32_t wd = S->w[k];
-      const int32_t tk = (int32_t)S->t[k];
-      if (tk >= A1) break;
-      if ((wd & 3u) != HM_OP_MATCH) continue;
-      const int32_t len = (int32_t)(wd >> 2);
-      const int32_t lo = max(tk, a), hi = min(tk + len, a + 32);
-      if (j >= nw || lo >= hi) continue;
-      const int nb = hi - lo, sh = lo - a;
-      const int32_t qk = (int32_t)S->q[k];
-      const int32_t qb = qk + (lo - tk); // query position of the first base
-      uint32_t g = __funnelshift_r(S->qg[qb >> 5], S->qg[(qb >> 5) + 1], (uint32_t)(qb & 31)) & low_mask(nb);
-      if (max_mm != 0 && g) { // general threshold: count the list entries in the window of every candidate base
-        int u, d;
-        block_ud(qk, &u, &d);
-        uint32_t todo = g;
-        while (todo) {
-          const int bit = __ffs(todo) - 1;
-          todo &= todo - 1;
-          const int32_t o = lo + bit;
-          int cnt = 0;
-          for (uint32_t m = 0; m < nmm; m++) {
-            const int32_t x1 = (int32_t)S->t[S->mm[m]] + 1;
-            if (x1 > o + d) break;
-            cnt += (x1 >= o - u);
-          }
-          if (cnt > max_mm) g &= ~(1u << bit);
-        }
-      }
-      cal |= g << sh;
-      { // a cs match that is not the FASTA's base makes the column impure
-        const uint32_t s = (uint32_t)qb >> 4, bsh = 2u * ((uint32_t)qb & 15u);
-        const uint32_t need = bsh + 2u * (uint32_t)nb; // bits of the stream from word s on
-        const uint32_t w0 = __ldg(seq32 + s), w1 = need > 32u ? __ldg(seq32 + s + 1) : 0u, w2 = need > 64u ? __ldg(seq32 + s + 2) : 0u;
-        const unsigned long long rd = (unsigned long long)__funnelshift_r(w0, w1, bsh) | ((unsigned long long)__funnelshift_r(w1, w2, bsh) << 32);
-        const unsigned long long rng = (nb >= 32 ? ~0ull : ((1ull << (2 * nb)) - 1ull)) << (2 * sh);
-        const unsigned long long x = ((rd << (2 * sh)) ^ rf64) & rng;
-        if (x) {
-          unsigned long long dd = (x | (x >> 1)) & 0x5555555555555555ull;
-          while (dd) {
-            const int bit = __ffsll((long long)dd) - 1;
-            dd &= dd - 1;
-            mark_impure(impure, imp_words, (int64_t)(W << 5) + (bit >> 1));
-          }
-        }
-      }
-    }
-    if (j < nw) out[j] = cal;
   }
 }
 

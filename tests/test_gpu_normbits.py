@@ -58,13 +58,19 @@ def test_parameters(ctx, over):
     assert same(g, o)
 
 
-def test_reads_longer_than_the_staged_bitmap(ctx):
-    """reads of 40 - 60 kb do not fit the per-warp quality bitmap (32 768 bases): their whole span is evaluated exactly"""
-    d = synth.generate(400_000, seed=43, read_len_min=40_000, read_len_max=60_000, depth=8.0)
-    p = gtmodel.make_params(**cases.call_args(min_ref_count=2, min_alt_count=1))
+def test_reads_of_several_segments(ctx):
+    """reads of 40 - 60 kb: k_norm_prep walks a read in segments of 8192 query bases; words of cal bits that two
+    segments share, match runs and mismatch windows that cross a segment border"""
+    d = synth.generate(400_000, seed=43, read_len_min=40_000, read_len_max=60_000, depth=20.0)
+    p = gtmodel.make_params(**gtmodel.DEFAULT_CALL_ARGS)
     g, o = run(ctx, p, d, cases.chunkloci(0, 400_000))
     assert same(g, o)
-    assert ctx.last_norm_exact_sites() > 300_000
+    assert ctx.last_norm_exact_sites() < 40_000
+    # no mismatch at all for long stretches: match runs longer than a segment
+    d = synth.generate(300_000, seed=47, read_len_min=20_000, read_len_max=30_000, depth=15.0, sub_err_rate=0.0, indel_rate=0.0,
+                       somatic_rate=0.0, het_rate=2e-5, hom_rate=1e-5)
+    g, o = run(ctx, p, d, cases.chunkloci(0, 300_000))
+    assert same(g, o)
 
 
 def test_dense_ops(ctx):
