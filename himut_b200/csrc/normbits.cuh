@@ -42,8 +42,10 @@
 struct __align__(16) PrepWarp {
   uint32_t qg[NB_SEG / 32 + 4];     // bit q: BQ of the segment's query base q >= min_bq (then: "counts")
   uint32_t sq[NB_SEG / 16 + 4];     // the segment's 2-bit bases
+  uint32_t rf[NB_SEG / 16 + 16];    // the 2-bit reference under the segment (a segment with long deletions reads ref2 directly)
   uint32_t w[NB_OPS], t[NB_OPS + 1], q[NB_OPS + 1]; // t / q[k + 1] = where op k ends (t / q[nops]: the read's totals)
   int32_t mm[NB_OPS];               // op index of every entry of the mismatch list
+  uint32_t mr[NB_OPS];              // op index of every match run, ascending
 };
 
 // ============================================================================ k_ref_pack
@@ -93,7 +95,7 @@ __device__ __forceinline__ void mark_impure_range(uint32_t* impure, uint64_t imp
 // order; the trimmed ends are two masks; the mismatch window of a block (get_mismatch_range is anchored at the block's
 // first base, so the window of a mismatch differs from block to block) clears, per (mismatch, nearby block), one range
 // of query positions.  What is left is moved to reference coordinates run by run: a funnel shift per 32 positions.
-__global__ void __launch_bounds__(32 * NB_PREP_WARPS) k_norm_prep(DevBatch b, DevParams p, const uint32_t* ref2, const uint32_t* cw_off,
+__global__ void __launch_bounds__(32 * NB_PREP_WARPS, 6) k_norm_prep(DevBatch b, DevParams p, const uint32_t* ref2, const uint32_t* cw_off,
                                                                    uint32_t* calw, uint32_t* impure, uint64_t imp_words) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   const uint64_t r = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -111,6 +113,7 @@ __global__ void __launch_bounds__(32 * NB_PREP_WARPS) k_norm_prep(DevBatch b, De
   // ---- phase 1: op prefix scan (k_read_scan), ops staged, non-match ops -> impure
   uint32_t t_carry = 0, q_carry = qstart;
   int mm_base = 0, nm = 0, ns = 0, il = 0, dl = 0;
+  uint32_t n_runs = 0;
   for (uint32_t base = 0; base < nops; base += 32) {
     const uint32_t k = base + lane;
     const bool valid = k < nops;
@@ -136,6 +139,12 @@ __global__ void __launch_bounds__(32 * NB_PREP_WARPS) k_norm_prep(DevBatch b, De
       if (at < NB_OPS) S->mm[at] = (int32_t)k; // the op that is this entry of the list
     }
     mm_base += __popc(bal);
+    {
+      const bool is_run = valid && kind == HM_OP_MATCH && v != 0u;
+      const uint32_t br = __ballot_sync(HM_FULL, is_run);
+      if (is_run) { const uint32_t at = n_runs + __popc(br & ((1u << lane) - 1u)); if (at < NB_OPS) S->mr[at] = k; }
+      n_runs += __popc(br);
+    }
     if (valid) {
       if (kind == HM_OP_MATCH) nm += (int)v;
       else if (kind == HM_OP_SUB) ns += 1;
@@ -183,12 +192,37 @@ __global__ void __launch_bounds__(32 * NB_PREP_WARPS) k_norm_prep(DevBatch b, De
     else { *u = wsz; *d = wsz; }
   };
   uint32_t acc = 0, zacc = 0;
-  uint32_t ks = 0;                 // first op whose query bases reach into the current segment
   int32_t o_seg = 0;               // read offset at which the current segment's reference positions begin
-  uint32_t carry = 0;              // the bits an earlier segment left in word carry_j
-  int32_t carry_j = -1;
+  uint32_t rp = 0;                 // first match run that can reach into the current segment
+  // words that several match runs (or two segments) share are OR-ed into place; words no run reaches stay 0
+  for (uint32_t j = (uint32_t)lane; j < nw; j += 32) out[j] = 0u;
+  __syncwarp();
   for (int32_t seg0 = 0; seg0 < qlen; seg0 += (int32_t)NB_SEG) {
     const int32_t seg1 = min(seg0 + (int32_t)NB_SEG, qlen);
+    // The segment owns the read offsets [o_seg, o_next): o_next = where the next segment's first base lies.
+    // ks / ke: the first op that ends past query position seg0 / seg1 (op ends ascend: a count is an index)
+    uint32_t ks = 0, ke = 0;
+    int32_t o_next = te - ts;
+    uint32_t R0 = 0;
+    bool rf_staged = false;
+    if (do_bits) {
+      for (uint32_t base = 0; base < nops; base += 32) {
+        const uint32_t k = base + (uint32_t)lane;
+        const int32_t qe = k < nops ? (int32_t)S->q[k + 1] : INT32_MAX;
+        ks += __popc(__ballot_sync(HM_FULL, qe <= seg0));
+        ke += __popc(__ballot_sync(HM_FULL, qe <= seg1));
+      }
+      if (seg1 < qlen && ke < nops) {
+        const uint32_t wd = S->w[ke];
+        o_next = (int32_t)S->t[ke] + ((wd & 3u) == HM_OP_MATCH ? max(seg1 - (int32_t)S->q[ke], 0) : 0);
+      }
+      if (o_next > o_seg) { // the 2-bit reference under the segment, from its first 32-position word on
+        R0 = (uint32_t)((ts + o_seg) >> 5) << 1;
+        const uint32_t cnt = ((uint32_t)((ts + o_next - 1) >> 5) << 1) + 2u - R0;
+        rf_staged = cnt <= NB_SEG / 16 + 16;
+        if (rf_staged) for (uint32_t i = (uint32_t)lane; i < cnt; i += 32) S->rf[i] = __ldg(ref2 + R0 + i);
+      }
+    }
     // -- phase 2: the segment's quality words once — whole-read sum (np.mean is an exact integer sum divided once),
     // one bit per base "BQ >= min_bq"; the segment's bases staged next to them
     const uint32_t i0 = (uint32_t)seg0 >> 4, i1 = ((uint32_t)seg1 + 15u) >> 4;
@@ -286,90 +320,65 @@ __global__ void __launch_bounds__(32 * NB_PREP_WARPS) k_norm_prep(DevBatch b, De
     }
 
     // -- phase 3: the bits of the match runs to reference coordinates; the bases of the runs against the FASTA.
-    // The segment owns the read offsets [o_seg, o_next): o_next = where the next segment's first base lies.
-    // ks / ke: the first op that ends past query position seg0 / seg1 (op ends ascend: a count is an index)
-    uint32_t ke = 0;
-    {
-      uint32_t c0 = 0, c1 = 0;
-      for (uint32_t base = 0; base < nops; base += 32) {
-        const uint32_t k = base + (uint32_t)lane;
-        const int32_t qe = k < nops ? (int32_t)S->q[k + 1] : INT32_MAX;
-        c0 += __popc(__ballot_sync(HM_FULL, qe <= seg0));
-        c1 += __popc(__ballot_sync(HM_FULL, qe <= seg1));
-      }
-      ks = c0; ke = c1;
-    }
-    int32_t o_next = te - ts;
-    if (seg1 < qlen && ke < nops) {
-      const uint32_t wd = S->w[ke];
-      o_next = (int32_t)S->t[ke] + ((wd & 3u) == HM_OP_MATCH ? max(seg1 - (int32_t)S->q[ke], 0) : 0);
-    }
-    const uint32_t jA = (uint32_t)(o_seg + ts_lo) >> 5;
-    const uint32_t jB = o_next > o_seg ? (uint32_t)(o_next - 1 + ts_lo) >> 5 : jA; // last word with a position of the segment
-    uint32_t kl = ks; // this lane's op pointer: its words ascend, so it only advances
-    uint32_t last_cal = 0;
-    for (uint32_t jb = jA; jb <= jB && o_next > o_seg; jb += 32) {
-      const uint32_t j = jb + (uint32_t)lane;
-      uint32_t cal = (int32_t)j == carry_j ? carry : 0u;
-      if (j <= jB) {
-        const int32_t a = (int32_t)(j * 32u) - ts_lo; // read offset of this lane's first position
-        const int32_t lo_w = max(a, o_seg), hi_w = min(a + 32, o_next); // the word's positions this segment owns
-        const uint64_t W = (uint64_t)(ts >> 5) + j;
-        const uint2 rf = __ldg(reinterpret_cast<const uint2*>(ref2) + W);
-        const unsigned long long rf64 = (unsigned long long)rf.x | ((unsigned long long)rf.y << 32);
-        while (kl < nops && (int32_t)S->t[kl + 1] <= lo_w) kl++;
-        for (uint32_t k = kl; k < nops; k++) {
-          const int32_t tk = (int32_t)S->t[k];
-          if (tk >= hi_w) break;
-          const uint32_t wd = S->w[k];
-          if ((wd & 3u) != HM_OP_MATCH) continue;
-          const int32_t lo = max(tk, lo_w), hi = min((int32_t)S->t[k + 1], hi_w);
-          if (lo >= hi) continue;
-          const int nb = hi - lo, sh = lo - a;
-          const int32_t qk = (int32_t)S->q[k];
-          const int32_t qb = qk + (lo - tk) - seg0; // query position of the first base, in the segment
-          uint32_t g = __funnelshift_r(S->qg[qb >> 5], S->qg[(qb >> 5) + 1], (uint32_t)(qb & 31)) & low_mask(nb);
-          if (max_mm != 0 && g) { // general threshold: count the list entries in the window of every candidate base
-            int u, d;
-            block_ud(qk, &u, &d);
-            uint32_t todo = g;
-            while (todo) {
-              const int bit = __ffs(todo) - 1;
-              todo &= todo - 1;
-              const int32_t o = lo + bit;
-              int cnt = 0;
-              for (uint32_t m = 0; m < nmm; m++) {
-                const int32_t x1 = (int32_t)S->t[S->mm[m]] + 1;
-                if (x1 > o + d) break;
-                cnt += (x1 >= o - u);
-              }
-              if (cnt > max_mm) g &= ~(1u << bit);
+    // Run by run (warp-uniform), lanes = the run's 32-position words.
+    while (rp < n_runs && S->mr[rp] < ks) rp++; // first match run of the segment (runs ascend with the segments)
+    for (uint32_t ri = rp; ri < n_runs && o_next > o_seg; ri++) {
+      const uint32_t k = S->mr[ri];
+      const int32_t tk = (int32_t)S->t[k];
+      if (tk >= o_next) break;
+      const int32_t lo_s = max(tk, o_seg), hi_s = min((int32_t)S->t[k + 1], o_next); // the run's part in this segment
+      if (lo_s >= hi_s) continue;
+      const int32_t qk = (int32_t)S->q[k];
+      const uint32_t jf = (uint32_t)(lo_s + ts_lo) >> 5, jl = (uint32_t)(hi_s - 1 + ts_lo) >> 5;
+      for (uint32_t j = jf + (uint32_t)lane; j <= jl; j += 32) {
+        const int32_t a = (int32_t)(j * 32u) - ts_lo; // read offset of this word's first position
+        const int32_t lo = max(a, lo_s), hi = min(a + 32, hi_s);
+        const int nb = hi - lo, sh = lo - a;
+        const int32_t qb = qk + (lo - tk) - seg0; // query position of the first base, in the segment
+        uint32_t g = __funnelshift_r(S->qg[qb >> 5], S->qg[(qb >> 5) + 1], (uint32_t)(qb & 31)) & low_mask(nb);
+        if (max_mm != 0 && g) { // general threshold: count the list entries in the window of every candidate base
+          int u, d;
+          block_ud(qk, &u, &d);
+          uint32_t todo = g;
+          while (todo) {
+            const int bit = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const int32_t o = lo + bit;
+            int cnt = 0;
+            for (uint32_t m = 0; m < nmm; m++) {
+              const int32_t x1 = (int32_t)S->t[S->mm[m]] + 1;
+              if (x1 > o + d) break;
+              cnt += (x1 >= o - u);
             }
+            if (cnt > max_mm) g &= ~(1u << bit);
           }
-          cal |= g << sh;
-          { // a cs match that is not the FASTA's base makes the column impure
-            const uint32_t s = (uint32_t)qb >> 4, bsh = 2u * ((uint32_t)qb & 15u);
-            const uint32_t w0 = S->sq[s], w1 = S->sq[s + 1], w2 = S->sq[s + 2];
-            const unsigned long long rd = (unsigned long long)__funnelshift_r(w0, w1, bsh) | ((unsigned long long)__funnelshift_r(w1, w2, bsh) << 32);
-            const unsigned long long rng = (nb >= 32 ? ~0ull : ((1ull << (2 * nb)) - 1ull)) << (2 * sh);
-            const unsigned long long x = ((rd << (2 * sh)) ^ rf64) & rng;
-            if (x) {
-              unsigned long long dd = (x | (x >> 1)) & 0x5555555555555555ull;
-              while (dd) {
-                const int bit = __ffsll((long long)dd) - 1;
-                dd &= dd - 1;
-                mark_impure(impure, imp_words, (int64_t)(W << 5) + (bit >> 1));
-              }
+        }
+        if (nb == 32) out[j] = g;                    // the word is this run's alone
+        else if (g) atomicOr(out + j, g << sh);
+        { // a cs match that is not the FASTA's base makes the column impure
+          const uint64_t W = (uint64_t)(ts >> 5) + j;
+          uint2 rf;
+          if (rf_staged) rf = *reinterpret_cast<const uint2*>(&S->rf[2u * (uint32_t)W - R0]);
+          else rf = __ldg(reinterpret_cast<const uint2*>(ref2) + W);
+          const unsigned long long rf64 = (unsigned long long)rf.x | ((unsigned long long)rf.y << 32);
+          const uint32_t s = (uint32_t)qb >> 4, bsh = 2u * ((uint32_t)qb & 15u);
+          const uint32_t w0 = S->sq[s], w1 = S->sq[s + 1], w2 = S->sq[s + 2];
+          const unsigned long long rd = (unsigned long long)__funnelshift_r(w0, w1, bsh) | ((unsigned long long)__funnelshift_r(w1, w2, bsh) << 32);
+          const unsigned long long rng = (nb >= 32 ? ~0ull : ((1ull << (2 * nb)) - 1ull)) << (2 * sh);
+          const unsigned long long x = ((rd << (2 * sh)) ^ rf64) & rng;
+          if (x) {
+            unsigned long long dd = (x | (x >> 1)) & 0x5555555555555555ull;
+            while (dd) {
+              const int bit = __ffsll((long long)dd) - 1;
+              dd &= dd - 1;
+              mark_impure(impure, imp_words, (int64_t)(W << 5) + (bit >> 1));
             }
           }
         }
-        out[j] = cal;
       }
-      if (jb + 32 > jB) last_cal = __shfl_sync(HM_FULL, cal, (int)(jB - jb)); // the segment's last word: the next segment may add to it
     }
-    if (o_next > o_seg) { carry = last_cal; carry_j = (int32_t)jB; }
     o_seg = o_next;
-    __syncwarp(); // the stores of this segment's last word precede the next segment's
+    __syncwarp(); // shared memory is refilled by the next segment
   }
   unsigned long long tot = acc;
 #pragma unroll
@@ -388,7 +397,6 @@ __global__ void __launch_bounds__(32 * NB_PREP_WARPS) k_norm_prep(DevBatch b, De
     b.gate[r] = ok ? 1 : 0;
   }
   if (nw != 0 && (!staged || has_zero)) {
-    if (!staged) for (uint32_t j = (uint32_t)lane; j < nw; j += 32) out[j] = 0u;
     const int64_t per = ((int64_t)(te - ts) + 31) / 32; // every lane a piece of [ts, te)
     mark_impure_range(impure, imp_words, (int64_t)ts + per * lane, min((int64_t)te, (int64_t)ts + per * (lane + 1)));
   }
