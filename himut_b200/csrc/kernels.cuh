@@ -198,8 +198,10 @@ __global__ void __launch_bounds__(256) k_read_scan(DevBatch b, DevParams p) {
 // hm_bq_compact -> the one-byte-per-base quality stream.  One warp per read, 16 bases per lane and step: the lane's
 // 16 mask bits, a warp scan of the clear-bit counts to find its first exception, then the exceptions dropped into
 // the modal-filled 16-byte word.  Bytes past the read's length (padding) are written as 0.
+// exc_minmax[2 r], [2 r + 1]: the smallest / largest exception of read r (255 / 0 when it has none): what lets the
+// normcounts pass take "BQ >= min_bq" straight from the bitmap (normbits.cuh).
 __global__ void __launch_bounds__(256) k_bq_expand(DevBatch b, const uint8_t* mask, const uint8_t* exc, const uint64_t* exc_off,
-                                                   uint32_t modal, uint8_t* bq_out) {
+                                                   uint32_t modal, uint8_t* bq_out, uint8_t* exc_minmax, unsigned long long* exp_total) {
   const uint64_t r = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (r >= b.n_reads) return;
@@ -211,6 +213,7 @@ __global__ void __launch_bounds__(256) k_bq_expand(DevBatch b, const uint8_t* ma
   const uint32_t n16 = (qlen + 15u) >> 4;
   const uint32_t fill = modal * 0x01010101u;
   uint32_t run = 0; // exceptions consumed by earlier steps
+  uint32_t e_min = 255u, e_max = 0u, acc = 0u;
   for (uint32_t base = 0; base < n16; base += 32) {
     const uint32_t i = base + lane;
     uint32_t bits = 0xffffu, valid = 0;
@@ -236,14 +239,23 @@ __global__ void __launch_bounds__(256) k_bq_expand(DevBatch b, const uint8_t* ma
         while (z4) {
           const int k = __ffs(z4) - 1;
           z4 &= z4 - 1;
-          word = (word & ~(0xffu << (8 * k))) | ((uint32_t)__ldg(ex + at) << (8 * k));
+          const uint32_t ev = (uint32_t)__ldg(ex + at);
+          e_min = min(e_min, ev); e_max = max(e_max, ev);
+          word = (word & ~(0xffu << (8 * k))) | (ev << (8 * k));
           at++;
         }
         o[wd] = word;
+        acc = sum4(word, acc);
       }
       out[i] = make_uint4(o[0], o[1], o[2], o[3]);
     }
   }
+  e_min = __reduce_min_sync(HM_FULL, e_min);
+  e_max = __reduce_max_sync(HM_FULL, e_max);
+  unsigned long long tot = acc; // the read's quality sum (bamlib.get_qv divides it once)
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) tot += __shfl_xor_sync(HM_FULL, tot, d);
+  if (lane == 0) { exc_minmax[2 * r] = (uint8_t)e_min; exc_minmax[2 * r + 1] = (uint8_t)e_max; exp_total[r] = tot; }
 }
 
 // ============================================================================ lookups

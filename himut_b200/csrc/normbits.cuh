@@ -96,7 +96,9 @@ __device__ __forceinline__ void mark_impure_range(uint32_t* impure, uint64_t imp
 // first base, so the window of a mismatch differs from block to block) clears, per (mismatch, nearby block), one range
 // of query positions.  What is left is moved to reference coordinates run by run: a funnel shift per 32 positions.
 __global__ void __launch_bounds__(32 * NB_PREP_WARPS, 6) k_norm_prep(DevBatch b, DevParams p, const uint32_t* ref2, const uint32_t* cw_off,
-                                                                   uint32_t* calw, uint32_t* impure, uint64_t imp_words) {
+                                                                   uint32_t* calw, uint32_t* impure, uint64_t imp_words,
+                                                                   const uint16_t* mask16, const uint8_t* exc_minmax,
+                                                                   const unsigned long long* exp_total, uint32_t modal) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   const uint64_t r = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
@@ -191,6 +193,16 @@ __global__ void __launch_bounds__(32 * NB_PREP_WARPS, 6) k_norm_prep(DevBatch b,
     else if (qe > qlen) { *u = wsz + (qe - qlen); *d = qlen - qk; }
     else { *u = wsz; *d = wsz; }
   };
+  // A batch that came as bitmap + exceptions (hm_bq_compact) and whose exceptions of this read all lie below min_bq:
+  // "BQ >= min_bq" is the bitmap itself (or nothing, when the modal value is below min_bq too), the quality sum was
+  // taken when the stream was expanded, and no quality byte is touched here.
+  bool use_mask = false;
+  uint32_t e_min = 255u;
+  if (mask16 != nullptr && modal != 0u) {
+    e_min = __ldg(exc_minmax + 2 * r);
+    use_mask = (int)__ldg(exc_minmax + 2 * r + 1) < p.min_bq;
+  }
+  const uint64_t bq_bit0 = __ldg(b.bq_off + r); // the read's first bit in the bitmap
   uint32_t acc = 0, zacc = 0;
   int32_t o_seg = 0;               // read offset at which the current segment's reference positions begin
   uint32_t rp = 0;                 // first match run that can reach into the current segment
@@ -198,6 +210,7 @@ __global__ void __launch_bounds__(32 * NB_PREP_WARPS, 6) k_norm_prep(DevBatch b,
   for (uint32_t j = (uint32_t)lane; j < nw; j += 32) out[j] = 0u;
   __syncwarp();
   for (int32_t seg0 = 0; seg0 < qlen; seg0 += (int32_t)NB_SEG) {
+    if (use_mask && !do_bits) break; // nothing of this read is wanted
     const int32_t seg1 = min(seg0 + (int32_t)NB_SEG, qlen);
     // The segment owns the read offsets [o_seg, o_next): o_next = where the next segment's first base lies.
     // ks / ke: the first op that ends past query position seg0 / seg1 (op ends ascend: a count is an index)
@@ -216,11 +229,18 @@ __global__ void __launch_bounds__(32 * NB_PREP_WARPS, 6) k_norm_prep(DevBatch b,
         const uint32_t wd = S->w[ke];
         o_next = (int32_t)S->t[ke] + ((wd & 3u) == HM_OP_MATCH ? max(seg1 - (int32_t)S->q[ke], 0) : 0);
       }
-      if (o_next > o_seg) { // the 2-bit reference under the segment, from its first 32-position word on
-        R0 = (uint32_t)((ts + o_seg) >> 5) << 1;
-        const uint32_t cnt = ((uint32_t)((ts + o_next - 1) >> 5) << 1) + 2u - R0;
-        rf_staged = cnt <= NB_SEG / 16 + 16;
-        if (rf_staged) for (uint32_t i = (uint32_t)lane; i < cnt; i += 32) S->rf[i] = __ldg(ref2 + R0 + i);
+      if (o_next > o_seg) { // the 2-bit reference under the segment, from a 64-position border on; loads first, then stores
+        R0 = (uint32_t)((ts + o_seg) >> 6) << 2;
+        const uint32_t cnt4 = ((((uint32_t)((ts + o_next - 1) >> 5) << 1) + 2u - R0) + 3u) >> 2;
+        rf_staged = cnt4 <= (NB_SEG / 16 + 16) / 4;
+        if (rf_staged) {
+          const uint4* src = reinterpret_cast<const uint4*>(ref2 + R0);
+          uint4 v[5];
+#pragma unroll
+          for (int u = 0; u < 5; u++) { const uint32_t i = (uint32_t)lane + 32u * u; v[u] = i < cnt4 ? __ldg(src + i) : make_uint4(0u, 0u, 0u, 0u); }
+#pragma unroll
+          for (int u = 0; u < 5; u++) { const uint32_t i = (uint32_t)lane + 32u * u; if (i < cnt4) reinterpret_cast<uint4*>(S->rf)[i] = v[u]; }
+        }
       }
     }
     // -- phase 2: the segment's quality words once — whole-read sum (np.mean is an exact integer sum divided once),
@@ -251,7 +271,35 @@ __global__ void __launch_bounds__(32 * NB_PREP_WARPS, 6) k_norm_prep(DevBatch b,
       }
       if (do_bits) qg16[i - i0] = (uint16_t)(bits & live);
     };
-    {
+    if (use_mask) {
+      // -- phase 2 without the quality bytes: the segment's bitmap words and its bases
+      const uint32_t nqw = ((uint32_t)(seg1 - seg0) + 31u) >> 5;
+      const uint64_t u16_0 = (bq_bit0 >> 4) + ((uint32_t)seg0 >> 4); // bq_off is a multiple of 16: the bitmap is 16-bit aligned per read
+      const uint32_t* m32 = reinterpret_cast<const uint32_t*>(mask16 + (u16_0 & ~1ull));
+      const uint32_t msh = (uint32_t)(u16_0 & 1ull) * 16u;
+      const bool modal_counts = modal >= (uint32_t)p.min_bq;
+      const uint4* s4 = reinterpret_cast<const uint4*>(seq32 + i0);
+      const uint32_t n4 = (i1 - i0 + 3u) >> 2;
+      uint32_t ma[NB_SEG / 1024], mb[NB_SEG / 1024];
+      uint4 sv[NB_SEG / 2048];
+#pragma unroll
+      for (uint32_t u = 0; u < NB_SEG / 1024; u++) { // all loads first
+        const uint32_t wi = (uint32_t)lane + 32u * u;
+        const bool on = wi < nqw && modal_counts;
+        ma[u] = on ? __ldg(m32 + wi) : 0u; mb[u] = on ? __ldg(m32 + wi + 1) : 0u;
+      }
+#pragma unroll
+      for (uint32_t u = 0; u < NB_SEG / 2048; u++) { const uint32_t i = (uint32_t)lane + 32u * u; sv[u] = i < n4 ? __ldg(s4 + i) : make_uint4(0u, 0u, 0u, 0u); }
+#pragma unroll
+      for (uint32_t u = 0; u < NB_SEG / 1024; u++) {
+        const uint32_t wi = (uint32_t)lane + 32u * u;
+        // past the read: padding, then the next read's bits
+        if (wi < nqw) S->qg[wi] = __funnelshift_r(ma[u], mb[u], msh) & low_mask(qlen - (seg0 + (int32_t)(wi * 32u)));
+      }
+#pragma unroll
+      for (uint32_t u = 0; u < NB_SEG / 2048; u++) { const uint32_t i = (uint32_t)lane + 32u * u; if (i < n4) reinterpret_cast<uint4*>(S->sq)[i] = sv[u]; }
+      __syncwarp();
+    } else {
       uint32_t i = i0 + (uint32_t)lane;
       for (; i + 96 < i1; i += 128) {
         const uint4 a0 = ldg_stream16(q4 + i), a1 = ldg_stream16(q4 + i + 32), a2 = ldg_stream16(q4 + i + 64), a3 = ldg_stream16(q4 + i + 96);
@@ -269,7 +317,7 @@ __global__ void __launch_bounds__(32 * NB_PREP_WARPS, 6) k_norm_prep(DevBatch b,
     if (!do_bits) continue;
     { // the words the funnel shifts below may touch past the segment's last base
       const uint32_t n16 = i1 - i0;
-      for (uint32_t i = n16 + (uint32_t)lane; i < ((n16 + 1u) & ~1u) + 4u; i += 32) qg16[i] = 0;
+      for (uint32_t i = (use_mask ? ((n16 + 1u) & ~1u) : n16) + (uint32_t)lane; i < ((n16 + 1u) & ~1u) + 4u; i += 32) qg16[i] = 0;
       for (uint32_t i = n16 + (uint32_t)lane; i < n16 + 3u; i += 32) S->sq[i] = 0;
     }
     __syncwarp();
@@ -286,7 +334,11 @@ __global__ void __launch_bounds__(32 * NB_PREP_WARPS, 6) k_norm_prep(DevBatch b,
     __syncwarp();
     // with max_mismatch_count = 0 a single list entry in its window blocks a base: lane = one entry of the list,
     // which clears o in [x1 - d, x1 + u] in the blocks around it (the part that lies in this segment)
+#ifdef NB_X_NO_2B
+    if (max_mm == 12345) {
+#else
     if (max_mm == 0) {
+#endif
       for (uint32_t m = (uint32_t)lane; m < nmm; m += 32) {
         const int32_t km = S->mm[m];
         const int32_t x1 = (int32_t)S->t[km] + 1;
@@ -321,6 +373,9 @@ __global__ void __launch_bounds__(32 * NB_PREP_WARPS, 6) k_norm_prep(DevBatch b,
 
     // -- phase 3: the bits of the match runs to reference coordinates; the bases of the runs against the FASTA.
     // Run by run (warp-uniform), lanes = the run's 32-position words.
+#ifdef NB_X_NO_P3
+    if (o_next > -5) { o_seg = o_next; __syncwarp(); continue; }
+#endif
     while (rp < n_runs && S->mr[rp] < ks) rp++; // first match run of the segment (runs ascend with the segments)
     for (uint32_t ri = rp; ri < n_runs && o_next > o_seg; ri++) {
       const uint32_t k = S->mr[ri];
@@ -355,6 +410,7 @@ __global__ void __launch_bounds__(32 * NB_PREP_WARPS, 6) k_norm_prep(DevBatch b,
         }
         if (nb == 32) out[j] = g;                    // the word is this run's alone
         else if (g) atomicOr(out + j, g << sh);
+#ifndef NB_X_NO_SEQ
         { // a cs match that is not the FASTA's base makes the column impure
           const uint64_t W = (uint64_t)(ts >> 5) + j;
           uint2 rf;
@@ -375,6 +431,7 @@ __global__ void __launch_bounds__(32 * NB_PREP_WARPS, 6) k_norm_prep(DevBatch b,
             }
           }
         }
+#endif
       }
     }
     o_seg = o_next;
@@ -383,7 +440,8 @@ __global__ void __launch_bounds__(32 * NB_PREP_WARPS, 6) k_norm_prep(DevBatch b,
   unsigned long long tot = acc;
 #pragma unroll
   for (int d = 16; d > 0; d >>= 1) tot += __shfl_xor_sync(HM_FULL, tot, d);
-  const bool has_zero = __any_sync(HM_FULL, (zacc & 0x80808080u) != 0u);
+  bool has_zero = __any_sync(HM_FULL, (zacc & 0x80808080u) != 0u);
+  if (use_mask) { tot = __ldg(exp_total + r); has_zero = e_min == 0u; }
   if (lane == 0) {
     b.bq_total[r] = tot;
     b.n_match[r] = nm; b.n_sub[r] = ns; b.ins_len[r] = il; b.del_len[r] = dl; b.n_mm[r] = mm_base;

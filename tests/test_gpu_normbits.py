@@ -109,3 +109,29 @@ def test_phase_and_sets_cases_on_the_bit_path(ctx):
         o = oracle.normcounts_chunks(c["params"], c["batch"], c["ref"].encode(), c["chunk_table"], c["common"], c["pon"], c["phase"])
         assert same(g, o), name
         assert "k_norm_bits" in [n for n, _ in ctx.last_kernel_times()], name
+
+
+@pytest.mark.parametrize("over", [dict(), dict(min_bq=20), dict(min_bq=94), dict(min_bq=60, min_trim=0.05), dict(min_qv=92)])
+def test_compact_upload_takes_the_bits_from_the_bitmap(ctx, over, monkeypatch):
+    """a batch uploaded as modal bitmap + exceptions (what the workers upload): where every exception of a read lies
+    below min_bq the bit "BQ >= min_bq" is the bitmap's and the quality sum is the one taken at expansion; a read with
+    an exception at or above min_bq goes through its quality bytes; both must equal the plain upload and the oracle"""
+    from himut_b200 import bamdec
+    d = synth.generate(250_000, seed=48, read_len_min=9_000, read_len_max=21_000)
+    p = gtmodel.make_params(**cases.call_args(**over))
+    loci = cases.chunkloci(0, 250_000)
+    chunks = d.batch.chunk_table(loci)
+    o = oracle.normcounts_chunks(p, d.batch, d.ref, chunks)
+    cq = bamdec.compact_bq(d.batch, threads=2)
+    ctx.set_params(p)
+    ctx.set_site_sets()
+    ctx.upload_compact(d.batch, cq)
+    g = ctx.normcounts_chunks(d.ref, chunks)
+    assert same(g, o)
+    monkeypatch.setenv("HIMUT_B200_NORM_BYTES", "1")
+    g2 = ctx.normcounts_chunks(d.ref, chunks)
+    assert same(g2, o)
+    monkeypatch.delenv("HIMUT_B200_NORM_BYTES")
+    rec, log = ctx.call_chunks(chunks)  # the expanded stream is still what `call` reads
+    o_rec, o_log = oracle.call_chunks(p, d.batch, chunks)
+    assert list(log) == list(o_log)

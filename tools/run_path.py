@@ -14,6 +14,7 @@ ap.add_argument("path", choices=["call", "normcounts"])
 ap.add_argument("--contig-mb", type=int, default=8)
 ap.add_argument("--reps", type=int, default=3)
 ap.add_argument("--with-seq", action="store_true", help="call: upload the 2-bit base stream too (the worker mirror does not)")
+ap.add_argument("--compact", action="store_true", help="upload the qualities as bitmap + exceptions, as the workers do")
 a = ap.parse_args()
 
 import cases  # noqa: E402
@@ -26,7 +27,12 @@ chunks = d.batch.chunk_table(cases.chunkloci(0, n))
 with lib.Context(0) as ctx:
     ctx.set_params(params)
     ctx.set_site_sets()
-    ctx.upload(d.batch if (a.path == "normcounts" or a.with_seq) else d.batch.without_seq())
+    batch = d.batch if (a.path == "normcounts" or a.with_seq) else d.batch.without_seq()
+    if a.compact:
+        from himut_b200 import bamdec
+        ctx.upload_compact(batch, bamdec.compact_bq(d.batch))
+    else:
+        ctx.upload(batch)
     for _ in range(a.reps):
         if a.path == "call":
             rec, log = ctx.call_chunks(chunks, view=True)
