@@ -34,7 +34,7 @@
 #include "normfast.cuh"
 
 #define NB_OPS 192u                 // ops of a read staged in shared memory (more: the read's span goes to the exact pass)
-#define NB_SEG 8192u                // query bases a warp holds in shared memory at a time (a read is walked segment by segment)
+#define NB_SEG 4096u                // query bases a warp holds in shared memory at a time (a read is walked segment by segment)
 #define NB_PREP_WARPS 4
 #define NB_SPAN 1024                // reference positions per warp of k_norm_bits
 #define NB_BITS_WARPS 4
@@ -95,7 +95,7 @@ __device__ __forceinline__ void mark_impure_range(uint32_t* impure, uint64_t imp
 // order; the trimmed ends are two masks; the mismatch window of a block (get_mismatch_range is anchored at the block's
 // first base, so the window of a mismatch differs from block to block) clears, per (mismatch, nearby block), one range
 // of query positions.  What is left is moved to reference coordinates run by run: a funnel shift per 32 positions.
-__global__ void __launch_bounds__(32 * NB_PREP_WARPS, 6) k_norm_prep(DevBatch b, DevParams p, const uint32_t* ref2, const uint32_t* cw_off,
+__global__ void __launch_bounds__(32 * NB_PREP_WARPS, 8) k_norm_prep(DevBatch b, DevParams p, const uint32_t* ref2, const uint32_t* cw_off,
                                                                    uint32_t* calw, uint32_t* impure, uint64_t imp_words,
                                                                    const uint16_t* mask16, const uint8_t* exc_minmax,
                                                                    const unsigned long long* exp_total, uint32_t modal) {
