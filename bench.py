@@ -486,29 +486,46 @@ def leg_phase(args, T, ctx, d):
 
 
 def leg_normcounts(args, T, ctx, d, chunks):
+    """the callable-base half of `himut normcounts` on the resident batch, uploaded as himut_b200/normcounts.py uploads
+    it (qualities as modal bitmap + exceptions, expanded on the device); `plain_upload`: the same on a batch uploaded
+    with one quality byte per base"""
+    from himut_b200 import bamdec
     batch = d.batch
-    ctx.upload(batch)
-    ctx.normcounts_chunks(d.ref, chunks)
+    n_norm = max(2, args.steps // 3)
     state = {}
 
     def step():
         state["r"] = ctx.normcounts_chunks(d.ref, chunks)
 
-    n_norm = max(2, args.steps // 3)
-    ms = T.run(step, n_norm) / n_norm
+    def measure():
+        ctx.normcounts_chunks(d.ref, chunks)
+        ms = T.run(step, n_norm) / n_norm
+        ctx.kernel_timing(True)
+        step()
+        nk = {k: v for k, v in ctx.last_kernel_times()}
+        ctx.kernel_timing(False)
+        return ms, nk
+
+    ctx.upload(batch)
+    ms_plain, nk_plain = measure()
+    plain = state["r"]
+    ctx.upload_compact(batch, bamdec.compact_bq(batch))
+    ms, nk = measure()
     ccs_tri, ref_tri, nlog, nties = state["r"]
-    ctx.kernel_timing(True)
-    step()
-    nk = {k: v for k, v in ctx.last_kernel_times()}
-    ctx.kernel_timing(False)
+    same = all(np.array_equal(np.asarray(a), np.asarray(b)) for a, b in zip(plain[:3], state["r"][:3])) and plain[3] == nties
     n_base, n_op, n_read = batch_counts(batch)
     peak, _ = measured_peak()
     nbytes = 1.25 * n_base + 4.0 * n_op + 40.0 * n_read + 1.0 * len(d.ref)
     return {"value": d.aligned_bases / (ms * 1e-3), "unit": "bases/s", "ms_per_step": ms, "steps": n_norm, "kernel_ms_per_step": nk,
             "frac_step": nbytes / (ms * 1e-3) / 1e9 / peak,
+            "step_bytes_formula": "SURVEY 8(d): 1.25*N_base + 4*N_op + 40*N_read + 1*N_refpos",
+            "upload": "hm_upload_batch_compact (what himut_b200/normcounts.py does per decode group)",
+            "plain_upload": {"value": d.aligned_bases / (ms_plain * 1e-3), "ms_per_step": ms_plain, "kernel_ms_per_step": nk_plain,
+                             "frac_step": nbytes / (ms_plain * 1e-3) / 1e9 / peak, "same_result": bool(same)},
             "callable_bases": int(nlog[13]), "callable_positions": int(ref_tri.sum()), "alt_ties_flagged": int(nties),
             "positions_evaluated_exactly": ctx.last_norm_exact_sites(), "positions": int(len(d.ref)),
-            "bound": "instruction issue (integer pass over every aligned base) + the exact fp64 pass over the listed positions, see DESIGN.md"}
+            "bound": "k_norm_prep: instruction issue (one pass over every read: bit vectors in reference coordinates); k_norm_bits: "
+                     "latency; then the exact fp64 pass over the listed positions (sector gather), see DESIGN.md 4.1"}
 
 
 def leg_bam_to_vcf(bam_path, contig_len, aligned_bases, tmp):

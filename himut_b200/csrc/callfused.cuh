@@ -35,8 +35,12 @@
 #define HC_TILE_WORDS (HC_TILE / 32u)
 #define HC_CAPD 4096u                  // distinct positions of a tile kept in shared memory (more: global scratch)
 #define HC_SORT_THREADS 512
+#ifndef HC_BLK
 #define HC_BLK 2048u                   // bytes per quality stage
+#endif
+#ifndef HC_NS
 #define HC_NS 2                        // stages per warp
+#endif
 #define HC_WARPS 8                     // warps per CTA of k_call_pairs / k_call_scan
 #define HC_KEY_POS_BITS 27             // a chunk may span < 2^27 positions on this path (else the first version runs)
 
@@ -563,7 +567,9 @@ __global__ void __launch_bounds__(256) k_site_range2(DevBatch b, const hm_chunk*
 // and the site list are built while they fly — and keeps HC_NS copies in flight; every block is summed from shared
 // memory and then serves the listed sites whose query position lies in it.  Other pairs fetch their few quality bytes
 // directly.
+#ifndef HC_SCAN_WARPS
 #define HC_SCAN_WARPS 4
+#endif
 #define HC_SITES 96 // sites of a pair kept in the list (a 15 kb read at 30x sees ~70); the rest go the direct way
 
 struct __align__(16) ScanWarp {
