@@ -123,7 +123,7 @@ struct hm_ctx {
   uint64_t n_cw = 0;                        // words of all cal bit vectors (>= 2^32: the path is not used)
   uint16_t cert_thr[256];                   // smallest callable count that certifies a pure position of depth n (0xffff: none)
   uint64_t packed_pos = 0;                  // positions b_ref2 / b_tri8 cover for the reference now in b_ref (0: not packed)
-  DevBuf b_cw_off, b_calw, b_impure, b_ref2, b_tri8, b_thr, b_span_off, b_exc_minmax, b_exp_total;
+  DevBuf b_cw_off, b_calw, b_impure, b_ref2, b_tri8, b_thr, b_span_off, b_exc_minmax, b_exp_total, b_sdiff, b_cal_ok;
   bool compact_resident = false;            // the resident batch came as bitmap + exceptions: both are still on the device
   uint32_t modal = 0;
 };
@@ -353,7 +353,7 @@ void hm_destroy(hm_ctx* ctx) {
                     &ctx->b_pair_off, &ctx->b_pair_hap, &ctx->b_qseen, &ctx->b_keys, &ctx->b_keys_sorted, &ctx->b_cub,
                     &ctx->b_records, &ctx->b_counters, &ctx->b_ref, &ctx->b_norm_out, &ctx->b_lut, &ctx->b_tile_off, &ctx->b_agg, &ctx->b_geom, &ctx->b_bidx, &ctx->b_brecs, &ctx->b_sites, &ctx->b_koff, &ctx->b_tile_info, &ctx->b_edge_counts, &ctx->b_edge_hpos, &ctx->b_edge_href, &ctx->b_bqmask, &ctx->b_bqexc, &ctx->b_bqexc_off,
                     &ctx->b_cgeom, &ctx->b_seg_keys, &ctx->b_seg_read, &ctx->b_keys_tmp, &ctx->b_gscratch, &ctx->b_czero, &ctx->b_first_pair, &ctx->b_tiles, &ctx->b_site_valid, &ctx->b_pair_c,
-                    &ctx->b_cw_off, &ctx->b_calw, &ctx->b_impure, &ctx->b_ref2, &ctx->b_tri8, &ctx->b_thr, &ctx->b_span_off, &ctx->b_exc_minmax, &ctx->b_exp_total};
+                    &ctx->b_cw_off, &ctx->b_calw, &ctx->b_impure, &ctx->b_ref2, &ctx->b_tri8, &ctx->b_thr, &ctx->b_span_off, &ctx->b_exc_minmax, &ctx->b_exp_total, &ctx->b_sdiff, &ctx->b_cal_ok};
   for (DevBuf* b : bufs) b->release();
   if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
   if (ctx->h_cnt_pin) cudaFreeHost(ctx->h_cnt_pin);
@@ -1482,6 +1482,9 @@ static int hm_normcounts_impl(hm_ctx* ctx, const uint8_t* refseq, size_t ref_len
     imp_words = n_pos / 32;
     CU(ctx->b_impure.ensure(imp_words * 4 + 16));
     CU(cudaMemsetAsync(ctx->b_impure.p, 0, imp_words * 4, ctx->stream));
+    CU(ctx->b_sdiff.ensure(imp_words * 4 + 16));
+    CU(cudaMemsetAsync(ctx->b_sdiff.p, 0, imp_words * 4, ctx->stream));
+    CU(ctx->b_cal_ok.ensure((size_t)ctx->n_reads + 16));
     CU(ctx->b_calw.ensure((size_t)ctx->n_cw * 4 + 16));
     if ((rc = upload(ctx, ctx->b_thr, ctx->cert_thr, 256))) return rc;
     if ((rc = upload(ctx, ctx->b_span_off, span_off.data(), span_off.size()))) return rc;
@@ -1489,7 +1492,7 @@ static int hm_normcounts_impl(hm_ctx* ctx, const uint8_t* refseq, size_t ref_len
     k_norm_prep<<<(unsigned)((ctx->n_reads + NB_PREP_WARPS - 1) / NB_PREP_WARPS), 32 * NB_PREP_WARPS, sizeof(PrepWarp) * NB_PREP_WARPS, ctx->stream>>>(
         ctx->db, ctx->dp, ctx->b_ref2.as<uint32_t>(), ctx->b_cw_off.as<uint32_t>(), ctx->b_calw.as<uint32_t>(), ctx->b_impure.as<uint32_t>(), imp_words,
         ctx->compact_resident && !getenv("HIMUT_B200_NORM_BYTES") ? ctx->b_bqmask.as<uint16_t>() : nullptr, ctx->b_exc_minmax.as<uint8_t>(),
-        ctx->b_exp_total.as<unsigned long long>(), ctx->modal);
+        ctx->b_exp_total.as<unsigned long long>(), ctx->modal, ctx->b_sdiff.as<uint32_t>(), ctx->b_cal_ok.as<uint8_t>());
     t_end(ctx);
     CU(cudaGetLastError());
   } else if ((rc = launch_read_scan(ctx))) return rc;
@@ -1554,6 +1557,14 @@ static int hm_normcounts_impl(hm_ctx* ctx, const uint8_t* refseq, size_t ref_len
         const double md = ctx->params.md_threshold;
         const int md_k = !(md == md) ? 256 : md < 0.0 ? 0 : md >= 255.0 ? 256 : (int)floor(md) + 1; // depth >= md_k <=> depth > md_threshold
         const unsigned bgrid = (unsigned)std::min<uint64_t>((n_spans + NB_BITS_WARPS - 1) / NB_BITS_WARPS, (uint64_t)n_sm * (ctx->params.phase ? 4 : 6));
+        CU(ctx->b_tile_info.ensure((size_t)n_spans * 16 + 16));
+        if (n_spans) {
+          t_begin(ctx, "k_span_ranges");
+          k_span_ranges<<<(unsigned)((n_spans + 255) / 256), 256, 0, ctx->stream>>>(ctx->db, ctx->b_chunks.as<hm_chunk>(), (uint32_t)n_chunks,
+                                                                                ctx->b_span_off.as<uint64_t>(), n_spans, ctx->b_tile_info.as<uint4>());
+          t_end(ctx);
+          CU(cudaGetLastError());
+        }
         for (int attempt = 0; attempt < 2 && n_spans; attempt++) {
           CU(ctx->b_sites.ensure(site_cap * 8));
           if (attempt) { // the list overflowed: start over with the exact size
@@ -1563,7 +1574,7 @@ static int hm_normcounts_impl(hm_ctx* ctx, const uint8_t* refseq, size_t ref_len
           t_begin(ctx, "k_norm_bits");
           (ctx->params.phase ? k_norm_bits<true> : k_norm_bits<false>)<<<bgrid, 32 * NB_BITS_WARPS, 0, ctx->stream>>>(
               ctx->db, ctx->dp, ctx->b_thr.as<uint16_t>(), (int)ctx->cert.n_min, md_k, ctx->b_chunks.as<hm_chunk>(), (uint32_t)n_chunks,
-              ctx->b_pair_off.as<uint64_t>(), ctx->b_pair_hap.as<uint8_t>(), ctx->b_span_off.as<uint64_t>(), n_spans, ctx->b_cw_off.as<uint32_t>(),
+              ctx->b_pair_off.as<uint64_t>(), ctx->b_pair_hap.as<uint8_t>(), ctx->b_tile_info.as<uint4>(), n_spans, ctx->b_cw_off.as<uint32_t>(),
               ctx->b_calw.as<uint32_t>(), ctx->b_impure.as<uint32_t>(), ctx->b_tri8.as<uint8_t>(), ctx->b_norm_out.as<NormOut>(),
               ctx->b_sites.as<unsigned long long>(), site_cap, d_nsites);
           t_end(ctx);
@@ -1643,8 +1654,15 @@ static int hm_normcounts_impl(hm_ctx* ctx, const uint8_t* refseq, size_t ref_len
                                                                               keys, nb, site_lo, site_n, entries, stride);
           t_end(ctx);
         } else {
-          t_begin(ctx, "k_norm_entries_by_read");
+          t_begin(ctx, use_bits ? "k_norm_entries_bits" : "k_norm_entries_by_read");
           CU(cudaMemsetAsync(entries, 0xff, stride * HM_SITE_SLOTS * 4, ctx->stream));
+          if (use_bits)
+            k_norm_entries_bits<<<(unsigned)((n_pairs * 32 + 255) / 256), 256, 0, ctx->stream>>>(
+                ctx->db, ctx->dp, ctx->b_chunks.as<hm_chunk>(), (uint32_t)n_chunks, ctx->b_pair_off.as<uint64_t>(), n_pairs,
+                ctx->b_pair_hap.as<uint8_t>(), site_keys, ctx->b_koff.as<uint32_t>(), (uint64_t)s0, nb, site_lo, site_n, entries, stride,
+                ctx->b_cw_off.as<uint32_t>(), ctx->b_calw.as<uint32_t>(), ctx->b_cal_ok.as<uint8_t>(), ctx->b_sdiff.as<uint32_t>(),
+                ctx->b_ref2.as<uint32_t>(), ctx->compact_resident && !getenv("HIMUT_B200_NORM_BYTES") ? ctx->b_bqmask.as<uint16_t>() : nullptr, ctx->modal);
+          else
           k_norm_entries_by_read<<<(unsigned)((n_pairs * 32 + 255) / 256), 256, 0, ctx->stream>>>(
               ctx->db, ctx->dp, ctx->b_chunks.as<hm_chunk>(), (uint32_t)n_chunks, ctx->b_pair_off.as<uint64_t>(), n_pairs,
               ctx->b_pair_hap.as<uint8_t>(), site_keys, ctx->b_koff.as<uint32_t>(), (uint64_t)s0, nb, site_lo, site_n, entries, stride);

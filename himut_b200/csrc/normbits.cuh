@@ -98,7 +98,8 @@ __device__ __forceinline__ void mark_impure_range(uint32_t* impure, uint64_t imp
 __global__ void __launch_bounds__(32 * NB_PREP_WARPS, 8) k_norm_prep(DevBatch b, DevParams p, const uint32_t* ref2, const uint32_t* cw_off,
                                                                    uint32_t* calw, uint32_t* impure, uint64_t imp_words,
                                                                    const uint16_t* mask16, const uint8_t* exc_minmax,
-                                                                   const unsigned long long* exp_total, uint32_t modal) {
+                                                                   const unsigned long long* exp_total, uint32_t modal, uint32_t* sdiff,
+                                                                   uint8_t* cal_ok) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   const uint64_t r = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
@@ -428,6 +429,7 @@ __global__ void __launch_bounds__(32 * NB_PREP_WARPS, 8) k_norm_prep(DevBatch b,
               const int bit = __ffsll((long long)dd) - 1;
               dd &= dd - 1;
               mark_impure(impure, imp_words, (int64_t)(W << 5) + (bit >> 1));
+              mark_impure(sdiff, imp_words, (int64_t)(W << 5) + (bit >> 1)); // the exact pass reads this read's base here
             }
           }
         }
@@ -443,6 +445,7 @@ __global__ void __launch_bounds__(32 * NB_PREP_WARPS, 8) k_norm_prep(DevBatch b,
   bool has_zero = __any_sync(HM_FULL, (zacc & 0x80808080u) != 0u);
   if (use_mask) { tot = __ldg(exp_total + r); has_zero = e_min == 0u; }
   if (lane == 0) {
+    cal_ok[r] = do_bits ? 1 : 0; // the read's cal words are what update_tri2count counts (the exact pass takes them from there)
     b.bq_total[r] = tot;
     b.n_match[r] = nm; b.n_sub[r] = ns; b.ins_len[r] = il; b.del_len[r] = dl; b.n_mm[r] = mm_base;
     bool ok = true; // caller.py:310-317 / normcounts.py:302-309, in order
@@ -457,6 +460,86 @@ __global__ void __launch_bounds__(32 * NB_PREP_WARPS, 8) k_norm_prep(DevBatch b,
   if (nw != 0 && (!staged || has_zero)) {
     const int64_t per = ((int64_t)(te - ts) + 31) / 32; // every lane a piece of [ts, te)
     mark_impure_range(impure, imp_words, (int64_t)ts + per * lane, min((int64_t)te, (int64_t)ts + per * (lane + 1)));
+  }
+}
+
+// ============================================================================ k_norm_entries_bits
+// k_norm_entries_by_read (normfast.cuh) for the bit-vector path: "is this base counted by update_tri2count" is the
+// read's cal bit (no window / trim arithmetic), the base of a match run is the FASTA's unless k_norm_prep saw it
+// differ (sdiff), and on a compact upload the quality is the modal value wherever the bitmap says so — the byte
+// stream is touched for the exceptions only.  Reads k_norm_prep could not stage go the general way (norm_entry).
+__global__ void __launch_bounds__(256) k_norm_entries_bits(DevBatch b, DevParams p, const hm_chunk* chunks, uint32_t n_chunks,
+                                                           const uint64_t* pair_off, uint64_t n_pairs, const uint8_t* pair_flag,
+                                                           const unsigned long long* keys, const uint32_t* koff, uint64_t s0, uint64_t nb,
+                                                           const uint32_t* site_lo, const uint32_t* site_n, uint32_t* entries,
+                                                           uint64_t stride, const uint32_t* cw_off, const uint32_t* calw,
+                                                           const uint8_t* cal_ok, const uint32_t* sdiff, const uint32_t* ref2,
+                                                           const uint16_t* mask16, uint32_t modal) {
+  __shared__ uint32_t s_w[8][HM_BYREAD_MAX_OPS], s_t[8][HM_BYREAD_MAX_OPS], s_q[8][HM_BYREAD_MAX_OPS];
+  const uint64_t pr = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (pr >= n_pairs) return;
+  const uint32_t pf = pair_flag[pr];
+  if (!(pf & HM_PF_FETCHED)) return;
+  const uint32_t c = upper_bound_dev(pair_off, n_chunks + 1, pr) - 1;
+  const hm_chunk ch = chunks[c];
+  const uint32_t r = ch.read_lo + (uint32_t)(pr - pair_off[c]);
+  const int32_t ts = __ldg(b.tstart + r), te = __ldg(b.tend + r);
+  const uint32_t n = __ldg(b.n_ops + r);
+  if (n == 0) return;
+  const uint32_t k_lo = max(koff[c], (uint32_t)s0), k_hi = min(koff[c + 1], (uint32_t)(s0 + nb));
+  if (k_lo >= k_hi) return;
+  const unsigned long long base = (unsigned long long)c << 36;
+  const uint32_t s_lo = warp_lower_bound_u64(keys, k_lo, k_hi, base | ((unsigned long long)(uint32_t)(ts + 1) << 4), lane);
+  const uint32_t s_hi = warp_lower_bound_u64(keys, s_lo, k_hi, base | ((unsigned long long)(uint32_t)(te + 2) << 4), lane);
+  if (s_lo >= s_hi) return;
+  const uint64_t o0 = __ldg(b.op_off + r);
+  const bool staged = n <= HM_BYREAD_MAX_OPS && __ldg(cal_ok + r) != 0;
+  if (staged) {
+    for (uint32_t k = lane; k < n; k += 32) {
+      s_w[wid][k] = __ldg(b.ops + o0 + k); s_t[wid][k] = __ldg(b.op_t + o0 + k); s_q[wid][k] = __ldg(b.op_q + o0 + k);
+    }
+    __syncwarp();
+  }
+  const uint64_t bq0 = __ldg(b.bq_off + r), sq0 = __ldg(b.seq_off + r);
+  const uint32_t* cw = calw + __ldg(cw_off + r);
+  const uint32_t w_first = (uint32_t)ts >> 5;
+  for (uint32_t ki = s_lo + lane; ki < s_hi; ki += 32) {
+    const uint32_t li = ki - (uint32_t)s0;
+    const uint32_t slot = r - __ldg(site_lo + li);
+    if (slot >= HM_SITE_SLOTS || slot >= __ldg(site_n + li)) continue; // deep pileups: k_norm_reduce computes these itself
+    const int32_t pos = (int32_t)((__ldg(keys + ki) >> 4) & 0xffffffffull) - 1;
+    uint32_t e;
+    if (!staged) e = norm_entry(b, p, ch, pf, r, pos);
+    else {
+      const uint32_t off = (uint32_t)(pos - ts);
+      uint32_t lo = 0, hi = n; // last op with op_t <= off
+      while (lo < hi) { const uint32_t m = (lo + hi) >> 1; if (s_t[wid][m] <= off) lo = m + 1; else hi = m; }
+      const int k = (int)lo - 1;
+      int ins = 0;
+      for (int j = k; j >= 0 && s_t[wid][j] == off; j--) ins += ((s_w[wid][j] & 3u) == HM_OP_INS);
+      const uint32_t wd = s_w[wid][k], kind = wd & 3u, t_op = s_t[wid][k], q0 = s_q[wid][k];
+      const uint32_t rl = (uint32_t)op_ref_len(wd);
+      uint32_t a = HM_ENT_NONE, bq = 0, cnt = 0;
+      if (rl != 0 && off < t_op + rl) {
+        if (kind == HM_OP_DEL) a = 5u;
+        else {
+          const uint32_t q = q0 + (kind == HM_OP_MATCH ? off - t_op : 0u);
+          bool is_modal = false;
+          if (mask16 != nullptr) { const uint64_t bit = bq0 + q; is_modal = (__ldg(mask16 + (bit >> 4)) >> (bit & 15u)) & 1u; }
+          bq = is_modal ? modal : (uint32_t)b.bq[bq0 + q];
+          if (kind == HM_OP_SUB) { a = (wd >> 5) & 3u; cnt = (pf & HM_PF_PASS) ? 1u : 0u; } // normcounts.py:95-108: always counted
+          else {
+            const bool differs = (__ldg(sdiff + ((uint32_t)pos >> 5)) >> ((uint32_t)pos & 31u)) & 1u;
+            a = differs ? (uint32_t)((b.seq[sq0 + (q >> 2)] >> (2 * (q & 3u))) & 3u)
+                        : ((__ldg(ref2 + ((uint32_t)pos >> 4)) >> (2u * ((uint32_t)pos & 15u))) & 3u);
+            if (pf & HM_PF_PASS) cnt = (__ldg(cw + (((uint32_t)pos >> 5) - w_first)) >> ((uint32_t)pos & 31u)) & 1u;
+          }
+        }
+      }
+      e = a | (bq << 3) | ((uint32_t)min(ins, 255) << 11) | (((pf >> HM_PF_HAP_SHIFT) & 3u) << 19) | (cnt << 21);
+    }
+    entries[(uint64_t)slot * stride + li] = e;
   }
 }
 
@@ -499,12 +582,28 @@ __device__ __forceinline__ uint32_t bits_sum(const uint32_t (&P)[8], uint32_t m)
   return s;
 }
 
+// per span of k_norm_bits: chunk, origin on the 1024 grid, the file-order range of reads that can cover one of its
+// positions (running-max(tend) > first position, tstart < end) — so the warps of k_norm_bits do not search
+__global__ void __launch_bounds__(256) k_span_ranges(DevBatch b, const hm_chunk* chunks, uint32_t n_chunks, const uint64_t* span_off,
+                                                     uint64_t n_spans, uint4* span_info) {
+  const uint64_t span = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (span >= n_spans) return;
+  const uint32_t c = upper_bound_dev(span_off, n_chunks + 1, span) - 1;
+  const hm_chunk ch = chunks[c];
+  const int32_t s0 = (int32_t)(((uint32_t)(ch.start >> 10) + (uint32_t)(span - __ldg(span_off + c))) << 10);
+  const int32_t lo_pos = max(s0, ch.start), hi_pos = min(s0 + NB_SPAN, ch.end);
+  const uint32_t n_in = ch.read_hi - ch.read_lo;
+  const uint32_t r_lo = ch.read_lo + count_le_kary_i32(b.pmax_tend + ch.read_lo, n_in, lo_pos);
+  const uint32_t r_hi = ch.read_lo + count_le_kary_i32(b.tstart + ch.read_lo, n_in, hi_pos - 1);
+  span_info[span] = make_uint4(c, (uint32_t)s0, r_lo, r_hi);
+}
+
 // thr[n]: the smallest callable count that certifies a pure position of depth n (host, make_norm_cert), 0xffff: none.
 // md_k: depth >= md_k is "read_depth > md_threshold" (256: never).
 template <bool kPhase>
-__global__ void __launch_bounds__(32 * NB_BITS_WARPS, kPhase ? 3 : 5) k_norm_bits(DevBatch b, DevParams p, const uint16_t* thr, int n_min, int md_k, const hm_chunk* chunks,
+__global__ void __launch_bounds__(32 * NB_BITS_WARPS, kPhase ? 4 : 6) k_norm_bits(DevBatch b, DevParams p, const uint16_t* thr, int n_min, int md_k, const hm_chunk* chunks,
                                                                    uint32_t n_chunks, const uint64_t* pair_off, const uint8_t* pair_flag,
-                                                                   const uint64_t* span_off, uint64_t n_spans, const uint32_t* cw_off,
+                                                                   const uint4* span_info, uint64_t n_spans, const uint32_t* cw_off,
                                                                    const uint32_t* calw, const uint32_t* impure, const uint8_t* tri8,
                                                                    NormOut* out, unsigned long long* sites, unsigned long long site_cap,
                                                                    unsigned long long* n_sites) {
@@ -519,14 +618,11 @@ __global__ void __launch_bounds__(32 * NB_BITS_WARPS, kPhase ? 3 : 5) k_norm_bit
   __syncthreads();
 
   for (uint64_t span = (uint64_t)blockIdx.x * NB_BITS_WARPS + wid; span < n_spans; span += (uint64_t)gridDim.x * NB_BITS_WARPS) {
-    const uint32_t c = upper_bound_dev(span_off, n_chunks + 1, span) - 1;
+    const uint4 si = __ldg(span_info + span); // chunk, origin, read range (k_span_ranges)
+    const uint32_t c = si.x, r_lo = si.z, r_hi = si.w;
     const hm_chunk ch = chunks[c];
-    const int32_t s0 = (int32_t)(((uint32_t)(ch.start >> 10) + (uint32_t)(span - __ldg(span_off + c))) << 10);
+    const int32_t s0 = (int32_t)si.y;
     const int32_t lo_pos = max(s0, ch.start), hi_pos = min(s0 + NB_SPAN, ch.end);
-    const uint32_t n_in = ch.read_hi - ch.read_lo;
-    // reads that cover a position of [lo_pos, hi_pos): running-max(tend) > lo_pos, tstart < hi_pos
-    const uint32_t r_lo = ch.read_lo + count_le_kary_i32(b.pmax_tend + ch.read_lo, n_in, lo_pos);
-    const uint32_t r_hi = ch.read_lo + count_le_kary_i32(b.tstart + ch.read_lo, n_in, hi_pos - 1);
     const bool deep = r_hi > r_lo && r_hi - r_lo > 255u; // the 8-bit counters would overflow: every position to the exact pass
     const uint64_t pbase = __ldg(pair_off + c);
     const int32_t P0 = s0 + 32 * lane;
@@ -571,6 +667,7 @@ __global__ void __launch_bounds__(32 * NB_BITS_WARPS, kPhase ? 3 : 5) k_norm_bit
 
     // ---- per position, bit-parallel (normcounts.py:317-400)
     const uint4 ta = __ldg(reinterpret_cast<const uint4*>(tri8 + P0)), tb = __ldg(reinterpret_cast<const uint4*>(tri8 + P0) + 1);
+    const uint32_t imp = __ldg(impure + W);
     const uint32_t tw[8] = {ta.x, ta.y, ta.z, ta.w, tb.x, tb.y, tb.z, tb.w};
     uint32_t alive = 0;
 #pragma unroll
@@ -580,7 +677,6 @@ __global__ void __launch_bounds__(32 * NB_BITS_WARPS, kPhase ? 3 : 5) k_norm_bit
       alive |= (((nz * 0x00204081u) >> 21) & 15u) << (4 * g);
     }
     alive &= low_mask(hi_pos - P0) & ~low_mask(lo_pos - P0);
-    const uint32_t imp = __ldg(impure + W);
     uint32_t push = deep ? alive : (alive & imp);
     uint32_t ok = 0;
     if (!deep) {
