@@ -366,8 +366,6 @@ def leg_contig(args, T, ctx, d, params, chunks, tmpdir):
     assert list(sync_state["log"]) == list(log)
     k_ms, launches = kernel_breakdown(ctx, step_sync)
     ctx.records_wait()
-    ctx_b.close()
-    ctx.set_stream(T.stream.cuda_stream)
     # ---- end to end: the worker's call on the decoder's own buffers ----
     bam = os.path.join(tmpdir, "contig.bam")
     t0 = time.perf_counter()
@@ -387,10 +385,37 @@ def leg_contig(args, T, ctx, d, params, chunks, tmpdir):
 
     for _ in range(2):
         step_e2e()
-    ms_e2e = T.run(step_e2e, args.steps)
+    ms_e2e_one = T.run(step_e2e, args.steps, streams=streams[:1])
     assert list(state["log_e"]) == list(log), "the decoded batch gives other counters than the generated one"
     srt = lambda a: np.sort(a, order=["chunk", "tpos", "ref", "alt"]).tobytes()  # records come back in no particular order
     assert srt(state["rec_e"]) == srt(rec), "end-to-end records differ from the resident call's"
+    # the same host buffers through the worker's two alternating contexts (himut_b200/caller.py:call_region): upload + submit
+    # on one, then collect the other — the upload of a call overlaps the kernels and the record copy of the call before it
+    e_state = {"k": 0, "pending": None}
+
+    def step_e2e_alt():
+        c = pair[e_state["k"] % 2]
+        e_state["k"] += 1
+        c.upload_compact(dbatch, cq)
+        c.call_chunks_submit(dchunks)
+        if e_state["pending"] is not None:
+            e_state["rec"], e_state["log"] = e_state["pending"].call_chunks_collect(view=True)
+        e_state["pending"] = c
+
+    def drain_e2e():
+        if e_state["pending"] is not None:
+            e_state["rec"], e_state["log"] = e_state["pending"].call_chunks_collect(view=True)
+            e_state["pending"] = None
+        for c in pair:
+            c.records_wait()
+
+    for _ in range(4):
+        step_e2e_alt()
+    drain_e2e()
+    ms_e2e = T.run(step_e2e_alt, args.steps, after=drain_e2e, streams=streams)
+    assert list(e_state["log"]) == list(log) and srt(e_state["rec"]) == srt(rec), "pipelined end-to-end records differ from the resident call's"
+    ctx_b.close()
+    ctx.set_stream(T.stream.cuda_stream)
     h2d = int(cq.nbytes() + dbatch.ops.nbytes + sum(a.nbytes for a in small) + dchunks.nbytes)
     # the same call with one quality byte per base and the 2-bit bases (what round 1's workers uploaded)
     ctx.pin(batch)
@@ -415,10 +440,14 @@ def leg_contig(args, T, ctx, d, params, chunks, tmpdir):
         "value": aligned * args.steps / (ms_total * 1e-3), "ms_per_step": step_ms,
         "e2e": {"value": aligned * args.steps / (ms_e2e * 1e-3), "unit": "bases/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": int(rec.nbytes + 256), "ms_per_step": ms_e2e / args.steps,
-                "call": "hm_call_batch_compact = hm_upload_batch_compact + hm_call_chunks, what himut_b200/caller.py:call_region does per "
-                        "decode group; host buffers exactly as csrc/bamdec.c leaves them (no base stream, qualities as modal bitmap + "
-                        "exceptions written by its record-parse pass), page-locked once before the loop; records byte-identical to the "
-                        "resident call's",
+                "call": "hm_upload_batch_compact + hm_call_chunks_submit / hm_call_chunks_collect on two alternating contexts: what "
+                        "himut_b200/caller.py:call_region does from decode group to decode group (the upload of a call overlaps the "
+                        "kernels and the record copy of the call before it; every step uploads the whole batch again and its records "
+                        "reach host memory inside the timed region); host buffers exactly as csrc/bamdec.c leaves them (no base stream, "
+                        "qualities as modal bitmap + exceptions written by its record-parse pass), page-locked once before the loop; "
+                        "records byte-identical to the resident call's",
+                "one_context": {"value": aligned * args.steps / (ms_e2e_one * 1e-3), "ms_per_step": ms_e2e_one / args.steps,
+                                "call": "hm_call_batch_compact on one context, each call finished before the next upload starts"},
                 "decode_seconds_outside_timed_region": t_decode, "bam_write_seconds": t_write},
         "value_one_context": {"value": aligned / (ms_sync * 1e-3), "unit": "bases/s", "ms_per_step": ms_sync,
                               "call": "hm_call_chunks on one context, every call collected before the next is enqueued"},

@@ -109,6 +109,7 @@ struct hm_ctx {
   uint32_t edge_band = 0;
   // fused call path
   std::vector<uint64_t> h_ops_prefix;       // ops of the reads before read r (candidate slots a chunk can need)
+  std::vector<uint8_t> h_named;             // scratch of the shared-query-name test of an upload
   bool dup_names = false;                   // two primary records of the resident batch share a query name
   int call_path = 0;                        // hm_last_call_path
   bool ktiming = true;                      // HM_OPT_KERNEL_TIMING: CUDA events around the kernels of a call
@@ -474,6 +475,18 @@ static int upload_batch_impl(hm_ctx* ctx, const hm_read_batch* b, const hm_bq_co
   const uint64_t n = b->n_reads;
   if (n >= (1ull << 32)) return fail(ctx, HM_ERR_ARG, "too many reads in one batch");
   if ((b->seq_bytes & 15) || (b->bq_bytes & 15)) return fail(ctx, HM_ERR_ARG, "seq / bq buffers must be padded to 16 bytes");
+  // The large streams leave first (copy engine, in stream order); the O(reads) validation below runs on the host while
+  // they move.  A batch that fails it is never used (have_batch stays false); the copies are waited for before the
+  // error is returned, so the caller may free its buffers.
+  int rc;
+#define UP(buf, field, count) if ((rc = upload(ctx, ctx->buf, b->field, (size_t)(count)))) return rc
+  if (cq) {
+    if ((rc = upload(ctx, ctx->b_bqmask, cq->mask, (size_t)cq->mask_bytes))) return rc;
+    if ((rc = upload(ctx, ctx->b_bqexc, cq->exc, (size_t)cq->exc_bytes, 16))) return rc;
+  } else { UP(b_bq, bq, b->bq_bytes); }
+  if (has_seq) { UP(b_seq, seq, b->seq_bytes); }
+  UP(b_ops, ops, b->n_ops_total);
+#define BAD(...) do { cudaStreamSynchronize(ctx->stream); return fail(ctx, HM_ERR_ARG, __VA_ARGS__); } while (0)
   // structural validation (cheap, O(reads)); the kernels binary-search on these invariants
   ctx->h_pmax.resize(n);
   ctx->h_tix_off.resize(n + 1);
@@ -482,13 +495,15 @@ static int upload_batch_impl(hm_ctx* ctx, const hm_read_batch* b, const hm_bq_co
   int32_t run = INT32_MIN;
   uint32_t max_q = 0;
   for (uint64_t r = 0; r < n; r++) {
-    if (r && b->tstart[r] < b->tstart[r - 1]) return fail(ctx, HM_ERR_ARG, "read %llu: batch is not sorted by reference_start", (unsigned long long)r);
+    if (r && b->tstart[r] < b->tstart[r - 1]) BAD("read %llu: batch is not sorted by reference_start", (unsigned long long)r);
     if (b->tend[r] < b->tstart[r] || b->qlen[r] <= 0 || b->qstart[r] < 0 || b->qstart[r] > b->qlen[r])
-      return fail(ctx, HM_ERR_ARG, "read %llu: inconsistent coordinates", (unsigned long long)r);
-    if ((has_seq && (b->seq_off[r] & 15)) || (b->bq_off[r] & 15)) return fail(ctx, HM_ERR_ARG, "read %llu: seq_off / bq_off not 16-byte aligned", (unsigned long long)r);
+      BAD("read %llu: inconsistent coordinates", (unsigned long long)r);
+    if ((has_seq && (b->seq_off[r] & 15)) || (b->bq_off[r] & 15)) BAD("read %llu: seq_off / bq_off not 16-byte aligned", (unsigned long long)r);
     if (b->bq_off[r] + (uint64_t)b->qlen[r] > b->bq_bytes || (has_seq && b->seq_off[r] + ((uint64_t)b->qlen[r] + 3) / 4 > b->seq_bytes) ||
         b->op_off[r] + b->n_ops[r] > b->n_ops_total)
-      return fail(ctx, HM_ERR_ARG, "read %llu: offsets outside the buffers", (unsigned long long)r);
+      BAD("read %llu: offsets outside the buffers", (unsigned long long)r);
+    if (cq && (cq->exc_off[r] > cq->exc_off[r + 1] || cq->exc_off[r + 1] > cq->exc_bytes || cq->exc_off[r + 1] - cq->exc_off[r] > (uint64_t)b->qlen[r]))
+      BAD("read %llu: hm_bq_compact.exc_off is inconsistent", (unsigned long long)r);
     if (b->tend[r] > run) run = b->tend[r];
     ctx->h_pmax[r] = run;
     ctx->h_tix_off[r] = (uint32_t)n_tix;
@@ -504,7 +519,8 @@ static int upload_batch_impl(hm_ctx* ctx, const hm_read_batch* b, const hm_bq_co
   ctx->h_ops_prefix[0] = 0;
   ctx->dup_names = false;
   {
-    std::vector<uint8_t> named((size_t)max_q + 1, 0);
+    ctx->h_named.assign((size_t)max_q + 1, 0);
+    uint8_t* named = ctx->h_named.data();
     for (uint64_t r = 0; r < n; r++) {
       ctx->h_ops_prefix[r + 1] = ctx->h_ops_prefix[r] + b->n_ops[r];
       if (b->flags[r] & HM_READ_SECONDARY) continue;
@@ -512,25 +528,17 @@ static int upload_batch_impl(hm_ctx* ctx, const hm_read_batch* b, const hm_bq_co
       named[b->qname_id[r]] = 1;
     }
   }
-  int rc;
-#define UP(buf, field, count) if ((rc = upload(ctx, ctx->buf, b->field, (size_t)(count)))) return rc
   UP(b_tstart, tstart, n); UP(b_tend, tend, n); UP(b_qstart, qstart, n); UP(b_qlen, qlen, n);
   UP(b_mapq, mapq, n); UP(b_flags, flags, n); UP(b_qname, qname_id, n);
   UP(b_bq_off, bq_off, n); UP(b_op_off, op_off, n); UP(b_n_ops, n_ops, n);
-  if (has_seq) { UP(b_seq_off, seq_off, n); UP(b_seq, seq, b->seq_bytes); }
-  UP(b_ops, ops, b->n_ops_total);
-  if (!cq) { UP(b_bq, bq, b->bq_bytes); }
-  else {
-    for (uint64_t r = 0; r < n; r++)
-      if (cq->exc_off[r] > cq->exc_off[r + 1] || cq->exc_off[r + 1] > cq->exc_bytes || cq->exc_off[r + 1] - cq->exc_off[r] > (uint64_t)b->qlen[r])
-        return fail(ctx, HM_ERR_ARG, "read %llu: hm_bq_compact.exc_off is inconsistent", (unsigned long long)r);
+  if (has_seq) { UP(b_seq_off, seq_off, n); }
+  if (cq) {
     CU(ctx->b_bq.ensure(b->bq_bytes + 16));
-    if ((rc = upload(ctx, ctx->b_bqmask, cq->mask, (size_t)cq->mask_bytes))) return rc;
-    if ((rc = upload(ctx, ctx->b_bqexc, cq->exc, (size_t)cq->exc_bytes, 16))) return rc;
     if ((rc = upload(ctx, ctx->b_bqexc_off, cq->exc_off, (size_t)n + 1))) return rc;
   }
 #undef UP
-  if (b->n_reads && (b->tstart[0] < 0 || n_tix >= (1ull << 32))) return fail(ctx, HM_ERR_ARG, "negative reference_start, or too many (read, tile) pairs in one batch");
+  if (b->n_reads && (b->tstart[0] < 0 || n_tix >= (1ull << 32))) BAD("negative reference_start, or too many (read, tile) pairs in one batch");
+#undef BAD
   ctx->h_tix_off[n] = (uint32_t)n_tix;
   ctx->n_tix = n_tix;
   if ((rc = upload(ctx, ctx->b_pmax, ctx->h_pmax.data(), n))) return rc;

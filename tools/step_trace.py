@@ -1,0 +1,92 @@
+#!/usr/bin/env python
+"""Where a resident `himut call` step goes when two contexts alternate (bench.py's headline loop): host wall time of
+submit / collect per step, the CUDA-event time of every kernel group of every call, and the whole loop by wall clock
+and by events.  Diagnostics only: python tools/step_trace.py [--contig-mb 64] [--steps 12] [--mode alt|sync|sync_wait]"""
+import argparse
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--contig-mb", type=int, default=64)
+ap.add_argument("--steps", type=int, default=12)
+ap.add_argument("--mode", default="alt,sync,sync_wait")
+ap.add_argument("--no-ktiming", action="store_true")
+a = ap.parse_args()
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+import cases  # noqa: E402
+from himut_b200 import gtmodel, lib, synth  # noqa: E402
+
+n = a.contig_mb * 1_000_000
+d = synth.generate(n, seed=5, copy=False)
+params = gtmodel.make_params(**gtmodel.DEFAULT_CALL_ARGS)
+chunks = d.batch.chunk_table(cases.chunkloci(0, n))
+batch = d.batch.without_seq()
+torch.cuda.set_device(0)
+ctxs = [lib.Context(0), lib.Context(0)]
+streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+for c, st in zip(ctxs, streams):
+    c.set_stream(st.cuda_stream)
+    c.set_params(params)
+    c.set_site_sets()
+    c.omit_restatements(True)
+    c.kernel_timing(not a.no_ktiming)
+    c.upload(batch)
+
+
+def fmt(kt):
+    return " ".join("%s %.3f" % (k.replace("k_", ""), v) for k, v in kt)
+
+
+for mode in a.mode.split(","):
+    state = {"k": 0, "pending": None}
+    rows = []
+
+    def step():
+        t0 = time.perf_counter()
+        if mode == "alt":
+            c = ctxs[state["k"] % 2]
+            state["k"] += 1
+            c.call_chunks_submit(chunks)
+            t1 = time.perf_counter()
+            kt = None
+            if state["pending"] is not None:
+                state["pending"].call_chunks_collect(view=True)
+                kt = state["pending"].last_kernel_times()
+            state["pending"] = c
+        else:
+            ctxs[0].call_chunks(chunks, view=True, wait=(mode == "sync_wait"))
+            t1 = time.perf_counter()
+            kt = ctxs[0].last_kernel_times()
+        t2 = time.perf_counter()
+        rows.append((1e3 * (t1 - t0), 1e3 * (t2 - t1), kt))
+
+    def drain():
+        if state["pending"] is not None:
+            state["pending"].call_chunks_collect(view=True)
+            state["pending"] = None
+        for c in ctxs:
+            c.records_wait()
+
+    for _ in range(8):
+        step()
+    drain()
+    rows.clear()
+    torch.cuda.synchronize()
+    w0 = time.perf_counter()
+    for _ in range(a.steps):
+        step()
+    drain()
+    torch.cuda.synchronize()
+    wall = 1e3 * (time.perf_counter() - w0)
+    print("== mode %s: %.3f ms per step by wall clock (%d steps)" % (mode, wall / a.steps, a.steps))
+    for i, (s, c, kt) in enumerate(rows):
+        print("  step %2d  host submit %.3f collect %.3f ms | %s" % (i, s, c, fmt(kt) if kt else ""))
+for c in ctxs:
+    c.close()
