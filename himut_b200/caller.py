@@ -99,18 +99,22 @@ def call_region(ctx, bam_file, chrom, chunkloci_lst, chunk_sets, phase, want_nam
         kept.append(rec)
         laters.append(min(starts[idx[-1] + 1:], default=None))
 
+    lap = worker.Laps("call_region %s" % chrom)  # HIMUT_B200_WORKER_TIMING=1: where the host time of a contig goes
     try:
         k = 0
         for idx, batch, cq, table, release in worker.pipelined_groups(src, chrom, chunkloci_lst, groups, chunk_sets, seq=False,
                                                                       pad=1 if phase else 0):
+            lap("wait for decode")
             if batch.n_reads == 0:
                 release()
                 continue
             c = ctxs[k % len(ctxs)]
             k += 1
             pins.pin([cq.mask, cq.exc, batch.ops])
+            lap("page-lock")
             c.upload_compact(batch, cq)
             release()  # everything is on the device: the decoder may reuse the buffers
+            lap("upload")
             if len(ctxs) > 1:
                 c.call_chunks_submit(table)
                 if pending is not None:
@@ -118,14 +122,19 @@ def call_region(ctx, bam_file, chrom, chunkloci_lst, chunk_sets, phase, want_nam
                 pending = (c, idx)
             else:
                 finish((c, idx, c.call_chunks(table)))
+            lap("submit + collect")
         if pending is not None:
             finish(pending)
+        lap("submit + collect")
         names = src.reader.qnames_blob(tally.seen) if want_names else None
     finally:
         pins.close()
         src.close()
+        lap("unlock + close")
     kept = carry_som_seen(kept, laters)
     rec = np.concatenate(kept) if kept else np.zeros(0, abi.SITE_DTYPE)
+    lap("merge")
+    lap.report()
     return rec, tally.count(), names
 
 

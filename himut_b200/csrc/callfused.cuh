@@ -29,7 +29,9 @@
 #include "kernels.cuh"
 #include "normcounts.cuh" // mbarrier / cp.async.bulk helpers
 
-#define HC_MAX_OPS 128                 // ops of a read staged per warp; longer lists use the batch's global op_t / op_q
+#ifndef HC_MAX_OPS
+#define HC_MAX_OPS 96                  // ops of a read staged per warp; longer lists use the batch's global op_t / op_q
+#endif
 #define HC_TILE_BITS 17
 #define HC_TILE (1u << HC_TILE_BITS)   // positions per sort tile
 #define HC_TILE_WORDS (HC_TILE / 32u)
@@ -570,7 +572,17 @@ __global__ void __launch_bounds__(256) k_site_range2(DevBatch b, const hm_chunk*
 #ifndef HC_SCAN_WARPS
 #define HC_SCAN_WARPS 4
 #endif
-#define HC_SITES 96 // sites of a pair kept in the list (a 15 kb read at 30x sees ~70); the rest go the direct way
+// Ten CTAs of four warps per SM is where the kernel runs best (B200, 64 Mb contig at 30x: 0.365 ms; eight CTAs with a
+// 96-site list and 128 staged ops 0.397 ms; twelve CTAs need spills: 0.40 - 0.42 ms): 48 registers and 21 KB per CTA.
+#ifndef HC_SITES
+#define HC_SITES 64 // sites of a pair kept in the list (registers); the rest go the direct way
+#endif
+#ifndef HC_SCAN_MINB
+#define HC_SCAN_MINB 10 // resident CTAs per SM asked of the compiler (register budget)
+#endif
+#ifndef HC_PREFETCH
+#define HC_PREFETCH 1 // the rest of the read is requested into L2 when its first blocks are asked for
+#endif
 
 struct __align__(16) ScanWarp {
   uint8_t bq[HC_NS][HC_BLK];
@@ -580,7 +592,7 @@ struct __align__(16) ScanWarp {
 };
 
 template <bool kSeq>
-__global__ void __launch_bounds__(32 * HC_SCAN_WARPS) k_call_scan(DevBatch b, DevParams p, const hm_chunk* chunks, const uint64_t* pair_off,
+__global__ void __launch_bounds__(32 * HC_SCAN_WARPS, HC_SCAN_MINB) k_call_scan(DevBatch b, DevParams p, const hm_chunk* chunks, const uint64_t* pair_off,
                                                                   uint64_t n_pairs, const uint32_t* pair_c, const uint8_t* pair_hap,
                                                                   const uint8_t* read_counted, const uint32_t* first_pair,
                                                                   const uint32_t* tile_off, const uint32_t* tile_dst,
@@ -623,6 +635,9 @@ __global__ void __launch_bounds__(32 * HC_SCAN_WARPS) k_call_scan(DevBatch b, De
         mbar_arrive_expect_tx(&S->bar[s], bytes);
         bulk_g2s(S->bq[s], bqg + (size_t)s * HC_BLK, bytes, &S->bar[s]);
       }
+#if HC_PREFETCH
+      if (nbytes > HC_NS * HC_BLK) bulk_prefetch_l2(bqg + (size_t)HC_NS * HC_BLK, nbytes - HC_NS * HC_BLK);
+#endif
     }
     __syncwarp();
   }

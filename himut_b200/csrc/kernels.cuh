@@ -828,7 +828,10 @@ __global__ void __launch_bounds__(256) k_site_entries_by_read(DevBatch b, DevPar
 //   restatement when omit != 0) are written to compact_out only — a block reserves its range with one atomic on
 //   *n_kept, inside the block the order is the key order — and a boundary record carries its position there
 //   (0xffffffff: not kept).  `out` is not written then.
-__global__ void __launch_bounds__(128) k_site_reduce(DevBatch b, DevParams p, DevSets sets, DevLut lut, DevPhase ph, int dup_names,
+#ifndef HM_REDUCE_MINB
+#define HM_REDUCE_MINB 5 // 96 registers; six CTAs (80 registers, a few spills) run the same, four are 12 % slower
+#endif
+__global__ void __launch_bounds__(128, HM_REDUCE_MINB) k_site_reduce(DevBatch b, DevParams p, DevSets sets, DevLut lut, DevPhase ph, int dup_names,
                                                      const hm_chunk* chunks,
                                                      const uint64_t* pair_off, const uint8_t* pair_hap, const int32_t* prev_max_end,
                                                      const int32_t* next_min_start, const unsigned long long* keys,

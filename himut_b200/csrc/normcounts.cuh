@@ -357,6 +357,11 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
+// ask for [src, src + bytes) to be brought into L2 (bytes: a multiple of 16); nothing waits for it
+__device__ __forceinline__ void bulk_prefetch_l2(const void* src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
+
 // set bits [lo, hi) of a 512-bit mask in shared memory (single writer)
 __device__ __forceinline__ void mask_set(uint32_t* m, int32_t lo, int32_t hi) {
   if (lo < 0) lo = 0;

@@ -171,6 +171,30 @@ class PinCache:
             self.held = {}
 
 
+class Laps:
+    """wall-clock laps of a worker's host loop, reported to stderr when HIMUT_B200_WORKER_TIMING is set (diagnostics)"""
+
+    def __init__(self, title):
+        self.on = bool(os.environ.get("HIMUT_B200_WORKER_TIMING"))
+        self.title, self.acc = title, {}
+        if self.on:
+            import time
+            self.clock = time.perf_counter
+            self.t = self.t0 = self.clock()
+
+    def __call__(self, name):
+        if self.on:
+            now = self.clock()
+            self.acc[name] = self.acc.get(name, 0.0) + now - self.t
+            self.t = now
+
+    def report(self):
+        if self.on:
+            import sys
+            print("[%s] %.3f s: %s" % (self.title, self.clock() - self.t0, ", ".join("%s %.3f" % kv for kv in self.acc.items())),
+                  file=sys.stderr)
+
+
 class QnameTally:
     """distinct query names that passed the read gates, across groups (m.num_ccs)"""
 
