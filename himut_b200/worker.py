@@ -144,11 +144,13 @@ def pipelined_groups(src, chrom, chunkloci_lst, groups, chunk_sets, seq, pad=0):
 
 class PinCache:
     """page-locks the decoder's big output buffers once per (address, size): they are reused from group to group, so
-    the H2D copies of every group but the first run at PCIe speed.  Off for single-group contigs (locking pages costs
-    about what one pageable copy does)."""
+    the H2D copies of every group but the first run at PCIe speed.  Opt-in (HIMUT_B200_PIN_DECODE=1): on the B200 boxes
+    measured (VMs), cudaHostRegister of a contig's two buffer sets (0.45 GB) takes 0.6 - 4 s, where the pageable copies it
+    saves take under 0.1 s per 64 Mb contig and the decode itself 0.5 s (tools/worker_trace.py)."""
 
     def __init__(self, ctx, enabled):
-        self.ctx, self.enabled, self.held = ctx, enabled, {}
+        self.ctx, self.held = ctx, {}
+        self.enabled = enabled and os.environ.get("HIMUT_B200_PIN_DECODE", "0") not in ("", "0")
 
     def pin(self, arrays):
         if not self.enabled:
