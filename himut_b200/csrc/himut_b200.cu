@@ -104,6 +104,7 @@ struct hm_ctx {
   size_t ref_len = 0; // length of the contig left resident by hm_set_reference (0: none)
   NormCert cert;      // certified-verdict constants of the normcounts fast pass
   unsigned long long last_norm_sites = 0; // positions the last normcounts call evaluated exactly
+  DevBuf b_push, b_span_cnt; // k_norm_bits: 32 site words and a site count per span
   DevBuf b_sites, b_koff, b_tile_info, b_edge_counts, b_edge_hpos, b_edge_href, b_bqmask, b_bqexc, b_bqexc_off;
   uint64_t edge_n = 0;
   uint32_t edge_band = 0;
@@ -352,7 +353,7 @@ void hm_destroy(hm_ctx* ctx) {
                     &ctx->b_ins_len, &ctx->b_del_len, &ctx->b_n_mm, &ctx->b_gate, &ctx->b_pmax, &ctx->b_tix_off, &ctx->b_tix, &ctx->b_common, &ctx->b_pon,
                     &ctx->b_hpos, &ctx->b_href, &ctx->b_halt, &ctx->b_hbit, &ctx->b_set_off, &ctx->b_chunks,
                     &ctx->b_pair_off, &ctx->b_pair_hap, &ctx->b_qseen, &ctx->b_keys, &ctx->b_keys_sorted, &ctx->b_cub,
-                    &ctx->b_records, &ctx->b_counters, &ctx->b_ref, &ctx->b_norm_out, &ctx->b_lut, &ctx->b_tile_off, &ctx->b_agg, &ctx->b_geom, &ctx->b_bidx, &ctx->b_brecs, &ctx->b_sites, &ctx->b_koff, &ctx->b_tile_info, &ctx->b_edge_counts, &ctx->b_edge_hpos, &ctx->b_edge_href, &ctx->b_bqmask, &ctx->b_bqexc, &ctx->b_bqexc_off,
+                    &ctx->b_records, &ctx->b_counters, &ctx->b_ref, &ctx->b_norm_out, &ctx->b_lut, &ctx->b_tile_off, &ctx->b_agg, &ctx->b_geom, &ctx->b_bidx, &ctx->b_brecs, &ctx->b_sites, &ctx->b_push, &ctx->b_span_cnt, &ctx->b_koff, &ctx->b_tile_info, &ctx->b_edge_counts, &ctx->b_edge_hpos, &ctx->b_edge_href, &ctx->b_bqmask, &ctx->b_bqexc, &ctx->b_bqexc_off,
                     &ctx->b_cgeom, &ctx->b_seg_keys, &ctx->b_seg_read, &ctx->b_keys_tmp, &ctx->b_gscratch, &ctx->b_czero, &ctx->b_first_pair, &ctx->b_tiles, &ctx->b_site_valid, &ctx->b_pair_c,
                     &ctx->b_cw_off, &ctx->b_calw, &ctx->b_impure, &ctx->b_ref2, &ctx->b_tri8, &ctx->b_thr, &ctx->b_span_off, &ctx->b_exc_minmax, &ctx->b_exp_total, &ctx->b_sdiff, &ctx->b_cal_ok};
   for (DevBuf* b : bufs) b->release();
@@ -1573,24 +1574,31 @@ static int hm_normcounts_impl(hm_ctx* ctx, const uint8_t* refseq, size_t ref_len
           t_end(ctx);
           CU(cudaGetLastError());
         }
-        for (int attempt = 0; attempt < 2 && n_spans; attempt++) {
-          CU(ctx->b_sites.ensure(site_cap * 8));
-          if (attempt) { // the list overflowed: start over with the exact size
-            CU(cudaMemsetAsync(ctx->b_norm_out.p, 0, sizeof(NormOut), ctx->stream));
-            CU(cudaMemsetAsync(d_nsites, 0, 8, ctx->stream));
-          }
+        if (n_spans) {
+          // every span leaves its 32 site words and its count; the counts are scanned and the keys written span by span:
+          // the site list comes out in (chunk, position) order and in exactly the room it needs
+          CU(ctx->b_push.ensure((size_t)n_spans * 128 + 16));
+          CU(ctx->b_span_cnt.ensure(((size_t)n_spans + 1) * 8 + 16));
+          uint32_t* span_cnt = ctx->b_span_cnt.as<uint32_t>();
+          uint32_t* span_dst = span_cnt + n_spans;
           t_begin(ctx, "k_norm_bits");
           (ctx->params.phase ? k_norm_bits<true> : k_norm_bits<false>)<<<bgrid, 32 * NB_BITS_WARPS, 0, ctx->stream>>>(
               ctx->db, ctx->dp, ctx->b_thr.as<uint16_t>(), (int)ctx->cert.n_min, md_k, ctx->b_chunks.as<hm_chunk>(), (uint32_t)n_chunks,
               ctx->b_pair_off.as<uint64_t>(), ctx->b_pair_hap.as<uint8_t>(), ctx->b_tile_info.as<uint4>(), n_spans, ctx->b_cw_off.as<uint32_t>(),
               ctx->b_calw.as<uint32_t>(), ctx->b_impure.as<uint32_t>(), ctx->b_tri8.as<uint8_t>(), ctx->b_norm_out.as<NormOut>(),
-              ctx->b_sites.as<unsigned long long>(), site_cap, d_nsites);
+              ctx->b_push.as<uint32_t>(), span_cnt);
           t_end(ctx);
           CU(cudaGetLastError());
+          t_begin(ctx, "k_emit_sites");
+          k_span_scan<<<1, 1024, 0, ctx->stream>>>(span_cnt, n_spans, span_dst, d_nsites);
           CU(cudaMemcpyAsync(&n_sites, d_nsites, 8, cudaMemcpyDeviceToHost, ctx->stream));
           CU(cudaStreamSynchronize(ctx->stream));
-          if (n_sites <= site_cap) break;
-          site_cap = n_sites;
+          CU(ctx->b_sites.ensure((size_t)std::max<unsigned long long>(n_sites, 1) * 8));
+          if (n_sites)
+            k_emit_sites<<<(unsigned)((n_spans * 32 + 255) / 256), 256, 0, ctx->stream>>>(ctx->b_tile_info.as<uint4>(), n_spans, ctx->b_push.as<uint32_t>(),
+                                                                                       span_dst, ctx->b_sites.as<unsigned long long>());
+          t_end(ctx);
+          CU(cudaGetLastError());
         }
       } else {
       CU(ctx->b_tix.ensure((size_t)ctx->n_tix * 16 + 16));
@@ -1626,7 +1634,10 @@ static int hm_normcounts_impl(hm_ctx* ctx, const uint8_t* refseq, size_t ref_len
       ctx->last_norm_sites = n_sites;
       const bool by_site = getenv("HIMUT_B200_ENTRIES_BY_SITE") != nullptr; // thread-per-(site, read) gather (A/B)
       const unsigned long long* site_keys = ctx->b_sites.as<unsigned long long>();
-      if (n_sites && !by_site) {
+      if (n_sites && !by_site && use_bits) { // already in (chunk, position) order
+        CU(ctx->b_koff.ensure((n_chunks + 2) * 4));
+        k_chunk_key_ranges<<<(unsigned)((n_chunks + 1 + 127) / 128), 128, 0, ctx->stream>>>(site_keys, d_nsites, (uint32_t)n_chunks, ctx->b_koff.as<uint32_t>());
+      } else if (n_sites && !by_site) {
         // the list comes out in tile-completion order: sort it (chunk, position) so a read finds its sites by range
         CU(ctx->b_keys_sorted.ensure(n_sites * 8));
         int end_bit = 36;

@@ -605,8 +605,7 @@ __global__ void __launch_bounds__(32 * NB_BITS_WARPS, kPhase ? 4 : 6) k_norm_bit
                                                                    uint32_t n_chunks, const uint64_t* pair_off, const uint8_t* pair_flag,
                                                                    const uint4* span_info, uint64_t n_spans, const uint32_t* cw_off,
                                                                    const uint32_t* calw, const uint32_t* impure, const uint8_t* tri8,
-                                                                   NormOut* out, unsigned long long* sites, unsigned long long site_cap,
-                                                                   unsigned long long* n_sites) {
+                                                                   NormOut* out, uint32_t* push_words, uint32_t* span_cnt) {
   __shared__ unsigned long long s_ccs[HM_TRI_BINS], s_ref[HM_TRI_BINS], s_log[HM_NORM_LOG_LEN];
   __shared__ unsigned int s_wccs[NB_BITS_WARPS][HM_TRI_BINS + 1], s_wref[NB_BITS_WARPS][HM_TRI_BINS + 1];
   __shared__ uint16_t s_thr[256];
@@ -725,25 +724,12 @@ __global__ void __launch_bounds__(32 * NB_BITS_WARPS, kPhase ? 4 : 6) k_norm_bit
         }
       }
     }
-    // the site list of the exact pass
+    // the site list of the exact pass: the lane's word and the span's count now, the keys in position order once the
+    // counts are scanned (k_span_scan, k_emit_sites) — the list comes out sorted, nothing sorts it
+    push_words[span * 32 + (uint64_t)lane] = push;
     {
-      const uint32_t np = (uint32_t)__popc(push);
-      uint32_t incl = np;
-#pragma unroll
-      for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(HM_FULL, incl, d); if (lane >= d) incl += t; }
-      const uint32_t total = __shfl_sync(HM_FULL, incl, 31);
-      if (total) {
-        unsigned long long at = 0;
-        if (lane == 0) at = atomicAdd(n_sites, (unsigned long long)total);
-        at = __shfl_sync(HM_FULL, at, 0) + (incl - np);
-        uint32_t todo = push;
-        while (todo) {
-          const int bit = __ffs(todo) - 1;
-          todo &= todo - 1;
-          if (at < site_cap) sites[at] = ((unsigned long long)c << 36) | ((unsigned long long)(uint32_t)(P0 + bit + 1) << 4);
-          at++;
-        }
-      }
+      const uint32_t total = __reduce_add_sync(HM_FULL, (uint32_t)__popc(push));
+      if (lane == 0) span_cnt[span] = total;
     }
     // the warp's 32-bit bins into the CTA's 64-bit ones before they can overflow
     __syncwarp();
@@ -766,4 +752,41 @@ __global__ void __launch_bounds__(32 * NB_BITS_WARPS, kPhase ? 4 : 6) k_norm_bit
     if (s_ref[tid]) atomicAdd(&out->ref_tri[tid], s_ref[tid]);
   }
   if (tid < HM_NORM_LOG_LEN && s_log[tid]) atomicAdd(&out->log[tid], s_log[tid]);
+}
+
+// exclusive scan of the spans' site counts -> span_dst[0 .. n_spans], *n_sites = their sum (one CTA: every thread owns a
+// run of consecutive spans, one block scan of the run totals)
+__global__ void __launch_bounds__(1024) k_span_scan(const uint32_t* span_cnt, uint64_t n_spans, uint32_t* span_dst, unsigned long long* n_sites) {
+  __shared__ uint32_t s_warp[33];
+  const uint64_t per = (n_spans + blockDim.x - 1) / blockDim.x;
+  const uint64_t i0 = min((uint64_t)threadIdx.x * per, n_spans), i1 = min(i0 + per, n_spans);
+  uint32_t local = 0;
+  for (uint64_t i = i0; i < i1; i++) local += span_cnt[i];
+  uint32_t total;
+  uint32_t run = block_excl_scan(local, s_warp, &total);
+  for (uint64_t i = i0; i < i1; i++) { const uint32_t v = span_cnt[i]; span_dst[i] = run; run += v; }
+  if (threadIdx.x == 0) { span_dst[n_spans] = total; *n_sites = (unsigned long long)total; }
+}
+
+// the keys (chunk << 36 | (position + 1) << 4) of the listed positions, span by span and ascending inside a span: sorted
+__global__ void __launch_bounds__(256) k_emit_sites(const uint4* span_info, uint64_t n_spans, const uint32_t* push_words, const uint32_t* span_dst,
+                                                    unsigned long long* sites) {
+  const uint64_t span = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (span >= n_spans) return;
+  const uint32_t d0 = __ldg(span_dst + span);
+  if (__ldg(span_dst + span + 1) == d0) return;
+  const uint4 si = __ldg(span_info + span);
+  uint32_t todo = __ldg(push_words + span * 32 + (uint64_t)lane);
+  const uint32_t np = (uint32_t)__popc(todo);
+  uint32_t incl = np;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(HM_FULL, incl, d); if (lane >= d) incl += t; }
+  unsigned long long at = (unsigned long long)d0 + (incl - np);
+  const int32_t P0 = (int32_t)si.y + 32 * lane;
+  while (todo) {
+    const int bit = __ffs(todo) - 1;
+    todo &= todo - 1;
+    sites[at++] = ((unsigned long long)si.x << 36) | ((unsigned long long)(uint32_t)(P0 + bit + 1) << 4);
+  }
 }
