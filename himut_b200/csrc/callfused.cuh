@@ -540,7 +540,7 @@ __global__ void __launch_bounds__(1024) k_tile_scan(const uint32_t* tile_cnt, ui
 __global__ void __launch_bounds__(256) k_site_range2(DevBatch b, const hm_chunk* chunks, const uint32_t* tile_chunk, const uint32_t* tile_src,
                                                      const uint32_t* tile_dst, uint32_t n_tiles, const uint32_t* keys_tmp,
                                                      const unsigned long long* n_keys_dev, unsigned long long* keys, uint32_t* site_lo,
-                                                     uint32_t* site_n, uint32_t* entries, uint64_t stride, uint8_t* site_valid) {
+                                                     uint32_t* site_n, uint32_t* entries, uint64_t stride, uint8_t* site_valid, uint32_t n_slots) {
   const uint64_t ki = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (ki >= *n_keys_dev) return;
   const uint32_t t = upper_bound_dev(tile_dst, n_tiles + 1, (uint32_t)ki) - 1; // last tile with tile_dst <= ki (empty tiles repeat a value)
@@ -557,7 +557,7 @@ __global__ void __launch_bounds__(256) k_site_range2(DevBatch b, const hm_chunk*
   site_lo[ki] = ch.read_lo + lo;
   site_n[ki] = n;
   site_valid[ki] = 0;
-  const uint32_t ns = min(n, (uint32_t)HM_SITE_SLOTS);
+  const uint32_t ns = min(n, n_slots);
   for (uint32_t s = 0; s < ns; s++) entries[(uint64_t)s * stride + ki] = HM_ENT_UNWRITTEN;
 }
 
@@ -599,7 +599,7 @@ __global__ void __launch_bounds__(32 * HC_SCAN_WARPS, HC_SCAN_MINB) k_call_scan(
                                                                   const unsigned long long* keys, const uint32_t* site_lo,
                                                                   const uint32_t* site_n, uint32_t* entries, uint32_t stride,
                                                                   uint8_t* qv_fail_read, unsigned int* qv_fail_any, uint32_t* qname_seen32,
-                                                                  unsigned long long* num_ccs, const unsigned long long* n_keys_dev) {
+                                                                  unsigned long long* num_ccs, const unsigned long long* n_keys_dev, uint32_t n_slots) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   const uint64_t pr = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -677,7 +677,7 @@ __global__ void __launch_bounds__(32 * HC_SCAN_WARPS, HC_SCAN_MINB) k_call_scan(
   auto site = [&](uint32_t ki, uint32_t* q_out, uint32_t* e_out, uint32_t* at_out) {
     *q_out = 0xffffffffu; *e_out = 0; *at_out = 0;
     const uint32_t slot = r - __ldg(site_lo + ki);
-    if (slot >= HM_SITE_SLOTS || slot >= __ldg(site_n + ki)) return; // deep pileups: k_site_reduce computes these itself
+    if (slot >= n_slots || slot >= __ldg(site_n + ki)) return; // pileups deeper than the slots: k_site_reduce computes these itself
     const unsigned long long key = __ldg(keys + ki);
     const int32_t rpos = (int32_t)((key >> 4) & 0xffffffffull) - 1;
     uint32_t q; int ins;

@@ -111,6 +111,7 @@ struct hm_ctx {
   // fused call path
   std::vector<uint64_t> h_ops_prefix;       // ops of the reads before read r (candidate slots a chunk can need)
   std::vector<uint8_t> h_named;             // scratch of the shared-query-name test of an upload
+  uint32_t site_slots = HM_SITE_SLOTS;      // entry slots per site of the fused call path: about twice the batch's mean depth
   bool dup_names = false;                   // two primary records of the resident batch share a query name
   int call_path = 0;                        // hm_last_call_path
   bool ktiming = true;                      // HM_OPT_KERNEL_TIMING: CUDA events around the kernels of a call
@@ -492,7 +493,7 @@ static int upload_batch_impl(hm_ctx* ctx, const hm_read_batch* b, const hm_bq_co
   ctx->h_pmax.resize(n);
   ctx->h_tix_off.resize(n + 1);
   ctx->h_cw_off.resize(n + 1);
-  uint64_t n_tix = 0, n_cw = 0;
+  uint64_t n_tix = 0, n_cw = 0, span_sum = 0;
   int32_t run = INT32_MIN;
   uint32_t max_q = 0;
   for (uint64_t r = 0; r < n; r++) {
@@ -506,6 +507,7 @@ static int upload_batch_impl(hm_ctx* ctx, const hm_read_batch* b, const hm_bq_co
     if (cq && (cq->exc_off[r] > cq->exc_off[r + 1] || cq->exc_off[r + 1] > cq->exc_bytes || cq->exc_off[r + 1] - cq->exc_off[r] > (uint64_t)b->qlen[r]))
       BAD("read %llu: hm_bq_compact.exc_off is inconsistent", (unsigned long long)r);
     if (b->tend[r] > run) run = b->tend[r];
+    span_sum += (uint64_t)(b->tend[r] - b->tstart[r]);
     ctx->h_pmax[r] = run;
     ctx->h_tix_off[r] = (uint32_t)n_tix;
     n_tix += (uint64_t)((b->tend[r] >> 11) - (b->tstart[r] >> 11) + 1);
@@ -514,6 +516,15 @@ static int upload_batch_impl(hm_ctx* ctx, const hm_read_batch* b, const hm_bq_co
     if (b->qname_id[r] > max_q) max_q = b->qname_id[r];
   }
   ctx->max_qname_id = max_q;
+  { // entry slots per site: a site's file-order read range holds about `depth` reads; twice the mean depth (64 at least,
+    // 512 at most, a multiple of 32) keeps all but the deepest pileups out of k_site_reduce's own op walk
+    const double covered = n ? (double)std::max<int64_t>((int64_t)run - (int64_t)b->tstart[0], 1) : 1.0;
+    const double depth = (double)span_sum / covered;
+    uint32_t slots = (uint32_t)std::min(512.0, std::max(64.0, 2.0 * depth));
+    slots = (slots + 31u) & ~31u;
+    if (const char* e = getenv("HIMUT_B200_SITE_SLOTS")) slots = (uint32_t)std::min(512, std::max(1, atoi(e))); // tests: force the deep-pileup walk
+    ctx->site_slots = slots;
+  }
   // candidate slots a chunk can need = ops of the reads it fetches; shared query names among primary records
   // (the phase check of a site then goes by name, caller.py:556-567)
   ctx->h_ops_prefix.resize(n + 1);
@@ -709,9 +720,10 @@ int fused_enqueue(hm_ctx* ctx, const hm_chunk* chunks, size_t n_chunks, const st
   CU(ctx->b_pair_c.ensure((size_t)n_pairs * 4 + 16));
   CU(ctx->b_tiles.ensure(((size_t)n_tiles * 3 + 4) * 4));
   const uint64_t stride = (site_cap + 31) & ~31ull;
-  if (stride * HM_SITE_SLOTS + site_cap >= (1ull << 32)) return fail(ctx, HM_ERR_ARG, "%llu candidate sites in one call: split the chunk list", (unsigned long long)site_cap);
+  const uint32_t n_slots = ctx->site_slots;
+  if (stride * n_slots + site_cap >= (1ull << 32)) return fail(ctx, HM_ERR_ARG, "%llu candidate sites in one call: split the chunk list", (unsigned long long)site_cap);
   CU(ctx->b_keys.ensure(site_cap * 8 + 16));
-  CU(ctx->b_agg.ensure(stride * HM_SITE_SLOTS * 4 + site_cap * 8 + 16));
+  CU(ctx->b_agg.ensure(stride * n_slots * 4 + site_cap * 8 + 16));
   CU(ctx->b_site_valid.ensure(site_cap + 16));
   CU(ctx->b_compact[parity].ensure(site_cap * sizeof(hm_site_record)));
   const unsigned n_red = (unsigned)((site_cap + 127) / 128);
@@ -734,7 +746,7 @@ int fused_enqueue(hm_ctx* ctx, const hm_chunk* chunks, size_t n_chunks, const st
   unsigned long long* d_cnt = ctx->b_counters.as<unsigned long long>();
   unsigned long long* keys = ctx->b_keys.as<unsigned long long>();
   uint32_t* entries = ctx->b_agg.as<uint32_t>();
-  uint32_t* site_lo = entries + stride * HM_SITE_SLOTS;
+  uint32_t* site_lo = entries + stride * n_slots;
   uint32_t* site_n = site_lo + site_cap;
   uint8_t* pair_hap = ctx->params.phase ? ctx->b_pair_hap.as<uint8_t>() : nullptr;
   uint32_t* pair_c = ctx->b_pair_c.as<uint32_t>();
@@ -777,7 +789,7 @@ int fused_enqueue(hm_ctx* ctx, const hm_chunk* chunks, size_t n_chunks, const st
   k_tile_scan<<<1, 1024, 0, ctx->stream>>>(tile_cnt, (uint32_t)n_tiles, tile_dst, (unsigned long long)site_cap, d_cnt);
   k_site_range2<<<(unsigned)((site_cap + 255) / 256), 256, 0, ctx->stream>>>(ctx->db, G.chunks, G.tile_chunk, tile_src, tile_dst, (uint32_t)n_tiles,
                                                                             ctx->b_keys_tmp.as<uint32_t>(), d_cnt + 1, keys, site_lo, site_n, entries, stride,
-                                                                            ctx->b_site_valid.as<uint8_t>());
+                                                                            ctx->b_site_valid.as<uint8_t>(), n_slots);
   t_end(ctx);
   CU(cudaGetLastError());
   int rc = flush_deferred(ctx, true); // the previous call's records start moving now, under the quality scan
@@ -789,12 +801,12 @@ int fused_enqueue(hm_ctx* ctx, const hm_chunk* chunks, size_t n_chunks, const st
     k_call_scan<true><<<pair_blocks_b, 32 * HC_SCAN_WARPS, scan_smem, ctx->stream>>>(ctx->db, ctx->dp, G.chunks, G.pair_off, n_pairs, pair_c, pair_hap, read_counted,
                                                                                     ctx->b_first_pair.as<uint32_t>(), G.tile_off, tile_dst, keys, site_lo, site_n,
                                                                                     entries, (uint32_t)stride, qv_fail_read, qv_any, ctx->b_qseen.as<uint32_t>(),
-                                                                                    d_cnt + 24, d_cnt + 1);
+                                                                                    d_cnt + 24, d_cnt + 1, n_slots);
   else
     k_call_scan<false><<<pair_blocks_b, 32 * HC_SCAN_WARPS, scan_smem, ctx->stream>>>(ctx->db, ctx->dp, G.chunks, G.pair_off, n_pairs, pair_c, pair_hap, read_counted,
                                                                                      ctx->b_first_pair.as<uint32_t>(), G.tile_off, tile_dst, keys, site_lo, site_n,
                                                                                      entries, (uint32_t)stride, qv_fail_read, qv_any, ctx->b_qseen.as<uint32_t>(),
-                                                                                     d_cnt + 24, d_cnt + 1);
+                                                                                     d_cnt + 24, d_cnt + 1, n_slots);
   t_end(ctx);
   CU(cudaGetLastError());
   CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_copy_done[parity], 0)); // the copy that last read this record buffer
@@ -807,7 +819,7 @@ int fused_enqueue(hm_ctx* ctx, const hm_chunk* chunks, size_t n_chunks, const st
                                                 G.geom, G.geom + n_chunks, keys, d_cnt + 1, site_lo, site_n, entries, stride,
                                                 nullptr, d_cnt + 8, ctx->b_bidx.as<uint32_t>(), ctx->b_brecs.as<hm_site_record>(),
                                                 (uint32_t)boundary_cap, d_cnt + 4, reinterpret_cast<int*>(d_cnt + 3), ctx->b_site_valid.as<uint8_t>(),
-                                                qv_any, ctx->b_compact[parity].as<hm_site_record>(), d_cnt + 6, ctx->b_bpos.as<uint32_t>(), omit ? 1 : 0);
+                                                qv_any, ctx->b_compact[parity].as<hm_site_record>(), d_cnt + 6, ctx->b_bpos.as<uint32_t>(), omit ? 1 : 0, n_slots);
   t_end(ctx);
   CU(cudaGetLastError());
   return HM_OK;
@@ -1029,7 +1041,8 @@ static int call_chunks_impl(hm_ctx* ctx, const hm_chunk* chunks, size_t n_chunks
           ctx->db, ctx->dp, ctx->dsets, ctx->dlut, ctx->dphase, ctx->dup_names ? 1 : 0, ctx->b_chunks.as<hm_chunk>(), ctx->b_pair_off.as<uint64_t>(),
           ctx->b_pair_hap.as<uint8_t>(), ctx->b_geom.as<int32_t>(), ctx->b_geom.as<int32_t>() + n_chunks, k_in, d_cnt + 1, site_lo,
           site_n, entries, stride, rec_buf.as<hm_site_record>(), d_cnt + 8, ctx->b_bidx.as<uint32_t>(),
-          ctx->b_brecs.as<hm_site_record>(), (uint32_t)HM_BOUNDARY_CAP, d_cnt + 4, reinterpret_cast<int*>(d_cnt + 3), nullptr, nullptr, nullptr, nullptr, nullptr, 0);
+          ctx->b_brecs.as<hm_site_record>(), (uint32_t)HM_BOUNDARY_CAP, d_cnt + 4, reinterpret_cast<int*>(d_cnt + 3), nullptr, nullptr, nullptr, nullptr, nullptr, 0,
+          (uint32_t)HM_SITE_SLOTS);
       if (omit) { // records of germline restatements stay here: flags -> scan -> stable compaction
         CU(ctx->b_keep.ensure(n_unique * 4 + 16)); CU(ctx->b_kpos.ensure(n_unique * 4 + 16));
         CU(ctx->b_bpos.ensure(((size_t)HM_BOUNDARY_CAP + HM_BOUNDARY_FIRST) * 4));

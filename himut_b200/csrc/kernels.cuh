@@ -841,7 +841,7 @@ __global__ void __launch_bounds__(128, HM_REDUCE_MINB) k_site_reduce(DevBatch b,
                                                      hm_site_record* boundary_recs, uint32_t boundary_cap,
                                                      unsigned long long* n_boundary, int* err_flag,
                                                      const uint8_t* site_valid, const unsigned int* qv_fail, hm_site_record* compact_out,
-                                                     unsigned long long* n_kept, uint32_t* boundary_pos, int omit) {
+                                                     unsigned long long* n_kept, uint32_t* boundary_pos, int omit, uint32_t n_slots) {
   __shared__ unsigned int s_hist[16];
   __shared__ unsigned int s_wkeep[4], s_kbase;
   __shared__ double s_lut[3][256];
@@ -895,7 +895,7 @@ __global__ void __launch_bounds__(128, HM_REDUCE_MINB) k_site_reduce(DevBatch b,
     };
     // slots in file order: the first HM_SITE_SLOTS from the gathered entries (eight independent loads at a time),
     // deeper pileups computed here
-    const uint32_t n_slot = min(n, (uint32_t)HM_SITE_SLOTS);
+    const uint32_t n_slot = min(n, n_slots);
     for (uint32_t s0 = 0; s0 < n_slot; s0 += 8) {
       uint32_t ev[8];
 #pragma unroll
@@ -903,7 +903,7 @@ __global__ void __launch_bounds__(128, HM_REDUCE_MINB) k_site_reduce(DevBatch b,
 #pragma unroll
       for (int j = 0; j < 8; j++) acc(ev[j]);
     }
-    for (uint32_t s = HM_SITE_SLOTS; s < n; s++) acc(site_entry(b, p, ch, c, pair_off, pair_hap, lo + s, tpos - 1, ref, fused));
+    for (uint32_t s = n_slots; s < n; s++) acc(site_entry(b, p, ch, c, pair_off, pair_hap, lo + s, tpos - 1, ref, fused));
     if (bq_zero) *err_flag = HM_ERR_BQ_ZERO;
 
     double pl[10];
@@ -954,8 +954,8 @@ __global__ void __launch_bounds__(128, HM_REDUCE_MINB) k_site_reduce(DevBatch b,
               bool in_wt = false, in_alt = false;
               for (uint32_t s = 0; s < n; s++) {
                 if (__ldg(b.qname_id + lo + s) != q) continue;
-                const uint32_t e = s < HM_SITE_SLOTS ? __ldg(entries + (uint64_t)s * stride + ki)
-                                                     : site_entry(b, p, ch, c, pair_off, pair_hap, lo + s, tpos - 1, ref, fused);
+                const uint32_t e = s < n_slots ? __ldg(entries + (uint64_t)s * stride + ki)
+                                               : site_entry(b, p, ch, c, pair_off, pair_hap, lo + s, tpos - 1, ref, fused);
                 if (e == HM_ENT_UNWRITTEN) continue;
                 const int a = (int)(e & 7u);
                 if (a == ref) { in_wt = true; break; }

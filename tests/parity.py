@@ -46,11 +46,13 @@ def load_random_sweep():
         return json.load(f)
 
 
-def first_diff(a, b):
+def first_diff(a, b, rec=None):
+    """where two tuple lists part; rec: the record array the first came from (its PL-tie count goes into the message)"""
+    note = tie_note(rec) if rec is not None else ""
     for i, (x, y) in enumerate(zip(a, b)):
         if not (len(x) == len(y) and all(u == v for u, v in zip(x, y))):
-            return "row %d: %r != %r" % (i, x, y)
-    return "lengths %d vs %d; extra: %r" % (len(a), len(b), (a[len(b):] or b[len(a):])[:3])
+            return "row %d: %r != %r" % (i, x, y) + note
+    return "lengths %d vs %d; extra: %r" % (len(a), len(b), (a[len(b):] or b[len(a):])[:3]) + note
 
 
 def tri_dict_to_bins(d):
@@ -67,14 +69,20 @@ def sort_records(rec):
     return rec[order]
 
 
+def tie_note(*recs):
+    """how many records of each array carry HM_SITE_PL_TIE (the PL minimum is shared by two genotypes: the reference's
+    choice there rests on numpy's argsort being stable) — part of every parity message"""
+    return " [PL-tie flagged records: %s]" % ", ".join("%d of %d" % (int(((r["flags"] & abi.SITE_PL_TIE) != 0).sum()), r.size) for r in recs)
+
+
 def records_equal(a, b):
     a, b = sort_records(a), sort_records(b)
     if a.shape != b.shape:
-        return False, "record counts %d vs %d" % (a.size, b.size)
+        return False, "record counts %d vs %d" % (a.size, b.size) + tie_note(a, b)
     for name in abi.SITE_DTYPE.names:
         if name == "pad0":
             continue
         if not np.array_equal(a[name], b[name]):
             bad = np.flatnonzero((a[name] != b[name]).reshape(a.size, -1).any(axis=1))[:3]
-            return False, "field %s differs at %s: %r vs %r" % (name, bad, a[bad], b[bad])
+            return False, "field %s differs at %s: %r vs %r" % (name, bad, a[bad], b[bad]) + tie_note(a, b)
     return True, ""

@@ -36,7 +36,7 @@ def test_call_matches_oracle_and_reference(ctx, name):
     fx = parity.load_golden(name)
     rows = records.records_to_tsbs_lst(cases.CHROM, rec)
     gold = parity.golden_rows(fx)
-    assert parity.rows_equal(rows, gold), parity.first_diff(rows, gold)
+    assert parity.rows_equal(rows, gold), parity.first_diff(rows, gold, rec)
     assert [int(v) for v in log] == fx["expected"]["log"]
 
 

@@ -89,14 +89,36 @@ def test_compact_without_seq_one_megabase(ctx):
 
 
 @pytest.mark.gpu
-def test_deep_pileup_without_seq(ctx):
-    """more than 64 reads per site: k_site_reduce gathers the slots beyond the entry table itself"""
+@pytest.mark.parametrize("slots", [None, "64", "96"])
+def test_deep_pileup_without_seq(ctx, slots, monkeypatch):
+    """400x: the entry table has about twice the batch's mean depth in slots per site (512 at most: here every site is
+    deeper than that, and with HIMUT_B200_SITE_SLOTS forced to 64 / 96 far deeper) — k_site_reduce gathers the slots
+    beyond the table itself, with the same result"""
+    if slots is not None:
+        monkeypatch.setenv("HIMUT_B200_SITE_SLOTS", slots)  # read at upload
     d = synth.generate(30_000, seed=34, depth=400.0)
     p = gtmodel.make_params(**cases.call_args(md_threshold=1000))
     chunks = d.batch.chunk_table([(0, 12_345), (12_345, 30_000)])
     ctx.set_params(p)
     ctx.set_site_sets()
     rec, log = ctx.call_batch(d.batch.without_seq(), chunks)
+    o_rec, o_log = oracle.call_chunks(p, d.batch, chunks)
+    ok, why = parity.records_equal(rec, o_rec)
+    assert ok, why
+    assert list(log) == list(o_log)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("depth", [60.0, 100.0])
+def test_deeper_samples_stay_inside_the_entry_table(ctx, depth):
+    """60x / 100x: the slots follow the depth (128 / 224), so no site takes the walk; records equal the oracle's"""
+    d = synth.generate(60_000, seed=35, depth=depth)
+    p = gtmodel.make_params(**cases.call_args(md_threshold=1000))
+    chunks = d.batch.chunk_table([(0, 30_000), (30_000, 60_000)])
+    ctx.set_params(p)
+    ctx.set_site_sets()
+    rec, log = ctx.call_batch(d.batch.without_seq(), chunks)
+    assert ctx.last_call_path() == 2
     o_rec, o_log = oracle.call_chunks(p, d.batch, chunks)
     ok, why = parity.records_equal(rec, o_rec)
     assert ok, why

@@ -20,7 +20,7 @@ def test_call_matches_reference(name):
     rec, log = oracle.call_chunks(c["params"], c["batch"], c["chunk_table"], c["common"], c["pon"], c["phase"])
     rows = records.records_to_tsbs_lst(cases.CHROM, rec)
     gold = parity.golden_rows(fx)
-    assert parity.rows_equal(rows, gold), parity.first_diff(rows, gold)
+    assert parity.rows_equal(rows, gold), parity.first_diff(rows, gold, rec)
     assert [int(v) for v in log] == fx["expected"]["log"]
 
 

@@ -13,6 +13,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("path", choices=["call", "normcounts"])
 ap.add_argument("--contig-mb", type=int, default=8)
 ap.add_argument("--reps", type=int, default=3)
+ap.add_argument("--depth", type=float, default=30.0)
 ap.add_argument("--with-seq", action="store_true", help="call: upload the 2-bit base stream too (the worker mirror does not)")
 ap.add_argument("--compact", action="store_true", help="upload the qualities as bitmap + exceptions, as the workers do")
 a = ap.parse_args()
@@ -21,8 +22,8 @@ import cases  # noqa: E402
 from himut_b200 import gtmodel, lib, synth  # noqa: E402
 
 n = a.contig_mb * 1_000_000
-d = synth.generate(n, seed=5, copy=False)
-params = gtmodel.make_params(**gtmodel.DEFAULT_CALL_ARGS)
+d = synth.generate(n, seed=5, copy=False, depth=a.depth)
+params = gtmodel.make_params(**dict(gtmodel.DEFAULT_CALL_ARGS, md_threshold=max(gtmodel.DEFAULT_CALL_ARGS["md_threshold"], 4 * a.depth)))
 chunks = d.batch.chunk_table(cases.chunkloci(0, n))
 with lib.Context(0) as ctx:
     ctx.set_params(params)
