@@ -1667,13 +1667,15 @@ static int hm_normcounts_impl(hm_ctx* ctx, const uint8_t* refseq, size_t ref_len
         k_chunk_key_ranges<<<(unsigned)((n_chunks + 1 + 127) / 128), 128, 0, ctx->stream>>>(site_keys, d_nsites, (uint32_t)n_chunks, ctx->b_koff.as<uint32_t>());
         t_end(ctx);
       }
-      const unsigned long long SITE_BATCH = 1ull << 21;
+      // sites per round of the exact pass: the entry table (slots x sites x 4 B) stays at 0.5 GB
+      const unsigned long long SITE_BATCH = std::max<unsigned long long>(1ull << 16, (1ull << 27) / std::max<uint32_t>(by_site ? (uint32_t)HM_SITE_SLOTS : ctx->site_slots, 1u));
       for (unsigned long long s0 = 0; s0 < n_sites; s0 += SITE_BATCH) {
         const uint64_t nb = (uint64_t)std::min<unsigned long long>(SITE_BATCH, n_sites - s0);
         const uint64_t stride = (nb + 31) & ~31ull;
-        CU(ctx->b_agg.ensure(stride * HM_SITE_SLOTS * 4 + nb * 8));
+        const uint32_t n_slots = by_site ? (uint32_t)HM_SITE_SLOTS : ctx->site_slots; // as the call path: about twice the mean depth
+        CU(ctx->b_agg.ensure(stride * n_slots * 4 + nb * 8));
         uint32_t* entries = ctx->b_agg.as<uint32_t>();
-        uint32_t* site_lo = entries + stride * HM_SITE_SLOTS;
+        uint32_t* site_lo = entries + stride * n_slots;
         uint32_t* site_n = site_lo + nb;
         const unsigned long long* keys = site_keys + s0;
         t_begin(ctx, "k_norm_site_range");
@@ -1687,24 +1689,25 @@ static int hm_normcounts_impl(hm_ctx* ctx, const uint8_t* refseq, size_t ref_len
           t_end(ctx);
         } else {
           t_begin(ctx, use_bits ? "k_norm_entries_bits" : "k_norm_entries_by_read");
-          CU(cudaMemsetAsync(entries, 0xff, stride * HM_SITE_SLOTS * 4, ctx->stream));
+          CU(cudaMemsetAsync(entries, 0xff, stride * n_slots * 4, ctx->stream));
           if (use_bits)
             k_norm_entries_bits<<<(unsigned)((n_pairs * 32 + 255) / 256), 256, 0, ctx->stream>>>(
                 ctx->db, ctx->dp, ctx->b_chunks.as<hm_chunk>(), (uint32_t)n_chunks, ctx->b_pair_off.as<uint64_t>(), n_pairs,
                 ctx->b_pair_hap.as<uint8_t>(), site_keys, ctx->b_koff.as<uint32_t>(), (uint64_t)s0, nb, site_lo, site_n, entries, stride,
                 ctx->b_cw_off.as<uint32_t>(), ctx->b_calw.as<uint32_t>(), ctx->b_cal_ok.as<uint8_t>(), ctx->b_sdiff.as<uint32_t>(),
-                ctx->b_ref2.as<uint32_t>(), ctx->compact_resident && !getenv("HIMUT_B200_NORM_BYTES") ? ctx->b_bqmask.as<uint16_t>() : nullptr, ctx->modal);
+                ctx->b_ref2.as<uint32_t>(), ctx->compact_resident && !getenv("HIMUT_B200_NORM_BYTES") ? ctx->b_bqmask.as<uint16_t>() : nullptr, ctx->modal,
+                n_slots);
           else
           k_norm_entries_by_read<<<(unsigned)((n_pairs * 32 + 255) / 256), 256, 0, ctx->stream>>>(
               ctx->db, ctx->dp, ctx->b_chunks.as<hm_chunk>(), (uint32_t)n_chunks, ctx->b_pair_off.as<uint64_t>(), n_pairs,
-              ctx->b_pair_hap.as<uint8_t>(), site_keys, ctx->b_koff.as<uint32_t>(), (uint64_t)s0, nb, site_lo, site_n, entries, stride);
+              ctx->b_pair_hap.as<uint8_t>(), site_keys, ctx->b_koff.as<uint32_t>(), (uint64_t)s0, nb, site_lo, site_n, entries, stride, n_slots);
           t_end(ctx);
         }
         t_begin(ctx, "k_norm_reduce");
         k_norm_reduce<<<(unsigned)((nb + 127) / 128), 128, 0, ctx->stream>>>(
             ctx->db, ctx->dp, ctx->dsets, ctx->dlut, ctx->b_chunks.as<hm_chunk>(), ctx->b_pair_off.as<uint64_t>(),
             ctx->b_pair_hap.as<uint8_t>(), keys, nb, site_lo, site_n, entries, stride, ctx->b_ref.as<uint8_t>(), (uint64_t)ref_len,
-            ctx->b_norm_out.as<NormOut>());
+            ctx->b_norm_out.as<NormOut>(), n_slots);
         t_end(ctx);
         CU(cudaGetLastError());
       }

@@ -474,7 +474,7 @@ __global__ void __launch_bounds__(256) k_norm_entries_bits(DevBatch b, DevParams
                                                            const uint32_t* site_lo, const uint32_t* site_n, uint32_t* entries,
                                                            uint64_t stride, const uint32_t* cw_off, const uint32_t* calw,
                                                            const uint8_t* cal_ok, const uint32_t* sdiff, const uint32_t* ref2,
-                                                           const uint16_t* mask16, uint32_t modal) {
+                                                           const uint16_t* mask16, uint32_t modal, uint32_t n_slots) {
   __shared__ uint32_t s_w[8][HM_BYREAD_MAX_OPS], s_t[8][HM_BYREAD_MAX_OPS], s_q[8][HM_BYREAD_MAX_OPS];
   const uint64_t pr = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -507,7 +507,7 @@ __global__ void __launch_bounds__(256) k_norm_entries_bits(DevBatch b, DevParams
   for (uint32_t ki = s_lo + lane; ki < s_hi; ki += 32) {
     const uint32_t li = ki - (uint32_t)s0;
     const uint32_t slot = r - __ldg(site_lo + li);
-    if (slot >= HM_SITE_SLOTS || slot >= __ldg(site_n + li)) continue; // deep pileups: k_norm_reduce computes these itself
+    if (slot >= n_slots || slot >= __ldg(site_n + li)) continue; // pileups deeper than the slots: k_norm_reduce computes these itself
     const int32_t pos = (int32_t)((__ldg(keys + ki) >> 4) & 0xffffffffull) - 1;
     uint32_t e;
     if (!staged) e = norm_entry(b, p, ch, pf, r, pos);

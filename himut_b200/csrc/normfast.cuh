@@ -724,7 +724,7 @@ __global__ void __launch_bounds__(256) k_norm_entries_by_read(DevBatch b, DevPar
                                                               const uint64_t* pair_off, uint64_t n_pairs, const uint8_t* pair_flag,
                                                               const unsigned long long* keys, const uint32_t* koff, uint64_t s0, uint64_t nb,
                                                               const uint32_t* site_lo, const uint32_t* site_n, uint32_t* entries,
-                                                              uint64_t stride) {
+                                                              uint64_t stride, uint32_t n_slots) {
   __shared__ uint32_t s_w[8][HM_BYREAD_MAX_OPS], s_t[8][HM_BYREAD_MAX_OPS], s_q[8][HM_BYREAD_MAX_OPS];
   __shared__ int32_t s_m[8][HM_BYREAD_MAX_OPS];
   const uint64_t pr = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -762,7 +762,7 @@ __global__ void __launch_bounds__(256) k_norm_entries_by_read(DevBatch b, DevPar
   for (uint32_t ki = s_lo + lane; ki < s_hi; ki += 32) {
     const uint32_t li = ki - (uint32_t)s0;
     const uint32_t slot = r - __ldg(site_lo + li);
-    if (slot >= HM_SITE_SLOTS || slot >= __ldg(site_n + li)) continue; // deep pileups: k_norm_reduce computes these itself
+    if (slot >= n_slots || slot >= __ldg(site_n + li)) continue; // pileups deeper than the slots: k_norm_reduce computes these itself
     const int32_t pos = (int32_t)((__ldg(keys + ki) >> 4) & 0xffffffffull) - 1;
     uint32_t e;
     if (!staged) e = norm_entry(b, p, ch, pf, r, pos);
@@ -810,7 +810,7 @@ __global__ void __launch_bounds__(128) k_norm_reduce(DevBatch b, DevParams p, De
                                                      const uint64_t* pair_off, const uint8_t* pair_flag,
                                                      const unsigned long long* keys, uint64_t n_keys, const uint32_t* site_lo,
                                                      const uint32_t* site_n, const uint32_t* entries, uint64_t stride,
-                                                     const uint8_t* refseq, uint64_t ref_len, NormOut* out) {
+                                                     const uint8_t* refseq, uint64_t ref_len, NormOut* out, uint32_t n_slots) {
   __shared__ double s_lut[3][256];
   __shared__ unsigned long long s_ccs[HM_TRI_BINS], s_ref[HM_TRI_BINS], s_log[HM_NORM_LOG_LEN], s_tie;
   __shared__ int s_err;
@@ -836,8 +836,8 @@ __global__ void __launch_bounds__(128) k_norm_reduce(DevBatch b, DevParams p, De
 #pragma unroll
     for (int x = 0; x < 4; x++) { S[x][0] = 0.0; S[x][1] = 0.0; S[x][2] = 0.0; }
     for (uint32_t s = 0; s < n; s++) {
-      const uint32_t e = s < HM_SITE_SLOTS ? __ldg(entries + (uint64_t)s * stride + ki)
-                                           : norm_entry(b, p, ch, pair_flag[pair_off[c] + (lo + s - ch.read_lo)], lo + s, pos);
+      const uint32_t e = s < n_slots ? __ldg(entries + (uint64_t)s * stride + ki)
+                                     : norm_entry(b, p, ch, pair_flag[pair_off[c] + (lo + s - ch.read_lo)], lo + s, pos);
       if (e == HM_ENT_UNWRITTEN) continue; // a read of the range that does not reach the site
       const uint32_t a = e & 7u;
       cnt[4] += (int)((e >> 11) & 255u);

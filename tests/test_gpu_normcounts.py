@@ -96,9 +96,13 @@ def test_normcounts_certification_edges(ctx, over):
     assert np.array_equal(g[0], o[0]) and np.array_equal(g[1], o[1]) and list(g[2]) == list(o[2]) and g[3] == o[3]
 
 
-def test_normcounts_deep_pileup(ctx):
+@pytest.mark.parametrize("slots", [None, "64"])
+def test_normcounts_deep_pileup(ctx, slots, monkeypatch):
     """400x: more than 255 reads per 2048-position tile (the packed 8-bit tallies of the fast pass would overflow:
-    the whole tile goes to the exact pass) and more than 64 reads per position (slots beyond the entry table)"""
+    the whole tile goes to the exact pass) and more reads per position than the entry table has slots (512 at most;
+    64 when HIMUT_B200_SITE_SLOTS forces it): the reduce computes the slots beyond the table itself"""
+    if slots is not None:
+        monkeypatch.setenv("HIMUT_B200_SITE_SLOTS", slots)  # read at upload
     d = synth.generate(30_000, seed=34, depth=400.0)
     p = gtmodel.make_params(**cases.call_args(md_threshold=1000))
     chunks = d.batch.chunk_table([(0, 12_345), (12_345, 30_000)])
@@ -115,3 +119,17 @@ def test_normcounts_deep_pileup(ctx):
     ok, why = parity.records_equal(rec, o_rec)
     assert ok, why
     assert list(log) == list(o_log)
+
+
+@pytest.mark.parametrize("depth", [60.0, 100.0])
+def test_normcounts_deeper_samples(ctx, depth):
+    """60x / 100x: the entry slots of the exact pass follow the depth, the bit-sliced counters hold up to 255 reads"""
+    d = synth.generate(60_000, seed=36, depth=depth)
+    p = gtmodel.make_params(**cases.call_args(md_threshold=1000))
+    chunks = d.batch.chunk_table([(0, 30_000), (30_000, 60_000)])
+    ctx.set_params(p)
+    ctx.set_site_sets()
+    ctx.upload(d.batch)
+    g = ctx.normcounts_chunks(d.ref, chunks)
+    o = oracle.normcounts_chunks(p, d.batch, d.ref, chunks)
+    assert np.array_equal(g[0], o[0]) and np.array_equal(g[1], o[1]) and list(g[2]) == list(o[2]) and g[3] == o[3]
