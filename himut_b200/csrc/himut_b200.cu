@@ -89,6 +89,7 @@ struct hm_ctx {
   std::vector<PendingCopy> deferred;        // record copies of the last async call, not enqueued yet
   int deferred_parity = 0;
   cudaEvent_t ev_go = nullptr;              // recorded after k_read_scan: the deferred copies start behind it
+  cudaEvent_t ev_up = nullptr;              // recorded behind the last host -> device copy of an upload
   unsigned long long* h_cnt_pin = nullptr; // pinned: counters + boundary indices + boundary records of a call
   DevLut dlut = {nullptr};
   // pinned staging for records coming back, final records of the last call
@@ -331,7 +332,8 @@ int hm_create(int cuda_device, hm_ctx** out) {
   if (cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaEventCreateWithFlags(&ctx->ev_copy_done[0], cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&ctx->ev_copy_done[1], cudaEventDisableTiming) != cudaSuccess ||
-      cudaEventCreateWithFlags(&ctx->ev_go, cudaEventDisableTiming) != cudaSuccess) {
+      cudaEventCreateWithFlags(&ctx->ev_go, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&ctx->ev_up, cudaEventDisableTiming | cudaEventBlockingSync) != cudaSuccess) {
     delete ctx;
     return HM_ERR_CUDA;
   }
@@ -346,6 +348,7 @@ void hm_destroy(hm_ctx* ctx) {
   if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
   for (cudaEvent_t e : ctx->ev_copy_done) if (e) cudaEventDestroy(e);
   if (ctx->ev_go) cudaEventDestroy(ctx->ev_go);
+  if (ctx->ev_up) cudaEventDestroy(ctx->ev_up);
   ctx->b_records_alt.release();
   ctx->b_compact[0].release(); ctx->b_compact[1].release(); ctx->b_keep.release(); ctx->b_kpos.release(); ctx->b_bpos.release();
   DevBuf* bufs[] = {&ctx->b_tstart, &ctx->b_tend, &ctx->b_qstart, &ctx->b_qlen, &ctx->b_mapq, &ctx->b_flags, &ctx->b_qname,
@@ -576,6 +579,7 @@ static int upload_batch_impl(hm_ctx* ctx, const hm_read_batch* b, const hm_bq_co
   d.n_mm = ctx->b_n_mm.as<int32_t>(); d.gate = ctx->b_gate.as<uint8_t>(); d.pmax_tend = ctx->b_pmax.as<int32_t>();
   ctx->n_reads = n; ctx->n_ops_total = b->n_ops_total; ctx->seq_bytes = b->seq_bytes; ctx->bq_bytes = b->bq_bytes;
   ctx->compact_resident = false;
+  CU(cudaEventRecord(ctx->ev_up, ctx->stream)); // every host buffer has been read once this fires
   if (cq && n) {
     CU(ctx->b_exc_minmax.ensure(2 * n + 16));
     CU(ctx->b_exp_total.ensure(8 * n + 16));
@@ -589,7 +593,7 @@ static int upload_batch_impl(hm_ctx* ctx, const hm_read_batch* b, const hm_bq_co
     t_end(ctx);
     CU(cudaGetLastError());
   }
-  CU(cudaStreamSynchronize(ctx->stream)); // caller may reuse its buffers after return
+  CU(cudaEventSynchronize(ctx->ev_up)); // the caller may reuse its buffers after return; k_bq_expand may still be running
   ctx->have_batch = true;
   return HM_OK;
 }
@@ -683,7 +687,7 @@ int fused_enqueue(hm_ctx* ctx, const hm_chunk* chunks, size_t n_chunks, const st
   if (g_bytes > ctx->h_geom_cap) {
     if (ctx->h_geom_pin) cudaFreeHost(ctx->h_geom_pin);
     ctx->h_geom_pin = nullptr; ctx->h_geom_cap = 0;
-    CU(cudaHostAlloc((void**)&ctx->h_geom_pin, g_bytes + g_bytes / 4, cudaHostAllocDefault));
+    CU(cudaHostAlloc((void**)&ctx->h_geom_pin, g_bytes + g_bytes / 4, cudaHostAllocMapped));
     ctx->h_geom_cap = g_bytes + g_bytes / 4;
   }
   char* hp = ctx->h_geom_pin;
@@ -702,7 +706,13 @@ int fused_enqueue(hm_ctx* ctx, const hm_chunk* chunks, size_t n_chunks, const st
   }
   memcpy(hp + o_geom, geom, 2 * n_chunks * 4);
   CU(ctx->b_cgeom.ensure(g_bytes));
-  CU(cudaMemcpyAsync(ctx->b_cgeom.p, hp, g_bytes, cudaMemcpyHostToDevice, ctx->stream));
+  { // g_bytes is a multiple of 16
+    void* mapped = nullptr;
+    CU(cudaHostGetDevicePointer(&mapped, hp, 0));
+    const uint32_t n16 = (uint32_t)(g_bytes / 16);
+    k_fetch_block<<<std::max(1u, std::min(32u, (n16 + 255u) / 256u)), 256, 0, ctx->stream>>>(reinterpret_cast<const uint4*>(mapped), ctx->b_cgeom.as<uint4>(), n16);
+    CU(cudaGetLastError());
+  }
   char* dp = ctx->b_cgeom.as<char>();
   FusedGeom G = {reinterpret_cast<const hm_chunk*>(dp + o_chunks), reinterpret_cast<const uint64_t*>(dp + o_pair),
                  reinterpret_cast<const uint64_t*>(dp + o_seg), reinterpret_cast<const uint32_t*>(dp + o_tile),
@@ -909,9 +919,9 @@ static int call_chunks_impl(hm_ctx* ctx, const hm_chunk* chunks, size_t n_chunks
                                                    ctx->b_bpos.as<uint32_t>(), ctx->b_brecs.as<uint32_t>(), (uint32_t)std::min<size_t>(HM_BOUNDARY_FIRST, bcap),
                                                    d_cnt + 4, reinterpret_cast<uint32_t*>(ctx->h_cnt_pin), h_bidx, h_bpos, reinterpret_cast<uint32_t*>(h_brecs));
         CU(cudaGetLastError());
-        // own kernels launched by this attempt: k_call_pairs, k_site_sort, k_tile_scan, k_site_range2, k_call_scan, k_site_valid,
+        // own kernels launched by this attempt: k_fetch_block, k_call_pairs, k_site_sort, k_tile_scan, k_site_range2, k_call_scan, k_site_valid,
         // k_site_reduce, k_publish_call (+ k_bq_expand when the batch came compact, counted by the upload)
-        n_launched += 6 + (n_tiles ? 1 : 0) + (n_chunks ? 1 : 0);
+        n_launched += 7 + (n_tiles ? 1 : 0) + (n_chunks ? 1 : 0);
       }
       if (stage == 1) { // submitted: the rest happens at collect
         ctx->pend.active = true;

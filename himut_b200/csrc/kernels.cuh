@@ -1019,6 +1019,13 @@ __global__ void __launch_bounds__(128, HM_REDUCE_MINB) k_site_reduce(DevBatch b,
 // Small results go to the host through mapped pinned memory (plain stores over PCIe) instead of the copy engine,
 // where they would queue behind a previous call's 20 MB record copy.  words of 4 bytes; *n_src_limit (optional)
 // bounds how many `item_words`-sized items of src are worth sending.
+// The other way round: a call's few KB of chunk geometry come from mapped pinned host memory through plain loads over
+// PCIe, not through the copy engine — there a small copy of this context waits behind the other context's 0.46 GB upload
+// (measured: the whole device path of every second call started 9 ms late, tools/step_trace.py --mode e2e).
+__global__ void __launch_bounds__(256) k_fetch_block(const uint4* mapped_src, uint4* dst, uint32_t n16) {
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += gridDim.x * blockDim.x) dst[i] = mapped_src[i];
+}
+
 __global__ void k_publish(const uint32_t* src, uint32_t* mapped_dst, uint32_t n_words) {
   for (uint32_t i = threadIdx.x; i < n_words; i += blockDim.x) mapped_dst[i] = src[i];
   __threadfence_system();
