@@ -30,8 +30,6 @@ import sys
 import tempfile
 import time
 
-os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")  # before CUDA is initialised: himut_b200/lib.py says why
-
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))

@@ -10,12 +10,6 @@ import numpy as np
 
 from . import abi
 
-# A process drives several streams at once (two contexts, each with a main and a copy stream).  With the default of 8
-# hardware work queues two of them can share one, and a stream that waits for an event then holds back the other's
-# kernels (measured: one context's whole device path ran only after the other's 8.7 ms upload, tools/step_trace.py
-# --mode e2e).  Read by the CUDA driver when the process creates its context: set before anything touches the device.
-os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
-
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("HIMUT_B200_LIB") or os.path.join(_HERE, "libhimut_b200.so")  # override: instrumented builds
 _LIB = None

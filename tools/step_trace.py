@@ -7,9 +7,6 @@ import os
 import sys
 import time
 
-if "--default-connections" not in sys.argv:
-    os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
-
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -21,7 +18,6 @@ ap.add_argument("--mode", default="alt,sync,sync_wait", help="alt | sync | sync_
 ap.add_argument("--no-ktiming", action="store_true")
 ap.add_argument("--own-streams", action="store_true", help="the contexts keep the streams the library created for them")
 ap.add_argument("--start", type=int, default=0, help="index of the context that takes the first step")
-ap.add_argument("--default-connections", action="store_true", help="leave CUDA_DEVICE_MAX_CONNECTIONS at the driver's default (8)")
 a = ap.parse_args()
 
 import numpy as np  # noqa: E402
