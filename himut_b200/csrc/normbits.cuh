@@ -72,11 +72,15 @@ __global__ void __launch_bounds__(256) k_ref_pack(const uint8_t* refseq, uint64_
   reinterpret_cast<uint4*>(tri8)[w] = make_uint4(tb[0], tb[1], tb[2], tb[3]);
 }
 
-// the k lowest bits (k <= 0: none, k >= 32: all): one BMSK with its width clamped to [0, 32]
+// the k lowest bits (k <= 0: none, k >= 32: all); NB_BMSK: as one BMSK with its width clamped to [0, 32]
 __device__ __forceinline__ uint32_t low_mask(int k) {
+#ifdef NB_BMSK
   uint32_t m;
   asm("bmsk.clamp.b32 %0, 0, %1;" : "=r"(m) : "r"((uint32_t)max(k, 0)));
   return m;
+#else
+  return k >= 32 ? 0xffffffffu : (k <= 0 ? 0u : ((1u << k) - 1u));
+#endif
 }
 __device__ __forceinline__ void mark_impure(uint32_t* impure, uint64_t imp_words, int64_t pos) {
   if (pos >= 0 && (uint64_t)(pos >> 5) < imp_words) atomicOr(impure + (pos >> 5), 1u << (pos & 31));
