@@ -822,7 +822,10 @@ def main():
                 except Exception as ex:
                     out["phase"] = {"error": repr(ex)}
             if not args.no_normcounts:
-                out["normcounts"] = leg_normcounts(args, T, ctx, d, chunks)
+                try:
+                    out["normcounts"] = leg_normcounts(args, T, ctx, d, chunks)
+                except Exception as ex:  # a side measurement: never costs the line
+                    out["normcounts"] = {"error": repr(ex)}
             ctx.close()
             if not args.no_bam_leg:
                 try:
