@@ -131,3 +131,45 @@ def test_phase_edge_worker_host_logic(octx, tmp_path, monkeypatch, name, span):
     got = [[int(i), int(j)] + [int(v) for v in e2c[(i, j)]] for (i, j) in edge_lst]
     assert got == json.load(open(os.path.join(cases.GOLDEN_DIR, "edges.json")))["expected"][name]
     assert all(isinstance(v, np.ndarray) and v.dtype == np.float64 for v in e2c.values())
+
+
+def test_decoder_buffers_are_page_locked_only_on_request(monkeypatch):
+    """PinCache: cudaHostRegister of the decoder's buffers is opt-in (HIMUT_B200_PIN_DECODE=1); each (address, size) is
+    locked once, a larger array at the same address replaces the smaller lock, close() unlocks what is held"""
+    calls = []
+
+    class Ctx:
+        def pin_arrays(self, arrays):
+            calls.append(("pin", [a.nbytes for a in arrays]))
+
+        def unpin_arrays(self, arrays):
+            calls.append(("unpin", [a.nbytes for a in arrays]))
+
+    big = np.zeros(1 << 23, np.uint8)
+    monkeypatch.delenv("HIMUT_B200_PIN_DECODE", raising=False)
+    pins = worker.PinCache(Ctx(), enabled=True)
+    pins.pin([big])
+    pins.close()
+    assert calls == []
+    monkeypatch.setenv("HIMUT_B200_PIN_DECODE", "1")
+    pins = worker.PinCache(Ctx(), enabled=True)
+    pins.pin([big, np.zeros(16, np.uint8), None])  # small arrays and missing ones are left alone
+    pins.pin([big])                                  # already held
+    pins.pin([big[: 1 << 22]])                       # a smaller view at the same address: the lock covers it
+    pins.close()
+    assert calls == [("pin", [1 << 23]), ("unpin", [1 << 23])]
+    assert worker.PinCache(Ctx(), enabled=False).enabled is False
+
+
+def test_worker_timing_laps(monkeypatch, capsys):
+    monkeypatch.delenv("HIMUT_B200_WORKER_TIMING", raising=False)
+    lap = worker.Laps("quiet")
+    lap("a")
+    lap.report()
+    assert capsys.readouterr().err == ""
+    monkeypatch.setenv("HIMUT_B200_WORKER_TIMING", "1")
+    lap = worker.Laps("call_region chrT")
+    lap("wait for decode"); lap("upload"); lap("wait for decode")
+    lap.report()
+    err = capsys.readouterr().err
+    assert err.startswith("[call_region chrT]") and "wait for decode" in err and "upload" in err
