@@ -165,8 +165,12 @@ def write_sites_vcf(path, chrom, keys):
 
 
 def phase_dicts(c):
-    """the worker's phase_set2hbit_lst / hpos_lst / hetsnp_lst dicts (vcflib.load_phased_hetsnps)"""
-    ph = c["phase"]
+    """the worker's phase_set2hbit_lst / hpos_lst / hetsnp_lst dicts (vcflib.load_phased_hetsnps).
+    c["phase_snps"] (optional): the SNP table the dicts start from when c["phase"] holds the converted table of a case
+    with indel records; c["phase_alleles"] (optional): {index in the table: (REF string, ALT string, hbit string)} —
+    phased records that are not SNPs (load_phased_hetsnps does not filter them out)"""
+    ph = c.get("phase_snps") if c.get("phase_snps") is not None else c["phase"]
+    over = c.get("phase_alleles") or {}
     hbit, hpos, hetsnp = {}, {}, {}
     if ph is None:
         return hbit, hpos, hetsnp
@@ -176,6 +180,11 @@ def phase_dicts(c):
         hpos[key] = [int(x) for x in ph["hpos"][a:b]]
         hbit[key] = [str(int(x)) for x in ph["hbit"][a:b]]
         hetsnp[key] = [(int(p), "ATGC"[r], "ATGC"[al]) for p, r, al in zip(ph["hpos"][a:b], ph["href"][a:b], ph["halt"][a:b])]
+        for i in range(a, b):
+            if i in over:
+                ref_s, alt_s, bit_s = over[i]
+                hetsnp[key][i - a] = (hetsnp[key][i - a][0], ref_s, alt_s)
+                hbit[key][i - a] = bit_s
     return hbit, hpos, hetsnp
 
 
@@ -244,6 +253,32 @@ def _call_phase():
     ph, chunks, sets = phase_case(d, 50_000)
     return dict(kind="call", batch=d.batch, ref=d.ref.decode(), contig_len=210_000,
                 chunks=chunks, phase_sets=sets, phase=ph, args=call_args(phase=True))
+
+
+@case("call_phase_indel")
+def _call_phase_indel():
+    # phased records that are not SNPs (vcflib.load_phased_hetsnps keeps them): haplib.get_ccs_hbit compares the read's
+    # one-letter base with the REF / ALT *strings*, so at a deletion record (REF = two bases, ALT = the first) a read
+    # that shows the reference base gets bit 1, at an insertion record (ALT = two bases) bit 0, and a read with the other
+    # allele "-" (unphased).  The record's bit is set so that the haplotype with the reference base stays consistent.
+    from himut_b200 import vcfio
+    d = _synth_case(210_000, 18, somatic_rate=2e-5, phase_block=50_000)
+    ph, chunks, sets = phase_case(d, 50_000)
+    ref = d.ref.decode()
+    over = {}
+    for i in range(4, ph["hpos"].size, 9):
+        p, r, bit = int(ph["hpos"][i]), "ATGC"[int(ph["href"][i])], int(ph["hbit"][i])
+        if (i // 9) % 2 == 0:
+            over[i] = (r + ref[p].upper(), r, str(1 - bit))       # deletion: hpos is 1-based, ref[p] is the next base
+        else:
+            over[i] = (r, r + "G", str(bit))                      # insertion
+    c = dict(kind="call", batch=d.batch, ref=ref, contig_len=210_000, chunks=chunks, phase_sets=sets, phase=None,
+             phase_snps=ph, phase_alleles=over, args=call_args(phase=True))
+    hbit, hpos, hetsnp = phase_dicts(c)
+    table, chunk_sets = vcfio.phase_tables([(CHROM, s_, e_) for s_, e_ in chunks], hbit, hpos, hetsnp)
+    assert chunk_sets == sets
+    c["phase"] = table  # what the worker mirror hands to the device for these dicts
+    return c
 
 
 @case("call_phase_shallow")
