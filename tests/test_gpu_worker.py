@@ -39,7 +39,7 @@ def _run_call(c, tmp_path):
     return lst[cases.CHROM], log[cases.CHROM]
 
 
-@pytest.mark.parametrize("name", ["call_basic", "call_sets", "call_pon_params", "call_phase", "call_adversarial_b"])
+@pytest.mark.parametrize("name", ["call_basic", "call_sets", "call_pon_params", "call_phase", "call_phase_indel", "call_adversarial_b"])
 def test_call_worker_matches_reference(name, tmp_path):
     c = cases.build_case(name)
     fx = parity.load_golden(name)
