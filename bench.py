@@ -396,7 +396,9 @@ def leg_contig(args, T, ctx, d, params, chunks, tmpdir):
     def step_e2e_alt():
         c = pair[e_state["k"] % 2]
         e_state["k"] += 1
-        c.upload_compact(dbatch, cq)
+        c.upload_compact(dbatch, cq, wait=False)  # enqueued before the previous upload is waited for, as the worker does
+        if e_state["pending"] is not None:
+            e_state["pending"].upload_wait()      # where the worker hands the previous group's buffers back to the decoder
         c.call_chunks_submit(dchunks)
         if e_state["pending"] is not None:
             e_state["rec"], e_state["log"] = e_state["pending"].call_chunks_collect(view=True)
@@ -404,6 +406,7 @@ def leg_contig(args, T, ctx, d, params, chunks, tmpdir):
 
     def drain_e2e():
         if e_state["pending"] is not None:
+            e_state["pending"].upload_wait()
             e_state["rec"], e_state["log"] = e_state["pending"].call_chunks_collect(view=True)
             e_state["pending"] = None
         for c in pair:
@@ -441,9 +444,9 @@ def leg_contig(args, T, ctx, d, params, chunks, tmpdir):
         "e2e": {"value": aligned * args.steps / (ms_e2e * 1e-3), "unit": "bases/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": int(rec.nbytes + 256), "ms_per_step": ms_e2e / args.steps,
                 "call": "hm_upload_batch_compact + hm_call_chunks_submit / hm_call_chunks_collect on two alternating contexts: what "
-                        "himut_b200/caller.py:call_region does from decode group to decode group (the upload of a call overlaps the "
-                        "kernels and the record copy of the call before it; every step uploads the whole batch again and its records "
-                        "reach host memory inside the timed region); host buffers exactly as csrc/bamdec.c leaves them (no base stream, "
+                        "himut_b200/caller.py:call_region does from decode group to decode group (the upload of a call is enqueued before the previous "
+                        "one is waited for and overlaps the kernels and the record copy of the call before it; every step uploads the "
+                        "whole batch again and its records reach host memory inside the timed region); host buffers exactly as csrc/bamdec.c leaves them (no base stream, "
                         "qualities as modal bitmap + exceptions written by its record-parse pass), page-locked once before the loop; "
                         "records byte-identical to the resident call's",
                 "one_context": {"value": aligned * args.steps / (ms_e2e_one * 1e-3), "ms_per_step": ms_e2e_one / args.steps,

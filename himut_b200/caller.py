@@ -91,6 +91,7 @@ def call_region(ctx, bam_file, chrom, chunkloci_lst, chunk_sets, phase, want_nam
     # at tpos: decode that position too, so a record that starts there is in the batch (it can only matter through a
     # shared query name)
     pending = None  # (context, chunk indices) of the call that is enqueued but not collected
+    uploading = None  # (context, release) of the group whose upload has been enqueued but not waited for
 
     def finish(p):
         c, idx = p[0], p[1]
@@ -112,8 +113,17 @@ def call_region(ctx, bam_file, chrom, chunkloci_lst, chunk_sets, phase, want_nam
             k += 1
             pins.pin([cq.mask, cq.exc, batch.ops])
             lap("page-lock")
-            c.upload_compact(batch, cq)
-            release()  # everything is on the device: the decoder may reuse the buffers
+            if len(ctxs) > 1 and hasattr(c, "upload_wait"):
+                # the copies of this group are enqueued before the previous group's are waited for (the copy engine goes
+                # from one to the other), then the previous group's buffers go back to the decoder
+                c.upload_compact(batch, cq, wait=False)
+                if uploading is not None:
+                    uploading[0].upload_wait()
+                    uploading[1]()
+                uploading = (c, release)
+            else:
+                c.upload_compact(batch, cq)
+                release()  # everything is on the device: the decoder may reuse the buffers
             lap("upload")
             if len(ctxs) > 1:
                 c.call_chunks_submit(table)
@@ -123,11 +133,20 @@ def call_region(ctx, bam_file, chrom, chunkloci_lst, chunk_sets, phase, want_nam
             else:
                 finish((c, idx, c.call_chunks(table)))
             lap("submit + collect")
+        if uploading is not None:
+            uploading[0].upload_wait()
+            uploading[1]()
+            uploading = None
         if pending is not None:
             finish(pending)
         lap("submit + collect")
         names = src.reader.qnames_blob(tally.seen) if want_names else None
     finally:
+        if uploading is not None:  # an exception on the way: the copies must not outlive the decoder's buffers
+            try:
+                uploading[0].upload_wait()
+            except Exception:
+                pass
         pins.close()
         src.close()
         lap("unlock + close")

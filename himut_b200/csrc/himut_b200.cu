@@ -49,6 +49,29 @@ struct DevBuf {
   template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
 };
 
+// a host array in page-locked memory that grows like a vector: the library's own per-read tables are uploaded from it
+// without a staging copy, so an upload that is not waited for (hm_upload_batch_compact_begin) never blocks the host
+template <typename T>
+struct PinVec {
+  T* p = nullptr;
+  size_t cap = 0, n = 0;
+  bool resize(size_t m) { // false: out of page-locked memory
+    if (m > cap) {
+      if (p) cudaFreeHost(p);
+      p = nullptr; cap = 0;
+      const size_t want = m + m / 4 + 64;
+      if (cudaHostAlloc((void**)&p, want * sizeof(T), cudaHostAllocDefault) != cudaSuccess) { p = nullptr; n = 0; return false; }
+      cap = want;
+    }
+    n = m;
+    return true;
+  }
+  void release() { if (p) cudaFreeHost(p); p = nullptr; cap = n = 0; }
+  T& operator[](size_t i) { return p[i]; }
+  T* data() { return p; }
+  T& back() { return p[n - 1]; }
+};
+
 struct KTime { const char* name; cudaEvent_t a, b; float ms; };
 
 }  // namespace
@@ -64,8 +87,9 @@ struct hm_ctx {
   // resident batch
   uint64_t n_reads = 0, n_ops_total = 0, seq_bytes = 0, bq_bytes = 0;
   uint32_t max_qname_id = 0;
-  std::vector<int32_t> h_pmax;
-  std::vector<uint32_t> h_tix_off; // per read: first entry of its tile index (k_tile_index)
+  PinVec<int32_t> h_pmax;
+  PinVec<uint32_t> h_tix_off; // per read: first entry of its tile index (k_tile_index)
+  bool upload_pending = false;  // hm_upload_batch_compact_begin: the copies of the last upload have not been waited for
   uint64_t n_tix = 0;
   DevBuf b_tstart, b_tend, b_qstart, b_qlen, b_mapq, b_flags, b_qname, b_seq_off, b_bq_off, b_op_off, b_n_ops,
       b_seq, b_bq, b_ops, b_op_t, b_op_q, b_mm, b_bq_total, b_n_match, b_n_sub, b_ins_len, b_del_len, b_n_mm, b_gate,
@@ -123,7 +147,7 @@ struct hm_ctx {
   struct Pending { bool active = false; std::vector<hm_chunk> chunks; uint64_t site_cap = 0; size_t bcap = 0; int n_launched = 0, parity = 0; bool omit = false; } pend;
   DevBuf b_cgeom, b_seg_keys, b_seg_read, b_keys_tmp, b_gscratch, b_czero, b_first_pair, b_tiles, b_site_valid, b_pair_c;
   // bit-vector normcounts path (normbits.cuh)
-  std::vector<uint32_t> h_cw_off;           // per read: first word of its cal bit vector
+  PinVec<uint32_t> h_cw_off;                // per read: first word of its cal bit vector
   uint64_t n_cw = 0;                        // words of all cal bit vectors (>= 2^32: the path is not used)
   uint16_t cert_thr[256];                   // smallest callable count that certifies a pure position of depth n (0xffff: none)
   uint64_t packed_pos = 0;                  // positions b_ref2 / b_tri8 cover for the reference now in b_ref (0: not packed)
@@ -344,7 +368,7 @@ int hm_create(int cuda_device, hm_ctx** out) {
 void hm_destroy(hm_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
-  cudaStreamSynchronize(ctx->stream);
+  cudaStreamSynchronize(ctx->stream); // also ends an upload that was not waited for
   if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
   for (cudaEvent_t e : ctx->ev_copy_done) if (e) cudaEventDestroy(e);
   if (ctx->ev_go) cudaEventDestroy(ctx->ev_go);
@@ -364,6 +388,7 @@ void hm_destroy(hm_ctx* ctx) {
   if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
   if (ctx->h_cnt_pin) cudaFreeHost(ctx->h_cnt_pin);
   if (ctx->h_geom_pin) cudaFreeHost(ctx->h_geom_pin);
+  ctx->h_pmax.release(); ctx->h_tix_off.release(); ctx->h_cw_off.release();
   for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
   if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
@@ -453,7 +478,7 @@ int hm_set_phase_sets(hm_ctx* ctx, const int32_t* hpos, const uint8_t* href, con
   return HM_OK;
 }
 
-static int upload_batch_impl(hm_ctx* ctx, const hm_read_batch* b, const hm_bq_compact* cq);
+static int upload_batch_impl(hm_ctx* ctx, const hm_read_batch* b, const hm_bq_compact* cq, bool wait = true);
 
 int hm_upload_batch(hm_ctx* ctx, const hm_read_batch* b) { return upload_batch_impl(ctx, b, nullptr); }
 
@@ -462,7 +487,25 @@ int hm_upload_batch_compact(hm_ctx* ctx, const hm_read_batch* b, const hm_bq_com
   return upload_batch_impl(ctx, b, cq);
 }
 
-static int upload_batch_impl(hm_ctx* ctx, const hm_read_batch* b, const hm_bq_compact* cq) {
+/* hm_upload_batch_compact that returns as soon as its copies are enqueued: the caller's buffers must stay as they are
+ * until hm_upload_wait (or the next hm_upload_* / hm_destroy of the context) has returned.  Calls may be enqueued on the
+ * context meanwhile (they run behind the copies).  A worker that alternates two contexts enqueues the upload of group
+ * k + 1 on one before it waits for the upload of group k on the other, so the copy engine never idles between them. */
+int hm_upload_batch_compact_begin(hm_ctx* ctx, const hm_read_batch* b, const hm_bq_compact* cq) {
+  if (!cq) return HM_ERR_ARG;
+  return upload_batch_impl(ctx, b, cq, false);
+}
+int hm_upload_wait(hm_ctx* ctx) {
+  if (!ctx) return HM_ERR_ARG;
+  if (ctx->upload_pending) {
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaEventSynchronize(ctx->ev_up));
+    ctx->upload_pending = false;
+  }
+  return HM_OK;
+}
+
+static int upload_batch_impl(hm_ctx* ctx, const hm_read_batch* b, const hm_bq_compact* cq, bool wait) {
   if (!ctx || !b) return HM_ERR_ARG;
   if (!cq && !b->bq) return fail(ctx, HM_ERR_ARG, "batch has no quality stream");
   // seq == NULL: no base stream.  The bases of match runs are then the reference allele of the site that asks
@@ -476,6 +519,10 @@ static int upload_batch_impl(hm_ctx* ctx, const hm_read_batch* b, const hm_bq_co
     if (cq->mask_bytes * 8 != b->bq_bytes) return fail(ctx, HM_ERR_ARG, "hm_bq_compact.mask_bytes must be bq_bytes / 8");
   }
   CU(cudaSetDevice(ctx->device));
+  if (ctx->upload_pending) { // an upload that was not waited for: its copies still read the page-locked tables rewritten below
+    CU(cudaEventSynchronize(ctx->ev_up));
+    ctx->upload_pending = false;
+  }
   ctx->have_batch = false;
   const uint64_t n = b->n_reads;
   if (n >= (1ull << 32)) return fail(ctx, HM_ERR_ARG, "too many reads in one batch");
@@ -493,9 +540,7 @@ static int upload_batch_impl(hm_ctx* ctx, const hm_read_batch* b, const hm_bq_co
   UP(b_ops, ops, b->n_ops_total);
 #define BAD(...) do { cudaStreamSynchronize(ctx->stream); return fail(ctx, HM_ERR_ARG, __VA_ARGS__); } while (0)
   // structural validation (cheap, O(reads)); the kernels binary-search on these invariants
-  ctx->h_pmax.resize(n);
-  ctx->h_tix_off.resize(n + 1);
-  ctx->h_cw_off.resize(n + 1);
+  if (!ctx->h_pmax.resize(n) || !ctx->h_tix_off.resize(n + 1) || !ctx->h_cw_off.resize(n + 1)) BAD("out of page-locked host memory for %llu reads", (unsigned long long)n);
   uint64_t n_tix = 0, n_cw = 0, span_sum = 0;
   int32_t run = INT32_MIN;
   uint32_t max_q = 0;
@@ -593,7 +638,8 @@ static int upload_batch_impl(hm_ctx* ctx, const hm_read_batch* b, const hm_bq_co
     t_end(ctx);
     CU(cudaGetLastError());
   }
-  CU(cudaEventSynchronize(ctx->ev_up)); // the caller may reuse its buffers after return; k_bq_expand may still be running
+  if (wait) CU(cudaEventSynchronize(ctx->ev_up)); // the caller may reuse its buffers after return; k_bq_expand may still be running
+  ctx->upload_pending = !wait;
   ctx->have_batch = true;
   return HM_OK;
 }

@@ -20,7 +20,7 @@ EXPORTS = [
     "hm_set_phase_sets", "hm_upload_batch", "hm_call_chunks", "hm_call_batch", "hm_normcounts_chunks",
     "hm_read_stats", "hm_last_timing", "hm_last_kernel_times", "hm_set_stream", "hm_host_register",
     "hm_host_unregister", "hm_abi_sizeof", "hm_last_records", "hm_qname_seen", "hm_set_reference", "hm_ref_tricounts", "hm_last_norm_exact_sites",
-    "hm_phase_edges_begin", "hm_phase_edges_add", "hm_phase_edges_end", "hm_upload_batch_compact", "hm_call_batch_compact", "hm_call_chunks_async", "hm_records_wait", "hm_set_option", "hm_last_call_path", "hm_call_chunks_submit", "hm_call_chunks_collect", "hm_device_count",
+    "hm_phase_edges_begin", "hm_phase_edges_add", "hm_phase_edges_end", "hm_upload_batch_compact", "hm_call_batch_compact", "hm_call_chunks_async", "hm_records_wait", "hm_set_option", "hm_last_call_path", "hm_call_chunks_submit", "hm_call_chunks_collect", "hm_device_count", "hm_upload_batch_compact_begin", "hm_upload_wait",
 ]
 
 
@@ -55,6 +55,8 @@ def load():
         lib.hm_call_chunks_async.argtypes = [vp, vp, sz, vp, sz, C.POINTER(sz), vp]
         lib.hm_call_batch.argtypes = [vp, C.POINTER(abi.hm_read_batch), vp, sz, vp, sz, C.POINTER(sz), vp]
         lib.hm_upload_batch_compact.argtypes = [vp, C.POINTER(abi.hm_read_batch), C.POINTER(abi.hm_bq_compact)]
+        lib.hm_upload_batch_compact_begin.argtypes = [vp, C.POINTER(abi.hm_read_batch), C.POINTER(abi.hm_bq_compact)]
+        lib.hm_upload_wait.argtypes = [vp]
         lib.hm_call_batch_compact.argtypes = [vp, C.POINTER(abi.hm_read_batch), C.POINTER(abi.hm_bq_compact), vp, sz, vp, sz,
                                               C.POINTER(sz), vp]
         lib.hm_normcounts_chunks.argtypes = [vp, vp, sz, vp, sz, vp, vp, vp, C.POINTER(C.c_int64)]
@@ -170,9 +172,20 @@ class Context:
     def upload(self, batch):
         self._chk(self.lib.hm_upload_batch(self.h, C.byref(batch.as_struct())))
 
-    def upload_compact(self, batch, cq):
-        """upload with the quality stream as modal bitmap + exceptions (abi.BqCompact); expanded on the device"""
-        self._chk(self.lib.hm_upload_batch_compact(self.h, C.byref(batch.as_struct()), C.byref(cq.struct)))
+    def upload_compact(self, batch, cq, wait=True):
+        """upload with the quality stream as modal bitmap + exceptions (abi.BqCompact); expanded on the device.
+        wait=False: returns as soon as the copies are enqueued — the arrays of `batch` and `cq` must stay untouched until
+        upload_wait() (calls may be submitted meanwhile: they run behind the copies)"""
+        if wait:
+            self._chk(self.lib.hm_upload_batch_compact(self.h, C.byref(batch.as_struct()), C.byref(cq.struct)))
+        else:
+            self._uploading = (batch, cq)  # alive until the copies are done
+            self._chk(self.lib.hm_upload_batch_compact_begin(self.h, C.byref(batch.as_struct()), C.byref(cq.struct)))
+
+    def upload_wait(self):
+        """the copies of the last upload_compact(..., wait=False) are done: its arrays may be reused"""
+        self._chk(self.lib.hm_upload_wait(self.h))
+        self._uploading = None
 
     def call_batch_compact(self, batch, cq, chunks, cap=None, view=False):
         """call_batch with the compact quality stream: fewer bytes over PCIe, identical records"""

@@ -313,6 +313,15 @@ int hm_upload_batch_compact(hm_ctx* ctx, const hm_read_batch* batch, const hm_bq
 int hm_call_batch_compact(hm_ctx* ctx, const hm_read_batch* batch, const hm_bq_compact* bq, const hm_chunk* chunks,
                           size_t n_chunks, hm_site_record* out, size_t cap, size_t* n_out, int64_t log[HM_CALL_LOG_LEN]);
 
+/* hm_upload_batch_compact in two halves: _begin returns as soon as the host -> device copies are enqueued (the buffers
+ * of `batch` and `bq` must stay untouched until hm_upload_wait, the next hm_upload_* or hm_destroy of the context has
+ * returned; calls enqueued meanwhile run behind the copies), hm_upload_wait returns when they are done.  A worker that
+ * alternates two contexts between the decode groups of a contig (caller.py:268-299 is the loop this replaces) begins
+ * the upload of group k + 1 on one context before it waits for group k's on the other and hands its buffers back to
+ * the decoder. */
+int hm_upload_batch_compact_begin(hm_ctx* ctx, const hm_read_batch* batch, const hm_bq_compact* bq);
+int hm_upload_wait(hm_ctx* ctx);
+
 /* keep a contig's reference sequence (the `seq` argument of get_callable_tricounts,
  * normcounts.py:208) resident on the device; hm_normcounts_chunks then accepts refseq = NULL */
 int hm_set_reference(hm_ctx* ctx, const uint8_t* refseq, size_t ref_len);

@@ -66,7 +66,9 @@ for mode in a.mode.split(","):
             c = ctxs[state["k"] % 2]
             state["k"] += 1
             if mode == "e2e":
-                c.upload_compact(batch, cq)
+                c.upload_compact(batch, cq, wait=False)  # as the worker: enqueue, then wait for the previous upload
+                if state["pending"] is not None:
+                    state["pending"].upload_wait()
                 tu = time.perf_counter()
                 ups.append(1e3 * (tu - t0))
                 t0 = tu
@@ -92,6 +94,7 @@ for mode in a.mode.split(","):
 
     def drain():
         if state["pending"] is not None:
+            state["pending"].upload_wait()
             state["pending"].call_chunks_collect(view=True)
             state["pending"] = None
         for c in ctxs:
