@@ -443,7 +443,7 @@ def leg_contig(args, T, ctx, d, params, chunks, tmpdir):
         "value": aligned * args.steps / (ms_total * 1e-3), "ms_per_step": step_ms,
         "e2e": {"value": aligned * args.steps / (ms_e2e * 1e-3), "unit": "bases/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": int(rec.nbytes + 256), "ms_per_step": ms_e2e / args.steps,
-                "call": "hm_upload_batch_compact + hm_call_chunks_submit / hm_call_chunks_collect on two alternating contexts: what "
+                "call": "hm_upload_batch_compact_begin / hm_upload_wait + hm_call_chunks_submit / hm_call_chunks_collect on two alternating contexts: what "
                         "himut_b200/caller.py:call_region does from decode group to decode group (the upload of a call is enqueued before the previous "
                         "one is waited for and overlaps the kernels and the record copy of the call before it; every step uploads the "
                         "whole batch again and its records reach host memory inside the timed region); host buffers exactly as csrc/bamdec.c leaves them (no base stream, "
@@ -690,12 +690,15 @@ def leg_genome(args, T, lib, torch, rank, world, local_rank, stream):
         prev = None
         for it in items:
             c = it["pair"][0]
-            c.upload_compact(it["sub"], it["cq"])
+            c.upload_compact(it["sub"], it["cq"], wait=False)  # begun before the previous run's upload is waited for
+            if prev is not None:
+                prev.upload_wait()
             c.call_chunks_submit(it["table"])
             if prev is not None:
                 prev.call_chunks_collect(view=True)
             prev = c
         if prev is not None:
+            prev.upload_wait()
             prev.call_chunks_collect(view=True)
         for it in items:
             it["pair"][0].records_wait()
@@ -736,7 +739,7 @@ def leg_genome(args, T, lib, torch, rank, world, local_rank, stream):
         "value": bases * args.steps / (float(t[0]) * 1e-3), "ms_per_step": float(t[0]) / args.steps,
         "e2e": {"value": bases * args.steps / (float(t[1]) * 1e-3), "unit": "bases/s", "ms_per_step": float(t[1]) / args.steps,
                 "h2d_bytes_per_step": int(s[2]), "d2h_bytes_per_step": int(s[3]),
-                "call": "hm_upload_batch_compact + hm_call_chunks_submit / collect per chunk run (a run's kernels overlap the next run's "
+                "call": "hm_upload_batch_compact_begin / hm_upload_wait + hm_call_chunks_submit / collect per chunk run (a run's upload is begun before the previous run's is waited for, a run's kernels overlap the next run's "
                         "upload), host buffers in the decoder's layout (no base stream, qualities as modal "
                         "bitmap + exceptions — here built by hm_bq_compact_build from the generated batch, the same bytes the decoder's "
                         "parse pass writes: tests/test_bamdec.py), page-locked before the loop"},
